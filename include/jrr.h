@@ -1,0 +1,174 @@
+/*
+ * jrr.h -- C ABI of libjrr.so, the B200-native (sm_100a) replacement for the
+ * data-parallel hot path of ubc-vision/joint-regressor-refinement.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, a JrrStatus otherwise; the message of the
+ *     last failure on the calling thread is available from jrr_last_error()
+ *   - plain pointers and sizes only (no torch / C++ types); all data pointers are DEVICE
+ *     pointers unless the name ends in _host
+ *   - no entry point allocates caller-visible memory, synchronises the device or calls
+ *     back into the host: work is enqueued on the cudaStream_t handed in (passed as
+ *     void*), so sequences of calls can be captured into a CUDA graph
+ *   - "B" is the number of poses (frames) of a call, "BP" = B rounded up to 128; device
+ *     workspaces are sized by jrr_workspace_bytes() and owned by the caller
+ *
+ * Each declaration cites the reference interface (file:line under /root/reference) it
+ * replaces.  The reference is pure Python; INTEGRATION.md shows the ctypes stub a
+ * maintainer adds to call these from scripts/smpl.py, scripts/utils.py and
+ * scripts/optimize.py.
+ */
+#ifndef JRR_H_
+#define JRR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JRR_ABI_VERSION 1
+
+#define JRR_NUM_VERTS 6890
+#define JRR_NUM_JOINTS 24
+#define JRR_NUM_BETAS 10
+#define JRR_NUM_POSE_FEATS 207
+#define JRR_NUM_H36M 17
+#define JRR_NUM_EXTRA 9
+#define JRR_NUM_PICKS 21
+#define JRR_NUM_OUT_JOINTS 49
+#define JRR_CRITIC_PARAMS 1840153
+
+typedef enum JrrStatus {
+  JRR_OK = 0,
+  JRR_ERR_INVALID = 1,   /* bad argument / shape */
+  JRR_ERR_CUDA = 2,      /* a CUDA runtime/driver call failed */
+  JRR_ERR_STATE = 3,     /* e.g. regressor or critic not set */
+  JRR_ERR_WORKSPACE = 4  /* workspace too small */
+} JrrStatus;
+
+/* how the 24 joint rotations of a call are encoded */
+typedef enum JrrPoseKind {
+  JRR_POSE_ROTMAT = 0,     /* [B,24,3,3] row-major (pose2rot=False; utils.py:94-95) */
+  JRR_POSE_AXIS_ANGLE = 1, /* [B,24,3]   (pose2rot=True, smplx default; smpl.py:72-74) */
+  JRR_POSE_ROT6D = 2       /* [B,24,6]   interleaved view(-1,3,2) layout (utils.py:198-200) */
+} JrrPoseKind;
+
+typedef struct JrrModel JrrModel; /* opaque: packed, padded, tf32 hi/lo-split constants */
+
+/* Host-side description of the body-model constants, i.e. the buffers smplx.SMPL registers
+ * plus the two that scripts/smpl.py:67-70 adds.  All pointers are HOST pointers, dense,
+ * row-major, fp32 unless noted. */
+typedef struct JrrModelDesc {
+  const float* v_template_host;        /* [6890,3] */
+  const float* shapedirs_host;         /* [6890,3,10] */
+  const float* posedirs_host;          /* [207,20670] */
+  const float* J_regressor_host;       /* [24,6890] */
+  const int64_t* parents_host;         /* [24], parents[0] = -1 */
+  const float* lbs_weights_host;       /* [6890,24] (any sparsity; packed as ELL-4 runs when
+                                          every vertex has <= 4 non-zeros, which SMPL has) */
+  const float* J_regressor_extra_host; /* [9,6890]  (smpl.py:67-69) */
+  const int64_t* joint_map_host;       /* [49] into the 54-joint stack (smpl.py:66,70) */
+  const int64_t* vertex_picks_host;    /* [21] VertexJointSelector ids (smplx) */
+  int32_t device;                      /* CUDA device ordinal the model lives on */
+  int32_t gemm_impl;                   /* 0 = tcgen05 3xTF32 (product), 1 = SIMT fp32 (kernel validation only) */
+} JrrModelDesc;
+
+const char* jrr_last_error(void);
+int jrr_abi_version(void);
+
+/* replaces: SMPL.__init__ (scripts/smpl.py:64-70, smplx.SMPL.__init__) */
+int jrr_model_create(const JrrModelDesc* desc, JrrModel** out);
+int jrr_model_destroy(JrrModel* model);
+
+/* replaces: the per-call "J*mask, ReLU, row-normalise" of find_joints (scripts/utils.py:87-92);
+ * done once per regressor version.  J17_raw / mask are DEVICE [17,6890] row-major, mask may
+ * be NULL (== all ones, which is what utils.py:182-187 returns). */
+int jrr_set_regressor(JrrModel* model, const float* J17_raw, const float* mask, void* stream);
+
+/* replaces: Discriminator.__init__/load_state_dict (scripts/discriminator.py:7-30).
+ * `params` is DEVICE fp32, the state_dict tensors flattened and concatenated in this order:
+ * conv_operations.0.weight[32,6] .bias[32] conv_operations.2.weight[32,32] .bias[32]
+ * linears.0..23 (weight[32], bias[1]) x24, linear_operations.0.weight[1024,768] .bias[1024]
+ * linear_operations.2.weight[1024,1024] .bias[1024] linear_operations.4.weight[1024] .bias[1]
+ * (JRR_CRITIC_PARAMS floats). */
+int jrr_critic_load(JrrModel* model, const float* params, void* stream);
+
+/* bytes of caller-owned device workspace needed by any entry point below for B poses */
+size_t jrr_workspace_bytes(const JrrModel* model, int64_t B);
+
+/* replaces: SMPL.forward (scripts/smpl.py:72-85 -> smplx.SMPL.forward -> smplx.lbs.lbs).
+ * betas [B,10]; pose per `kind`; vertices_out [B,6890,3] or NULL; joints49_out [B,49,3] or
+ * NULL. */
+int jrr_smpl_forward(JrrModel* model, int64_t B, const float* betas, const float* pose,
+                     int kind, float* vertices_out, float* joints49_out, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* replaces: autograd backward of SMPL.forward (optimize.py:264 through smpl.py:72-85).
+ * dvertices [B,6890,3] or NULL, djoints49 [B,49,3] or NULL -> dbetas_out [B,10],
+ * dpose_out in the layout of `kind`.  Recomputes the forward intermediates. */
+int jrr_smpl_backward(JrrModel* model, int64_t B, const float* betas, const float* pose,
+                      int kind, const float* dvertices, const float* djoints49,
+                      float* dbetas_out, float* dpose_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* replaces: utils.find_joints (scripts/utils.py:85-103) on the loss path: regressed
+ * 17 joints [B,17,3] WITHOUT materialising vertices (needs jrr_set_regressor). */
+int jrr_find_joints(JrrModel* model, int64_t B, const float* betas, const float* pose, int kind,
+                    float* joints17_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces: Discriminator.forward (scripts/discriminator.py:32-54): rot6d [B,24,6] ->
+ * sigmoid scores [B,25] ordered [global, joint0..23]. */
+int jrr_critic_forward(JrrModel* model, int64_t B, const float* rot6d, float* scores_out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces: one iteration of the refinement loop, optimize.py:220-229,238-253,263-265
+ * (rot6d_to_rotmat, find_joints, move_pelvis + MSELoss, Discriminator + MSELoss, backward,
+ * Adam.step) restricted to the in-scope loss w_joint*joint + w_pose*pose_critic.
+ *   x6 [B,24,6], betas [B,10]      updated in place
+ *   adam_m / adam_v [B,154]        first/second moments, per pose [x6(144) | betas(10)]
+ *   step_count                     DEVICE int32 scalar, incremented by the call (bias correction)
+ *   gt_mm [B,17,3]                 pelvis-centred target joints in millimetres
+ *   B_logical                      batch size used by the two mean reductions (optimize.py:128),
+ *                                  so a shard of a larger batch reproduces its gradients
+ *   loss_out                       DEVICE float[3] {total, joint_mse, pose_mse} sums over this
+ *                                  shard already divided by the logical element counts; or NULL */
+int jrr_refine_step(JrrModel* model, int64_t B, int64_t B_logical, float* x6, float* betas,
+                    const float* gt_mm, float* adam_m, float* adam_v, int32_t* step_count,
+                    float lr, float w_joint, float w_pose, float* loss_out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* replaces: the forward/backward half of the regressor refit, optimize.py:300-309
+ * (find_joints on detached refined poses, move_pelvis + MSELoss, backward to J_regressor).
+ * Accumulates G += dL/dJhat (17x6890, gradient w.r.t. the NORMALISED regressor) and
+ * loss_accum += shard loss; both are what a multi-GPU caller all-reduces. */
+int jrr_regressor_grad_accumulate(JrrModel* model, int64_t B, int64_t B_logical, const float* x6,
+                                  const float* betas, const float* gt_mm, float* G_accum,
+                                  float* loss_accum, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+
+/* replaces: backward through row-normalise/ReLU/mask (utils.py:87-92) followed by
+ * J_Regressor_optimizer.step() (optimize.py:125-126,310-312): Adam on the raw regressor
+ * with persistent state.  J17_raw, adam_m, adam_v [17,6890] are updated in place; the
+ * model's normalised copy is refreshed.  step_count as in jrr_refine_step. */
+int jrr_regressor_apply(JrrModel* model, float* J17_raw, const float* mask, const float* G_accum,
+                        float* adam_m, float* adam_v, int32_t* step_count, float lr,
+                        void* stream);
+
+/* Diagnostic: the 3xTF32 GEMM on its own, C[M,N] (row-major) = A[M,K] . B[N,K]^T with fp32
+ * inputs that are split into tf32 hi/lo pairs inside the call (scratch = 2*(M+N)*K floats,
+ * device).  impl 0 = tcgen05 kernel, 1 = SIMT validation kernel.  M%128 == 0, K%32 == 0,
+ * N%128 == 0 or N == 224.  Used by the kernel-level parity tests and the GEMM roofline
+ * micro-benchmark; not on the reference's interface. */
+int jrr_debug_gemm(JrrModel* model, int impl, int64_t M, int64_t N, int64_t K, const float* A,
+                   const float* B, float* C, float* scratch, void* stream);
+
+/* number of kernels the last call of the named entry point enqueued (bench.py's
+ * gpu_launches claim is counted, not guessed) */
+int64_t jrr_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JRR_H_ */

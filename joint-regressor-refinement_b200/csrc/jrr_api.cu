@@ -1,0 +1,262 @@
+// C-ABI entry points: argument checks, workspace carving and the kernel sequences.
+#include "jrr_internal.cuh"
+
+namespace jrr {
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+Workspace carve(const JrrModel* m, int64_t B, void* base) {
+  Workspace w{};
+  w.B = B;
+  w.BP = round_up(B, 128);
+  const size_t BP = (size_t)w.BP;
+  size_t off = 0;
+  char* p = (char*)base;
+  auto take = [&](size_t nfloats) -> float* {
+    float* r = base ? (float*)(p + off) : nullptr;
+    off += align256(nfloats * sizeof(float));
+    return r;
+  };
+  w.AT = take(288 * BP);
+  w.feat_hi = take(BP * KA);
+  w.feat_lo = take(BP * KA);
+  w.vpT = take((size_t)NP * BP);
+  w.part = take((size_t)NSPLIT * NACC * BP);
+  w.gT = take(NACC * BP);
+  w.pred = take(BP * NACC);
+  w.dvp_hi = take(BP * (size_t)NP);
+  w.dvp_lo = take(BP * (size_t)NP);
+  w.dAflush = take((size_t)m->n_flush * 12 * BP);
+  w.dAT = take(288 * BP);
+  w.dfeat = take((size_t)KSPLIT * BP * KA);
+  w.dJp = take(BP * 72);
+  w.Jp = take(BP * 72);
+  w.d30T = take(90 * BP);
+  w.loss_part = take(LOSS_PART_POSE + BP / 8 + 64);
+  w.h_hi = take(BP * C_H);
+  w.h_lo = take(BP * C_H);
+  w.z1_hi = take(BP * C_Z);
+  w.z1_lo = take(BP * C_Z);
+  w.z2_hi = take(BP * C_Z);
+  w.z2_lo = take(BP * C_Z);
+  w.dz2_hi = take(BP * C_Z);
+  w.dz2_lo = take(BP * C_Z);
+  w.dz1_hi = take(BP * C_Z);
+  w.dz1_lo = take(BP * C_Z);
+  w.dh = take(BP * C_H);
+  w.dzj = take(BP * NJ);
+  w.dx6c = take(BP * 144);
+  w.scores = take(BP * 25);
+  w.bytes = off;
+  return w;
+}
+
+static int check_common(const JrrModel* m, int64_t B, const void* ws, size_t ws_bytes, Workspace* w) {
+  if (!m) return fail(JRR_ERR_INVALID, "null model");
+  if (B <= 0 || B > MAX_POSES_PER_CALL) return fail(JRR_ERR_INVALID, "B out of range (1..262144 per call)");
+  if (!ws) return fail(JRR_ERR_WORKSPACE, "null workspace");
+  if (((uintptr_t)ws & 255) != 0) return fail(JRR_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  *w = carve(m, B, const_cast<void*>(ws));
+  if (w->bytes > ws_bytes) return fail(JRR_ERR_WORKSPACE, "workspace too small; see jrr_workspace_bytes");
+  reset_launch_count();
+  return JRR_OK;
+}
+
+// pose decode + chain, then the augmented blend GEMM: feat[BP,224] x Pt[20736,224]^T -> vpT
+static int forward_common(const JrrModel* m, const Workspace& w, const float* betas, const float* pose,
+                          int kind, bool want_Jp, cudaStream_t st) {
+  int rc = launch_pose_fwd(m, w.B, w.BP, betas, pose, kind, w.AT, w.feat_hi, w.feat_lo,
+                           want_Jp ? w.Jp : nullptr, st);
+  if (rc) return rc;
+  GemmDesc g{};
+  g.A_hi = w.feat_hi; g.A_lo = w.feat_lo; g.lda = KA;
+  g.B_hi = m->Pt_hi; g.B_lo = m->Pt_lo; g.ldb = KA;
+  g.M = w.BP; g.N = NP; g.K = KA; g.ksplit = 1; g.epi = EPI_STORE_T;
+  g.out0 = w.vpT; g.ldo = w.BP;
+  return launch_gemm(m, g, st);
+}
+
+// dfeat[s][BP,224] = dvp[BP, 20736 (split s)] x P[224, 20736]^T
+static int blend_backward_gemm(const JrrModel* m, const Workspace& w, cudaStream_t st) {
+  GemmDesc g{};
+  g.A_hi = w.dvp_hi; g.A_lo = w.dvp_lo; g.lda = NP;
+  g.B_hi = m->P_hi; g.B_lo = m->P_lo; g.ldb = NP;
+  g.M = w.BP; g.N = KA; g.K = NP / KSPLIT; g.ksplit = KSPLIT; g.epi = EPI_STORE_SPLITK;
+  g.out0 = w.dfeat; g.ldo = KA;
+  return launch_gemm(m, g, st);
+}
+
+int launch_gemm(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
+  if (m->gemm_impl == 1) return launch_gemm_simt(g, st);
+  return launch_gemm_tc(m, g, st);
+}
+
+}  // namespace jrr
+
+using namespace jrr;
+
+extern "C" size_t jrr_workspace_bytes(const JrrModel* m, int64_t B) {
+  if (!m || B <= 0) return 0;
+  return carve(m, B, nullptr).bytes;
+}
+
+extern "C" int jrr_smpl_forward(JrrModel* m, int64_t B, const float* betas, const float* pose, int kind,
+                                float* vertices_out, float* joints49_out, void* ws, size_t ws_bytes,
+                                void* stream) {
+  Workspace w;
+  if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
+  if (!betas || !pose) return fail(JRR_ERR_INVALID, "null input");
+  if (!vertices_out && !joints49_out) return fail(JRR_ERR_INVALID, "no output requested");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = forward_common(m, w, betas, pose, kind, joints49_out != nullptr, st)) return rc;
+  // joints49 reads vertices: use caller's buffer, else scratch (dvp_hi is [BP][NP] >= [B][6890][3])
+  float* verts = vertices_out ? vertices_out : w.dvp_hi;
+  if (int rc = launch_skin_fwd(m, w, verts, nullptr, false, st)) return rc;
+  if (joints49_out)
+    if (int rc = launch_joints49_fwd(m, w, verts, joints49_out, st)) return rc;
+  return JRR_OK;
+}
+
+extern "C" int jrr_smpl_backward(JrrModel* m, int64_t B, const float* betas, const float* pose, int kind,
+                                 const float* dvertices, const float* djoints49, float* dbetas_out,
+                                 float* dpose_out, void* ws, size_t ws_bytes, void* stream) {
+  Workspace w;
+  if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
+  if (!betas || !pose || !dbetas_out || !dpose_out) return fail(JRR_ERR_INVALID, "null argument");
+  if (!dvertices && !djoints49) return fail(JRR_ERR_INVALID, "no upstream gradient given");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = forward_common(m, w, betas, pose, kind, false, st)) return rc;
+  const bool use_x = djoints49 != nullptr;
+  if (use_x)
+    if (int rc = launch_joints49_bwd(m, w, djoints49, st)) return rc;
+  if (int rc = launch_skin_bwd(m, w, dvertices, false, use_x, st)) return rc;
+  if (int rc = launch_dA_reduce(m, w, st)) return rc;
+  if (int rc = blend_backward_gemm(m, w, st)) return rc;
+  return launch_pose_bwd(m, w, betas, pose, kind, use_x, false, dbetas_out, dpose_out, nullptr, nullptr,
+                         nullptr, nullptr, nullptr, 0.f, st);
+}
+
+extern "C" int jrr_find_joints(JrrModel* m, int64_t B, const float* betas, const float* pose, int kind,
+                               float* joints17_out, void* ws, size_t ws_bytes, void* stream) {
+  Workspace w;
+  if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
+  if (!m->has_regressor) return fail(JRR_ERR_STATE, "jrr_set_regressor has not been called");
+  if (!betas || !pose || !joints17_out) return fail(JRR_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = forward_common(m, w, betas, pose, kind, false, st)) return rc;
+  if (int rc = launch_skin_fwd(m, w, nullptr, nullptr, true, st)) return rc;
+  return launch_loss_seed(m, w, nullptr, 1, 0.f, joints17_out, st);
+}
+
+extern "C" int jrr_critic_forward(JrrModel* m, int64_t B, const float* rot6d, float* scores_out, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  Workspace w;
+  if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
+  if (!m->has_critic) return fail(JRR_ERR_STATE, "jrr_critic_load has not been called");
+  if (!rot6d || !scores_out) return fail(JRR_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = launch_critic_pre(m, w, rot6d, st)) return rc;
+  if (int rc = critic_forward_gemms(m, w, st)) return rc;
+  return launch_critic_head(m, w, B, 0.f, scores_out, false, st);
+}
+
+extern "C" int jrr_refine_step(JrrModel* m, int64_t B, int64_t B_logical, float* x6, float* betas,
+                               const float* gt_mm, float* adam_m, float* adam_v, int32_t* step_count,
+                               float lr, float w_joint, float w_pose, float* loss_out, void* ws,
+                               size_t ws_bytes, void* stream) {
+  Workspace w;
+  if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
+  if (!m->has_regressor) return fail(JRR_ERR_STATE, "jrr_set_regressor has not been called");
+  if (!x6 || !betas || !gt_mm || !adam_m || !adam_v || !step_count) return fail(JRR_ERR_INVALID, "null argument");
+  if (B_logical < B) return fail(JRR_ERR_INVALID, "B_logical must be >= B");
+  const bool critic = w_pose != 0.f;
+  if (critic && !m->has_critic) return fail(JRR_ERR_STATE, "w_pose != 0 but jrr_critic_load has not been called");
+  cudaStream_t st = (cudaStream_t)stream;
+  // forward: chain, blend, skinning fused with the 17x6890 regressor reduction
+  if (int rc = forward_common(m, w, betas, x6, JRR_POSE_ROT6D, false, st)) return rc;
+  if (int rc = launch_skin_fwd(m, w, nullptr, nullptr, true, st)) return rc;
+  if (int rc = launch_loss_seed(m, w, gt_mm, B_logical, w_joint, nullptr, st)) return rc;
+  // backward: regressor transpose seed, skinning, blend
+  if (int rc = launch_skin_bwd(m, w, nullptr, true, false, st)) return rc;
+  if (int rc = launch_dA_reduce(m, w, st)) return rc;
+  if (int rc = blend_backward_gemm(m, w, st)) return rc;
+  // critic forward + input gradient
+  if (critic) {
+    if (int rc = launch_critic_pre(m, w, x6, st)) return rc;
+    if (int rc = critic_forward_gemms(m, w, st)) return rc;
+    if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, st)) return rc;
+    if (int rc = critic_backward_gemms(m, w, st)) return rc;
+    if (int rc = launch_critic_post(m, w, x6, st)) return rc;
+  }
+  if (loss_out)
+    if (int rc = launch_loss_finish(w, B_logical, w_joint, w_pose, critic, loss_out, nullptr, st)) return rc;
+  // chain backward + Adam
+  return launch_pose_bwd(m, w, betas, x6, JRR_POSE_ROT6D, false, critic, nullptr, nullptr, x6, betas,
+                         adam_m, adam_v, step_count, lr, st);
+}
+
+extern "C" int jrr_regressor_grad_accumulate(JrrModel* m, int64_t B, int64_t B_logical, const float* x6,
+                                             const float* betas, const float* gt_mm, float* G_accum,
+                                             float* loss_accum, void* ws, size_t ws_bytes, void* stream) {
+  Workspace w;
+  if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
+  if (!m->has_regressor) return fail(JRR_ERR_STATE, "jrr_set_regressor has not been called");
+  if (!x6 || !betas || !gt_mm || !G_accum) return fail(JRR_ERR_INVALID, "null argument");
+  if (B_logical < B) return fail(JRR_ERR_INVALID, "B_logical must be >= B");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = forward_common(m, w, betas, x6, JRR_POSE_ROT6D, false, st)) return rc;
+  // vertices kept pose-contiguous in the (otherwise idle) dvp_hi buffer
+  float* vT = w.dvp_hi;
+  if (int rc = launch_skin_fwd(m, w, nullptr, vT, true, st)) return rc;
+  if (int rc = launch_loss_seed(m, w, gt_mm, B_logical, 1.f, nullptr, st)) return rc;
+  if (int rc = launch_regressor_accumulate(m, w, vT, G_accum, st)) return rc;
+  if (loss_accum)
+    if (int rc = launch_loss_finish(w, B_logical, 1.f, 0.f, false, nullptr, loss_accum, st)) return rc;
+  return JRR_OK;
+}
+
+extern "C" int jrr_regressor_apply(JrrModel* m, float* J17_raw, const float* mask, const float* G_accum,
+                                   float* adam_m, float* adam_v, int32_t* step_count, float lr,
+                                   void* stream) {
+  if (!m || !J17_raw || !G_accum || !adam_m || !adam_v || !step_count) return fail(JRR_ERR_INVALID, "null argument");
+  if (!m->has_regressor) return fail(JRR_ERR_STATE, "jrr_set_regressor has not been called");
+  reset_launch_count();
+  return launch_regressor_apply(m, J17_raw, mask, G_accum, adam_m, adam_v, step_count, lr, (cudaStream_t)stream);
+}
+
+namespace jrr {
+__global__ void debug_split_kernel(const float* __restrict__ src, int64_t n, float* __restrict__ hi,
+                                   float* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t r;
+  const float x = src[i];
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  const float h = __uint_as_float(r);
+  hi[i] = h;
+  const float d = x - h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
+  lo[i] = __uint_as_float(r);
+}
+}  // namespace jrr
+
+extern "C" int jrr_debug_gemm(JrrModel* m, int impl, int64_t M, int64_t N, int64_t K, const float* A,
+                              const float* B, float* C, float* scratch, void* stream) {
+  if (!m || !A || !B || !C || !scratch) return fail(JRR_ERR_INVALID, "null argument");
+  reset_launch_count();
+  cudaStream_t st = (cudaStream_t)stream;
+  float* Ah = scratch;
+  float* Al = Ah + M * K;
+  float* Bh = Al + M * K;
+  float* Bl = Bh + N * K;
+  debug_split_kernel<<<(unsigned)((M * K + 255) / 256), 256, 0, st>>>(A, M * K, Ah, Al);
+  JRR_LAUNCH_CHECK();
+  debug_split_kernel<<<(unsigned)((N * K + 255) / 256), 256, 0, st>>>(B, N * K, Bh, Bl);
+  JRR_LAUNCH_CHECK();
+  GemmDesc g{};
+  g.A_hi = Ah; g.A_lo = Al; g.lda = K;
+  g.B_hi = Bh; g.B_lo = Bl; g.ldb = K;
+  g.M = M; g.N = N; g.K = K; g.ksplit = 1; g.epi = EPI_STORE_SPLITK;
+  g.out0 = C; g.ldo = N;
+  return impl == 1 ? launch_gemm_simt(g, st) : launch_gemm_tc(m, g, st);
+}

@@ -1,0 +1,250 @@
+// Pose critic (scripts/discriminator.py:7-54) on the refinement path: the per-joint 1x1
+// conv stack, the 24 joint heads, the sigmoid + MSE-vs-ones loss (scripts/optimize.py:241-247)
+// and the analytic INPUT gradient (weights are frozen inside the inner loop).  The two wide
+// layers 768->1024->1024 (and their transposes in the backward) are 3xTF32 tensor-core GEMMs
+// (jrr_gemm_tc.cu); this file holds the small fused pieces around them.
+#include "jrr_internal.cuh"
+
+namespace jrr {
+
+// offsets into JrrModel::critic_small (floats)
+constexpr int CS_C1W = 0;       // [32][6]
+constexpr int CS_C1B = 192;     // [32]
+constexpr int CS_C2W = 224;     // [32][32]
+constexpr int CS_C2B = 1248;    // [32]
+constexpr int CS_HW = 1280;     // [24][32]
+constexpr int CS_HB = 2048;     // [24]
+constexpr int CS_B1 = 2072;     // [1024]
+constexpr int CS_B2 = 3096;     // [1024]
+constexpr int CS_W3 = 4120;     // [1024]
+constexpr int CS_B3 = 5144;     // [1]
+constexpr int CS_TOTAL = 5145;
+
+__device__ __forceinline__ float tf32_hi_c(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// thread = (pose, joint): conv1x1 6->32, ReLU, conv1x1 32->32, ReLU -> h[b][j*32+c] (hi/lo)
+__global__ void __launch_bounds__(256)
+critic_pre_kernel(const float* __restrict__ cs, const float* __restrict__ x6, int64_t B, int64_t BP,
+                  float* __restrict__ h_hi, float* __restrict__ h_lo) {
+  __shared__ float sw[CS_HW];
+  for (int i = threadIdx.x; i < CS_HW; i += blockDim.x) sw[i] = cs[i];
+  __syncthreads();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= BP * NJ) return;
+  const int64_t b = idx / NJ;
+  float h2[32];
+  if (b < B) {
+    float x[6];
+    for (int i = 0; i < 6; i++) x[i] = x6[idx * 6 + i];
+    float h1[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+      float a = sw[CS_C1B + k];
+#pragma unroll
+      for (int i = 0; i < 6; i++) a = fmaf(sw[CS_C1W + k * 6 + i], x[i], a);
+      h1[k] = fmaxf(a, 0.f);
+    }
+#pragma unroll 4
+    for (int c = 0; c < 32; c++) {
+      float a = sw[CS_C2B + c];
+#pragma unroll
+      for (int k = 0; k < 32; k++) a = fmaf(sw[CS_C2W + c * 32 + k], h1[k], a);
+      h2[c] = fmaxf(a, 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; c++) h2[c] = 0.f;
+  }
+  float4* ph = reinterpret_cast<float4*>(h_hi + idx * 32);
+  float4* pl = reinterpret_cast<float4*>(h_lo + idx * 32);
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    float hi[4], lo[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      hi[t] = tf32_hi_c(h2[q * 4 + t]);
+      lo[t] = tf32_hi_c(h2[q * 4 + t] - hi[t]);
+    }
+    ph[q] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    pl[q] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// warp = pose: global head 1024->1, 24 joint heads 32->1, sigmoid, loss partial, logits grads
+constexpr int HEAD_WARPS = 8;
+__global__ void __launch_bounds__(HEAD_WARPS * 32)
+critic_head_kernel(const float* __restrict__ cs, const float* __restrict__ h_hi,
+                   const float* __restrict__ h_lo, const float* __restrict__ z2_hi,
+                   const float* __restrict__ z2_lo, int64_t B, int64_t BP, float gscale,
+                   float* __restrict__ scores_out, float* __restrict__ dz2_hi,
+                   float* __restrict__ dz2_lo, float* __restrict__ dzj, float* __restrict__ loss_part) {
+  __shared__ float red[HEAD_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * HEAD_WARPS + warp;
+  float lsum = 0.f;
+  if (b < BP) {
+    float z2[32];
+    float zg = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+      const int i = lane + 32 * q;
+      z2[q] = z2_hi[b * C_Z + i] + z2_lo[b * C_Z + i];
+      zg = fmaf(cs[CS_W3 + i], z2[q], zg);
+    }
+    for (int o = 16; o > 0; o >>= 1) zg += __shfl_xor_sync(0xffffffffu, zg, o);
+    zg += cs[CS_B3];
+    float zj = 0.f;
+    if (lane < NJ) {
+      const float* hh = h_hi + b * C_H + lane * 32;
+      const float* hl = h_lo + b * C_H + lane * 32;
+      zj = cs[CS_HB + lane];
+#pragma unroll
+      for (int c = 0; c < 32; c++) zj = fmaf(cs[CS_HW + lane * 32 + c], hh[c] + hl[c], zj);
+    }
+    const float sg = 1.f / (1.f + expf(-zg));
+    const float sj = 1.f / (1.f + expf(-zj));
+    if (b < B) {
+      if (scores_out != nullptr) {
+        if (lane == 0) scores_out[b * 25] = sg;
+        if (lane < NJ) scores_out[b * 25 + 1 + lane] = sj;
+      }
+      float l = (lane < NJ) ? (sj - 1.f) * (sj - 1.f) : 0.f;
+      if (lane == 0) l += (sg - 1.f) * (sg - 1.f);
+      for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+      lsum = l;
+    }
+    if (dz2_hi != nullptr) {
+      const float dg = (b < B) ? gscale * (sg - 1.f) * sg * (1.f - sg) : 0.f;
+      const float dj = (b < B && lane < NJ) ? gscale * (sj - 1.f) * sj * (1.f - sj) : 0.f;
+      if (lane < NJ) dzj[b * NJ + lane] = dj;
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        const int i = lane + 32 * q;
+        const float v = z2[q] > 0.f ? dg * cs[CS_W3 + i] : 0.f;
+        const float hi = tf32_hi_c(v);
+        dz2_hi[b * C_Z + i] = hi;
+        dz2_lo[b * C_Z + i] = tf32_hi_c(v - hi);
+      }
+    }
+  }
+  if (lane == 0) red[warp] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_part != nullptr) {
+    float t = 0.f;
+    for (int i = 0; i < HEAD_WARPS; i++) t += red[i];
+    loss_part[blockIdx.x] = t;
+  }
+}
+
+// thread = (pose, joint): back through the joint head and the two 1x1 convs -> dx6c[b][j*6+i]
+__global__ void __launch_bounds__(256)
+critic_post_kernel(const float* __restrict__ cs, const float* __restrict__ x6,
+                   const float* __restrict__ dh, const float* __restrict__ dzj, int64_t B,
+                   float* __restrict__ dx6c) {
+  __shared__ float sw[CS_HB];
+  for (int i = threadIdx.x; i < CS_HB; i += blockDim.x) sw[i] = cs[i];
+  __syncthreads();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * NJ) return;
+  const int j = (int)(idx % NJ);
+  float x[6];
+  for (int i = 0; i < 6; i++) x[i] = x6[idx * 6 + i];
+  float h1[32];
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    float a = sw[CS_C1B + k];
+#pragma unroll
+    for (int i = 0; i < 6; i++) a = fmaf(sw[CS_C1W + k * 6 + i], x[i], a);
+    h1[k] = fmaxf(a, 0.f);
+  }
+  const float dj = dzj[idx];
+  float dh1[32];
+#pragma unroll
+  for (int k = 0; k < 32; k++) dh1[k] = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < 32; c++) {
+    float a = sw[CS_C2B + c];
+#pragma unroll
+    for (int k = 0; k < 32; k++) a = fmaf(sw[CS_C2W + c * 32 + k], h1[k], a);
+    if (a > 0.f) {
+      const float d = dh[idx * 32 + c] + dj * sw[CS_HW + j * 32 + c];
+#pragma unroll
+      for (int k = 0; k < 32; k++) dh1[k] = fmaf(sw[CS_C2W + c * 32 + k], d, dh1[k]);
+    }
+  }
+  float dx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    if (h1[k] > 0.f) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) dx[i] = fmaf(sw[CS_C1W + k * 6 + i], dh1[k], dx[i]);
+    }
+  }
+  for (int i = 0; i < 6; i++) dx6c[idx * 6 + i] = dx[i];
+}
+
+int launch_critic_pre(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st) {
+  const int64_t n = w.BP * NJ;
+  critic_pre_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->critic_small, x6, w.B, w.BP,
+                                                                w.h_hi, w.h_lo);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_critic_head(const JrrModel* m, Workspace& w, int64_t B_logical, float w_pose,
+                       float* scores_out, bool want_grad, cudaStream_t st) {
+  const unsigned nblk = (unsigned)((w.BP + HEAD_WARPS - 1) / HEAD_WARPS);
+  const float gscale = w_pose * 2.f / (25.f * (float)B_logical);
+  w.n_pose_part = (int)nblk;
+  critic_head_kernel<<<nblk, HEAD_WARPS * 32, 0, st>>>(
+      m->critic_small, w.h_hi, w.h_lo, w.z2_hi, w.z2_lo, w.B, w.BP, gscale, scores_out,
+      want_grad ? w.dz2_hi : nullptr, w.dz2_lo, w.dzj, w.loss_part + LOSS_PART_POSE);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_critic_post(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st) {
+  const int64_t n = w.B * NJ;
+  critic_post_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->critic_small, x6, w.dh, w.dzj,
+                                                                 w.B, w.dx6c);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+// The four wide GEMMs around the small kernels.
+int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st) {
+  GemmDesc g{};
+  g.A_hi = w.h_hi; g.A_lo = w.h_lo; g.lda = C_H;
+  g.B_hi = m->W1_hi; g.B_lo = m->W1_lo; g.ldb = C_H;
+  g.M = w.BP; g.N = C_Z; g.K = C_H; g.ksplit = 1; g.epi = EPI_BIAS_RELU_SPLIT;
+  g.out0 = w.z1_hi; g.out1 = w.z1_lo; g.ldo = C_Z; g.bias = m->critic_small + CS_B1;
+  int rc = launch_gemm(m, g, st);
+  if (rc) return rc;
+  g.A_hi = w.z1_hi; g.A_lo = w.z1_lo; g.lda = C_Z;
+  g.B_hi = m->W2_hi; g.B_lo = m->W2_lo; g.ldb = C_Z;
+  g.K = C_Z; g.out0 = w.z2_hi; g.out1 = w.z2_lo; g.bias = m->critic_small + CS_B2;
+  return launch_gemm(m, g, st);
+}
+
+int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st) {
+  GemmDesc g{};
+  // dz1 = (dz2 . W2) * [z1 > 0]
+  g.A_hi = w.dz2_hi; g.A_lo = w.dz2_lo; g.lda = C_Z;
+  g.B_hi = m->W2t_hi; g.B_lo = m->W2t_lo; g.ldb = C_Z;
+  g.M = w.BP; g.N = C_Z; g.K = C_Z; g.ksplit = 1; g.epi = EPI_MASK_SPLIT;
+  g.out0 = w.dz1_hi; g.out1 = w.dz1_lo; g.ldo = C_Z; g.mask = w.z1_hi; g.ldmask = C_Z;
+  int rc = launch_gemm(m, g, st);
+  if (rc) return rc;
+  // dh = dz1 . W1
+  g.A_hi = w.dz1_hi; g.A_lo = w.dz1_lo; g.lda = C_Z;
+  g.B_hi = m->W1t_hi; g.B_lo = m->W1t_lo; g.ldb = C_Z;
+  g.N = C_H; g.K = C_Z; g.epi = EPI_STORE_SPLITK; g.out0 = w.dh; g.out1 = nullptr; g.ldo = C_H;
+  g.mask = nullptr;
+  return launch_gemm(m, g, st);
+}
+
+}  // namespace jrr

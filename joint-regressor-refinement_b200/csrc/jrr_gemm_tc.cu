@@ -1,0 +1,378 @@
+// 3xTF32 tensor-core GEMM for sm_100a: C[m][n] = sum_k A[m][k] * B[n][k] with both operands
+// K-major and pre-split into tf32 hi/lo pairs; D = A_hi.B_hi + A_lo.B_hi + A_hi.B_lo is
+// accumulated in fp32 in TMEM, which holds fp32 accuracy (the dropped lo.lo term is 2^-22).
+//
+//   * persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA
+//     issuer (one elected lane, tcgen05.mma.cta_group::1.kind::tf32), warps 2-5 = epilogue
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, 32 fp32 = 128 B per row)
+//     into an mbarrier ring; UMMA smem descriptors walk the swizzle atom in 32-byte steps
+//   * two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1
+//   * fused epilogues: transposed (pose-contiguous) store, bias+ReLU+tf32-split,
+//     ReLU-mask+tf32-split, split-K partial store
+//
+// Used for: the augmented pose/shape blend [B,224]x[224,20736] and its transpose-side
+// backward (smplx.lbs blend_shapes + pose_feature @ posedirs, reached through
+// scripts/smpl.py:72-74), and the 768->1024->1024 layers of the pose critic and their input
+// gradients (scripts/discriminator.py:24-30,41).
+#include <cuda.h>
+
+#include "jrr_internal.cuh"
+
+namespace jrr {
+
+constexpr int BM = 128;
+constexpr int BK = 32;  // fp32 per stage row = 128 bytes = one swizzle atom
+constexpr int TC_THREADS = 192;
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float v[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tf32_hi_g(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major, SWIZZLE_128B smem matrix descriptor (rows of 128 bytes, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);          // start address  [0,14)
+  d |= (uint64_t)0 << 16;                           // leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  return d;
+}
+
+struct TcParams {
+  int64_t M, N, K;     // K = per-split extent
+  int ksplit;
+  int m_tiles, n_tiles;
+  float* out0; float* out1; int64_t ldo;
+  const float* bias;
+  const float* mask; int64_t ldmask;
+};
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = (BN <= 128) ? 3 : 2;
+  static constexpr int A_BYTES = BM * BK * 4;       // 16 KB
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+               const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+               const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (int)(p.K / BK);
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int num_tiles = tiles_mn * p.ksplit;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int r = t % tiles_mn;
+        const int mb = r % p.m_tiles, nb = r / p.m_tiles;
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int kc = (int)(split * p.K) + kb * BK;
+          tma_load_2d(&mapAh, &full_bar[stage], sa, kc, mb * BM);
+          tma_load_2d(&mapAl, &full_bar[stage], sa + Cfg::A_BYTES, kc, mb * BM);
+          tma_load_2d(&mapBh, &full_bar[stage], sa + 2 * Cfg::A_BYTES, kc, nb * BN);
+          tma_load_2d(&mapBl, &full_bar[stage], sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, kc, nb * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+      for (int kb = 0; kb < num_kb; kb++) {
+        if (lane == 0) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t dAh = make_sdesc(sa);
+          const uint64_t dAl = make_sdesc(sa + Cfg::A_BYTES);
+          const uint64_t dBh = make_sdesc(sa + 2 * Cfg::A_BYTES);
+          const uint64_t dBl = make_sdesc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 8; k++) {
+            const uint64_t ko = (uint64_t)(k * 32 >> 4);  // 8 tf32 = 32 bytes along K
+            tc_mma_tf32(d_tmem, dAl + ko, dBh + ko, idesc, (kb | k) != 0);
+            tc_mma_tf32(d_tmem, dAh + ko, dBl + ko, idesc, 1);
+            tc_mma_tf32(d_tmem, dAh + ko, dBh + ko, idesc, 1);
+          }
+          tc_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) tc_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int split = t / tiles_mn;
+      const int r = t % tiles_mn;
+      const int mb = r % p.m_tiles, nb = r / p.m_tiles;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int64_t m = (int64_t)mb * BM + q * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        float v[32];
+        tc_ld32(trow + c * 32, v);
+        const int64_t n0 = (int64_t)nb * BN + c * 32;
+        if (EPI == EPI_STORE_T) {
+          // out[n][m]: lanes hold consecutive m -> one 128-byte line per column
+          if (m < p.M) {
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+              if (n0 + i < p.N) p.out0[(n0 + i) * p.ldo + m] = v[i];
+          }
+        } else if (EPI == EPI_BIAS_RELU_SPLIT || EPI == EPI_MASK_SPLIT) {
+          if (m < p.M && n0 < p.N) {
+            float hi[32], lo[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+              float x = v[i];
+              if (EPI == EPI_BIAS_RELU_SPLIT) x = fmaxf(x + __ldg(p.bias + n0 + i), 0.f);
+              else x = (p.mask[m * p.ldmask + n0 + i] > 0.f) ? x : 0.f;
+              hi[i] = tf32_hi_g(x);
+              lo[i] = tf32_hi_g(x - hi[i]);
+            }
+            float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
+            float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+          }
+        } else {
+          if (m < p.M && n0 < p.N) {
+            float4* o = reinterpret_cast<float4*>(p.out0 + ((int64_t)split * p.M + m) * p.ldo + n0);
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(JRR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(JRR_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return JRR_OK;
+}
+
+static int num_sms(int device) {
+  static int cached[64] = {0};
+  if (device < 0 || device >= 64) device = 0;
+  if (!cached[device]) cudaDeviceGetAttribute(&cached[device], cudaDevAttrMultiProcessorCount, device);
+  return cached[device];
+}
+
+template <int BN, int EPI>
+static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  const int64_t Ktot = g.K * g.ksplit;
+  if (int rc = make_map(&mAh, g.A_hi, g.M, Ktot, g.lda, BM)) return rc;
+  if (int rc = make_map(&mAl, g.A_lo, g.M, Ktot, g.lda, BM)) return rc;
+  if (int rc = make_map(&mBh, g.B_hi, g.N, Ktot, g.ldb, BN)) return rc;
+  if (int rc = make_map(&mBl, g.B_lo, g.N, Ktot, g.ldb, BN)) return rc;
+  TcParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K; p.ksplit = g.ksplit;
+  p.m_tiles = (int)(g.M / BM);
+  p.n_tiles = (int)((g.N + BN - 1) / BN);
+  p.out0 = g.out0; p.out1 = g.out1; p.ldo = g.ldo; p.bias = g.bias; p.mask = g.mask; p.ldmask = g.ldmask;
+  auto kern = gemm_tc_kernel<BN, EPI>;
+  JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
+  const int grid = std::min(tiles, num_sms(m->device));
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
+  if (g.M % BM != 0 || g.K % BK != 0) return fail(JRR_ERR_INVALID, "tc gemm: M%128 or K%32");
+  if (((uintptr_t)g.A_hi | (uintptr_t)g.A_lo | (uintptr_t)g.B_hi | (uintptr_t)g.B_lo) & 15)
+    return fail(JRR_ERR_INVALID, "tc gemm: operands must be 16-byte aligned");
+  switch (g.epi) {
+    case EPI_STORE_T:
+      if (g.N % 128 == 0) return launch_tc<128, EPI_STORE_T>(m, g, st);
+      break;
+    case EPI_BIAS_RELU_SPLIT:
+      if (g.N % 128 == 0) return launch_tc<128, EPI_BIAS_RELU_SPLIT>(m, g, st);
+      break;
+    case EPI_MASK_SPLIT:
+      if (g.N % 128 == 0) return launch_tc<128, EPI_MASK_SPLIT>(m, g, st);
+      break;
+    case EPI_STORE_SPLITK:
+      if (g.N == 224) return launch_tc<224, EPI_STORE_SPLITK>(m, g, st);
+      if (g.N % 128 == 0) return launch_tc<128, EPI_STORE_SPLITK>(m, g, st);
+      break;
+  }
+  return fail(JRR_ERR_INVALID, "tc gemm: unsupported shape/epilogue");
+}
+
+}  // namespace jrr

@@ -1,0 +1,223 @@
+// Internal declarations shared by the libjrr.so translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+
+#include "../../include/jrr.h"
+
+namespace jrr {
+
+// ---- canonical sizes -------------------------------------------------------------------
+constexpr int V = JRR_NUM_VERTS;    // 6890
+constexpr int VP = 6912;            // vertices padded to 54*128
+constexpr int NP = 3 * VP;          // 20736 blend columns (3 per packed vertex)
+constexpr int NJ = 24;
+constexpr int NB = 10;
+constexpr int NF = 207;             // pose-feature length
+constexpr int KA = 224;             // augmented K: 207 pose + 10 beta + 1 template, padded to 7*32
+constexpr int FEAT_BETA = 207;
+constexpr int FEAT_ONE = 217;
+constexpr int NH = 17;              // regressed joints
+constexpr int NACC = 51;            // 17*3
+constexpr int JH_STRIDE = 20;       // padded Jhat column record
+constexpr int VS = 256;             // packed vertices per skinning range (one CTA column)
+constexpr int NSPLIT = VP / VS;     // 27
+constexpr int KSPLIT = 6;           // split-K of the backward blend GEMM (20736 = 6*3456)
+constexpr int NPARAM = 154;         // 144 rot6d + 10 betas per pose
+constexpr int MAXCH = 4;            // children per joint supported by the chain kernels
+
+constexpr int C_H = 768;            // critic: 24*32 conv features
+constexpr int C_Z = 1024;
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- error handling ----------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int status, const std::string& msg);
+void count_launch(int n = 1);
+void reset_launch_count();
+
+#define JRR_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ::jrr::fail(JRR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+  } while (0)
+
+#define JRR_LAUNCH_CHECK()                                                                     \
+  do {                                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess)                                                                     \
+      return ::jrr::fail(JRR_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+    ::jrr::count_launch();                                                                     \
+  } while (0)
+
+// ---- small tables passed to the chain kernels by value ------------------------------------
+struct ChainTab {
+  int parent[NJ];
+  int depth[NJ];
+  int child[NJ][MAXCH];  // -1 when absent
+  int max_depth;
+};
+
+// per packed vertex: skinning run record (ELL-4 with register-cached joint slots)
+//   meta bits [5k,5k+5)  joint id of slot k (k=0..3)
+//   meta bits [20+k]     slot k must be (re)loaded before this vertex
+//   meta bit  24         this vertex has a non-zero column in the normalised regressor
+//   meta bit  25         first vertex of a range (slots are loaded without a flush)
+//   xptr/xcnt           slice of (source, coef) pairs: the joints49 sources (21 vertex picks,
+//                       9 extra-regressor rows) this vertex feeds (module backward)
+struct VtxRec {
+  uint32_t meta;
+  float w[4];
+  int xptr;
+  int xcnt;
+  int pad;
+};
+static_assert(sizeof(VtxRec) == 32, "VtxRec is loaded as two uint4");
+constexpr int LOSS_PART_POSE = 4096;  // offset of the critic partials inside Workspace::loss_part
+constexpr int64_t MAX_POSES_PER_CALL = 262144;
+
+// sparse rows (CSR over ORIGINAL vertex ids) for the joints49 path
+struct Csr {
+  int* ptr = nullptr;
+  int* col = nullptr;
+  float* val = nullptr;
+  int rows = 0;
+};
+
+}  // namespace jrr
+
+struct JrrModel {
+  int device = 0;
+  int gemm_impl = 0;
+  jrr::ChainTab chain;
+  // augmented blend matrix, tf32 hi/lo split, both majors
+  float *Pt_hi = nullptr, *Pt_lo = nullptr;  // [NP][KA]  (K contiguous)  forward B operand
+  float *P_hi = nullptr, *P_lo = nullptr;    // [KA][NP]  (N contiguous)  backward B operand
+  float* J0 = nullptr;                       // [24][3]      J_regressor . v_template
+  float* JS = nullptr;                       // [24][3][10]  J_regressor . shapedirs
+  jrr::VtxRec* vrec = nullptr;               // [VP]
+  int* vx_src = nullptr;                     // joints49 sources per vertex (see VtxRec)
+  float* vx_coef = nullptr;
+  int n_flush = 0;                           // dA flush events per pose
+  int* flush_ptr = nullptr;                  // [25] CSR joint -> flush ids
+  int* flush_idx = nullptr;                  // [n_flush]
+  int* range_flush_base = nullptr;           // [NSPLIT]
+  // joints49 path
+  jrr::Csr extra;                            // [9] rows over original vertex ids
+  int* picks = nullptr;                      // [21]
+  int* joint_map = nullptr;                  // [49]
+  // regressor (normalised), refreshed by jrr_set_regressor / jrr_regressor_apply
+  float* Jhat = nullptr;                     // [17][V]   original vertex order
+  float* Jhat_cols = nullptr;                // [VP][20]  packed order, zero padded
+  float* rowsum = nullptr;                   // [17]
+  float* regdot = nullptr;                   // [17] scratch of jrr_regressor_apply
+  bool has_regressor = false;
+  // critic
+  float* critic_small = nullptr;             // conv + heads + w3/b3 + biases (see jrr_critic.cu)
+  float *W1_hi = nullptr, *W1_lo = nullptr;    // [1024][768]
+  float *W2_hi = nullptr, *W2_lo = nullptr;    // [1024][1024]
+  float *W1t_hi = nullptr, *W1t_lo = nullptr;  // [768][1024]
+  float *W2t_hi = nullptr, *W2t_lo = nullptr;  // [1024][1024]
+  bool has_critic = false;
+  std::vector<void*> allocs;
+};
+
+namespace jrr {
+
+// ---- workspace ---------------------------------------------------------------------------
+struct Workspace {
+  int64_t B, BP;
+  float* AT;        // [288][BP]   relative transforms, pose contiguous
+  float* feat_hi;   // [BP][224]
+  float* feat_lo;
+  float* vpT;       // [NP][BP]    posed-blend vertices, pose contiguous
+  float* part;      // [NSPLIT][51][BP] regressor partial sums
+  float* gT;        // [51][BP]    loss seed (pelvis adjusted)
+  float* pred;      // [BP][51]
+  float* dvp_hi;    // [BP][NP]
+  float* dvp_lo;
+  float* dAflush;   // [n_flush][12][BP]
+  float* dAT;       // [288][BP]
+  float* dfeat;     // [KSPLIT][BP][224]
+  float* dJp;       // [BP][72]    grad wrt posed joints (module path)
+  float* Jp;        // [BP][72]    posed joints
+  float* d30T;      // [90][BP]    joints49 gradient gathered onto picks / extra rows
+  float* loss_part; // [2][4096]   per-CTA loss partials: joint term, critic term
+  int n_pose_part;  // CTAs that wrote critic partials in this step
+  // critic
+  float *h_hi, *h_lo;      // [BP][768]
+  float *z1_hi, *z1_lo;    // [BP][1024]
+  float *z2_hi, *z2_lo;    // [BP][1024]
+  float *dz2_hi, *dz2_lo;  // [BP][1024]
+  float *dz1_hi, *dz1_lo;  // [BP][1024]
+  float* dh;               // [BP][768]
+  float* dzj;              // [BP][24]   grads wrt the 24 joint-head logits
+  float* dx6c;             // [BP][144]  critic grad wrt rot6d
+  float* scores;           // [BP][25]
+  size_t bytes;
+};
+Workspace carve(const JrrModel* m, int64_t B, void* base);
+
+// ---- kernels (host launch wrappers; all asynchronous on `st`) --------------------------------
+int launch_pose_fwd(const JrrModel* m, int64_t B, int64_t BP, const float* betas, const float* pose,
+                    int kind, float* AT, float* feat_hi, float* feat_lo, float* Jp, cudaStream_t st);
+
+// C[m][n] = sum_k A[m][k] * B[n][k], operands given as tf32 hi/lo pairs
+enum GemmEpi { EPI_STORE_T = 0, EPI_BIAS_RELU_SPLIT = 1, EPI_MASK_SPLIT = 2, EPI_STORE_SPLITK = 3 };
+struct GemmDesc {
+  const float *A_hi, *A_lo; int64_t lda;
+  const float *B_hi, *B_lo; int64_t ldb;
+  int64_t M, N, K;          // K here is the per-split K extent
+  int ksplit;               // number of K splits (EPI_STORE_SPLITK), else 1
+  int epi;
+  float* out0; float* out1; int64_t ldo;   // out (or out_hi/out_lo)
+  const float* bias;                       // [N] (EPI_BIAS_RELU_SPLIT)
+  const float* mask; int64_t ldmask;       // (EPI_MASK_SPLIT) multiply by (mask>0)
+};
+int launch_gemm(const JrrModel* m, const GemmDesc& g, cudaStream_t st);
+int launch_gemm_simt(const GemmDesc& g, cudaStream_t st);
+int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st);
+
+int launch_skin_fwd(const JrrModel* m, const Workspace& w, float* vertices_out, float* vT_out,
+                    bool want_part, cudaStream_t st);
+int launch_loss_seed(const JrrModel* m, const Workspace& w, const float* gt_mm, int64_t B_logical,
+                     float w_joint, float* joints17_out, cudaStream_t st);
+int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_g,
+                    bool use_x, cudaStream_t st);
+int launch_dA_reduce(const JrrModel* m, const Workspace& w, cudaStream_t st);
+int launch_joints49_fwd(const JrrModel* m, const Workspace& w, const float* vertices,
+                        float* joints49_out, cudaStream_t st);
+int launch_joints49_bwd(const JrrModel* m, const Workspace& w, const float* djoints49,
+                        cudaStream_t st);
+int launch_pose_bwd(const JrrModel* m, const Workspace& w, const float* betas, const float* pose,
+                    int kind, bool use_dJp, bool use_critic, float* dbetas_out, float* dpose_out,
+                    // Adam (refine step) -- all NULL on the module path
+                    float* x6, float* betas_rw, float* adam_m, float* adam_v, int32_t* step_count,
+                    float lr, cudaStream_t st);
+
+int launch_critic_pre(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st);
+int launch_critic_head(const JrrModel* m, Workspace& w, int64_t B_logical, float w_pose,
+                       float* scores_out, bool want_grad, cudaStream_t st);
+int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st);
+int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st);
+int launch_critic_post(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st);
+
+int launch_loss_finish(const Workspace& w, int64_t B_logical, float w_joint, float w_pose,
+                       bool have_pose, float* loss_out, float* loss_accum, cudaStream_t st);
+
+int launch_regressor_normalise(JrrModel* m, const float* Jraw, const float* mask, cudaStream_t st);
+int launch_regressor_accumulate(const JrrModel* m, const Workspace& w, const float* vT,
+                                float* G_accum, cudaStream_t st);
+int launch_regressor_apply(JrrModel* m, float* Jraw, const float* mask, const float* G,
+                           float* adam_m, float* adam_v, int32_t* step_count, float lr,
+                           cudaStream_t st);
+
+// tf32 helpers (host): round-to-nearest-even into the 19-bit tf32 container
+float tf32_round_host(float x);
+
+}  // namespace jrr

@@ -1,0 +1,513 @@
+// Model packing (host) and the regressor / critic state kernels.
+//
+// jrr_model_create turns the smplx buffers into the layouts the kernels want:
+//   * augmented blend matrix [posedirs ; shapedirs^T ; v_template] (K = 218 -> 224,
+//     N = 3*6890 -> 20736), tf32 hi/lo split, in both majors
+//   * J0 = J24.v_template and JS = J24.shapedirs so rest joints are J0 + JS.beta (72x10)
+//   * skinning "run" records: <= 4 (joint, weight) slots per vertex, slot-stable so that the
+//     kernels re-fetch a joint transform only when a slot's joint changes; the matching list
+//     of dA flush events per joint
+//   * CSR rows of J_regressor_extra, the 21 vertex picks and the 49-joint map
+// Replaces: smplx.SMPL.__init__ buffers + scripts/smpl.py:64-70.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "jrr_internal.cuh"
+
+namespace jrr {
+
+static thread_local std::string g_err;
+static thread_local int64_t g_launches = 0;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int status, const std::string& msg) { g_err = msg; return status; }
+void count_launch(int n) { g_launches += n; }
+void reset_launch_count() { g_launches = 0; }
+
+float tf32_round_host(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  // round to nearest, ties away from zero in magnitude (matches cvt.rna)
+  u += 0x00001000u;
+  u &= 0xffffe000u;
+  float r;
+  std::memcpy(&r, &u, 4);
+  return r;
+}
+
+template <typename T>
+static int upload(JrrModel* m, T** dst, const std::vector<T>& src) {
+  JRR_CUDA(cudaMalloc((void**)dst, std::max<size_t>(src.size(), 1) * sizeof(T)));
+  m->allocs.push_back(*dst);
+  if (!src.empty()) JRR_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return JRR_OK;
+}
+template <typename T>
+static int dalloc(JrrModel* m, T** dst, size_t n, bool zero = true) {
+  JRR_CUDA(cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T)));
+  m->allocs.push_back(*dst);
+  if (zero) JRR_CUDA(cudaMemset(*dst, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  return JRR_OK;
+}
+
+static void split_hi_lo(const std::vector<float>& x, std::vector<float>& hi, std::vector<float>& lo) {
+  hi.resize(x.size());
+  lo.resize(x.size());
+  for (size_t i = 0; i < x.size(); i++) {
+    hi[i] = tf32_round_host(x[i]);
+    lo[i] = tf32_round_host(x[i] - hi[i]);
+  }
+}
+
+// --------------------------------------------------------------------- regressor kernels
+__global__ void reg_rowsum_kernel(const float* __restrict__ J, const float* __restrict__ mask,
+                                  float* __restrict__ rowsum) {
+  __shared__ float red[256];
+  const int j = blockIdx.x;
+  float a = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    float x = J[j * V + v] * (mask ? mask[j * V + v] : 1.f);
+    a += fmaxf(x, 0.f);
+  }
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) rowsum[j] = red[0];
+}
+
+__global__ void reg_normalise_kernel(const float* __restrict__ J, const float* __restrict__ mask,
+                                     const float* __restrict__ rowsum, float* __restrict__ Jhat,
+                                     float* __restrict__ Jhat_cols) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NH * V) return;
+  const int j = idx / V, v = idx % V;
+  float x = J[idx] * (mask ? mask[idx] : 1.f);
+  float r = fmaxf(x, 0.f) / rowsum[j];
+  Jhat[idx] = r;
+  Jhat_cols[v * JH_STRIDE + j] = r;
+}
+
+__global__ void reg_flags_kernel(const float* __restrict__ Jhat_cols, VtxRec* __restrict__ vrec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= VP) return;
+  bool any = false;
+  for (int j = 0; j < NH; j++) any |= (Jhat_cols[i * JH_STRIDE + j] != 0.f);
+  uint32_t meta = vrec[i].meta & ~(1u << 24);
+  vrec[i].meta = meta | (any ? (1u << 24) : 0u);
+}
+
+// G[j][i] += sum_b sum_c gT[3j+c][b] * vT[3i+c][b]; one warp per vertex, g tile in smem
+constexpr int RA_WARPS = 8;
+constexpr int RA_BCH = 128;
+__global__ void __launch_bounds__(RA_WARPS * 32)
+reg_accumulate_kernel(const float* __restrict__ gT, const float* __restrict__ vT, int64_t B,
+                      int64_t BP, float* __restrict__ G) {
+  __shared__ float sg[NACC][RA_BCH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * RA_WARPS + warp;
+  float acc[NH];
+#pragma unroll
+  for (int j = 0; j < NH; j++) acc[j] = 0.f;
+  for (int64_t bc = 0; bc < BP; bc += RA_BCH) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < NACC * RA_BCH; e += blockDim.x) {
+      const int a = e / RA_BCH, bb = e % RA_BCH;
+      sg[a][bb] = (bc + bb < B) ? gT[(int64_t)a * BP + bc + bb] : 0.f;
+    }
+    __syncthreads();
+    if (i < V) {
+#pragma unroll
+      for (int q = 0; q < RA_BCH / 32; q++) {
+        const int bb = lane + 32 * q;
+        const float x = vT[(int64_t)(3 * i + 0) * BP + bc + bb];
+        const float y = vT[(int64_t)(3 * i + 1) * BP + bc + bb];
+        const float z = vT[(int64_t)(3 * i + 2) * BP + bc + bb];
+#pragma unroll
+        for (int j = 0; j < NH; j++)
+          acc[j] += sg[j * 3 + 0][bb] * x + sg[j * 3 + 1][bb] * y + sg[j * 3 + 2][bb] * z;
+      }
+    }
+  }
+  if (i < V) {
+#pragma unroll
+    for (int j = 0; j < NH; j++) {
+      float a = acc[j];
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) G[j * V + i] += a;
+    }
+  }
+}
+
+__global__ void reg_dot_kernel(const float* __restrict__ G, const float* __restrict__ Jhat,
+                               float* __restrict__ dot) {
+  __shared__ float red[256];
+  const int j = blockIdx.x;
+  float a = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) a += G[j * V + v] * Jhat[j * V + v];
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dot[j] = red[0];
+}
+
+__global__ void reg_adam_kernel(float* __restrict__ J, const float* __restrict__ mask,
+                                const float* __restrict__ G, const float* __restrict__ dot,
+                                const float* __restrict__ rowsum, float* __restrict__ am,
+                                float* __restrict__ av, const int32_t* __restrict__ step_count, float lr) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NH * V) return;
+  const int j = idx / V;
+  const float mk = mask ? mask[idx] : 1.f;
+  const float x = J[idx] * mk;
+  // d/dJ of relu(J*mask)/rowsum contracted with G (utils.py:87-92 backward)
+  const float g = x > 0.f ? (G[idx] - dot[j]) / rowsum[j] * mk : 0.f;
+  const int t = *step_count + 1;
+  const float bc2s = (float)sqrt(1.0 - pow(0.999, (double)t));
+  const float step = (float)((double)lr / (1.0 - pow(0.9, (double)t)));
+  const float m = 0.9f * am[idx] + 0.1f * g;
+  const float v = 0.999f * av[idx] + 0.001f * g * g;
+  am[idx] = m;
+  av[idx] = v;
+  J[idx] = J[idx] - step * (m / (sqrtf(v) / bc2s + 1e-8f));
+}
+
+__global__ void bump_kernel(int32_t* c) { *c += 1; }
+
+int launch_regressor_normalise(JrrModel* m, const float* Jraw, const float* mask, cudaStream_t st) {
+  reg_rowsum_kernel<<<NH, 256, 0, st>>>(Jraw, mask, m->rowsum);
+  JRR_LAUNCH_CHECK();
+  reg_normalise_kernel<<<(NH * V + 255) / 256, 256, 0, st>>>(Jraw, mask, m->rowsum, m->Jhat, m->Jhat_cols);
+  JRR_LAUNCH_CHECK();
+  reg_flags_kernel<<<(VP + 255) / 256, 256, 0, st>>>(m->Jhat_cols, m->vrec);
+  JRR_LAUNCH_CHECK();
+  m->has_regressor = true;
+  return JRR_OK;
+}
+
+int launch_regressor_accumulate(const JrrModel* m, const Workspace& w, const float* vT,
+                                float* G_accum, cudaStream_t st) {
+  (void)m;
+  reg_accumulate_kernel<<<(V + RA_WARPS - 1) / RA_WARPS, RA_WARPS * 32, 0, st>>>(w.gT, vT, w.B, w.BP, G_accum);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_regressor_apply(JrrModel* m, float* Jraw, const float* mask, const float* G, float* adam_m,
+                           float* adam_v, int32_t* step_count, float lr, cudaStream_t st) {
+  reg_dot_kernel<<<NH, 256, 0, st>>>(G, m->Jhat, m->regdot);
+  JRR_LAUNCH_CHECK();
+  reg_adam_kernel<<<(NH * V + 255) / 256, 256, 0, st>>>(Jraw, mask, G, m->regdot, m->rowsum, adam_m,
+                                                       adam_v, step_count, lr);
+  JRR_LAUNCH_CHECK();
+  bump_kernel<<<1, 1, 0, st>>>(step_count);
+  JRR_LAUNCH_CHECK();
+  return launch_regressor_normalise(m, Jraw, mask, st);
+}
+
+// --------------------------------------------------------------------- critic load kernels
+__global__ void split_kernel(const float* __restrict__ src, int64_t n, float* __restrict__ hi,
+                             float* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t r;
+  float x = src[i];
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  float h = __uint_as_float(r);
+  hi[i] = h;
+  float d = x - h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
+  lo[i] = __uint_as_float(r);
+}
+
+__global__ void split_transpose_kernel(const float* __restrict__ src, int rows, int cols,
+                                       float* __restrict__ hi, float* __restrict__ lo) {
+  // src [rows][cols] -> hi/lo [cols][rows]
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * cols) return;
+  const int c = (int)(i / rows), r = (int)(i % rows);
+  uint32_t q;
+  float x = src[(int64_t)r * cols + c];
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(x));
+  float h = __uint_as_float(q);
+  hi[i] = h;
+  float d = x - h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(d));
+  lo[i] = __uint_as_float(q);
+}
+
+}  // namespace jrr
+
+using namespace jrr;
+
+extern "C" const char* jrr_last_error(void) { return g_err.c_str(); }
+extern "C" int jrr_abi_version(void) { return JRR_ABI_VERSION; }
+extern "C" int64_t jrr_last_launch_count(void) { return g_launches; }
+
+extern "C" int jrr_model_destroy(JrrModel* m) {
+  if (!m) return JRR_OK;
+  cudaSetDevice(m->device);
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+  return JRR_OK;
+}
+
+static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
+  m->device = d->device;
+  m->gemm_impl = d->gemm_impl;
+  JRR_CUDA(cudaSetDevice(d->device));
+
+  // ---- kinematic tree
+  ChainTab& ct = m->chain;
+  ct.max_depth = 0;
+  for (int j = 0; j < NJ; j++)
+    for (int c = 0; c < MAXCH; c++) ct.child[j][c] = -1;
+  for (int j = 0; j < NJ; j++) {
+    int p = (int)d->parents_host[j];
+    if (j == 0) p = -1;
+    if (j > 0 && (p < 0 || p >= j)) return fail(JRR_ERR_INVALID, "parents must precede their children");
+    ct.parent[j] = p;
+    ct.depth[j] = p < 0 ? 0 : ct.depth[p] + 1;
+    ct.max_depth = std::max(ct.max_depth, ct.depth[j]);
+    if (p >= 0) {
+      int c = 0;
+      while (c < MAXCH && ct.child[p][c] >= 0) c++;
+      if (c == MAXCH) return fail(JRR_ERR_INVALID, "more than 4 children per joint not supported");
+      ct.child[p][c] = j;
+    }
+  }
+
+  // ---- augmented blend matrix
+  {
+    std::vector<float> P((size_t)KA * NP, 0.f), Pt((size_t)NP * KA, 0.f), hi, lo;
+    for (int v = 0; v < V; v++)
+      for (int c = 0; c < 3; c++) {
+        const size_t n = (size_t)3 * v + c;
+        for (int k = 0; k < NF; k++) P[(size_t)k * NP + n] = d->posedirs_host[(size_t)k * (3 * V) + 3 * v + c];
+        for (int l = 0; l < NB; l++) P[(size_t)(FEAT_BETA + l) * NP + n] = d->shapedirs_host[((size_t)v * 3 + c) * NB + l];
+        P[(size_t)FEAT_ONE * NP + n] = d->v_template_host[(size_t)v * 3 + c];
+      }
+    for (int k = 0; k < KA; k++)
+      for (size_t n = 0; n < (size_t)NP; n++) Pt[n * KA + k] = P[(size_t)k * NP + n];
+    split_hi_lo(P, hi, lo);
+    if (int rc = upload(m, &m->P_hi, hi)) return rc;
+    if (int rc = upload(m, &m->P_lo, lo)) return rc;
+    split_hi_lo(Pt, hi, lo);
+    if (int rc = upload(m, &m->Pt_hi, hi)) return rc;
+    if (int rc = upload(m, &m->Pt_lo, lo)) return rc;
+  }
+
+  // ---- rest-joint pre-contraction
+  {
+    std::vector<float> J0(NJ * 3), JS(NJ * 3 * NB);
+    for (int j = 0; j < NJ; j++)
+      for (int c = 0; c < 3; c++) {
+        double a = 0.0;
+        double s[NB] = {0};
+        for (int v = 0; v < V; v++) {
+          const double r = d->J_regressor_host[(size_t)j * V + v];
+          if (r == 0.0) continue;
+          a += r * d->v_template_host[(size_t)v * 3 + c];
+          for (int l = 0; l < NB; l++) s[l] += r * d->shapedirs_host[((size_t)v * 3 + c) * NB + l];
+        }
+        J0[j * 3 + c] = (float)a;
+        for (int l = 0; l < NB; l++) JS[(j * 3 + c) * NB + l] = (float)s[l];
+      }
+    if (int rc = upload(m, &m->J0, J0)) return rc;
+    if (int rc = upload(m, &m->JS, JS)) return rc;
+  }
+
+  // ---- joints49 tables
+  std::vector<std::vector<std::pair<int, float>>> vx(VP);  // per vertex: (source-24, coef)
+  {
+    std::vector<int> picks(JRR_NUM_PICKS), jm(JRR_NUM_OUT_JOINTS);
+    for (int p = 0; p < JRR_NUM_PICKS; p++) {
+      int64_t v = d->vertex_picks_host[p];
+      if (v < 0 || v >= V) return fail(JRR_ERR_INVALID, "vertex pick out of range");
+      picks[p] = (int)v;
+      vx[v].push_back({p, 1.f});
+    }
+    for (int o = 0; o < JRR_NUM_OUT_JOINTS; o++) {
+      int64_t s = d->joint_map_host[o];
+      if (s < 0 || s >= 54) return fail(JRR_ERR_INVALID, "joint_map entry out of range");
+      jm[o] = (int)s;
+    }
+    std::vector<int> ptr(JRR_NUM_EXTRA + 1, 0), col;
+    std::vector<float> val;
+    for (int e = 0; e < JRR_NUM_EXTRA; e++) {
+      for (int v = 0; v < V; v++) {
+        const float x = d->J_regressor_extra_host[(size_t)e * V + v];
+        if (x != 0.f) {
+          col.push_back(v);
+          val.push_back(x);
+          vx[v].push_back({JRR_NUM_PICKS + e, x});
+        }
+      }
+      ptr[e + 1] = (int)col.size();
+    }
+    m->extra.rows = JRR_NUM_EXTRA;
+    if (int rc = upload(m, &m->extra.ptr, ptr)) return rc;
+    if (int rc = upload(m, &m->extra.col, col)) return rc;
+    if (int rc = upload(m, &m->extra.val, val)) return rc;
+    if (int rc = upload(m, &m->picks, picks)) return rc;
+    if (int rc = upload(m, &m->joint_map, jm)) return rc;
+  }
+
+  // ---- skinning run records + dA flush lists
+  {
+    std::vector<VtxRec> rec(VP);
+    std::vector<int> vx_src;
+    std::vector<float> vx_coef;
+    std::vector<int> flush_joint;
+    std::vector<int> range_base(NSPLIT);
+    int cur[4] = {0, 0, 0, 0};
+    for (int i = 0; i < VP; i++) {
+      const bool first = (i % VS) == 0;
+      if (first) range_base[i / VS] = (int)flush_joint.size();
+      std::vector<std::pair<int, float>> nz;
+      if (i < V)
+        for (int j = 0; j < NJ; j++) {
+          const float x = d->lbs_weights_host[(size_t)i * NJ + j];
+          if (x != 0.f) nz.push_back({j, x});
+        }
+      if (nz.size() > 4)
+        return fail(JRR_ERR_INVALID, "lbs_weights row with more than 4 non-zeros is not supported by this build");
+      int nj[4];
+      float nw[4] = {0.f, 0.f, 0.f, 0.f};
+      bool used[4] = {false, false, false, false};
+      for (int k = 0; k < 4; k++) nj[k] = first ? 0 : cur[k];
+      std::vector<std::pair<int, float>> rest;
+      for (auto& e : nz) {
+        int hit = -1;
+        if (!first)
+          for (int k = 0; k < 4; k++)
+            if (!used[k] && cur[k] == e.first) { hit = k; break; }
+        if (hit >= 0) { used[hit] = true; nw[hit] = e.second; }
+        else rest.push_back(e);
+      }
+      for (auto& e : rest)
+        for (int k = 0; k < 4; k++)
+          if (!used[k]) { used[k] = true; nj[k] = e.first; nw[k] = e.second; break; }
+      uint32_t meta = 0;
+      for (int k = 0; k < 4; k++) {
+        meta |= (uint32_t)nj[k] << (5 * k);
+        const bool reload = first || nj[k] != cur[k];
+        if (reload) {
+          meta |= 1u << (20 + k);
+          if (!first) flush_joint.push_back(cur[k]);
+        }
+        cur[k] = nj[k];
+      }
+      if (first) meta |= 1u << 25;
+      rec[i].meta = meta;
+      for (int k = 0; k < 4; k++) rec[i].w[k] = nw[k];
+      rec[i].xptr = (int)vx_src.size();
+      rec[i].xcnt = (int)vx[i].size();
+      rec[i].pad = 0;
+      for (auto& e : vx[i]) { vx_src.push_back(e.first); vx_coef.push_back(e.second); }
+      if ((i % VS) == VS - 1)
+        for (int k = 0; k < 4; k++) flush_joint.push_back(cur[k]);
+    }
+    m->n_flush = (int)flush_joint.size();
+    std::vector<int> fptr(NJ + 1, 0), fidx(flush_joint.size());
+    for (int f : flush_joint) fptr[f + 1]++;
+    for (int j = 0; j < NJ; j++) fptr[j + 1] += fptr[j];
+    std::vector<int> fill(fptr.begin(), fptr.end() - 1);
+    for (int f = 0; f < (int)flush_joint.size(); f++) fidx[fill[flush_joint[f]]++] = f;
+    if (int rc = upload(m, &m->vrec, rec)) return rc;
+    if (int rc = upload(m, &m->vx_src, vx_src)) return rc;
+    if (int rc = upload(m, &m->vx_coef, vx_coef)) return rc;
+    if (int rc = upload(m, &m->flush_ptr, fptr)) return rc;
+    if (int rc = upload(m, &m->flush_idx, fidx)) return rc;
+    if (int rc = upload(m, &m->range_flush_base, range_base)) return rc;
+  }
+
+  // ---- regressor state
+  if (int rc = dalloc(m, &m->Jhat, (size_t)NH * V)) return rc;
+  if (int rc = dalloc(m, &m->Jhat_cols, (size_t)VP * JH_STRIDE)) return rc;
+  if (int rc = dalloc(m, &m->rowsum, NH)) return rc;
+  if (int rc = dalloc(m, &m->regdot, NH)) return rc;
+  // ---- critic state
+  if (int rc = dalloc(m, &m->critic_small, 8192)) return rc;
+  if (int rc = dalloc(m, &m->W1_hi, (size_t)C_Z * C_H)) return rc;
+  if (int rc = dalloc(m, &m->W1_lo, (size_t)C_Z * C_H)) return rc;
+  if (int rc = dalloc(m, &m->W1t_hi, (size_t)C_Z * C_H)) return rc;
+  if (int rc = dalloc(m, &m->W1t_lo, (size_t)C_Z * C_H)) return rc;
+  if (int rc = dalloc(m, &m->W2_hi, (size_t)C_Z * C_Z)) return rc;
+  if (int rc = dalloc(m, &m->W2_lo, (size_t)C_Z * C_Z)) return rc;
+  if (int rc = dalloc(m, &m->W2t_hi, (size_t)C_Z * C_Z)) return rc;
+  if (int rc = dalloc(m, &m->W2t_lo, (size_t)C_Z * C_Z)) return rc;
+  JRR_CUDA(cudaDeviceSynchronize());
+  return JRR_OK;
+}
+
+extern "C" int jrr_model_create(const JrrModelDesc* d, JrrModel** out) {
+  if (!d || !out) return fail(JRR_ERR_INVALID, "null argument");
+  if (!d->v_template_host || !d->shapedirs_host || !d->posedirs_host || !d->J_regressor_host ||
+      !d->parents_host || !d->lbs_weights_host || !d->J_regressor_extra_host || !d->joint_map_host ||
+      !d->vertex_picks_host)
+    return fail(JRR_ERR_INVALID, "JrrModelDesc has a null array");
+  JrrModel* m = new JrrModel();
+  int rc = model_create_impl(d, m);
+  if (rc != JRR_OK) {
+    std::string keep = g_err;
+    jrr_model_destroy(m);
+    g_err = keep;
+    return rc;
+  }
+  *out = m;
+  return JRR_OK;
+}
+
+extern "C" int jrr_set_regressor(JrrModel* m, const float* J17_raw, const float* mask, void* stream) {
+  if (!m || !J17_raw) return fail(JRR_ERR_INVALID, "null argument");
+  reset_launch_count();
+  return launch_regressor_normalise(m, J17_raw, mask, (cudaStream_t)stream);
+}
+
+extern "C" int jrr_critic_load(JrrModel* m, const float* p, void* stream) {
+  if (!m || !p) return fail(JRR_ERR_INVALID, "null argument");
+  reset_launch_count();
+  cudaStream_t st = (cudaStream_t)stream;
+  // state_dict order (see jrr.h)
+  const float* c1w = p;               // 192
+  const float* c1b = c1w + 192;       // 32
+  const float* c2w = c1b + 32;        // 1024
+  const float* c2b = c2w + 1024;      // 32
+  const float* heads = c2b + 32;      // 24 x (32 + 1)
+  const float* W1 = heads + 24 * 33;  // 1024*768
+  const float* b1 = W1 + (size_t)C_Z * C_H;
+  const float* W2 = b1 + C_Z;
+  const float* b2 = W2 + (size_t)C_Z * C_Z;
+  const float* w3 = b2 + C_Z;
+  const float* b3 = w3 + C_Z;
+  float* cs = m->critic_small;
+  JRR_CUDA(cudaMemcpyAsync(cs + 0, c1w, 192 * 4, cudaMemcpyDeviceToDevice, st));
+  JRR_CUDA(cudaMemcpyAsync(cs + 192, c1b, 32 * 4, cudaMemcpyDeviceToDevice, st));
+  JRR_CUDA(cudaMemcpyAsync(cs + 224, c2w, 1024 * 4, cudaMemcpyDeviceToDevice, st));
+  JRR_CUDA(cudaMemcpyAsync(cs + 1248, c2b, 32 * 4, cudaMemcpyDeviceToDevice, st));
+  // heads: weight[32], bias[1] interleaved per joint -> [24][32] and [24]
+  JRR_CUDA(cudaMemcpy2DAsync(cs + 1280, 32 * 4, heads, 33 * 4, 32 * 4, 24, cudaMemcpyDeviceToDevice, st));
+  JRR_CUDA(cudaMemcpy2DAsync(cs + 2048, 4, heads + 32, 33 * 4, 4, 24, cudaMemcpyDeviceToDevice, st));
+  JRR_CUDA(cudaMemcpyAsync(cs + 2072, b1, C_Z * 4, cudaMemcpyDeviceToDevice, st));
+  JRR_CUDA(cudaMemcpyAsync(cs + 3096, b2, C_Z * 4, cudaMemcpyDeviceToDevice, st));
+  JRR_CUDA(cudaMemcpyAsync(cs + 4120, w3, C_Z * 4, cudaMemcpyDeviceToDevice, st));
+  JRR_CUDA(cudaMemcpyAsync(cs + 5144, b3, 4, cudaMemcpyDeviceToDevice, st));
+  const int64_t n1 = (int64_t)C_Z * C_H, n2 = (int64_t)C_Z * C_Z;
+  split_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(W1, n1, m->W1_hi, m->W1_lo);
+  JRR_LAUNCH_CHECK();
+  split_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(W2, n2, m->W2_hi, m->W2_lo);
+  JRR_LAUNCH_CHECK();
+  split_transpose_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(W1, C_Z, C_H, m->W1t_hi, m->W1t_lo);
+  JRR_LAUNCH_CHECK();
+  split_transpose_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(W2, C_Z, C_Z, m->W2t_hi, m->W2t_lo);
+  JRR_LAUNCH_CHECK();
+  m->has_critic = true;
+  return JRR_OK;
+}

@@ -1,0 +1,449 @@
+// Warp-per-pose kernels: rotation decode (rot6d / Rodrigues / rotmat), rest joints
+// J = J0 + (J24.S) beta, the 24-joint kinematic chain walked level by level with warp
+// shuffles (lane = joint), and the analytic reverse walk fused with the per-pose Adam update.
+//
+// Replaces (file:line under /root/reference): scripts/utils.py:190-204 rot6d_to_rotmat,
+// smplx.lbs.{batch_rodrigues, vertices2joints, batch_rigid_transform} reached through
+// scripts/smpl.py:72-74, their autograd backward (scripts/optimize.py:264) and
+// torch.optim.Adam.step (scripts/optimize.py:201-202,265).
+#include "jrr_internal.cuh"
+
+namespace jrr {
+
+constexpr int POSES_PER_CTA = 8;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---- rotation decoders -------------------------------------------------------------------
+__device__ __forceinline__ void rot6d_decode(const float x[6], float R[9]) {
+  // utils.py:198-204: a1 = even entries, a2 = odd entries, columns b1,b2,b3
+  float a1x = x[0], a1y = x[2], a1z = x[4];
+  float a2x = x[1], a2y = x[3], a2z = x[5];
+  float n1 = fmaxf(sqrtf(a1x * a1x + a1y * a1y + a1z * a1z), 1e-12f);
+  float b1x = a1x / n1, b1y = a1y / n1, b1z = a1z / n1;
+  float s = b1x * a2x + b1y * a2y + b1z * a2z;
+  float ux = a2x - s * b1x, uy = a2y - s * b1y, uz = a2z - s * b1z;
+  float n2 = fmaxf(sqrtf(ux * ux + uy * uy + uz * uz), 1e-12f);
+  float b2x = ux / n2, b2y = uy / n2, b2z = uz / n2;
+  float b3x = b1y * b2z - b1z * b2y;
+  float b3y = b1z * b2x - b1x * b2z;
+  float b3z = b1x * b2y - b1y * b2x;
+  R[0] = b1x; R[1] = b2x; R[2] = b3x;
+  R[3] = b1y; R[4] = b2y; R[5] = b3y;
+  R[6] = b1z; R[7] = b2z; R[8] = b3z;
+}
+
+// backward of rot6d_decode: dR (row-major 3x3) -> dx[6]
+__device__ __forceinline__ void rot6d_backward(const float x[6], const float dR[9], float dx[6]) {
+  float a1[3] = {x[0], x[2], x[4]}, a2[3] = {x[1], x[3], x[5]};
+  float n1r = sqrtf(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]);
+  float n1 = fmaxf(n1r, 1e-12f);
+  float b1[3] = {a1[0] / n1, a1[1] / n1, a1[2] / n1};
+  float s = b1[0] * a2[0] + b1[1] * a2[1] + b1[2] * a2[2];
+  float u[3] = {a2[0] - s * b1[0], a2[1] - s * b1[1], a2[2] - s * b1[2]};
+  float n2r = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+  float n2 = fmaxf(n2r, 1e-12f);
+  float b2[3] = {u[0] / n2, u[1] / n2, u[2] / n2};
+  float db1[3] = {dR[0], dR[3], dR[6]};
+  float db2[3] = {dR[1], dR[4], dR[7]};
+  float db3[3] = {dR[2], dR[5], dR[8]};
+  // b3 = b1 x b2
+  db1[0] += b2[1] * db3[2] - b2[2] * db3[1];
+  db1[1] += b2[2] * db3[0] - b2[0] * db3[2];
+  db1[2] += b2[0] * db3[1] - b2[1] * db3[0];
+  db2[0] += db3[1] * b1[2] - db3[2] * b1[1];
+  db2[1] += db3[2] * b1[0] - db3[0] * b1[2];
+  db2[2] += db3[0] * b1[1] - db3[1] * b1[0];
+  // b2 = u / max(|u|, eps)
+  float du[3];
+  if (n2r > 1e-12f) {
+    float d = b2[0] * db2[0] + b2[1] * db2[1] + b2[2] * db2[2];
+    for (int i = 0; i < 3; i++) du[i] = (db2[i] - b2[i] * d) / n2;
+  } else {
+    for (int i = 0; i < 3; i++) du[i] = db2[i] / n2;
+  }
+  // u = a2 - s*b1, s = b1.a2
+  float ds = -(b1[0] * du[0] + b1[1] * du[1] + b1[2] * du[2]);
+  float da2[3];
+  for (int i = 0; i < 3; i++) {
+    da2[i] = du[i] + ds * b1[i];
+    db1[i] += -s * du[i] + ds * a2[i];
+  }
+  float da1[3];
+  if (n1r > 1e-12f) {
+    float d = b1[0] * db1[0] + b1[1] * db1[1] + b1[2] * db1[2];
+    for (int i = 0; i < 3; i++) da1[i] = (db1[i] - b1[i] * d) / n1;
+  } else {
+    for (int i = 0; i < 3; i++) da1[i] = db1[i] / n1;
+  }
+  dx[0] = da1[0]; dx[2] = da1[1]; dx[4] = da1[2];
+  dx[1] = da2[0]; dx[3] = da2[1]; dx[5] = da2[2];
+}
+
+__device__ __forceinline__ void rodrigues_decode(const float r[3], float R[9]) {
+  // smplx.lbs.batch_rodrigues: angle = |r + 1e-8|, n = r/angle
+  float ex = r[0] + 1e-8f, ey = r[1] + 1e-8f, ez = r[2] + 1e-8f;
+  float th = sqrtf(ex * ex + ey * ey + ez * ez);
+  float x = r[0] / th, y = r[1] / th, z = r[2] / th;
+  float s, c;
+  sincosf(th, &s, &c);
+  float oc = 1.f - c;
+  // K = [[0,-z,y],[z,0,-x],[-y,x,0]];  K^2 = n n^T - |n|^2 I
+  float nn = x * x + y * y + z * z;
+  R[0] = 1.f + oc * (x * x - nn); R[1] = -s * z + oc * x * y;     R[2] = s * y + oc * x * z;
+  R[3] = s * z + oc * x * y;      R[4] = 1.f + oc * (y * y - nn); R[5] = -s * x + oc * y * z;
+  R[6] = -s * y + oc * x * z;     R[7] = s * x + oc * y * z;      R[8] = 1.f + oc * (z * z - nn);
+}
+
+__device__ __forceinline__ void rodrigues_backward(const float r[3], const float dR[9], float dr[3]) {
+  float e[3] = {r[0] + 1e-8f, r[1] + 1e-8f, r[2] + 1e-8f};
+  float th = sqrtf(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+  float n[3] = {r[0] / th, r[1] / th, r[2] / th};
+  float s, c;
+  sincosf(th, &s, &c);
+  float oc = 1.f - c;
+  float K[9] = {0.f, -n[2], n[1], n[2], 0.f, -n[0], -n[1], n[0], 0.f};
+  float K2[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      K2[i * 3 + j] = K[i * 3 + 0] * K[0 * 3 + j] + K[i * 3 + 1] * K[1 * 3 + j] + K[i * 3 + 2] * K[2 * 3 + j];
+  // R = I + s K + oc K^2
+  float dth = 0.f;
+  for (int i = 0; i < 9; i++) dth += dR[i] * (c * K[i] + s * K2[i]);
+  // dK = s dR + oc (dR K^T + K^T dR)
+  float dK[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      float a = 0.f, b = 0.f;
+      for (int k = 0; k < 3; k++) {
+        a += dR[i * 3 + k] * K[j * 3 + k];   // dR K^T
+        b += K[k * 3 + i] * dR[k * 3 + j];   // K^T dR
+      }
+      dK[i * 3 + j] = s * dR[i * 3 + j] + oc * (a + b);
+    }
+  float dn[3] = {dK[7] - dK[5], dK[2] - dK[6], dK[3] - dK[1]};
+  // n = r/th, th = |r + eps|
+  float ndn = n[0] * dn[0] + n[1] * dn[1] + n[2] * dn[2];
+  float dth_tot = dth - ndn / th;
+  for (int i = 0; i < 3; i++) dr[i] = dn[i] / th + dth_tot * e[i] / th;
+}
+
+template <int KIND>
+__device__ __forceinline__ void decode_rot(const float* __restrict__ pose, int64_t b, int j, bool valid,
+                                           float raw[9], float R[9]) {
+  if (!valid) {
+    for (int i = 0; i < 9; i++) { raw[i] = 0.f; R[i] = (i % 4 == 0) ? 1.f : 0.f; }
+    if (KIND == JRR_POSE_ROT6D) { raw[0] = 1.f; raw[3] = 1.f; }
+    if (KIND == JRR_POSE_ROTMAT) for (int i = 0; i < 9; i++) raw[i] = R[i];
+    return;
+  }
+  if (KIND == JRR_POSE_ROT6D) {
+    const float* p = pose + (b * NJ + j) * 6;
+    for (int i = 0; i < 6; i++) raw[i] = p[i];
+    rot6d_decode(raw, R);
+  } else if (KIND == JRR_POSE_AXIS_ANGLE) {
+    const float* p = pose + (b * NJ + j) * 3;
+    for (int i = 0; i < 3; i++) raw[i] = p[i];
+    rodrigues_decode(raw, R);
+  } else {
+    const float* p = pose + (b * NJ + j) * 9;
+    for (int i = 0; i < 9; i++) { raw[i] = p[i]; R[i] = raw[i]; }
+  }
+}
+
+// Forward chain for lane j: fills GR (world rotation), Gt (world translation = posed joint),
+// Jr (rest joint), and GRp (parent's world rotation; identity for the root).
+__device__ __forceinline__ void chain_forward(const ChainTab& tab, int j, const float R[9],
+                                              const float Jr[3], float GR[9], float Gt[3],
+                                              float GRp[9], float rel[3]) {
+  const int par = tab.parent[j];
+  const int src = par < 0 ? 0 : par;
+  const int dep = tab.depth[j];
+  float Jp[3];
+  for (int i = 0; i < 3; i++) Jp[i] = __shfl_sync(FULL, Jr[i], src);
+  for (int i = 0; i < 3; i++) rel[i] = par < 0 ? Jr[i] : Jr[i] - Jp[i];
+  for (int i = 0; i < 9; i++) { GR[i] = R[i]; GRp[i] = (i % 4 == 0) ? 1.f : 0.f; }
+  for (int i = 0; i < 3; i++) Gt[i] = rel[i];
+  for (int d = 1; d <= tab.max_depth; d++) {
+    float PR[9], Pt[3];
+    for (int i = 0; i < 9; i++) PR[i] = __shfl_sync(FULL, GR[i], src);
+    for (int i = 0; i < 3; i++) Pt[i] = __shfl_sync(FULL, Gt[i], src);
+    if (dep == d) {
+      for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++)
+          GR[r * 3 + c] = PR[r * 3 + 0] * R[0 * 3 + c] + PR[r * 3 + 1] * R[1 * 3 + c] + PR[r * 3 + 2] * R[2 * 3 + c];
+        Gt[r] = PR[r * 3 + 0] * rel[0] + PR[r * 3 + 1] * rel[1] + PR[r * 3 + 2] * rel[2] + Pt[r];
+      }
+      for (int i = 0; i < 9; i++) GRp[i] = PR[i];
+    }
+  }
+}
+
+__device__ __forceinline__ void rest_joint(const float* __restrict__ J0, const float* __restrict__ JS,
+                                           const float beta[NB], int j, float Jr[3]) {
+  for (int c = 0; c < 3; c++) {
+    float a = J0[j * 3 + c];
+    const float* s = JS + (j * 3 + c) * NB;
+    for (int l = 0; l < NB; l++) a = fmaf(s[l], beta[l], a);
+    Jr[c] = a;
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(POSES_PER_CTA * 32)
+pose_fwd_kernel(const __grid_constant__ ChainTab tab, const float* __restrict__ J0,
+                const float* __restrict__ JS, const float* __restrict__ betas,
+                const float* __restrict__ pose, int64_t B, int64_t BP, float* __restrict__ AT,
+                float* __restrict__ feat_hi, float* __restrict__ feat_lo, float* __restrict__ Jp_out) {
+  __shared__ float sA[NJ * 12][POSES_PER_CTA];
+  __shared__ float sF[POSES_PER_CTA][KA];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * POSES_PER_CTA + warp;
+  const bool valid = b < B;
+  const int j = lane < NJ ? lane : NJ - 1;
+
+  float beta[NB];
+  for (int l = 0; l < NB; l++) beta[l] = valid ? betas[b * NB + l] : 0.f;
+  float raw[9], R[9], Jr[3], GR[9], Gt[3], GRp[9], rel[3];
+  decode_rot<KIND>(pose, b, j, valid, raw, R);
+  rest_joint(J0, JS, beta, j, Jr);
+  chain_forward(tab, j, R, Jr, GR, Gt, GRp, rel);
+
+  for (int i = lane; i < KA; i += 32) sF[warp][i] = 0.f;
+  __syncwarp();
+  if (lane < NJ) {
+    for (int r = 0; r < 3; r++) {
+      float t = Gt[r] - (GR[r * 3 + 0] * Jr[0] + GR[r * 3 + 1] * Jr[1] + GR[r * 3 + 2] * Jr[2]);
+      sA[lane * 12 + r * 4 + 0][warp] = GR[r * 3 + 0];
+      sA[lane * 12 + r * 4 + 1][warp] = GR[r * 3 + 1];
+      sA[lane * 12 + r * 4 + 2][warp] = GR[r * 3 + 2];
+      sA[lane * 12 + r * 4 + 3][warp] = t;
+    }
+    if (lane >= 1)
+      for (int i = 0; i < 9; i++) sF[warp][(lane - 1) * 9 + i] = R[i] - ((i % 4 == 0) ? 1.f : 0.f);
+    if (Jp_out != nullptr && valid)
+      for (int r = 0; r < 3; r++) Jp_out[b * 72 + lane * 3 + r] = Gt[r];
+  }
+  if (lane < NB) sF[warp][FEAT_BETA + lane] = beta[lane];
+  if (lane == 0) sF[warp][FEAT_ONE] = 1.f;
+  __syncthreads();
+  // feature rows (hi/lo split for the 3xTF32 blend GEMM), coalesced
+  if (b < BP) {
+    for (int i = lane; i < KA; i += 32) {
+      float f = sF[warp][i];
+      float hi = tf32_hi(f);
+      feat_hi[b * KA + i] = hi;
+      feat_lo[b * KA + i] = tf32_hi(f - hi);
+    }
+  }
+  // transforms, pose contiguous: each thread stores one full 32-byte sector
+  const int64_t b0 = (int64_t)blockIdx.x * POSES_PER_CTA;
+  for (int e = threadIdx.x; e < NJ * 12; e += blockDim.x) {
+    float4 v0 = make_float4(sA[e][0], sA[e][1], sA[e][2], sA[e][3]);
+    float4 v1 = make_float4(sA[e][4], sA[e][5], sA[e][6], sA[e][7]);
+    float4* dst = reinterpret_cast<float4*>(AT + (int64_t)e * BP + b0);
+    dst[0] = v0;
+    dst[1] = v1;
+  }
+}
+
+// ---- backward + Adam ----------------------------------------------------------------------
+// One warp per pose, lane = joint.  Inputs (all produced earlier in the same step):
+//   dAT   [288][BP]           d loss / d relative transform (from the skinning backward)
+//   dfeat [KSPLIT][BP][224]   split-K partials of d loss / d blend features
+//   dJp   [BP][72]            d loss / d posed joints (module path only)
+//   dx6c  [BP][144]           critic gradient w.r.t. rot6d (refine path only)
+template <int KIND, bool ADAM>
+__global__ void __launch_bounds__(POSES_PER_CTA * 32)
+pose_bwd_kernel(const __grid_constant__ ChainTab tab, const float* __restrict__ J0,
+                const float* __restrict__ JS, const float* betas /* may alias betas_rw */,
+                const float* pose /* may alias x6_rw */, int64_t B, int64_t BP, const float* __restrict__ dAT,
+                const float* __restrict__ dfeat, int ksplit, const float* __restrict__ dJp,
+                const float* __restrict__ dx6c, float* __restrict__ dbetas_out,
+                float* __restrict__ dpose_out, float* x6_rw, float* betas_rw,
+                float* __restrict__ adam_m, float* __restrict__ adam_v,
+                const int32_t* __restrict__ step_count, float lr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * POSES_PER_CTA + warp;
+  if (b >= B) return;  // whole warp exits together
+  const int j = lane < NJ ? lane : NJ - 1;
+  const bool act = lane < NJ;
+
+  float beta[NB];
+  for (int l = 0; l < NB; l++) beta[l] = betas[b * NB + l];
+  float raw[9], R[9], Jr[3], GR[9], Gt[3], GRp[9], rel[3];
+  decode_rot<KIND>(pose, b, j, true, raw, R);
+  rest_joint(J0, JS, beta, j, Jr);
+  chain_forward(tab, j, R, Jr, GR, Gt, GRp, rel);
+
+  // upstream grads of the relative transform A_j = [GR_j | Gt_j - GR_j Jr_j]
+  float dGR[9], dGt[3], dJr[3];
+  {
+    float dA[12];
+    for (int e = 0; e < 12; e++) dA[e] = act ? dAT[(int64_t)(j * 12 + e) * BP + b] : 0.f;
+    for (int r = 0; r < 3; r++) {
+      float dt = dA[r * 4 + 3];
+      dGt[r] = dt + ((dJp != nullptr && act) ? dJp[b * 72 + j * 3 + r] : 0.f);
+      for (int c = 0; c < 3; c++) dGR[r * 3 + c] = dA[r * 4 + c] - dt * Jr[c];
+    }
+    // At = Gt - GR Jr  ->  dJr += -GR^T dAt
+    for (int c = 0; c < 3; c++)
+      dJr[c] = -(GR[0 * 3 + c] * dA[3] + GR[1 * 3 + c] * dA[7] + GR[2 * 3 + c] * dA[11]);
+  }
+  // reverse walk, deepest level first.  A joint at depth d sends its parent
+  //   mR = dGR R^T + dGt rel^T (9), mt = dGt (3), mJ = -GRp^T dGt (3)
+  const int dep = tab.depth[j];
+  for (int d = tab.max_depth; d >= 1; d--) {
+    float msg[15];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++)
+        msg[r * 3 + c] = dGR[r * 3 + 0] * R[c * 3 + 0] + dGR[r * 3 + 1] * R[c * 3 + 1] +
+                         dGR[r * 3 + 2] * R[c * 3 + 2] + dGt[r] * rel[c];
+    float gpt[3];
+    for (int c = 0; c < 3; c++)
+      gpt[c] = GRp[0 * 3 + c] * dGt[0] + GRp[1 * 3 + c] * dGt[1] + GRp[2 * 3 + c] * dGt[2];
+    for (int r = 0; r < 3; r++) { msg[9 + r] = dGt[r]; msg[12 + r] = -gpt[r]; }
+    if (act && dep == d)
+      for (int c = 0; c < 3; c++) dJr[c] += gpt[c];   // rel_j = Jr_j - Jr_parent
+    for (int ci = 0; ci < MAXCH; ci++) {
+      int ch = tab.child[j][ci];
+      int src = ch < 0 ? 0 : ch;
+      bool take = act && ch >= 0 && tab.depth[src] == d;
+      for (int i = 0; i < 15; i++) {
+        float v = __shfl_sync(FULL, msg[i], src);
+        if (take) {
+          if (i < 9) dGR[i] += v;
+          else if (i < 12) dGt[i - 9] += v;
+          else dJr[i - 12] += v;
+        }
+      }
+    }
+  }
+  // root: Gt_0 = Jr_0
+  if (lane == 0)
+    for (int c = 0; c < 3; c++) dJr[c] += dGt[c];
+  // local rotation gradient dR_j = GRp^T dGR_j (+ blend-feature gradient for j >= 1)
+  float dR[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++)
+      dR[r * 3 + c] = GRp[0 * 3 + r] * dGR[0 * 3 + c] + GRp[1 * 3 + r] * dGR[1 * 3 + c] + GRp[2 * 3 + r] * dGR[2 * 3 + c];
+  if (act && lane >= 1)
+    for (int s = 0; s < ksplit; s++) {
+      const float* df = dfeat + ((int64_t)s * BP + b) * KA + (lane - 1) * 9;
+      for (int i = 0; i < 9; i++) dR[i] += df[i];
+    }
+  // d beta_l = sum_j JS_j[:,l] . dJr_j  + dfeat[207+l]
+  float dbeta = 0.f;
+  for (int l = 0; l < NB; l++) {
+    float p = 0.f;
+    if (act)
+      for (int c = 0; c < 3; c++) p += JS[(j * 3 + c) * NB + l] * dJr[c];
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
+    if (lane == l) dbeta = p;
+  }
+  if (lane < NB)
+    for (int s = 0; s < ksplit; s++) dbeta += dfeat[((int64_t)s * BP + b) * KA + FEAT_BETA + lane];
+
+  // rotation parameter gradient
+  float dp[9];
+  int np;
+  if (KIND == JRR_POSE_ROT6D) { rot6d_backward(raw, dR, dp); np = 6; }
+  else if (KIND == JRR_POSE_AXIS_ANGLE) { rodrigues_backward(raw, dR, dp); np = 3; }
+  else { for (int i = 0; i < 9; i++) dp[i] = dR[i]; np = 9; }
+
+  if (!ADAM) {
+    if (act)
+      for (int i = 0; i < np; i++) dpose_out[(b * NJ + j) * np + i] = dp[i];
+    if (lane < NB) dbetas_out[b * NB + lane] = dbeta;
+  } else {
+    // torch.optim.Adam (no weight decay / amsgrad), optimize.py:201-202,265
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    const int t = *step_count + 1;
+    // bias corrections in double, like the Python scalars of torch.optim.Adam
+    const float bc2s = (float)sqrt(1.0 - pow(0.999, (double)t));
+    const float step = (float)((double)lr / (1.0 - pow(0.9, (double)t)));
+    if (act) {
+      for (int i = 0; i < 6; i++) {
+        float g = dp[i] + (dx6c != nullptr ? dx6c[b * 144 + j * 6 + i] : 0.f);
+        int64_t pi = b * NPARAM + j * 6 + i;
+        float m = b1 * adam_m[pi] + (1.f - b1) * g;
+        float v = b2 * adam_v[pi] + (1.f - b2) * g * g;
+        adam_m[pi] = m;
+        adam_v[pi] = v;
+        float denom = sqrtf(v) / bc2s + eps;
+        x6_rw[(b * NJ + j) * 6 + i] = raw[i] - step * (m / denom);
+      }
+    }
+    if (lane < NB) {
+      int64_t pi = b * NPARAM + 144 + lane;
+      float g = dbeta;
+      float m = b1 * adam_m[pi] + (1.f - b1) * g;
+      float v = b2 * adam_v[pi] + (1.f - b2) * g * g;
+      adam_m[pi] = m;
+      adam_v[pi] = v;
+      float denom = sqrtf(v) / bc2s + eps;
+      betas_rw[b * NB + lane] = beta[lane] - step * (m / denom);
+    }
+  }
+}
+
+__global__ void bump_step_kernel(int32_t* step_count) { *step_count += 1; }
+
+// ---- host wrappers ---------------------------------------------------------------------------
+int launch_pose_fwd(const JrrModel* m, int64_t B, int64_t BP, const float* betas, const float* pose,
+                    int kind, float* AT, float* feat_hi, float* feat_lo, float* Jp, cudaStream_t st) {
+  dim3 grid((unsigned)(BP / POSES_PER_CTA)), block(POSES_PER_CTA * 32);
+  switch (kind) {
+    case JRR_POSE_ROTMAT:
+      pose_fwd_kernel<JRR_POSE_ROTMAT><<<grid, block, 0, st>>>(m->chain, m->J0, m->JS, betas, pose, B, BP, AT, feat_hi, feat_lo, Jp);
+      break;
+    case JRR_POSE_AXIS_ANGLE:
+      pose_fwd_kernel<JRR_POSE_AXIS_ANGLE><<<grid, block, 0, st>>>(m->chain, m->J0, m->JS, betas, pose, B, BP, AT, feat_hi, feat_lo, Jp);
+      break;
+    case JRR_POSE_ROT6D:
+      pose_fwd_kernel<JRR_POSE_ROT6D><<<grid, block, 0, st>>>(m->chain, m->J0, m->JS, betas, pose, B, BP, AT, feat_hi, feat_lo, Jp);
+      break;
+    default:
+      return fail(JRR_ERR_INVALID, "unknown pose kind");
+  }
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_pose_bwd(const JrrModel* m, const Workspace& w, const float* betas, const float* pose,
+                    int kind, bool use_dJp, bool use_critic, float* dbetas_out, float* dpose_out,
+                    float* x6, float* betas_rw, float* adam_m, float* adam_v, int32_t* step_count,
+                    float lr, cudaStream_t st) {
+  dim3 grid((unsigned)((w.B + POSES_PER_CTA - 1) / POSES_PER_CTA)), block(POSES_PER_CTA * 32);
+  const float* dJp = use_dJp ? w.dJp : nullptr;
+  const float* dx6c = use_critic ? w.dx6c : nullptr;
+  const bool adam = x6 != nullptr;
+#define JRR_PB(KIND, AD)                                                                          \
+  pose_bwd_kernel<KIND, AD><<<grid, block, 0, st>>>(m->chain, m->J0, m->JS, betas, pose, w.B, w.BP, \
+      w.dAT, w.dfeat, KSPLIT, dJp, dx6c, dbetas_out, dpose_out, x6, betas_rw, adam_m, adam_v,      \
+      step_count, lr)
+  if (adam) {
+    if (kind != JRR_POSE_ROT6D) return fail(JRR_ERR_INVALID, "Adam step needs rot6d parameters");
+    JRR_PB(JRR_POSE_ROT6D, true);
+    JRR_LAUNCH_CHECK();
+    bump_step_kernel<<<1, 1, 0, st>>>(step_count);
+    JRR_LAUNCH_CHECK();
+  } else {
+    switch (kind) {
+      case JRR_POSE_ROTMAT: JRR_PB(JRR_POSE_ROTMAT, false); break;
+      case JRR_POSE_AXIS_ANGLE: JRR_PB(JRR_POSE_AXIS_ANGLE, false); break;
+      case JRR_POSE_ROT6D: JRR_PB(JRR_POSE_ROT6D, false); break;
+      default: return fail(JRR_ERR_INVALID, "unknown pose kind");
+    }
+    JRR_LAUNCH_CHECK();
+  }
+#undef JRR_PB
+  return JRR_OK;
+}
+
+}  // namespace jrr

@@ -1,0 +1,517 @@
+// Linear blend skinning over the sparse skinning weights, fused with the 17x6890
+// J-regressor reduction (forward) and with the regressor-transpose seed, the dA reduction
+// and the pose-blend gradient (backward).  One thread owns one pose and walks a range of
+// packed vertices; every per-vertex constant (joint ids, weights, regressor column) is a
+// warp-uniform broadcast load, the four joint transforms a vertex needs are cached in
+// registers and only re-fetched when the joint id of a slot changes ("runs"), and all
+// per-pose arrays are laid out pose-contiguous so every global access is a coalesced 128 B
+// line.  Reductions over vertices stay inside a thread (fixed order, no float atomics).
+//
+// Replaces (file:line under /root/reference): the W.A / T.v part of smplx.lbs.lbs reached
+// through scripts/smpl.py:72-74, vertex_joint_selector + J_regressor_extra + joint_map
+// (scripts/smpl.py:75-78), the regressor contraction of utils.find_joints
+// (scripts/utils.py:96-98), move_pelvis + MSELoss (scripts/utils.py:106-114,
+// scripts/optimize.py:238-239) and their autograd backward (scripts/optimize.py:264).
+#include "jrr_internal.cuh"
+
+namespace jrr {
+
+constexpr int SK_THREADS = 128;
+constexpr int VT = 32;               // vertices per transposition tile
+constexpr int TILE_LD = 3 * VT + 1;  // 97: conflict-free column access
+
+__device__ __forceinline__ float tf32_hi_k(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void load_rec(const VtxRec* __restrict__ vrec, int i, uint32_t& meta,
+                                         float w[4], int& xptr, int& xcnt) {
+  const uint4* p = reinterpret_cast<const uint4*>(vrec + i);
+  uint4 a = __ldg(p), c = __ldg(p + 1);
+  meta = a.x;
+  w[0] = __uint_as_float(a.y); w[1] = __uint_as_float(a.z); w[2] = __uint_as_float(a.w);
+  w[3] = __uint_as_float(c.x);
+  xptr = (int)c.y; xcnt = (int)c.z;
+}
+
+// ---------------------------------------------------------------------------- forward
+template <bool WRITE_V, bool WRITE_VT, bool PART>
+__global__ void __launch_bounds__(SK_THREADS)
+skin_fwd_kernel(const VtxRec* __restrict__ vrec, const float* __restrict__ Jhat_cols,
+                const float* __restrict__ AT, const float* __restrict__ vpT, int64_t B, int64_t BP,
+                float* __restrict__ vertices_out, float* __restrict__ vT_out, float* __restrict__ part) {
+  extern __shared__ float tile[];  // [128][97] when WRITE_V
+  const int tid = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * SK_THREADS;
+  const int64_t b = b0 + tid;
+  const int s = blockIdx.y;
+  const int i0 = s * VS;
+  float A[4][12];
+  float acc[NACC];
+#pragma unroll
+  for (int a = 0; a < NACC; a++) acc[a] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int e = 0; e < 12; e++) A[k][e] = 0.f;
+
+  for (int t0 = 0; t0 < VS; t0 += VT) {
+#pragma unroll 1
+    for (int ii = 0; ii < VT; ii++) {
+      const int i = i0 + t0 + ii;
+      uint32_t meta; float w[4]; int xptr, xcnt;
+      load_rec(vrec, i, meta, w, xptr, xcnt);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if ((meta >> (20 + k)) & 1u) {
+          const int j = (meta >> (5 * k)) & 31u;
+          const float* src = AT + (int64_t)(j * 12) * BP + b;
+#pragma unroll
+          for (int e = 0; e < 12; e++) A[k][e] = src[(int64_t)e * BP];
+        }
+      }
+      const float x = vpT[(int64_t)(3 * i + 0) * BP + b];
+      const float y = vpT[(int64_t)(3 * i + 1) * BP + b];
+      const float z = vpT[(int64_t)(3 * i + 2) * BP + b];
+      float T[12];
+#pragma unroll
+      for (int e = 0; e < 12; e++)
+        T[e] = w[0] * A[0][e] + w[1] * A[1][e] + w[2] * A[2][e] + w[3] * A[3][e];
+      float v[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) v[r] = T[r * 4 + 0] * x + T[r * 4 + 1] * y + T[r * 4 + 2] * z + T[r * 4 + 3];
+      if (WRITE_VT) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) vT_out[(int64_t)(3 * i + r) * BP + b] = v[r];
+      }
+      if (WRITE_V) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) tile[tid * TILE_LD + ii * 3 + r] = v[r];
+      }
+      if (PART && ((meta >> 24) & 1u)) {
+        const float4* jc = reinterpret_cast<const float4*>(Jhat_cols + (int64_t)i * JH_STRIDE);
+        float jh[JH_STRIDE];
+#pragma unroll
+        for (int q = 0; q < JH_STRIDE / 4; q++) {
+          float4 t = __ldg(jc + q);
+          jh[q * 4 + 0] = t.x; jh[q * 4 + 1] = t.y; jh[q * 4 + 2] = t.z; jh[q * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int j = 0; j < NH; j++) {
+          acc[j * 3 + 0] = fmaf(jh[j], v[0], acc[j * 3 + 0]);
+          acc[j * 3 + 1] = fmaf(jh[j], v[1], acc[j * 3 + 1]);
+          acc[j * 3 + 2] = fmaf(jh[j], v[2], acc[j * 3 + 2]);
+        }
+      }
+    }
+    if (WRITE_V) {
+      __syncthreads();
+      const int warp = tid >> 5, lane = tid & 31;
+      const int it0 = i0 + t0;
+      for (int r = warp; r < SK_THREADS; r += SK_THREADS / 32) {
+        const int64_t bb = b0 + r;
+        if (bb >= B) break;
+        float* dst = vertices_out + bb * (int64_t)(V * 3) + (int64_t)it0 * 3;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          const int f = lane + 32 * q;
+          if (it0 * 3 + f < V * 3) dst[f] = tile[r * TILE_LD + f];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (PART) {
+#pragma unroll
+    for (int a = 0; a < NACC; a++) part[((int64_t)s * NACC + a) * BP + b] = acc[a];
+  }
+}
+
+// ------------------------------------------------------------------ loss seed (joint term)
+// pred = sum of range partials (fixed order); pc = pred - pred[0]; diff = pc - gt/1000;
+// g = w_joint * 2 diff / (51 B_logical); pelvis adjustment; per-CTA loss partial.
+__global__ void __launch_bounds__(SK_THREADS)
+loss_seed_kernel(const float* __restrict__ part, const float* __restrict__ gt_mm, int64_t B,
+                 int64_t BP, float scale, float* __restrict__ gT, float* __restrict__ joints17_out,
+                 float* __restrict__ loss_part) {
+  __shared__ float red[SK_THREADS / 32];
+  const int64_t b = (int64_t)blockIdx.x * SK_THREADS + threadIdx.x;
+  float pred[NACC];
+#pragma unroll
+  for (int a = 0; a < NACC; a++) {
+    float p = 0.f;
+    for (int s = 0; s < NSPLIT; s++) p += part[((int64_t)s * NACC + a) * BP + b];
+    pred[a] = p;
+  }
+  float loss = 0.f;
+  if (b < B) {
+    if (joints17_out != nullptr)
+#pragma unroll
+      for (int a = 0; a < NACC; a++) joints17_out[b * NACC + a] = pred[a];
+  }
+  if (gT != nullptr) {
+    float g[NACC];
+    float sum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < NACC; a++) {
+      float d = 0.f;
+      if (b < B) d = (pred[a] - pred[a % 3]) - gt_mm[b * NACC + a] / 1000.f;
+      loss += d * d;
+      g[a] = scale * d;
+      sum[a % 3] += g[a];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) g[c] -= sum[c];
+#pragma unroll
+    for (int a = 0; a < NACC; a++) gT[(int64_t)a * BP + b] = g[a];
+    // deterministic block reduction
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < SK_THREADS / 32; i++) t += red[i];
+      loss_part[blockIdx.x] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- backward
+// dv_i = Jhat^T g (USE_G) + dvertices (USE_DV, natural layout staged through smem) +
+//        picks / extra-regressor rows of the joints49 gradient (USE_X)
+// dvp_i = (sum_k w_k AR_k)^T dv_i                        -> dvp_hi/lo [BP][NP] (A operand of the
+//                                                           backward blend GEMM, tf32 split)
+// dA_k += w_k dv_i (x) [vp_i ; 1]                        -> flushed per run to dAflush
+template <bool USE_G, bool USE_DV, bool USE_X>
+__global__ void __launch_bounds__(SK_THREADS)
+skin_bwd_kernel(const VtxRec* __restrict__ vrec, const float* __restrict__ Jhat_cols,
+                const int* __restrict__ range_flush_base, const int* __restrict__ vx_src,
+                const float* __restrict__ vx_coef, const float* __restrict__ AT,
+                const float* __restrict__ vpT, const float* __restrict__ gT,
+                const float* __restrict__ dvertices, const float* __restrict__ d30T, int64_t B,
+                int64_t BP, float* __restrict__ dvp_hi, float* __restrict__ dvp_lo,
+                float* __restrict__ dAflush) {
+  extern __shared__ float smem[];
+  float* tile_out = smem;                               // [128][97]
+  float* tile_in = smem + SK_THREADS * TILE_LD;         // [128][97] (USE_DV)
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int64_t b0 = (int64_t)blockIdx.x * SK_THREADS;
+  const int64_t b = b0 + tid;
+  const int s = blockIdx.y;
+  const int i0 = s * VS;
+  int fl = range_flush_base[s];
+
+  float g[USE_G ? NACC : 1];
+  if (USE_G) {
+#pragma unroll
+    for (int a = 0; a < NACC; a++) g[a] = gT[(int64_t)a * BP + b];
+  }
+  float AR[4][9], dA[4][12];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+#pragma unroll
+    for (int e = 0; e < 9; e++) AR[k][e] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 12; e++) dA[k][e] = 0.f;
+  }
+
+  for (int t0 = 0; t0 < VS; t0 += VT) {
+    const int it0 = i0 + t0;
+    if (USE_DV) {
+      for (int r = warp; r < SK_THREADS; r += SK_THREADS / 32) {
+        const int64_t bb = b0 + r;
+        const float* src = dvertices + bb * (int64_t)(V * 3) + (int64_t)it0 * 3;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          const int f = lane + 32 * q;
+          tile_in[r * TILE_LD + f] = (bb < B && it0 * 3 + f < V * 3) ? src[f] : 0.f;
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll 1
+    for (int ii = 0; ii < VT; ii++) {
+      const int i = it0 + ii;
+      uint32_t meta; float w[4]; int xptr, xcnt;
+      load_rec(vrec, i, meta, w, xptr, xcnt);
+      const bool first = (meta >> 25) & 1u;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if ((meta >> (20 + k)) & 1u) {
+          if (!first) {
+            float* dst = dAflush + (int64_t)fl * 12 * BP + b;
+#pragma unroll
+            for (int e = 0; e < 12; e++) { dst[(int64_t)e * BP] = dA[k][e]; dA[k][e] = 0.f; }
+            fl++;
+          }
+          const int j = (meta >> (5 * k)) & 31u;
+          const float* src = AT + (int64_t)(j * 12) * BP + b;
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) AR[k][r * 3 + c] = src[(int64_t)(r * 4 + c) * BP];
+        }
+      }
+      float vp[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) vp[c] = vpT[(int64_t)(3 * i + c) * BP + b];
+      float dv[3] = {0.f, 0.f, 0.f};
+      if (USE_G && ((meta >> 24) & 1u)) {
+        const float4* jc = reinterpret_cast<const float4*>(Jhat_cols + (int64_t)i * JH_STRIDE);
+        float jh[JH_STRIDE];
+#pragma unroll
+        for (int q = 0; q < JH_STRIDE / 4; q++) {
+          float4 t = __ldg(jc + q);
+          jh[q * 4 + 0] = t.x; jh[q * 4 + 1] = t.y; jh[q * 4 + 2] = t.z; jh[q * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int j = 0; j < NH; j++) {
+          dv[0] = fmaf(jh[j], g[USE_G ? j * 3 + 0 : 0], dv[0]);
+          dv[1] = fmaf(jh[j], g[USE_G ? j * 3 + 1 : 0], dv[1]);
+          dv[2] = fmaf(jh[j], g[USE_G ? j * 3 + 2 : 0], dv[2]);
+        }
+      }
+      if (USE_DV) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) dv[c] += tile_in[tid * TILE_LD + ii * 3 + c];
+      }
+      if (USE_X) {
+        for (int q = 0; q < xcnt; q++) {
+          const int src = __ldg(vx_src + xptr + q);
+          const float cf = __ldg(vx_coef + xptr + q);
+#pragma unroll
+          for (int c = 0; c < 3; c++) dv[c] = fmaf(cf, d30T[(int64_t)(src * 3 + c) * BP + b], dv[c]);
+        }
+      }
+      float TR[9];
+#pragma unroll
+      for (int e = 0; e < 9; e++) TR[e] = w[0] * AR[0][e] + w[1] * AR[1][e] + w[2] * AR[2][e] + w[3] * AR[3][e];
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+        tile_out[tid * TILE_LD + ii * 3 + c] = TR[0 * 3 + c] * dv[0] + TR[1 * 3 + c] * dv[1] + TR[2 * 3 + c] * dv[2];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          const float wd = w[k] * dv[r];
+          dA[k][r * 4 + 0] = fmaf(wd, vp[0], dA[k][r * 4 + 0]);
+          dA[k][r * 4 + 1] = fmaf(wd, vp[1], dA[k][r * 4 + 1]);
+          dA[k][r * 4 + 2] = fmaf(wd, vp[2], dA[k][r * 4 + 2]);
+          dA[k][r * 4 + 3] += wd;
+        }
+      }
+    }
+    __syncthreads();
+    for (int r = warp; r < SK_THREADS; r += SK_THREADS / 32) {
+      const int64_t bb = b0 + r;
+      float* dh = dvp_hi + bb * (int64_t)NP + (int64_t)it0 * 3;
+      float* dl = dvp_lo + bb * (int64_t)NP + (int64_t)it0 * 3;
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const int f = lane + 32 * q;
+        const float v = tile_out[r * TILE_LD + f];
+        const float hi = tf32_hi_k(v);
+        dh[f] = hi;
+        dl[f] = tf32_hi_k(v - hi);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float* dst = dAflush + (int64_t)fl * 12 * BP + b;
+#pragma unroll
+    for (int e = 0; e < 12; e++) dst[(int64_t)e * BP] = dA[k][e];
+    fl++;
+  }
+}
+
+// dAT[k][e][b] = sum over the flush events of joint k (fixed order)
+__global__ void __launch_bounds__(SK_THREADS)
+dA_reduce_kernel(const int* __restrict__ flush_ptr, const int* __restrict__ flush_idx,
+                 const float* __restrict__ dAflush, int64_t BP, float* __restrict__ dAT) {
+  const int64_t b = (int64_t)blockIdx.x * SK_THREADS + threadIdx.x;
+  const int k = blockIdx.y;
+  float acc[12];
+#pragma unroll
+  for (int e = 0; e < 12; e++) acc[e] = 0.f;
+  const int p0 = flush_ptr[k], p1 = flush_ptr[k + 1];
+  for (int p = p0; p < p1; p++) {
+    const float* src = dAflush + (int64_t)__ldg(flush_idx + p) * 12 * BP + b;
+#pragma unroll
+    for (int e = 0; e < 12; e++) acc[e] += src[(int64_t)e * BP];
+  }
+#pragma unroll
+  for (int e = 0; e < 12; e++) dAT[(int64_t)(k * 12 + e) * BP + b] = acc[e];
+}
+
+// ----------------------------------------------------------------------- joints49 (module)
+// smplx vertex_joint_selector + scripts/smpl.py:75-78
+__global__ void joints49_fwd_kernel(const int* __restrict__ joint_map, const int* __restrict__ picks,
+                                    Csr extra, const float* __restrict__ Jp,
+                                    const float* __restrict__ vertices, int64_t B,
+                                    float* __restrict__ joints49) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * JRR_NUM_OUT_JOINTS) return;
+  const int64_t b = idx / JRR_NUM_OUT_JOINTS;
+  const int o = (int)(idx % JRR_NUM_OUT_JOINTS);
+  const int src = joint_map[o];
+  float out[3] = {0.f, 0.f, 0.f};
+  const float* vb = vertices + b * (int64_t)(V * 3);
+  if (src < NJ) {
+    for (int c = 0; c < 3; c++) out[c] = Jp[b * 72 + src * 3 + c];
+  } else if (src < NJ + JRR_NUM_PICKS) {
+    const int v = picks[src - NJ];
+    for (int c = 0; c < 3; c++) out[c] = vb[v * 3 + c];
+  } else {
+    const int e = src - NJ - JRR_NUM_PICKS;
+    for (int p = extra.ptr[e]; p < extra.ptr[e + 1]; p++) {
+      const int v = extra.col[p];
+      const float cf = extra.val[p];
+      for (int c = 0; c < 3; c++) out[c] = fmaf(cf, vb[v * 3 + c], out[c]);
+    }
+  }
+  for (int c = 0; c < 3; c++) joints49[idx * 3 + c] = out[c];
+}
+
+// gather the joints49 gradient back onto its 54 sources: first 24 -> dJp [BP][72], the 30
+// vertex-borne sources -> d30T [90][BP] (consumed by skin_bwd USE_X)
+__global__ void joints49_bwd_kernel(const int* __restrict__ joint_map, const float* __restrict__ dj49,
+                                    int64_t B, int64_t BP, float* __restrict__ dJp,
+                                    float* __restrict__ d30T) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= BP * 54) return;
+  const int src = (int)(idx / BP);
+  const int64_t b = idx % BP;
+  float d[3] = {0.f, 0.f, 0.f};
+  if (b < B && dj49 != nullptr)
+    for (int o = 0; o < JRR_NUM_OUT_JOINTS; o++)
+      if (joint_map[o] == src)
+        for (int c = 0; c < 3; c++) d[c] += dj49[(b * JRR_NUM_OUT_JOINTS + o) * 3 + c];
+  if (src < NJ) {
+    for (int c = 0; c < 3; c++) dJp[b * 72 + src * 3 + c] = d[c];
+  } else {
+    for (int c = 0; c < 3; c++) d30T[(int64_t)((src - NJ) * 3 + c) * BP + b] = d[c];
+  }
+}
+
+// ---------------------------------------------------------------------------- loss finish
+__global__ void loss_finish_kernel(const float* __restrict__ lp_joint, int n_joint, float sj,
+                                   const float* __restrict__ lp_pose, int n_pose, float sp,
+                                   float wj, float wp, float* __restrict__ loss_out,
+                                   float* __restrict__ loss_accum) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float a = 0.f, p = 0.f;
+  for (int i = 0; i < n_joint; i++) a += lp_joint[i];
+  for (int i = 0; i < n_pose; i++) p += lp_pose[i];
+  a *= sj;
+  p *= sp;
+  if (loss_out != nullptr) {
+    loss_out[0] = wj * a + wp * p;
+    loss_out[1] = a;
+    loss_out[2] = p;
+  }
+  if (loss_accum != nullptr) loss_accum[0] += a;
+}
+
+// ---------------------------------------------------------------------------- host side
+int launch_skin_fwd(const JrrModel* m, const Workspace& w, float* vertices_out, float* vT_out,
+                    bool want_part, cudaStream_t st) {
+  dim3 grid((unsigned)(w.BP / SK_THREADS), NSPLIT), block(SK_THREADS);
+#define JRR_SF(WV, WVT, P)                                                                       \
+  do {                                                                                           \
+    auto kern = skin_fwd_kernel<WV, WVT, P>;                                                     \
+    const size_t smem = WV ? (size_t)SK_THREADS * TILE_LD * sizeof(float) : 0;                   \
+    cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e_ != cudaSuccess) return fail(JRR_ERR_CUDA, cudaGetErrorString(e_));                    \
+    kern<<<grid, block, smem, st>>>(m->vrec, m->Jhat_cols, w.AT, w.vpT, w.B, w.BP, vertices_out, \
+                                    vT_out, w.part);                                             \
+  } while (0)
+  const bool wv = vertices_out != nullptr, wvt = vT_out != nullptr;
+  if (wv && !wvt && !want_part) JRR_SF(true, false, false);
+  else if (wv && !wvt && want_part) JRR_SF(true, false, true);
+  else if (!wv && !wvt && want_part) JRR_SF(false, false, true);
+  else if (!wv && wvt && want_part) JRR_SF(false, true, true);
+  else if (!wv && wvt && !want_part) JRR_SF(false, true, false);
+  else return fail(JRR_ERR_INVALID, "skin_fwd: unsupported output combination");
+#undef JRR_SF
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_loss_seed(const JrrModel* m, const Workspace& w, const float* gt_mm, int64_t B_logical,
+                     float w_joint, float* joints17_out, cudaStream_t st) {
+  (void)m;
+  dim3 grid((unsigned)(w.BP / SK_THREADS)), block(SK_THREADS);
+  const float scale = gt_mm != nullptr ? w_joint * 2.f / (51.f * (float)B_logical) : 0.f;
+  loss_seed_kernel<<<grid, block, 0, st>>>(w.part, gt_mm, w.B, w.BP, scale,
+                                           gt_mm != nullptr ? w.gT : nullptr, joints17_out,
+                                           w.loss_part);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_g,
+                    bool use_x, cudaStream_t st) {
+  dim3 grid((unsigned)(w.BP / SK_THREADS), NSPLIT), block(SK_THREADS);
+  const bool use_dv = dvertices != nullptr;
+  const size_t smem = (size_t)SK_THREADS * TILE_LD * sizeof(float) * (use_dv ? 2 : 1);
+#define JRR_SB(G, DV, X)                                                                          \
+  do {                                                                                            \
+    auto kern = skin_bwd_kernel<G, DV, X>;                                                        \
+    cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e_ != cudaSuccess) return fail(JRR_ERR_CUDA, cudaGetErrorString(e_));                     \
+    kern<<<grid, block, smem, st>>>(m->vrec, m->Jhat_cols, m->range_flush_base, m->vx_src,        \
+                                    m->vx_coef, w.AT, w.vpT, w.gT, dvertices, w.d30T, w.B, w.BP,  \
+                                    w.dvp_hi, w.dvp_lo, w.dAflush);                               \
+  } while (0)
+  if (use_g && !use_dv && !use_x) JRR_SB(true, false, false);
+  else if (!use_g && use_dv && use_x) JRR_SB(false, true, true);
+  else if (!use_g && use_dv && !use_x) JRR_SB(false, true, false);
+  else if (!use_g && !use_dv && use_x) JRR_SB(false, false, true);
+  else return fail(JRR_ERR_INVALID, "skin_bwd: unsupported input combination");
+#undef JRR_SB
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_dA_reduce(const JrrModel* m, const Workspace& w, cudaStream_t st) {
+  dim3 grid((unsigned)(w.BP / SK_THREADS), NJ), block(SK_THREADS);
+  dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr, m->flush_idx, w.dAflush, w.BP, w.dAT);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_joints49_fwd(const JrrModel* m, const Workspace& w, const float* vertices,
+                        float* joints49_out, cudaStream_t st) {
+  const int64_t n = w.B * JRR_NUM_OUT_JOINTS;
+  joints49_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->joint_map, m->picks, m->extra,
+                                                                  w.Jp, vertices, w.B, joints49_out);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_joints49_bwd(const JrrModel* m, const Workspace& w, const float* djoints49,
+                        cudaStream_t st) {
+  const int64_t n = w.BP * 54;
+  joints49_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->joint_map, djoints49, w.B, w.BP,
+                                                                  w.dJp, w.d30T);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_loss_finish(const Workspace& w, int64_t B_logical, float w_joint, float w_pose,
+                       bool have_pose, float* loss_out, float* loss_accum, cudaStream_t st) {
+  const int nj = (int)(w.BP / SK_THREADS);
+  const int np = have_pose ? w.n_pose_part : 0;
+  loss_finish_kernel<<<1, 32, 0, st>>>(w.loss_part, nj, 1.f / (51.f * (float)B_logical),
+                                       w.loss_part + LOSS_PART_POSE, np, 1.f / (25.f * (float)B_logical),
+                                       w_joint, w_pose, loss_out, loss_accum);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+}  // namespace jrr

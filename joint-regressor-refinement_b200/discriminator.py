@@ -1,0 +1,43 @@
+"""Pose critic with the reference's parameter layout (``scripts/discriminator.py:7-54``):
+``conv_operations.{0,2}``, ``linears.{0..23}``, ``linear_operations.{0,2,4}`` -- a reference
+``state_dict`` loads unchanged.  ``forward`` runs the CUDA kernels (fused 1x1 convs + heads,
+3xTF32 tensor-core GEMMs for 768->1024->1024).  The input gradient used by the refinement
+loop lives inside ``jrr_refine_step``; this module's forward is inference-only."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .native import NativeModel
+
+
+class Discriminator(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.num_inputs = 24
+        self.conv_operations = nn.Sequential(nn.Conv2d(6, 32, 1), nn.ReLU(), nn.Conv2d(32, 32, 1), nn.ReLU())
+        self.linears = nn.ModuleList([nn.Linear(32, 1) for _ in range(self.num_inputs)])
+        self.linear_operations = nn.Sequential(nn.Linear(32 * self.num_inputs, 1024), nn.ReLU(),
+                                               nn.Linear(1024, 1024), nn.ReLU(), nn.Linear(1024, 1))
+        self._native = None
+        self._loaded_key = None
+
+    def bind(self, native: NativeModel):
+        """Use `native`'s device copy of the weights (shared with the refinement kernels)."""
+        self._native = native
+        self._loaded_key = None
+        return self
+
+    def _sync_weights(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if key != self._loaded_key:
+            self._native.load_critic(self.state_dict())
+            self._loaded_key = key
+
+    def forward(self, rot6d: torch.Tensor) -> torch.Tensor:
+        """[B,24,6] -> sigmoid scores [B,25,1] ordered [global, joint 0..23]."""
+        if self._native is None:
+            raise RuntimeError("Discriminator.bind(smpl.native()) must be called first: the critic "
+                               "runs on the CUDA kernels only")
+        self._sync_weights()
+        return self._native.critic_forward(rot6d.detach().reshape(-1, 24, 6)).unsqueeze(-1)

@@ -1,0 +1,222 @@
+"""Thin object wrapper over the C ABI (include/jrr.h): owns the JrrModel handle and the
+caller-side device workspace.  PyTorch is used for device memory and streams only."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import POSE_AXIS_ANGLE, POSE_ROT6D, POSE_ROTMAT, JrrError, check  # noqa: F401
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise JrrError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def flatten_critic_state_dict(sd: dict) -> torch.Tensor:
+    """state_dict of scripts/discriminator.py:Discriminator -> the flat parameter vector
+    jrr_critic_load expects (registration order: conv_operations, linears, linear_operations)."""
+    keys = ["conv_operations.0.weight", "conv_operations.0.bias",
+            "conv_operations.2.weight", "conv_operations.2.bias"]
+    for i in range(24):
+        keys += [f"linears.{i}.weight", f"linears.{i}.bias"]
+    for i in (0, 2, 4):
+        keys += [f"linear_operations.{i}.weight", f"linear_operations.{i}.bias"]
+    flat = torch.cat([sd[k].detach().float().reshape(-1) for k in keys])
+    if flat.numel() != _lib.CRITIC_PARAMS:
+        raise JrrError(f"critic state_dict has {flat.numel()} parameters, expected {_lib.CRITIC_PARAMS}")
+    return flat
+
+
+class NativeModel:
+    """Device-resident packed body model + regressor + critic (JrrModel*)."""
+
+    def __init__(self, model: dict, device: torch.device, gemm_impl: int = 0):
+        self.L = _lib.lib()
+        if not torch.cuda.is_available():
+            raise JrrError("CUDA device required: the hot path has no CPU fallback")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise JrrError("NativeModel needs a CUDA device")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        f = lambda k: np.ascontiguousarray(np.asarray(model[k], dtype=np.float32))
+        i = lambda k: np.ascontiguousarray(np.asarray(model[k], dtype=np.int64))
+        keep = {k: f(k) for k in ("v_template", "shapedirs", "posedirs", "J_regressor",
+                                  "lbs_weights", "J_regressor_extra")}
+        keep.update({k: i(k) for k in ("parents", "joint_map", "vertex_picks")})
+        assert keep["v_template"].shape == (6890, 3) and keep["shapedirs"].shape == (6890, 3, 10)
+        assert keep["posedirs"].shape == (207, 20670) and keep["J_regressor"].shape == (24, 6890)
+        assert keep["lbs_weights"].shape == (6890, 24) and keep["J_regressor_extra"].shape == (9, 6890)
+        d = _lib.JrrModelDesc()
+        for k, a in keep.items():
+            setattr(d, k + "_host", a.ctypes.data)
+        d.device = idx
+        d.gemm_impl = gemm_impl
+        h = C.c_void_p()
+        check(self.L.jrr_model_create(C.byref(d), C.byref(h)), "jrr_model_create")
+        self.h = h
+        self._ws = None
+        self._ws_B = 0
+        self._reg_key = None
+        self.launches = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.jrr_model_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ workspace
+    def workspace(self, B: int):
+        if self._ws is None or self._ws_B < B:
+            need = self.L.jrr_workspace_bytes(self.h, B)
+            self._ws = None
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+            self._ws_B = B
+        off = (-self._ws.data_ptr()) % 256
+        return C.c_void_p(self._ws.data_ptr() + off), C.c_size_t(self._ws.numel() - off)
+
+    def _done(self):
+        self.launches = int(self.L.jrr_last_launch_count())
+
+    # ------------------------------------------------------------------ state
+    def set_regressor(self, J17_raw: torch.Tensor, mask: torch.Tensor | None = None):
+        J = _f32c(J17_raw.detach(), "J_regressor")
+        if tuple(J.shape) != (17, 6890):
+            raise JrrError(f"J_regressor must be [17,6890], got {tuple(J.shape)}")
+        m = _f32c(mask.detach(), "mask") if mask is not None else None
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_set_regressor(self.h, _ptr(J), _ptr(m), _stream()), "jrr_set_regressor")
+        self._reg_key = None
+
+    def set_regressor_cached(self, J17_raw: torch.Tensor, mask=None):
+        """find_joints re-normalises on every call in the reference (utils.py:87-92); here the
+        normalised copy is refreshed only when the tensor (or its version) changed."""
+        key = (J17_raw.data_ptr(), J17_raw._version, None if mask is None else (mask.data_ptr(), mask._version))
+        if key != self._reg_key:
+            self.set_regressor(J17_raw, mask)
+            self._reg_key = key
+
+    def load_critic(self, state_dict: dict):
+        flat = flatten_critic_state_dict(state_dict).to(self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_critic_load(self.h, _ptr(flat), _stream()), "jrr_critic_load")
+            torch.cuda.current_stream().synchronize()   # `flat` may be freed after return
+
+    # ------------------------------------------------------------------ SMPL forward / backward
+    def smpl_forward(self, betas, pose, kind, want_verts=True, want_joints=True):
+        B = pose.shape[0]
+        betas, pose = _f32c(betas, "betas"), _f32c(pose, "pose")
+        verts = torch.empty(B, 6890, 3, device=self.device) if want_verts else None
+        joints = torch.empty(B, 49, 3, device=self.device) if want_joints else None
+        ws, wsz = self.workspace(B)
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_smpl_forward(self.h, B, _ptr(betas), _ptr(pose), kind, _ptr(verts),
+                                          _ptr(joints), ws, wsz, _stream()), "jrr_smpl_forward")
+        self._done()
+        return verts, joints
+
+    def smpl_backward(self, betas, pose, kind, dverts, djoints):
+        B = pose.shape[0]
+        betas, pose = _f32c(betas, "betas"), _f32c(pose, "pose")
+        dverts = _f32c(dverts, "dvertices") if dverts is not None else None
+        djoints = _f32c(djoints, "djoints") if djoints is not None else None
+        dbetas = torch.empty(B, 10, device=self.device)
+        dpose = torch.empty_like(pose)
+        ws, wsz = self.workspace(B)
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_smpl_backward(self.h, B, _ptr(betas), _ptr(pose), kind, _ptr(dverts),
+                                           _ptr(djoints), _ptr(dbetas), _ptr(dpose), ws, wsz, _stream()),
+                  "jrr_smpl_backward")
+        self._done()
+        return dbetas, dpose
+
+    def find_joints(self, betas, pose, kind):
+        B = pose.shape[0]
+        betas, pose = _f32c(betas, "betas"), _f32c(pose, "pose")
+        out = torch.empty(B, 17, 3, device=self.device)
+        ws, wsz = self.workspace(B)
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_find_joints(self.h, B, _ptr(betas), _ptr(pose), kind, _ptr(out), ws, wsz,
+                                         _stream()), "jrr_find_joints")
+        self._done()
+        return out
+
+    def critic_forward(self, rot6d):
+        B = rot6d.shape[0]
+        x = _f32c(rot6d, "rot6d")
+        out = torch.empty(B, 25, device=self.device)
+        ws, wsz = self.workspace(B)
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_critic_forward(self.h, B, _ptr(x), _ptr(out), ws, wsz, _stream()),
+                  "jrr_critic_forward")
+        self._done()
+        return out
+
+    # ------------------------------------------------------------------ refinement
+    def refine_step(self, x6, betas, gt_mm, adam_m, adam_v, step_count, lr, w_joint, w_pose,
+                    logical_batch=None, loss_out=None):
+        """One fused iteration; x6/betas/adam_m/adam_v/step_count are updated in place."""
+        B = x6.shape[0]
+        for t, n in ((x6, "x6"), (betas, "betas"), (gt_mm, "gt_mm"), (adam_m, "adam_m"), (adam_v, "adam_v")):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise JrrError(f"{n} must be a contiguous fp32 CUDA tensor")
+        LB = B if logical_batch is None else int(logical_batch)
+        ws, wsz = self.workspace(B)
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_refine_step(self.h, B, LB, _ptr(x6), _ptr(betas), _ptr(gt_mm), _ptr(adam_m),
+                                         _ptr(adam_v), _ptr(step_count), lr, w_joint, w_pose,
+                                         _ptr(loss_out), ws, wsz, _stream()), "jrr_refine_step")
+        self._done()
+
+    def regressor_grad_accumulate(self, x6, betas, gt_mm, G_accum, loss_accum, logical_batch=None):
+        B = x6.shape[0]
+        LB = B if logical_batch is None else int(logical_batch)
+        x6, betas, gt_mm = _f32c(x6, "x6"), _f32c(betas, "betas"), _f32c(gt_mm, "gt_mm")
+        ws, wsz = self.workspace(B)
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_regressor_grad_accumulate(self.h, B, LB, _ptr(x6), _ptr(betas), _ptr(gt_mm),
+                                                       _ptr(G_accum), _ptr(loss_accum), ws, wsz, _stream()),
+                  "jrr_regressor_grad_accumulate")
+        self._done()
+
+    def regressor_apply(self, J17_raw, mask, G_accum, adam_m, adam_v, step_count, lr):
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_regressor_apply(self.h, _ptr(J17_raw), _ptr(mask), _ptr(G_accum), _ptr(adam_m),
+                                             _ptr(adam_v), _ptr(step_count), lr, _stream()),
+                  "jrr_regressor_apply")
+        self._done()
+        self._reg_key = None
+
+    # ------------------------------------------------------------------ diagnostics
+    def debug_gemm(self, A, B, impl=0):
+        """C[M,N] = A[M,K] @ B[N,K]^T through the 3xTF32 kernel (impl 0) or the SIMT one (1)."""
+        M, K = A.shape
+        N = B.shape[0]
+        A, B = _f32c(A, "A"), _f32c(B, "B")
+        Cc = torch.empty(M, N, device=self.device)
+        scratch = torch.empty(2 * (M + N) * K, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_debug_gemm(self.h, impl, M, N, K, _ptr(A), _ptr(B), _ptr(Cc), _ptr(scratch),
+                                        _stream()), "jrr_debug_gemm")
+        self._done()
+        return Cc

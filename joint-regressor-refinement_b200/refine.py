@@ -1,0 +1,168 @@
+"""The pseudo-ground-truth refinement loop of ``scripts/optimize.py`` on the CUDA path.
+
+``PoseRefiner.refine`` is the 100-iteration inner loop (optimize.py:201-202,220-265,
+in-scope loss ``w_joint*MSE(joints) + w_pose*MSE(critic, 1)``): every iteration is one
+``jrr_refine_step`` (SMPL forward + 17x6890 regressor + loss + analytic backward + Adam),
+captured once into a CUDA graph and replayed.  ``RegressorRefit.step`` is the regressor
+update that follows each batch (optimize.py:300-312); with ``torch.distributed`` initialised
+its 17x6890 gradient accumulator is all-reduced (NCCL) so every rank applies the same step.
+Frames are independent, so multi-GPU refinement is plain sharding with no communication.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .native import NativeModel
+
+
+def shard_range(n_frames: int, rank: int, world: int):
+    """Contiguous frame range [lo, hi) owned by `rank`."""
+    lo = (n_frames * rank) // world
+    hi = (n_frames * (rank + 1)) // world
+    return lo, hi
+
+
+class PoseRefiner:
+    def __init__(self, smpl, J_regressor, critic_state_dict=None, mask=None, lr=1e-2,
+                 w_joint=10000.0, w_pose=10.0, chunk=4096, use_graph=True):
+        self.native: NativeModel = smpl.native() if hasattr(smpl, "native") else smpl
+        self.device = self.native.device
+        self.lr, self.w_joint = float(lr), float(w_joint)
+        self.w_pose = float(w_pose) if critic_state_dict is not None else 0.0
+        self.chunk = int(chunk)
+        self.use_graph = use_graph
+        self.set_regressor(J_regressor, mask)
+        if critic_state_dict is not None:
+            self.native.load_critic(critic_state_dict)
+        self._bufs = {}      # B -> static buffers (+ graph)
+        self.launches_per_step = 0
+
+    def set_regressor(self, J_regressor, mask=None):
+        self.native.set_regressor(J_regressor.to(self.device), None if mask is None else mask.to(self.device))
+
+    def _buffers(self, B):
+        st = self._bufs.get(B)
+        if st is None:
+            dev = self.device
+            st = {
+                "x6": torch.zeros(B, 24, 6, device=dev), "betas": torch.zeros(B, 10, device=dev),
+                "gt": torch.zeros(B, 17, 3, device=dev), "m": torch.zeros(B, 154, device=dev),
+                "v": torch.zeros(B, 154, device=dev),
+                "t": torch.zeros(1, dtype=torch.int32, device=dev),
+                "loss": torch.zeros(3, device=dev), "graph": None, "LB": None,
+            }
+            self._bufs[B] = st
+        return st
+
+    def _step(self, st, LB):
+        self.native.refine_step(st["x6"], st["betas"], st["gt"], st["m"], st["v"], st["t"], self.lr,
+                                self.w_joint, self.w_pose, logical_batch=LB, loss_out=st["loss"])
+
+    def _run_chunk(self, st, iters, LB):
+        st["m"].zero_()
+        st["v"].zero_()
+        st["t"].zero_()
+        if not self.use_graph:
+            for _ in range(iters):
+                self._step(st, LB)
+            self.launches_per_step = self.native.launches
+            return
+        if st["graph"] is None or st["LB"] != LB:
+            # warm-up outside capture (module loading, attribute calls), on a side stream
+            keep = [st[k].clone() for k in ("x6", "betas", "m", "v", "t")]
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                self._step(st, LB)
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            self.launches_per_step = self.native.launches
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step(st, LB)
+            for k, v in zip(("x6", "betas", "m", "v", "t"), keep):
+                st[k].copy_(v)
+            st["graph"], st["LB"] = g, LB
+        for _ in range(iters):
+            st["graph"].replay()
+
+    def refine(self, x6, betas, gt_mm, iters=100, logical_batch=None):
+        """In-place refinement of x6 [N,24,6] / betas [N,10] against gt_mm [N,17,3] (mm,
+        pelvis-centred).  Frames are processed in chunks of ``chunk``; each chunk is one
+        reference "batch" (fresh Adam state; its size is the divisor of the mean losses unless
+        ``logical_batch`` is given).  Returns the last iteration's [total, joint, pose] loss
+        of the last chunk (device tensor)."""
+        N = x6.shape[0]
+        x6v, bv, gv = x6.view(N, 24, 6), betas.view(N, 10), gt_mm.view(N, 17, 3)
+        last = None
+        with torch.cuda.device(self.device):
+            for lo in range(0, N, self.chunk):
+                hi = min(N, lo + self.chunk)
+                B = hi - lo
+                st = self._buffers(B)
+                st["x6"].copy_(x6v[lo:hi], non_blocking=True)
+                st["betas"].copy_(bv[lo:hi], non_blocking=True)
+                st["gt"].copy_(gv[lo:hi], non_blocking=True)
+                self._run_chunk(st, iters, B if logical_batch is None else logical_batch)
+                x6v[lo:hi].copy_(st["x6"], non_blocking=True)
+                bv[lo:hi].copy_(st["betas"], non_blocking=True)
+                last = st["loss"]
+        return last
+
+
+class RegressorRefit:
+    """optimize.py:125-126,300-312 with the published no-op fixed (the raw regressor is the
+    optimised tensor): persistent Adam(lr=j_reg_lr) on J_raw [17,6890]."""
+
+    def __init__(self, smpl, J_regressor, mask=None, lr=1e-2, chunk=4096):
+        self.native: NativeModel = smpl.native() if hasattr(smpl, "native") else smpl
+        dev = self.native.device
+        self.J = J_regressor.detach().to(dev).float().contiguous().clone()
+        self.mask = None if mask is None else mask.detach().to(dev).float().contiguous()
+        self.m = torch.zeros_like(self.J)
+        self.v = torch.zeros_like(self.J)
+        self.t = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.G = torch.zeros_like(self.J)
+        self.loss = torch.zeros(1, device=dev)
+        self.lr = float(lr)
+        self.chunk = int(chunk)
+        self.native.set_regressor(self.J, self.mask)
+
+    def accumulate(self, x6, betas, gt_mm, logical_batch=None):
+        """G += dL/dJhat over these frames (L = MSE with divisor 51*logical_batch)."""
+        N = x6.shape[0]
+        LB = N if logical_batch is None else int(logical_batch)
+        for lo in range(0, N, self.chunk):
+            hi = min(N, lo + self.chunk)
+            self.native.regressor_grad_accumulate(x6[lo:hi], betas[lo:hi], gt_mm[lo:hi], self.G, self.loss,
+                                                  logical_batch=LB)
+
+    def step(self, x6=None, betas=None, gt_mm=None, logical_batch=None):
+        """One refit step over this rank's frames (already refined).  With torch.distributed
+        initialised the accumulators are summed over ranks first and `logical_batch` must be
+        the GLOBAL frame count."""
+        if x6 is not None:
+            self.G.zero_()
+            self.loss.zero_()
+            self.accumulate(x6, betas, gt_mm, logical_batch)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.G, op=dist.ReduceOp.SUM)
+            dist.all_reduce(self.loss, op=dist.ReduceOp.SUM)
+        self.native.regressor_apply(self.J, self.mask, self.G, self.m, self.v, self.t, self.lr)
+        return self.loss
+
+    @property
+    def J_regressor(self):
+        return self.J
+
+
+def load_j_regressor(path, device="cpu"):
+    """``models/retrained_J_Regressor.pt`` (saved from cuda:0, requires_grad, column-major)
+    loads unchanged: map_location + detach + contiguous (test.py:46-47 omits map_location)."""
+    t = torch.load(path, map_location="cpu", weights_only=True)
+    return t.detach().float().contiguous().to(device)
+
+
+def save_j_regressor(J, path):
+    """Plain ``torch.save(tensor)`` so the artefact stays loadable by test.py:46-47."""
+    torch.save(J.detach().clone(), path)

@@ -1,0 +1,95 @@
+"""Call-compatible mirrors of the reference's loss / geometry helpers
+(``scripts/utils.py:85-215``, ``scripts/eval_utils.py:7-58``).  ``find_joints`` is the one on
+the hot path: without autograd it runs the fused CUDA kernels (vertices never materialised);
+with autograd it goes through ``SMPLFunction`` so gradients reach betas / rotations / J."""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+import torch
+
+from ._lib import POSE_ROTMAT
+
+
+def rot6d_to_rotmat(x: torch.Tensor) -> torch.Tensor:
+    """scripts/utils.py:190-204 ([B,6] interleaved -> [B,3,3], columns b1,b2,b3)."""
+    x = x.reshape(-1, 3, 2)
+    a1, a2 = x[:, :, 0], x[:, :, 1]
+    b1 = torch.nn.functional.normalize(a1)
+    b2 = torch.nn.functional.normalize(a2 - (b1 * a2).sum(-1, keepdim=True) * b1)
+    b3 = torch.linalg.cross(b1, b2, dim=1)
+    return torch.stack((b1, b2, b3), dim=-1)
+
+
+def find_j_reg_mask(j_reg: torch.Tensor) -> torch.Tensor:
+    """scripts/utils.py:182-187.  The reference builds the mask from two all-ones tensors, so
+    it is all ones; reproduced (sparsity is preserved by relu'(x<=0)=0 instead)."""
+    return torch.ones_like(j_reg)
+
+
+def find_joints(smpl, shape, orient, pose, J_regressor, mask=None, return_verts=False):
+    """scripts/utils.py:85-103: regressed 17 joints [B,17,3] (and optionally the vertices)."""
+    needs_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (shape, orient, pose, J_regressor))
+    if return_verts or needs_grad:
+        J = J_regressor * mask if mask is not None else J_regressor
+        Jn = torch.relu(J)
+        Jn = Jn / Jn.sum(dim=1, keepdim=True)
+        verts = smpl(global_orient=orient, body_pose=pose, betas=shape, pose2rot=False).vertices
+        pred = torch.matmul(Jn.to(verts.device)[None], verts)
+        return (pred, verts) if return_verts else pred
+    native = smpl.native()
+    native.set_regressor_cached(J_regressor.to(native.device), None if mask is None else mask.to(native.device))
+    B = max(shape.shape[0], pose.shape[0])
+    full = torch.cat([orient.reshape(-1, 1, 3, 3).expand(B, -1, -1, -1),
+                      pose.reshape(-1, 23, 3, 3).expand(B, -1, -1, -1)], dim=1).reshape(B, 24, 9)
+    betas = shape if shape.shape[0] == B else shape.expand(B, -1)
+    return native.find_joints(betas, full, POSE_ROTMAT)
+
+
+def move_pelvis(j3ds: torch.Tensor) -> torch.Tensor:
+    """scripts/utils.py:106-114."""
+    return j3ds - j3ds[:, [0], :]
+
+
+def batch_compute_similarity_transform_torch(S1, S2):
+    """scripts/eval_utils.py:7-58 (metric only, plain torch): similarity-align S1 to S2."""
+    transposed = False
+    if S1.shape[0] != 3 and S1.shape[0] != 2:
+        S1, S2 = S1.permute(0, 2, 1), S2.permute(0, 2, 1)
+        transposed = True
+    mu1, mu2 = S1.mean(dim=-1, keepdim=True), S2.mean(dim=-1, keepdim=True)
+    X1, X2 = S1 - mu1, S2 - mu2
+    var1 = (X1 ** 2).sum(dim=(1, 2))
+    K = X1 @ X2.transpose(1, 2)
+    U, _, Vh = torch.linalg.svd(K)
+    Vm = Vh.transpose(1, 2)
+    Z = torch.eye(U.shape[1], device=S1.device, dtype=S1.dtype).repeat(U.shape[0], 1, 1)
+    Z[:, -1, -1] *= torch.sign(torch.det(U @ Vh))
+    R = Vm @ Z @ U.transpose(1, 2)
+    scale = torch.diagonal(R @ K, dim1=1, dim2=2).sum(1) / var1
+    t = mu2 - scale[:, None, None] * (R @ mu1)
+    out = scale[:, None, None] * (R @ S1) + t
+    return out.permute(0, 2, 1) if transposed else out
+
+
+def evaluate(pred_j3ds, target_j3ds):
+    """scripts/utils.py:117-145: (MPJPE, PA-MPJPE) in mm; target in mm, prediction in m."""
+    with torch.no_grad():
+        p = move_pelvis(pred_j3ds.detach().clone().float())
+        t = move_pelvis(target_j3ds.detach().clone().float() / 1000)
+        mpjpe = ((p - t) ** 2).sum(-1).sqrt().mean(-1).cpu().numpy().mean() * 1000
+        pa = ((batch_compute_similarity_transform_torch(p, t) - t) ** 2).sum(-1).sqrt().mean(-1).cpu().numpy().mean() * 1000
+    return mpjpe, pa
+
+
+def set_seed(seed):
+    """scripts/utils.py:207-215."""
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True

@@ -1,0 +1,325 @@
+"""CPU oracle for the refinement hot path -- TEST INFRASTRUCTURE ONLY.
+
+Nothing in the product package imports this file.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may use it, as the checker or as the timed CPU baseline.
+
+Pinning status
+--------------
+* ``rot6d_to_rotmat``, ``find_joints``, ``move_pelvis``, ``find_j_reg_mask``, ``evaluate``,
+  ``procrustes`` and ``discriminator_forward`` restate ``/root/reference/scripts/utils.py``,
+  ``eval_utils.py`` and ``discriminator.py``.  They are PINNED: ``tests/test_oracle_pinning.py``
+  compares them against the reference functions imported by path (when /root/reference
+  exists) and against the golden vectors in ``tests/golden/`` generated from the
+  reference functions by ``tests/golden/make_golden.py``.
+* ``lbs`` / ``OracleSMPL`` restate the un-vendored third-party dependency
+  ``smplx==0.1.26`` (``requirements.txt:12``; call sites ``scripts/smpl.py:7-9,65,72-85``).
+  smplx is neither in /root/reference nor installable offline and the reference has no
+  tests or golden vectors, so this part is **PARITY UNPINNED** against the real package; it
+  follows the published SMPL formulation (Loper et al. 2015) and is
+  anchored by analytic known-answer tests and fp64 gradcheck in ``tests/test_oracle.py``.
+"""
+from __future__ import annotations
+
+import types
+
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------- smplx.lbs
+def batch_rodrigues(r: torch.Tensor) -> torch.Tensor:
+    """Axis-angle [N,3] -> rotation matrices [N,3,3] (smplx.lbs.batch_rodrigues:
+    the 1e-8 is added to every component inside the norm)."""
+    angle = torch.norm(r + 1e-8, dim=1, keepdim=True)
+    n = r / angle
+    c = torch.cos(angle)[:, None]
+    s = torch.sin(angle)[:, None]
+    x, y, z = n[:, 0], n[:, 1], n[:, 2]
+    zero = torch.zeros_like(x)
+    K = torch.stack([zero, -z, y, z, zero, -x, -y, x, zero], dim=1).view(-1, 3, 3)
+    eye = torch.eye(3, dtype=r.dtype, device=r.device)[None]
+    return eye + s * K + (1 - c) * torch.bmm(K, K)
+
+
+def lbs(betas, rot_mats, v_template, shapedirs, posedirs, J_regressor, parents, lbs_weights):
+    """Linear blend skinning (smplx.lbs.lbs with rotation matrices already formed).
+    betas [B,10], rot_mats [B,24,3,3] -> vertices [B,V,3], posed joints [B,24,3]."""
+    B = rot_mats.shape[0]
+    dtype = rot_mats.dtype
+    # 1. shape blend
+    v_shaped = v_template[None] + torch.einsum('bl,vkl->bvk', betas, shapedirs)
+    # 2. rest joints
+    J = torch.einsum('jv,bvk->bjk', J_regressor, v_shaped)
+    # 3. pose blend (joint-major, row-major 3x3)
+    eye = torch.eye(3, dtype=dtype)
+    pose_feature = (rot_mats[:, 1:] - eye).reshape(B, -1)
+    v_posed = v_shaped + (pose_feature @ posedirs).view(B, -1, 3)
+    # 4. kinematic chain
+    GR = [rot_mats[:, 0]]
+    Gt = [J[:, 0]]
+    for j in range(1, parents.shape[0]):
+        p = int(parents[j])
+        GR.append(GR[p] @ rot_mats[:, j])
+        Gt.append((GR[p] @ (J[:, j] - J[:, p])[..., None])[..., 0] + Gt[p])
+    GR = torch.stack(GR, dim=1)                      # [B,24,3,3]
+    Gt = torch.stack(Gt, dim=1)                      # [B,24,3]  == posed joints
+    At = Gt - (GR @ J[..., None])[..., 0]            # translation of the relative transform
+    # 5. skinning
+    TR = torch.einsum('vj,bjrc->bvrc', lbs_weights, GR)
+    Tt = torch.einsum('vj,bjr->bvr', lbs_weights, At)
+    verts = (TR @ v_posed[..., None])[..., 0] + Tt
+    return verts, Gt
+
+
+class OracleSMPL:
+    """Callable like the reference's ``smpl`` (scripts/smpl.py:61-85, utils.py:94-95):
+    ``smpl(betas=, body_pose=, global_orient=, pose2rot=)`` -> object with ``.vertices``
+    [B,6890,3] and ``.joints`` [B,49,3]."""
+
+    def __init__(self, model: dict, dtype=torch.float32):
+        self.dtype = dtype
+        t = lambda k: torch.as_tensor(model[k]).to(dtype)
+        self.v_template = t("v_template")
+        self.shapedirs = t("shapedirs")
+        self.posedirs = t("posedirs")
+        self.J_regressor = t("J_regressor")
+        self.lbs_weights = t("lbs_weights")
+        self.J_regressor_extra = t("J_regressor_extra")
+        self.parents = torch.as_tensor(model["parents"]).long()
+        self.joint_map = torch.as_tensor(model["joint_map"]).long()
+        self.vertex_picks = torch.as_tensor(model["vertex_picks"]).long()
+
+    def __call__(self, betas=None, body_pose=None, global_orient=None, transl=None,
+                 return_verts=True, return_full_pose=False, pose2rot=True, **kwargs):
+        B = max(betas.shape[0], body_pose.shape[0], global_orient.shape[0])
+        if betas.shape[0] != B:
+            betas = betas.expand(B, -1)
+        if pose2rot:
+            full = torch.cat([global_orient.reshape(B, -1), body_pose.reshape(B, -1)], dim=1)
+            rot = batch_rodrigues(full.reshape(-1, 3)).view(B, 24, 3, 3)
+        else:
+            rot = torch.cat([global_orient.reshape(B, 1, 3, 3), body_pose.reshape(B, 23, 3, 3)], dim=1)
+        verts, joints24 = lbs(betas, rot, self.v_template, self.shapedirs, self.posedirs,
+                              self.J_regressor, self.parents, self.lbs_weights)
+        # VertexJointSelector: 24 posed joints + 21 vertex picks
+        joints45 = torch.cat([joints24, verts[:, self.vertex_picks]], dim=1)
+        if transl is not None:
+            joints45 = joints45 + transl[:, None]
+            verts = verts + transl[:, None]
+        # scripts/smpl.py:75-78
+        extra = torch.einsum('ev,bvk->bek', self.J_regressor_extra, verts)
+        joints = torch.cat([joints45, extra], dim=1)[:, self.joint_map]
+        return types.SimpleNamespace(vertices=verts, joints=joints, betas=betas,
+                                     global_orient=global_orient, body_pose=body_pose,
+                                     full_pose=None)
+
+
+# --------------------------------------------------------------------------- scripts/utils.py
+def rot6d_to_rotmat(x: torch.Tensor) -> torch.Tensor:
+    """scripts/utils.py:190-204.  x viewed as [-1,3,2]; a1 = even entries, a2 = odd entries;
+    Gram-Schmidt; b1,b2,b3 are the COLUMNS of R."""
+    x = x.reshape(-1, 3, 2)
+    a1, a2 = x[:, :, 0], x[:, :, 1]
+    b1 = a1 / a1.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    u = a2 - (b1 * a2).sum(dim=1, keepdim=True) * b1
+    b2 = u / u.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    b3 = torch.linalg.cross(b1, b2, dim=1)
+    return torch.stack([b1, b2, b3], dim=-1)
+
+
+def find_j_reg_mask(j_reg: torch.Tensor) -> torch.Tensor:
+    """scripts/utils.py:182-187 -- reproduces the reference bug: the mask is all ones."""
+    return torch.ones_like(j_reg)
+
+
+def normalise_regressor(J: torch.Tensor, mask=None) -> torch.Tensor:
+    """scripts/utils.py:87-92: relu(J*mask) with rows normalised to sum 1."""
+    if mask is not None:
+        J = J * mask
+    Jr = torch.relu(J)
+    return Jr / Jr.sum(dim=1, keepdim=True)
+
+
+def find_joints(smpl, shape, orient, pose, J_regressor, mask=None, return_verts=False):
+    """scripts/utils.py:85-103."""
+    Jn = normalise_regressor(J_regressor, mask)
+    verts = smpl(global_orient=orient, body_pose=pose, betas=shape, pose2rot=False).vertices
+    pred = torch.einsum('jv,bvk->bjk', Jn.to(verts.dtype), verts)
+    if return_verts:
+        return pred, verts
+    return pred
+
+
+def move_pelvis(j3ds: torch.Tensor) -> torch.Tensor:
+    """scripts/utils.py:106-114."""
+    return j3ds - j3ds[:, [0], :]
+
+
+def procrustes(S1: torch.Tensor, S2: torch.Tensor) -> torch.Tensor:
+    """scripts/eval_utils.py:7-58 for [B,N,3] inputs: similarity-align S1 to S2."""
+    X1 = S1.permute(0, 2, 1)
+    X2 = S2.permute(0, 2, 1)
+    mu1 = X1.mean(dim=-1, keepdim=True)
+    mu2 = X2.mean(dim=-1, keepdim=True)
+    Y1, Y2 = X1 - mu1, X2 - mu2
+    var1 = (Y1 ** 2).sum(dim=(1, 2))
+    K = Y1 @ Y2.transpose(1, 2)
+    U, s, Vh = torch.linalg.svd(K)
+    V = Vh.transpose(1, 2)
+    Z = torch.eye(3, dtype=S1.dtype).repeat(S1.shape[0], 1, 1)
+    Z[:, -1, -1] *= torch.sign(torch.det(U @ V.transpose(1, 2)))
+    R = V @ Z @ U.transpose(1, 2)
+    scale = torch.diagonal(R @ K, dim1=1, dim2=2).sum(dim=1) / var1
+    t = mu2 - scale[:, None, None] * (R @ mu1)
+    return (scale[:, None, None] * (R @ X1) + t).permute(0, 2, 1)
+
+
+def evaluate(pred_j3ds: torch.Tensor, target_j3ds: torch.Tensor):
+    """scripts/utils.py:117-145: MPJPE / PA-MPJPE in mm (target given in mm)."""
+    with torch.no_grad():
+        p = move_pelvis(pred_j3ds.detach().clone())
+        t = move_pelvis(target_j3ds.detach().clone() / 1000)
+        mpjpe = ((p - t) ** 2).sum(-1).sqrt().mean(-1).mean().item() * 1000
+        pa = ((procrustes(p, t) - t) ** 2).sum(-1).sqrt().mean(-1).mean().item() * 1000
+    return mpjpe, pa
+
+
+# --------------------------------------------------------------------------- scripts/discriminator.py
+def discriminator_forward(sd: dict, rot6d: torch.Tensor) -> torch.Tensor:
+    """scripts/discriminator.py:32-54 as a function of the module's state_dict
+    (keys conv_operations.{0,2}, linears.{0..23}, linear_operations.{0,2,4}).
+    rot6d [B,24,6] -> sigmoid scores [B,25,1] ordered [global, joint0..joint23]."""
+    B = rot6d.shape[0]
+    dt = rot6d.dtype
+    g = lambda k: sd[k].to(dt)
+    w1 = g("conv_operations.0.weight").reshape(32, 6)
+    w2 = g("conv_operations.2.weight").reshape(32, 32)
+    h = torch.relu(rot6d @ w1.t() + g("conv_operations.0.bias"))
+    h = torch.relu(h @ w2.t() + g("conv_operations.2.bias"))            # [B,24,32]
+    z = h.reshape(B, 24 * 32)
+    z = torch.relu(z @ g("linear_operations.0.weight").t() + g("linear_operations.0.bias"))
+    z = torch.relu(z @ g("linear_operations.2.weight").t() + g("linear_operations.2.bias"))
+    zg = z @ g("linear_operations.4.weight").t() + g("linear_operations.4.bias")   # [B,1]
+    wj = torch.stack([g(f"linears.{i}.weight").reshape(32) for i in range(24)])    # [24,32]
+    bj = torch.stack([g(f"linears.{i}.bias").reshape(()) for i in range(24)])      # [24]
+    zj = (h * wj[None]).sum(-1) + bj[None]                                         # [B,24]
+    return torch.sigmoid(torch.cat([zg, zj], dim=1))[..., None]
+
+
+def make_critic_state_dict(seed: int = 0) -> dict:
+    """Default-init ``Discriminator()`` parameters under torch.manual_seed(seed), built
+    from the same nn layers in the same construction order as discriminator.py:14-30 so
+    the values equal the reference module's (checked in tests/test_oracle_pinning.py)."""
+    from torch import nn
+    gen_state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    conv = nn.Sequential(nn.Conv2d(6, 32, 1), nn.ReLU(), nn.Conv2d(32, 32, 1), nn.ReLU())
+    linears = nn.ModuleList([nn.Linear(32, 1) for _ in range(24)])
+    lin = nn.Sequential(nn.Linear(768, 1024), nn.ReLU(), nn.Linear(1024, 1024), nn.ReLU(),
+                        nn.Linear(1024, 1))
+    torch.random.set_rng_state(gen_state)
+    sd = {}
+    for prefix, mod in (("conv_operations", conv), ("linears", linears), ("linear_operations", lin)):
+        for k, v in mod.state_dict().items():
+            sd[f"{prefix}.{k}"] = v.detach().clone()
+    return sd
+
+
+# --------------------------------------------------------------------------- scripts/optimize.py
+def refine_loss(smpl, Jraw, critic_sd, x6, betas, gt_mm, w_joint=10000.0, w_pose=10.0,
+                logical_batch=None, mask=None):
+    """In-scope terms of optimize.py:222-253 for one iteration.  ``logical_batch`` replaces
+    B in the two mean reductions so that a shard reproduces the full-batch gradients."""
+    B = x6.shape[0]
+    R = rot6d_to_rotmat(x6.reshape(-1, 6)).view(B, 24, 3, 3)
+    pred = find_joints(smpl, betas, R[:, :1], R[:, 1:], Jraw, mask=mask)
+    diff = move_pelvis(pred) - gt_mm / 1000
+    LB = B if logical_batch is None else logical_batch
+    joint_loss = (diff ** 2).sum() / (LB * 17 * 3)
+    total = w_joint * joint_loss
+    pose_loss = torch.zeros((), dtype=x6.dtype)
+    if critic_sd is not None and w_pose != 0:
+        sig = discriminator_forward(critic_sd, x6)
+        pose_loss = ((sig - 1) ** 2).sum() / (LB * 25)
+        total = total + w_pose * pose_loss
+    return total, joint_loss, pose_loss, pred
+
+
+def refine(smpl, Jraw, critic_sd, x6, betas, gt_mm, iters=100, lr=1e-2, w_joint=10000.0,
+           w_pose=10.0, logical_batch=None):
+    """optimize.py:201-202,220-265 restricted to the in-scope loss: fresh
+    torch.optim.Adam([pose, orient, betas], lr) per batch, `iters` steps."""
+    x6 = x6.detach().clone().requires_grad_(True)
+    betas = betas.detach().clone().requires_grad_(True)
+    opt = torch.optim.Adam([x6, betas], lr=lr)
+    hist = []
+    for _ in range(iters):
+        total, jl, pl, _ = refine_loss(smpl, Jraw, critic_sd, x6, betas, gt_mm, w_joint, w_pose,
+                                       logical_batch)
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+        hist.append((float(total), float(jl), float(pl)))
+    return x6.detach(), betas.detach(), hist
+
+
+def regressor_grad(smpl, Jraw, x6, betas, gt_mm, logical_batch=None, mask=None):
+    """optimize.py:300-309 with the published no-op fixed (requires_grad on J):
+    returns dL/dJraw [17,6890] and the loss."""
+    B = x6.shape[0]
+    J = Jraw.detach().clone().requires_grad_(True)
+    with torch.no_grad():
+        R = rot6d_to_rotmat(x6.reshape(-1, 6)).view(B, 24, 3, 3)
+    pred = find_joints(smpl, betas.detach(), R[:, :1], R[:, 1:], J, mask=mask)
+    diff = move_pelvis(pred) - gt_mm / 1000
+    LB = B if logical_batch is None else logical_batch
+    loss = (diff ** 2).sum() / (LB * 17 * 3)
+    loss.backward()
+    return J.grad.detach(), float(loss)
+
+
+class RegressorAdam:
+    """optimize.py:125-126,310-312: Adam(lr=j_reg_lr) on the raw regressor with state
+    that persists across batches."""
+
+    def __init__(self, Jraw, lr=1e-2):
+        self.J = Jraw.detach().clone().requires_grad_(True)
+        self.opt = torch.optim.Adam([self.J], lr=lr)
+
+    def step(self, grad):
+        self.opt.zero_grad()
+        self.J.grad = grad.clone()
+        self.opt.step()
+        return self.J.detach()
+
+
+def make_gt(smpl, Jraw, true_rotmat, true_betas, gt_noise_mm):
+    """Synthetic GT 3-D joints in mm, pelvis-centred."""
+    with torch.no_grad():
+        pred = find_joints(smpl, true_betas, true_rotmat[:, :1], true_rotmat[:, 1:], Jraw)
+        return 1000 * move_pelvis(pred) + gt_noise_mm
+
+
+def load_reference_modules(root="/root/reference"):
+    """Import the reference's own utils / discriminator by path (CPU device) for
+    pinning.  Returns (utils, discriminator, eval_utils) or None when the tree is absent."""
+    import importlib
+    import os
+    import sys
+    if not os.path.isdir(os.path.join(root, "scripts")):
+        return None
+    argv = sys.argv
+    sys.argv = ["oracle", "--device", "cpu"]          # scripts/args.py:100 parses at import
+    sys.path.insert(0, root)
+    try:
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            u = importlib.import_module("scripts.utils")
+            d = importlib.import_module("scripts.discriminator")
+            e = importlib.import_module("scripts.eval_utils")
+        return u, d, e
+    finally:
+        sys.argv = argv
+        sys.path.remove(root)

@@ -1,0 +1,57 @@
+"""Generates the committed golden fixtures from the REFERENCE's own code and artefact
+(run in the build container, where /root/reference exists):
+
+  j_regressor_nnz.npz   the 107 non-zeros of models/retrained_J_Regressor.pt (+ its sha256)
+  ref_utils_golden.npz  inputs/outputs of the reference's rot6d_to_rotmat, move_pelvis,
+                        find_joints (on the oracle SMPL), evaluate, Discriminator.forward,
+                        computed by importing /root/reference/scripts/{utils,discriminator}.py
+
+    python tests/golden/make_golden.py
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("JRR_REFERENCE_ROOT", "/root/reference")
+
+import jrr_b200 as jrr  # noqa: E402
+from oracle import jrr_oracle as O  # noqa: E402
+
+
+def main():
+    art = os.path.join(REF, "models", "retrained_J_Regressor.pt")
+    sha = hashlib.sha256(open(art, "rb").read()).hexdigest()
+    J = torch.load(art, map_location="cpu", weights_only=True).detach().contiguous()
+    r, c = torch.nonzero(J, as_tuple=True)
+    np.savez(os.path.join(HERE, "j_regressor_nnz.npz"), row=r.numpy().astype(np.int32),
+             col=c.numpy().astype(np.int32), val=J[r, c].numpy(), sha256=np.array(sha))
+
+    u, d, e = O.load_reference_modules(REF)
+    model = jrr.synthetic.make_smpl_model(0)
+    smpl = O.OracleSMPL(model)
+    g = torch.Generator().manual_seed(1234)
+    x6 = torch.randn(6, 24, 6, generator=g)
+    R = u.rot6d_to_rotmat(x6.reshape(-1, 6)).view(6, 24, 3, 3)
+    betas = torch.randn(6, 10, generator=g)
+    pred = u.find_joints(smpl, betas, R[:, :1], R[:, 1:], J, mask=u.find_j_reg_mask(J))
+    pelvis = u.move_pelvis(pred)
+    gt = 1000 * pelvis + 7.0 * torch.randn(6, 17, 3, generator=g)
+    mpjpe, pampjpe = u.evaluate(pred, gt)
+    torch.manual_seed(0)
+    D = d.Discriminator()
+    scores = D(x6).detach()
+    np.savez(os.path.join(HERE, "ref_utils_golden.npz"), x6=x6.numpy(), rotmat=R.numpy(),
+             betas=betas.numpy(), find_joints=pred.detach().numpy(), move_pelvis=pelvis.detach().numpy(),
+             gt_mm=gt.detach().numpy(), mpjpe=np.float64(mpjpe), pa_mpjpe=np.float64(pampjpe),
+             critic_scores=scores.numpy(), mask_sum=np.float64(u.find_j_reg_mask(J).sum().item()))
+    print("wrote fixtures; artefact sha256", sha)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,297 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, on the B200.
+Tolerances are the north star's: vertices/joints 1e-5 relative (max-abs difference over
+max-abs reference), refined MPJPE within 0.01 mm, regressor weights within 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_frames
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def smpl_tc(jrr, model):
+    return jrr.SMPL(model_dict=model, create_transl=False, gemm_impl=0).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def smpl_simt(jrr, model):
+    return jrr.SMPL(model_dict=model, create_transl=False, gemm_impl=1).to(DEV)
+
+
+# ------------------------------------------------------------------ kernel level: the GEMM
+@pytest.mark.parametrize("shape", [(128, 128, 32), (256, 256, 224), (128, 224, 3456), (384, 1024, 768)])
+def test_gemm_simt_vs_torch(smpl_simt, shape):
+    M, N, K = shape
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    B = torch.randn(N, K, generator=g).to(DEV)
+    C = smpl_simt.native().debug_gemm(A, B, impl=1)
+    ref = A.double() @ B.double().t()
+    assert rel(C, ref) < 2e-6
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 32), (128, 128, 224), (256, 256, 224), (128, 224, 3456),
+                                   (384, 1024, 768), (1024, 20736, 224)])
+def test_gemm_tcgen05_3xtf32_vs_fp64(smpl_tc, shape):
+    M, N, K = shape
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    B = torch.randn(N, K, generator=g).to(DEV)
+    C = smpl_tc.native().debug_gemm(A, B, impl=0)
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t()
+    # 3xTF32 keeps ~21 mantissa bits per product; fp32 accumulation over K
+    assert rel(C, ref) < 4e-6
+
+
+# ------------------------------------------------------------------ SMPL forward (config C1)
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("pose2rot", [False, True])
+def test_smpl_forward_matches_oracle(impl, pose2rot, smpl_tc, smpl_simt, osmpl32, osmpl64, jrr):
+    smpl = smpl_tc if impl == "tc" else smpl_simt
+    inp = jrr.synthetic.make_pose_inputs(64, 3)
+    betas = torch.from_numpy(inp["true_betas"])
+    if pose2rot:
+        g = torch.Generator().manual_seed(5)
+        go = torch.randn(64, 3, generator=g)
+        bp = 0.3 * torch.randn(64, 69, generator=g)
+        kw = dict(global_orient=go, body_pose=bp)
+    else:
+        R = torch.from_numpy(inp["true_rotmat"])
+        kw = dict(global_orient=R[:, :1], body_pose=R[:, 1:])
+    ref = osmpl64(betas=betas.double(), pose2rot=pose2rot, **{k: v.double() for k, v in kw.items()})
+    ref32 = osmpl32(betas=betas, pose2rot=pose2rot, **kw)
+    out = smpl(betas=betas.to(DEV), pose2rot=pose2rot, **{k: v.to(DEV) for k, v in kw.items()})
+    assert out.vertices.shape == (64, 6890, 3) and out.joints.shape == (64, 49, 3)
+    ev, ej = rel(out.vertices, ref.vertices), rel(out.joints, ref.joints)
+    print(f"[{impl} pose2rot={pose2rot}] vertices rel {ev:.2e} joints rel {ej:.2e}; "
+          f"fp32 oracle vs fp64: {rel(ref32.vertices, ref.vertices):.2e}")
+    assert ev < 1e-5 and ej < 1e-5
+
+
+def test_smpl_forward_known_answers(smpl_tc, model):
+    """identity rotations + zero betas -> template; global rotation only -> rigid motion."""
+    B = 3
+    I = torch.eye(3, device=DEV).expand(B, 24, 3, 3).contiguous()
+    z = torch.zeros(B, 10, device=DEV)
+    out = smpl_tc(betas=z, body_pose=I[:, 1:], global_orient=I[:, :1], pose2rot=False)
+    vt = torch.from_numpy(model["v_template"]).to(DEV)
+    assert (out.vertices - vt[None]).abs().max().item() < 2e-6
+    c, s = np.cos(0.7), np.sin(0.7)
+    R0 = torch.tensor([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]], device=DEV, dtype=torch.float32)
+    Rg = I.clone()
+    Rg[:, 0] = R0
+    out = smpl_tc(betas=z, body_pose=Rg[:, 1:], global_orient=Rg[:, :1], pose2rot=False)
+    J0 = torch.from_numpy(model["J_regressor"][0] @ model["v_template"]).to(DEV)
+    expect = (vt - J0) @ R0.t() + J0
+    assert (out.vertices - expect[None]).abs().max().item() < 5e-6
+
+
+def test_smpl_ragged_batch_and_beta_broadcast(smpl_tc, osmpl32, jrr):
+    """B not a multiple of the 128-pose tile, batch-1 betas broadcast (smplx semantics)."""
+    inp = jrr.synthetic.make_pose_inputs(131, 9)
+    R = torch.from_numpy(inp["true_rotmat"])
+    b1 = torch.from_numpy(inp["true_betas"][:1])
+    ref = osmpl32(betas=b1, body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False)
+    out = smpl_tc(betas=b1.to(DEV), body_pose=R[:, 1:].to(DEV), global_orient=R[:, :1].to(DEV), pose2rot=False)
+    assert rel(out.vertices, ref.vertices) < 1e-5 and rel(out.joints, ref.joints) < 1e-5
+
+
+# ------------------------------------------------------------------ SMPL backward
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("pose2rot", [False, True])
+def test_smpl_backward_matches_oracle_autograd(impl, pose2rot, smpl_tc, smpl_simt, osmpl64, jrr):
+    smpl = smpl_tc if impl == "tc" else smpl_simt
+    B = 48
+    inp = jrr.synthetic.make_pose_inputs(B, 11)
+    g = torch.Generator().manual_seed(17)
+    betas = torch.from_numpy(inp["true_betas"])
+    if pose2rot:
+        go = torch.randn(B, 3, generator=g)
+        bp = 0.3 * torch.randn(B, 69, generator=g)
+    else:
+        R = torch.from_numpy(inp["true_rotmat"])
+        go, bp = R[:, :1].contiguous(), R[:, 1:].contiguous()
+    wv = torch.randn(B, 6890, 3, generator=g)
+    wj = torch.randn(B, 49, 3, generator=g)
+
+    def run(fn, dt, dev):
+        b = betas.to(dev, dt).requires_grad_(True)
+        o = go.to(dev, dt).requires_grad_(True)
+        p = bp.to(dev, dt).requires_grad_(True)
+        out = fn(betas=b, body_pose=p, global_orient=o, pose2rot=pose2rot)
+        loss = (out.vertices * wv.to(dev, dt)).sum() + (out.joints * wj.to(dev, dt)).sum()
+        loss.backward()
+        return b.grad, o.grad, p.grad
+
+    rb, ro, rp = run(osmpl64, torch.float64, "cpu")
+    gb, go_, gp = run(smpl, torch.float32, DEV)
+    eb, eo, ep = rel(gb, rb), rel(go_, ro), rel(gp, rp)
+    print(f"[{impl} pose2rot={pose2rot}] dbetas {eb:.2e} dorient {eo:.2e} dpose {ep:.2e}")
+    assert eb < 1e-4 and eo < 1e-4 and ep < 1e-4
+
+
+# ------------------------------------------------------------------ find_joints / critic
+@pytest.mark.parametrize("which", ["shipped", "dense"])
+def test_find_joints_matches_oracle(which, smpl_tc, osmpl64, oracle, jrr, J_shipped, J_dense, frames64):
+    J = J_shipped if which == "shipped" else J_dense
+    R = frames64["true_rotmat"]
+    b = frames64["true_betas"]
+    ref = oracle.find_joints(osmpl64, b.double(), R[:, :1].double(), R[:, 1:].double(), J.double(),
+                             mask=oracle.find_j_reg_mask(J.double()))
+    with torch.no_grad():
+        out = jrr.find_joints(smpl_tc, b.to(DEV), R[:, :1].to(DEV), R[:, 1:].to(DEV), J.to(DEV),
+                              mask=jrr.find_j_reg_mask(J.to(DEV)))
+    assert out.shape == (64, 17, 3)
+    assert rel(out, ref) < 1e-5
+    # return_verts goes through the module path
+    with torch.no_grad():
+        out2, verts = jrr.find_joints(smpl_tc, b.to(DEV), R[:, :1].to(DEV), R[:, 1:].to(DEV), J.to(DEV),
+                                      return_verts=True)
+    assert rel(out2, ref) < 1e-5 and verts.shape == (64, 6890, 3)
+
+
+def test_find_joints_golden(smpl_tc, jrr, J_shipped):
+    z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "ref_utils_golden.npz"))
+    R = torch.from_numpy(z["rotmat"]).to(DEV)
+    with torch.no_grad():
+        out = jrr.find_joints(smpl_tc, torch.from_numpy(z["betas"]).to(DEV), R[:, :1], R[:, 1:],
+                              J_shipped.to(DEV))
+    assert rel(out, torch.from_numpy(z["find_joints"])) < 1e-5
+    mp, pa = jrr.evaluate(out, torch.from_numpy(z["gt_mm"]).to(DEV))
+    assert abs(mp - float(z["mpjpe"])) < 1e-2 and abs(pa - float(z["pa_mpjpe"])) < 1e-2
+
+
+def test_critic_forward_matches_oracle(smpl_tc, jrr, oracle, critic_sd):
+    D = jrr.Discriminator()
+    D.load_state_dict(critic_sd)           # reference state_dict layout loads unchanged
+    D.bind(smpl_tc.native())
+    g = torch.Generator().manual_seed(3)
+    x6 = torch.randn(200, 24, 6, generator=g)
+    ref = oracle.discriminator_forward({k: v.double() for k, v in critic_sd.items()}, x6.double())
+    out = D(x6.to(DEV))
+    assert out.shape == (200, 25, 1)
+    assert (out.cpu().double() - ref).abs().max().item() < 2e-6
+    z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "ref_utils_golden.npz"))
+    out = D(torch.from_numpy(z["x6"]).to(DEV))
+    assert (out.cpu() - torch.from_numpy(z["critic_scores"])).abs().max().item() < 2e-6
+
+
+# ------------------------------------------------------------------ the fused refinement step
+def _oracle_refine(oracle, osmpl, J, critic_sd, fr, iters, **kw):
+    return oracle.refine(osmpl, J, critic_sd, fr["x6"], fr["betas"], fr["gt_mm"], iters=iters, **kw)
+
+
+@pytest.mark.parametrize("which", ["shipped", "dense"])
+def test_refine_single_step_gradients(which, smpl_tc, jrr, oracle, osmpl64, critic_sd, J_shipped, J_dense):
+    """After ONE Adam step from zero state the update is -lr*g/(|g|+eps'): compare the
+    implied per-parameter direction with the fp64 oracle's, and the losses."""
+    J = J_shipped if which == "shipped" else J_dense
+    fr = make_frames(jrr, oracle, oracle.OracleSMPL(jrr.synthetic.make_smpl_model(0)), J, 40, 21)
+    sd64 = {k: v.double() for k, v in critic_sd.items()}
+    x6 = fr["x6"].double().requires_grad_(True)
+    be = fr["betas"].double().requires_grad_(True)
+    total, jl, pl, _ = oracle.refine_loss(osmpl64, J.double(), sd64, x6, be, fr["gt_mm"].double())
+    total.backward()
+    ref = jrr.PoseRefiner(smpl_tc, J, critic_sd, use_graph=False)
+    st = ref._buffers(40)
+    st["x6"].copy_(fr["x6"]); st["betas"].copy_(fr["betas"]); st["gt"].copy_(fr["gt_mm"])
+    ref._run_chunk(st, 1, 40)
+    torch.cuda.synchronize()
+    loss = st["loss"].cpu().double()
+    assert abs(loss[1] - jl.item()) / jl.item() < 1e-5
+    assert abs(loss[2] - pl.item()) / pl.item() < 1e-5
+    assert abs(loss[0] - total.item()) / total.item() < 1e-5
+    # Adam's first step: m_hat = g, v_hat = g^2  ->  delta = -lr * g / (|g| + eps)
+    for name, g in (("x6", x6.grad), ("betas", be.grad)):
+        exp = -1e-2 * g / (g.abs() + 1e-8)
+        got = (st[name].cpu().double() - fr[name].double())
+        big = g.abs() > 1e-6          # where the direction is well defined
+        assert (got[big] - exp[big]).abs().max().item() < 1e-5, name
+        # recover the gradient itself from m (first moment = 0.1*g after one step)
+    m = st["m"].cpu().double() * 10
+    gall = torch.cat([x6.grad.reshape(40, 144), be.grad], dim=1)
+    err = (m - gall).abs().max().item() / gall.abs().max().item()
+    print(f"[{which}] gradient rel err vs fp64 oracle: {err:.2e}")
+    assert err < 1e-4
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_refine_100_iterations_mpjpe(use_graph, smpl_tc, jrr, oracle, osmpl32, critic_sd, J_shipped, frames64):
+    """64 frames x 100 Adam iterations: refined MPJPE within 0.01 mm of the oracle's."""
+    fr = frames64
+    x6o, bo, hist = _oracle_refine(oracle, osmpl32, J_shipped, critic_sd, fr, 100)
+    Ro = oracle.rot6d_to_rotmat(x6o.reshape(-1, 6)).view(-1, 24, 3, 3)
+    mp_o, pa_o = oracle.evaluate(oracle.find_joints(osmpl32, bo, Ro[:, :1], Ro[:, 1:], J_shipped), fr["gt_mm"])
+    ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, use_graph=use_graph)
+    x6 = fr["x6"].to(DEV).clone()
+    be = fr["betas"].to(DEV).clone()
+    loss = ref.refine(x6, be, fr["gt_mm"].to(DEV), iters=100)
+    Rg = jrr.rot6d_to_rotmat(x6.reshape(-1, 6)).view(-1, 24, 3, 3)
+    with torch.no_grad():
+        pred = jrr.find_joints(smpl_tc, be, Rg[:, :1], Rg[:, 1:], J_shipped.to(DEV))
+    mp_g, pa_g = jrr.evaluate(pred, fr["gt_mm"].to(DEV))
+    R0 = oracle.rot6d_to_rotmat(fr["x6"].reshape(-1, 6)).view(-1, 24, 3, 3)
+    mp_0, _ = oracle.evaluate(oracle.find_joints(osmpl32, fr["betas"], R0[:, :1], R0[:, 1:], J_shipped), fr["gt_mm"])
+    print(f"MPJPE initial {mp_0:.3f} mm -> oracle {mp_o:.4f} / cuda {mp_g:.4f} mm; PA {pa_o:.4f} / {pa_g:.4f}; "
+          f"final loss oracle {hist[-1][0]:.5f} cuda {loss[0].item():.5f}; "
+          f"max |dx6| {(x6.cpu() - x6o).abs().max().item():.2e}")
+    assert mp_g < mp_0
+    assert abs(mp_g - mp_o) < 0.01
+    assert abs(pa_g - pa_o) < 0.01
+
+
+def test_refine_shard_equals_full_batch(smpl_tc, jrr, critic_sd, J_shipped, frames64):
+    """Two shards with logical_batch = full batch reproduce the full-batch trajectory
+    bit for bit (frames are independent; only the mean divisors couple them)."""
+    fr = frames64
+    ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, use_graph=False)
+    gt = fr["gt_mm"].to(DEV)
+    xa, ba = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+    ref.refine(xa, ba, gt, iters=5)
+    xb, bb = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+    for lo, hi in ((0, 24), (24, 64)):
+        ref.refine(xb[lo:hi], bb[lo:hi], gt[lo:hi], iters=5, logical_batch=64)
+    assert torch.equal(xa, xb) and torch.equal(ba, bb)
+
+
+# ------------------------------------------------------------------ regressor refit
+@pytest.mark.parametrize("which", ["shipped", "dense"])
+def test_regressor_refit_matches_oracle(which, smpl_tc, jrr, oracle, osmpl32, osmpl64, J_shipped, J_dense, frames64):
+    J = J_shipped if which == "shipped" else J_dense
+    fr = frames64
+    refit = jrr.RegressorRefit(smpl_tc, J, lr=1e-2, chunk=48)      # ragged chunks: 48 + 16
+    opt = oracle.RegressorAdam(J.double(), lr=1e-2)
+    x6, be, gt = fr["x6"].to(DEV), fr["betas"].to(DEV), fr["gt_mm"].to(DEV)
+    for it in range(3):
+        g64, l64 = oracle.regressor_grad(osmpl64, opt.J.detach(), fr["x6"].double(), fr["betas"].double(),
+                                         fr["gt_mm"].double())
+        Jo = opt.step(g64)
+        loss = refit.step(x6, be, gt)
+        torch.cuda.synchronize()
+        assert abs(loss.item() - l64) / l64 < 1e-4
+        d = (refit.J_regressor.cpu().double() - Jo).abs().max().item()
+        print(f"[{which}] refit step {it}: loss {loss.item():.6e} (oracle {l64:.6e}); max |dJ| {d:.2e}")
+        assert d < 1e-4
+    # zero entries of the raw regressor never move (relu'(<=0) = 0)
+    assert torch.equal(refit.J_regressor.cpu()[J <= 0], J[J <= 0])
+
+
+def test_artefact_round_trip(tmp_path, jrr, J_shipped):
+    """A tensor saved the way the reference artefact was (cuda-tagged, requires_grad,
+    column-major) loads unchanged."""
+    t = J_shipped.to(DEV).t().contiguous().t().requires_grad_(True)
+    assert t.stride() == (1, 17)
+    p = tmp_path / "retrained_J_Regressor.pt"
+    torch.save(t, p)
+    back = jrr.load_j_regressor(str(p), DEV)
+    assert back.is_contiguous() and not back.requires_grad and torch.equal(back.cpu(), J_shipped)
