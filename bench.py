@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark: refine-step poses/sec (SMPL fwd + 17x6890 J-regressor + loss + analytic
+bwd + Adam) on config C2 of BASELINE.json -- 4096 synthetic frames per GPU, one "step" = one
+Adam iteration of the refinement loop over the whole batch (optimize.py:220-265).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); frames shard with no data-path
+collective (weak scaling: every rank refines its own 4096 frames).  Rank 0 prints ONE JSON
+line.  `--impl reference` times the CPU oracle port of the reference path on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "refine_step_poses_per_sec"
+UNIT = "poses/s"
+FRAMES = 4096
+WORKLOAD = ("C2: optimize.py pose refinement, 4096 synthetic frames/GPU x Adam iterations, "
+            "loss 10000*joint_MSE + 10*pose_critic_MSE, random-init SMPL (6890 v, 24 j, 10 betas, 207 pose dims)")
+
+# algorithmic work per pose-step ("useful-minimum" formulation)
+F_POSE_BLEND = 2 * 207 * 20670          # pose blend, one direction
+F_SHAPE_BLEND = 2 * 10 * 20670
+F_TEMPLATE = 20670
+F_CRITIC = 3_731_968                    # one direction
+F_USEFUL = 28.5e6
+F_GEMM = 24.46e6                        # tensor-eligible (blend + critic, fwd + bwd)
+ALG_BYTES_PER_POSE_STEP = 3900
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"],
+                "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_problem(jrr, smpl, J, n, seed, dev):
+    """Synthetic frames; GT joints come from the CUDA path itself."""
+    import torch
+    inp = jrr.synthetic.make_pose_inputs(n, seed)
+    t = {k: torch.from_numpy(v) for k, v in inp.items()}
+    R = t["true_rotmat"].to(dev)
+    with torch.no_grad():
+        pred = jrr.find_joints(smpl, t["true_betas"].to(dev), R[:, :1], R[:, 1:], J.to(dev))
+    gt = (1000 * jrr.move_pelvis(pred)).cpu() + t["gt_noise"]
+    return t["x6"].contiguous(), t["betas"].contiguous(), gt.contiguous()
+
+
+def cpu_reference_rate(n_frames, iters, warm, seed=0):
+    """The oracle port of the reference path (torch CPU, all host threads): pose-steps/s."""
+    import torch
+    import jrr_b200 as jrr
+    from oracle import jrr_oracle as O
+    from conftest import shipped_regressor
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = jrr.synthetic.make_smpl_model(0)
+    osmpl = O.OracleSMPL(model)
+    J = shipped_regressor()
+    sd = O.make_critic_state_dict(0)
+    inp = jrr.synthetic.make_pose_inputs(n_frames, seed)
+    t = {k: torch.from_numpy(v) for k, v in inp.items()}
+    gt = O.make_gt(osmpl, J, t["true_rotmat"], t["true_betas"], t["gt_noise"])
+    x6 = t["x6"].clone().requires_grad_(True)
+    be = t["betas"].clone().requires_grad_(True)
+    opt = torch.optim.Adam([x6, be], lr=1e-2)
+
+    def step():
+        total, _, _, _ = O.refine_loss(osmpl, J, sd, x6, be, gt)
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        step()
+    dt = time.perf_counter() - t0
+    return n_frames * iters / dt, dt / iters * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 512
+    rate, ms, cores = cpu_reference_rate(n, args.steps, args.warmup)
+    sample = f"{n} of the {FRAMES} frames per step, {args.steps} steps, torch {cores} threads, fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": n},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--regressor", default="dense", choices=["dense", "shipped"],
+                    help="dense 17x6890 (headline: the full reduction) or the shipped sparse artefact")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-impl", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import jrr_b200 as jrr
+    from conftest import shipped_regressor
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = args.steps
+    B = args.frames
+
+    # identical model / regressor / critic on every rank; frames seeded per rank
+    model = jrr.synthetic.make_smpl_model(0)
+    smpl = jrr.SMPL(model_dict=model, create_transl=False, gemm_impl=args.gemm_impl).to(dev)
+    J = torch.from_numpy(jrr.synthetic.make_dense_regressor(0)) if args.regressor == "dense" else shipped_regressor()
+    torch.manual_seed(0)
+    critic = jrr.Discriminator()                      # default init, frozen
+    sd = critic.state_dict()
+    refiner = jrr.PoseRefiner(smpl, J, sd, lr=1e-2, w_joint=10000.0, w_pose=10.0, chunk=B, use_graph=True)
+    x6_h, be_h, gt_h = make_problem(jrr, smpl, J, B, seed=rank, dev=dev)
+    x6_pin, be_pin, gt_pin = x6_h.pin_memory(), be_h.pin_memory(), gt_h.pin_memory()
+
+    # ---------------------------------------------------------------- device-resident timing
+    st = refiner._buffers(B)
+    st["x6"].copy_(x6_pin); st["betas"].copy_(be_pin); st["gt"].copy_(gt_pin)
+    st["m"].zero_(); st["v"].zero_(); st["t"].zero_()
+    refiner._run_chunk(st, W, B)                      # warm-up (captures the CUDA graph)
+    graph = st["graph"]
+    st["x6"].copy_(x6_pin); st["betas"].copy_(be_pin)
+    st["m"].zero_(); st["v"].zero_(); st["t"].zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(K):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_total = t_ms.item()
+    value = world * B * K / (ms_total * 1e-3)
+
+    # refined-pose quality of this run (K iterations from the initial estimate)
+    with torch.no_grad():
+        Rg = jrr.rot6d_to_rotmat(st["x6"].reshape(-1, 6)).view(-1, 24, 3, 3)
+        pred = jrr.find_joints(smpl, st["betas"], Rg[:, :1], Rg[:, 1:], J.to(dev))
+        mpjpe, pampjpe = jrr.evaluate(pred, st["gt"])
+        R0 = jrr.rot6d_to_rotmat(x6_h.to(dev).reshape(-1, 6)).view(-1, 24, 3, 3)
+        mp0, _ = jrr.evaluate(jrr.find_joints(smpl, be_h.to(dev), R0[:, :1], R0[:, 1:], J.to(dev)), st["gt"])
+    refiner.set_regressor(J)
+
+    # ---------------------------------------------------------------- end to end (host buffers)
+    loss_pin = torch.zeros(K, 3).pin_memory()
+    out_x6, out_be = torch.empty_like(x6_pin).pin_memory(), torch.empty_like(be_pin).pin_memory()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    st["x6"].copy_(x6_pin, non_blocking=True)
+    st["betas"].copy_(be_pin, non_blocking=True)
+    st["gt"].copy_(gt_pin, non_blocking=True)
+    st["m"].zero_(); st["v"].zero_(); st["t"].zero_()
+    for i in range(K):
+        graph.replay()
+        loss_pin[i].copy_(st["loss"], non_blocking=True)
+    out_x6.copy_(st["x6"], non_blocking=True)
+    out_be.copy_(st["betas"], non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (t_ms.item() * 1e-3)
+    h2d = (x6_pin.numel() + be_pin.numel() + gt_pin.numel()) * 4
+    d2h = (out_x6.numel() + out_be.numel()) * 4
+
+    # ---------------------------------------------------------------- per-kernel timing / roofline
+    P = 5
+    acc = {}
+    st["x6"].copy_(x6_pin); st["betas"].copy_(be_pin)
+    st["m"].zero_(); st["v"].zero_(); st["t"].zero_()
+    for i in range(P + 2):
+        ms = refiner.native.refine_step_profiled(st["x6"], st["betas"], st["gt"], st["m"], st["v"], st["t"],
+                                                 refiner.lr, refiner.w_joint, refiner.w_pose, logical_batch=B,
+                                                 loss_out=st["loss"])
+        if i >= 2:
+            for k, v in ms.items():
+                acc[k] = acc.get(k, 0.0) + v / P
+    pk = peaks()
+    BP = (B + 127) // 128 * 128
+    tf32_peak = pk["bf16_sustained"] / 2           # dense TF32 = half the bf16 rate; kernels timed inside a long step
+    kern = []
+    for name, ms in acc.items():
+        if ms <= 0:
+            continue
+        e = {"name": name, "ms": round(ms, 4)}
+        if name == "blend_gemm_fwd":
+            fl = 3 * 2.0 * B * 20670 * 218
+            e.update(bound="tensor", achieved=fl / (ms * 1e-3) / 1e12, peak=tf32_peak, unit="TFLOP/s")
+        elif name == "blend_gemm_bwd":
+            fl = 3 * 2.0 * B * 20670 * 217
+            e.update(bound="tensor", achieved=fl / (ms * 1e-3) / 1e12, peak=tf32_peak, unit="TFLOP/s")
+        elif name in ("critic_gemm_fwd", "critic_gemm_bwd"):
+            fl = 3 * 2.0 * B * (768 * 1024 + 1024 * 1024)
+            e.update(bound="tensor", achieved=fl / (ms * 1e-3) / 1e12, peak=tf32_peak, unit="TFLOP/s")
+        elif name == "skin_fwd":
+            by = 4.0 * B * (20670 + 288 + 51)        # read vp + transforms, write 51 partial sums
+            e.update(bound="hbm", achieved=by / (ms * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s")
+        elif name == "skin_bwd":
+            by = 4.0 * B * (20670 + 288 + 51 + 2 * 20670 + 288)   # + write dvp (hi/lo) and dA
+            e.update(bound="hbm", achieved=by / (ms * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s")
+        if "achieved" in e:
+            e["frac"] = e["achieved"] / e["peak"]
+            e["achieved"] = round(e["achieved"], 2)
+            e["frac"] = round(e["frac"], 4)
+        kern.append(e)
+    kern.sort(key=lambda e: -e["ms"])
+    step_ms_prof = sum(e["ms"] for e in kern)
+    dom = next((e for e in kern if "achieved" in e), None)
+    roofline = None
+    if dom is not None:
+        roofline = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
+                    "frac": dom["frac"], "traffic": None, "kernel": dom["name"],
+                    "share_of_step": round(dom["ms"] / step_ms_prof, 3),
+                    "peak_source": pk["source"] + (" bf16_sustained/2 (dense TF32)" if dom["bound"] == "tensor" else " hbm copy")}
+    pose_steps_per_s = value / world
+    whole = {"tensor_frac_3xtf32": round(3 * F_GEMM * pose_steps_per_s / (tf32_peak * 1e12), 4),
+             "hbm_frac_algorithmic": round(ALG_BYTES_PER_POSE_STEP * pose_steps_per_s / (pk["hbm_gbs"] * 1e9), 6),
+             "useful_tflops": round(F_USEFUL * pose_steps_per_s / 1e12, 2)}
+
+    # ---------------------------------------------------------------- regressor refit (C4), untimed extra
+    refit = jrr.RegressorRefit(smpl, J, lr=1e-2, chunk=B)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for rep in range(2):
+        refit.G.zero_(); refit.loss.zero_()
+        torch.cuda.synchronize()
+        ev[0].record()
+        refit.accumulate(st["x6"], st["betas"], st["gt"], logical_batch=world * B)
+        ev[1].record()
+        if world > 1:
+            dist.all_reduce(refit.G); dist.all_reduce(refit.loss)
+        ev[2].record()
+        refit.native.regressor_apply(refit.J, refit.mask, refit.G, refit.m, refit.v, refit.t, refit.lr)
+        ev[3].record()
+        torch.cuda.synchronize()
+    refit_ms = {"accumulate": round(ev[0].elapsed_time(ev[1]), 3), "allreduce": round(ev[1].elapsed_time(ev[2]), 3),
+                "apply": round(ev[2].elapsed_time(ev[3]), 3), "allreduce_bytes": 17 * 6890 * 4 + 4}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, ms_cpu, cores = cpu_reference_rate(1024, 6, 1)
+        cpu = {"value": round(rate, 1), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"1024 of the {B} frames x 6 Adam iterations (1 warm-up), oracle port, torch {cores} threads, fp32"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": B, "regressor": args.regressor,
+                       "parallelism": f"frame-shard x{world}, no data-path collective",
+                       "l2": "per-step working set ~1.2 GB of intermediates per GPU, larger than the 126 MB L2",
+                       "graph": "one CUDA graph per step, replayed", "gemm": "tcgen05 3xTF32" if args.gemm_impl == 0 else "simt"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K + 12,
+                    "note": "one user call: pinned-host x6/betas/gt -> device, K steps (loss read back every step), refined x6/betas -> pinned host"},
+            "gpu_launches": refiner.launches_per_step * K,
+            "roofline": roofline, "kernels": kern, "whole_step": whole,
+            "quality": {"mpjpe_initial_mm": round(float(mp0), 3), "mpjpe_after_mm": round(float(mpjpe), 3),
+                        "pa_mpjpe_after_mm": round(float(pampjpe), 3), "iterations": K},
+            "refit_ms": refit_ms,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

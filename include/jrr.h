@@ -156,6 +156,17 @@ int jrr_regressor_apply(JrrModel* model, float* J17_raw, const float* mask, cons
                         float* adam_m, float* adam_v, int32_t* step_count, float lr,
                         void* stream);
 
+/* Diagnostic (SYNCHRONISES the stream, not graph-capturable): jrr_refine_step with a CUDA
+ * event recorded on `stream` between its kernel groups; ms_out_host[JRR_STEP_KERNELS] (HOST)
+ * receives each group's device time in milliseconds, names from jrr_step_kernel_name().
+ * bench.py uses it for the per-kernel roofline. */
+#define JRR_STEP_KERNELS 14
+int jrr_refine_step_profiled(JrrModel* model, int64_t B, int64_t B_logical, float* x6, float* betas,
+                             const float* gt_mm, float* adam_m, float* adam_v, int32_t* step_count,
+                             float lr, float w_joint, float w_pose, float* loss_out, void* workspace,
+                             size_t workspace_bytes, void* stream, float* ms_out_host);
+const char* jrr_step_kernel_name(int i);
+
 /* Diagnostic: the 3xTF32 GEMM on its own, C[M,N] (row-major) = A[M,K] . B[N,K]^T with fp32
  * inputs that are split into tf32 hi/lo pairs inside the call (scratch = 2*(M+N)*K floats,
  * device).  impl 0 = tcgen05 kernel, 1 = SIMT validation kernel.  M%128 == 0, K%32 == 0,

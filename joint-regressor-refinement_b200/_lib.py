@@ -10,13 +10,14 @@ LIB_PATH = os.path.join(HERE, "libjrr.so")
 
 POSE_ROTMAT, POSE_AXIS_ANGLE, POSE_ROT6D = 0, 1, 2
 CRITIC_PARAMS = 1840153
+STEP_KERNELS = 14
 
 EXPORTS = [
     "jrr_last_error", "jrr_abi_version", "jrr_model_create", "jrr_model_destroy",
     "jrr_set_regressor", "jrr_critic_load", "jrr_workspace_bytes", "jrr_smpl_forward",
     "jrr_smpl_backward", "jrr_find_joints", "jrr_critic_forward", "jrr_refine_step",
     "jrr_regressor_grad_accumulate", "jrr_regressor_apply", "jrr_last_launch_count",
-    "jrr_debug_gemm",
+    "jrr_debug_gemm", "jrr_refine_step_profiled", "jrr_step_kernel_name",
 ]
 
 
@@ -62,6 +63,9 @@ def lib():
     L.jrr_regressor_grad_accumulate.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, sz, vp]
     L.jrr_regressor_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, f32, vp]
     L.jrr_last_launch_count.restype = i64
+    L.jrr_refine_step_profiled.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, sz, vp, vp]
+    L.jrr_step_kernel_name.argtypes = [C.c_int]
+    L.jrr_step_kernel_name.restype = C.c_char_p
     L.jrr_debug_gemm.argtypes = [vp, C.c_int, i64, i64, i64, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -63,17 +63,21 @@ static int check_common(const JrrModel* m, int64_t B, const void* ws, size_t ws_
 }
 
 // pose decode + chain, then the augmented blend GEMM: feat[BP,224] x Pt[20736,224]^T -> vpT
-static int forward_common(const JrrModel* m, const Workspace& w, const float* betas, const float* pose,
-                          int kind, bool want_Jp, cudaStream_t st) {
-  int rc = launch_pose_fwd(m, w.B, w.BP, betas, pose, kind, w.AT, w.feat_hi, w.feat_lo,
-                           want_Jp ? w.Jp : nullptr, st);
-  if (rc) return rc;
+static int blend_forward_gemm(const JrrModel* m, const Workspace& w, cudaStream_t st) {
   GemmDesc g{};
   g.A_hi = w.feat_hi; g.A_lo = w.feat_lo; g.lda = KA;
   g.B_hi = m->Pt_hi; g.B_lo = m->Pt_lo; g.ldb = KA;
   g.M = w.BP; g.N = NP; g.K = KA; g.ksplit = 1; g.epi = EPI_STORE_T;
   g.out0 = w.vpT; g.ldo = w.BP;
   return launch_gemm(m, g, st);
+}
+
+static int forward_common(const JrrModel* m, const Workspace& w, const float* betas, const float* pose,
+                          int kind, bool want_Jp, cudaStream_t st) {
+  int rc = launch_pose_fwd(m, w.B, w.BP, betas, pose, kind, w.AT, w.feat_hi, w.feat_lo,
+                           want_Jp ? w.Jp : nullptr, st);
+  if (rc) return rc;
+  return blend_forward_gemm(m, w, st);
 }
 
 // dfeat[s][BP,224] = dvp[BP, 20736 (split s)] x P[224, 20736]^T
@@ -160,10 +164,17 @@ extern "C" int jrr_critic_forward(JrrModel* m, int64_t B, const float* rot6d, fl
   return launch_critic_head(m, w, B, 0.f, scores_out, false, st);
 }
 
-extern "C" int jrr_refine_step(JrrModel* m, int64_t B, int64_t B_logical, float* x6, float* betas,
-                               const float* gt_mm, float* adam_m, float* adam_v, int32_t* step_count,
-                               float lr, float w_joint, float w_pose, float* loss_out, void* ws,
-                               size_t ws_bytes, void* stream) {
+// Kernel groups of one refinement step (order of execution); jrr_refine_step_profiled
+// reports one duration per group.
+static const char* const kStepKernelNames[JRR_STEP_KERNELS] = {
+    "pose_fwd", "blend_gemm_fwd", "skin_fwd", "loss_seed", "skin_bwd", "dA_reduce", "blend_gemm_bwd",
+    "critic_pre", "critic_gemm_fwd", "critic_head", "critic_gemm_bwd", "critic_post", "loss_finish",
+    "pose_bwd_adam"};
+
+static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6, float* betas,
+                            const float* gt_mm, float* adam_m, float* adam_v, int32_t* step_count, float lr,
+                            float w_joint, float w_pose, float* loss_out, void* ws, size_t ws_bytes,
+                            cudaStream_t st, cudaEvent_t* ev) {
   Workspace w;
   if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
   if (!m->has_regressor) return fail(JRR_ERR_STATE, "jrr_set_regressor has not been called");
@@ -171,28 +182,82 @@ extern "C" int jrr_refine_step(JrrModel* m, int64_t B, int64_t B_logical, float*
   if (B_logical < B) return fail(JRR_ERR_INVALID, "B_logical must be >= B");
   const bool critic = w_pose != 0.f;
   if (critic && !m->has_critic) return fail(JRR_ERR_STATE, "w_pose != 0 but jrr_critic_load has not been called");
-  cudaStream_t st = (cudaStream_t)stream;
-  // forward: chain, blend, skinning fused with the 17x6890 regressor reduction
-  if (int rc = forward_common(m, w, betas, x6, JRR_POSE_ROT6D, false, st)) return rc;
+  int mark = 0;
+#define JRR_MARK()                                                      \
+  do {                                                                  \
+    if (ev) JRR_CUDA(cudaEventRecord(ev[mark], st));                    \
+    mark++;                                                             \
+  } while (0)
+  JRR_MARK();
+  // forward: chain | blend GEMM | skinning fused with the 17x6890 regressor reduction | loss seed
+  if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, x6, JRR_POSE_ROT6D, w.AT, w.feat_hi, w.feat_lo, nullptr, st)) return rc;
+  JRR_MARK();
+  if (int rc = blend_forward_gemm(m, w, st)) return rc;
+  JRR_MARK();
   if (int rc = launch_skin_fwd(m, w, nullptr, nullptr, true, st)) return rc;
+  JRR_MARK();
   if (int rc = launch_loss_seed(m, w, gt_mm, B_logical, w_joint, nullptr, st)) return rc;
-  // backward: regressor transpose seed, skinning, blend
+  JRR_MARK();
+  // backward: regressor-transpose seed + skinning | dA reduction | blend GEMM
   if (int rc = launch_skin_bwd(m, w, nullptr, true, false, st)) return rc;
+  JRR_MARK();
   if (int rc = launch_dA_reduce(m, w, st)) return rc;
+  JRR_MARK();
   if (int rc = blend_backward_gemm(m, w, st)) return rc;
+  JRR_MARK();
   // critic forward + input gradient
-  if (critic) {
-    if (int rc = launch_critic_pre(m, w, x6, st)) return rc;
-    if (int rc = critic_forward_gemms(m, w, st)) return rc;
-    if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, st)) return rc;
-    if (int rc = critic_backward_gemms(m, w, st)) return rc;
-    if (int rc = launch_critic_post(m, w, x6, st)) return rc;
-  }
+  if (critic) if (int rc = launch_critic_pre(m, w, x6, st)) return rc;
+  JRR_MARK();
+  if (critic) if (int rc = critic_forward_gemms(m, w, st)) return rc;
+  JRR_MARK();
+  if (critic) if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, st)) return rc;
+  JRR_MARK();
+  if (critic) if (int rc = critic_backward_gemms(m, w, st)) return rc;
+  JRR_MARK();
+  if (critic) if (int rc = launch_critic_post(m, w, x6, st)) return rc;
+  JRR_MARK();
   if (loss_out)
     if (int rc = launch_loss_finish(w, B_logical, w_joint, w_pose, critic, loss_out, nullptr, st)) return rc;
+  JRR_MARK();
   // chain backward + Adam
-  return launch_pose_bwd(m, w, betas, x6, JRR_POSE_ROT6D, false, critic, nullptr, nullptr, x6, betas,
-                         adam_m, adam_v, step_count, lr, st);
+  if (int rc = launch_pose_bwd(m, w, betas, x6, JRR_POSE_ROT6D, false, critic, nullptr, nullptr, x6, betas,
+                               adam_m, adam_v, step_count, lr, st)) return rc;
+  JRR_MARK();
+#undef JRR_MARK
+  return JRR_OK;
+}
+
+extern "C" int jrr_refine_step(JrrModel* m, int64_t B, int64_t B_logical, float* x6, float* betas,
+                               const float* gt_mm, float* adam_m, float* adam_v, int32_t* step_count,
+                               float lr, float w_joint, float w_pose, float* loss_out, void* ws,
+                               size_t ws_bytes, void* stream) {
+  return refine_step_impl(m, B, B_logical, x6, betas, gt_mm, adam_m, adam_v, step_count, lr, w_joint, w_pose,
+                          loss_out, ws, ws_bytes, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" const char* jrr_step_kernel_name(int i) {
+  return (i >= 0 && i < JRR_STEP_KERNELS) ? kStepKernelNames[i] : nullptr;
+}
+
+extern "C" int jrr_refine_step_profiled(JrrModel* m, int64_t B, int64_t B_logical, float* x6, float* betas,
+                                        const float* gt_mm, float* adam_m, float* adam_v,
+                                        int32_t* step_count, float lr, float w_joint, float w_pose,
+                                        float* loss_out, void* ws, size_t ws_bytes, void* stream,
+                                        float* ms_out_host) {
+  if (!ms_out_host) return fail(JRR_ERR_INVALID, "null ms_out_host");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t ev[JRR_STEP_KERNELS + 1];
+  for (int i = 0; i <= JRR_STEP_KERNELS; i++) JRR_CUDA(cudaEventCreate(&ev[i]));
+  int rc = refine_step_impl(m, B, B_logical, x6, betas, gt_mm, adam_m, adam_v, step_count, lr, w_joint, w_pose,
+                            loss_out, ws, ws_bytes, st, ev);
+  if (rc == JRR_OK) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(JRR_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (rc == JRR_OK)
+    for (int i = 0; i < JRR_STEP_KERNELS; i++) cudaEventElapsedTime(&ms_out_host[i], ev[i], ev[i + 1]);
+  for (int i = 0; i <= JRR_STEP_KERNELS; i++) cudaEventDestroy(ev[i]);
+  return rc;
 }
 
 extern "C" int jrr_regressor_grad_accumulate(JrrModel* m, int64_t B, int64_t B_logical, const float* x6,

@@ -74,7 +74,6 @@ class NativeModel:
         self.h = h
         self._ws = None
         self._ws_B = 0
-        self._reg_key = None
         self.launches = 0
 
     def __del__(self):
@@ -106,15 +105,6 @@ class NativeModel:
         m = _f32c(mask.detach(), "mask") if mask is not None else None
         with torch.cuda.device(self.device):
             check(self.L.jrr_set_regressor(self.h, _ptr(J), _ptr(m), _stream()), "jrr_set_regressor")
-        self._reg_key = None
-
-    def set_regressor_cached(self, J17_raw: torch.Tensor, mask=None):
-        """find_joints re-normalises on every call in the reference (utils.py:87-92); here the
-        normalised copy is refreshed only when the tensor (or its version) changed."""
-        key = (J17_raw.data_ptr(), J17_raw._version, None if mask is None else (mask.data_ptr(), mask._version))
-        if key != self._reg_key:
-            self.set_regressor(J17_raw, mask)
-            self._reg_key = key
 
     def load_critic(self, state_dict: dict):
         flat = flatten_critic_state_dict(state_dict).to(self.device)
@@ -188,6 +178,21 @@ class NativeModel:
                                          _ptr(loss_out), ws, wsz, _stream()), "jrr_refine_step")
         self._done()
 
+    def refine_step_profiled(self, x6, betas, gt_mm, adam_m, adam_v, step_count, lr, w_joint, w_pose,
+                             logical_batch=None, loss_out=None):
+        """refine_step with per-kernel-group CUDA-event timing -> {name: ms} (synchronises)."""
+        B = x6.shape[0]
+        LB = B if logical_batch is None else int(logical_batch)
+        ws, wsz = self.workspace(B)
+        ms = (C.c_float * _lib.STEP_KERNELS)()
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_refine_step_profiled(self.h, B, LB, _ptr(x6), _ptr(betas), _ptr(gt_mm),
+                                                  _ptr(adam_m), _ptr(adam_v), _ptr(step_count), lr, w_joint,
+                                                  w_pose, _ptr(loss_out), ws, wsz, _stream(), ms),
+                  "jrr_refine_step_profiled")
+        self._done()
+        return {self.L.jrr_step_kernel_name(i).decode(): float(ms[i]) for i in range(_lib.STEP_KERNELS)}
+
     def regressor_grad_accumulate(self, x6, betas, gt_mm, G_accum, loss_accum, logical_batch=None):
         B = x6.shape[0]
         LB = B if logical_batch is None else int(logical_batch)
@@ -205,7 +210,6 @@ class NativeModel:
                                              _ptr(adam_v), _ptr(step_count), lr, _stream()),
                   "jrr_regressor_apply")
         self._done()
-        self._reg_key = None
 
     # ------------------------------------------------------------------ diagnostics
     def debug_gemm(self, A, B, impl=0):

@@ -40,7 +40,9 @@ def find_joints(smpl, shape, orient, pose, J_regressor, mask=None, return_verts=
         pred = torch.matmul(Jn.to(verts.device)[None], verts)
         return (pred, verts) if return_verts else pred
     native = smpl.native()
-    native.set_regressor_cached(J_regressor.to(native.device), None if mask is None else mask.to(native.device))
+    # like the reference (utils.py:87-92) the regressor is re-normalised on every call: three
+    # tiny kernels; the refinement loop itself normalises once per regressor version
+    native.set_regressor(J_regressor.to(native.device), None if mask is None else mask.to(native.device))
     B = max(shape.shape[0], pose.shape[0])
     full = torch.cat([orient.reshape(-1, 1, 3, 3).expand(B, -1, -1, -1),
                       pose.reshape(-1, 23, 3, 3).expand(B, -1, -1, -1)], dim=1).reshape(B, 24, 9)

@@ -260,7 +260,7 @@ def refine(smpl, Jraw, critic_sd, x6, betas, gt_mm, iters=100, lr=1e-2, w_joint=
         opt.zero_grad()
         total.backward()
         opt.step()
-        hist.append((float(total), float(jl), float(pl)))
+        hist.append((total.item(), jl.item(), pl.item()))
     return x6.detach(), betas.detach(), hist
 
 

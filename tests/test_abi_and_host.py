@@ -1,0 +1,127 @@
+"""CPU-side checks: libjrr.so loads and exports every symbol include/jrr.h declares (no
+compute without a GPU), host-side helpers, and the multi-rank refit logic over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol(jrr):
+    hdr = open(os.path.join(ROOT, "include", "jrr.h")).read()
+    declared = set(re.findall(r"\b(jrr_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 16
+    L = ctypes.CDLL(jrr.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    from jrr_b200 import _lib
+    assert set(_lib.EXPORTS) == declared
+    assert _lib.lib().jrr_abi_version() == 1
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma(jrr):
+    sass = subprocess.run(["cuobjdump", "-sass", jrr.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+
+
+def test_argument_errors_surface_without_a_gpu(jrr):
+    from jrr_b200 import _lib
+    L = _lib.lib()
+    assert L.jrr_model_create(None, None) == 1
+    assert b"null" in L.jrr_last_error()
+    assert L.jrr_workspace_bytes(None, 10) == 0
+
+
+def test_no_cpu_fallback(jrr, model):
+    smpl = jrr.SMPL(model_dict=model)
+    with pytest.raises(jrr.JrrError):
+        smpl(betas=torch.zeros(1, 10), body_pose=torch.zeros(1, 69), global_orient=torch.zeros(1, 3))
+
+
+def test_smpl_module_interface(jrr, model):
+    smpl = jrr.SMPL(model_dict=model, batch_size=2)
+    names = dict(smpl.named_buffers())
+    for k, shape in (("v_template", (6890, 3)), ("shapedirs", (6890, 3, 10)), ("posedirs", (207, 20670)),
+                     ("J_regressor", (24, 6890)), ("lbs_weights", (6890, 24)), ("J_regressor_extra", (9, 6890)),
+                     ("parents", (24,))):
+        assert tuple(names[k].shape) == shape
+    assert smpl.parents[0] == -1 and smpl.joint_map.shape == (49,)
+    assert smpl.transl.shape == (2, 3) and smpl.betas.shape == (2, 10)
+    import inspect
+    params = list(inspect.signature(smpl.forward).parameters)
+    assert params[:3] == ["betas", "body_pose", "global_orient"]
+    assert jrr.SMPLOutput._fields[:2] == ("vertices", "joints")
+
+
+def test_shard_range_partitions_frames(jrr):
+    for n, w in ((312000, 8), (4096, 3), (7, 8)):
+        r = [jrr.shard_range(n, k, w) for k in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n
+        assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+
+
+def test_flatten_critic_order(jrr, critic_sd):
+    flat = jrr.flatten_critic_state_dict(critic_sd)
+    assert flat.numel() == 1840153
+    assert torch.equal(flat[:192], critic_sd["conv_operations.0.weight"].reshape(-1))
+    off = 192 + 32 + 1024 + 32
+    assert torch.equal(flat[off:off + 32], critic_sd["linears.0.weight"].reshape(-1))
+    assert flat[off + 32] == critic_sd["linears.0.bias"][0]
+    assert flat[-1] == critic_sd["linear_operations.4.bias"][0]
+
+
+def test_synthetic_inputs_are_deterministic(jrr):
+    a, b = jrr.synthetic.make_pose_inputs(5, 3), jrr.synthetic.make_pose_inputs(5, 3)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    m1, m2 = jrr.synthetic.make_smpl_model(0), jrr.synthetic.make_smpl_model(0)
+    assert all(np.array_equal(m1[k], m2[k]) for k in m1)
+    assert list(m1["parents"][:4]) == [-1, 0, 0, 0]
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import jrr_b200 as jrr
+from oracle import jrr_oracle as O
+from conftest import shipped_regressor, make_frames
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+model = jrr.synthetic.make_smpl_model(0)
+osmpl = O.OracleSMPL(model, torch.float64)
+J = shipped_regressor().double()
+fr = make_frames(jrr, O, O.OracleSMPL(model), shipped_regressor(), 10, 4)
+lo, hi = jrr.shard_range(10, rank, world)
+g, l = O.regressor_grad(osmpl, J, fr["x6"][lo:hi].double(), fr["betas"][lo:hi].double(),
+                        fr["gt_mm"][lo:hi].double(), logical_batch=10)
+l = torch.tensor([l], dtype=torch.float64)
+dist.all_reduce(g); dist.all_reduce(l)
+gf, lf = O.regressor_grad(osmpl, J, fr["x6"].double(), fr["betas"].double(), fr["gt_mm"].double())
+assert torch.allclose(g, gf, atol=1e-14), (g - gf).abs().max()
+assert abs(l.item() - lf) < 1e-14
+opt = O.RegressorAdam(J); Jn = opt.step(g)
+gathered = [torch.zeros_like(Jn) for _ in range(world)]
+dist.all_gather(gathered, Jn)
+assert all(torch.equal(gathered[0], x) for x in gathered)     # replicated optimiser stays in sync
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_refit_allreduce_gloo(tmp_path):
+    """world_size-2 gloo run of the refit data flow: shard -> accumulate with the GLOBAL
+    divisor -> all-reduce -> identical Adam step on every rank."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517", WORLD_SIZE="2",
+               OMP_NUM_THREADS="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
