@@ -22,9 +22,11 @@ constexpr int FEAT_BETA = 207;
 constexpr int FEAT_ONE = 217;
 constexpr int NH = 17;              // regressed joints
 constexpr int NACC = 51;            // 17*3
-constexpr int JH_STRIDE = 20;       // padded Jhat column record
-constexpr int VS = 256;             // packed vertices per skinning range (one CTA column)
-constexpr int NSPLIT = VP / VS;     // 27
+constexpr int JH_STRIDE = 20;       // padded Jhat column inside a vertex record
+constexpr int VS_F = 576;           // packed vertices per CTA range, forward skinning
+constexpr int NSPLIT = VP / VS_F;   // 12 regressor partial sums per pose
+constexpr int VS_B = 768;           // packed vertices per CTA range, backward skinning
+constexpr int NSPLIT_B = VP / VS_B; // 9
 constexpr int KSPLIT = 6;           // split-K of the backward blend GEMM (20736 = 6*3456)
 constexpr int NPARAM = 154;         // 144 rot6d + 10 betas per pose
 constexpr int MAXCH = 4;            // children per joint supported by the chain kernels
@@ -70,14 +72,17 @@ struct ChainTab {
 //   meta bit  25         first vertex of a range (slots are loaded without a flush)
 //   xptr/xcnt           slice of (source, coef) pairs: the joints49 sources (21 vertex picks,
 //                       9 extra-regressor rows) this vertex feeds (module backward)
+//   jh[0..16]           this vertex's column of the normalised 17x6890 regressor
 struct VtxRec {
   uint32_t meta;
   float w[4];
   int xptr;
   int xcnt;
   int pad;
+  float jh[JH_STRIDE];
 };
-static_assert(sizeof(VtxRec) == 32, "VtxRec is loaded as two uint4");
+static_assert(sizeof(VtxRec) == 112, "VtxRec tiles are staged as float4");
+constexpr int REC_WORDS = 28;
 constexpr int LOSS_PART_POSE = 4096;  // offset of the critic partials inside Workspace::loss_part
 constexpr int64_t MAX_POSES_PER_CALL = 262144;
 
@@ -100,20 +105,21 @@ struct JrrModel {
   float *P_hi = nullptr, *P_lo = nullptr;    // [KA][NP]  (N contiguous)  backward B operand
   float* J0 = nullptr;                       // [24][3]      J_regressor . v_template
   float* JS = nullptr;                       // [24][3][10]  J_regressor . shapedirs
-  jrr::VtxRec* vrec = nullptr;               // [VP]
+  jrr::VtxRec* vrec = nullptr;               // [VP]  forward ranges (VS_F)
+  jrr::VtxRec* vrec_b = nullptr;             // [VP]  backward ranges (VS_B): reload/first flags differ
+  int* perm = nullptr;                       // [VP] packed index -> original vertex id (-1 = padding)
   int* vx_src = nullptr;                     // joints49 sources per vertex (see VtxRec)
   float* vx_coef = nullptr;
   int n_flush = 0;                           // dA flush events per pose
   int* flush_ptr = nullptr;                  // [25] CSR joint -> flush ids
   int* flush_idx = nullptr;                  // [n_flush]
-  int* range_flush_base = nullptr;           // [NSPLIT]
+  int* range_flush_base = nullptr;           // [NSPLIT_B]
   // joints49 path
   jrr::Csr extra;                            // [9] rows over original vertex ids
   int* picks = nullptr;                      // [21]
   int* joint_map = nullptr;                  // [49]
   // regressor (normalised), refreshed by jrr_set_regressor / jrr_regressor_apply
   float* Jhat = nullptr;                     // [17][V]   original vertex order
-  float* Jhat_cols = nullptr;                // [VP][20]  packed order, zero padded
   float* rowsum = nullptr;                   // [17]
   float* regdot = nullptr;                   // [17] scratch of jrr_regressor_apply
   bool has_regressor = false;

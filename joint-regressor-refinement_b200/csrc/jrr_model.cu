@@ -80,24 +80,31 @@ __global__ void reg_rowsum_kernel(const float* __restrict__ J, const float* __re
 }
 
 __global__ void reg_normalise_kernel(const float* __restrict__ J, const float* __restrict__ mask,
-                                     const float* __restrict__ rowsum, float* __restrict__ Jhat,
-                                     float* __restrict__ Jhat_cols) {
+                                     const float* __restrict__ rowsum, float* __restrict__ Jhat) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= NH * V) return;
-  const int j = idx / V, v = idx % V;
+  const int j = idx / V;
   float x = J[idx] * (mask ? mask[idx] : 1.f);
-  float r = fmaxf(x, 0.f) / rowsum[j];
-  Jhat[idx] = r;
-  Jhat_cols[v * JH_STRIDE + j] = r;
+  Jhat[idx] = fmaxf(x, 0.f) / rowsum[j];
 }
 
-__global__ void reg_flags_kernel(const float* __restrict__ Jhat_cols, VtxRec* __restrict__ vrec) {
+// scatter the normalised columns into the packed vertex records (both range layouts) and set
+// the "column is non-zero" flag
+__global__ void reg_records_kernel(const float* __restrict__ Jhat, const int* __restrict__ perm,
+                                   VtxRec* __restrict__ vrec, VtxRec* __restrict__ vrec_b) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= VP) return;
+  const int v = perm[i];
   bool any = false;
-  for (int j = 0; j < NH; j++) any |= (Jhat_cols[i * JH_STRIDE + j] != 0.f);
-  uint32_t meta = vrec[i].meta & ~(1u << 24);
-  vrec[i].meta = meta | (any ? (1u << 24) : 0u);
+  for (int j = 0; j < JH_STRIDE; j++) {
+    const float r = (v >= 0 && j < NH) ? Jhat[j * V + v] : 0.f;
+    any |= (r != 0.f);
+    vrec[i].jh[j] = r;
+    vrec_b[i].jh[j] = r;
+  }
+  const uint32_t f = any ? (1u << 24) : 0u;
+  vrec[i].meta = (vrec[i].meta & ~(1u << 24)) | f;
+  vrec_b[i].meta = (vrec_b[i].meta & ~(1u << 24)) | f;
 }
 
 // G[j][i] += sum_b sum_c gT[3j+c][b] * vT[3i+c][b]; one warp per vertex, g tile in smem
@@ -105,10 +112,11 @@ constexpr int RA_WARPS = 8;
 constexpr int RA_BCH = 128;
 __global__ void __launch_bounds__(RA_WARPS * 32)
 reg_accumulate_kernel(const float* __restrict__ gT, const float* __restrict__ vT, int64_t B,
-                      int64_t BP, float* __restrict__ G) {
+                      int64_t BP, const int* __restrict__ perm, float* __restrict__ G) {
   __shared__ float sg[NACC][RA_BCH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * RA_WARPS + warp;
+  const int vorig = i < VP ? perm[i] : -1;
   float acc[NH];
 #pragma unroll
   for (int j = 0; j < NH; j++) acc[j] = 0.f;
@@ -119,7 +127,7 @@ reg_accumulate_kernel(const float* __restrict__ gT, const float* __restrict__ vT
       sg[a][bb] = (bc + bb < B) ? gT[(int64_t)a * BP + bc + bb] : 0.f;
     }
     __syncthreads();
-    if (i < V) {
+    if (vorig >= 0) {
 #pragma unroll
       for (int q = 0; q < RA_BCH / 32; q++) {
         const int bb = lane + 32 * q;
@@ -132,12 +140,12 @@ reg_accumulate_kernel(const float* __restrict__ gT, const float* __restrict__ vT
       }
     }
   }
-  if (i < V) {
+  if (vorig >= 0) {
 #pragma unroll
     for (int j = 0; j < NH; j++) {
       float a = acc[j];
       for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0) G[j * V + i] += a;
+      if (lane == 0) G[j * V + vorig] += a;
     }
   }
 }
@@ -183,9 +191,9 @@ __global__ void bump_kernel(int32_t* c) { *c += 1; }
 int launch_regressor_normalise(JrrModel* m, const float* Jraw, const float* mask, cudaStream_t st) {
   reg_rowsum_kernel<<<NH, 256, 0, st>>>(Jraw, mask, m->rowsum);
   JRR_LAUNCH_CHECK();
-  reg_normalise_kernel<<<(NH * V + 255) / 256, 256, 0, st>>>(Jraw, mask, m->rowsum, m->Jhat, m->Jhat_cols);
+  reg_normalise_kernel<<<(NH * V + 255) / 256, 256, 0, st>>>(Jraw, mask, m->rowsum, m->Jhat);
   JRR_LAUNCH_CHECK();
-  reg_flags_kernel<<<(VP + 255) / 256, 256, 0, st>>>(m->Jhat_cols, m->vrec);
+  reg_records_kernel<<<(VP + 255) / 256, 256, 0, st>>>(m->Jhat, m->perm, m->vrec, m->vrec_b);
   JRR_LAUNCH_CHECK();
   m->has_regressor = true;
   return JRR_OK;
@@ -193,8 +201,7 @@ int launch_regressor_normalise(JrrModel* m, const float* Jraw, const float* mask
 
 int launch_regressor_accumulate(const JrrModel* m, const Workspace& w, const float* vT,
                                 float* G_accum, cudaStream_t st) {
-  (void)m;
-  reg_accumulate_kernel<<<(V + RA_WARPS - 1) / RA_WARPS, RA_WARPS * 32, 0, st>>>(w.gT, vT, w.B, w.BP, G_accum);
+  reg_accumulate_kernel<<<(VP + RA_WARPS - 1) / RA_WARPS, RA_WARPS * 32, 0, st>>>(w.gT, vT, w.B, w.BP, m->perm, G_accum);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
@@ -283,16 +290,48 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
     }
   }
 
-  // ---- augmented blend matrix
+  // ---- vertex permutation: vertices that share a joint set become neighbours, so a
+  // skinning thread re-fetches joint transforms (and flushes dA accumulators) only a few
+  // hundred times per pose instead of at almost every vertex
+  std::vector<int> perm(VP, -1);
+  {
+    std::vector<uint32_t> key(V);
+    for (int v = 0; v < V; v++) {
+      uint32_t k = 0;
+      int n = 0;
+      for (int j = 0; j < NJ; j++)
+        if (d->lbs_weights_host[(size_t)v * NJ + j] != 0.f) { k |= 1u << j; n++; }
+      if (n > 4) return fail(JRR_ERR_INVALID, "lbs_weights row with more than 4 non-zeros is not supported by this build");
+      key[v] = k;
+    }
+    std::vector<int> order(V);
+    for (int v = 0; v < V; v++) order[v] = v;
+    auto lowest_first = [](uint32_t a, uint32_t b) {
+      // compare joint sets as ascending lists: the set holding the smaller differing joint first
+      const uint32_t diff = a ^ b;
+      const uint32_t low = diff & (~diff + 1u);
+      return (a & low) != 0;
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      if (key[x] == key[y]) return false;
+      return lowest_first(key[x], key[y]);
+    });
+    for (int i = 0; i < V; i++) perm[i] = order[i];
+    if (int rc = upload(m, &m->perm, perm)) return rc;
+  }
+
+  // ---- augmented blend matrix (columns in packed vertex order)
   {
     std::vector<float> P((size_t)KA * NP, 0.f), Pt((size_t)NP * KA, 0.f), hi, lo;
-    for (int v = 0; v < V; v++)
+    for (int i = 0; i < V; i++) {
+      const int v = perm[i];
       for (int c = 0; c < 3; c++) {
-        const size_t n = (size_t)3 * v + c;
+        const size_t n = (size_t)3 * i + c;
         for (int k = 0; k < NF; k++) P[(size_t)k * NP + n] = d->posedirs_host[(size_t)k * (3 * V) + 3 * v + c];
         for (int l = 0; l < NB; l++) P[(size_t)(FEAT_BETA + l) * NP + n] = d->shapedirs_host[((size_t)v * 3 + c) * NB + l];
         P[(size_t)FEAT_ONE * NP + n] = d->v_template_host[(size_t)v * 3 + c];
       }
+    }
     for (int k = 0; k < KA; k++)
       for (size_t n = 0; n < (size_t)NP; n++) Pt[n * KA + k] = P[(size_t)k * NP + n];
     split_hi_lo(P, hi, lo);
@@ -324,7 +363,7 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   }
 
   // ---- joints49 tables
-  std::vector<std::vector<std::pair<int, float>>> vx(VP);  // per vertex: (source-24, coef)
+  std::vector<std::vector<std::pair<int, float>>> vx(V);  // per ORIGINAL vertex: (source-24, coef)
   {
     std::vector<int> picks(JRR_NUM_PICKS), jm(JRR_NUM_OUT_JOINTS);
     for (int p = 0; p < JRR_NUM_PICKS; p++) {
@@ -334,9 +373,9 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
       vx[v].push_back({p, 1.f});
     }
     for (int o = 0; o < JRR_NUM_OUT_JOINTS; o++) {
-      int64_t s = d->joint_map_host[o];
-      if (s < 0 || s >= 54) return fail(JRR_ERR_INVALID, "joint_map entry out of range");
-      jm[o] = (int)s;
+      int64_t s2 = d->joint_map_host[o];
+      if (s2 < 0 || s2 >= 54) return fail(JRR_ERR_INVALID, "joint_map entry out of range");
+      jm[o] = (int)s2;
     }
     std::vector<int> ptr(JRR_NUM_EXTRA + 1, 0), col;
     std::vector<float> val;
@@ -359,68 +398,77 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
     if (int rc = upload(m, &m->joint_map, jm)) return rc;
   }
 
-  // ---- skinning run records + dA flush lists
+  // ---- skinning run records (forward ranges VS_F, backward ranges VS_B) + dA flush lists
   {
-    std::vector<VtxRec> rec(VP);
     std::vector<int> vx_src;
     std::vector<float> vx_coef;
-    std::vector<int> flush_joint;
-    std::vector<int> range_base(NSPLIT);
-    int cur[4] = {0, 0, 0, 0};
+    std::vector<int> xptr(VP, 0), xcnt(VP, 0);
     for (int i = 0; i < VP; i++) {
-      const bool first = (i % VS) == 0;
-      if (first) range_base[i / VS] = (int)flush_joint.size();
-      std::vector<std::pair<int, float>> nz;
-      if (i < V)
-        for (int j = 0; j < NJ; j++) {
-          const float x = d->lbs_weights_host[(size_t)i * NJ + j];
-          if (x != 0.f) nz.push_back({j, x});
-        }
-      if (nz.size() > 4)
-        return fail(JRR_ERR_INVALID, "lbs_weights row with more than 4 non-zeros is not supported by this build");
-      int nj[4];
-      float nw[4] = {0.f, 0.f, 0.f, 0.f};
-      bool used[4] = {false, false, false, false};
-      for (int k = 0; k < 4; k++) nj[k] = first ? 0 : cur[k];
-      std::vector<std::pair<int, float>> rest;
-      for (auto& e : nz) {
-        int hit = -1;
-        if (!first)
-          for (int k = 0; k < 4; k++)
-            if (!used[k] && cur[k] == e.first) { hit = k; break; }
-        if (hit >= 0) { used[hit] = true; nw[hit] = e.second; }
-        else rest.push_back(e);
-      }
-      for (auto& e : rest)
-        for (int k = 0; k < 4; k++)
-          if (!used[k]) { used[k] = true; nj[k] = e.first; nw[k] = e.second; break; }
-      uint32_t meta = 0;
-      for (int k = 0; k < 4; k++) {
-        meta |= (uint32_t)nj[k] << (5 * k);
-        const bool reload = first || nj[k] != cur[k];
-        if (reload) {
-          meta |= 1u << (20 + k);
-          if (!first) flush_joint.push_back(cur[k]);
-        }
-        cur[k] = nj[k];
-      }
-      if (first) meta |= 1u << 25;
-      rec[i].meta = meta;
-      for (int k = 0; k < 4; k++) rec[i].w[k] = nw[k];
-      rec[i].xptr = (int)vx_src.size();
-      rec[i].xcnt = (int)vx[i].size();
-      rec[i].pad = 0;
-      for (auto& e : vx[i]) { vx_src.push_back(e.first); vx_coef.push_back(e.second); }
-      if ((i % VS) == VS - 1)
-        for (int k = 0; k < 4; k++) flush_joint.push_back(cur[k]);
+      xptr[i] = (int)vx_src.size();
+      if (perm[i] >= 0)
+        for (auto& e : vx[perm[i]]) { vx_src.push_back(e.first); vx_coef.push_back(e.second); }
+      xcnt[i] = (int)vx_src.size() - xptr[i];
     }
+    auto build = [&](int VS, std::vector<VtxRec>& rec, std::vector<int>* flush_joint, std::vector<int>* range_base) {
+      rec.assign(VP, VtxRec{});
+      int cur[4] = {0, 0, 0, 0};
+      for (int i = 0; i < VP; i++) {
+        const bool first = (i % VS) == 0;
+        if (first && range_base) (*range_base)[i / VS] = (int)flush_joint->size();
+        std::vector<std::pair<int, float>> nz;
+        if (perm[i] >= 0)
+          for (int j = 0; j < NJ; j++) {
+            const float x = d->lbs_weights_host[(size_t)perm[i] * NJ + j];
+            if (x != 0.f) nz.push_back({j, x});
+          }
+        int nj[4];
+        float nw[4] = {0.f, 0.f, 0.f, 0.f};
+        bool used[4] = {false, false, false, false};
+        for (int k = 0; k < 4; k++) nj[k] = first ? 0 : cur[k];
+        std::vector<std::pair<int, float>> rest;
+        for (auto& e : nz) {
+          int hit = -1;
+          if (!first)
+            for (int k = 0; k < 4; k++)
+              if (!used[k] && cur[k] == e.first) { hit = k; break; }
+          if (hit >= 0) { used[hit] = true; nw[hit] = e.second; }
+          else rest.push_back(e);
+        }
+        for (auto& e : rest)
+          for (int k = 0; k < 4; k++)
+            if (!used[k]) { used[k] = true; nj[k] = e.first; nw[k] = e.second; break; }
+        uint32_t meta = 0;
+        for (int k = 0; k < 4; k++) {
+          meta |= (uint32_t)nj[k] << (5 * k);
+          const bool reload = first || nj[k] != cur[k];
+          if (reload) {
+            meta |= 1u << (20 + k);
+            if (!first && flush_joint) flush_joint->push_back(cur[k]);
+          }
+          cur[k] = nj[k];
+        }
+        if (first) meta |= 1u << 25;
+        if (xcnt[i] > 0) meta |= 1u << 26;
+        rec[i].meta = meta;
+        for (int k = 0; k < 4; k++) rec[i].w[k] = nw[k];
+        rec[i].xptr = xptr[i];
+        rec[i].xcnt = xcnt[i];
+        if (flush_joint && (i % VS) == VS - 1)
+          for (int k = 0; k < 4; k++) flush_joint->push_back(cur[k]);
+      }
+    };
+    std::vector<VtxRec> rec_f, rec_b;
+    std::vector<int> flush_joint, range_base(NSPLIT_B);
+    build(VS_F, rec_f, nullptr, nullptr);
+    build(VS_B, rec_b, &flush_joint, &range_base);
     m->n_flush = (int)flush_joint.size();
     std::vector<int> fptr(NJ + 1, 0), fidx(flush_joint.size());
     for (int f : flush_joint) fptr[f + 1]++;
     for (int j = 0; j < NJ; j++) fptr[j + 1] += fptr[j];
     std::vector<int> fill(fptr.begin(), fptr.end() - 1);
     for (int f = 0; f < (int)flush_joint.size(); f++) fidx[fill[flush_joint[f]]++] = f;
-    if (int rc = upload(m, &m->vrec, rec)) return rc;
+    if (int rc = upload(m, &m->vrec, rec_f)) return rc;
+    if (int rc = upload(m, &m->vrec_b, rec_b)) return rc;
     if (int rc = upload(m, &m->vx_src, vx_src)) return rc;
     if (int rc = upload(m, &m->vx_coef, vx_coef)) return rc;
     if (int rc = upload(m, &m->flush_ptr, fptr)) return rc;
@@ -430,7 +478,6 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
 
   // ---- regressor state
   if (int rc = dalloc(m, &m->Jhat, (size_t)NH * V)) return rc;
-  if (int rc = dalloc(m, &m->Jhat_cols, (size_t)VP * JH_STRIDE)) return rc;
   if (int rc = dalloc(m, &m->rowsum, NH)) return rc;
   if (int rc = dalloc(m, &m->regdot, NH)) return rc;
   // ---- critic state

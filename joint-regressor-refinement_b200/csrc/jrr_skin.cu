@@ -17,8 +17,10 @@
 namespace jrr {
 
 constexpr int SK_THREADS = 128;
-constexpr int VT = 32;               // vertices per transposition tile
+constexpr int VT = 32;               // vertices per tile (constants staging + transposition)
 constexpr int TILE_LD = 3 * VT + 1;  // 97: conflict-free column access
+constexpr int GV = 4;                // vertices per register-prefetch group
+constexpr int TILE_F4 = VT * REC_WORDS / 4;  // 224 float4 of vertex records per tile
 
 __device__ __forceinline__ float tf32_hi_k(float x) {
   uint32_t r;
@@ -26,106 +28,157 @@ __device__ __forceinline__ float tf32_hi_k(float x) {
   return __uint_as_float(r);
 }
 
-__device__ __forceinline__ void load_rec(const VtxRec* __restrict__ vrec, int i, uint32_t& meta,
-                                         float w[4], int& xptr, int& xcnt) {
-  const uint4* p = reinterpret_cast<const uint4*>(vrec + i);
-  uint4 a = __ldg(p), c = __ldg(p + 1);
-  meta = a.x;
-  w[0] = __uint_as_float(a.y); w[1] = __uint_as_float(a.z); w[2] = __uint_as_float(a.w);
-  w[3] = __uint_as_float(c.x);
-  xptr = (int)c.y; xcnt = (int)c.z;
+// the tile's vertex records live in shared memory; every read below is a warp-wide broadcast
+struct RecView {
+  const float4* p;
+  __device__ __forceinline__ void head(int lv, uint32_t& meta, float w[4], int& xptr, int& xcnt) const {
+    const float4 a = p[lv * 7], c = p[lv * 7 + 1];
+    meta = __float_as_uint(a.x);
+    w[0] = a.y; w[1] = a.z; w[2] = a.w; w[3] = c.x;
+    xptr = __float_as_int(c.y); xcnt = __float_as_int(c.z);
+  }
+  __device__ __forceinline__ void jh(int lv, float out[JH_STRIDE]) const {
+#pragma unroll
+    for (int q = 0; q < JH_STRIDE / 4; q++) {
+      const float4 t = p[lv * 7 + 2 + q];
+      out[q * 4 + 0] = t.x; out[q * 4 + 1] = t.y; out[q * 4 + 2] = t.z; out[q * 4 + 3] = t.w;
+    }
+  }
+};
+
+__device__ __forceinline__ void load_vp_group(const float* __restrict__ vpT, int64_t BP, int64_t b, int i,
+                                              float out[3 * GV]) {
+  const float* src = vpT + (int64_t)(3 * i) * BP + b;
+#pragma unroll
+  for (int q = 0; q < 3 * GV; q++) out[q] = src[(int64_t)q * BP];
 }
 
 // ---------------------------------------------------------------------------- forward
 template <bool WRITE_V, bool WRITE_VT, bool PART>
-__global__ void __launch_bounds__(SK_THREADS)
-skin_fwd_kernel(const VtxRec* __restrict__ vrec, const float* __restrict__ Jhat_cols,
+__global__ void __launch_bounds__(SK_THREADS, 3)
+skin_fwd_kernel(const VtxRec* __restrict__ vrec, const int* __restrict__ perm,
                 const float* __restrict__ AT, const float* __restrict__ vpT, int64_t B, int64_t BP,
                 float* __restrict__ vertices_out, float* __restrict__ vT_out, float* __restrict__ part) {
-  extern __shared__ float tile[];  // [128][97] when WRITE_V
+  extern __shared__ float4 smem4[];
+  float4* sconst = smem4;                                         // [2][224]
+  float* tile = reinterpret_cast<float*>(smem4 + 2 * TILE_F4);    // [128][97] when WRITE_V
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * SK_THREADS;
   const int64_t b = b0 + tid;
   const int s = blockIdx.y;
-  const int i0 = s * VS;
+  const int i0 = s * VS_F;
+  constexpr int NT = VS_F / VT;
   float A[4][12];
-  float acc[NACC];
+  float acc[PART ? NACC : 1];
 #pragma unroll
-  for (int a = 0; a < NACC; a++) acc[a] = 0.f;
+  for (int a = 0; a < (PART ? NACC : 1); a++) acc[a] = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; k++)
 #pragma unroll
     for (int e = 0; e < 12; e++) A[k][e] = 0.f;
 
-  for (int t0 = 0; t0 < VS; t0 += VT) {
+  {
+    const float4* g = reinterpret_cast<const float4*>(vrec + i0);
+    for (int e = tid; e < TILE_F4; e += SK_THREADS) sconst[e] = __ldg(g + e);
+  }
+  float nx[3 * GV];
+  load_vp_group(vpT, BP, b, i0, nx);
+  __syncthreads();
+
 #pragma unroll 1
-    for (int ii = 0; ii < VT; ii++) {
-      const int i = i0 + t0 + ii;
-      uint32_t meta; float w[4]; int xptr, xcnt;
-      load_rec(vrec, i, meta, w, xptr, xcnt);
+  for (int t = 0; t < NT; t++) {
+    const RecView rv{sconst + (t & 1) * TILE_F4};
+    const bool has_next = t + 1 < NT;
+    float4 pf0 = make_float4(0, 0, 0, 0), pf1 = pf0;
+    if (has_next) {
+      const float4* g = reinterpret_cast<const float4*>(vrec + i0 + (t + 1) * VT);
+      pf0 = __ldg(g + tid);
+      if (tid + SK_THREADS < TILE_F4) pf1 = __ldg(g + tid + SK_THREADS);
+    }
+#pragma unroll 1
+    for (int sub = 0; sub < VT / GV; sub++) {
+      float cur[3 * GV];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if ((meta >> (20 + k)) & 1u) {
-          const int j = (meta >> (5 * k)) & 31u;
-          const float* src = AT + (int64_t)(j * 12) * BP + b;
+      for (int q = 0; q < 3 * GV; q++) cur[q] = nx[q];
+      const int inext = i0 + t * VT + (sub + 1) * GV;
+      if (inext < i0 + VS_F) load_vp_group(vpT, BP, b, inext, nx);
 #pragma unroll
-          for (int e = 0; e < 12; e++) A[k][e] = src[(int64_t)e * BP];
+      for (int ii = 0; ii < GV; ii++) {
+        const int lv = sub * GV + ii;
+        const int i = i0 + t * VT + lv;
+        uint32_t meta; float w[4]; int xptr, xcnt;
+        rv.head(lv, meta, w, xptr, xcnt);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if ((meta >> (20 + k)) & 1u) {
+            const int j = (meta >> (5 * k)) & 31u;
+            const float* src = AT + (int64_t)(j * 12) * BP + b;
+#pragma unroll
+            for (int e = 0; e < 12; e++) A[k][e] = src[(int64_t)e * BP];
+          }
         }
-      }
-      const float x = vpT[(int64_t)(3 * i + 0) * BP + b];
-      const float y = vpT[(int64_t)(3 * i + 1) * BP + b];
-      const float z = vpT[(int64_t)(3 * i + 2) * BP + b];
-      float T[12];
+        const float x = cur[ii * 3 + 0], y = cur[ii * 3 + 1], z = cur[ii * 3 + 2];
+        float v[3];
 #pragma unroll
-      for (int e = 0; e < 12; e++)
-        T[e] = w[0] * A[0][e] + w[1] * A[1][e] + w[2] * A[2][e] + w[3] * A[3][e];
-      float v[3];
-#pragma unroll
-      for (int r = 0; r < 3; r++) v[r] = T[r * 4 + 0] * x + T[r * 4 + 1] * y + T[r * 4 + 2] * z + T[r * 4 + 3];
-      if (WRITE_VT) {
-#pragma unroll
-        for (int r = 0; r < 3; r++) vT_out[(int64_t)(3 * i + r) * BP + b] = v[r];
-      }
-      if (WRITE_V) {
-#pragma unroll
-        for (int r = 0; r < 3; r++) tile[tid * TILE_LD + ii * 3 + r] = v[r];
-      }
-      if (PART && ((meta >> 24) & 1u)) {
-        const float4* jc = reinterpret_cast<const float4*>(Jhat_cols + (int64_t)i * JH_STRIDE);
-        float jh[JH_STRIDE];
-#pragma unroll
-        for (int q = 0; q < JH_STRIDE / 4; q++) {
-          float4 t = __ldg(jc + q);
-          jh[q * 4 + 0] = t.x; jh[q * 4 + 1] = t.y; jh[q * 4 + 2] = t.z; jh[q * 4 + 3] = t.w;
+        for (int r = 0; r < 3; r++) {
+          const float t0 = w[0] * A[0][r * 4 + 0] + w[1] * A[1][r * 4 + 0] + w[2] * A[2][r * 4 + 0] + w[3] * A[3][r * 4 + 0];
+          const float t1 = w[0] * A[0][r * 4 + 1] + w[1] * A[1][r * 4 + 1] + w[2] * A[2][r * 4 + 1] + w[3] * A[3][r * 4 + 1];
+          const float t2 = w[0] * A[0][r * 4 + 2] + w[1] * A[1][r * 4 + 2] + w[2] * A[2][r * 4 + 2] + w[3] * A[3][r * 4 + 2];
+          const float t3 = w[0] * A[0][r * 4 + 3] + w[1] * A[1][r * 4 + 3] + w[2] * A[2][r * 4 + 3] + w[3] * A[3][r * 4 + 3];
+          v[r] = t0 * x + t1 * y + t2 * z + t3;
         }
+        if (WRITE_VT) {
 #pragma unroll
-        for (int j = 0; j < NH; j++) {
-          acc[j * 3 + 0] = fmaf(jh[j], v[0], acc[j * 3 + 0]);
-          acc[j * 3 + 1] = fmaf(jh[j], v[1], acc[j * 3 + 1]);
-          acc[j * 3 + 2] = fmaf(jh[j], v[2], acc[j * 3 + 2]);
+          for (int r = 0; r < 3; r++) vT_out[(int64_t)(3 * i + r) * BP + b] = v[r];
+        }
+        if (WRITE_V) {
+#pragma unroll
+          for (int r = 0; r < 3; r++) tile[tid * TILE_LD + lv * 3 + r] = v[r];
+        }
+        if (PART && ((meta >> 24) & 1u)) {
+          float jh[JH_STRIDE];
+          rv.jh(lv, jh);
+#pragma unroll
+          for (int j = 0; j < NH; j++) {
+            acc[PART ? j * 3 + 0 : 0] = fmaf(jh[j], v[0], acc[PART ? j * 3 + 0 : 0]);
+            acc[PART ? j * 3 + 1 : 0] = fmaf(jh[j], v[1], acc[PART ? j * 3 + 1 : 0]);
+            acc[PART ? j * 3 + 2 : 0] = fmaf(jh[j], v[2], acc[PART ? j * 3 + 2 : 0]);
+          }
         }
       }
     }
     if (WRITE_V) {
+      // natural-order vertices [B][6890][3]: rows leave through smem, scattered by the packing
+      // permutation in 12-byte pieces
       __syncthreads();
       const int warp = tid >> 5, lane = tid & 31;
-      const int it0 = i0 + t0;
+      const int it0 = i0 + t * VT;
+      int dstoff[3];
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const int f = lane + 32 * q;
+        const int v = perm[it0 + f / 3];
+        dstoff[q] = v >= 0 ? v * 3 + f % 3 : -1;
+      }
       for (int r = warp; r < SK_THREADS; r += SK_THREADS / 32) {
         const int64_t bb = b0 + r;
         if (bb >= B) break;
-        float* dst = vertices_out + bb * (int64_t)(V * 3) + (int64_t)it0 * 3;
+        float* dst = vertices_out + bb * (int64_t)(V * 3);
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
-          const int f = lane + 32 * q;
-          if (it0 * 3 + f < V * 3) dst[f] = tile[r * TILE_LD + f];
-        }
+        for (int q = 0; q < 3; q++)
+          if (dstoff[q] >= 0) dst[dstoff[q]] = tile[r * TILE_LD + lane + 32 * q];
       }
-      __syncthreads();
     }
+    if (has_next) {
+      float4* dstc = sconst + ((t + 1) & 1) * TILE_F4;
+      dstc[tid] = pf0;
+      if (tid + SK_THREADS < TILE_F4) dstc[tid + SK_THREADS] = pf1;
+    }
+    __syncthreads();
   }
   if (PART) {
 #pragma unroll
-    for (int a = 0; a < NACC; a++) part[((int64_t)s * NACC + a) * BP + b] = acc[a];
+    for (int a = 0; a < (PART ? NACC : 1); a++) part[((int64_t)s * NACC + a) * BP + b] = acc[a];
   }
 }
 
@@ -185,29 +238,31 @@ loss_seed_kernel(const float* __restrict__ part, const float* __restrict__ gt_mm
 //                                                           backward blend GEMM, tf32 split)
 // dA_k += w_k dv_i (x) [vp_i ; 1]                        -> flushed per run to dAflush
 template <bool USE_G, bool USE_DV, bool USE_X>
-__global__ void __launch_bounds__(SK_THREADS)
-skin_bwd_kernel(const VtxRec* __restrict__ vrec, const float* __restrict__ Jhat_cols,
+__global__ void __launch_bounds__(SK_THREADS, 2)
+skin_bwd_kernel(const VtxRec* __restrict__ vrec, const int* __restrict__ perm,
                 const int* __restrict__ range_flush_base, const int* __restrict__ vx_src,
                 const float* __restrict__ vx_coef, const float* __restrict__ AT,
                 const float* __restrict__ vpT, const float* __restrict__ gT,
                 const float* __restrict__ dvertices, const float* __restrict__ d30T, int64_t B,
                 int64_t BP, float* __restrict__ dvp_hi, float* __restrict__ dvp_lo,
                 float* __restrict__ dAflush) {
-  extern __shared__ float smem[];
-  float* tile_out = smem;                               // [128][97]
-  float* tile_in = smem + SK_THREADS * TILE_LD;         // [128][97] (USE_DV)
+  extern __shared__ float4 smem4[];
+  float4* sconst = smem4;                                             // [2][224]
+  float* tile_out = reinterpret_cast<float*>(smem4 + 2 * TILE_F4);    // [128][97]
+  float* tile_in = tile_out + SK_THREADS * TILE_LD;                   // [128][97] (USE_DV)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int64_t b0 = (int64_t)blockIdx.x * SK_THREADS;
   const int64_t b = b0 + tid;
   const int s = blockIdx.y;
-  const int i0 = s * VS;
+  const int i0 = s * VS_B;
+  constexpr int NT = VS_B / VT;
   int fl = range_flush_base[s];
 
   float g[USE_G ? NACC : 1];
   if (USE_G) {
 #pragma unroll
-    for (int a = 0; a < NACC; a++) g[a] = gT[(int64_t)a * BP + b];
+    for (int a = 0; a < NACC; a++) g[USE_G ? a : 0] = gT[(int64_t)a * BP + b];
   }
   float AR[4][9], dA[4][12];
 #pragma unroll
@@ -217,94 +272,118 @@ skin_bwd_kernel(const VtxRec* __restrict__ vrec, const float* __restrict__ Jhat_
 #pragma unroll
     for (int e = 0; e < 12; e++) dA[k][e] = 0.f;
   }
+  {
+    const float4* gsrc = reinterpret_cast<const float4*>(vrec + i0);
+    for (int e = tid; e < TILE_F4; e += SK_THREADS) sconst[e] = __ldg(gsrc + e);
+  }
+  float nx[3 * GV];
+  load_vp_group(vpT, BP, b, i0, nx);
+  __syncthreads();
 
-  for (int t0 = 0; t0 < VS; t0 += VT) {
-    const int it0 = i0 + t0;
+#pragma unroll 1
+  for (int t = 0; t < NT; t++) {
+    const RecView rv{sconst + (t & 1) * TILE_F4};
+    const int it0 = i0 + t * VT;
+    const bool has_next = t + 1 < NT;
+    float4 pf0 = make_float4(0, 0, 0, 0), pf1 = pf0;
+    if (has_next) {
+      const float4* gsrc = reinterpret_cast<const float4*>(vrec + it0 + VT);
+      pf0 = __ldg(gsrc + tid);
+      if (tid + SK_THREADS < TILE_F4) pf1 = __ldg(gsrc + tid + SK_THREADS);
+    }
+    int voff[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const int f = lane + 32 * q;
+      const int v = USE_DV ? perm[it0 + f / 3] : -1;
+      voff[q] = v >= 0 ? v * 3 + f % 3 : -1;
+    }
     if (USE_DV) {
+      // gather the natural-order dvertices rows of this tile into smem (pose-major -> thread-major)
       for (int r = warp; r < SK_THREADS; r += SK_THREADS / 32) {
         const int64_t bb = b0 + r;
-        const float* src = dvertices + bb * (int64_t)(V * 3) + (int64_t)it0 * 3;
+        const float* src = dvertices + bb * (int64_t)(V * 3);
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
-          const int f = lane + 32 * q;
-          tile_in[r * TILE_LD + f] = (bb < B && it0 * 3 + f < V * 3) ? src[f] : 0.f;
-        }
+        for (int q = 0; q < 3; q++)
+          tile_in[r * TILE_LD + lane + 32 * q] = (bb < B && voff[q] >= 0) ? src[voff[q]] : 0.f;
       }
       __syncthreads();
     }
 #pragma unroll 1
-    for (int ii = 0; ii < VT; ii++) {
-      const int i = it0 + ii;
-      uint32_t meta; float w[4]; int xptr, xcnt;
-      load_rec(vrec, i, meta, w, xptr, xcnt);
-      const bool first = (meta >> 25) & 1u;
+    for (int sub = 0; sub < VT / GV; sub++) {
+      float cur[3 * GV];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if ((meta >> (20 + k)) & 1u) {
-          if (!first) {
-            float* dst = dAflush + (int64_t)fl * 12 * BP + b;
+      for (int q = 0; q < 3 * GV; q++) cur[q] = nx[q];
+      const int inext = it0 + (sub + 1) * GV;
+      if (inext < i0 + VS_B) load_vp_group(vpT, BP, b, inext, nx);
 #pragma unroll
-            for (int e = 0; e < 12; e++) { dst[(int64_t)e * BP] = dA[k][e]; dA[k][e] = 0.f; }
-            fl++;
+      for (int ii = 0; ii < GV; ii++) {
+        const int lv = sub * GV + ii;
+        uint32_t meta; float w[4]; int xptr, xcnt;
+        rv.head(lv, meta, w, xptr, xcnt);
+        const bool first = (meta >> 25) & 1u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if ((meta >> (20 + k)) & 1u) {
+            if (!first) {
+              float* dst = dAflush + (int64_t)fl * 12 * BP + b;
+#pragma unroll
+              for (int e = 0; e < 12; e++) { dst[(int64_t)e * BP] = dA[k][e]; dA[k][e] = 0.f; }
+              fl++;
+            }
+            const int j = (meta >> (5 * k)) & 31u;
+            const float* src = AT + (int64_t)(j * 12) * BP + b;
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+              for (int c = 0; c < 3; c++) AR[k][r * 3 + c] = src[(int64_t)(r * 4 + c) * BP];
           }
-          const int j = (meta >> (5 * k)) & 31u;
-          const float* src = AT + (int64_t)(j * 12) * BP + b;
-#pragma unroll
-          for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) AR[k][r * 3 + c] = src[(int64_t)(r * 4 + c) * BP];
         }
-      }
-      float vp[3];
+        const float vp0 = cur[ii * 3 + 0], vp1 = cur[ii * 3 + 1], vp2 = cur[ii * 3 + 2];
+        float dv[3] = {0.f, 0.f, 0.f};
+        if (USE_G && ((meta >> 24) & 1u)) {
+          float jh[JH_STRIDE];
+          rv.jh(lv, jh);
 #pragma unroll
-      for (int c = 0; c < 3; c++) vp[c] = vpT[(int64_t)(3 * i + c) * BP + b];
-      float dv[3] = {0.f, 0.f, 0.f};
-      if (USE_G && ((meta >> 24) & 1u)) {
-        const float4* jc = reinterpret_cast<const float4*>(Jhat_cols + (int64_t)i * JH_STRIDE);
-        float jh[JH_STRIDE];
-#pragma unroll
-        for (int q = 0; q < JH_STRIDE / 4; q++) {
-          float4 t = __ldg(jc + q);
-          jh[q * 4 + 0] = t.x; jh[q * 4 + 1] = t.y; jh[q * 4 + 2] = t.z; jh[q * 4 + 3] = t.w;
+          for (int j = 0; j < NH; j++) {
+            dv[0] = fmaf(jh[j], g[USE_G ? j * 3 + 0 : 0], dv[0]);
+            dv[1] = fmaf(jh[j], g[USE_G ? j * 3 + 1 : 0], dv[1]);
+            dv[2] = fmaf(jh[j], g[USE_G ? j * 3 + 2 : 0], dv[2]);
+          }
         }
+        if (USE_DV) {
 #pragma unroll
-        for (int j = 0; j < NH; j++) {
-          dv[0] = fmaf(jh[j], g[USE_G ? j * 3 + 0 : 0], dv[0]);
-          dv[1] = fmaf(jh[j], g[USE_G ? j * 3 + 1 : 0], dv[1]);
-          dv[2] = fmaf(jh[j], g[USE_G ? j * 3 + 2 : 0], dv[2]);
+          for (int c = 0; c < 3; c++) dv[c] += tile_in[tid * TILE_LD + lv * 3 + c];
         }
-      }
-      if (USE_DV) {
+        if (USE_X && ((meta >> 26) & 1u)) {
+          for (int q = 0; q < xcnt; q++) {
+            const int src = __ldg(vx_src + xptr + q);
+            const float cf = __ldg(vx_coef + xptr + q);
 #pragma unroll
-        for (int c = 0; c < 3; c++) dv[c] += tile_in[tid * TILE_LD + ii * 3 + c];
-      }
-      if (USE_X) {
-        for (int q = 0; q < xcnt; q++) {
-          const int src = __ldg(vx_src + xptr + q);
-          const float cf = __ldg(vx_coef + xptr + q);
-#pragma unroll
-          for (int c = 0; c < 3; c++) dv[c] = fmaf(cf, d30T[(int64_t)(src * 3 + c) * BP + b], dv[c]);
+            for (int c = 0; c < 3; c++) dv[c] = fmaf(cf, d30T[(int64_t)(src * 3 + c) * BP + b], dv[c]);
+          }
         }
-      }
-      float TR[9];
+        float TR[9];
 #pragma unroll
-      for (int e = 0; e < 9; e++) TR[e] = w[0] * AR[0][e] + w[1] * AR[1][e] + w[2] * AR[2][e] + w[3] * AR[3][e];
+        for (int e = 0; e < 9; e++) TR[e] = w[0] * AR[0][e] + w[1] * AR[1][e] + w[2] * AR[2][e] + w[3] * AR[3][e];
 #pragma unroll
-      for (int c = 0; c < 3; c++)
-        tile_out[tid * TILE_LD + ii * 3 + c] = TR[0 * 3 + c] * dv[0] + TR[1 * 3 + c] * dv[1] + TR[2 * 3 + c] * dv[2];
+        for (int c = 0; c < 3; c++)
+          tile_out[tid * TILE_LD + lv * 3 + c] = TR[0 * 3 + c] * dv[0] + TR[1 * 3 + c] * dv[1] + TR[2 * 3 + c] * dv[2];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 4; k++) {
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-          const float wd = w[k] * dv[r];
-          dA[k][r * 4 + 0] = fmaf(wd, vp[0], dA[k][r * 4 + 0]);
-          dA[k][r * 4 + 1] = fmaf(wd, vp[1], dA[k][r * 4 + 1]);
-          dA[k][r * 4 + 2] = fmaf(wd, vp[2], dA[k][r * 4 + 2]);
-          dA[k][r * 4 + 3] += wd;
+          for (int r = 0; r < 3; r++) {
+            const float wd = w[k] * dv[r];
+            dA[k][r * 4 + 0] = fmaf(wd, vp0, dA[k][r * 4 + 0]);
+            dA[k][r * 4 + 1] = fmaf(wd, vp1, dA[k][r * 4 + 1]);
+            dA[k][r * 4 + 2] = fmaf(wd, vp2, dA[k][r * 4 + 2]);
+            dA[k][r * 4 + 3] += wd;
+          }
         }
       }
     }
     __syncthreads();
+    // dvp rows (A operand of the backward blend GEMM, K-major, tf32 hi/lo), coalesced
     for (int r = warp; r < SK_THREADS; r += SK_THREADS / 32) {
       const int64_t bb = b0 + r;
       float* dh = dvp_hi + bb * (int64_t)NP + (int64_t)it0 * 3;
@@ -317,6 +396,11 @@ skin_bwd_kernel(const VtxRec* __restrict__ vrec, const float* __restrict__ Jhat_
         dh[f] = hi;
         dl[f] = tf32_hi_k(v - hi);
       }
+    }
+    if (has_next) {
+      float4* dstc = sconst + ((t + 1) & 1) * TILE_F4;
+      dstc[tid] = pf0;
+      if (tid + SK_THREADS < TILE_F4) dstc[tid + SK_THREADS] = pf1;
     }
     __syncthreads();
   }
@@ -421,13 +505,14 @@ __global__ void loss_finish_kernel(const float* __restrict__ lp_joint, int n_joi
 int launch_skin_fwd(const JrrModel* m, const Workspace& w, float* vertices_out, float* vT_out,
                     bool want_part, cudaStream_t st) {
   dim3 grid((unsigned)(w.BP / SK_THREADS), NSPLIT), block(SK_THREADS);
+  const size_t cbytes = 2 * TILE_F4 * sizeof(float4);
 #define JRR_SF(WV, WVT, P)                                                                       \
   do {                                                                                           \
     auto kern = skin_fwd_kernel<WV, WVT, P>;                                                     \
-    const size_t smem = WV ? (size_t)SK_THREADS * TILE_LD * sizeof(float) : 0;                   \
+    const size_t smem = cbytes + (WV ? (size_t)SK_THREADS * TILE_LD * sizeof(float) : 0);        \
     cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e_ != cudaSuccess) return fail(JRR_ERR_CUDA, cudaGetErrorString(e_));                    \
-    kern<<<grid, block, smem, st>>>(m->vrec, m->Jhat_cols, w.AT, w.vpT, w.B, w.BP, vertices_out, \
+    kern<<<grid, block, smem, st>>>(m->vrec, m->perm, w.AT, w.vpT, w.B, w.BP, vertices_out,      \
                                     vT_out, w.part);                                             \
   } while (0)
   const bool wv = vertices_out != nullptr, wvt = vT_out != nullptr;
@@ -456,15 +541,15 @@ int launch_loss_seed(const JrrModel* m, const Workspace& w, const float* gt_mm, 
 
 int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_g,
                     bool use_x, cudaStream_t st) {
-  dim3 grid((unsigned)(w.BP / SK_THREADS), NSPLIT), block(SK_THREADS);
+  dim3 grid((unsigned)(w.BP / SK_THREADS), NSPLIT_B), block(SK_THREADS);
   const bool use_dv = dvertices != nullptr;
-  const size_t smem = (size_t)SK_THREADS * TILE_LD * sizeof(float) * (use_dv ? 2 : 1);
+  const size_t smem = 2 * TILE_F4 * sizeof(float4) + (size_t)SK_THREADS * TILE_LD * sizeof(float) * (use_dv ? 2 : 1);
 #define JRR_SB(G, DV, X)                                                                          \
   do {                                                                                            \
     auto kern = skin_bwd_kernel<G, DV, X>;                                                        \
     cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e_ != cudaSuccess) return fail(JRR_ERR_CUDA, cudaGetErrorString(e_));                     \
-    kern<<<grid, block, smem, st>>>(m->vrec, m->Jhat_cols, m->range_flush_base, m->vx_src,        \
+    kern<<<grid, block, smem, st>>>(m->vrec_b, m->perm, m->range_flush_base, m->vx_src,           \
                                     m->vx_coef, w.AT, w.vpT, w.gT, dvertices, w.d30T, w.B, w.BP,  \
                                     w.dvp_hi, w.dvp_lo, w.dAflush);                               \
   } while (0)

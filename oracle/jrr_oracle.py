@@ -276,7 +276,7 @@ def regressor_grad(smpl, Jraw, x6, betas, gt_mm, logical_batch=None, mask=None):
     LB = B if logical_batch is None else logical_batch
     loss = (diff ** 2).sum() / (LB * 17 * 3)
     loss.backward()
-    return J.grad.detach(), float(loss)
+    return J.grad.detach(), loss.item()
 
 
 class RegressorAdam:

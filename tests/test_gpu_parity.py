@@ -53,7 +53,7 @@ def test_gemm_tcgen05_3xtf32_vs_fp64(smpl_tc, shape):
     # truncation, so the error grows ~linearly with the number of K steps (K/8 per pass)
     err = rel(C, ref)
     print(f"tcgen05 3xTF32 {shape}: rel err {err:.2e}")
-    assert err < (4e-6 if K <= 1024 else 4e-5)
+    assert err < (1e-5 if K <= 1024 else 4e-5)
 
 
 # ------------------------------------------------------------------ SMPL forward (config C1)
