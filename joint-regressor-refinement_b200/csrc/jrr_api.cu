@@ -28,7 +28,21 @@ Workspace carve(const JrrModel* m, int64_t B, void* base) {
   w.dvp_lo = take(BP * (size_t)NP);
   w.dAflush = take((size_t)m->n_flush * 12 * BP);
   w.dAT = take(288 * BP);
-  w.dfeat = take((size_t)KSPLIT * BP * KA);
+  w.dfeat = take((size_t)KSPLIT_MAX * BP * KA);
+  {
+    // tiles = (BP/128) * ksplit CTAs of the backward blend GEMM: pick the split that wastes the
+    // least of the last wave (ties -> fewer splits, less partial traffic)
+    const int cand[4] = {6, 9, 12, 18};
+    const int64_t mt = w.BP / 128;
+    double best = -1.0;
+    w.ksplit = 6;
+    for (int c : cand) {
+      const int64_t tiles = mt * c;
+      const int64_t waves = (tiles + m->num_sms - 1) / m->num_sms;
+      const double eff = (double)tiles / (double)(waves * m->num_sms);
+      if (eff > best + 1e-9) { best = eff; w.ksplit = c; }
+    }
+  }
   w.dJp = take(BP * 72);
   w.Jp = take(BP * 72);
   w.d30T = take(90 * BP);
@@ -85,7 +99,7 @@ static int blend_backward_gemm(const JrrModel* m, const Workspace& w, cudaStream
   GemmDesc g{};
   g.A_hi = w.dvp_hi; g.A_lo = w.dvp_lo; g.lda = NP;
   g.B_hi = m->P_hi; g.B_lo = m->P_lo; g.ldb = NP;
-  g.M = w.BP; g.N = KA; g.K = NP / KSPLIT; g.ksplit = KSPLIT; g.epi = EPI_STORE_SPLITK;
+  g.M = w.BP; g.N = KA; g.K = NP / w.ksplit; g.ksplit = w.ksplit; g.epi = EPI_STORE_SPLITK;
   g.out0 = w.dfeat; g.ldo = KA;
   return launch_gemm(m, g, st);
 }
@@ -188,6 +202,21 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
     if (ev) JRR_CUDA(cudaEventRecord(ev[mark], st));                    \
     mark++;                                                             \
   } while (0)
+  // The critic chain only reads x6 and its own workspace slices, so outside profiling it is
+  // forked onto the model's side stream and joins again before the Adam kernel (inside a
+  // CUDA-graph capture this becomes a parallel branch of the graph).
+  const bool fork = critic && ev == nullptr && m->overlap_critic;
+  cudaStream_t cs = fork ? m->side : st;
+  if (fork) {
+    JRR_CUDA(cudaEventRecord(m->ev_fork, st));
+    JRR_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+    if (int rc = launch_critic_pre(m, w, x6, cs)) return rc;
+    if (int rc = critic_forward_gemms(m, w, cs)) return rc;
+    if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, cs)) return rc;
+    if (int rc = critic_backward_gemms(m, w, cs)) return rc;
+    if (int rc = launch_critic_post(m, w, x6, cs)) return rc;
+    JRR_CUDA(cudaEventRecord(m->ev_join, m->side));
+  }
   JRR_MARK();
   // forward: chain | blend GEMM | skinning fused with the 17x6890 regressor reduction | loss seed
   if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, x6, JRR_POSE_ROT6D, w.AT, w.feat_hi, w.feat_lo, nullptr, st)) return rc;
@@ -205,17 +234,19 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   JRR_MARK();
   if (int rc = blend_backward_gemm(m, w, st)) return rc;
   JRR_MARK();
-  // critic forward + input gradient
-  if (critic) if (int rc = launch_critic_pre(m, w, x6, st)) return rc;
+  // critic forward + input gradient (inline when profiling or when the fork is disabled)
+  const bool inl = critic && !fork;
+  if (inl) if (int rc = launch_critic_pre(m, w, x6, st)) return rc;
   JRR_MARK();
-  if (critic) if (int rc = critic_forward_gemms(m, w, st)) return rc;
+  if (inl) if (int rc = critic_forward_gemms(m, w, st)) return rc;
   JRR_MARK();
-  if (critic) if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, st)) return rc;
+  if (inl) if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, st)) return rc;
   JRR_MARK();
-  if (critic) if (int rc = critic_backward_gemms(m, w, st)) return rc;
+  if (inl) if (int rc = critic_backward_gemms(m, w, st)) return rc;
   JRR_MARK();
-  if (critic) if (int rc = launch_critic_post(m, w, x6, st)) return rc;
+  if (inl) if (int rc = launch_critic_post(m, w, x6, st)) return rc;
   JRR_MARK();
+  if (fork) JRR_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
   if (loss_out)
     if (int rc = launch_loss_finish(w, B_logical, w_joint, w_pose, critic, loss_out, nullptr, st)) return rc;
   JRR_MARK();

@@ -27,7 +27,7 @@ constexpr int VS_F = 576;           // packed vertices per CTA range, forward sk
 constexpr int NSPLIT = VP / VS_F;   // 12 regressor partial sums per pose
 constexpr int VS_B = 768;           // packed vertices per CTA range, backward skinning
 constexpr int NSPLIT_B = VP / VS_B; // 9
-constexpr int KSPLIT = 6;           // split-K of the backward blend GEMM (20736 = 6*3456)
+constexpr int KSPLIT_MAX = 18;      // split-K of the backward blend GEMM: 6, 9, 12 or 18 (chosen per batch to fill whole waves)
 constexpr int NPARAM = 154;         // 144 rot6d + 10 betas per pose
 constexpr int MAXCH = 4;            // children per joint supported by the chain kernels
 
@@ -99,6 +99,7 @@ struct Csr {
 struct JrrModel {
   int device = 0;
   int gemm_impl = 0;
+  int num_sms = 148;
   jrr::ChainTab chain;
   // augmented blend matrix, tf32 hi/lo split, both majors
   float *Pt_hi = nullptr, *Pt_lo = nullptr;  // [NP][KA]  (K contiguous)  forward B operand
@@ -130,6 +131,10 @@ struct JrrModel {
   float *W1t_hi = nullptr, *W1t_lo = nullptr;  // [768][1024]
   float *W2t_hi = nullptr, *W2t_lo = nullptr;  // [1024][1024]
   bool has_critic = false;
+  // the critic chain of a refinement step runs on a forked side stream (joins before Adam)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap_critic = true;
   std::vector<void*> allocs;
 };
 
@@ -149,7 +154,8 @@ struct Workspace {
   float* dvp_lo;
   float* dAflush;   // [n_flush][12][BP]
   float* dAT;       // [288][BP]
-  float* dfeat;     // [KSPLIT][BP][224]
+  float* dfeat;     // [ksplit][BP][224]
+  int ksplit;       // split-K factor of the backward blend GEMM for this batch
   float* dJp;       // [BP][72]    grad wrt posed joints (module path)
   float* Jp;        // [BP][72]    posed joints
   float* d30T;      // [90][BP]    joints49 gradient gathered onto picks / extra rows

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 #include "jrr_internal.cuh"
 
@@ -261,6 +262,9 @@ extern "C" int jrr_model_destroy(JrrModel* m) {
   if (!m) return JRR_OK;
   cudaSetDevice(m->device);
   for (void* p : m->allocs) cudaFree(p);
+  if (m->side) cudaStreamDestroy(m->side);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
   delete m;
   return JRR_OK;
 }
@@ -269,6 +273,7 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   m->device = d->device;
   m->gemm_impl = d->gemm_impl;
   JRR_CUDA(cudaSetDevice(d->device));
+  JRR_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, d->device));
 
   // ---- kinematic tree
   ChainTab& ct = m->chain;
@@ -490,6 +495,10 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   if (int rc = dalloc(m, &m->W2_lo, (size_t)C_Z * C_Z)) return rc;
   if (int rc = dalloc(m, &m->W2t_hi, (size_t)C_Z * C_Z)) return rc;
   if (int rc = dalloc(m, &m->W2t_lo, (size_t)C_Z * C_Z)) return rc;
+  JRR_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+  JRR_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  JRR_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+  if (const char* e = getenv("JRR_OVERLAP_CRITIC")) m->overlap_critic = (e[0] != '0');
   JRR_CUDA(cudaDeviceSynchronize());
   return JRR_OK;
 }

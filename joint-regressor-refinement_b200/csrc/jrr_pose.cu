@@ -425,7 +425,7 @@ int launch_pose_bwd(const JrrModel* m, const Workspace& w, const float* betas, c
   const bool adam = x6 != nullptr;
 #define JRR_PB(KIND, AD)                                                                          \
   pose_bwd_kernel<KIND, AD><<<grid, block, 0, st>>>(m->chain, m->J0, m->JS, betas, pose, w.B, w.BP, \
-      w.dAT, w.dfeat, KSPLIT, dJp, dx6c, dbetas_out, dpose_out, x6, betas_rw, adam_m, adam_v,      \
+      w.dAT, w.dfeat, w.ksplit, dJp, dx6c, dbetas_out, dpose_out, x6, betas_rw, adam_m, adam_v,      \
       step_count, lr)
   if (adam) {
     if (kind != JRR_POSE_ROT6D) return fail(JRR_ERR_INVALID, "Adam step needs rot6d parameters");
