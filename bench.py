@@ -39,6 +39,25 @@ F_GEMM = 24.46e6                        # tensor-eligible (blend + critic, fwd +
 ALG_BYTES_PER_POSE_STEP = 3900
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Library chatter (e.g. NCCL's version banner) goes to stderr: stdout carries exactly one
+    JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -134,14 +153,14 @@ def run_reference(args):
     n = 512
     rate, ms, cores = cpu_reference_rate(n, args.steps, args.warmup)
     sample = f"{n} of the {FRAMES} frames per step, {args.steps} steps, torch {cores} threads, fp32"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step": n},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
@@ -156,6 +175,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-impl", type=int, default=0)
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -355,7 +375,7 @@ def main():
             "refit_ms": refit_ms,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 

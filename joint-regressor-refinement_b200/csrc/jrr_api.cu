@@ -1,4 +1,6 @@
 // C-ABI entry points: argument checks, workspace carving and the kernel sequences.
+#include <algorithm>
+
 #include "jrr_internal.cuh"
 
 namespace jrr {
@@ -21,7 +23,7 @@ Workspace carve(const JrrModel* m, int64_t B, void* base) {
   w.feat_hi = take(BP * KA);
   w.feat_lo = take(BP * KA);
   w.vpT = take((size_t)NP * BP);
-  w.part = take((size_t)NSPLIT * NACC * BP);
+  w.part = take((size_t)std::max(NSPLIT, fused_fwd_slots(w.BP, m->num_sms)) * NACC * BP);
   w.gT = take(NACC * BP);
   w.pred = take(BP * NACC);
   w.dvp_hi = take(BP * (size_t)NP);
@@ -94,6 +96,23 @@ static int forward_common(const JrrModel* m, const Workspace& w, const float* be
   return blend_forward_gemm(m, w, st);
 }
 
+// Forward of the loss path up to the regressor partial sums.  store: 0 nothing, 1 blended
+// vertices vp -> out (pose-contiguous, the backward needs them), 2 skinned vertices -> out.
+static int loss_forward(const JrrModel* m, const Workspace& w, const float* betas, const float* pose, int kind,
+                        int store, float* out, cudaStream_t st, cudaEvent_t* ev_after_pose,
+                        cudaEvent_t* ev_after_gemm) {
+  if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, pose, kind, w.AT, w.feat_hi, w.feat_lo, nullptr, st)) return rc;
+  if (ev_after_pose) JRR_CUDA(cudaEventRecord(*ev_after_pose, st));
+  if (m->fused_fwd) {
+    if (int rc = launch_fused_fwd(m, w, store, out, st)) return rc;
+    if (ev_after_gemm) JRR_CUDA(cudaEventRecord(*ev_after_gemm, st));
+    return JRR_OK;
+  }
+  if (int rc = blend_forward_gemm(m, w, st)) return rc;      // writes w.vpT
+  if (ev_after_gemm) JRR_CUDA(cudaEventRecord(*ev_after_gemm, st));
+  return launch_skin_fwd(m, w, nullptr, store == 2 ? out : nullptr, true, st);
+}
+
 // dfeat[s][BP,224] = dvp[BP, 20736 (split s)] x P[224, 20736]^T
 static int blend_backward_gemm(const JrrModel* m, const Workspace& w, cudaStream_t st) {
   GemmDesc g{};
@@ -161,9 +180,8 @@ extern "C" int jrr_find_joints(JrrModel* m, int64_t B, const float* betas, const
   if (!m->has_regressor) return fail(JRR_ERR_STATE, "jrr_set_regressor has not been called");
   if (!betas || !pose || !joints17_out) return fail(JRR_ERR_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = forward_common(m, w, betas, pose, kind, false, st)) return rc;
-  if (int rc = launch_skin_fwd(m, w, nullptr, nullptr, true, st)) return rc;
-  return launch_loss_seed(m, w, nullptr, 1, 0.f, joints17_out, st);
+  if (int rc = loss_forward(m, w, betas, pose, kind, 0, nullptr, st, nullptr, nullptr)) return rc;
+  return launch_loss_seed(m, w, m->fused_fwd, nullptr, 1, 0.f, joints17_out, st);
 }
 
 extern "C" int jrr_critic_forward(JrrModel* m, int64_t B, const float* rot6d, float* scores_out, void* ws,
@@ -218,14 +236,12 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
     JRR_CUDA(cudaEventRecord(m->ev_join, m->side));
   }
   JRR_MARK();
-  // forward: chain | blend GEMM | skinning fused with the 17x6890 regressor reduction | loss seed
-  if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, x6, JRR_POSE_ROT6D, w.AT, w.feat_hi, w.feat_lo, nullptr, st)) return rc;
+  // forward: chain | blend GEMM with the skinning + 17x6890 regressor epilogue | loss seed
+  // (events: pose_fwd | blend_gemm_fwd [fused: the whole forward] | skin_fwd [fused: empty])
+  if (int rc = loss_forward(m, w, betas, x6, JRR_POSE_ROT6D, 1, w.vpT, st, ev ? &ev[1] : nullptr, ev ? &ev[2] : nullptr)) return rc;
+  mark = 3;
   JRR_MARK();
-  if (int rc = blend_forward_gemm(m, w, st)) return rc;
-  JRR_MARK();
-  if (int rc = launch_skin_fwd(m, w, nullptr, nullptr, true, st)) return rc;
-  JRR_MARK();
-  if (int rc = launch_loss_seed(m, w, gt_mm, B_logical, w_joint, nullptr, st)) return rc;
+  if (int rc = launch_loss_seed(m, w, m->fused_fwd, gt_mm, B_logical, w_joint, nullptr, st)) return rc;
   JRR_MARK();
   // backward: regressor-transpose seed + skinning | dA reduction | blend GEMM
   if (int rc = launch_skin_bwd(m, w, nullptr, true, false, st)) return rc;
@@ -300,11 +316,10 @@ extern "C" int jrr_regressor_grad_accumulate(JrrModel* m, int64_t B, int64_t B_l
   if (!x6 || !betas || !gt_mm || !G_accum) return fail(JRR_ERR_INVALID, "null argument");
   if (B_logical < B) return fail(JRR_ERR_INVALID, "B_logical must be >= B");
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = forward_common(m, w, betas, x6, JRR_POSE_ROT6D, false, st)) return rc;
-  // vertices kept pose-contiguous in the (otherwise idle) dvp_hi buffer
+  // skinned vertices kept pose-contiguous in the (otherwise idle) dvp_hi buffer
   float* vT = w.dvp_hi;
-  if (int rc = launch_skin_fwd(m, w, nullptr, vT, true, st)) return rc;
-  if (int rc = launch_loss_seed(m, w, gt_mm, B_logical, 1.f, nullptr, st)) return rc;
+  if (int rc = loss_forward(m, w, betas, x6, JRR_POSE_ROT6D, 2, vT, st, nullptr, nullptr)) return rc;
+  if (int rc = launch_loss_seed(m, w, m->fused_fwd, gt_mm, B_logical, 1.f, nullptr, st)) return rc;
   if (int rc = launch_regressor_accumulate(m, w, vT, G_accum, st)) return rc;
   if (loss_accum)
     if (int rc = launch_loss_finish(w, B_logical, 1.f, 0.f, false, nullptr, loss_accum, st)) return rc;

@@ -14,95 +14,14 @@
 // backward (smplx.lbs blend_shapes + pose_feature @ posedirs, reached through
 // scripts/smpl.py:72-74), and the 768->1024->1024 layers of the pose critic and their input
 // gradients (scripts/discriminator.py:24-30,41).
-#include <cuda.h>
-
 #include "jrr_internal.cuh"
+#include "jrr_tc.cuh"
 
 namespace jrr {
 
 constexpr int BM = 128;
 constexpr int BK = 32;  // fp32 per stage row = 128 bytes = one swizzle atom
 constexpr int TC_THREADS = 192;
-
-// ------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float v[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ float tf32_hi_g(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-// K-major, SWIZZLE_128B smem matrix descriptor (rows of 128 bytes, 8-row groups 1024 B apart)
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3ffff) >> 4);          // start address  [0,14)
-  d |= (uint64_t)0 << 16;                           // leading byte offset (unused for SW128 K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset [32,46)
-  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
-  return d;
-}
 
 struct TcParams {
   int64_t M, N, K;     // K = per-split extent
@@ -309,7 +228,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_tensor_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(JRR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -323,7 +242,7 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
   return JRR_OK;
 }
 
-static int num_sms(int device) {
+int device_num_sms(int device) {
   static int cached[64] = {0};
   if (device < 0 || device >= 64) device = 0;
   if (!cached[device]) cudaDeviceGetAttribute(&cached[device], cudaDevAttrMultiProcessorCount, device);
@@ -335,10 +254,10 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   CUtensorMap mAh, mAl, mBh, mBl;
   const int64_t Ktot = g.K * g.ksplit;
-  if (int rc = make_map(&mAh, g.A_hi, g.M, Ktot, g.lda, BM)) return rc;
-  if (int rc = make_map(&mAl, g.A_lo, g.M, Ktot, g.lda, BM)) return rc;
-  if (int rc = make_map(&mBh, g.B_hi, g.N, Ktot, g.ldb, BN)) return rc;
-  if (int rc = make_map(&mBl, g.B_lo, g.N, Ktot, g.ldb, BN)) return rc;
+  if (int rc = make_tensor_map_2d(&mAh, g.A_hi, g.M, Ktot, g.lda, BM)) return rc;
+  if (int rc = make_tensor_map_2d(&mAl, g.A_lo, g.M, Ktot, g.lda, BM)) return rc;
+  if (int rc = make_tensor_map_2d(&mBh, g.B_hi, g.N, Ktot, g.ldb, BN)) return rc;
+  if (int rc = make_tensor_map_2d(&mBl, g.B_lo, g.N, Ktot, g.ldb, BN)) return rc;
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.ksplit = g.ksplit;
   p.m_tiles = (int)(g.M / BM);
@@ -347,7 +266,7 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   auto kern = gemm_tc_kernel<BN, EPI>;
   JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
-  const int grid = std::min(tiles, num_sms(m->device));
+  const int grid = std::min(tiles, device_num_sms(m->device));
   kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
   JRR_LAUNCH_CHECK();
   return JRR_OK;

@@ -135,6 +135,7 @@ struct JrrModel {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_critic = true;
+  bool fused_fwd = true;   // loss path: skinning + regressor in the blend GEMM's epilogue
   std::vector<void*> allocs;
 };
 
@@ -197,8 +198,12 @@ int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st);
 
 int launch_skin_fwd(const JrrModel* m, const Workspace& w, float* vertices_out, float* vT_out,
                     bool want_part, cudaStream_t st);
-int launch_loss_seed(const JrrModel* m, const Workspace& w, const float* gt_mm, int64_t B_logical,
-                     float w_joint, float* joints17_out, cudaStream_t st);
+int launch_loss_seed(const JrrModel* m, const Workspace& w, bool fused_partials, const float* gt_mm,
+                     int64_t B_logical, float w_joint, float* joints17_out, cudaStream_t st);
+// fused blend GEMM + skinning + regressor partial sums (jrr_fused_fwd.cu)
+int fused_fwd_slots(int64_t BP, int num_sms);
+int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store /*0 none, 1 vp, 2 skinned v*/,
+                     float* vT_out, cudaStream_t st);
 int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_g,
                     bool use_x, cudaStream_t st);
 int launch_dA_reduce(const JrrModel* m, const Workspace& w, cudaStream_t st);

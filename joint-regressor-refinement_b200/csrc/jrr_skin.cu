@@ -186,16 +186,23 @@ skin_fwd_kernel(const VtxRec* __restrict__ vrec, const int* __restrict__ perm,
 // pred = sum of range partials (fixed order); pc = pred - pred[0]; diff = pc - gt/1000;
 // g = w_joint * 2 diff / (51 B_logical); pelvis adjustment; per-CTA loss partial.
 __global__ void __launch_bounds__(SK_THREADS)
-loss_seed_kernel(const float* __restrict__ part, const float* __restrict__ gt_mm, int64_t B,
-                 int64_t BP, float scale, float* __restrict__ gT, float* __restrict__ joints17_out,
-                 float* __restrict__ loss_part) {
+loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T, int G,
+                 const float* __restrict__ gt_mm, int64_t B, int64_t BP, float scale,
+                 float* __restrict__ gT, float* __restrict__ joints17_out, float* __restrict__ loss_part) {
   __shared__ float red[SK_THREADS / 32];
   const int64_t b = (int64_t)blockIdx.x * SK_THREADS + threadIdx.x;
+  if (nslots <= 0) {
+    // partials written by the fused forward kernel: two per CTA segment of this pose block
+    const int mb = blockIdx.x;  // SK_THREADS == 128 == pose block of the fused kernel
+    const int c0 = (int)(((int64_t)mb * n_tiles * G) / T);
+    const int c1 = (int)((((int64_t)(mb + 1) * n_tiles - 1) * G) / T);
+    nslots = 2 * (c1 - c0 + 1);
+  }
   float pred[NACC];
 #pragma unroll
   for (int a = 0; a < NACC; a++) {
     float p = 0.f;
-    for (int s = 0; s < NSPLIT; s++) p += part[((int64_t)s * NACC + a) * BP + b];
+    for (int s = 0; s < nslots; s++) p += part[((int64_t)s * NACC + a) * BP + b];
     pred[a] = p;
   }
   float loss = 0.f;
@@ -527,12 +534,12 @@ int launch_skin_fwd(const JrrModel* m, const Workspace& w, float* vertices_out, 
   return JRR_OK;
 }
 
-int launch_loss_seed(const JrrModel* m, const Workspace& w, const float* gt_mm, int64_t B_logical,
-                     float w_joint, float* joints17_out, cudaStream_t st) {
-  (void)m;
+int launch_loss_seed(const JrrModel* m, const Workspace& w, bool fused_partials, const float* gt_mm,
+                     int64_t B_logical, float w_joint, float* joints17_out, cudaStream_t st) {
   dim3 grid((unsigned)(w.BP / SK_THREADS)), block(SK_THREADS);
   const float scale = gt_mm != nullptr ? w_joint * 2.f / (51.f * (float)B_logical) : 0.f;
-  loss_seed_kernel<<<grid, block, 0, st>>>(w.part, gt_mm, w.B, w.BP, scale,
+  const int n_tiles = VP / 64, T = (int)(w.BP / 128) * n_tiles, G = T < m->num_sms ? T : m->num_sms;
+  loss_seed_kernel<<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, gt_mm, w.B, w.BP, scale,
                                            gt_mm != nullptr ? w.gT : nullptr, joints17_out,
                                            w.loss_part);
   JRR_LAUNCH_CHECK();
