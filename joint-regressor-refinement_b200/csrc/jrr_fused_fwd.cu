@@ -19,6 +19,7 @@
 
 #include "jrr_internal.cuh"
 #include "jrr_tc.cuh"
+#include "jrr_f32x2.cuh"
 
 namespace jrr {
 
@@ -50,7 +51,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
                  const VtxRec* __restrict__ vrec, const float* __restrict__ AT, int64_t BP, int m_tiles,
                  int n_tiles, float* __restrict__ vT_out, float* __restrict__ part) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still provably shared
   float4* srec = (float4*)(smem + F_STAGES * F_STAGE_BYTES);            // [2][448]
   uint64_t* bars = (uint64_t*)(smem + F_STAGES * F_STAGE_BYTES + 2 * F_REC_F4 * 16);
   uint64_t* full_bar = bars;                      // [F_STAGES]
@@ -148,14 +149,19 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
     const int etid = threadIdx.x - 64;  // 0..255
     int acc = 0;
     uint32_t acc_phase = 0;
-    float A[4][12];
-    float sum[NACC];
+    // joint transforms of the 4 cached slots: rows 0/1 packed per column, row 2 scalar
+    f32x2 A01[4][4];
+    float A2[4][4];
+    // regressor accumulators: sum2[c][p] = (joint 2p, joint 2p+1) of coordinate c
+    f32x2 sum2[3][9];
 #pragma unroll
-    for (int a = 0; a < NACC; a++) sum[a] = 0.f;
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int p = 0; p < 9; p++) sum2[c][p] = pk2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 4; k++)
 #pragma unroll
-      for (int e = 0; e < 12; e++) A[k][e] = 0.f;
+      for (int c = 0; c < 4; c++) { A01[k][c] = pk2(0.f, 0.f); A2[k][c] = 0.f; }
 
     if (t_begin < t_end) {
       const float4* g = reinterpret_cast<const float4*>(vrec + (t_begin % n_tiles) * FV);
@@ -181,59 +187,93 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
       float nxt[12];
       tc_ld12_issue(trow, nxt);
       tc_wait_ld12(nxt);
+      // rows of the pose-contiguous vertex store this warp walks (3 rows per vertex)
+      float* vout = (STORE != FSTORE_NONE) ? vT_out + (int64_t)(3 * (nb * FV + h * 32)) * BP + b : nullptr;
+      const float4* rh = rec + (h * 32) * 7;     // records of my 32 vertices
 #pragma unroll 1
-      for (int g = 0; g < 8; g++) {
+      for (int g = 0; g < 8; g++, rh += 4 * 7) {
         float vp[12];
 #pragma unroll
         for (int e = 0; e < 12; e++) vp[e] = nxt[e];
         if (g + 1 < 8) tc_ld12_issue(trow + (g + 1) * 12, nxt);   // lands while this group is skinned
+        float4 r0[4];
+        float w3[4];
+        uint32_t meta[4], many = 0;
 #pragma unroll
         for (int ii = 0; ii < 4; ii++) {
-          const int lv = h * 32 + g * 4 + ii;                 // vertex within the tile
-          const int i = nb * FV + lv;                         // packed vertex id
-          const float4 r0 = rec[lv * 7], r1 = rec[lv * 7 + 1];
-          uint32_t meta = __float_as_uint(r0.x);
-          const float w0 = r0.y, w1 = r0.z, w2 = r0.w, w3 = r1.x;
-          if (g == 0 && ii == 0) meta |= 0xFu << 20;          // (re)load all slots at the start of my half
+          r0[ii] = rh[ii * 7];
+          w3[ii] = rh[ii * 7 + 1].x;
+          meta[ii] = __float_as_uint(r0[ii].x);
+          many |= meta[ii];
+        }
+        if (g == 0) { meta[0] |= 0xFu << 20; many |= 0xFu << 20; }   // (re)load all slots at the start of my half
+        const bool any_reload = (many >> 20) & 0xFu;
+        const bool any_col = (many >> 24) & 1u;
+        float v[4][3];
+        // ---- skinning.  Fast path: no slot changes inside the group -> branch-free, the four
+        // vertices interleave in the instruction stream.
+#define JRR_SKIN_VERTEX(ii)                                                                         \
+        {                                                                                           \
+          const float x = vp[ii * 3 + 0], y = vp[ii * 3 + 1], z = vp[ii * 3 + 2];                   \
+          const f32x2 xx = pk2(x, x), yy = pk2(y, y), zz = pk2(z, z);                               \
+          const float wk[4] = {r0[ii].y, r0[ii].z, r0[ii].w, w3[ii]};                               \
+          f32x2 v01 = pk2(0.f, 0.f);                                                                \
+          float v2 = 0.f;                                                                           \
+          _Pragma("unroll") for (int k = 0; k < 4; k++) {                                           \
+            const f32x2 y01 = fma2(A01[k][2], zz, fma2(A01[k][1], yy, fma2(A01[k][0], xx, A01[k][3]))); \
+            const float y2 = fmaf(A2[k][2], z, fmaf(A2[k][1], y, fmaf(A2[k][0], x, A2[k][3])));     \
+            const f32x2 ww = pk2(wk[k], wk[k]);                                                     \
+            v01 = (k == 0) ? mul2(ww, y01) : fma2(ww, y01, v01);                                    \
+            v2 = (k == 0) ? wk[k] * y2 : fmaf(wk[k], y2, v2);                                       \
+          }                                                                                         \
+          upk2(v01, v[ii][0], v[ii][1]);                                                            \
+          v[ii][2] = v2;                                                                            \
+        }
+        if (!any_reload) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            if ((meta >> (20 + k)) & 1u) {
-              const int j = (meta >> (5 * k)) & 31u;
-              const float* src = AT + (int64_t)(j * 12) * BP + b;
+          for (int ii = 0; ii < 4; ii++) JRR_SKIN_VERTEX(ii)
+        } else {
 #pragma unroll
-              for (int e = 0; e < 12; e++) A[k][e] = src[(int64_t)e * BP];
+          for (int ii = 0; ii < 4; ii++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              if ((meta[ii] >> (20 + k)) & 1u) {
+                const int j = (meta[ii] >> (5 * k)) & 31u;
+                const float* src = AT + (int64_t)(j * 12) * BP + b;
+                float a[12];
+#pragma unroll
+                for (int e = 0; e < 12; e++) { a[e] = *src; src += BP; }
+#pragma unroll
+                for (int c = 0; c < 4; c++) { A01[k][c] = pk2(a[c], a[4 + c]); A2[k][c] = a[8 + c]; }
+              }
             }
+            JRR_SKIN_VERTEX(ii)
           }
-          const float x = vp[ii * 3 + 0], y = vp[ii * 3 + 1], z = vp[ii * 3 + 2];
-          float v[3];
+        }
+#undef JRR_SKIN_VERTEX
+        if (STORE == FSTORE_VP) {
 #pragma unroll
-          for (int r = 0; r < 3; r++) {
-            const float t0 = w0 * A[0][r * 4 + 0] + w1 * A[1][r * 4 + 0] + w2 * A[2][r * 4 + 0] + w3 * A[3][r * 4 + 0];
-            const float t1 = w0 * A[0][r * 4 + 1] + w1 * A[1][r * 4 + 1] + w2 * A[2][r * 4 + 1] + w3 * A[3][r * 4 + 1];
-            const float t2 = w0 * A[0][r * 4 + 2] + w1 * A[1][r * 4 + 2] + w2 * A[2][r * 4 + 2] + w3 * A[3][r * 4 + 2];
-            const float t3 = w0 * A[0][r * 4 + 3] + w1 * A[1][r * 4 + 3] + w2 * A[2][r * 4 + 3] + w3 * A[3][r * 4 + 3];
-            v[r] = t0 * x + t1 * y + t2 * z + t3;
-          }
-          if (STORE == FSTORE_VP) {
-            vT_out[(int64_t)(3 * i + 0) * BP + b] = x;
-            vT_out[(int64_t)(3 * i + 1) * BP + b] = y;
-            vT_out[(int64_t)(3 * i + 2) * BP + b] = z;
-          } else if (STORE == FSTORE_V) {
+          for (int e = 0; e < 12; e++) { *vout = vp[e]; vout += BP; }
+        } else if (STORE == FSTORE_V) {
 #pragma unroll
-            for (int r = 0; r < 3; r++) vT_out[(int64_t)(3 * i + r) * BP + b] = v[r];
-          }
-          if ((meta >> 24) & 1u) {
-            float jh[JH_STRIDE];
+          for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+            for (int r = 0; r < 3; r++) { *vout = v[ii][r]; vout += BP; }
+        }
+        // ---- 17x6890 regressor reduction (zero columns contribute zeros; skipped per group)
+        if (any_col) {
+#pragma unroll
+          for (int ii = 0; ii < 4; ii++) {
+            const f32x2 vb[3] = {pk2(v[ii][0], v[ii][0]), pk2(v[ii][1], v[ii][1]), pk2(v[ii][2], v[ii][2])};
 #pragma unroll
             for (int qq = 0; qq < JH_STRIDE / 4; qq++) {
-              const float4 tt = rec[lv * 7 + 2 + qq];
-              jh[qq * 4 + 0] = tt.x; jh[qq * 4 + 1] = tt.y; jh[qq * 4 + 2] = tt.z; jh[qq * 4 + 3] = tt.w;
-            }
+              const float4 tt = rh[ii * 7 + 2 + qq];
+              const f32x2 ja = pk2(tt.x, tt.y), jb = pk2(tt.z, tt.w);
 #pragma unroll
-            for (int j = 0; j < NH; j++) {
-              sum[j * 3 + 0] = fmaf(jh[j], v[0], sum[j * 3 + 0]);
-              sum[j * 3 + 1] = fmaf(jh[j], v[1], sum[j * 3 + 1]);
-              sum[j * 3 + 2] = fmaf(jh[j], v[2], sum[j * 3 + 2]);
+              for (int c = 0; c < 3; c++) {
+                if (2 * qq < 9) sum2[c][2 * qq] = fma2(ja, vb[c], sum2[c][2 * qq]);
+                if (2 * qq + 1 < 9) sum2[c][2 * qq + 1] = fma2(jb, vb[c], sum2[c][2 * qq + 1]);
+              }
             }
           }
         }
@@ -249,7 +289,15 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
         const int seg = blockIdx.x - fused_cta_of_tile(mb * n_tiles, T, G);
         float* dst = part + ((int64_t)(seg * 2 + h) * NACC) * BP + b;
 #pragma unroll
-        for (int a = 0; a < NACC; a++) { dst[(int64_t)a * BP] = sum[a]; sum[a] = 0.f; }
+        for (int p = 0; p < 9; p++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            float lo, hi;
+            upk2(sum2[c][p], lo, hi);
+            dst[(int64_t)((2 * p) * 3 + c) * BP] = lo;
+            if (2 * p + 1 < NH) dst[(int64_t)((2 * p + 1) * 3 + c) * BP] = hi;
+            sum2[c][p] = pk2(0.f, 0.f);
+          }
       }
       if (has_next) {
         float4* d = srec + (buf ^ 1) * F_REC_F4;
