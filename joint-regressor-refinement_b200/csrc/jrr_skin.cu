@@ -13,6 +13,7 @@
 // (scripts/utils.py:96-98), move_pelvis + MSELoss (scripts/utils.py:106-114,
 // scripts/optimize.py:238-239) and their autograd backward (scripts/optimize.py:264).
 #include "jrr_internal.cuh"
+#include "jrr_f32x2.cuh"
 
 namespace jrr {
 
@@ -264,32 +265,44 @@ skin_bwd_kernel(const VtxRec* __restrict__ vrec, const int* __restrict__ perm,
   const int s = blockIdx.y;
   const int i0 = s * VS_B;
   constexpr int NT = VS_B / VT;
-  int fl = range_flush_base[s];
+  float* flush_dst = dAflush + (int64_t)range_flush_base[s] * 12 * BP + b;
 
-  float g[USE_G ? NACC : 1];
+  // loss seed, packed over joint pairs: gp[c][p] = (g[2p][c], g[2p+1][c])
+  f32x2 gp[USE_G ? 3 : 1][USE_G ? 9 : 1];
   if (USE_G) {
 #pragma unroll
-    for (int a = 0; a < NACC; a++) g[USE_G ? a : 0] = gT[(int64_t)a * BP + b];
+    for (int p = 0; p < 9; p++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float lo = gT[(int64_t)((2 * p) * 3 + c) * BP + b];
+        const float hi = (2 * p + 1 < NH) ? gT[(int64_t)((2 * p + 1) * 3 + c) * BP + b] : 0.f;
+        gp[USE_G ? c : 0][USE_G ? p : 0] = pk2(lo, hi);
+      }
   }
-  float AR[4][9], dA[4][12];
+  // cached joint rotations (rows packed over columns 0/1, column 2 scalar) and the dA slot
+  // accumulators (row r: columns (0,1) and (2,3))
+  f32x2 AR01[4][3], dA01[4][3], dA23[4][3];
+  float AR2[4][3];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < 4; k++)
 #pragma unroll
-    for (int e = 0; e < 9; e++) AR[k][e] = 0.f;
-#pragma unroll
-    for (int e = 0; e < 12; e++) dA[k][e] = 0.f;
-  }
+    for (int r = 0; r < 3; r++) {
+      AR01[k][r] = pk2(0.f, 0.f); AR2[k][r] = 0.f;
+      dA01[k][r] = pk2(0.f, 0.f); dA23[k][r] = pk2(0.f, 0.f);
+    }
   {
     const float4* gsrc = reinterpret_cast<const float4*>(vrec + i0);
     for (int e = tid; e < TILE_F4; e += SK_THREADS) sconst[e] = __ldg(gsrc + e);
   }
   float nx[3 * GV];
-  load_vp_group(vpT, BP, b, i0, nx);
+  const float* vsrc = vpT + (int64_t)(3 * i0) * BP + b;      // walks 3 rows per vertex
+#pragma unroll
+  for (int q = 0; q < 3 * GV; q++) { nx[q] = *vsrc; vsrc += BP; }
   __syncthreads();
 
 #pragma unroll 1
   for (int t = 0; t < NT; t++) {
-    const RecView rv{sconst + (t & 1) * TILE_F4};
+    const float4* rt = sconst + (t & 1) * TILE_F4;
     const int it0 = i0 + t * VT;
     const bool has_next = t + 1 < NT;
     float4 pf0 = make_float4(0, 0, 0, 0), pf1 = pf0;
@@ -321,73 +334,135 @@ skin_bwd_kernel(const VtxRec* __restrict__ vrec, const int* __restrict__ perm,
       float cur[3 * GV];
 #pragma unroll
       for (int q = 0; q < 3 * GV; q++) cur[q] = nx[q];
-      const int inext = it0 + (sub + 1) * GV;
-      if (inext < i0 + VS_B) load_vp_group(vpT, BP, b, inext, nx);
+      if (it0 + (sub + 1) * GV < i0 + VS_B) {
+#pragma unroll
+        for (int q = 0; q < 3 * GV; q++) { nx[q] = *vsrc; vsrc += BP; }
+      }
+      const float4* rh = rt + (sub * GV) * 7;
+      float4 r0[GV];
+      float w3[GV];
+      uint32_t meta[GV], many = 0;
 #pragma unroll
       for (int ii = 0; ii < GV; ii++) {
-        const int lv = sub * GV + ii;
-        uint32_t meta; float w[4]; int xptr, xcnt;
-        rv.head(lv, meta, w, xptr, xcnt);
-        const bool first = (meta >> 25) & 1u;
+        r0[ii] = rh[ii * 7];
+        const float4 r1 = rh[ii * 7 + 1];
+        w3[ii] = r1.x;
+        meta[ii] = __float_as_uint(r0[ii].x);
+        many |= meta[ii];
+      }
+      const bool any_reload = (many >> 20) & 0xFu;
+      // ---- per-vertex gradient dv
+      float dv[GV][3];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          if ((meta >> (20 + k)) & 1u) {
-            if (!first) {
-              float* dst = dAflush + (int64_t)fl * 12 * BP + b;
+      for (int ii = 0; ii < GV; ii++) { dv[ii][0] = 0.f; dv[ii][1] = 0.f; dv[ii][2] = 0.f; }
+      if (USE_G && ((many >> 24) & 1u)) {
 #pragma unroll
-              for (int e = 0; e < 12; e++) { dst[(int64_t)e * BP] = dA[k][e]; dA[k][e] = 0.f; }
-              fl++;
+        for (int ii = 0; ii < GV; ii++) {
+          f32x2 a[3] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
+#pragma unroll
+          for (int qq = 0; qq < JH_STRIDE / 4; qq++) {
+            const float4 tt = rh[ii * 7 + 2 + qq];
+            const f32x2 ja = pk2(tt.x, tt.y), jb = pk2(tt.z, tt.w);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              if (2 * qq < 9) a[c] = fma2(ja, gp[USE_G ? c : 0][USE_G ? 2 * qq : 0], a[c]);
+              if (2 * qq + 1 < 9) a[c] = fma2(jb, gp[USE_G ? c : 0][USE_G ? 2 * qq + 1 : 0], a[c]);
             }
-            const int j = (meta >> (5 * k)) & 31u;
-            const float* src = AT + (int64_t)(j * 12) * BP + b;
+          }
 #pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-              for (int c = 0; c < 3; c++) AR[k][r * 3 + c] = src[(int64_t)(r * 4 + c) * BP];
+          for (int c = 0; c < 3; c++) {
+            float lo, hi;
+            upk2(a[c], lo, hi);
+            dv[ii][c] = lo + hi;
           }
         }
-        const float vp0 = cur[ii * 3 + 0], vp1 = cur[ii * 3 + 1], vp2 = cur[ii * 3 + 2];
-        float dv[3] = {0.f, 0.f, 0.f};
-        if (USE_G && ((meta >> 24) & 1u)) {
-          float jh[JH_STRIDE];
-          rv.jh(lv, jh);
+      }
+      if (USE_DV) {
 #pragma unroll
-          for (int j = 0; j < NH; j++) {
-            dv[0] = fmaf(jh[j], g[USE_G ? j * 3 + 0 : 0], dv[0]);
-            dv[1] = fmaf(jh[j], g[USE_G ? j * 3 + 1 : 0], dv[1]);
-            dv[2] = fmaf(jh[j], g[USE_G ? j * 3 + 2 : 0], dv[2]);
-          }
-        }
-        if (USE_DV) {
+        for (int ii = 0; ii < GV; ii++)
 #pragma unroll
-          for (int c = 0; c < 3; c++) dv[c] += tile_in[tid * TILE_LD + lv * 3 + c];
-        }
-        if (USE_X && ((meta >> 26) & 1u)) {
+          for (int c = 0; c < 3; c++) dv[ii][c] += tile_in[tid * TILE_LD + (sub * GV + ii) * 3 + c];
+      }
+      if (USE_X && ((many >> 26) & 1u)) {
+#pragma unroll
+        for (int ii = 0; ii < GV; ii++) {
+          const float4 r1 = rh[ii * 7 + 1];
+          const int xptr = __float_as_int(r1.y), xcnt = __float_as_int(r1.z);
           for (int q = 0; q < xcnt; q++) {
             const int src = __ldg(vx_src + xptr + q);
             const float cf = __ldg(vx_coef + xptr + q);
 #pragma unroll
-            for (int c = 0; c < 3; c++) dv[c] = fmaf(cf, d30T[(int64_t)(src * 3 + c) * BP + b], dv[c]);
-          }
-        }
-        float TR[9];
-#pragma unroll
-        for (int e = 0; e < 9; e++) TR[e] = w[0] * AR[0][e] + w[1] * AR[1][e] + w[2] * AR[2][e] + w[3] * AR[3][e];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-          tile_out[tid * TILE_LD + lv * 3 + c] = TR[0 * 3 + c] * dv[0] + TR[1 * 3 + c] * dv[1] + TR[2 * 3 + c] * dv[2];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-#pragma unroll
-          for (int r = 0; r < 3; r++) {
-            const float wd = w[k] * dv[r];
-            dA[k][r * 4 + 0] = fmaf(wd, vp0, dA[k][r * 4 + 0]);
-            dA[k][r * 4 + 1] = fmaf(wd, vp1, dA[k][r * 4 + 1]);
-            dA[k][r * 4 + 2] = fmaf(wd, vp2, dA[k][r * 4 + 2]);
-            dA[k][r * 4 + 3] += wd;
+            for (int c = 0; c < 3; c++) dv[ii][c] = fmaf(cf, d30T[(int64_t)(src * 3 + c) * BP + b], dv[ii][c]);
           }
         }
       }
+      // ---- dvp = sum_k w_k AR_k^T dv   and   dA_k += w_k dv (x) [vp;1]
+#define JRR_BWD_VERTEX(ii)                                                                            \
+      {                                                                                               \
+        const float wk[4] = {r0[ii].y, r0[ii].z, r0[ii].w, w3[ii]};                                   \
+        const f32x2 d0 = pk2(dv[ii][0], dv[ii][0]), d1 = pk2(dv[ii][1], dv[ii][1]),                   \
+                    d2 = pk2(dv[ii][2], dv[ii][2]);                                                   \
+        const f32x2 vp01 = pk2(cur[ii * 3 + 0], cur[ii * 3 + 1]), vp21 = pk2(cur[ii * 3 + 2], 1.f);   \
+        f32x2 o01 = pk2(0.f, 0.f);                                                                    \
+        float o2 = 0.f;                                                                               \
+        _Pragma("unroll") for (int k = 0; k < 4; k++) {                                               \
+          const f32x2 u01 = fma2(AR01[k][2], d2, fma2(AR01[k][1], d1, mul2(AR01[k][0], d0)));         \
+          const float u2 = fmaf(AR2[k][2], dv[ii][2], fmaf(AR2[k][1], dv[ii][1], AR2[k][0] * dv[ii][0])); \
+          const f32x2 ww = pk2(wk[k], wk[k]);                                                         \
+          o01 = fma2(ww, u01, o01);                                                                   \
+          o2 = fmaf(wk[k], u2, o2);                                                                   \
+          _Pragma("unroll") for (int r = 0; r < 3; r++) {                                             \
+            const float wd = wk[k] * dv[ii][r];                                                       \
+            const f32x2 wdd = pk2(wd, wd);                                                            \
+            dA01[k][r] = fma2(wdd, vp01, dA01[k][r]);                                                 \
+            dA23[k][r] = fma2(wdd, vp21, dA23[k][r]);                                                 \
+          }                                                                                           \
+        }                                                                                             \
+        float o0, o1;                                                                                 \
+        upk2(o01, o0, o1);                                                                            \
+        float* to = tile_out + tid * TILE_LD + (sub * GV + ii) * 3;                                   \
+        to[0] = o0; to[1] = o1; to[2] = o2;                                                           \
+      }
+      if (!any_reload) {
+#pragma unroll
+        for (int ii = 0; ii < GV; ii++) JRR_BWD_VERTEX(ii)
+      } else {
+#pragma unroll
+        for (int ii = 0; ii < GV; ii++) {
+          const bool first = (meta[ii] >> 25) & 1u;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if ((meta[ii] >> (20 + k)) & 1u) {
+              if (!first) {
+                // this slot's joint changes: its accumulated dA leaves as one flush event
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                  float a0, a1, a2, a3;
+                  upk2(dA01[k][r], a0, a1);
+                  upk2(dA23[k][r], a2, a3);
+                  flush_dst[(int64_t)(r * 4 + 0) * BP] = a0;
+                  flush_dst[(int64_t)(r * 4 + 1) * BP] = a1;
+                  flush_dst[(int64_t)(r * 4 + 2) * BP] = a2;
+                  flush_dst[(int64_t)(r * 4 + 3) * BP] = a3;
+                  dA01[k][r] = pk2(0.f, 0.f);
+                  dA23[k][r] = pk2(0.f, 0.f);
+                }
+                flush_dst += 12 * BP;
+              }
+              const int j = (meta[ii] >> (5 * k)) & 31u;
+              const float* src = AT + (int64_t)(j * 12) * BP + b;
+#pragma unroll
+              for (int r = 0; r < 3; r++) {
+                const float a0 = src[(int64_t)(r * 4 + 0) * BP], a1 = src[(int64_t)(r * 4 + 1) * BP];
+                AR01[k][r] = pk2(a0, a1);
+                AR2[k][r] = src[(int64_t)(r * 4 + 2) * BP];
+              }
+            }
+          }
+          JRR_BWD_VERTEX(ii)
+        }
+      }
+#undef JRR_BWD_VERTEX
     }
     __syncthreads();
     // dvp rows (A operand of the backward blend GEMM, K-major, tf32 hi/lo), coalesced
@@ -413,10 +488,17 @@ skin_bwd_kernel(const VtxRec* __restrict__ vrec, const int* __restrict__ perm,
   }
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    float* dst = dAflush + (int64_t)fl * 12 * BP + b;
 #pragma unroll
-    for (int e = 0; e < 12; e++) dst[(int64_t)e * BP] = dA[k][e];
-    fl++;
+    for (int r = 0; r < 3; r++) {
+      float a0, a1, a2, a3;
+      upk2(dA01[k][r], a0, a1);
+      upk2(dA23[k][r], a2, a3);
+      flush_dst[(int64_t)(r * 4 + 0) * BP] = a0;
+      flush_dst[(int64_t)(r * 4 + 1) * BP] = a1;
+      flush_dst[(int64_t)(r * 4 + 2) * BP] = a2;
+      flush_dst[(int64_t)(r * 4 + 3) * BP] = a3;
+    }
+    flush_dst += 12 * BP;
   }
 }
 
