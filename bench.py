@@ -294,10 +294,13 @@ def main():
     BP = (B + 127) // 128 * 128
     tf32_peak = pk["bf16_sustained"] / 2           # dense TF32 = half the bf16 rate; kernels timed inside a long step
     kern = []
+    fused_fwd = acc.get("skin_fwd", 0.0) < 0.01      # skinning + regressor ran in the GEMM epilogue
     for name, ms in acc.items():
-        if ms <= 0:
+        if ms <= 0 or (fused_fwd and name == "skin_fwd"):
             continue
         e = {"name": name, "ms": round(ms, 4)}
+        if name == "blend_gemm_fwd" and fused_fwd:
+            e["name"] = "fused_fwd(blend_gemm+skinning+regressor)"
         if name == "blend_gemm_fwd":
             fl = 3 * 2.0 * B * 20670 * 218
             e.update(bound="tensor", achieved=fl / (ms * 1e-3) / 1e12, peak=tf32_peak, unit="TFLOP/s")

@@ -199,12 +199,14 @@ loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T,
     const int c1 = (int)((((int64_t)(mb + 1) * n_tiles - 1) * G) / T);
     nslots = 2 * (c1 - c0 + 1);
   }
+  // fixed-order sum over the partial slots; slot-outer so the 51 loads of a slot are in flight together
   float pred[NACC];
 #pragma unroll
-  for (int a = 0; a < NACC; a++) {
-    float p = 0.f;
-    for (int s = 0; s < nslots; s++) p += part[((int64_t)s * NACC + a) * BP + b];
-    pred[a] = p;
+  for (int a = 0; a < NACC; a++) pred[a] = 0.f;
+  for (int s = 0; s < nslots; s++) {
+    const float* src = part + (int64_t)s * NACC * BP + b;
+#pragma unroll
+    for (int a = 0; a < NACC; a++) pred[a] += src[(int64_t)a * BP];
   }
   float loss = 0.f;
   if (b < B) {
@@ -576,10 +578,16 @@ __global__ void loss_finish_kernel(const float* __restrict__ lp_joint, int n_joi
                                    const float* __restrict__ lp_pose, int n_pose, float sp,
                                    float wj, float wp, float* __restrict__ loss_out,
                                    float* __restrict__ loss_accum) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one warp; lane-strided partial sums + xor-shuffle tree: a fixed summation order
+  const int lane = threadIdx.x;
   float a = 0.f, p = 0.f;
-  for (int i = 0; i < n_joint; i++) a += lp_joint[i];
-  for (int i = 0; i < n_pose; i++) p += lp_pose[i];
+  for (int i = lane; i < n_joint; i += 32) a += lp_joint[i];
+  for (int i = lane; i < n_pose; i += 32) p += lp_pose[i];
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    p += __shfl_xor_sync(0xffffffffu, p, o);
+  }
+  if (lane != 0) return;
   a *= sj;
   p *= sp;
   if (loss_out != nullptr) {
