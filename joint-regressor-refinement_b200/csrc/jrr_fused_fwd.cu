@@ -163,6 +163,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
 #pragma unroll
       for (int c = 0; c < 4; c++) { A01[k][c] = pk2(0.f, 0.f); A2[k][c] = 0.f; }
 
+    int cached_joint[4] = {-1, -1, -1, -1};   // joints whose transforms A01/A2 hold (for the current pose block)
     if (t_begin < t_end) {
       const float4* g = reinterpret_cast<const float4*>(vrec + (t_begin % n_tiles) * FV);
       for (int e = etid; e < F_REC_F4; e += 32 * F_EPI_WARPS) srec[e] = __ldg(g + e);
@@ -206,7 +207,17 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
           meta[ii] = __float_as_uint(r0[ii].x);
           many |= meta[ii];
         }
-        if (g == 0) { meta[0] |= 0xFu << 20; many |= 0xFu << 20; }   // (re)load all slots at the start of my half
+        if (g == 0) {
+          // my first vertex of this tile: the record's reload bits refer to a vertex another warp
+          // handled, so compare the slot joints with what this thread still caches from its last
+          // vertex (32 packed vertices earlier, same pose block) and fetch only what changed
+          uint32_t need = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (cached_joint[k] != (int)((meta[0] >> (5 * k)) & 31u)) need |= 1u << (20 + k);
+          meta[0] = (meta[0] & ~(0xFu << 20)) | need;
+          many = meta[0] | meta[1] | meta[2] | meta[3];
+        }
         const bool any_reload = (many >> 20) & 0xFu;
         const bool any_col = (many >> 24) & 1u;
         float v[4][3];
@@ -277,6 +288,8 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
             }
           }
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++) cached_joint[k] = (int)((meta[3] >> (5 * k)) & 31u);
         if (g + 1 < 8) tc_wait_ld12(nxt);
       }
       // TMEM stage drained -> the MMA warp may start tile t+2 in it
@@ -286,6 +299,8 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       // per-CTA partial sums leave when the pose block changes (or the CTA runs out of tiles)
       if (!has_next || (t + 1) / n_tiles != mb) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) cached_joint[k] = -1;   // next tile belongs to other poses
         const int seg = blockIdx.x - fused_cta_of_tile(mb * n_tiles, T, G);
         float* dst = part + ((int64_t)(seg * 2 + h) * NACC) * BP + b;
 #pragma unroll
