@@ -1,3 +1,5 @@
+# Regenerates everything under profiles/ on a B200 (run through gpurun from the repo root):
+#   gpurun --timeout 1800 -- "bash benchmarks/gpu_validate.sh"   then copy gpurun_out/r1_* to profiles/
 timeout 900 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -4 | tee gpurun_out/r1_gpu_tests_tail.txt
 timeout 900 python -m pytest tests -m gpu -q --timeout 600 -s 2>&1 | grep -E "^\[|MPJPE|refit|gradient rel|tcgen05 3xTF32|passed|failed" > gpurun_out/r1_gpu_tests.txt
 python bench.py > gpurun_out/r1_bench.json 2> gpurun_out/r1_bench.err; tail -2 gpurun_out/r1_bench.err
