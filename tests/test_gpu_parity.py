@@ -298,3 +298,117 @@ def test_artefact_round_trip(tmp_path, jrr, J_shipped):
     torch.save(t, p)
     back = jrr.load_j_regressor(str(p), DEV)
     assert back.is_contiguous() and not back.requires_grad and torch.equal(back.cpu(), J_shipped)
+
+
+# ------------------------------------------------------------------ edge cases, errors, determinism
+@pytest.mark.parametrize("B", [1, 127, 129, 300])
+def test_ragged_batches_through_the_fused_step(B, smpl_tc, jrr, oracle, osmpl32, critic_sd, J_shipped):
+    """Batches that do not fill the 128-pose tile: 2 fused steps agree with the oracle."""
+    fr = make_frames(jrr, oracle, osmpl32, J_shipped, B, 40 + B)
+    x6o, bo, hist = oracle.refine(osmpl32, J_shipped, critic_sd, fr["x6"], fr["betas"], fr["gt_mm"], iters=2)
+    ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, use_graph=False)
+    x6, be = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+    loss = ref.refine(x6, be, fr["gt_mm"].to(DEV), iters=2)
+    assert (x6.cpu() - x6o).abs().max().item() < 2e-4
+    assert (be.cpu() - bo).abs().max().item() < 2e-4
+    assert abs(loss[0].item() - hist[-1][0]) / hist[-1][0] < 1e-4
+
+
+def test_refinement_is_bitwise_deterministic(smpl_tc, jrr, critic_sd, J_dense, frames64):
+    """Fixed-order reductions, no float atomics: two runs are identical bit for bit."""
+    outs = []
+    for _ in range(2):
+        ref = jrr.PoseRefiner(smpl_tc, J_dense, critic_sd, use_graph=True)
+        x6, be = frames64["x6"].to(DEV).clone(), frames64["betas"].to(DEV).clone()
+        ref.refine(x6, be, frames64["gt_mm"].to(DEV), iters=10)
+        outs.append((x6.clone(), be.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_tensor_core_and_simt_paths_agree(smpl_tc, smpl_simt, jrr, critic_sd, J_dense, frames64):
+    """Product path (tcgen05 3xTF32, fused epilogue) vs the fp32 SIMT validation kernels."""
+    res, losses = [], []
+    for smpl in (smpl_tc, smpl_simt):
+        ref = jrr.PoseRefiner(smpl, J_dense, critic_sd, use_graph=False)
+        x6, be = frames64["x6"].to(DEV).clone(), frames64["betas"].to(DEV).clone()
+        loss = ref.refine(x6, be, frames64["gt_mm"].to(DEV), iters=5)
+        res.append(x6)
+        losses.append(loss.clone())
+    d = (res[0] - res[1]).abs()
+    print(f"tc vs simt after 5 Adam steps: max |dx6| {d.max().item():.2e}, mean {d.mean().item():.2e}, "
+          f"loss {losses[0][0].item():.6f} vs {losses[1][0].item():.6f}")
+    # Adam's m/sqrt(v) amplifies rounding differences on parameters whose gradient is ~0, so the
+    # bulk statistic and the loss are compared, not the worst element
+    assert d.mean().item() < 1e-5
+    assert abs(losses[0][0].item() - losses[1][0].item()) / losses[1][0].item() < 1e-4
+
+
+def test_full_size_properties_4096(smpl_tc, jrr, model, J_dense):
+    """Size-independent properties at the benchmark batch (no oracle at this size): regressed
+    joints are convex combinations (rows of J-hat sum to 1), so a rigid global rotation of the
+    body rotates the pelvis-centred joints, and the fused path equals the module path."""
+    B = 4096
+    inp = jrr.synthetic.make_pose_inputs(B, 77)
+    R = torch.from_numpy(inp["true_rotmat"]).to(DEV)
+    b = torch.from_numpy(inp["true_betas"]).to(DEV)
+    J = J_dense.to(DEV)
+    with torch.no_grad():
+        fused = jrr.find_joints(smpl_tc, b, R[:, :1], R[:, 1:], J)
+        full, verts = jrr.find_joints(smpl_tc, b, R[:, :1], R[:, 1:], J, return_verts=True)
+    assert rel(fused, full) < 1e-5
+    c, s = np.cos(1.1), np.sin(1.1)
+    Q = torch.tensor([[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]], device=DEV, dtype=torch.float32)
+    R2 = R.clone()
+    R2[:, 0] = Q @ R[:, 0]
+    with torch.no_grad():
+        rot = jrr.find_joints(smpl_tc, b, R2[:, :1], R2[:, 1:], J)
+    a = jrr.move_pelvis(fused) @ Q.t()
+    # the root joint J0(beta) is the centre of rotation; pelvis-centring removes it only if the
+    # regressed pelvis is rotated about the same point, which holds for convex combinations
+    d = jrr.move_pelvis(rot) - a
+    assert d.abs().max().item() < 5e-5
+    assert verts.shape == (B, 6890, 3) and torch.isfinite(verts).all()
+
+
+def test_errors_are_loud(smpl_tc, jrr, critic_sd, J_shipped):
+    nat = smpl_tc.native()
+    with pytest.raises(jrr.JrrError):
+        nat.smpl_forward(torch.zeros(0, 10, device=DEV), torch.zeros(0, 24, 9, device=DEV), 0)      # empty batch
+    with pytest.raises(jrr.JrrError):
+        nat.find_joints(torch.zeros(2, 10), torch.zeros(2, 24, 9), 0)                               # CPU tensors
+    with pytest.raises(jrr.JrrError):
+        nat.set_regressor(torch.zeros(17, 100, device=DEV))                                          # wrong shape
+    m2 = jrr.SMPL(model_dict=dict(smpl_tc._model_np), create_transl=False).to(DEV)
+    fresh = m2.native()
+    x6 = torch.zeros(4, 24, 6, device=DEV); be = torch.zeros(4, 10, device=DEV); gt = torch.zeros(4, 17, 3, device=DEV)
+    mm = torch.zeros(4, 154, device=DEV); t = torch.zeros(1, dtype=torch.int32, device=DEV)
+    with pytest.raises(jrr.JrrError, match="jrr_set_regressor"):
+        fresh.refine_step(x6, be, gt, mm, mm.clone(), t, 1e-2, 1e4, 0.0)
+    fresh.set_regressor(J_shipped.to(DEV))
+    with pytest.raises(jrr.JrrError, match="jrr_critic_load"):
+        fresh.refine_step(x6, be, gt, mm, mm.clone(), t, 1e-2, 1e4, 10.0)
+
+
+def test_model_with_five_weights_per_vertex_is_rejected(jrr, model):
+    bad = dict(model)
+    w = model["lbs_weights"].copy()
+    w[0, :] = 0
+    w[0, :5] = 0.2
+    bad["lbs_weights"] = w
+    with pytest.raises(jrr.JrrError, match="more than 4"):
+        jrr.SMPL(model_dict=bad, create_transl=False).to(DEV).native()
+
+
+def test_transl_and_default_parameters(smpl_tc, jrr, model, osmpl32):
+    """smplx semantics: module parameters are the defaults, transl is added to both outputs."""
+    m = jrr.SMPL(model_dict=model, batch_size=2, create_transl=True).to(DEV)
+    with torch.no_grad():
+        m.transl.copy_(torch.tensor([[0.1, -0.2, 0.3], [1.0, 2.0, 3.0]]))
+        m.betas.normal_()
+        m.body_pose.normal_(std=0.2)
+    out = m()
+    ref = osmpl32(betas=m.betas.detach().cpu(), body_pose=m.body_pose.detach().cpu(),
+                  global_orient=m.global_orient.detach().cpu(), transl=m.transl.detach().cpu(), pose2rot=True)
+    assert rel(out.vertices, ref.vertices) < 1e-5 and rel(out.joints, ref.joints) < 1e-5
+    out.vertices.sum().backward()
+    assert m.transl.grad is not None and abs(m.transl.grad[0, 0].item() - 6890) < 1e-2
