@@ -10,7 +10,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 Workspace carve(const JrrModel* m, int64_t B, void* base) {
   Workspace w{};
   w.B = B;
-  w.BP = round_up(B, 128);
+  w.BP = round_up(B, 256);   // 128-pose GEMM tiles; the fused backward works on 256-pose blocks
   const size_t BP = (size_t)w.BP;
   size_t off = 0;
   char* p = (char*)base;
@@ -244,12 +244,22 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   if (int rc = launch_loss_seed(m, w, m->fused_fwd, gt_mm, B_logical, w_joint, nullptr, st)) return rc;
   JRR_MARK();
   // backward: regressor-transpose seed + skinning | dA reduction | blend GEMM
-  if (int rc = launch_skin_bwd(m, w, nullptr, true, false, st)) return rc;
-  JRR_MARK();
-  if (int rc = launch_dA_reduce(m, w, st)) return rc;
-  JRR_MARK();
-  if (int rc = blend_backward_gemm(m, w, st)) return rc;
-  JRR_MARK();
+  // (events: skin_bwd [fused: skinning backward + blend-gradient GEMM] | dA_reduce | blend_gemm_bwd [fused: empty])
+  if (m->fused_bwd) {
+    w.ksplit = NSPLIT_B;
+    if (int rc = launch_fused_bwd(m, w, st)) return rc;
+    JRR_MARK();
+    if (int rc = launch_dA_reduce(m, w, st)) return rc;
+    JRR_MARK();
+    JRR_MARK();
+  } else {
+    if (int rc = launch_skin_bwd(m, w, nullptr, true, false, st)) return rc;
+    JRR_MARK();
+    if (int rc = launch_dA_reduce(m, w, st)) return rc;
+    JRR_MARK();
+    if (int rc = blend_backward_gemm(m, w, st)) return rc;
+    JRR_MARK();
+  }
   // critic forward + input gradient (inline when profiling or when the fork is disabled)
   const bool inl = critic && !fork;
   if (inl) if (int rc = launch_critic_pre(m, w, x6, st)) return rc;

@@ -1,0 +1,397 @@
+// Fused backward of the loss path: skinning backward (SIMT "generator" warps) feeding the
+// transpose-side blend GEMM (tcgen05) through shared memory -- the pose-blend gradient
+// dvp[B,20736] never exists in HBM.
+//
+//   generator (8 warps, thread = pose, 256 poses per CTA): for every vertex of the CTA's K range
+//     dv = Jhat^T g, dvp = (sum_k w_k AR_k)^T dv, dA_k += w_k dv (x) [vp;1] (flushed per run)
+//     and the 4-vertex group's 12 dvp values are tf32-split and stored as three 16-byte chunks
+//     into the K-major SWIZZLE_128B A-operand tile of the current 32-column K block
+//   TMA warp: P_hi / P_lo tiles [224 x 32] of the augmented blend matrix (B operand)
+//   MMA warp: dfeat[2 x 128 poses, 224] += dvp . P^T, 3xTF32, accumulators in TMEM
+//   epilogue (the generator warps): TMEM -> split-K partial dfeat[ks][b][224]
+//
+// Work item = (256-pose block, K split of 768 packed vertices = the backward skinning range, so
+// the dA flush lists are the ones the unfused kernel uses).  A tiles are double-buffered, the P
+// tile single-buffered (its reload hides behind the generator, which paces the pipeline).
+//
+// Replaces: autograd backward of smplx.lbs.lbs (skinning, pose/shape blend) and of the regressor
+// contraction in utils.find_joints, as reached from scripts/optimize.py:264.
+#include <algorithm>
+
+#include "jrr_internal.cuh"
+#include "jrr_tc.cuh"
+#include "jrr_f32x2.cuh"
+
+namespace jrr {
+
+constexpr int GB_POSES = 256;                    // poses per CTA (two M=128 accumulators)
+constexpr int GB_BK = 32;                        // K columns per block (one swizzle atom)
+constexpr int GB_GEN_WARPS = 8;
+constexpr int GB_THREADS = 32 * GB_GEN_WARPS;   // 8 generator warps own the whole register file (255 regs/thread);
+                                                // thread 0 additionally drives the TMA loads and the MMA issue
+constexpr int GB_A_TILE = 128 * GB_BK * 4;       // 16 KB: one [128 x 32] fp32 tile
+constexpr int GB_A_STAGE = 4 * GB_A_TILE;        // {pose half 0,1} x {hi,lo} = 64 KB
+constexpr int GB_P_TILE = KA * GB_BK * 4;        // 28 KB
+constexpr int GB_P_BYTES = 2 * GB_P_TILE;        // hi + lo = 56 KB
+constexpr int GB_REC_F4 = 32 * REC_WORDS / 4;    // vertex records per 32-vertex tile (224 float4)
+constexpr int GB_SMEM = 2 * GB_A_STAGE + GB_P_BYTES + 2 * GB_REC_F4 * 16 + 1024 + 256;
+constexpr int GB_KB_PER_ITEM = VS_B * 3 / GB_BK; // 72 K blocks per item
+constexpr int GB_TMEM_COLS = 512;                // accumulators at columns 0 and 256
+
+__global__ void __launch_bounds__(GB_THREADS, 1)
+fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ CUtensorMap mapPl,
+                 const VtxRec* __restrict__ vrec, const int* __restrict__ range_flush_base,
+                 const float* __restrict__ AT, const float* __restrict__ vpT, const float* __restrict__ gT,
+                 int64_t BP, int n_items, float* __restrict__ dfeat, float* __restrict__ dAflush) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                      // [2 stages][64 KB]
+  uint8_t* sP = smem + 2 * GB_A_STAGE;                     // [56 KB]
+  float4* srec = (float4*)(sP + GB_P_BYTES);               // [2][224]
+  uint64_t* bars = (uint64_t*)((uint8_t*)srec + 2 * GB_REC_F4 * 16);
+  uint64_t* afull = bars;        // [2] generators -> MMA
+  uint64_t* aempty = bars + 2;   // [2] MMA -> generators
+  uint64_t* pfull = bars + 4;    // TMA -> MMA
+  uint64_t* pempty = bars + 5;   // MMA -> TMA
+  uint64_t* tfull = bars + 6;    // MMA -> epilogue
+  uint64_t* tempty = bars + 7;   // epilogue -> MMA
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapPh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapPl) : "memory");
+    for (int s = 0; s < 2; s++) { mbar_init(&afull[s], GB_GEN_WARPS); mbar_init(&aempty[s], 1); }
+    mbar_init(pfull, 1);
+    mbar_init(pempty, 1);
+    mbar_init(tfull, 1);
+    mbar_init(tempty, GB_GEN_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(GB_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  {
+    // ===================== generators (skinning backward) + epilogue; thread 0 also = control =====================
+    // Control (thread 0 only): a non-blocking state machine polled from the generator loop.
+    //   P(n) is loaded once the MMAs of block n-1 have drained the single P buffer;
+    //   MMA(n) is issued once all 8 warps have written A(n) and P(n) has landed.
+    // Thread 0 never blocks without polling, and drains its queue before every CTA-wide barrier,
+    // so the other warps (which block on aempty) always make progress.
+    const bool ctl = threadIdx.x == 0;
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KA >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+    const uint32_t my_items = (n_items > (int)blockIdx.x) ? (uint32_t)((n_items - 1 - blockIdx.x) / gridDim.x + 1) : 0u;
+    const uint32_t total_kb = my_items * GB_KB_PER_ITEM;
+    uint32_t tma_n = 0, mma_n = 0;
+    auto poll = [&]() {
+      if (tma_n < total_kb && tma_n <= mma_n && mbar_try(pempty, (tma_n & 1) ^ 1)) {
+        const int item_t = blockIdx.x + (int)(tma_n / GB_KB_PER_ITEM) * gridDim.x;
+        const int col = (item_t % NSPLIT_B) * (VS_B * 3) + (int)(tma_n % GB_KB_PER_ITEM) * GB_BK;
+        mbar_expect_tx(pfull, GB_P_BYTES);
+        tma_load_2d(&mapPh, pfull, sP, col, 0);
+        tma_load_2d(&mapPl, pfull, sP + GB_P_TILE, col, 0);
+        tma_n++;
+      }
+      if (mma_n < tma_n) {
+        const uint32_t nn = mma_n;
+        const int s = nn & 1;
+        const uint32_t kb = nn % GB_KB_PER_ITEM, itn = nn / GB_KB_PER_ITEM;
+        bool ready = mbar_try(&afull[s], (nn >> 1) & 1) && mbar_try(pfull, nn & 1);
+        if (ready && kb == 0) ready = mbar_try(tempty, (itn & 1) ^ 1);   // accumulators drained by the last epilogue
+        if (ready) {
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + s * GB_A_STAGE);
+          const uint32_t pb = smem_u32(sP);
+          const uint64_t dPh = make_sdesc(pb), dPl = make_sdesc(pb + GB_P_TILE);
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            const uint64_t dAh = make_sdesc(a0 + hf * 2 * GB_A_TILE);
+            const uint64_t dAl = make_sdesc(a0 + hf * 2 * GB_A_TILE + GB_A_TILE);
+            const uint32_t d_tmem = tmem_base + hf * 256;
+#pragma unroll
+            for (int k = 0; k < GB_BK / 8; k++) {
+              const uint64_t ko = (uint64_t)(k * 32 >> 4);
+              tc_mma_tf32(d_tmem, dAl + ko, dPh + ko, idesc, (kb | (uint32_t)k) != 0);
+              tc_mma_tf32(d_tmem, dAh + ko, dPl + ko, idesc, 1);
+              tc_mma_tf32(d_tmem, dAh + ko, dPh + ko, idesc, 1);
+            }
+          }
+          tc_commit(&aempty[s]);
+          tc_commit(pempty);
+          if (kb == GB_KB_PER_ITEM - 1) tc_commit(tfull);
+          mma_n++;
+        }
+      }
+    };
+
+    const int half = warp >> 2;                    // which 128-pose accumulator
+    const int row = (warp & 3) * 32 + lane;        // TMEM lane == A-tile row of this thread
+    const int gtid = threadIdx.x;                  // 0..255
+    uint32_t n = 0, it = 0;                        // K-block / item counters
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+      const int ks = item % NSPLIT_B, mb2 = item / NSPLIT_B;
+      const int64_t b = (int64_t)mb2 * GB_POSES + half * 128 + row;
+      const int i0 = ks * VS_B;
+      float* flush_dst = dAflush + (int64_t)range_flush_base[ks] * 12 * BP + b;
+
+      f32x2 gp[3][9];
+#pragma unroll
+      for (int p = 0; p < 9; p++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float lo = gT[(int64_t)((2 * p) * 3 + c) * BP + b];
+          const float hi = (2 * p + 1 < NH) ? gT[(int64_t)((2 * p + 1) * 3 + c) * BP + b] : 0.f;
+          gp[c][p] = pk2(lo, hi);
+        }
+      f32x2 AR01[4][3], dA01[4][3], dA23[4][3];
+      float AR2[4][3];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          AR01[k][r] = pk2(0.f, 0.f); AR2[k][r] = 0.f;
+          dA01[k][r] = pk2(0.f, 0.f); dA23[k][r] = pk2(0.f, 0.f);
+        }
+      {
+        const float4* gsrc = reinterpret_cast<const float4*>(vrec + i0);
+        if (gtid < GB_REC_F4) srec[gtid] = __ldg(gsrc + gtid);
+      }
+      const float* vsrc = vpT + (int64_t)(3 * i0) * BP + b;
+      float nx[12];
+#pragma unroll
+      for (int q = 0; q < 12; q++) { nx[q] = *vsrc; vsrc += BP; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // (nothing of this item is queued yet)
+
+      constexpr int NT = VS_B / 32;   // 24 record tiles per item
+#pragma unroll 1
+      for (int t = 0; t < NT; t++) {
+        const float4* rt = srec + (t & 1) * GB_REC_F4;
+        const bool has_next = t + 1 < NT;
+        float4 pf = make_float4(0, 0, 0, 0);
+        if (has_next && gtid < GB_REC_F4)
+          pf = __ldg(reinterpret_cast<const float4*>(vrec + i0 + (t + 1) * 32) + gtid);
+#pragma unroll 1
+        for (int sub = 0; sub < 8; sub++) {
+          const int g = t * 8 + sub;               // 4-vertex group index inside the item (0..191)
+          if (ctl) poll();
+          float cur[12];
+#pragma unroll
+          for (int q = 0; q < 12; q++) cur[q] = nx[q];
+          if (g + 1 < NT * 8) {
+#pragma unroll
+            for (int q = 0; q < 12; q++) { nx[q] = *vsrc; vsrc += BP; }
+          }
+          const float4* rh = rt + (sub * 4) * 7;
+          float4 r0[4];
+          float w3[4];
+          uint32_t meta[4], many = 0;
+#pragma unroll
+          for (int ii = 0; ii < 4; ii++) {
+            r0[ii] = rh[ii * 7];
+            w3[ii] = rh[ii * 7 + 1].x;
+            meta[ii] = __float_as_uint(r0[ii].x);
+            many |= meta[ii];
+          }
+          const bool any_reload = (many >> 20) & 0xFu;
+          float dv[4][3];
+#pragma unroll
+          for (int ii = 0; ii < 4; ii++) { dv[ii][0] = 0.f; dv[ii][1] = 0.f; dv[ii][2] = 0.f; }
+          if ((many >> 24) & 1u) {
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) {
+              f32x2 a[3] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
+#pragma unroll
+              for (int qq = 0; qq < JH_STRIDE / 4; qq++) {
+                const float4 tt = rh[ii * 7 + 2 + qq];
+                const f32x2 ja = pk2(tt.x, tt.y), jb = pk2(tt.z, tt.w);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                  if (2 * qq < 9) a[c] = fma2(ja, gp[c][2 * qq], a[c]);
+                  if (2 * qq + 1 < 9) a[c] = fma2(jb, gp[c][2 * qq + 1], a[c]);
+                }
+              }
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                float lo, hi;
+                upk2(a[c], lo, hi);
+                dv[ii][c] = lo + hi;
+              }
+            }
+          }
+          float o[12];
+#define JRR_GB_VERTEX(ii)                                                                             \
+          {                                                                                           \
+            const float wk[4] = {r0[ii].y, r0[ii].z, r0[ii].w, w3[ii]};                               \
+            const f32x2 d0 = pk2(dv[ii][0], dv[ii][0]), d1 = pk2(dv[ii][1], dv[ii][1]),               \
+                        d2 = pk2(dv[ii][2], dv[ii][2]);                                               \
+            const f32x2 vp01 = pk2(cur[ii * 3 + 0], cur[ii * 3 + 1]), vp21 = pk2(cur[ii * 3 + 2], 1.f); \
+            f32x2 o01 = pk2(0.f, 0.f);                                                                \
+            float o2 = 0.f;                                                                           \
+            _Pragma("unroll") for (int k = 0; k < 4; k++) {                                           \
+              const f32x2 u01 = fma2(AR01[k][2], d2, fma2(AR01[k][1], d1, mul2(AR01[k][0], d0)));     \
+              const float u2 = fmaf(AR2[k][2], dv[ii][2], fmaf(AR2[k][1], dv[ii][1], AR2[k][0] * dv[ii][0])); \
+              const f32x2 ww = pk2(wk[k], wk[k]);                                                     \
+              o01 = fma2(ww, u01, o01);                                                               \
+              o2 = fmaf(wk[k], u2, o2);                                                               \
+              _Pragma("unroll") for (int r = 0; r < 3; r++) {                                         \
+                const float wd = wk[k] * dv[ii][r];                                                   \
+                const f32x2 wdd = pk2(wd, wd);                                                        \
+                dA01[k][r] = fma2(wdd, vp01, dA01[k][r]);                                             \
+                dA23[k][r] = fma2(wdd, vp21, dA23[k][r]);                                             \
+              }                                                                                       \
+            }                                                                                         \
+            upk2(o01, o[ii * 3 + 0], o[ii * 3 + 1]);                                                  \
+            o[ii * 3 + 2] = o2;                                                                       \
+          }
+          if (!any_reload) {
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) JRR_GB_VERTEX(ii)
+          } else {
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) {
+              const bool first = (meta[ii] >> 25) & 1u;
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                if ((meta[ii] >> (20 + k)) & 1u) {
+                  if (!first) {
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                      float a0, a1, a2, a3;
+                      upk2(dA01[k][r], a0, a1);
+                      upk2(dA23[k][r], a2, a3);
+                      flush_dst[(int64_t)(r * 4 + 0) * BP] = a0;
+                      flush_dst[(int64_t)(r * 4 + 1) * BP] = a1;
+                      flush_dst[(int64_t)(r * 4 + 2) * BP] = a2;
+                      flush_dst[(int64_t)(r * 4 + 3) * BP] = a3;
+                      dA01[k][r] = pk2(0.f, 0.f);
+                      dA23[k][r] = pk2(0.f, 0.f);
+                    }
+                    flush_dst += 12 * BP;
+                  }
+                  const int j = (meta[ii] >> (5 * k)) & 31u;
+                  const float* src = AT + (int64_t)(j * 12) * BP + b;
+#pragma unroll
+                  for (int r = 0; r < 3; r++) {
+                    const float a0 = src[(int64_t)(r * 4 + 0) * BP], a1 = src[(int64_t)(r * 4 + 1) * BP];
+                    AR01[k][r] = pk2(a0, a1);
+                    AR2[k][r] = src[(int64_t)(r * 4 + 2) * BP];
+                  }
+                }
+              }
+              JRR_GB_VERTEX(ii)
+            }
+          }
+#undef JRR_GB_VERTEX
+          // ---- the group's 12 dvp columns -> A-operand tiles (tf32 hi / lo), 3 swizzled 16-byte chunks
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            const int col = g * 12 + j * 4;          // column inside the item's K range
+            const int kbl = col >> 5;                // K block inside the item
+            const uint32_t nk = n + kbl;             // global K-block number (ring position)
+            const int s = nk & 1;
+            if ((col & 31) == 0) {
+              // first chunk this thread writes into K block kbl: its A stage must have been consumed
+              if (ctl) {
+                while (!mbar_try(&aempty[s], ((nk >> 1) & 1) ^ 1)) poll();
+              } else {
+                mbar_wait(&aempty[s], ((nk >> 1) & 1) ^ 1);
+              }
+            }
+            float hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              hi[e] = tf32_hi_g(o[j * 4 + e]);
+              lo[e] = tf32_hi_g(o[j * 4 + e] - hi[e]);
+            }
+            const int chunk = ((col & 31) >> 2) ^ (row & 7);
+            uint8_t* dsth = sA + s * GB_A_STAGE + half * 2 * GB_A_TILE + row * 128 + chunk * 16;
+            *reinterpret_cast<float4*>(dsth) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(dsth + GB_A_TILE) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            if ((col & 31) == 28) {
+              // K block complete for this thread: publish to the async proxy, one arrive per warp
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&afull[s]);
+            }
+          }
+        }
+        if (has_next && gtid < GB_REC_F4) srec[((t + 1) & 1) * GB_REC_F4 + gtid] = pf;
+        if (ctl) {
+          // all K blocks of this tile must be issued before thread 0 parks at the barrier
+          const uint32_t upto = n + (uint32_t)(t + 1) * 3;
+          while (mma_n < upto) poll();
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      n += GB_KB_PER_ITEM;
+      // remaining dA slot contents leave as the range's last 4 flush events
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          float a0, a1, a2, a3;
+          upk2(dA01[k][r], a0, a1);
+          upk2(dA23[k][r], a2, a3);
+          flush_dst[(int64_t)(r * 4 + 0) * BP] = a0;
+          flush_dst[(int64_t)(r * 4 + 1) * BP] = a1;
+          flush_dst[(int64_t)(r * 4 + 2) * BP] = a2;
+          flush_dst[(int64_t)(r * 4 + 3) * BP] = a3;
+        }
+        flush_dst += 12 * BP;
+      }
+      // ---- epilogue: split-K partial of the blend-feature gradient
+      if (ctl) {
+        while (mma_n < n) poll();
+      }
+      __syncwarp();
+      mbar_wait(tfull, it & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + half * 256;
+      float* out = dfeat + ((int64_t)ks * BP + b) * KA;
+#pragma unroll 1
+      for (int c = 0; c < KA / 32; c++) {
+        float v[32];
+        tc_ld32(trow + c * 32, v);
+        float4* o4 = reinterpret_cast<float4*>(out + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(GB_TMEM_COLS));
+  }
+}
+
+int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st) {
+  if (w.BP % GB_POSES != 0) return fail(JRR_ERR_INVALID, "fused backward needs BP % 256 == 0");
+  CUtensorMap mPh, mPl;
+  if (int rc = make_tensor_map_2d(&mPh, m->P_hi, KA, NP, NP, KA)) return rc;
+  if (int rc = make_tensor_map_2d(&mPl, m->P_lo, KA, NP, NP, KA)) return rc;
+  const int n_items = (int)(w.BP / GB_POSES) * NSPLIT_B;
+  const int grid = std::min(n_items, m->num_sms);
+  JRR_CUDA(cudaFuncSetAttribute(fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM));
+  fused_bwd_kernel<<<grid, GB_THREADS, GB_SMEM, st>>>(mPh, mPl, m->vrec_b, m->range_flush_base, w.AT, w.vpT, w.gT,
+                                                      w.BP, n_items, w.dfeat, w.dAflush);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+}  // namespace jrr

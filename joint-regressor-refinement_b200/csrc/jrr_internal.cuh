@@ -136,6 +136,7 @@ struct JrrModel {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_critic = true;
   bool fused_fwd = true;   // loss path: skinning + regressor in the blend GEMM's epilogue
+  bool fused_bwd = true;   // loss path: skinning backward generates the A operand of the blend-gradient GEMM
   std::vector<void*> allocs;
 };
 
@@ -204,6 +205,8 @@ int launch_loss_seed(const JrrModel* m, const Workspace& w, bool fused_partials,
 int fused_fwd_slots(int64_t BP, int num_sms);
 int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store /*0 none, 1 vp, 2 skinned v*/,
                      float* vT_out, cudaStream_t st);
+// fused skinning backward + transpose-side blend GEMM (jrr_fused_bwd.cu); writes dfeat[NSPLIT_B] and dAflush
+int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st);
 int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_g,
                     bool use_x, cudaStream_t st);
 int launch_dA_reduce(const JrrModel* m, const Workspace& w, cudaStream_t st);

@@ -500,7 +500,8 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   JRR_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
   if (const char* e = getenv("JRR_OVERLAP_CRITIC")) m->overlap_critic = (e[0] != '0');
   if (const char* e = getenv("JRR_FUSED_FWD")) m->fused_fwd = (e[0] != '0');
-  if (m->gemm_impl != 0) m->fused_fwd = false;
+  if (const char* e = getenv("JRR_FUSED_BWD")) m->fused_bwd = (e[0] != '0');
+  if (m->gemm_impl != 0) { m->fused_fwd = false; m->fused_bwd = false; }
   JRR_CUDA(cudaDeviceSynchronize());
   return JRR_OK;
 }
