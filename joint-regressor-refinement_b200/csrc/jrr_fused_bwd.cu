@@ -27,8 +27,10 @@ namespace jrr {
 constexpr int GB_POSES = 256;                    // poses per CTA (two M=128 accumulators)
 constexpr int GB_BK = 32;                        // K columns per block (one swizzle atom)
 constexpr int GB_GEN_WARPS = 8;
-constexpr int GB_THREADS = 32 * GB_GEN_WARPS;   // 8 generator warps own the whole register file (255 regs/thread);
-                                                // thread 0 additionally drives the TMA loads and the MMA issue
+constexpr int GB_CTRL_WARPS = 4;                 // warp group 0: warp 0 = TMA producer, warp 1 = MMA issuer, 2-3 idle
+constexpr int GB_THREADS = 32 * (GB_CTRL_WARPS + GB_GEN_WARPS);   // 384 threads, launched at 168 registers each ...
+constexpr int GB_CTRL_REGS = 24;                 // ... then the control group shrinks to 24
+constexpr int GB_GEN_REGS = 240;                 // ... and the two generator warp groups grow to 240 (setmaxnreg)
 constexpr int GB_A_TILE = 128 * GB_BK * 4;       // 16 KB: one [128 x 32] fp32 tile
 constexpr int GB_A_STAGE = 4 * GB_A_TILE;        // {pose half 0,1} x {hi,lo} = 64 KB
 constexpr int GB_P_TILE = KA * GB_BK * 4;        // 28 KB
@@ -80,35 +82,34 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  {
-    // ===================== generators (skinning backward) + epilogue; thread 0 also = control =====================
-    // Control (thread 0 only): a non-blocking state machine polled from the generator loop.
-    //   P(n) is loaded once the MMAs of block n-1 have drained the single P buffer;
-    //   MMA(n) is issued once all 8 warps have written A(n) and P(n) has landed.
-    // Thread 0 never blocks without polling, and drains its queue before every CTA-wide barrier,
-    // so the other warps (which block on aempty) always make progress.
-    const bool ctl = threadIdx.x == 0;
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KA >> 3) << 17) |
-                               ((uint32_t)(128 >> 4) << 24);
-    const uint32_t my_items = (n_items > (int)blockIdx.x) ? (uint32_t)((n_items - 1 - blockIdx.x) / gridDim.x + 1) : 0u;
-    const uint32_t total_kb = my_items * GB_KB_PER_ITEM;
-    uint32_t tma_n = 0, mma_n = 0;
-    auto poll = [&]() {
-      if (tma_n < total_kb && tma_n <= mma_n && mbar_try(pempty, (tma_n & 1) ^ 1)) {
-        const int item_t = blockIdx.x + (int)(tma_n / GB_KB_PER_ITEM) * gridDim.x;
-        const int col = (item_t % NSPLIT_B) * (VS_B * 3) + (int)(tma_n % GB_KB_PER_ITEM) * GB_BK;
-        mbar_expect_tx(pfull, GB_P_BYTES);
-        tma_load_2d(&mapPh, pfull, sP, col, 0);
-        tma_load_2d(&mapPl, pfull, sP + GB_P_TILE, col, 0);
-        tma_n++;
+  if (warp < GB_CTRL_WARPS) {
+    // ===================== control warp group: hands its registers to the generators =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GB_CTRL_REGS));
+    if (warp == 0 && lane == 0) {
+      // ---- TMA producer: P tiles (single buffer: refilled as soon as the MMAs that read it completed)
+      uint32_t n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int ks = item % NSPLIT_B;
+        for (int kb = 0; kb < GB_KB_PER_ITEM; kb++, n++) {
+          mbar_wait(pempty, (n & 1) ^ 1);
+          mbar_expect_tx(pfull, GB_P_BYTES);
+          const int col = ks * (VS_B * 3) + kb * GB_BK;
+          tma_load_2d(&mapPh, pfull, sP, col, 0);
+          tma_load_2d(&mapPl, pfull, sP + GB_P_TILE, col, 0);
+        }
       }
-      if (mma_n < tma_n) {
-        const uint32_t nn = mma_n;
-        const int s = nn & 1;
-        const uint32_t kb = nn % GB_KB_PER_ITEM, itn = nn / GB_KB_PER_ITEM;
-        bool ready = mbar_try(&afull[s], (nn >> 1) & 1) && mbar_try(pfull, nn & 1);
-        if (ready && kb == 0) ready = mbar_try(tempty, (itn & 1) ^ 1);   // accumulators drained by the last epilogue
-        if (ready) {
+    } else if (warp == 1 && lane == 0) {
+      // ---- MMA issuer
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KA >> 3) << 17) |
+                                 ((uint32_t)(128 >> 4) << 24);
+      uint32_t n = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+        mbar_wait(tempty, (it & 1) ^ 1);           // accumulators drained by the previous item's epilogue
+        tc_fence_after();
+        for (int kb = 0; kb < GB_KB_PER_ITEM; kb++, n++) {
+          const int s = n & 1;
+          mbar_wait(&afull[s], (n >> 1) & 1);
+          mbar_wait(pfull, n & 1);
           tc_fence_after();
           const uint32_t a0 = smem_u32(sA + s * GB_A_STAGE);
           const uint32_t pb = smem_u32(sP);
@@ -121,7 +122,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
 #pragma unroll
             for (int k = 0; k < GB_BK / 8; k++) {
               const uint64_t ko = (uint64_t)(k * 32 >> 4);
-              tc_mma_tf32(d_tmem, dAl + ko, dPh + ko, idesc, (kb | (uint32_t)k) != 0);
+              tc_mma_tf32(d_tmem, dAl + ko, dPh + ko, idesc, (kb | k) != 0);
               tc_mma_tf32(d_tmem, dAh + ko, dPl + ko, idesc, 1);
               tc_mma_tf32(d_tmem, dAh + ko, dPh + ko, idesc, 1);
             }
@@ -129,14 +130,16 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
           tc_commit(&aempty[s]);
           tc_commit(pempty);
           if (kb == GB_KB_PER_ITEM - 1) tc_commit(tfull);
-          mma_n++;
         }
       }
-    };
-
-    const int half = warp >> 2;                    // which 128-pose accumulator
+    }
+    __syncwarp();
+  } else {
+    // ===================== generators (skinning backward) + epilogue =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GB_GEN_REGS));
+    const int half = (warp - GB_CTRL_WARPS) >> 2;  // which 128-pose accumulator
     const int row = (warp & 3) * 32 + lane;        // TMEM lane == A-tile row of this thread
-    const int gtid = threadIdx.x;                  // 0..255
+    const int gtid = threadIdx.x - 32 * GB_CTRL_WARPS;   // 0..255
     uint32_t n = 0, it = 0;                        // K-block / item counters
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
@@ -184,7 +187,6 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
 #pragma unroll 1
         for (int sub = 0; sub < 8; sub++) {
           const int g = t * 8 + sub;               // 4-vertex group index inside the item (0..191)
-          if (ctl) poll();
           float cur[12];
 #pragma unroll
           for (int q = 0; q < 12; q++) cur[q] = nx[q];
@@ -302,11 +304,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
             const int s = nk & 1;
             if ((col & 31) == 0) {
               // first chunk this thread writes into K block kbl: its A stage must have been consumed
-              if (ctl) {
-                while (!mbar_try(&aempty[s], ((nk >> 1) & 1) ^ 1)) poll();
-              } else {
-                mbar_wait(&aempty[s], ((nk >> 1) & 1) ^ 1);
-              }
+              mbar_wait(&aempty[s], ((nk >> 1) & 1) ^ 1);
             }
             float hi[4], lo[4];
 #pragma unroll
@@ -327,11 +325,6 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
           }
         }
         if (has_next && gtid < GB_REC_F4) srec[((t + 1) & 1) * GB_REC_F4 + gtid] = pf;
-        if (ctl) {
-          // all K blocks of this tile must be issued before thread 0 parks at the barrier
-          const uint32_t upto = n + (uint32_t)(t + 1) * 3;
-          while (mma_n < upto) poll();
-        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       n += GB_KB_PER_ITEM;
@@ -351,10 +344,6 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
         flush_dst += 12 * BP;
       }
       // ---- epilogue: split-K partial of the blend-feature gradient
-      if (ctl) {
-        while (mma_n < n) poll();
-      }
-      __syncwarp();
       mbar_wait(tfull, it & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + half * 256;
