@@ -29,7 +29,10 @@ constexpr int FBM = 128;
 constexpr int FBK = 32;
 constexpr int F_STAGES = 2;
 constexpr int F_EPI_WARPS = 8;
-constexpr int F_THREADS = 64 + 32 * F_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int F_CTRL_WARPS = 4;                   // warp group 0: warp 0 TMA, warp 1 MMA, warps 2-3 idle
+constexpr int F_THREADS = 32 * (F_CTRL_WARPS + F_EPI_WARPS);   // 384 threads launched at 168 registers; setmaxnreg then
+constexpr int F_CTRL_REGS = 24;                   // shrinks the control group ...
+constexpr int F_EPI_REGS = 240;                   // ... and grows the two epilogue warp groups
 constexpr int F_A_BYTES = FBM * FBK * 4;          // 16 KB
 constexpr int F_B_BYTES = FBN * FBK * 4;          // 24 KB
 constexpr int F_STAGE_BYTES = 2 * F_A_BYTES + 2 * F_B_BYTES;   // 80 KB
@@ -85,7 +88,9 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp < F_CTRL_WARPS) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F_CTRL_REGS));
+   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -104,7 +109,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
+   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(FBN >> 3) << 17) |
                                ((uint32_t)(FBM >> 4) << 24);
@@ -141,12 +146,14 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+   }
   } else {
     // ===================== epilogue: skinning + regressor partial sums =====================
-    const int ew = warp - 2;            // 0..7
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F_EPI_REGS));
+    const int ew = warp - F_CTRL_WARPS; // 0..7
     const int q = warp & 3;             // TMEM lane quarter of this warp
     const int h = ew >> 2;              // which half of the tile's 64 vertices
-    const int etid = threadIdx.x - 64;  // 0..255
+    const int etid = threadIdx.x - 32 * F_CTRL_WARPS;  // 0..255
     int acc = 0;
     uint32_t acc_phase = 0;
     // joint transforms of the 4 cached slots: rows 0/1 packed per column, row 2 scalar
