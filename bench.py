@@ -295,12 +295,15 @@ def main():
     tf32_peak = pk["bf16_sustained"] / 2           # dense TF32 = half the bf16 rate; kernels timed inside a long step
     kern = []
     fused_fwd = acc.get("skin_fwd", 0.0) < 0.01      # skinning + regressor ran in the GEMM epilogue
+    fused_bwd = acc.get("blend_gemm_bwd", 0.0) < 0.01  # skinning backward generated the GEMM's A operand in smem
     for name, ms in acc.items():
-        if ms <= 0 or (fused_fwd and name == "skin_fwd"):
+        if ms <= 0 or (fused_fwd and name == "skin_fwd") or (fused_bwd and name == "blend_gemm_bwd"):
             continue
         e = {"name": name, "ms": round(ms, 4)}
         if name == "blend_gemm_fwd" and fused_fwd:
             e["name"] = "fused_fwd(blend_gemm+skinning+regressor)"
+        if name == "skin_bwd" and fused_bwd:
+            e["name"] = "fused_bwd(skinning_bwd+blend_gemm_bwd)"
         if name == "blend_gemm_fwd":
             fl = 3 * 2.0 * B * 20670 * 218
             e.update(bound="tensor", achieved=fl / (ms * 1e-3) / 1e12, peak=tf32_peak, unit="TFLOP/s")
@@ -313,6 +316,9 @@ def main():
         elif name == "skin_fwd":
             by = 4.0 * B * (20670 + 288 + 51)        # read vp + transforms, write 51 partial sums
             e.update(bound="hbm", achieved=by / (ms * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s")
+        elif name == "skin_bwd" and fused_bwd:
+            fl = 3 * 2.0 * B * 20670 * 217
+            e.update(bound="tensor", achieved=fl / (ms * 1e-3) / 1e12, peak=tf32_peak, unit="TFLOP/s")
         elif name == "skin_bwd":
             by = 4.0 * B * (20670 + 288 + 51 + 2 * 20670 + 288)   # + write dvp (hi/lo) and dA
             e.update(bound="hbm", achieved=by / (ms * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s")

@@ -184,60 +184,86 @@ skin_fwd_kernel(const VtxRec* __restrict__ vrec, const int* __restrict__ perm,
 }
 
 // ------------------------------------------------------------------ loss seed (joint term)
-// pred = sum of range partials (fixed order); pc = pred - pred[0]; diff = pc - gt/1000;
+// pred = sum of the partial slots (fixed order); pc = pred - pred[0]; diff = pc - gt/1000;
 // g = w_joint * 2 diff / (51 B_logical); pelvis adjustment; per-CTA loss partial.
-__global__ void __launch_bounds__(SK_THREADS)
+// CTA = one pose block of 128.  Phase 1: 8 warps sum the slots row by row (4 independent
+// 128-byte loads per slot and lane, slots unrolled) into smem; phase 2: 128 threads do the
+// per-pose maths; phase 3: all threads write gT coalesced.
+constexpr int LS_THREADS = 256;
+__global__ void __launch_bounds__(LS_THREADS)
 loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T, int G,
                  const float* __restrict__ gt_mm, int64_t B, int64_t BP, float scale,
                  float* __restrict__ gT, float* __restrict__ joints17_out, float* __restrict__ loss_part) {
-  __shared__ float red[SK_THREADS / 32];
-  const int64_t b = (int64_t)blockIdx.x * SK_THREADS + threadIdx.x;
+  __shared__ float sp[NACC][128];
+  __shared__ float red[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t b0 = (int64_t)blockIdx.x * 128;
   if (nslots <= 0) {
     // partials written by the fused forward kernel: two per CTA segment of this pose block
-    const int mb = blockIdx.x;  // SK_THREADS == 128 == pose block of the fused kernel
+    const int mb = blockIdx.x;
     const int c0 = (int)(((int64_t)mb * n_tiles * G) / T);
     const int c1 = (int)((((int64_t)(mb + 1) * n_tiles - 1) * G) / T);
     nslots = 2 * (c1 - c0 + 1);
   }
-  // fixed-order sum over the partial slots; slot-outer so the 51 loads of a slot are in flight together
-  float pred[NACC];
+  const int64_t slot_stride = (int64_t)NACC * BP;
+  for (int a = warp; a < NACC; a += LS_THREADS / 32) {
+    const float* src = part + (int64_t)a * BP + b0 + lane;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int s = 0;
+    for (; s + 4 <= nslots; s += 4) {
+      float v[4][4];
 #pragma unroll
-  for (int a = 0; a < NACC; a++) pred[a] = 0.f;
-  for (int s = 0; s < nslots; s++) {
-    const float* src = part + (int64_t)s * NACC * BP + b;
+      for (int u = 0; u < 4; u++)
 #pragma unroll
-    for (int a = 0; a < NACC; a++) pred[a] += src[(int64_t)a * BP];
+        for (int c = 0; c < 4; c++) v[u][c] = src[(int64_t)(s + u) * slot_stride + 32 * c];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[c] += v[u][c];
+    }
+    for (; s < nslots; s++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[c] += src[(int64_t)s * slot_stride + 32 * c];
+#pragma unroll
+    for (int c = 0; c < 4; c++) sp[a][lane + 32 * c] = acc[c];
   }
+  __syncthreads();
   float loss = 0.f;
-  if (b < B) {
-    if (joints17_out != nullptr)
+  if (tid < 128) {
+    const int64_t b = b0 + tid;
+    float pred[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; a++) pred[a] = sp[a][tid];
+    if (b < B && joints17_out != nullptr) {
 #pragma unroll
       for (int a = 0; a < NACC; a++) joints17_out[b * NACC + a] = pred[a];
+    }
+    if (gT != nullptr) {
+      float g[NACC];
+      float sum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int a = 0; a < NACC; a++) {
+        float d = 0.f;
+        if (b < B) d = (pred[a] - pred[a % 3]) - gt_mm[b * NACC + a] / 1000.f;
+        loss += d * d;
+        g[a] = scale * d;
+        sum[a % 3] += g[a];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) g[c] -= sum[c];
+#pragma unroll
+      for (int a = 0; a < NACC; a++) sp[a][tid] = g[a];
+    }
   }
-  if (gT != nullptr) {
-    float g[NACC];
-    float sum[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int a = 0; a < NACC; a++) {
-      float d = 0.f;
-      if (b < B) d = (pred[a] - pred[a % 3]) - gt_mm[b * NACC + a] / 1000.f;
-      loss += d * d;
-      g[a] = scale * d;
-      sum[a % 3] += g[a];
-    }
-#pragma unroll
-    for (int c = 0; c < 3; c++) g[c] -= sum[c];
-#pragma unroll
-    for (int a = 0; a < NACC; a++) gT[(int64_t)a * BP + b] = g[a];
-    // deterministic block reduction
-    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = loss;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float t = 0.f;
-      for (int i = 0; i < SK_THREADS / 32; i++) t += red[i];
-      loss_part[blockIdx.x] = t;
-    }
+  if (gT == nullptr) return;
+  // deterministic block reduction of the loss (warps 0..3 hold the poses)
+  for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+  if (tid < 128 && lane == 0) red[warp] = loss;
+  __syncthreads();
+  if (tid == 0) loss_part[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+  for (int idx = tid; idx < NACC * 128; idx += LS_THREADS) {
+    const int a = idx >> 7, bl = idx & 127;
+    gT[(int64_t)a * BP + b0 + bl] = sp[a][bl];
   }
 }
 
@@ -626,7 +652,7 @@ int launch_skin_fwd(const JrrModel* m, const Workspace& w, float* vertices_out, 
 
 int launch_loss_seed(const JrrModel* m, const Workspace& w, bool fused_partials, const float* gt_mm,
                      int64_t B_logical, float w_joint, float* joints17_out, cudaStream_t st) {
-  dim3 grid((unsigned)(w.BP / SK_THREADS)), block(SK_THREADS);
+  dim3 grid((unsigned)(w.BP / 128)), block(LS_THREADS);
   const float scale = gt_mm != nullptr ? w_joint * 2.f / (51.f * (float)B_logical) : 0.f;
   const int n_tiles = VP / 64, T = (int)(w.BP / 128) * n_tiles, G = T < m->num_sms ? T : m->num_sms;
   loss_seed_kernel<<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, gt_mm, w.B, w.BP, scale,
