@@ -412,3 +412,27 @@ def test_transl_and_default_parameters(smpl_tc, jrr, model, osmpl32):
     assert rel(out.vertices, ref.vertices) < 1e-5 and rel(out.joints, ref.joints) < 1e-5
     out.vertices.sum().backward()
     assert m.transl.grad is not None and abs(m.transl.grad[0, 0].item() - 6890) < 1e-2
+
+
+def test_fused_kernels_match_unfused_kernels(jrr, model, critic_sd, J_dense, frames64, monkeypatch):
+    """The fused forward (GEMM + skinning + regressor epilogue) and fused backward (generated-
+    operand GEMM) against the separate GEMM / skinning kernels: same inputs, 3 Adam steps."""
+    res = {}
+    for tag, ff, fb in (("fused", "1", "1"), ("unfused", "0", "0")):
+        monkeypatch.setenv("JRR_FUSED_FWD", ff)
+        monkeypatch.setenv("JRR_FUSED_BWD", fb)
+        smpl = jrr.SMPL(model_dict=model, create_transl=False).to(DEV)      # flags are read at model creation
+        ref = jrr.PoseRefiner(smpl, J_dense, critic_sd, use_graph=False)
+        st = ref._buffers(64)
+        st["x6"].copy_(frames64["x6"]); st["betas"].copy_(frames64["betas"]); st["gt"].copy_(frames64["gt_mm"])
+        ref._run_chunk(st, 1, 64)
+        torch.cuda.synchronize()
+        res[tag] = (st["m"].clone() * 10, st["loss"].clone(), ref.launches_per_step)   # m = 0.1 * gradient after one step
+    g_f, l_f, n_f = res["fused"]
+    g_u, l_u, n_u = res["unfused"]
+    err = (g_f - g_u).abs().max().item() / g_u.abs().max().item()
+    print(f"fused vs unfused: gradient rel diff {err:.2e}; loss {l_f[0].item():.6f} vs {l_u[0].item():.6f}; "
+          f"launches per step {n_f} vs {n_u}")
+    assert err < 2e-5
+    assert abs(l_f[0].item() - l_u[0].item()) / l_u[0].item() < 1e-6
+    assert n_f < n_u
