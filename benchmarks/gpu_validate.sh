@@ -15,5 +15,6 @@ for f in ("r1_bench","r1_bench_shipped"):
 print(open("gpurun_out/r1_bench_reference.json").read()[:300])
 PY
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r1_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'skin_bwd|fused_fwd|gemm_tc_kernel<224' -s 30 -c 6 -o gpurun_out/r1_prof python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'fused_bwd|fused_fwd|gemm_tc_kernel<128, 1' -s 30 -c 6 -o gpurun_out/r1_prof python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | head -30
+timeout 1500 python benchmarks/sweep.py > gpurun_out/r1_sweep.jsonl 2> gpurun_out/r1_sweep.err; tail -2 gpurun_out/r1_sweep.err

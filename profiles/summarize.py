@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Turns the raw artefacts of `benchmarks/gpu_validate.sh` (gpurun_out/r1_*) into the committed
+summaries under profiles/:  r1_launches_summary.txt (share of device time per kernel from the ncu
+launch list) and r1_ncu_top_kernels.txt (selected `ncu --set full` metrics of the top kernels).
+Needs `ncu` on PATH (reads the .ncu-rep; no GPU required)."""
+import collections
+import csv
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "gpurun_out")
+DST = os.path.join(ROOT, "profiles")
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"
+
+WANT = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+]
+
+
+def short(name):
+    return re.sub(r"\(.*", "", name).replace("void ", "").replace("jrr::", "")
+
+
+def launches():
+    rows = [r for r in csv.reader(open(os.path.join(SRC, f"{TAG}_launches.csv"))) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        t = float(r[vi].replace(",", ""))
+        t = t / 1000.0 if r[ui] == "ns" else t * 1000.0 if r[ui] in ("ms", "msecond") else t
+        a = agg.setdefault(short(r[ki]), [0, 0.0])
+        a[0] += 1
+        a[1] += t
+    tot = sum(v[1] for v in agg.values())
+    with open(os.path.join(DST, f"{TAG}_launches_summary.txt"), "w") as f:
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline\n")
+        f.write("(cold-cache, serialised per-launch times: compare SHARES, not absolutes; the command also runs set-up,\n"
+                " warm-up, the end-to-end leg, the profiled steps and the refit, so library kernels of those appear too)\n\n")
+        f.write(f"{'kernel':62s} {'launches':>8s} {'total_us':>10s} {'avg_us':>9s} {'share':>7s}\n")
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{k[:62]:62s} {n:8d} {t:10.1f} {t / n:9.2f} {100 * t / tot:6.2f}%\n")
+
+
+def top_kernels():
+    rep = os.path.join(SRC, f"{TAG}_prof.ncu-rep")
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    out = ["ncu --set full --clock-control none --import-source on -k regex:'fused_bwd|fused_fwd|gemm_tc_kernel<128, 1' "
+           "-s 30 -c 6 python bench.py --steps 3 --warmup 3 --no-cpu-baseline",
+           "(first captured launch of each kernel; B = 4096 poses, dense 17x6890 regressor; times under ncu are cold-cache and serialised)", ""]
+    seen = set()
+    for r in rows[2:]:
+        name = short(r[ki])
+        if name in seen:
+            continue
+        seen.add(name)
+        out.append(f"== {name}")
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                out.append(f"   {w:95s} {r[i]:>18s} {units[i]}")
+        out.append("")
+    open(os.path.join(DST, f"{TAG}_ncu_top_kernels.txt"), "w").write("\n".join(out))
+
+
+def main():
+    for f in (f"{TAG}_bench.json", f"{TAG}_bench_shipped.json", f"{TAG}_bench_reference.json", f"{TAG}_gpu_tests.txt",
+              f"{TAG}_sweep.jsonl", f"{TAG}_memcheck.txt", f"{TAG}_bench_2gpu.json"):
+        p = os.path.join(SRC, f)
+        if os.path.exists(p):
+            shutil.copy(p, os.path.join(DST, f))
+    launches()
+    top_kernels()
+    print("profiles/ refreshed for", TAG)
+
+
+if __name__ == "__main__":
+    main()
