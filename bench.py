@@ -330,10 +330,19 @@ def main():
     kern.sort(key=lambda e: -e["ms"])
     step_ms_prof = sum(e["ms"] for e in kern)
     dom = next((e for e in kern if "achieved" in e), None)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["dram_bytes_per_launch"]
+        if dom is not None and B == FRAMES and args.regressor == "dense":
+            key = "fused_bwd_kernel" if dom["name"].startswith("fused_bwd") else \
+                  "fused_fwd_kernel" if dom["name"].startswith("fused_fwd") else None
+            traffic = tj.get(key) if key else None
+    except Exception:
+        traffic = None
     roofline = None
     if dom is not None:
         roofline = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
-                    "frac": dom["frac"], "traffic": None, "kernel": dom["name"],
+                    "frac": dom["frac"], "traffic": traffic, "kernel": dom["name"],
                     "share_of_step": round(dom["ms"] / step_ms_prof, 3),
                     "peak_source": pk["source"] + (" bf16_sustained/2 (dense TF32)" if dom["bound"] == "tensor" else " hbm copy")}
     pose_steps_per_s = value / world

@@ -81,6 +81,17 @@ def top_kernels():
                 out.append(f"   {w:95s} {r[i]:>18s} {units[i]}")
         out.append("")
     open(os.path.join(DST, f"{TAG}_ncu_top_kernels.txt"), "w").write("\n".join(out))
+    # per-launch DRAM traffic of each captured kernel, read by bench.py for roofline.traffic
+    import json
+    traffic = {}
+    ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        name = short(r[ki]).split("<")[0]
+        if name not in traffic:
+            traffic[name] = float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
+    json.dump({"source": f"profiles/{TAG}_ncu_top_kernels.txt (ncu --set full, B = 4096, dense regressor)",
+               "dram_bytes_per_launch": traffic}, open(os.path.join(DST, "ncu_traffic.json"), "w"), indent=1)
 
 
 def main():
