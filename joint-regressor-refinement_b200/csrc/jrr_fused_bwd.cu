@@ -91,7 +91,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int ks = item % NSPLIT_B;
         for (int kb = 0; kb < GB_KB_PER_ITEM; kb++, n++) {
-          mbar_wait(pempty, (n & 1) ^ 1);
+          mbar_wait_backoff(pempty, (n & 1) ^ 1);
           mbar_expect_tx(pfull, GB_P_BYTES);
           const int col = ks * (VS_B * 3) + kb * GB_BK;
           tma_load_2d(&mapPh, pfull, sP, col, 0);
@@ -104,12 +104,12 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
                                  ((uint32_t)(128 >> 4) << 24);
       uint32_t n = 0, it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
-        mbar_wait(tempty, (it & 1) ^ 1);           // accumulators drained by the previous item's epilogue
+        mbar_wait_backoff(tempty, (it & 1) ^ 1);           // accumulators drained by the previous item's epilogue
         tc_fence_after();
         for (int kb = 0; kb < GB_KB_PER_ITEM; kb++, n++) {
           const int s = n & 1;
-          mbar_wait(&afull[s], (n >> 1) & 1);
-          mbar_wait(pfull, n & 1);
+          mbar_wait_backoff(&afull[s], (n >> 1) & 1);
+          mbar_wait_backoff(pfull, n & 1);
           tc_fence_after();
           const uint32_t a0 = smem_u32(sA + s * GB_A_STAGE);
           const uint32_t pb = smem_u32(sP);
@@ -308,10 +308,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
             }
             float hi[4], lo[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-              hi[e] = tf32_hi_g(o[j * 4 + e]);
-              lo[e] = tf32_hi_g(o[j * 4 + e] - hi[e]);
-            }
+            for (int e = 0; e < 4; e++) split_tf32(o[j * 4 + e], hi[e], lo[e]);
             const int chunk = ((col & 31) >> 2) ^ (row & 7);
             uint8_t* dsth = sA + s * GB_A_STAGE + half * 2 * GB_A_TILE + row * 128 + chunk * 16;
             *reinterpret_cast<float4*>(dsth) = make_float4(hi[0], hi[1], hi[2], hi[3]);

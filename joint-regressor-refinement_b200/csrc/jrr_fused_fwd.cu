@@ -98,7 +98,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
       for (int t = t_begin; t < t_end; t++) {
         const int mb = t / n_tiles, nb = t % n_tiles;
         for (int kb = 0; kb < num_kb; kb++) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_backoff(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * F_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], F_STAGE_BYTES);
           tma_load_2d(&mapAh, &full_bar[stage], sa, kb * FBK, mb * FBM);
@@ -118,13 +118,13 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = t_begin; t < t_end; t++) {
-      if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      if (lane == 0) mbar_wait_backoff(&tempty_bar[acc], acc_phase ^ 1);
       __syncwarp();
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * F_ACC_STRIDE;
       for (int kb = 0; kb < num_kb; kb++) {
         if (lane == 0) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_backoff(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * F_STAGE_BYTES);
           const uint64_t dAh = make_sdesc(sa);
