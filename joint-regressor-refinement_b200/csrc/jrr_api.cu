@@ -167,7 +167,7 @@ extern "C" int jrr_smpl_backward(JrrModel* m, int64_t B, const float* betas, con
   if (use_x)
     if (int rc = launch_joints49_bwd(m, w, djoints49, st)) return rc;
   if (int rc = launch_skin_bwd(m, w, dvertices, false, use_x, st)) return rc;
-  if (int rc = launch_dA_reduce(m, w, st)) return rc;
+  if (int rc = launch_dA_reduce(m, w, false, st)) return rc;
   if (int rc = blend_backward_gemm(m, w, st)) return rc;
   return launch_pose_bwd(m, w, betas, pose, kind, use_x, false, dbetas_out, dpose_out, nullptr, nullptr,
                          nullptr, nullptr, nullptr, 0.f, st);
@@ -246,16 +246,16 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   // backward: regressor-transpose seed + skinning | dA reduction | blend GEMM
   // (events: skin_bwd [fused: skinning backward + blend-gradient GEMM] | dA_reduce | blend_gemm_bwd [fused: empty])
   if (m->fused_bwd) {
-    w.ksplit = NSPLIT_B;
+    w.ksplit = m->nsplit_act;
     if (int rc = launch_fused_bwd(m, w, st)) return rc;
     JRR_MARK();
-    if (int rc = launch_dA_reduce(m, w, st)) return rc;
+    if (int rc = launch_dA_reduce(m, w, true, st)) return rc;
     JRR_MARK();
     JRR_MARK();
   } else {
     if (int rc = launch_skin_bwd(m, w, nullptr, true, false, st)) return rc;
     JRR_MARK();
-    if (int rc = launch_dA_reduce(m, w, st)) return rc;
+    if (int rc = launch_dA_reduce(m, w, false, st)) return rc;
     JRR_MARK();
     if (int rc = blend_backward_gemm(m, w, st)) return rc;
     JRR_MARK();

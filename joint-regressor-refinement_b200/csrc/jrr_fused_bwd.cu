@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1)
 fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ CUtensorMap mapPl,
                  const VtxRec* __restrict__ vrec, const int* __restrict__ range_flush_base,
                  const float* __restrict__ AT, const float* __restrict__ vpT, const float* __restrict__ gT,
-                 int64_t BP, int n_items, float* __restrict__ dfeat, float* __restrict__ dAflush) {
+                 int64_t BP, int n_items, int nsplit, float* __restrict__ dfeat, float* __restrict__ dAflush) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                      // [2 stages][64 KB]
@@ -89,7 +89,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
       // ---- TMA producer: P tiles (single buffer: refilled as soon as the MMAs that read it completed)
       uint32_t n = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int ks = item % NSPLIT_B;
+        const int ks = item % nsplit;
         for (int kb = 0; kb < GB_KB_PER_ITEM; kb++, n++) {
           mbar_wait_backoff(pempty, (n & 1) ^ 1);
           mbar_expect_tx(pfull, GB_P_BYTES);
@@ -143,7 +143,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
     uint32_t n = 0, it = 0;                        // K-block / item counters
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
-      const int ks = item % NSPLIT_B, mb2 = item / NSPLIT_B;
+      const int ks = item % nsplit, mb2 = item / nsplit;
       const int64_t b = (int64_t)mb2 * GB_POSES + half * 128 + row;
       const int i0 = ks * VS_B;
       float* flush_dst = dAflush + (int64_t)range_flush_base[ks] * 12 * BP + b;
@@ -371,11 +371,12 @@ int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st) {
   CUtensorMap mPh, mPl;
   if (int rc = make_tensor_map_2d(&mPh, m->P_hi, KA, NP, NP, KA)) return rc;
   if (int rc = make_tensor_map_2d(&mPl, m->P_lo, KA, NP, NP, KA)) return rc;
-  const int n_items = (int)(w.BP / GB_POSES) * NSPLIT_B;
+  const int nsplit = m->nsplit_act;      // K ranges of the active vertex prefix
+  const int n_items = (int)(w.BP / GB_POSES) * nsplit;
   const int grid = std::min(n_items, m->num_sms);
   JRR_CUDA(cudaFuncSetAttribute(fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM));
   fused_bwd_kernel<<<grid, GB_THREADS, GB_SMEM, st>>>(mPh, mPl, m->vrec_b, m->range_flush_base, w.AT, w.vpT, w.gT,
-                                                      w.BP, n_items, w.dfeat, w.dAflush);
+                                                      w.BP, n_items, nsplit, w.dfeat, w.dAflush);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }

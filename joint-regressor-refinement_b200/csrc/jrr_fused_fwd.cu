@@ -339,12 +339,16 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
 
 // number of partial-sum slots a pose block can receive for this batch (host; sizes `part`)
 int fused_fwd_slots(int64_t BP, int num_sms) {
-  const int m_tiles = (int)(BP / FBM), n_tiles = VP / FV;
-  const int T = m_tiles * n_tiles, G = std::min(T, num_sms);
+  // worst case over every possible active-vertex prefix (1..NSPLIT_B ranges of VS_B vertices)
+  const int m_tiles = (int)(BP / FBM);
   int worst = 1;
-  for (int mb = 0; mb < m_tiles; mb++) {
-    const int c0 = fused_cta_of_tile(mb * n_tiles, T, G), c1 = fused_cta_of_tile((mb + 1) * n_tiles - 1, T, G);
-    worst = std::max(worst, c1 - c0 + 1);
+  for (int ns = 1; ns <= NSPLIT_B; ns++) {
+    const int n_tiles = ns * VS_B / FV;
+    const int T = m_tiles * n_tiles, G = std::min(T, num_sms);
+    for (int mb = 0; mb < m_tiles; mb++) {
+      const int c0 = fused_cta_of_tile(mb * n_tiles, T, G), c1 = fused_cta_of_tile((mb + 1) * n_tiles - 1, T, G);
+      worst = std::max(worst, c1 - c0 + 1);
+    }
   }
   return 2 * worst;
 }
@@ -355,7 +359,7 @@ int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store, float* vT
   if (int rc = make_tensor_map_2d(&mAl, w.feat_lo, w.BP, KA, KA, FBM)) return rc;
   if (int rc = make_tensor_map_2d(&mBh, m->Pt_hi, NP, KA, KA, FBN)) return rc;
   if (int rc = make_tensor_map_2d(&mBl, m->Pt_lo, NP, KA, KA, FBN)) return rc;
-  const int m_tiles = (int)(w.BP / FBM), n_tiles = VP / FV;
+  const int m_tiles = (int)(w.BP / FBM), n_tiles = m->nv_act / FV;   // only the active vertex prefix
   const int T = m_tiles * n_tiles, G = std::min(T, m->num_sms);
 #define JRR_FF(S)                                                                                   \
   do {                                                                                              \

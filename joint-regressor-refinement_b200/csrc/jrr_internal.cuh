@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/jrr.h"
@@ -104,6 +105,7 @@ struct JrrModel {
   // augmented blend matrix, tf32 hi/lo split, both majors
   float *Pt_hi = nullptr, *Pt_lo = nullptr;  // [NP][KA]  (K contiguous)  forward B operand
   float *P_hi = nullptr, *P_lo = nullptr;    // [KA][NP]  (N contiguous)  backward B operand
+  float* Pn = nullptr;                       // [KA][3*6890] natural-order fp32 master the packings are gathered from
   float* J0 = nullptr;                       // [24][3]      J_regressor . v_template
   float* JS = nullptr;                       // [24][3][10]  J_regressor . shapedirs
   jrr::VtxRec* vrec = nullptr;               // [VP]  forward ranges (VS_F)
@@ -111,7 +113,15 @@ struct JrrModel {
   int* perm = nullptr;                       // [VP] packed index -> original vertex id (-1 = padding)
   int* vx_src = nullptr;                     // joints49 sources per vertex (see VtxRec)
   float* vx_coef = nullptr;
-  int n_flush = 0;                           // dA flush events per pose
+  int n_flush = 0;                           // dA flush events per pose (all ranges)
+  int n_flush_act = 0;                       // ... of the active ranges only (a prefix of the ids)
+  int nv_act = 0;                            // packed vertices the loss path walks (multiple of VS_B; VP when dense)
+  int nsplit_act = 0;                        // nv_act / VS_B
+  bool compact_active = true;                // pack vertices with a non-zero regressor column first
+  uint8_t* active_dev = nullptr;             // [V] scratch of jrr_set_regressor
+  std::vector<uint8_t> packed_active;        // support the current packing was built for
+  std::vector<uint32_t> h_key;               // host copies used by build_packing
+  std::vector<std::vector<std::pair<int, float>>> h_lbs, h_vx;
   int* flush_ptr = nullptr;                  // [25] CSR joint -> flush ids
   int* flush_idx = nullptr;                  // [n_flush]
   int* range_flush_base = nullptr;           // [NSPLIT_B]
@@ -209,7 +219,7 @@ int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store /*0 none, 
 int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st);
 int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_g,
                     bool use_x, cudaStream_t st);
-int launch_dA_reduce(const JrrModel* m, const Workspace& w, cudaStream_t st);
+int launch_dA_reduce(const JrrModel* m, const Workspace& w, bool active_only, cudaStream_t st);
 int launch_joints49_fwd(const JrrModel* m, const Workspace& w, const float* vertices,
                         float* joints49_out, cudaStream_t st);
 int launch_joints49_bwd(const JrrModel* m, const Workspace& w, const float* djoints49,

@@ -189,6 +189,38 @@ __global__ void reg_adam_kernel(float* __restrict__ J, const float* __restrict__
 
 __global__ void bump_kernel(int32_t* c) { *c += 1; }
 
+// packed blend matrices from the natural-order master: P[k][3i+c] = Pn[k][3 perm[i] + c]
+__global__ void repack_blend_kernel(const float* __restrict__ Pn, const int* __restrict__ perm,
+                                    float* __restrict__ P_hi, float* __restrict__ P_lo,
+                                    float* __restrict__ Pt_hi, float* __restrict__ Pt_lo) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)KA * NP) return;
+  const int k = (int)(idx / NP), n = (int)(idx % NP);
+  const int v = perm[n / 3];
+  const float x = v >= 0 ? Pn[(int64_t)k * (3 * V) + 3 * v + n % 3] : 0.f;
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  const float hi = __uint_as_float(r);
+  const float d = x - hi;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
+  const float lo = __uint_as_float(r);
+  P_hi[idx] = hi;
+  P_lo[idx] = lo;
+  Pt_hi[(int64_t)n * KA + k] = hi;
+  Pt_lo[(int64_t)n * KA + k] = lo;
+}
+
+// active[v] = 1 when column v of the normalised regressor has a non-zero entry
+__global__ void reg_active_kernel(const float* __restrict__ Jhat, uint8_t* __restrict__ active) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  bool any = false;
+  for (int j = 0; j < NH; j++) any |= (Jhat[j * V + v] != 0.f);
+  active[v] = any ? 1 : 0;
+}
+
+int build_packing(JrrModel* m, const std::vector<uint8_t>& active);
+
 int launch_regressor_normalise(JrrModel* m, const float* Jraw, const float* mask, cudaStream_t st) {
   reg_rowsum_kernel<<<NH, 256, 0, st>>>(Jraw, mask, m->rowsum);
   JRR_LAUNCH_CHECK();
@@ -202,7 +234,8 @@ int launch_regressor_normalise(JrrModel* m, const float* Jraw, const float* mask
 
 int launch_regressor_accumulate(const JrrModel* m, const Workspace& w, const float* vT,
                                 float* G_accum, cudaStream_t st) {
-  reg_accumulate_kernel<<<(VP + RA_WARPS - 1) / RA_WARPS, RA_WARPS * 32, 0, st>>>(w.gT, vT, w.B, w.BP, m->perm, G_accum);
+  // inactive columns cannot receive gradient (relu'(<=0) = 0): only the active prefix is accumulated
+  reg_accumulate_kernel<<<(m->nv_act + RA_WARPS - 1) / RA_WARPS, RA_WARPS * 32, 0, st>>>(w.gT, vT, w.B, w.BP, m->perm, G_accum);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
@@ -250,6 +283,117 @@ __global__ void split_transpose_kernel(const float* __restrict__ src, int rows, 
   lo[i] = __uint_as_float(q);
 }
 
+// (Re)builds everything that depends on the packed vertex order.  Vertices with a non-zero
+// regressor column ("active") come first, so the loss path only walks the first nv_act packed
+// vertices; inside each class vertices are sorted by joint set (long runs for the skinning
+// kernels).  With a dense regressor every vertex is active and nothing is skipped.
+int build_packing(JrrModel* m, const std::vector<uint8_t>& active) {
+  auto lowest_first = [](uint32_t a, uint32_t b) {
+    const uint32_t diff = a ^ b;
+    const uint32_t low = diff & (~diff + 1u);
+    return (a & low) != 0;
+  };
+  std::vector<int> order(V);
+  for (int v = 0; v < V; v++) order[v] = v;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    if (active[x] != active[y]) return active[x] > active[y];
+    if (m->h_key[x] == m->h_key[y]) return false;
+    return lowest_first(m->h_key[x], m->h_key[y]);
+  });
+  int n_active = 0;
+  for (int v = 0; v < V; v++) n_active += active[v] ? 1 : 0;
+  if (n_active == 0) return fail(JRR_ERR_INVALID, "the normalised regressor has no non-zero column");
+  std::vector<int> perm(VP, -1);
+  for (int i = 0; i < V; i++) perm[i] = order[i];
+  m->nv_act = (int)std::min<int64_t>(VP, round_up(n_active, VS_B));
+  m->nsplit_act = m->nv_act / VS_B;
+  m->packed_active = active;
+
+  std::vector<int> vx_src;
+  std::vector<float> vx_coef;
+  std::vector<int> xptr(VP, 0), xcnt(VP, 0);
+  for (int i = 0; i < VP; i++) {
+    xptr[i] = (int)vx_src.size();
+    if (perm[i] >= 0)
+      for (auto& e : m->h_vx[perm[i]]) { vx_src.push_back(e.first); vx_coef.push_back(e.second); }
+    xcnt[i] = (int)vx_src.size() - xptr[i];
+  }
+  auto build = [&](int VS, std::vector<VtxRec>& rec, std::vector<int>* flush_joint, std::vector<int>* range_base) {
+    rec.assign(VP, VtxRec{});
+    int cur[4] = {0, 0, 0, 0};
+    for (int i = 0; i < VP; i++) {
+      const bool first = (i % VS) == 0;
+      if (first && range_base) (*range_base)[i / VS] = (int)flush_joint->size();
+      static const std::vector<std::pair<int, float>> none;
+      const std::vector<std::pair<int, float>>& nz = perm[i] >= 0 ? m->h_lbs[perm[i]] : none;
+      int nj[4];
+      float nw[4] = {0.f, 0.f, 0.f, 0.f};
+      bool used[4] = {false, false, false, false};
+      for (int k = 0; k < 4; k++) nj[k] = first ? 0 : cur[k];
+      std::vector<std::pair<int, float>> rest;
+      for (auto& e : nz) {
+        int hit = -1;
+        if (!first)
+          for (int k = 0; k < 4; k++)
+            if (!used[k] && cur[k] == e.first) { hit = k; break; }
+        if (hit >= 0) { used[hit] = true; nw[hit] = e.second; }
+        else rest.push_back(e);
+      }
+      for (auto& e : rest)
+        for (int k = 0; k < 4; k++)
+          if (!used[k]) { used[k] = true; nj[k] = e.first; nw[k] = e.second; break; }
+      uint32_t meta = 0;
+      for (int k = 0; k < 4; k++) {
+        meta |= (uint32_t)nj[k] << (5 * k);
+        const bool reload = first || nj[k] != cur[k];
+        if (reload) {
+          meta |= 1u << (20 + k);
+          if (!first && flush_joint) flush_joint->push_back(cur[k]);
+        }
+        cur[k] = nj[k];
+      }
+      if (first) meta |= 1u << 25;
+      if (xcnt[i] > 0) meta |= 1u << 26;
+      rec[i].meta = meta;
+      for (int k = 0; k < 4; k++) rec[i].w[k] = nw[k];
+      rec[i].xptr = xptr[i];
+      rec[i].xcnt = xcnt[i];
+      if (flush_joint && (i % VS) == VS - 1)
+        for (int k = 0; k < 4; k++) flush_joint->push_back(cur[k]);
+    }
+  };
+  std::vector<VtxRec> rec_f, rec_b;
+  std::vector<int> flush_joint, range_base(NSPLIT_B + 1);
+  build(VS_F, rec_f, nullptr, nullptr);
+  build(VS_B, rec_b, &flush_joint, &range_base);
+  range_base[NSPLIT_B] = (int)flush_joint.size();
+  m->n_flush = (int)flush_joint.size();
+  m->n_flush_act = range_base[m->nsplit_act];
+  // CSR joint -> flush ids; ids ascend inside a joint's list, so "active ranges only" is a prefix test
+  std::vector<int> fptr(NJ + 1, 0), fidx(flush_joint.size());
+  for (int f : flush_joint) fptr[f + 1]++;
+  for (int j = 0; j < NJ; j++) fptr[j + 1] += fptr[j];
+  std::vector<int> fill(fptr.begin(), fptr.end() - 1);
+  for (int f = 0; f < (int)flush_joint.size(); f++) fidx[fill[flush_joint[f]]++] = f;
+  if (fidx.size() > (size_t)4 * VP + 4 * NSPLIT_B) return fail(JRR_ERR_INVALID, "flush list overflow");
+
+  JRR_CUDA(cudaMemcpy(m->perm, perm.data(), sizeof(int) * VP, cudaMemcpyHostToDevice));
+  JRR_CUDA(cudaMemcpy(m->vrec, rec_f.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
+  JRR_CUDA(cudaMemcpy(m->vrec_b, rec_b.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
+  if (!vx_src.empty()) {
+    JRR_CUDA(cudaMemcpy(m->vx_src, vx_src.data(), sizeof(int) * vx_src.size(), cudaMemcpyHostToDevice));
+    JRR_CUDA(cudaMemcpy(m->vx_coef, vx_coef.data(), sizeof(float) * vx_coef.size(), cudaMemcpyHostToDevice));
+  }
+  JRR_CUDA(cudaMemcpy(m->flush_ptr, fptr.data(), sizeof(int) * (NJ + 1), cudaMemcpyHostToDevice));
+  if (!fidx.empty()) JRR_CUDA(cudaMemcpy(m->flush_idx, fidx.data(), sizeof(int) * fidx.size(), cudaMemcpyHostToDevice));
+  JRR_CUDA(cudaMemcpy(m->range_flush_base, range_base.data(), sizeof(int) * (NSPLIT_B + 1), cudaMemcpyHostToDevice));
+  const int64_t n = (int64_t)KA * NP;
+  repack_blend_kernel<<<(unsigned)((n + 255) / 256), 256>>>(m->Pn, m->perm, m->P_hi, m->P_lo, m->Pt_hi, m->Pt_lo);
+  JRR_CUDA(cudaGetLastError());
+  JRR_CUDA(cudaDeviceSynchronize());
+  return JRR_OK;
+}
+
 }  // namespace jrr
 
 using namespace jrr;
@@ -274,6 +418,15 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   m->gemm_impl = d->gemm_impl;
   JRR_CUDA(cudaSetDevice(d->device));
   JRR_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, d->device));
+  // kernel-validation switches (the product configuration is all defaults)
+  if (const char* e = getenv("JRR_OVERLAP_CRITIC")) m->overlap_critic = (e[0] != '0');
+  if (const char* e = getenv("JRR_FUSED_FWD")) m->fused_fwd = (e[0] != '0');
+  if (const char* e = getenv("JRR_FUSED_BWD")) m->fused_bwd = (e[0] != '0');
+  if (const char* e = getenv("JRR_COMPACT_ACTIVE")) m->compact_active = (e[0] != '0');
+  if (m->gemm_impl != 0) { m->fused_fwd = false; m->fused_bwd = false; }
+  // the active-vertex prefix is only walked by the two fused kernels; the stand-alone skinning
+  // kernels always process every vertex, so compaction is tied to the fused configuration
+  if (!(m->fused_fwd && m->fused_bwd)) m->compact_active = false;
 
   // ---- kinematic tree
   ChainTab& ct = m->chain;
@@ -295,56 +448,35 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
     }
   }
 
-  // ---- vertex permutation: vertices that share a joint set become neighbours, so a
-  // skinning thread re-fetches joint transforms (and flushes dA accumulators) only a few
-  // hundred times per pose instead of at almost every vertex
-  std::vector<int> perm(VP, -1);
-  {
-    std::vector<uint32_t> key(V);
-    for (int v = 0; v < V; v++) {
-      uint32_t k = 0;
-      int n = 0;
-      for (int j = 0; j < NJ; j++)
-        if (d->lbs_weights_host[(size_t)v * NJ + j] != 0.f) { k |= 1u << j; n++; }
-      if (n > 4) return fail(JRR_ERR_INVALID, "lbs_weights row with more than 4 non-zeros is not supported by this build");
-      key[v] = k;
+  // ---- host copies the (re)packing needs: joint-set key and <= 4 (joint, weight) pairs per vertex
+  m->h_key.assign(V, 0);
+  m->h_lbs.assign(V, {});
+  for (int v = 0; v < V; v++) {
+    uint32_t k = 0;
+    for (int j = 0; j < NJ; j++) {
+      const float x = d->lbs_weights_host[(size_t)v * NJ + j];
+      if (x != 0.f) { k |= 1u << j; m->h_lbs[v].push_back({j, x}); }
     }
-    std::vector<int> order(V);
-    for (int v = 0; v < V; v++) order[v] = v;
-    auto lowest_first = [](uint32_t a, uint32_t b) {
-      // compare joint sets as ascending lists: the set holding the smaller differing joint first
-      const uint32_t diff = a ^ b;
-      const uint32_t low = diff & (~diff + 1u);
-      return (a & low) != 0;
-    };
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-      if (key[x] == key[y]) return false;
-      return lowest_first(key[x], key[y]);
-    });
-    for (int i = 0; i < V; i++) perm[i] = order[i];
-    if (int rc = upload(m, &m->perm, perm)) return rc;
+    if (m->h_lbs[v].size() > 4)
+      return fail(JRR_ERR_INVALID, "lbs_weights row with more than 4 non-zeros is not supported by this build");
+    m->h_key[v] = k;
   }
 
-  // ---- augmented blend matrix (columns in packed vertex order)
+  // ---- natural-order master of the augmented blend matrix [224][3*6890] (rows: posedirs, shapedirs^T, template)
   {
-    std::vector<float> P((size_t)KA * NP, 0.f), Pt((size_t)NP * KA, 0.f), hi, lo;
-    for (int i = 0; i < V; i++) {
-      const int v = perm[i];
+    std::vector<float> Pn((size_t)KA * 3 * V, 0.f);
+    for (int k = 0; k < NF; k++)
+      std::memcpy(&Pn[(size_t)k * 3 * V], d->posedirs_host + (size_t)k * 3 * V, sizeof(float) * 3 * V);
+    for (int v = 0; v < V; v++)
       for (int c = 0; c < 3; c++) {
-        const size_t n = (size_t)3 * i + c;
-        for (int k = 0; k < NF; k++) P[(size_t)k * NP + n] = d->posedirs_host[(size_t)k * (3 * V) + 3 * v + c];
-        for (int l = 0; l < NB; l++) P[(size_t)(FEAT_BETA + l) * NP + n] = d->shapedirs_host[((size_t)v * 3 + c) * NB + l];
-        P[(size_t)FEAT_ONE * NP + n] = d->v_template_host[(size_t)v * 3 + c];
+        for (int l = 0; l < NB; l++) Pn[(size_t)(FEAT_BETA + l) * 3 * V + 3 * v + c] = d->shapedirs_host[((size_t)v * 3 + c) * NB + l];
+        Pn[(size_t)FEAT_ONE * 3 * V + 3 * v + c] = d->v_template_host[(size_t)v * 3 + c];
       }
-    }
-    for (int k = 0; k < KA; k++)
-      for (size_t n = 0; n < (size_t)NP; n++) Pt[n * KA + k] = P[(size_t)k * NP + n];
-    split_hi_lo(P, hi, lo);
-    if (int rc = upload(m, &m->P_hi, hi)) return rc;
-    if (int rc = upload(m, &m->P_lo, lo)) return rc;
-    split_hi_lo(Pt, hi, lo);
-    if (int rc = upload(m, &m->Pt_hi, hi)) return rc;
-    if (int rc = upload(m, &m->Pt_lo, lo)) return rc;
+    if (int rc = upload(m, &m->Pn, Pn)) return rc;
+    if (int rc = dalloc(m, &m->P_hi, (size_t)KA * NP, false)) return rc;
+    if (int rc = dalloc(m, &m->P_lo, (size_t)KA * NP, false)) return rc;
+    if (int rc = dalloc(m, &m->Pt_hi, (size_t)KA * NP, false)) return rc;
+    if (int rc = dalloc(m, &m->Pt_lo, (size_t)KA * NP, false)) return rc;
   }
 
   // ---- rest-joint pre-contraction
@@ -368,14 +500,14 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   }
 
   // ---- joints49 tables
-  std::vector<std::vector<std::pair<int, float>>> vx(V);  // per ORIGINAL vertex: (source-24, coef)
+  m->h_vx.assign(V, {});      // per ORIGINAL vertex: (source-24, coef)
   {
     std::vector<int> picks(JRR_NUM_PICKS), jm(JRR_NUM_OUT_JOINTS);
     for (int p = 0; p < JRR_NUM_PICKS; p++) {
       int64_t v = d->vertex_picks_host[p];
       if (v < 0 || v >= V) return fail(JRR_ERR_INVALID, "vertex pick out of range");
       picks[p] = (int)v;
-      vx[v].push_back({p, 1.f});
+      m->h_vx[v].push_back({p, 1.f});
     }
     for (int o = 0; o < JRR_NUM_OUT_JOINTS; o++) {
       int64_t s2 = d->joint_map_host[o];
@@ -390,7 +522,7 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
         if (x != 0.f) {
           col.push_back(v);
           val.push_back(x);
-          vx[v].push_back({JRR_NUM_PICKS + e, x});
+          m->h_vx[v].push_back({JRR_NUM_PICKS + e, x});
         }
       }
       ptr[e + 1] = (int)col.size();
@@ -401,85 +533,21 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
     if (int rc = upload(m, &m->extra.val, val)) return rc;
     if (int rc = upload(m, &m->picks, picks)) return rc;
     if (int rc = upload(m, &m->joint_map, jm)) return rc;
+    size_t nvx = 0;
+    for (auto& l : m->h_vx) nvx += l.size();
+    if (int rc = dalloc(m, &m->vx_src, nvx)) return rc;
+    if (int rc = dalloc(m, &m->vx_coef, nvx)) return rc;
   }
 
-  // ---- skinning run records (forward ranges VS_F, backward ranges VS_B) + dA flush lists
-  {
-    std::vector<int> vx_src;
-    std::vector<float> vx_coef;
-    std::vector<int> xptr(VP, 0), xcnt(VP, 0);
-    for (int i = 0; i < VP; i++) {
-      xptr[i] = (int)vx_src.size();
-      if (perm[i] >= 0)
-        for (auto& e : vx[perm[i]]) { vx_src.push_back(e.first); vx_coef.push_back(e.second); }
-      xcnt[i] = (int)vx_src.size() - xptr[i];
-    }
-    auto build = [&](int VS, std::vector<VtxRec>& rec, std::vector<int>* flush_joint, std::vector<int>* range_base) {
-      rec.assign(VP, VtxRec{});
-      int cur[4] = {0, 0, 0, 0};
-      for (int i = 0; i < VP; i++) {
-        const bool first = (i % VS) == 0;
-        if (first && range_base) (*range_base)[i / VS] = (int)flush_joint->size();
-        std::vector<std::pair<int, float>> nz;
-        if (perm[i] >= 0)
-          for (int j = 0; j < NJ; j++) {
-            const float x = d->lbs_weights_host[(size_t)perm[i] * NJ + j];
-            if (x != 0.f) nz.push_back({j, x});
-          }
-        int nj[4];
-        float nw[4] = {0.f, 0.f, 0.f, 0.f};
-        bool used[4] = {false, false, false, false};
-        for (int k = 0; k < 4; k++) nj[k] = first ? 0 : cur[k];
-        std::vector<std::pair<int, float>> rest;
-        for (auto& e : nz) {
-          int hit = -1;
-          if (!first)
-            for (int k = 0; k < 4; k++)
-              if (!used[k] && cur[k] == e.first) { hit = k; break; }
-          if (hit >= 0) { used[hit] = true; nw[hit] = e.second; }
-          else rest.push_back(e);
-        }
-        for (auto& e : rest)
-          for (int k = 0; k < 4; k++)
-            if (!used[k]) { used[k] = true; nj[k] = e.first; nw[k] = e.second; break; }
-        uint32_t meta = 0;
-        for (int k = 0; k < 4; k++) {
-          meta |= (uint32_t)nj[k] << (5 * k);
-          const bool reload = first || nj[k] != cur[k];
-          if (reload) {
-            meta |= 1u << (20 + k);
-            if (!first && flush_joint) flush_joint->push_back(cur[k]);
-          }
-          cur[k] = nj[k];
-        }
-        if (first) meta |= 1u << 25;
-        if (xcnt[i] > 0) meta |= 1u << 26;
-        rec[i].meta = meta;
-        for (int k = 0; k < 4; k++) rec[i].w[k] = nw[k];
-        rec[i].xptr = xptr[i];
-        rec[i].xcnt = xcnt[i];
-        if (flush_joint && (i % VS) == VS - 1)
-          for (int k = 0; k < 4; k++) flush_joint->push_back(cur[k]);
-      }
-    };
-    std::vector<VtxRec> rec_f, rec_b;
-    std::vector<int> flush_joint, range_base(NSPLIT_B);
-    build(VS_F, rec_f, nullptr, nullptr);
-    build(VS_B, rec_b, &flush_joint, &range_base);
-    m->n_flush = (int)flush_joint.size();
-    std::vector<int> fptr(NJ + 1, 0), fidx(flush_joint.size());
-    for (int f : flush_joint) fptr[f + 1]++;
-    for (int j = 0; j < NJ; j++) fptr[j + 1] += fptr[j];
-    std::vector<int> fill(fptr.begin(), fptr.end() - 1);
-    for (int f = 0; f < (int)flush_joint.size(); f++) fidx[fill[flush_joint[f]]++] = f;
-    if (int rc = upload(m, &m->vrec, rec_f)) return rc;
-    if (int rc = upload(m, &m->vrec_b, rec_b)) return rc;
-    if (int rc = upload(m, &m->vx_src, vx_src)) return rc;
-    if (int rc = upload(m, &m->vx_coef, vx_coef)) return rc;
-    if (int rc = upload(m, &m->flush_ptr, fptr)) return rc;
-    if (int rc = upload(m, &m->flush_idx, fidx)) return rc;
-    if (int rc = upload(m, &m->range_flush_base, range_base)) return rc;
-  }
+  // ---- device buffers of the packing (filled by build_packing; sizes do not depend on the order)
+  if (int rc = dalloc(m, &m->perm, VP)) return rc;
+  if (int rc = dalloc(m, &m->vrec, VP)) return rc;
+  if (int rc = dalloc(m, &m->vrec_b, VP)) return rc;
+  if (int rc = dalloc(m, &m->flush_ptr, NJ + 1)) return rc;
+  if (int rc = dalloc(m, &m->flush_idx, (size_t)4 * VP + 4 * NSPLIT_B)) return rc;
+  if (int rc = dalloc(m, &m->range_flush_base, NSPLIT_B + 1)) return rc;
+  if (int rc = dalloc(m, &m->active_dev, V)) return rc;
+  if (int rc = build_packing(m, std::vector<uint8_t>(V, 1))) return rc;
 
   // ---- regressor state
   if (int rc = dalloc(m, &m->Jhat, (size_t)NH * V)) return rc;
@@ -498,10 +566,6 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   JRR_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
   JRR_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   JRR_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
-  if (const char* e = getenv("JRR_OVERLAP_CRITIC")) m->overlap_critic = (e[0] != '0');
-  if (const char* e = getenv("JRR_FUSED_FWD")) m->fused_fwd = (e[0] != '0');
-  if (const char* e = getenv("JRR_FUSED_BWD")) m->fused_bwd = (e[0] != '0');
-  if (m->gemm_impl != 0) { m->fused_fwd = false; m->fused_bwd = false; }
   JRR_CUDA(cudaDeviceSynchronize());
   return JRR_OK;
 }
@@ -527,7 +591,31 @@ extern "C" int jrr_model_create(const JrrModelDesc* d, JrrModel** out) {
 extern "C" int jrr_set_regressor(JrrModel* m, const float* J17_raw, const float* mask, void* stream) {
   if (!m || !J17_raw) return fail(JRR_ERR_INVALID, "null argument");
   reset_launch_count();
-  return launch_regressor_normalise(m, J17_raw, mask, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  // Normalise first (fills Jhat), then make sure every vertex with a non-zero column sits in the
+  // "active" prefix of the packing.  This entry point is outside the hot loop and SYNCHRONISES:
+  // the support is read back and, if it is not covered by the current packing, the packed
+  // constants are rebuilt (the refit itself can only shrink the support, so it never repacks).
+  reg_rowsum_kernel<<<NH, 256, 0, st>>>(J17_raw, mask, m->rowsum);
+  JRR_LAUNCH_CHECK();
+  reg_normalise_kernel<<<(NH * V + 255) / 256, 256, 0, st>>>(J17_raw, mask, m->rowsum, m->Jhat);
+  JRR_LAUNCH_CHECK();
+  if (m->compact_active) {
+    reg_active_kernel<<<(V + 255) / 256, 256, 0, st>>>(m->Jhat, m->active_dev);
+    JRR_LAUNCH_CHECK();
+    std::vector<uint8_t> act(V);
+    JRR_CUDA(cudaMemcpyAsync(act.data(), m->active_dev, V, cudaMemcpyDeviceToHost, st));
+    JRR_CUDA(cudaStreamSynchronize(st));
+    bool covered = true;
+    int n_act = 0;
+    for (int v = 0; v < V; v++) { n_act += act[v]; if (act[v] && !m->packed_active[v]) covered = false; }
+    // repack when the support is not covered, or when it shrank enough to drop a whole range
+    const int want = (int)std::min<int64_t>(VP, round_up(std::max(n_act, 1), VS_B));
+    if (!covered || want < m->nv_act) {
+      if (int rc = build_packing(m, act)) return rc;
+    }
+  }
+  return launch_regressor_normalise(m, J17_raw, mask, st);
 }
 
 extern "C" int jrr_critic_load(JrrModel* m, const float* p, void* stream) {

@@ -532,7 +532,7 @@ skin_bwd_kernel(const VtxRec* __restrict__ vrec, const int* __restrict__ perm,
 
 // dAT[k][e][b] = sum over the flush events of joint k (fixed order)
 __global__ void __launch_bounds__(SK_THREADS)
-dA_reduce_kernel(const int* __restrict__ flush_ptr, const int* __restrict__ flush_idx,
+dA_reduce_kernel(const int* __restrict__ flush_ptr, const int* __restrict__ flush_idx, int flush_limit,
                  const float* __restrict__ dAflush, int64_t BP, float* __restrict__ dAT) {
   const int64_t b = (int64_t)blockIdx.x * SK_THREADS + threadIdx.x;
   const int k = blockIdx.y;
@@ -541,7 +541,9 @@ dA_reduce_kernel(const int* __restrict__ flush_ptr, const int* __restrict__ flus
   for (int e = 0; e < 12; e++) acc[e] = 0.f;
   const int p0 = flush_ptr[k], p1 = flush_ptr[k + 1];
   for (int p = p0; p < p1; p++) {
-    const float* src = dAflush + (int64_t)__ldg(flush_idx + p) * 12 * BP + b;
+    const int f = __ldg(flush_idx + p);
+    if (f >= flush_limit) break;      // ids ascend inside a joint's list; later ranges were not walked
+    const float* src = dAflush + (int64_t)f * 12 * BP + b;
 #pragma unroll
     for (int e = 0; e < 12; e++) acc[e] += src[(int64_t)e * BP];
   }
@@ -654,7 +656,7 @@ int launch_loss_seed(const JrrModel* m, const Workspace& w, bool fused_partials,
                      int64_t B_logical, float w_joint, float* joints17_out, cudaStream_t st) {
   dim3 grid((unsigned)(w.BP / 128)), block(LS_THREADS);
   const float scale = gt_mm != nullptr ? w_joint * 2.f / (51.f * (float)B_logical) : 0.f;
-  const int n_tiles = VP / 64, T = (int)(w.BP / 128) * n_tiles, G = T < m->num_sms ? T : m->num_sms;
+  const int n_tiles = m->nv_act / 64, T = (int)(w.BP / 128) * n_tiles, G = T < m->num_sms ? T : m->num_sms;
   loss_seed_kernel<<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, gt_mm, w.B, w.BP, scale,
                                            gt_mm != nullptr ? w.gT : nullptr, joints17_out,
                                            w.loss_part);
@@ -686,9 +688,10 @@ int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertice
   return JRR_OK;
 }
 
-int launch_dA_reduce(const JrrModel* m, const Workspace& w, cudaStream_t st) {
+int launch_dA_reduce(const JrrModel* m, const Workspace& w, bool active_only, cudaStream_t st) {
   dim3 grid((unsigned)(w.BP / SK_THREADS), NJ), block(SK_THREADS);
-  dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr, m->flush_idx, w.dAflush, w.BP, w.dAT);
+  dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr, m->flush_idx, active_only ? m->n_flush_act : m->n_flush,
+                                           w.dAflush, w.BP, w.dAT);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }

@@ -105,6 +105,10 @@ class NativeModel:
         m = _f32c(mask.detach(), "mask") if mask is not None else None
         with torch.cuda.device(self.device):
             check(self.L.jrr_set_regressor(self.h, _ptr(J), _ptr(m), _stream()), "jrr_set_regressor")
+        # the packed vertex order (and with it the workspace layout) may have been rebuilt
+        self._ws = None
+        self._ws_B = 0
+        self.regressor_version = getattr(self, "regressor_version", 0) + 1
 
     def load_critic(self, state_dict: dict):
         flat = flatten_critic_state_dict(state_dict).to(self.device)

@@ -40,6 +40,8 @@ class PoseRefiner:
 
     def set_regressor(self, J_regressor, mask=None):
         self.native.set_regressor(J_regressor.to(self.device), None if mask is None else mask.to(self.device))
+        for st in getattr(self, "_bufs", {}).values():     # captured graphs hold the old packing's launch shapes
+            st["graph"] = None
 
     def _buffers(self, B):
         st = self._bufs.get(B)
@@ -68,7 +70,7 @@ class PoseRefiner:
                 self._step(st, LB)
             self.launches_per_step = self.native.launches
             return
-        if st["graph"] is None or st["LB"] != LB:
+        if st["graph"] is None or st["LB"] != LB or st.get("ver") != getattr(self.native, "regressor_version", 0):
             # warm-up outside capture (module loading, attribute calls), on a side stream
             keep = [st[k].clone() for k in ("x6", "betas", "m", "v", "t")]
             s = torch.cuda.Stream(device=self.device)
@@ -82,7 +84,7 @@ class PoseRefiner:
                 self._step(st, LB)
             for k, v in zip(("x6", "betas", "m", "v", "t"), keep):
                 st[k].copy_(v)
-            st["graph"], st["LB"] = g, LB
+            st["graph"], st["LB"], st["ver"] = g, LB, getattr(self.native, "regressor_version", 0)
         for _ in range(iters):
             st["graph"].replay()
 
