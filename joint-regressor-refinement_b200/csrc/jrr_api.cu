@@ -28,7 +28,7 @@ Workspace carve(const JrrModel* m, int64_t B, void* base) {
   w.pred = take(BP * NACC);
   w.dvp_hi = take(BP * (size_t)NP);
   w.dvp_lo = take(BP * (size_t)NP);
-  w.dAflush = take((size_t)m->n_flush * 12 * BP);
+  w.dAflush = take((size_t)std::max(m->n_flush, m->n_flush_l) * 12 * BP);
   w.dAT = take(288 * BP);
   w.dfeat = take((size_t)KSPLIT_MAX * BP * KA);
   {

@@ -37,14 +37,14 @@ constexpr int GB_P_TILE = KA * GB_BK * 4;        // 28 KB
 constexpr int GB_P_BYTES = 2 * GB_P_TILE;        // hi + lo = 56 KB
 constexpr int GB_REC_F4 = 32 * REC_WORDS / 4;    // vertex records per 32-vertex tile (224 float4)
 constexpr int GB_SMEM = 2 * GB_A_STAGE + GB_P_BYTES + 2 * GB_REC_F4 * 16 + 1024 + 256;
-constexpr int GB_KB_PER_ITEM = VS_B * 3 / GB_BK; // 72 K blocks per item
 constexpr int GB_TMEM_COLS = 512;                // accumulators at columns 0 and 256
 
 __global__ void __launch_bounds__(GB_THREADS, 1)
 fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ CUtensorMap mapPl,
                  const VtxRec* __restrict__ vrec, const int* __restrict__ range_flush_base,
                  const float* __restrict__ AT, const float* __restrict__ vpT, const float* __restrict__ gT,
-                 int64_t BP, int n_items, int nsplit, float* __restrict__ dfeat, float* __restrict__ dAflush) {
+                 int64_t BP, int n_items, int nsplit, int vs /* vertices per K range: 768, 384 or 192 */,
+                 float* __restrict__ dfeat, float* __restrict__ dAflush) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                      // [2 stages][64 KB]
@@ -60,6 +60,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
   uint32_t* tmem_slot = (uint32_t*)(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int GB_KB_PER_ITEM = vs * 3 / GB_BK;     // K blocks per item (72 / 36 / 18)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapPh) : "memory");
@@ -93,7 +94,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
         for (int kb = 0; kb < GB_KB_PER_ITEM; kb++, n++) {
           mbar_wait_backoff(pempty, (n & 1) ^ 1);
           mbar_expect_tx(pfull, GB_P_BYTES);
-          const int col = ks * (VS_B * 3) + kb * GB_BK;
+          const int col = ks * (vs * 3) + kb * GB_BK;
           tma_load_2d(&mapPh, pfull, sP, col, 0);
           tma_load_2d(&mapPl, pfull, sP + GB_P_TILE, col, 0);
         }
@@ -145,7 +146,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
       const int ks = item % nsplit, mb2 = item / nsplit;
       const int64_t b = (int64_t)mb2 * GB_POSES + half * 128 + row;
-      const int i0 = ks * VS_B;
+      const int i0 = ks * vs;
       float* flush_dst = dAflush + (int64_t)range_flush_base[ks] * 12 * BP + b;
 
       f32x2 gp[3][9];
@@ -176,7 +177,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
       for (int q = 0; q < 12; q++) { nx[q] = *vsrc; vsrc += BP; }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // (nothing of this item is queued yet)
 
-      constexpr int NT = VS_B / 32;   // 24 record tiles per item
+      const int NT = vs / 32;         // record tiles per item (24 / 12 / 6)
 #pragma unroll 1
       for (int t = 0; t < NT; t++) {
         const float4* rt = srec + (t & 1) * GB_REC_F4;
@@ -375,8 +376,8 @@ int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st) {
   const int n_items = (int)(w.BP / GB_POSES) * nsplit;
   const int grid = std::min(n_items, m->num_sms);
   JRR_CUDA(cudaFuncSetAttribute(fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM));
-  fused_bwd_kernel<<<grid, GB_THREADS, GB_SMEM, st>>>(mPh, mPl, m->vrec_b, m->range_flush_base, w.AT, w.vpT, w.gT,
-                                                      w.BP, n_items, nsplit, w.dfeat, w.dAflush);
+  fused_bwd_kernel<<<grid, GB_THREADS, GB_SMEM, st>>>(mPh, mPl, m->vrec_l, m->range_flush_base_l, w.AT, w.vpT, w.gT,
+                                                      w.BP, n_items, nsplit, m->vs_l, w.dfeat, w.dAflush);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }

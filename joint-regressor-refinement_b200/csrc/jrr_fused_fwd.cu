@@ -342,8 +342,8 @@ int fused_fwd_slots(int64_t BP, int num_sms) {
   // worst case over every possible active-vertex prefix (1..NSPLIT_B ranges of VS_B vertices)
   const int m_tiles = (int)(BP / FBM);
   int worst = 1;
-  for (int ns = 1; ns <= NSPLIT_B; ns++) {
-    const int n_tiles = ns * VS_B / FV;
+  for (int ns = 1; ns <= VP / 192; ns++) {          // every possible active prefix (multiples of 192 vertices)
+    const int n_tiles = ns * 192 / FV;
     const int T = m_tiles * n_tiles, G = std::min(T, num_sms);
     for (int mb = 0; mb < m_tiles; mb++) {
       const int c0 = fused_cta_of_tile(mb * n_tiles, T, G), c1 = fused_cta_of_tile((mb + 1) * n_tiles - 1, T, G);

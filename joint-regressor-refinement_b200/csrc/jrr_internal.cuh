@@ -28,7 +28,7 @@ constexpr int VS_F = 576;           // packed vertices per CTA range, forward sk
 constexpr int NSPLIT = VP / VS_F;   // 12 regressor partial sums per pose
 constexpr int VS_B = 768;           // packed vertices per CTA range, backward skinning
 constexpr int NSPLIT_B = VP / VS_B; // 9
-constexpr int KSPLIT_MAX = 18;      // split-K of the backward blend GEMM: 6, 9, 12 or 18 (chosen per batch to fill whole waves)
+constexpr int KSPLIT_MAX = 36;      // split-K of the backward blend GEMM: 6, 9, 12 or 18 (chosen per batch to fill whole waves)
 constexpr int NPARAM = 154;         // 144 rot6d + 10 betas per pose
 constexpr int MAXCH = 4;            // children per joint supported by the chain kernels
 
@@ -115,8 +115,14 @@ struct JrrModel {
   float* vx_coef = nullptr;
   int n_flush = 0;                           // dA flush events per pose (all ranges)
   int n_flush_act = 0;                       // ... of the active ranges only (a prefix of the ids)
-  int nv_act = 0;                            // packed vertices the loss path walks (multiple of VS_B; VP when dense)
-  int nsplit_act = 0;                        // nv_act / VS_B
+  int nv_act = 0;                            // packed vertices the loss path walks (VP when the regressor is dense)
+  int vs_l = jrr::VS_B;                      // vertices per K range of the fused backward: 768, 384 or 192
+  int nsplit_act = 0;                        // nv_act / vs_l (<= 36)
+  jrr::VtxRec* vrec_l = nullptr;             // [VP] records with vs_l range boundaries (fused backward)
+  int n_flush_l = 0;                         // flush events of the fused backward (active ranges only)
+  int* flush_ptr_l = nullptr;                // [25]
+  int* flush_idx_l = nullptr;
+  int* range_flush_base_l = nullptr;         // [37]
   bool compact_active = true;                // pack vertices with a non-zero regressor column first
   uint8_t* active_dev = nullptr;             // [V] scratch of jrr_set_regressor
   std::vector<uint8_t> packed_active;        // support the current packing was built for
@@ -219,7 +225,7 @@ int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store /*0 none, 
 int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st);
 int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_g,
                     bool use_x, cudaStream_t st);
-int launch_dA_reduce(const JrrModel* m, const Workspace& w, bool active_only, cudaStream_t st);
+int launch_dA_reduce(const JrrModel* m, const Workspace& w, bool loss_path_lists, cudaStream_t st);
 int launch_joints49_fwd(const JrrModel* m, const Workspace& w, const float* vertices,
                         float* joints49_out, cudaStream_t st);
 int launch_joints49_bwd(const JrrModel* m, const Workspace& w, const float* djoints49,

@@ -92,7 +92,8 @@ __global__ void reg_normalise_kernel(const float* __restrict__ J, const float* _
 // scatter the normalised columns into the packed vertex records (both range layouts) and set
 // the "column is non-zero" flag
 __global__ void reg_records_kernel(const float* __restrict__ Jhat, const int* __restrict__ perm,
-                                   VtxRec* __restrict__ vrec, VtxRec* __restrict__ vrec_b) {
+                                   VtxRec* __restrict__ vrec, VtxRec* __restrict__ vrec_b,
+                                   VtxRec* __restrict__ vrec_l) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= VP) return;
   const int v = perm[i];
@@ -102,10 +103,12 @@ __global__ void reg_records_kernel(const float* __restrict__ Jhat, const int* __
     any |= (r != 0.f);
     vrec[i].jh[j] = r;
     vrec_b[i].jh[j] = r;
+    vrec_l[i].jh[j] = r;
   }
   const uint32_t f = any ? (1u << 24) : 0u;
   vrec[i].meta = (vrec[i].meta & ~(1u << 24)) | f;
   vrec_b[i].meta = (vrec_b[i].meta & ~(1u << 24)) | f;
+  vrec_l[i].meta = (vrec_l[i].meta & ~(1u << 24)) | f;
 }
 
 // G[j][i] += sum_b sum_c gT[3j+c][b] * vT[3i+c][b]; one warp per vertex, g tile in smem
@@ -226,7 +229,7 @@ int launch_regressor_normalise(JrrModel* m, const float* Jraw, const float* mask
   JRR_LAUNCH_CHECK();
   reg_normalise_kernel<<<(NH * V + 255) / 256, 256, 0, st>>>(Jraw, mask, m->rowsum, m->Jhat);
   JRR_LAUNCH_CHECK();
-  reg_records_kernel<<<(VP + 255) / 256, 256, 0, st>>>(m->Jhat, m->perm, m->vrec, m->vrec_b);
+  reg_records_kernel<<<(VP + 255) / 256, 256, 0, st>>>(m->Jhat, m->perm, m->vrec, m->vrec_b, m->vrec_l);
   JRR_LAUNCH_CHECK();
   m->has_regressor = true;
   return JRR_OK;
@@ -283,6 +286,14 @@ __global__ void split_transpose_kernel(const float* __restrict__ src, int rows, 
   lo[i] = __uint_as_float(q);
 }
 
+// K-range size of the fused backward: the largest of 768/384/192 vertices that still yields >= 9
+// ranges over the active prefix (enough CTAs per 256-pose block), 192 for very sparse regressors
+static int loss_range_size(int n_active) {
+  for (int vs : {768, 384, 192})
+    if (round_up(n_active, vs) / vs >= 9) return vs;
+  return 192;
+}
+
 // (Re)builds everything that depends on the packed vertex order.  Vertices with a non-zero
 // regressor column ("active") come first, so the loss path only walks the first nv_act packed
 // vertices; inside each class vertices are sorted by joint set (long runs for the skinning
@@ -305,8 +316,9 @@ int build_packing(JrrModel* m, const std::vector<uint8_t>& active) {
   if (n_active == 0) return fail(JRR_ERR_INVALID, "the normalised regressor has no non-zero column");
   std::vector<int> perm(VP, -1);
   for (int i = 0; i < V; i++) perm[i] = order[i];
-  m->nv_act = (int)std::min<int64_t>(VP, round_up(n_active, VS_B));
-  m->nsplit_act = m->nv_act / VS_B;
+  m->vs_l = loss_range_size(n_active);
+  m->nv_act = (int)std::min<int64_t>(VP, round_up(n_active, m->vs_l));
+  m->nsplit_act = m->nv_act / m->vs_l;
   m->packed_active = active;
 
   std::vector<int> vx_src;
@@ -362,20 +374,32 @@ int build_packing(JrrModel* m, const std::vector<uint8_t>& active) {
         for (int k = 0; k < 4; k++) flush_joint->push_back(cur[k]);
     }
   };
-  std::vector<VtxRec> rec_f, rec_b;
-  std::vector<int> flush_joint, range_base(NSPLIT_B + 1);
+  std::vector<VtxRec> rec_f, rec_b, rec_l;
+  std::vector<int> flush_joint, range_base(NSPLIT_B + 1), flush_joint_l, range_base_l(VP / 192 + 1, 0);
   build(VS_F, rec_f, nullptr, nullptr);
-  build(VS_B, rec_b, &flush_joint, &range_base);
+  build(VS_B, rec_b, &flush_joint, &range_base);            // module backward: every vertex, 768-vertex ranges
+  build(m->vs_l, rec_l, &flush_joint_l, &range_base_l);     // fused backward: vs_l-vertex ranges
   range_base[NSPLIT_B] = (int)flush_joint.size();
   m->n_flush = (int)flush_joint.size();
-  m->n_flush_act = range_base[m->nsplit_act];
-  // CSR joint -> flush ids; ids ascend inside a joint's list, so "active ranges only" is a prefix test
-  std::vector<int> fptr(NJ + 1, 0), fidx(flush_joint.size());
-  for (int f : flush_joint) fptr[f + 1]++;
-  for (int j = 0; j < NJ; j++) fptr[j + 1] += fptr[j];
-  std::vector<int> fill(fptr.begin(), fptr.end() - 1);
-  for (int f = 0; f < (int)flush_joint.size(); f++) fidx[fill[flush_joint[f]]++] = f;
-  if (fidx.size() > (size_t)4 * VP + 4 * NSPLIT_B) return fail(JRR_ERR_INVALID, "flush list overflow");
+  // the fused backward only walks the active ranges: its flush ids are a prefix
+  flush_joint_l.resize(range_base_l[m->nsplit_act] ? range_base_l[m->nsplit_act] : flush_joint_l.size());
+  if (m->nsplit_act * m->vs_l >= VP) flush_joint_l.resize(flush_joint_l.size());
+  m->n_flush_l = (int)flush_joint_l.size();
+  m->n_flush_act = m->n_flush_l;
+  // CSR joint -> flush ids (ids ascend inside a joint's list)
+  auto csr = [](const std::vector<int>& fj, std::vector<int>& fptr, std::vector<int>& fidx) {
+    fptr.assign(NJ + 1, 0);
+    fidx.assign(fj.size(), 0);
+    for (int f : fj) fptr[f + 1]++;
+    for (int j = 0; j < NJ; j++) fptr[j + 1] += fptr[j];
+    std::vector<int> fill(fptr.begin(), fptr.end() - 1);
+    for (int f = 0; f < (int)fj.size(); f++) fidx[fill[fj[f]]++] = f;
+  };
+  std::vector<int> fptr, fidx, fptr_l, fidx_l;
+  csr(flush_joint, fptr, fidx);
+  csr(flush_joint_l, fptr_l, fidx_l);
+  if (fidx.size() > (size_t)4 * VP + 4 * NSPLIT_B || fidx_l.size() > (size_t)4 * VP + 4 * 36)
+    return fail(JRR_ERR_INVALID, "flush list overflow");
 
   JRR_CUDA(cudaMemcpy(m->perm, perm.data(), sizeof(int) * VP, cudaMemcpyHostToDevice));
   JRR_CUDA(cudaMemcpy(m->vrec, rec_f.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
@@ -387,6 +411,10 @@ int build_packing(JrrModel* m, const std::vector<uint8_t>& active) {
   JRR_CUDA(cudaMemcpy(m->flush_ptr, fptr.data(), sizeof(int) * (NJ + 1), cudaMemcpyHostToDevice));
   if (!fidx.empty()) JRR_CUDA(cudaMemcpy(m->flush_idx, fidx.data(), sizeof(int) * fidx.size(), cudaMemcpyHostToDevice));
   JRR_CUDA(cudaMemcpy(m->range_flush_base, range_base.data(), sizeof(int) * (NSPLIT_B + 1), cudaMemcpyHostToDevice));
+  JRR_CUDA(cudaMemcpy(m->vrec_l, rec_l.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
+  JRR_CUDA(cudaMemcpy(m->flush_ptr_l, fptr_l.data(), sizeof(int) * (NJ + 1), cudaMemcpyHostToDevice));
+  if (!fidx_l.empty()) JRR_CUDA(cudaMemcpy(m->flush_idx_l, fidx_l.data(), sizeof(int) * fidx_l.size(), cudaMemcpyHostToDevice));
+  JRR_CUDA(cudaMemcpy(m->range_flush_base_l, range_base_l.data(), sizeof(int) * 37, cudaMemcpyHostToDevice));
   const int64_t n = (int64_t)KA * NP;
   repack_blend_kernel<<<(unsigned)((n + 255) / 256), 256>>>(m->Pn, m->perm, m->P_hi, m->P_lo, m->Pt_hi, m->Pt_lo);
   JRR_CUDA(cudaGetLastError());
@@ -546,6 +574,10 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   if (int rc = dalloc(m, &m->flush_ptr, NJ + 1)) return rc;
   if (int rc = dalloc(m, &m->flush_idx, (size_t)4 * VP + 4 * NSPLIT_B)) return rc;
   if (int rc = dalloc(m, &m->range_flush_base, NSPLIT_B + 1)) return rc;
+  if (int rc = dalloc(m, &m->vrec_l, VP)) return rc;
+  if (int rc = dalloc(m, &m->flush_ptr_l, NJ + 1)) return rc;
+  if (int rc = dalloc(m, &m->flush_idx_l, (size_t)4 * VP + 4 * 36)) return rc;
+  if (int rc = dalloc(m, &m->range_flush_base_l, 37)) return rc;
   if (int rc = dalloc(m, &m->active_dev, V)) return rc;
   if (int rc = build_packing(m, std::vector<uint8_t>(V, 1))) return rc;
 
@@ -610,7 +642,8 @@ extern "C" int jrr_set_regressor(JrrModel* m, const float* J17_raw, const float*
     int n_act = 0;
     for (int v = 0; v < V; v++) { n_act += act[v]; if (act[v] && !m->packed_active[v]) covered = false; }
     // repack when the support is not covered, or when it shrank enough to drop a whole range
-    const int want = (int)std::min<int64_t>(VP, round_up(std::max(n_act, 1), VS_B));
+    const int vs = loss_range_size(std::max(n_act, 1));
+    const int want = (int)std::min<int64_t>(VP, round_up(std::max(n_act, 1), vs));
     if (!covered || want < m->nv_act) {
       if (int rc = build_packing(m, act)) return rc;
     }

@@ -688,10 +688,12 @@ int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertice
   return JRR_OK;
 }
 
-int launch_dA_reduce(const JrrModel* m, const Workspace& w, bool active_only, cudaStream_t st) {
+int launch_dA_reduce(const JrrModel* m, const Workspace& w, bool loss_path_lists, cudaStream_t st) {
   dim3 grid((unsigned)(w.BP / SK_THREADS), NJ), block(SK_THREADS);
-  dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr, m->flush_idx, active_only ? m->n_flush_act : m->n_flush,
-                                           w.dAflush, w.BP, w.dAT);
+  if (loss_path_lists)
+    dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr_l, m->flush_idx_l, m->n_flush_l, w.dAflush, w.BP, w.dAT);
+  else
+    dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr, m->flush_idx, m->n_flush, w.dAflush, w.BP, w.dAT);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
