@@ -52,7 +52,7 @@ def hbm_peak():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="c1,c3,c4,c5")
+    ap.add_argument("--only", default="c1,c3,c4,cam,c5")
     ap.add_argument("--frames", type=int, default=312000)
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--max-log2", type=int, default=16)
@@ -176,6 +176,20 @@ def main():
                   "NCCL all-reduce of 468 524 B", "n_gpus": world, "steps": res,
                   "max_abs_dJ_after_3_steps": (refit.J_regressor - J0).abs().max().item(),
                   "zero_entries_unchanged": bool(torch.equal(refit.J_regressor[J0 <= 0], J0[J0 <= 0]))})
+
+    if "cam" in only and rank == 0:
+        # widening row 8f-2: the 1000-iteration camera fit of optimize.py:187-199 on 4096 frames
+        B = 4096
+        inp = jrr.synthetic.make_pose_inputs(B, 11)
+        x6 = torch.from_numpy(inp["x6"]).to(dev).contiguous()
+        be = torch.from_numpy(inp["betas"]).to(dev).contiguous()
+        gt2d = 112 + 40 * torch.randn(B, 17, 2, device=dev)
+        refiner = jrr.PoseRefiner(smpl, J, sd, chunk=B)
+        cam0 = torch.tensor([0.0, 0.0, 40.0], device=dev).repeat(B, 1)
+        ms = cuda_time(lambda: refiner.native.camera_fit(x6, be, gt2d, cam0.clone(), 1000, 1e-2), warm=2, reps=5)
+        emit({"config": "camera_fit", "workload": "4096 frames x 1000 Adam iterations on the camera translation "
+              "(optimize.py:187-199); one body-model forward, then a per-frame kernel", "ms": round(ms, 3),
+              "frame_iterations_per_s": round(B * 1000 / ms * 1e3)})
 
     if "c5" in only and rank == 0:
         hbm, src = hbm_peak()

@@ -139,6 +139,28 @@ int jrr_refine_step(JrrModel* model, int64_t B, int64_t B_logical, float* x6, fl
                     float lr, float w_joint, float w_pose, float* loss_out, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* --- widening row "2-D reprojection loss + camera fit"  ---------------------
+ * replaces: return_2d_joints (scripts/renderer.py:10-51: flip x/y, x2, pytorch3d 0.3.0
+ * PerspectiveCameras(T=cam, focal 5000/224, principal point 0).transform_points_screen at
+ * 224x224) + MSELoss against gt_j2d.
+ *
+ * jrr_camera_fit: the 1000-iteration camera-only Adam loop of optimize.py:187-199.  The 3-D
+ * joints do not depend on the camera, so the body model runs ONCE (not 1000x) and every frame
+ * then iterates privately in one kernel.  cam [B,3] in/out; gt_j2d [B,17,2] pixels; loss_out
+ * DEVICE float[1] (final mean squared pixel error) or NULL.
+ *
+ * jrr_refine_step_2d: jrr_refine_step with the loss_j2d term added (optimize.py:231-233,252-253,
+ * weight w_2d = 1/100 there) and the camera translation as a fourth Adam parameter group
+ * (optimize.py:201-202).  cam_adam_m/v [B,3]; loss_out DEVICE float[4] {total, joint, pose, 2d}. */
+int jrr_camera_fit(JrrModel* model, int64_t B, int64_t B_logical, const float* x6, const float* betas,
+                   const float* gt_j2d, float* cam, int iters, float lr, float* loss_out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int jrr_refine_step_2d(JrrModel* model, int64_t B, int64_t B_logical, float* x6, float* betas,
+                       const float* gt_mm, const float* gt_j2d, float* cam, float* adam_m, float* adam_v,
+                       float* cam_adam_m, float* cam_adam_v, int32_t* step_count, float lr, float w_joint,
+                       float w_pose, float w_2d, float* loss_out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* replaces: the forward/backward half of the regressor refit, optimize.py:300-309
  * (find_joints on detached refined poses, move_pelvis + MSELoss, backward to J_regressor).
  * Accumulates G += dL/dJhat (17x6890, gradient w.r.t. the NORMALISED regressor) and

@@ -181,7 +181,7 @@ extern "C" int jrr_find_joints(JrrModel* m, int64_t B, const float* betas, const
   if (!betas || !pose || !joints17_out) return fail(JRR_ERR_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = loss_forward(m, w, betas, pose, kind, 0, nullptr, st, nullptr, nullptr)) return rc;
-  return launch_loss_seed(m, w, m->fused_fwd, nullptr, 1, 0.f, joints17_out, st);
+  return launch_loss_seed(m, w, m->fused_fwd, nullptr, 1, 0.f, joints17_out, Proj2D{}, st);
 }
 
 extern "C" int jrr_critic_forward(JrrModel* m, int64_t B, const float* rot6d, float* scores_out, void* ws,
@@ -206,7 +206,7 @@ static const char* const kStepKernelNames[JRR_STEP_KERNELS] = {
 static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6, float* betas,
                             const float* gt_mm, float* adam_m, float* adam_v, int32_t* step_count, float lr,
                             float w_joint, float w_pose, float* loss_out, void* ws, size_t ws_bytes,
-                            cudaStream_t st, cudaEvent_t* ev) {
+                            cudaStream_t st, cudaEvent_t* ev, Proj2D p2d = Proj2D{}, float w_2d = 0.f) {
   Workspace w;
   if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
   if (!m->has_regressor) return fail(JRR_ERR_STATE, "jrr_set_regressor has not been called");
@@ -241,7 +241,7 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   if (int rc = loss_forward(m, w, betas, x6, JRR_POSE_ROT6D, 1, w.vpT, st, ev ? &ev[1] : nullptr, ev ? &ev[2] : nullptr)) return rc;
   mark = 3;
   JRR_MARK();
-  if (int rc = launch_loss_seed(m, w, m->fused_fwd, gt_mm, B_logical, w_joint, nullptr, st)) return rc;
+  if (int rc = launch_loss_seed(m, w, m->fused_fwd, gt_mm, B_logical, w_joint, nullptr, p2d, st)) return rc;
   JRR_MARK();
   // backward: regressor-transpose seed + skinning | dA reduction | blend GEMM
   // (events: skin_bwd [fused: skinning backward + blend-gradient GEMM] | dA_reduce | blend_gemm_bwd [fused: empty])
@@ -274,7 +274,7 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   JRR_MARK();
   if (fork) JRR_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
   if (loss_out)
-    if (int rc = launch_loss_finish(w, B_logical, w_joint, w_pose, critic, loss_out, nullptr, st)) return rc;
+    if (int rc = launch_loss_finish(w, B_logical, w_joint, w_pose, critic, w_2d, loss_out, nullptr, st)) return rc;
   JRR_MARK();
   // chain backward + Adam
   if (int rc = launch_pose_bwd(m, w, betas, x6, JRR_POSE_ROT6D, false, critic, nullptr, nullptr, x6, betas,
@@ -290,6 +290,34 @@ extern "C" int jrr_refine_step(JrrModel* m, int64_t B, int64_t B_logical, float*
                                size_t ws_bytes, void* stream) {
   return refine_step_impl(m, B, B_logical, x6, betas, gt_mm, adam_m, adam_v, step_count, lr, w_joint, w_pose,
                           loss_out, ws, ws_bytes, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int jrr_refine_step_2d(JrrModel* m, int64_t B, int64_t B_logical, float* x6, float* betas,
+                                  const float* gt_mm, const float* gt_j2d, float* cam, float* adam_m, float* adam_v,
+                                  float* cam_adam_m, float* cam_adam_v, int32_t* step_count, float lr, float w_joint,
+                                  float w_pose, float w_2d, float* loss_out, void* ws, size_t ws_bytes, void* stream) {
+  if (!gt_j2d || !cam || !cam_adam_m || !cam_adam_v) return fail(JRR_ERR_INVALID, "null 2-D argument");
+  Proj2D p2d;
+  p2d.gt2d = gt_j2d; p2d.cam = cam; p2d.cam_m = cam_adam_m; p2d.cam_v = cam_adam_v;
+  p2d.step_count = step_count; p2d.lr = lr;
+  p2d.scale = w_2d * 2.f / (34.f * (float)B_logical);
+  return refine_step_impl(m, B, B_logical, x6, betas, gt_mm, adam_m, adam_v, step_count, lr, w_joint, w_pose,
+                          loss_out, ws, ws_bytes, (cudaStream_t)stream, nullptr, p2d, w_2d);
+}
+
+extern "C" int jrr_camera_fit(JrrModel* m, int64_t B, int64_t B_logical, const float* x6, const float* betas,
+                              const float* gt_j2d, float* cam, int iters, float lr, float* loss_out, void* ws,
+                              size_t ws_bytes, void* stream) {
+  Workspace w;
+  if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
+  if (!m->has_regressor) return fail(JRR_ERR_STATE, "jrr_set_regressor has not been called");
+  if (!x6 || !betas || !gt_j2d || !cam || iters < 0) return fail(JRR_ERR_INVALID, "bad argument");
+  if (B_logical < B) return fail(JRR_ERR_INVALID, "B_logical must be >= B");
+  cudaStream_t st = (cudaStream_t)stream;
+  // the 3-D joints do not depend on the camera: one forward, then every frame iterates privately
+  if (int rc = loss_forward(m, w, betas, x6, JRR_POSE_ROT6D, 0, nullptr, st, nullptr, nullptr)) return rc;
+  if (int rc = launch_loss_seed(m, w, m->fused_fwd, nullptr, 1, 0.f, w.pred, Proj2D{}, st)) return rc;
+  return launch_camera_fit(w, w.pred, gt_j2d, cam, iters, lr, B_logical, loss_out, st);
 }
 
 extern "C" const char* jrr_step_kernel_name(int i) {
@@ -329,10 +357,10 @@ extern "C" int jrr_regressor_grad_accumulate(JrrModel* m, int64_t B, int64_t B_l
   // skinned vertices kept pose-contiguous in the (otherwise idle) dvp_hi buffer
   float* vT = w.dvp_hi;
   if (int rc = loss_forward(m, w, betas, x6, JRR_POSE_ROT6D, 2, vT, st, nullptr, nullptr)) return rc;
-  if (int rc = launch_loss_seed(m, w, m->fused_fwd, gt_mm, B_logical, 1.f, nullptr, st)) return rc;
+  if (int rc = launch_loss_seed(m, w, m->fused_fwd, gt_mm, B_logical, 1.f, nullptr, Proj2D{}, st)) return rc;
   if (int rc = launch_regressor_accumulate(m, w, vT, G_accum, st)) return rc;
   if (loss_accum)
-    if (int rc = launch_loss_finish(w, B_logical, 1.f, 0.f, false, nullptr, loss_accum, st)) return rc;
+    if (int rc = launch_loss_finish(w, B_logical, 1.f, 0.f, false, 0.f, nullptr, loss_accum, st)) return rc;
   return JRR_OK;
 }
 

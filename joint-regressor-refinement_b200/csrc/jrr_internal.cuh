@@ -85,6 +85,7 @@ struct VtxRec {
 static_assert(sizeof(VtxRec) == 112, "VtxRec tiles are staged as float4");
 constexpr int REC_WORDS = 28;
 constexpr int LOSS_PART_POSE = 4096;  // offset of the critic partials inside Workspace::loss_part
+constexpr int LOSS_PART_2D = 2048;    // offset of the 2-D reprojection partials (<= 2048 pose blocks per call)
 constexpr int64_t MAX_POSES_PER_CALL = 262144;
 
 // sparse rows (CSR over ORIGINAL vertex ids) for the joints49 path
@@ -215,8 +216,21 @@ int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st);
 
 int launch_skin_fwd(const JrrModel* m, const Workspace& w, float* vertices_out, float* vT_out,
                     bool want_part, cudaStream_t st);
+// optional 2-D reprojection term of the refinement loss (optimize.py:231-233 via renderer.py:10-51);
+// the camera translation is a per-pose parameter of the same Adam optimiser (optimize.py:201-202)
+struct Proj2D {
+  const float* gt2d = nullptr;   // [B,17,2] screen pixels; nullptr disables the term
+  float* cam = nullptr;          // [B,3] camera translation, updated in place
+  float* cam_m = nullptr;        // [B,3] Adam moments
+  float* cam_v = nullptr;
+  const int32_t* step_count = nullptr;
+  float lr = 0.f;
+  float scale = 0.f;             // w_2d * 2 / (34 * B_logical)
+};
 int launch_loss_seed(const JrrModel* m, const Workspace& w, bool fused_partials, const float* gt_mm,
-                     int64_t B_logical, float w_joint, float* joints17_out, cudaStream_t st);
+                     int64_t B_logical, float w_joint, float* joints17_out, const Proj2D& p2d, cudaStream_t st);
+int launch_camera_fit(const Workspace& w, const float* joints17, const float* gt2d, float* cam, int iters, float lr,
+                      int64_t B_logical, float* loss_out, cudaStream_t st);
 // fused blend GEMM + skinning + regressor partial sums (jrr_fused_fwd.cu)
 int fused_fwd_slots(int64_t BP, int num_sms);
 int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store /*0 none, 1 vp, 2 skinned v*/,
@@ -244,7 +258,7 @@ int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st
 int launch_critic_post(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st);
 
 int launch_loss_finish(const Workspace& w, int64_t B_logical, float w_joint, float w_pose,
-                       bool have_pose, float* loss_out, float* loss_accum, cudaStream_t st);
+                       bool have_pose, float w_2d, float* loss_out, float* loss_accum, cudaStream_t st);
 
 int launch_regressor_normalise(JrrModel* m, const float* Jraw, const float* mask, cudaStream_t st);
 int launch_regressor_accumulate(const JrrModel* m, const Workspace& w, const float* vT,

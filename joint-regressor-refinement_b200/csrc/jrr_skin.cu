@@ -190,12 +190,48 @@ skin_fwd_kernel(const VtxRec* __restrict__ vrec, const int* __restrict__ perm,
 // 128-byte loads per slot and lane, slots unrolled) into smem; phase 2: 128 threads do the
 // per-pose maths; phase 3: all threads write gT coalesced.
 constexpr int LS_THREADS = 256;
+
+// 2-D reprojection of the 17 regressed joints (scripts/renderer.py:35-49 with pytorch3d 0.3.0
+// PerspectiveCameras, R = I, focal 5000/224, principal point 0, 224x224 screen):
+//   P = 2*(-x, -y, z) + T;  ndc = f*P.xy/P.z;  screen = 111.5*(1 - ndc)
+// Accumulates d loss/d pred (into g) and d loss/d T for residual scale `sc`; returns sum of squares.
+__device__ __forceinline__ float proj2d_grad(const float pred[NACC], const float T[3], const float* __restrict__ gt2d,
+                                             float sc, float g[NACC], float dT[3]) {
+  const float f = 5000.f / 224.f, half = 111.5f;
+  float loss = 0.f;
+#pragma unroll
+  for (int j = 0; j < NH; j++) {
+    const float Px = -2.f * pred[j * 3 + 0] + T[0], Py = -2.f * pred[j * 3 + 1] + T[1], Pz = 2.f * pred[j * 3 + 2] + T[2];
+    const float iz = 1.f / Pz;
+    const float xn = f * Px * iz, yn = f * Py * iz;
+    const float dx = half * (1.f - xn) - gt2d[j * 2 + 0], dy = half * (1.f - yn) - gt2d[j * 2 + 1];
+    loss += dx * dx + dy * dy;
+    const float dxn = -half * sc * dx, dyn = -half * sc * dy;
+    const float dPx = dxn * f * iz, dPy = dyn * f * iz, dPz = -(dxn * xn + dyn * yn) * iz;
+    dT[0] += dPx; dT[1] += dPy; dT[2] += dPz;
+    if (g != nullptr) { g[j * 3 + 0] += -2.f * dPx; g[j * 3 + 1] += -2.f * dPy; g[j * 3 + 2] += 2.f * dPz; }
+  }
+  return loss;
+}
+
+__device__ __forceinline__ void adam_update3(float T[3], const float dT[3], float m[3], float v[3], int t, float lr) {
+  const float bc2s = (float)sqrt(1.0 - pow(0.999, (double)t));
+  const float step = (float)((double)lr / (1.0 - pow(0.9, (double)t)));
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    m[c] = 0.9f * m[c] + 0.1f * dT[c];
+    v[c] = 0.999f * v[c] + 0.001f * dT[c] * dT[c];
+    T[c] -= step * (m[c] / (sqrtf(v[c]) / bc2s + 1e-8f));
+  }
+}
+
 __global__ void __launch_bounds__(LS_THREADS)
 loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T, int G,
                  const float* __restrict__ gt_mm, int64_t B, int64_t BP, float scale,
-                 float* __restrict__ gT, float* __restrict__ joints17_out, float* __restrict__ loss_part) {
+                 float* __restrict__ gT, float* __restrict__ joints17_out, float* __restrict__ loss_part,
+                 const Proj2D p2d) {
   __shared__ float sp[NACC][128];
-  __shared__ float red[4];
+  __shared__ float red[4], red2[4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t b0 = (int64_t)blockIdx.x * 128;
   if (nslots <= 0) {
@@ -228,7 +264,7 @@ loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T,
     for (int c = 0; c < 4; c++) sp[a][lane + 32 * c] = acc[c];
   }
   __syncthreads();
-  float loss = 0.f;
+  float loss = 0.f, loss2 = 0.f;
   if (tid < 128) {
     const int64_t b = b0 + tid;
     float pred[NACC];
@@ -251,16 +287,37 @@ loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T,
       }
 #pragma unroll
       for (int c = 0; c < 3; c++) g[c] -= sum[c];
+      if (p2d.gt2d != nullptr) {
+        // 2-D term: seeds the same backward through the (not pelvis-centred) joints, and its
+        // camera gradient is complete here, so the camera's Adam step happens in place
+        float l2 = 0.f;
+        if (b < B) {
+          float Tc[3], dT[3] = {0.f, 0.f, 0.f}, m3[3], v3[3];
+#pragma unroll
+          for (int c = 0; c < 3; c++) { Tc[c] = p2d.cam[b * 3 + c]; m3[c] = p2d.cam_m[b * 3 + c]; v3[c] = p2d.cam_v[b * 3 + c]; }
+          l2 = proj2d_grad(pred, Tc, p2d.gt2d + b * 34, p2d.scale, g, dT);
+          adam_update3(Tc, dT, m3, v3, *p2d.step_count + 1, p2d.lr);
+#pragma unroll
+          for (int c = 0; c < 3; c++) { p2d.cam[b * 3 + c] = Tc[c]; p2d.cam_m[b * 3 + c] = m3[c]; p2d.cam_v[b * 3 + c] = v3[c]; }
+        }
+        loss2 = l2;
+      }
 #pragma unroll
       for (int a = 0; a < NACC; a++) sp[a][tid] = g[a];
     }
   }
   if (gT == nullptr) return;
   // deterministic block reduction of the loss (warps 0..3 hold the poses)
-  for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
-  if (tid < 128 && lane == 0) red[warp] = loss;
+  for (int o = 16; o > 0; o >>= 1) {
+    loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    loss2 += __shfl_xor_sync(0xffffffffu, loss2, o);
+  }
+  if (tid < 128 && lane == 0) { red[warp] = loss; red2[warp] = loss2; }
   __syncthreads();
-  if (tid == 0) loss_part[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+  if (tid == 0) {
+    loss_part[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+    loss_part[LOSS_PART_2D + blockIdx.x] = (red2[0] + red2[1]) + (red2[2] + red2[3]);
+  }
   for (int idx = tid; idx < NACC * 128; idx += LS_THREADS) {
     const int a = idx >> 7, bl = idx & 127;
     gT[(int64_t)a * BP + b0 + bl] = sp[a][bl];
@@ -604,26 +661,68 @@ __global__ void joints49_bwd_kernel(const int* __restrict__ joint_map, const flo
 // ---------------------------------------------------------------------------- loss finish
 __global__ void loss_finish_kernel(const float* __restrict__ lp_joint, int n_joint, float sj,
                                    const float* __restrict__ lp_pose, int n_pose, float sp,
-                                   float wj, float wp, float* __restrict__ loss_out,
-                                   float* __restrict__ loss_accum) {
+                                   const float* __restrict__ lp_2d, float s2, float wj, float wp, float w2,
+                                   float* __restrict__ loss_out, float* __restrict__ loss_accum) {
   // one warp; lane-strided partial sums + xor-shuffle tree: a fixed summation order
   const int lane = threadIdx.x;
-  float a = 0.f, p = 0.f;
+  float a = 0.f, p = 0.f, q = 0.f;
   for (int i = lane; i < n_joint; i += 32) a += lp_joint[i];
   for (int i = lane; i < n_pose; i += 32) p += lp_pose[i];
+  if (w2 != 0.f)
+    for (int i = lane; i < n_joint; i += 32) q += lp_2d[i];
   for (int o = 16; o > 0; o >>= 1) {
     a += __shfl_xor_sync(0xffffffffu, a, o);
     p += __shfl_xor_sync(0xffffffffu, p, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
   }
   if (lane != 0) return;
   a *= sj;
   p *= sp;
+  q *= s2;
   if (loss_out != nullptr) {
-    loss_out[0] = wj * a + wp * p;
+    loss_out[0] = wj * a + wp * p + w2 * q;
     loss_out[1] = a;
     loss_out[2] = p;
+    if (w2 != 0.f) loss_out[3] = q;
   }
   if (loss_accum != nullptr) loss_accum[0] += a;
+}
+
+// ---------------------------------------------------------------------------- camera fit
+// optimize.py:187-199: Adam(lr) on the camera translation alone against the 2-D joints.  The 3-D
+// joints do not depend on the camera, so they are computed once and each frame iterates privately.
+__global__ void camera_fit_kernel(const float* __restrict__ joints17, const float* __restrict__ gt2d,
+                                  float* __restrict__ cam, int64_t B, int iters, float lr, float scale,
+                                  float* __restrict__ loss_part) {
+  __shared__ float red[4];
+  const int64_t b = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  float last = 0.f;
+  if (b < B) {
+    float pred[NACC], T[3], m3[3] = {0.f, 0.f, 0.f}, v3[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < NACC; a++) pred[a] = joints17[b * NACC + a];
+#pragma unroll
+    for (int c = 0; c < 3; c++) T[c] = cam[b * 3 + c];
+    for (int t = 1; t <= iters; t++) {
+      float dT[3] = {0.f, 0.f, 0.f};
+      last = proj2d_grad(pred, T, gt2d + b * 34, scale, nullptr, dT);
+      adam_update3(T, dT, m3, v3, t, lr);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) cam[b * 3 + c] = T[c];
+  }
+  for (int o = 16; o > 0; o >>= 1) last += __shfl_xor_sync(0xffffffffu, last, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = last;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_part != nullptr) loss_part[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+__global__ void sum_scale_kernel(const float* __restrict__ parts, int n, float scale, float* __restrict__ out) {
+  const int lane = threadIdx.x;
+  float a = 0.f;
+  for (int i = lane; i < n; i += 32) a += parts[i];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[0] = a * scale;
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -653,13 +752,13 @@ int launch_skin_fwd(const JrrModel* m, const Workspace& w, float* vertices_out, 
 }
 
 int launch_loss_seed(const JrrModel* m, const Workspace& w, bool fused_partials, const float* gt_mm,
-                     int64_t B_logical, float w_joint, float* joints17_out, cudaStream_t st) {
+                     int64_t B_logical, float w_joint, float* joints17_out, const Proj2D& p2d, cudaStream_t st) {
   dim3 grid((unsigned)(w.BP / 128)), block(LS_THREADS);
   const float scale = gt_mm != nullptr ? w_joint * 2.f / (51.f * (float)B_logical) : 0.f;
   const int n_tiles = m->nv_act / 64, T = (int)(w.BP / 128) * n_tiles, G = T < m->num_sms ? T : m->num_sms;
   loss_seed_kernel<<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, gt_mm, w.B, w.BP, scale,
                                            gt_mm != nullptr ? w.gT : nullptr, joints17_out,
-                                           w.loss_part);
+                                           w.loss_part, p2d);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
@@ -717,13 +816,27 @@ int launch_joints49_bwd(const JrrModel* m, const Workspace& w, const float* djoi
 }
 
 int launch_loss_finish(const Workspace& w, int64_t B_logical, float w_joint, float w_pose,
-                       bool have_pose, float* loss_out, float* loss_accum, cudaStream_t st) {
+                       bool have_pose, float w_2d, float* loss_out, float* loss_accum, cudaStream_t st) {
   const int nj = (int)(w.BP / SK_THREADS);
   const int np = have_pose ? w.n_pose_part : 0;
   loss_finish_kernel<<<1, 32, 0, st>>>(w.loss_part, nj, 1.f / (51.f * (float)B_logical),
                                        w.loss_part + LOSS_PART_POSE, np, 1.f / (25.f * (float)B_logical),
-                                       w_joint, w_pose, loss_out, loss_accum);
+                                       w.loss_part + LOSS_PART_2D, 1.f / (34.f * (float)B_logical),
+                                       w_joint, w_pose, w_2d, loss_out, loss_accum);
   JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_camera_fit(const Workspace& w, const float* joints17, const float* gt2d, float* cam, int iters, float lr,
+                      int64_t B_logical, float* loss_out, cudaStream_t st) {
+  const unsigned nblk = (unsigned)((w.B + 127) / 128);
+  camera_fit_kernel<<<nblk, 128, 0, st>>>(joints17, gt2d, cam, w.B, iters, lr, 2.f / (34.f * (float)B_logical),
+                                          loss_out ? w.loss_part + LOSS_PART_2D : nullptr);
+  JRR_LAUNCH_CHECK();
+  if (loss_out) {
+    sum_scale_kernel<<<1, 32, 0, st>>>(w.loss_part + LOSS_PART_2D, (int)nblk, 1.f / (34.f * (float)B_logical), loss_out);
+    JRR_LAUNCH_CHECK();
+  }
   return JRR_OK;
 }
 

@@ -197,6 +197,31 @@ class NativeModel:
         self._done()
         return {self.L.jrr_step_kernel_name(i).decode(): float(ms[i]) for i in range(_lib.STEP_KERNELS)}
 
+    def camera_fit(self, x6, betas, gt_j2d, cam, iters=1000, lr=1e-2, logical_batch=None, loss_out=None):
+        """optimize.py:187-199: Adam on the camera translation only; cam [B,3] is updated in place."""
+        B = x6.shape[0]
+        LB = B if logical_batch is None else int(logical_batch)
+        x6, betas, gt_j2d = _f32c(x6, "x6"), _f32c(betas, "betas"), _f32c(gt_j2d, "gt_j2d")
+        if not (cam.is_cuda and cam.dtype == torch.float32 and cam.is_contiguous()):
+            raise JrrError("cam must be a contiguous fp32 CUDA tensor")
+        ws, wsz = self.workspace(B)
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_camera_fit(self.h, B, LB, _ptr(x6), _ptr(betas), _ptr(gt_j2d), _ptr(cam), int(iters),
+                                        lr, _ptr(loss_out), ws, wsz, _stream()), "jrr_camera_fit")
+        self._done()
+
+    def refine_step_2d(self, x6, betas, gt_mm, gt_j2d, cam, adam_m, adam_v, cam_m, cam_v, step_count, lr, w_joint,
+                       w_pose, w_2d, logical_batch=None, loss_out=None):
+        B = x6.shape[0]
+        LB = B if logical_batch is None else int(logical_batch)
+        ws, wsz = self.workspace(B)
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_refine_step_2d(self.h, B, LB, _ptr(x6), _ptr(betas), _ptr(gt_mm), _ptr(gt_j2d), _ptr(cam),
+                                            _ptr(adam_m), _ptr(adam_v), _ptr(cam_m), _ptr(cam_v), _ptr(step_count),
+                                            lr, w_joint, w_pose, w_2d, _ptr(loss_out), ws, wsz, _stream()),
+                  "jrr_refine_step_2d")
+        self._done()
+
     def regressor_grad_accumulate(self, x6, betas, gt_mm, G_accum, loss_accum, logical_batch=None):
         B = x6.shape[0]
         LB = B if logical_batch is None else int(logical_batch)

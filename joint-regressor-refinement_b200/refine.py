@@ -88,6 +88,40 @@ class PoseRefiner:
         for _ in range(iters):
             st["graph"].replay()
 
+    def fit_camera(self, x6, betas, gt_j2d, cam, iters=1000, lr=1e-2, logical_batch=None):
+        """optimize.py:187-199: camera-only Adam against the 2-D joints; `cam` [N,3] updated in place.
+        One body-model forward per chunk (the joints do not depend on the camera)."""
+        N = x6.shape[0]
+        with torch.cuda.device(self.device):
+            for lo in range(0, N, self.chunk):
+                hi = min(N, lo + self.chunk)
+                c = cam[lo:hi].contiguous()
+                self.native.camera_fit(x6[lo:hi].reshape(-1, 24, 6), betas[lo:hi], gt_j2d[lo:hi], c, iters, lr,
+                                       logical_batch=(hi - lo) if logical_batch is None else logical_batch)
+                cam[lo:hi].copy_(c)
+        return cam
+
+    def refine_2d(self, x6, betas, cam, gt_mm, gt_j2d, iters=100, w_2d=0.01, logical_batch=None):
+        """`refine` with the 2-D reprojection term and the camera as a fourth Adam group
+        (optimize.py:201-202,231-233,252-253).  Eager launches (no graph); x6/betas/cam in place."""
+        N = x6.shape[0]
+        loss = torch.zeros(4, device=self.device)
+        with torch.cuda.device(self.device):
+            for lo in range(0, N, self.chunk):
+                hi = min(N, lo + self.chunk)
+                B = hi - lo
+                LB = B if logical_batch is None else logical_batch
+                xs, bs, cs = x6[lo:hi].reshape(B, 24, 6).contiguous(), betas[lo:hi].contiguous(), cam[lo:hi].contiguous()
+                m = torch.zeros(B, 154, device=self.device); v = torch.zeros_like(m)
+                cm = torch.zeros(B, 3, device=self.device); cv = torch.zeros_like(cm)
+                t = torch.zeros(1, dtype=torch.int32, device=self.device)
+                for _ in range(iters):
+                    self.native.refine_step_2d(xs, bs, gt_mm[lo:hi].contiguous(), gt_j2d[lo:hi].contiguous(), cs, m, v,
+                                               cm, cv, t, self.lr, self.w_joint, self.w_pose, w_2d,
+                                               logical_batch=LB, loss_out=loss)
+                x6[lo:hi].copy_(xs.view_as(x6[lo:hi])); betas[lo:hi].copy_(bs); cam[lo:hi].copy_(cs)
+        return loss
+
     def refine(self, x6, betas, gt_mm, iters=100, logical_batch=None):
         """In-place refinement of x6 [N,24,6] / betas [N,10] against gt_mm [N,17,3] (mm,
         pelvis-centred).  Frames are processed in chunks of ``chunk``; each chunk is one

@@ -264,6 +264,61 @@ def refine(smpl, Jraw, critic_sd, x6, betas, gt_mm, iters=100, lr=1e-2, w_joint=
     return x6.detach(), betas.detach(), hist
 
 
+# --------------------------------------------------------------------------- scripts/renderer.py
+def project_2d(joints, cam):
+    """scripts/renderer.py:35-49 with the joints already regressed: flip x and y, scale by 2,
+    then pytorch3d==0.3.0 ``PerspectiveCameras(T=cam, focal_length=5000/224, principal_point=0)``
+    ``.transform_points_screen(points, image_size=224)`` with R = I.  pytorch3d is not available
+    offline, so this projection is restated from its documented convention (PARITY UNPINNED):
+    view = X + T; ndc = f * view.xy / view.z; screen = (224 - 1)/2 * (1 - ndc)."""
+    P = joints * joints.new_tensor([-2.0, -2.0, 2.0]) + cam[:, None, :]
+    f = 5000.0 / 224.0
+    ndc = f * P[..., :2] / P[..., 2:3]
+    return (224 - 1.0) / 2.0 * (1.0 - ndc)
+
+
+def camera_fit(smpl, Jraw, x6, betas, gt_j2d, cam, iters=1000, lr=1e-2, logical_batch=None):
+    """optimize.py:187-199: Adam([cam], lr=1e-2) x iters on MSE(gt_j2d, joints_2d).  The joints do
+    not depend on cam, so they are computed once (the reference recomputes the body model in
+    every iteration; the value is identical)."""
+    B = x6.shape[0]
+    with torch.no_grad():
+        R = rot6d_to_rotmat(x6.reshape(-1, 6)).view(B, 24, 3, 3)
+        joints = find_joints(smpl, betas, R[:, :1], R[:, 1:], Jraw)
+    cam = cam.detach().clone().requires_grad_(True)
+    opt = torch.optim.Adam([cam], lr=lr)
+    LB = B if logical_batch is None else logical_batch
+    loss = None
+    for _ in range(iters):
+        loss = ((gt_j2d - project_2d(joints, cam)) ** 2).sum() / (LB * 17 * 2)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    return cam.detach(), (loss.item() if loss is not None else 0.0)
+
+
+def refine_2d(smpl, Jraw, critic_sd, x6, betas, cam, gt_mm, gt_j2d, iters=100, lr=1e-2, w_joint=10000.0,
+              w_pose=10.0, w_2d=0.01, logical_batch=None):
+    """optimize.py:201-202,220-265 with the 3-D joint, pose-critic and 2-D reprojection terms
+    (everything except the silhouette render): Adam([pose, orient, betas, cam])."""
+    x6 = x6.detach().clone().requires_grad_(True)
+    betas = betas.detach().clone().requires_grad_(True)
+    cam = cam.detach().clone().requires_grad_(True)
+    opt = torch.optim.Adam([x6, betas, cam], lr=lr)
+    B = x6.shape[0]
+    LB = B if logical_batch is None else logical_batch
+    hist = []
+    for _ in range(iters):
+        total, jl, pl, pred = refine_loss(smpl, Jraw, critic_sd, x6, betas, gt_mm, w_joint, w_pose, logical_batch)
+        l2 = ((gt_j2d - project_2d(pred, cam)) ** 2).sum() / (LB * 17 * 2)
+        total = total + w_2d * l2
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+        hist.append((total.item(), jl.item(), pl.item(), l2.item()))
+    return x6.detach(), betas.detach(), cam.detach(), hist
+
+
 def regressor_grad(smpl, Jraw, x6, betas, gt_mm, logical_batch=None, mask=None):
     """optimize.py:300-309 with the published no-op fixed (requires_grad on J):
     returns dL/dJraw [17,6890] and the loss."""

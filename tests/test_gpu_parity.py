@@ -436,3 +436,47 @@ def test_fused_kernels_match_unfused_kernels(jrr, model, critic_sd, J_dense, fra
     assert err < 2e-5
     assert abs(l_f[0].item() - l_u[0].item()) / l_u[0].item() < 1e-6
     assert n_f < n_u
+
+
+# ------------------------------------------------------------------ widening: 2-D reprojection + camera fit
+def _cam_problem(jrr, oracle, osmpl32, J, B, seed):
+    fr = make_frames(jrr, oracle, osmpl32, J, B, seed)
+    g = torch.Generator().manual_seed(seed)
+    cam_true = torch.stack([0.1 * torch.randn(B, generator=g), 0.1 * torch.randn(B, generator=g),
+                            40 + 5 * torch.randn(B, generator=g)], dim=1)
+    with torch.no_grad():
+        R = fr["true_rotmat"]
+        joints = oracle.find_joints(osmpl32, fr["true_betas"], R[:, :1], R[:, 1:], J)
+        gt2d = oracle.project_2d(joints, cam_true) + 0.5 * torch.randn(B, 17, 2, generator=g)
+    cam0 = cam_true + torch.tensor([0.05, -0.05, 3.0]) * torch.randn(B, 3, generator=g)
+    return fr, gt2d, cam0
+
+
+def test_camera_fit_matches_oracle(smpl_tc, jrr, oracle, osmpl32, critic_sd, J_shipped):
+    fr, gt2d, cam0 = _cam_problem(jrr, oracle, osmpl32, J_shipped, 48, 5)
+    cam_o, loss_o = oracle.camera_fit(osmpl32, J_shipped, fr["x6"], fr["betas"], gt2d, cam0, iters=300)
+    ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, use_graph=False)
+    cam = cam0.to(DEV).clone()
+    loss = torch.zeros(1, device=DEV)
+    ref.native.camera_fit(fr["x6"].to(DEV), fr["betas"].to(DEV), gt2d.to(DEV), cam, 300, 1e-2, loss_out=loss)
+    torch.cuda.synchronize()
+    d = (cam.cpu() - cam_o).abs().max().item()
+    print(f"camera fit (300 Adam steps): max |dcam| {d:.2e}; loss oracle {loss_o:.5f} cuda {loss.item():.5f}")
+    assert d < 2e-3 and abs(loss.item() - loss_o) / loss_o < 1e-3
+
+
+def test_refine_with_2d_term_matches_oracle(smpl_tc, jrr, oracle, osmpl32, critic_sd, J_shipped):
+    fr, gt2d, cam0 = _cam_problem(jrr, oracle, osmpl32, J_shipped, 40, 9)
+    x6o, bo, co, hist = oracle.refine_2d(osmpl32, J_shipped, critic_sd, fr["x6"], fr["betas"], cam0, fr["gt_mm"], gt2d,
+                                         iters=3)
+    ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, use_graph=False)
+    x6, be, cam = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone(), cam0.to(DEV).clone()
+    loss = ref.refine_2d(x6, be, cam, fr["gt_mm"].to(DEV), gt2d.to(DEV), iters=3)
+    torch.cuda.synchronize()
+    print(f"refine+2d 3 steps: |dx6| {(x6.cpu() - x6o).abs().max().item():.2e} |dcam| {(cam.cpu() - co).abs().max().item():.2e}; "
+          f"loss {loss.cpu().tolist()} vs {hist[-1]}")
+    assert (x6.cpu() - x6o).abs().max().item() < 2e-4
+    assert (be.cpu() - bo).abs().max().item() < 2e-4
+    assert (cam.cpu() - co).abs().max().item() < 2e-4
+    for got, exp in zip(loss.cpu().tolist(), hist[-1]):
+        assert abs(got - exp) / max(abs(exp), 1e-12) < 1e-4
