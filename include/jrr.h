@@ -161,6 +161,14 @@ int jrr_refine_step_2d(JrrModel* model, int64_t B, int64_t B_logical, float* x6,
                        float w_pose, float w_2d, float* loss_out, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/* --- widening row "evaluation"  ----------------------------------------------
+ * replaces: utils.evaluate (scripts/utils.py:117-145) + batch_compute_similarity_transform_torch
+ * (scripts/eval_utils.py:7-58): mean MPJPE and Procrustes-aligned MPJPE in millimetres.
+ * pred_j3d [B,17,3] metres, target_j3d_mm [B,17,3] millimetres (both are pelvis-centred inside);
+ * out_mm DEVICE float[2]; per_frame_mm DEVICE [B,2] or NULL; scratch: 16 bytes per 128 frames. */
+int jrr_evaluate(int64_t B, const float* pred_j3d, const float* target_j3d_mm, float* out_mm,
+                 float* per_frame_mm, void* scratch, size_t scratch_bytes, void* stream);
+
 /* replaces: the forward/backward half of the regressor refit, optimize.py:300-309
  * (find_joints on detached refined poses, move_pelvis + MSELoss, backward to J_regressor).
  * Accumulates G += dL/dJhat (17x6890, gradient w.r.t. the NORMALISED regressor) and

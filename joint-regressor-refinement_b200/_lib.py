@@ -17,7 +17,7 @@ EXPORTS = [
     "jrr_set_regressor", "jrr_critic_load", "jrr_workspace_bytes", "jrr_smpl_forward",
     "jrr_smpl_backward", "jrr_find_joints", "jrr_critic_forward", "jrr_refine_step",
     "jrr_regressor_grad_accumulate", "jrr_regressor_apply", "jrr_last_launch_count",
-    "jrr_debug_gemm", "jrr_refine_step_profiled", "jrr_step_kernel_name", "jrr_camera_fit", "jrr_refine_step_2d",
+    "jrr_debug_gemm", "jrr_refine_step_profiled", "jrr_step_kernel_name", "jrr_camera_fit", "jrr_refine_step_2d", "jrr_evaluate",
 ]
 
 
@@ -68,6 +68,7 @@ def lib():
     L.jrr_step_kernel_name.restype = C.c_char_p
     L.jrr_camera_fit.argtypes = [vp, i64, i64, vp, vp, vp, vp, C.c_int, f32, vp, vp, sz, vp]
     L.jrr_refine_step_2d.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, sz, vp]
+    L.jrr_evaluate.argtypes = [i64, vp, vp, vp, vp, vp, sz, vp]
     L.jrr_debug_gemm.argtypes = [vp, C.c_int, i64, i64, i64, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

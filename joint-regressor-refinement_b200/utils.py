@@ -76,8 +76,27 @@ def batch_compute_similarity_transform_torch(S1, S2):
     return out.permute(0, 2, 1) if transposed else out
 
 
-def evaluate(pred_j3ds, target_j3ds):
-    """scripts/utils.py:117-145: (MPJPE, PA-MPJPE) in mm; target in mm, prediction in m."""
+def evaluate(pred_j3ds, target_j3ds, per_frame=False):
+    """scripts/utils.py:117-145: (MPJPE, PA-MPJPE) in mm; target in mm, prediction in m.
+    CUDA tensors run the hand-written metric kernel (`jrr_evaluate`: per-frame Procrustes with a
+    Jacobi 3x3 SVD); CPU tensors use the plain torch restatement below."""
+    if pred_j3ds.is_cuda and pred_j3ds.shape[1:] == (17, 3):
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        B = pred_j3ds.shape[0]
+        p = pred_j3ds.detach().float().contiguous()
+        t = target_j3ds.detach().float().contiguous().to(p.device)
+        out = torch.empty(2, device=p.device)
+        pf = torch.empty(B, 2, device=p.device) if per_frame else None
+        scratch = torch.empty((B + 127) // 128 * 2 + 2, dtype=torch.float64, device=p.device)
+        with torch.cuda.device(p.device):
+            _lib.check(L.jrr_evaluate(B, C.c_void_p(p.data_ptr()), C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()),
+                                      C.c_void_p(pf.data_ptr()) if pf is not None else None,
+                                      C.c_void_p(scratch.data_ptr()), C.c_size_t(scratch.numel() * 8),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "jrr_evaluate")
+        o = out.cpu().numpy()
+        return (o[0], o[1], pf) if per_frame else (o[0], o[1])
     with torch.no_grad():
         p = move_pelvis(pred_j3ds.detach().clone().float())
         t = move_pelvis(target_j3ds.detach().clone().float() / 1000)

@@ -480,3 +480,21 @@ def test_refine_with_2d_term_matches_oracle(smpl_tc, jrr, oracle, osmpl32, criti
     assert (cam.cpu() - co).abs().max().item() < 2e-4
     for got, exp in zip(loss.cpu().tolist(), hist[-1]):
         assert abs(got - exp) / max(abs(exp), 1e-12) < 1e-4
+
+
+def test_evaluate_kernel_matches_oracle(jrr, oracle):
+    """On-device MPJPE / PA-MPJPE (Jacobi 3x3 SVD per frame) vs the pinned oracle `evaluate`,
+    including reflected and noisy configurations."""
+    g = torch.Generator().manual_seed(4)
+    for B, noise in ((1, 0.05), (300, 0.05), (257, 0.5)):
+        pred = 0.3 * torch.randn(B, 17, 3, generator=g)
+        tgt = 1000 * (pred + noise * torch.randn(B, 17, 3, generator=g))
+        if B > 1:
+            tgt[::7, :, 0] *= -1          # mirrored targets exercise the det < 0 branch
+        mo, po = oracle.evaluate(pred.double(), tgt.double())
+        mg, pg, pf = jrr.evaluate(pred.to(DEV), tgt.to(DEV), per_frame=True)
+        assert abs(mg - mo) < 1e-2 * max(1.0, mo * 1e-3) and abs(pg - po) < 1e-2 * max(1.0, po * 1e-3), (B, mg, mo, pg, po)
+        assert pf.shape == (B, 2) and abs(pf[:, 0].mean().item() - mo) < 1e-1
+    z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "ref_utils_golden.npz"))
+    mg, pg = jrr.evaluate(torch.from_numpy(z["find_joints"]).to(DEV), torch.from_numpy(z["gt_mm"]).to(DEV))
+    assert abs(mg - float(z["mpjpe"])) < 1e-3 and abs(pg - float(z["pa_mpjpe"])) < 1e-3
