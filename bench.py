@@ -251,7 +251,7 @@ def main():
     refiner.set_regressor(J)
 
     # ---------------------------------------------------------------- end to end (host buffers)
-    loss_pin = torch.zeros(K, 3).pin_memory()
+    loss_pin = torch.zeros(K, 5).pin_memory()
     out_x6, out_be = torch.empty_like(x6_pin).pin_memory(), torch.empty_like(be_pin).pin_memory()
     torch.cuda.synchronize()
     if world > 1:

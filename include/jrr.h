@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define JRR_ABI_VERSION 1
+#define JRR_ABI_VERSION 2
 
 #define JRR_NUM_VERTS 6890
 #define JRR_NUM_JOINTS 24
@@ -39,6 +39,8 @@ extern "C" {
 #define JRR_NUM_PICKS 21
 #define JRR_NUM_OUT_JOINTS 49
 #define JRR_CRITIC_PARAMS 1840153
+#define JRR_SHAPE_CRITIC_PARAMS 171
+#define JRR_LOSS_TERMS 5 /* length of every refine-step loss_out: {total, joint, pose, 2d, shape} */
 
 typedef enum JrrStatus {
   JRR_OK = 0,
@@ -95,6 +97,19 @@ int jrr_set_regressor(JrrModel* model, const float* J17_raw, const float* mask, 
  * (JRR_CRITIC_PARAMS floats). */
 int jrr_critic_load(JrrModel* model, const float* params, void* stream);
 
+/* replaces: Shape_Discriminator.__init__/load_state_dict (scripts/discriminator.py:57-74) and the
+ * weight of its loss term (optimize.py:244,249-250,253: 10).  `params` is DEVICE fp32, the
+ * state_dict flattened in order: shape_operations.0.weight[10,10] .bias[10]
+ * shape_operations.2.weight[5,10] .bias[5] shape_operations.4.weight[1,5] .bias[1]
+ * (JRR_SHAPE_CRITIC_PARAMS floats).  From then on every jrr_refine_step / jrr_refine_step_2d adds
+ * w_shape * mean((sigmoid(shape_critic(betas)) - 1)^2) to the loss and its gradient to the betas.
+ * params == NULL switches the term off again. */
+int jrr_shape_critic_load(JrrModel* model, const float* params, float w_shape, void* stream);
+
+/* replaces: Shape_Discriminator.forward (scripts/discriminator.py:70-74): betas [B,10] ->
+ * sigmoid scores [B]. */
+int jrr_shape_critic_forward(JrrModel* model, int64_t B, const float* betas, float* scores_out, void* stream);
+
 /* bytes of caller-owned device workspace needed by any entry point below for B poses */
 size_t jrr_workspace_bytes(const JrrModel* model, int64_t B);
 
@@ -132,8 +147,9 @@ int jrr_critic_forward(JrrModel* model, int64_t B, const float* rot6d, float* sc
  *   gt_mm [B,17,3]                 pelvis-centred target joints in millimetres
  *   B_logical                      batch size used by the two mean reductions (optimize.py:128),
  *                                  so a shard of a larger batch reproduces its gradients
- *   loss_out                       DEVICE float[3] {total, joint_mse, pose_mse} sums over this
- *                                  shard already divided by the logical element counts; or NULL */
+ *   loss_out                       DEVICE float[JRR_LOSS_TERMS] {total, joint_mse, pose_mse, 2d_mse,
+ *                                  shape_mse} sums over this shard already divided by the logical
+ *                                  element counts (terms that are off read 0); or NULL */
 int jrr_refine_step(JrrModel* model, int64_t B, int64_t B_logical, float* x6, float* betas,
                     const float* gt_mm, float* adam_m, float* adam_v, int32_t* step_count,
                     float lr, float w_joint, float w_pose, float* loss_out, void* workspace,
@@ -151,7 +167,7 @@ int jrr_refine_step(JrrModel* model, int64_t B, int64_t B_logical, float* x6, fl
  *
  * jrr_refine_step_2d: jrr_refine_step with the loss_j2d term added (optimize.py:231-233,252-253,
  * weight w_2d = 1/100 there) and the camera translation as a fourth Adam parameter group
- * (optimize.py:201-202).  cam_adam_m/v [B,3]; loss_out DEVICE float[4] {total, joint, pose, 2d}. */
+ * (optimize.py:201-202).  cam_adam_m/v [B,3]; loss_out as for jrr_refine_step. */
 int jrr_camera_fit(JrrModel* model, int64_t B, int64_t B_logical, const float* x6, const float* betas,
                    const float* gt_j2d, float* cam, int iters, float lr, float* loss_out, void* workspace,
                    size_t workspace_bytes, void* stream);

@@ -4,7 +4,7 @@ backward and the per-pose Adam update, behind the reference's own Python interfa
 from . import synthetic  # noqa: F401
 from . import utils  # noqa: F401
 from ._lib import JrrError, LIB_PATH  # noqa: F401
-from .discriminator import Discriminator  # noqa: F401
+from .discriminator import Discriminator, Shape_Discriminator  # noqa: F401
 from .native import NativeModel, flatten_critic_state_dict  # noqa: F401
 from .refine import PoseRefiner, RegressorRefit, load_j_regressor, save_j_regressor, shard_range  # noqa: F401
 from .smpl import SMPL, SMPLFunction, SMPLOutput  # noqa: F401

@@ -62,6 +62,8 @@ Workspace carve(const JrrModel* m, int64_t B, void* base) {
   w.dh = take(BP * C_H);
   w.dzj = take(BP * NJ);
   w.dx6c = take(BP * 144);
+  w.dbeta_s = take(BP * NB);
+  w.shape_part = take(BP / 128 + 64);
   w.scores = take(BP * 25);
   w.bytes = off;
   return w;
@@ -169,7 +171,7 @@ extern "C" int jrr_smpl_backward(JrrModel* m, int64_t B, const float* betas, con
   if (int rc = launch_skin_bwd(m, w, dvertices, false, use_x, st)) return rc;
   if (int rc = launch_dA_reduce(m, w, false, st)) return rc;
   if (int rc = blend_backward_gemm(m, w, st)) return rc;
-  return launch_pose_bwd(m, w, betas, pose, kind, use_x, false, dbetas_out, dpose_out, nullptr, nullptr,
+  return launch_pose_bwd(m, w, betas, pose, kind, use_x, false, false, dbetas_out, dpose_out, nullptr, nullptr,
                          nullptr, nullptr, nullptr, 0.f, st);
 }
 
@@ -196,6 +198,14 @@ extern "C" int jrr_critic_forward(JrrModel* m, int64_t B, const float* rot6d, fl
   return launch_critic_head(m, w, B, 0.f, scores_out, false, st);
 }
 
+extern "C" int jrr_shape_critic_forward(JrrModel* m, int64_t B, const float* betas, float* scores_out, void* stream) {
+  if (!m || !betas || !scores_out) return fail(JRR_ERR_INVALID, "null argument");
+  if (B <= 0 || B > MAX_POSES_PER_CALL) return fail(JRR_ERR_INVALID, "B out of range");
+  if (!m->has_shape_critic) return fail(JRR_ERR_STATE, "jrr_shape_critic_load has not been called");
+  reset_launch_count();
+  return launch_shape_critic_scores(m, B, betas, scores_out, (cudaStream_t)stream);
+}
+
 // Kernel groups of one refinement step (order of execution); jrr_refine_step_profiled
 // reports one duration per group.
 static const char* const kStepKernelNames[JRR_STEP_KERNELS] = {
@@ -214,6 +224,7 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   if (B_logical < B) return fail(JRR_ERR_INVALID, "B_logical must be >= B");
   const bool critic = w_pose != 0.f;
   if (critic && !m->has_critic) return fail(JRR_ERR_STATE, "w_pose != 0 but jrr_critic_load has not been called");
+  const bool shape = m->has_shape_critic && m->w_shape != 0.f;   // Shape_Discriminator term (optimize.py:244,249-250)
   int mark = 0;
 #define JRR_MARK()                                                      \
   do {                                                                  \
@@ -233,6 +244,7 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
     if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, cs)) return rc;
     if (int rc = critic_backward_gemms(m, w, cs)) return rc;
     if (int rc = launch_critic_post(m, w, x6, cs)) return rc;
+    if (shape) if (int rc = launch_shape_critic(m, w, betas, B_logical, cs)) return rc;
     JRR_CUDA(cudaEventRecord(m->ev_join, m->side));
   }
   JRR_MARK();
@@ -271,13 +283,14 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   if (inl) if (int rc = critic_backward_gemms(m, w, st)) return rc;
   JRR_MARK();
   if (inl) if (int rc = launch_critic_post(m, w, x6, st)) return rc;
+  if (shape && !fork) if (int rc = launch_shape_critic(m, w, betas, B_logical, st)) return rc;
   JRR_MARK();
   if (fork) JRR_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
   if (loss_out)
-    if (int rc = launch_loss_finish(w, B_logical, w_joint, w_pose, critic, w_2d, loss_out, nullptr, st)) return rc;
+    if (int rc = launch_loss_finish(w, B_logical, w_joint, w_pose, critic, w_2d, shape ? m->w_shape : 0.f, loss_out, nullptr, st)) return rc;
   JRR_MARK();
   // chain backward + Adam
-  if (int rc = launch_pose_bwd(m, w, betas, x6, JRR_POSE_ROT6D, false, critic, nullptr, nullptr, x6, betas,
+  if (int rc = launch_pose_bwd(m, w, betas, x6, JRR_POSE_ROT6D, false, critic, shape, nullptr, nullptr, x6, betas,
                                adam_m, adam_v, step_count, lr, st)) return rc;
   JRR_MARK();
 #undef JRR_MARK
@@ -360,7 +373,7 @@ extern "C" int jrr_regressor_grad_accumulate(JrrModel* m, int64_t B, int64_t B_l
   if (int rc = launch_loss_seed(m, w, m->fused_fwd, gt_mm, B_logical, 1.f, nullptr, Proj2D{}, st)) return rc;
   if (int rc = launch_regressor_accumulate(m, w, vT, G_accum, st)) return rc;
   if (loss_accum)
-    if (int rc = launch_loss_finish(w, B_logical, 1.f, 0.f, false, 0.f, nullptr, loss_accum, st)) return rc;
+    if (int rc = launch_loss_finish(w, B_logical, 1.f, 0.f, false, 0.f, 0.f, nullptr, loss_accum, st)) return rc;
   return JRR_OK;
 }
 

@@ -187,6 +187,91 @@ critic_post_kernel(const float* __restrict__ cs, const float* __restrict__ x6,
   for (int i = 0; i < 6; i++) dx6c[idx * 6 + i] = dx[i];
 }
 
+// Shape critic (scripts/discriminator.py:57-74; optimize.py:244,249-250): 10 -> 10 -> ReLU -> 5 -> ReLU -> 1
+// -> sigmoid, loss mean((sigma - 1)^2) over the batch.  171 parameters: one thread per pose does the
+// forward and the input gradient.  sc layout: W0[10][10] b0[10] W1[5][10] b1[5] W2[5] b2[1].
+__global__ void __launch_bounds__(128)
+shape_critic_kernel(const float* __restrict__ sc, const float* __restrict__ betas, int64_t B, float gscale,
+                    float* __restrict__ dbeta_s, float* __restrict__ loss_part, float* __restrict__ scores_out) {
+  __shared__ float sw[171];
+  __shared__ float red[4];
+  for (int i = threadIdx.x; i < 171; i += blockDim.x) sw[i] = sc[i];
+  __syncthreads();
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f;
+  if (b < B) {
+    float x[NB], h0[10], h1[5];
+#pragma unroll
+    for (int i = 0; i < NB; i++) x[i] = betas[b * NB + i];
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      float a = sw[100 + i];
+#pragma unroll
+      for (int k = 0; k < 10; k++) a = fmaf(sw[i * 10 + k], x[k], a);
+      h0[i] = fmaxf(a, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      float a = sw[160 + i];
+#pragma unroll
+      for (int k = 0; k < 10; k++) a = fmaf(sw[110 + i * 10 + k], h0[k], a);
+      h1[i] = fmaxf(a, 0.f);
+    }
+    float z = sw[170];
+#pragma unroll
+    for (int k = 0; k < 5; k++) z = fmaf(sw[165 + k], h1[k], z);
+    const float sg = 1.f / (1.f + expf(-z));
+    l = (sg - 1.f) * (sg - 1.f);
+    if (scores_out != nullptr) scores_out[b] = sg;
+    if (dbeta_s != nullptr) {   // nullptr: inference only
+    const float dz = gscale * (sg - 1.f) * sg * (1.f - sg);
+    float d0[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) d0[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      const float d1 = h1[i] > 0.f ? dz * sw[165 + i] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 10; k++) d0[k] = fmaf(sw[110 + i * 10 + k], d1, d0[k]);
+    }
+    float dx[NB];
+#pragma unroll
+    for (int k = 0; k < NB; k++) dx[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      const float d = h0[i] > 0.f ? d0[i] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 10; k++) dx[k] = fmaf(sw[i * 10 + k], d, dx[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NB; k++) dbeta_s[b * NB + k] = dx[k];
+    }
+  }
+  if (loss_part == nullptr) return;   // uniform over the grid
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 4; i++) t += red[i];
+    loss_part[blockIdx.x] = t;
+  }
+}
+
+int launch_shape_critic(const JrrModel* m, const Workspace& w, const float* betas, int64_t B_logical, cudaStream_t st) {
+  shape_critic_kernel<<<(unsigned)(w.BP / 128), 128, 0, st>>>(
+      m->shape_critic, betas, w.B, m->w_shape * 2.f / (float)B_logical, w.dbeta_s, w.shape_part, nullptr);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_shape_critic_scores(const JrrModel* m, int64_t B, const float* betas, float* scores_out, cudaStream_t st) {
+  shape_critic_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(m->shape_critic, betas, B, 0.f, nullptr, nullptr,
+                                                                  scores_out);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
 int launch_critic_pre(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st) {
   const int64_t n = w.BP * NJ;
   critic_pre_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->critic_small, x6, w.B, w.BP,

@@ -148,6 +148,9 @@ struct JrrModel {
   float *W1t_hi = nullptr, *W1t_lo = nullptr;  // [768][1024]
   float *W2t_hi = nullptr, *W2t_lo = nullptr;  // [1024][1024]
   bool has_critic = false;
+  float* shape_critic = nullptr;             // 171 floats: shape_operations.{0,2,4} weight/bias (discriminator.py:57-74)
+  bool has_shape_critic = false;
+  float w_shape = 0.f;                       // weight of the shape-critic term in the refinement loss (optimize.py:253: 10)
   // the critic chain of a refinement step runs on a forked side stream (joins before Adam)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -189,6 +192,8 @@ struct Workspace {
   float* dh;               // [BP][768]
   float* dzj;              // [BP][24]   grads wrt the 24 joint-head logits
   float* dx6c;             // [BP][144]  critic grad wrt rot6d
+  float* dbeta_s;          // [BP][10]   shape-critic grad wrt betas
+  float* shape_part;       // [BP/128]   shape-critic loss partials
   float* scores;           // [BP][25]
   size_t bytes;
 };
@@ -245,7 +250,7 @@ int launch_joints49_fwd(const JrrModel* m, const Workspace& w, const float* vert
 int launch_joints49_bwd(const JrrModel* m, const Workspace& w, const float* djoints49,
                         cudaStream_t st);
 int launch_pose_bwd(const JrrModel* m, const Workspace& w, const float* betas, const float* pose,
-                    int kind, bool use_dJp, bool use_critic, float* dbetas_out, float* dpose_out,
+                    int kind, bool use_dJp, bool use_critic, bool use_shape, float* dbetas_out, float* dpose_out,
                     // Adam (refine step) -- all NULL on the module path
                     float* x6, float* betas_rw, float* adam_m, float* adam_v, int32_t* step_count,
                     float lr, cudaStream_t st);
@@ -256,9 +261,11 @@ int launch_critic_head(const JrrModel* m, Workspace& w, int64_t B_logical, float
 int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st);
 int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st);
 int launch_critic_post(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st);
+int launch_shape_critic(const JrrModel* m, const Workspace& w, const float* betas, int64_t B_logical, cudaStream_t st);
+int launch_shape_critic_scores(const JrrModel* m, int64_t B, const float* betas, float* scores_out, cudaStream_t st);
 
 int launch_loss_finish(const Workspace& w, int64_t B_logical, float w_joint, float w_pose,
-                       bool have_pose, float w_2d, float* loss_out, float* loss_accum, cudaStream_t st);
+                       bool have_pose, float w_2d, float w_shape, float* loss_out, float* loss_accum, cudaStream_t st);
 
 int launch_regressor_normalise(JrrModel* m, const float* Jraw, const float* mask, cudaStream_t st);
 int launch_regressor_accumulate(const JrrModel* m, const Workspace& w, const float* vT,

@@ -587,6 +587,7 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   if (int rc = dalloc(m, &m->regdot, NH)) return rc;
   // ---- critic state
   if (int rc = dalloc(m, &m->critic_small, 8192)) return rc;
+  if (int rc = dalloc(m, &m->shape_critic, 256)) return rc;
   if (int rc = dalloc(m, &m->W1_hi, (size_t)C_Z * C_H)) return rc;
   if (int rc = dalloc(m, &m->W1_lo, (size_t)C_Z * C_H)) return rc;
   if (int rc = dalloc(m, &m->W1t_hi, (size_t)C_Z * C_H)) return rc;
@@ -689,5 +690,21 @@ extern "C" int jrr_critic_load(JrrModel* m, const float* p, void* stream) {
   split_transpose_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(W2, C_Z, C_Z, m->W2t_hi, m->W2t_lo);
   JRR_LAUNCH_CHECK();
   m->has_critic = true;
+  return JRR_OK;
+}
+
+extern "C" int jrr_shape_critic_load(JrrModel* m, const float* p, float w_shape, void* stream) {
+  if (!m) return fail(JRR_ERR_INVALID, "null argument");
+  reset_launch_count();
+  if (p == nullptr) {   // switch the term off
+    m->has_shape_critic = false;
+    m->w_shape = 0.f;
+    return JRR_OK;
+  }
+  // state_dict order is already the kernel's layout: W0[10][10] b0[10] W1[5][10] b1[5] W2[1][5] b2[1]
+  JRR_CUDA(cudaMemcpyAsync(m->shape_critic, p, JRR_SHAPE_CRITIC_PARAMS * sizeof(float), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  m->has_shape_critic = true;
+  m->w_shape = w_shape;
   return JRR_OK;
 }

@@ -264,7 +264,7 @@ pose_bwd_kernel(const __grid_constant__ ChainTab tab, const float* __restrict__ 
                 const float* __restrict__ JS, const float* betas /* may alias betas_rw */,
                 const float* pose /* may alias x6_rw */, int64_t B, int64_t BP, const float* __restrict__ dAT,
                 const float* __restrict__ dfeat, int ksplit, const float* __restrict__ dJp,
-                const float* __restrict__ dx6c, float* __restrict__ dbetas_out,
+                const float* __restrict__ dx6c, const float* __restrict__ dbeta_s, float* __restrict__ dbetas_out,
                 float* __restrict__ dpose_out, float* x6_rw, float* betas_rw,
                 float* __restrict__ adam_m, float* __restrict__ adam_v,
                 const int32_t* __restrict__ step_count, float lr) {
@@ -348,6 +348,7 @@ pose_bwd_kernel(const __grid_constant__ ChainTab tab, const float* __restrict__ 
   }
   if (lane < NB)
     for (int s = 0; s < ksplit; s++) dbeta += dfeat[((int64_t)s * BP + b) * KA + FEAT_BETA + lane];
+  if (lane < NB && dbeta_s != nullptr) dbeta += dbeta_s[b * NB + lane];   // shape-critic term
 
   // rotation parameter gradient
   float dp[9];
@@ -416,16 +417,17 @@ int launch_pose_fwd(const JrrModel* m, int64_t B, int64_t BP, const float* betas
 }
 
 int launch_pose_bwd(const JrrModel* m, const Workspace& w, const float* betas, const float* pose,
-                    int kind, bool use_dJp, bool use_critic, float* dbetas_out, float* dpose_out,
+                    int kind, bool use_dJp, bool use_critic, bool use_shape, float* dbetas_out, float* dpose_out,
                     float* x6, float* betas_rw, float* adam_m, float* adam_v, int32_t* step_count,
                     float lr, cudaStream_t st) {
   dim3 grid((unsigned)((w.B + POSES_PER_CTA - 1) / POSES_PER_CTA)), block(POSES_PER_CTA * 32);
   const float* dJp = use_dJp ? w.dJp : nullptr;
   const float* dx6c = use_critic ? w.dx6c : nullptr;
+  const float* dbs = use_shape ? w.dbeta_s : nullptr;
   const bool adam = x6 != nullptr;
 #define JRR_PB(KIND, AD)                                                                          \
   pose_bwd_kernel<KIND, AD><<<grid, block, 0, st>>>(m->chain, m->J0, m->JS, betas, pose, w.B, w.BP, \
-      w.dAT, w.dfeat, w.ksplit, dJp, dx6c, dbetas_out, dpose_out, x6, betas_rw, adam_m, adam_v,      \
+      w.dAT, w.dfeat, w.ksplit, dJp, dx6c, dbs, dbetas_out, dpose_out, x6, betas_rw, adam_m, adam_v, \
       step_count, lr)
   if (adam) {
     if (kind != JRR_POSE_ROT6D) return fail(JRR_ERR_INVALID, "Adam step needs rot6d parameters");

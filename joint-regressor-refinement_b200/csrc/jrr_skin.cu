@@ -661,12 +661,15 @@ __global__ void joints49_bwd_kernel(const int* __restrict__ joint_map, const flo
 // ---------------------------------------------------------------------------- loss finish
 __global__ void loss_finish_kernel(const float* __restrict__ lp_joint, int n_joint, float sj,
                                    const float* __restrict__ lp_pose, int n_pose, float sp,
-                                   const float* __restrict__ lp_2d, float s2, float wj, float wp, float w2,
+                                   const float* __restrict__ lp_2d, float s2, const float* __restrict__ lp_shape,
+                                   float ss, float wj, float wp, float w2, float wsh,
                                    float* __restrict__ loss_out, float* __restrict__ loss_accum) {
   // one warp; lane-strided partial sums + xor-shuffle tree: a fixed summation order
   const int lane = threadIdx.x;
-  float a = 0.f, p = 0.f, q = 0.f;
+  float a = 0.f, p = 0.f, q = 0.f, r = 0.f;
   for (int i = lane; i < n_joint; i += 32) a += lp_joint[i];
+  if (wsh != 0.f)
+    for (int i = lane; i < n_joint; i += 32) r += lp_shape[i];
   for (int i = lane; i < n_pose; i += 32) p += lp_pose[i];
   if (w2 != 0.f)
     for (int i = lane; i < n_joint; i += 32) q += lp_2d[i];
@@ -674,16 +677,19 @@ __global__ void loss_finish_kernel(const float* __restrict__ lp_joint, int n_joi
     a += __shfl_xor_sync(0xffffffffu, a, o);
     p += __shfl_xor_sync(0xffffffffu, p, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
+    r += __shfl_xor_sync(0xffffffffu, r, o);
   }
   if (lane != 0) return;
   a *= sj;
   p *= sp;
   q *= s2;
+  r *= ss;
   if (loss_out != nullptr) {
-    loss_out[0] = wj * a + wp * p + w2 * q;
+    loss_out[0] = wj * a + wp * p + w2 * q + wsh * r;
     loss_out[1] = a;
     loss_out[2] = p;
-    if (w2 != 0.f) loss_out[3] = q;
+    loss_out[3] = q;
+    loss_out[4] = r;
   }
   if (loss_accum != nullptr) loss_accum[0] += a;
 }
@@ -816,13 +822,14 @@ int launch_joints49_bwd(const JrrModel* m, const Workspace& w, const float* djoi
 }
 
 int launch_loss_finish(const Workspace& w, int64_t B_logical, float w_joint, float w_pose,
-                       bool have_pose, float w_2d, float* loss_out, float* loss_accum, cudaStream_t st) {
+                       bool have_pose, float w_2d, float w_shape, float* loss_out, float* loss_accum, cudaStream_t st) {
   const int nj = (int)(w.BP / SK_THREADS);
   const int np = have_pose ? w.n_pose_part : 0;
   loss_finish_kernel<<<1, 32, 0, st>>>(w.loss_part, nj, 1.f / (51.f * (float)B_logical),
                                        w.loss_part + LOSS_PART_POSE, np, 1.f / (25.f * (float)B_logical),
                                        w.loss_part + LOSS_PART_2D, 1.f / (34.f * (float)B_logical),
-                                       w_joint, w_pose, w_2d, loss_out, loss_accum);
+                                       w.shape_part, 1.f / (float)B_logical,
+                                       w_joint, w_pose, w_2d, w_shape, loss_out, loss_accum);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }

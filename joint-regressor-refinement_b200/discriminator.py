@@ -41,3 +41,33 @@ class Discriminator(nn.Module):
                                "runs on the CUDA kernels only")
         self._sync_weights()
         return self._native.critic_forward(rot6d.detach().reshape(-1, 24, 6)).unsqueeze(-1)
+
+
+class Shape_Discriminator(nn.Module):
+    """Shape critic with the reference's parameter layout (``scripts/discriminator.py:57-74``):
+    ``shape_operations.{0,2,4}`` = Linear(10,10), Linear(10,5), Linear(5,1).  ``forward`` runs the
+    CUDA kernel; the input gradient used by the refinement loop is inside ``jrr_refine_step``
+    once the weights are handed to ``PoseRefiner(shape_critic_state_dict=...)``."""
+
+    def __init__(self):
+        super().__init__()
+        self.shape_operations = nn.Sequential(nn.Linear(10, 10), nn.ReLU(), nn.Linear(10, 5), nn.ReLU(),
+                                              nn.Linear(5, 1))
+        self._native = None
+        self._loaded_key = None
+        self._w_shape = 10.0
+
+    def bind(self, native: NativeModel, w_shape: float = 10.0):
+        self._native, self._loaded_key, self._w_shape = native, None, float(w_shape)
+        return self
+
+    def forward(self, shapes: torch.Tensor) -> torch.Tensor:
+        """[B,10] -> sigmoid scores [B,1]."""
+        if self._native is None:
+            raise RuntimeError("Shape_Discriminator.bind(smpl.native()) must be called first: the critic "
+                               "runs on the CUDA kernels only")
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if key != self._loaded_key:
+            self._native.load_shape_critic(self.state_dict(), self._w_shape)
+            self._loaded_key = key
+        return self._native.shape_critic_forward(shapes.detach().reshape(-1, 10)).unsqueeze(-1)

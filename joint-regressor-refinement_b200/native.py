@@ -44,6 +44,16 @@ def flatten_critic_state_dict(sd: dict) -> torch.Tensor:
     return flat
 
 
+def flatten_shape_critic_state_dict(sd: dict) -> torch.Tensor:
+    """state_dict of scripts/discriminator.py:Shape_Discriminator -> the 171 floats
+    jrr_shape_critic_load expects."""
+    keys = [f"shape_operations.{i}.{n}" for i in (0, 2, 4) for n in ("weight", "bias")]
+    flat = torch.cat([sd[k].detach().float().reshape(-1) for k in keys])
+    if flat.numel() != 171:
+        raise JrrError(f"shape critic state_dict has {flat.numel()} parameters, expected 171")
+    return flat
+
+
 class NativeModel:
     """Device-resident packed body model + regressor + critic (JrrModel*)."""
 
@@ -115,6 +125,26 @@ class NativeModel:
         with torch.cuda.device(self.device):
             check(self.L.jrr_critic_load(self.h, _ptr(flat), _stream()), "jrr_critic_load")
             torch.cuda.current_stream().synchronize()   # `flat` may be freed after return
+
+    def load_shape_critic(self, state_dict, w_shape: float = 10.0):
+        """Shape_Discriminator weights (scripts/discriminator.py:57-74) + the weight of its loss
+        term (optimize.py:253).  ``state_dict=None`` switches the term off."""
+        with torch.cuda.device(self.device):
+            if state_dict is None:
+                check(self.L.jrr_shape_critic_load(self.h, None, 0.0, _stream()), "jrr_shape_critic_load")
+                return
+            flat = flatten_shape_critic_state_dict(state_dict).to(self.device)
+            check(self.L.jrr_shape_critic_load(self.h, _ptr(flat), float(w_shape), _stream()), "jrr_shape_critic_load")
+            torch.cuda.current_stream().synchronize()   # `flat` may be freed after return
+
+    def shape_critic_forward(self, betas):
+        betas = _f32c(betas, "betas")
+        B = betas.shape[0]
+        out = torch.empty(B, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_shape_critic_forward(self.h, B, _ptr(betas), _ptr(out), _stream()), "jrr_shape_critic_forward")
+        self._done()
+        return out
 
     # ------------------------------------------------------------------ SMPL forward / backward
     def smpl_forward(self, betas, pose, kind, want_verts=True, want_joints=True):

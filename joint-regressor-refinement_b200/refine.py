@@ -25,7 +25,8 @@ def shard_range(n_frames: int, rank: int, world: int):
 
 class PoseRefiner:
     def __init__(self, smpl, J_regressor, critic_state_dict=None, mask=None, lr=1e-2,
-                 w_joint=10000.0, w_pose=10.0, chunk=4096, use_graph=True):
+                 w_joint=10000.0, w_pose=10.0, chunk=4096, use_graph=True, shape_critic_state_dict=None,
+                 w_shape=10.0):
         self.native: NativeModel = smpl.native() if hasattr(smpl, "native") else smpl
         self.device = self.native.device
         self.lr, self.w_joint = float(lr), float(w_joint)
@@ -35,6 +36,9 @@ class PoseRefiner:
         self.set_regressor(J_regressor, mask)
         if critic_state_dict is not None:
             self.native.load_critic(critic_state_dict)
+        # Shape_Discriminator term (optimize.py:244,249-250,253); the weight lives in the native model
+        self.w_shape = float(w_shape) if shape_critic_state_dict is not None else 0.0
+        self.native.load_shape_critic(shape_critic_state_dict, self.w_shape)
         self._bufs = {}      # B -> static buffers (+ graph)
         self.launches_per_step = 0
 
@@ -52,7 +56,7 @@ class PoseRefiner:
                 "gt": torch.zeros(B, 17, 3, device=dev), "m": torch.zeros(B, 154, device=dev),
                 "v": torch.zeros(B, 154, device=dev),
                 "t": torch.zeros(1, dtype=torch.int32, device=dev),
-                "loss": torch.zeros(3, device=dev), "graph": None, "LB": None,
+                "loss": torch.zeros(5, device=dev), "graph": None, "LB": None,
             }
             self._bufs[B] = st
         return st
@@ -105,7 +109,7 @@ class PoseRefiner:
         """`refine` with the 2-D reprojection term and the camera as a fourth Adam group
         (optimize.py:201-202,231-233,252-253).  Eager launches (no graph); x6/betas/cam in place."""
         N = x6.shape[0]
-        loss = torch.zeros(4, device=self.device)
+        loss = torch.zeros(5, device=self.device)
         with torch.cuda.device(self.device):
             for lo in range(0, N, self.chunk):
                 hi = min(N, lo + self.chunk)
@@ -126,7 +130,7 @@ class PoseRefiner:
         """In-place refinement of x6 [N,24,6] / betas [N,10] against gt_mm [N,17,3] (mm,
         pelvis-centred).  Frames are processed in chunks of ``chunk``; each chunk is one
         reference "batch" (fresh Adam state; its size is the divisor of the mean losses unless
-        ``logical_batch`` is given).  Returns the last iteration's [total, joint, pose] loss
+        ``logical_batch`` is given).  Returns the last iteration's [total, joint, pose, 2d, shape] loss
         of the last chunk (device tensor)."""
         N = x6.shape[0]
         x6v, bv, gv = x6.view(N, 24, 6), betas.view(N, 10), gt_mm.view(N, 17, 3)

@@ -226,11 +226,42 @@ def make_critic_state_dict(seed: int = 0) -> dict:
     return sd
 
 
+def shape_discriminator_forward(sd: dict, betas: torch.Tensor) -> torch.Tensor:
+    """scripts/discriminator.py:57-74 as a function of the module's state_dict (keys
+    shape_operations.{0,2,4}): Linear(10,10) ReLU Linear(10,5) ReLU Linear(5,1) sigmoid.
+    betas [B,10] -> scores [B,1]."""
+    dt = betas.dtype
+    g = lambda k: sd[k].to(dt)
+    h = torch.relu(betas @ g("shape_operations.0.weight").t() + g("shape_operations.0.bias"))
+    h = torch.relu(h @ g("shape_operations.2.weight").t() + g("shape_operations.2.bias"))
+    return torch.sigmoid(h @ g("shape_operations.4.weight").t() + g("shape_operations.4.bias"))
+
+
+def make_shape_critic_state_dict(seed: int = 0) -> dict:
+    """Default-init ``Shape_Discriminator()`` parameters under torch.manual_seed(seed), built from
+    the same nn layers in the same order as discriminator.py:62-68 (checked against the reference
+    module in tests/test_oracle_pinning.py)."""
+    from torch import nn
+    gen_state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    ops = nn.Sequential(nn.Linear(10, 10), nn.ReLU(), nn.Linear(10, 5), nn.ReLU(), nn.Linear(5, 1))
+    torch.random.set_rng_state(gen_state)
+    return {f"shape_operations.{k}": v.detach().clone() for k, v in ops.state_dict().items()}
+
+
+def shape_loss(shape_sd, betas, logical_batch=None):
+    """optimize.py:244,249-250: MSE of the shape critic's score against ones."""
+    LB = betas.shape[0] if logical_batch is None else logical_batch
+    return ((shape_discriminator_forward(shape_sd, betas) - 1) ** 2).sum() / LB
+
+
 # --------------------------------------------------------------------------- scripts/optimize.py
 def refine_loss(smpl, Jraw, critic_sd, x6, betas, gt_mm, w_joint=10000.0, w_pose=10.0,
-                logical_batch=None, mask=None):
+                logical_batch=None, mask=None, shape_sd=None, w_shape=10.0):
     """In-scope terms of optimize.py:222-253 for one iteration.  ``logical_batch`` replaces
-    B in the two mean reductions so that a shard reproduces the full-batch gradients."""
+    B in the mean reductions so that a shard reproduces the full-batch gradients.  With
+    ``shape_sd`` the Shape_Discriminator term (weight 10 at optimize.py:253) is added to the
+    total (its value alone: ``shape_loss``)."""
     B = x6.shape[0]
     R = rot6d_to_rotmat(x6.reshape(-1, 6)).view(B, 24, 3, 3)
     pred = find_joints(smpl, betas, R[:, :1], R[:, 1:], Jraw, mask=mask)
@@ -243,11 +274,13 @@ def refine_loss(smpl, Jraw, critic_sd, x6, betas, gt_mm, w_joint=10000.0, w_pose
         sig = discriminator_forward(critic_sd, x6)
         pose_loss = ((sig - 1) ** 2).sum() / (LB * 25)
         total = total + w_pose * pose_loss
+    if shape_sd is not None and w_shape != 0:
+        total = total + w_shape * shape_loss(shape_sd, betas, LB)
     return total, joint_loss, pose_loss, pred
 
 
 def refine(smpl, Jraw, critic_sd, x6, betas, gt_mm, iters=100, lr=1e-2, w_joint=10000.0,
-           w_pose=10.0, logical_batch=None):
+           w_pose=10.0, logical_batch=None, shape_sd=None, w_shape=10.0):
     """optimize.py:201-202,220-265 restricted to the in-scope loss: fresh
     torch.optim.Adam([pose, orient, betas], lr) per batch, `iters` steps."""
     x6 = x6.detach().clone().requires_grad_(True)
@@ -256,11 +289,15 @@ def refine(smpl, Jraw, critic_sd, x6, betas, gt_mm, iters=100, lr=1e-2, w_joint=
     hist = []
     for _ in range(iters):
         total, jl, pl, _ = refine_loss(smpl, Jraw, critic_sd, x6, betas, gt_mm, w_joint, w_pose,
-                                       logical_batch)
+                                       logical_batch, shape_sd=shape_sd, w_shape=w_shape)
+        sl = None
+        if shape_sd is not None:
+            with torch.no_grad():
+                sl = shape_loss(shape_sd, betas, logical_batch).item()
         opt.zero_grad()
         total.backward()
         opt.step()
-        hist.append((total.item(), jl.item(), pl.item()))
+        hist.append((total.item(), jl.item(), pl.item()) + (() if sl is None else (0.0, sl)))
     return x6.detach(), betas.detach(), hist
 
 

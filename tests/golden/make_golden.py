@@ -50,6 +50,12 @@ def main():
              betas=betas.numpy(), find_joints=pred.detach().numpy(), move_pelvis=pelvis.detach().numpy(),
              gt_mm=gt.detach().numpy(), mpjpe=np.float64(mpjpe), pa_mpjpe=np.float64(pampjpe),
              critic_scores=scores.numpy(), mask_sum=np.float64(u.find_j_reg_mask(J).sum().item()))
+    # Shape_Discriminator (scripts/discriminator.py:57-74): default init under seed 0, scores on `betas`
+    torch.manual_seed(0)
+    S = d.Shape_Discriminator()
+    np.savez(os.path.join(HERE, "ref_shape_critic_golden.npz"), betas=betas.numpy(),
+             shape_scores=S(betas).detach().numpy(),
+             **{k.replace(".", "__"): v.detach().numpy() for k, v in S.state_dict().items()})
     print("wrote fixtures; artefact sha256", sha)
 
 

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(jrr):
         assert hasattr(L, name), name
     from jrr_b200 import _lib
     assert set(_lib.EXPORTS) == declared
-    assert _lib.lib().jrr_abi_version() == 1
+    assert _lib.lib().jrr_abi_version() == 2
 
 
 def test_library_is_sm100a_with_tcgen05_and_tma(jrr):

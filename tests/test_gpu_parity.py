@@ -498,3 +498,82 @@ def test_evaluate_kernel_matches_oracle(jrr, oracle):
     z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "ref_utils_golden.npz"))
     mg, pg = jrr.evaluate(torch.from_numpy(z["find_joints"]).to(DEV), torch.from_numpy(z["gt_mm"]).to(DEV))
     assert abs(mg - float(z["mpjpe"])) < 1e-3 and abs(pg - float(z["pa_mpjpe"])) < 1e-3
+
+
+# ------------------------------------------------------------------ row a7: Shape_Discriminator term
+def test_shape_critic_forward_matches_golden(smpl_tc, jrr, oracle):
+    import numpy as np, os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_shape_critic_golden.npz"))
+    S = jrr.Shape_Discriminator().to(DEV)
+    S.load_state_dict({k.replace("__", "."): torch.from_numpy(z[k]) for k in z.files if k.startswith("shape_operations")})
+    got = S.bind(smpl_tc.native())(torch.from_numpy(z["betas"]).to(DEV))
+    assert got.shape == (6, 1)
+    assert np.abs(got.cpu().numpy() - z["shape_scores"]).max() < 1e-6
+    b = torch.randn(1000, 10)
+    ref = oracle.shape_discriminator_forward(oracle.make_shape_critic_state_dict(0), b)
+    assert (S(b.to(DEV)).cpu() - ref).abs().max() < 1e-6
+    smpl_tc.native().load_shape_critic(None)
+
+
+@pytest.mark.parametrize("w_joint,with_pose", [(1.0, False), (10000.0, True)])
+def test_refine_step_with_shape_term(w_joint, with_pose, smpl_tc, jrr, oracle, osmpl64, critic_sd, J_shipped):
+    """One Adam step with the shape-critic term on: losses and the betas gradient against the fp64
+    oracle.  With w_joint = 1 the shape term is a visible share of d loss / d betas."""
+    n = 300          # ragged against the 128-frame blocks
+    fr = make_frames(jrr, oracle, oracle.OracleSMPL(jrr.synthetic.make_smpl_model(0)), J_shipped, n, 33)
+    ssd = oracle.make_shape_critic_state_dict(5)
+    sd64 = {k: v.double() for k, v in critic_sd.items()} if with_pose else None
+    x6 = fr["x6"].double().requires_grad_(True)
+    be = (2 * fr["betas"]).double().requires_grad_(True)
+    total, jl, pl, _ = oracle.refine_loss(osmpl64, J_shipped.double(), sd64, x6, be, fr["gt_mm"].double(), w_joint=w_joint,
+                                          shape_sd={k: v.double() for k, v in ssd.items()}, w_shape=10.0, logical_batch=n + 20)
+    sl = oracle.shape_loss({k: v.double() for k, v in ssd.items()}, be.detach(), n + 20).item()
+    total.backward()
+    try:
+        ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd if with_pose else None, w_joint=w_joint, use_graph=False,
+                              shape_critic_state_dict=ssd, w_shape=10.0)
+        st = ref._buffers(n)
+        st["x6"].copy_(fr["x6"]); st["betas"].copy_(2 * fr["betas"]); st["gt"].copy_(fr["gt_mm"])
+        ref._run_chunk(st, 1, n + 20)
+        torch.cuda.synchronize()
+        loss = st["loss"].cpu().double()
+        assert abs(loss[4] - sl) / sl < 1e-5
+        assert abs(loss[1] - jl.item()) / jl.item() < 1e-5
+        assert abs(loss[0] - total.item()) / total.item() < 1e-5
+        m = st["m"].cpu().double() * 10
+        gall = torch.cat([x6.grad.reshape(n, 144), be.grad], dim=1)
+        err_b = (m[:, 144:] - be.grad).abs().max().item() / be.grad.abs().max().item()
+        err = (m - gall).abs().max().item() / gall.abs().max().item()
+        # share of the shape term in the betas gradient (so the check is not vacuous)
+        be2 = be.detach().clone().requires_grad_(True)
+        (10.0 * oracle.shape_loss({k: v.double() for k, v in ssd.items()}, be2, n + 20)).backward()
+        share = be2.grad.abs().max().item() / be.grad.abs().max().item()
+        print(f"[w_joint={w_joint}] grad rel err {err:.2e}, betas {err_b:.2e}; shape-term share of max |dbeta| {share:.2e}")
+        assert err < 1e-4 and err_b < 1e-4
+        if w_joint == 1.0:
+            assert share > 1e-2
+            # without the term the same step gives a different betas gradient
+            ref.native.load_shape_critic(None)
+            st["x6"].copy_(fr["x6"]); st["betas"].copy_(2 * fr["betas"])
+            ref._run_chunk(st, 1, n + 20)
+            m0 = st["m"].cpu().double() * 10
+            assert (m0[:, 144:] - be.grad).abs().max().item() / be.grad.abs().max().item() > 1e-3
+            assert st["loss"].cpu()[4].item() == 0.0
+    finally:
+        smpl_tc.native().load_shape_critic(None)
+
+
+def test_refine_with_shape_term_graph_20_iterations(smpl_tc, jrr, oracle, osmpl32, critic_sd, J_shipped, frames64):
+    fr = frames64
+    ssd = oracle.make_shape_critic_state_dict(5)
+    x6o, bo, hist = oracle.refine(osmpl32, J_shipped, critic_sd, fr["x6"], fr["betas"], fr["gt_mm"], iters=20,
+                                  shape_sd=ssd, w_shape=10.0)
+    try:
+        ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, shape_critic_state_dict=ssd, w_shape=10.0)
+        x6 = fr["x6"].to(DEV).clone(); be = fr["betas"].to(DEV).clone()
+        loss = ref.refine(x6, be, fr["gt_mm"].to(DEV), iters=20).cpu()
+        assert abs(loss[0].item() - hist[-1][0]) / hist[-1][0] < 1e-3
+        assert abs(loss[4].item() - hist[-1][4]) / hist[-1][4] < 1e-4
+        assert (be.cpu() - bo).abs().max() < 2e-3
+    finally:
+        smpl_tc.native().load_shape_critic(None)

@@ -102,3 +102,20 @@ def test_shards_reproduce_full_batch_gradient(oracle, osmpl64, J_shipped, jrr):
         g += gi
         l += li
     assert torch.allclose(g, g_full, atol=1e-14) and abs(l - l_full) < 1e-14
+
+
+def test_shape_term_shards_and_gradient(oracle, osmpl64, J_shipped, jrr):
+    """The Shape_Discriminator term is a per-frame sum / logical batch: two shards add up to the
+    full-batch loss and gradient (optimize.py:244,249-250)."""
+    sd = {k: v.double() for k, v in oracle.make_shape_critic_state_dict(1).items()}
+    b = torch.randn(12, 10, dtype=torch.float64, requires_grad=True)
+    full = oracle.shape_loss(sd, b)
+    g_full, = torch.autograd.grad(full, b)
+    parts, grads = [], []
+    for lo, hi in ((0, 5), (5, 12)):
+        bs = b[lo:hi].detach().clone().requires_grad_(True)
+        l = oracle.shape_loss(sd, bs, logical_batch=12)
+        parts.append(l.item()); grads.append(torch.autograd.grad(l, bs)[0])
+    assert abs(sum(parts) - full.item()) < 1e-12
+    assert (torch.cat(grads) - g_full).abs().max() < 1e-14
+    assert g_full.abs().max() > 1e-4      # the default-init network is not dead on N(0,1) betas

@@ -38,6 +38,20 @@ def test_golden_critic(oracle, critic_sd, gold):
     assert np.abs(s.numpy() - gold["critic_scores"]).max() < 1e-6
 
 
+def test_golden_shape_critic(oracle):
+    """Shape_Discriminator (scripts/discriminator.py:57-74): scores of the reference module, default
+    init under seed 0, against the oracle restatement on the reference's own weights AND on the
+    oracle's re-creation of that init."""
+    z = np.load(os.path.join(GOLDEN, "ref_shape_critic_golden.npz"))
+    sd = {k.replace("__", "."): torch.from_numpy(z[k]) for k in z.files if k.startswith("shape_operations")}
+    mine = oracle.make_shape_critic_state_dict(0)
+    assert list(mine.keys()) == [f"shape_operations.{i}.{n}" for i in (0, 2, 4) for n in ("weight", "bias")]
+    assert all(torch.equal(sd[k], mine[k]) for k in mine)
+    s = oracle.shape_discriminator_forward(mine, torch.from_numpy(z["betas"]))
+    assert s.shape == (6, 1)
+    assert np.abs(s.numpy() - z["shape_scores"]).max() < 1e-6
+
+
 def test_golden_regressor_fixture_matches_documented_artefact(J_shipped):
     z = np.load(os.path.join(GOLDEN, "j_regressor_nnz.npz"))
     assert str(z["sha256"]) == "4ea32d1b3b9a135130722218f87eadfcf78321cf2ca6954e14f780eb9b60d079"
@@ -95,6 +109,13 @@ def test_live_reference_discriminator_and_state_dict_layout(ref, oracle, jrr, cr
     mine = jrr.Discriminator()
     mine.load_state_dict(sd)
     assert jrr.flatten_critic_state_dict(mine.state_dict()).numel() == 1840153
+    torch.manual_seed(3)
+    S = d.Shape_Discriminator()
+    b = torch.randn(9, 10)
+    assert (S(b) - oracle.shape_discriminator_forward(S.state_dict(), b)).abs().max() < 1e-6
+    mine_s = jrr.Shape_Discriminator()
+    mine_s.load_state_dict(S.state_dict())
+    assert jrr.native.flatten_shape_critic_state_dict(mine_s.state_dict()).numel() == 171
 
 
 @needs_ref
