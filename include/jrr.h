@@ -177,6 +177,34 @@ int jrr_refine_step_2d(JrrModel* model, int64_t B, int64_t B_logical, float* x6,
                        float w_pose, float w_2d, float* loss_out, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/* --- widening row "critic training step"  -----------------------------------
+ * replaces: optimize.py:276-293 -- after a batch has been refined both discriminators take one
+ * Adam step on MSE(D(refined), 0) + MSE(D(initial), 1) (disc_optimizer / shape_disc_optimizer,
+ * optimize.py:113-123).
+ *
+ * jrr_critic_grad_accumulate: G_accum[JRR_CRITIC_PARAMS] (DEVICE, jrr_critic_load's flat order)
+ * += d/dparams of sum_b sum_25 (D(x6)_b - target)^2 / (25 * B_logical) under the CURRENT critic
+ * weights; loss_accum[1] += that loss (or NULL).  Call it with target 0 on the refined poses and
+ * target 1 on the initial ones; per chunk (B <= 16384) and per rank, all-reduce G_accum
+ * (7.36 MB) when frames are sharded.  x6 [B,24,6].
+ *
+ * jrr_critic_apply: torch.optim.Adam step (defaults) on the caller's flat `params` (DEVICE,
+ * in/out; adam_m / adam_v same length; step_count DEVICE int32, incremented), then the model's
+ * packed copies are refreshed from `params` as by jrr_critic_load.
+ *
+ * The jrr_shape_critic_* pair is the same for Shape_Discriminator (betas [B,10], 171 params,
+ * one score per frame). */
+int jrr_critic_grad_accumulate(JrrModel* model, int64_t B, int64_t B_logical, const float* x6, float target,
+                               float* G_accum, float* loss_accum, void* workspace, size_t workspace_bytes,
+                               void* stream);
+int jrr_critic_apply(JrrModel* model, float* params, const float* G, float* adam_m, float* adam_v,
+                     int32_t* step_count, float lr, void* stream);
+int jrr_shape_critic_grad_accumulate(JrrModel* model, int64_t B, int64_t B_logical, const float* betas, float target,
+                                     float* G_accum, float* loss_accum, void* workspace, size_t workspace_bytes,
+                                     void* stream);
+int jrr_shape_critic_apply(JrrModel* model, float* params, const float* G, float* adam_m, float* adam_v,
+                           int32_t* step_count, float lr, void* stream);
+
 /* --- widening row "evaluation"  ----------------------------------------------
  * replaces: utils.evaluate (scripts/utils.py:117-145) + batch_compute_similarity_transform_torch
  * (scripts/eval_utils.py:7-58): mean MPJPE and Procrustes-aligned MPJPE in millimetres.

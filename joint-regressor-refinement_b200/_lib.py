@@ -18,7 +18,8 @@ EXPORTS = [
     "jrr_smpl_backward", "jrr_find_joints", "jrr_critic_forward", "jrr_refine_step",
     "jrr_regressor_grad_accumulate", "jrr_regressor_apply", "jrr_last_launch_count",
     "jrr_debug_gemm", "jrr_refine_step_profiled", "jrr_step_kernel_name", "jrr_camera_fit", "jrr_refine_step_2d", "jrr_evaluate",
-    "jrr_shape_critic_load", "jrr_shape_critic_forward",
+    "jrr_shape_critic_load", "jrr_shape_critic_forward", "jrr_critic_grad_accumulate", "jrr_critic_apply",
+    "jrr_shape_critic_grad_accumulate", "jrr_shape_critic_apply",
 ]
 
 
@@ -56,6 +57,10 @@ def lib():
     L.jrr_critic_load.argtypes = [vp, vp, vp]
     L.jrr_shape_critic_load.argtypes = [vp, vp, C.c_float, vp]
     L.jrr_shape_critic_forward.argtypes = [vp, i64, vp, vp, vp]
+    L.jrr_critic_grad_accumulate.argtypes = [vp, i64, i64, vp, C.c_float, vp, vp, vp, sz, vp]
+    L.jrr_critic_apply.argtypes = [vp, vp, vp, vp, vp, vp, C.c_float, vp]
+    L.jrr_shape_critic_grad_accumulate.argtypes = [vp, i64, i64, vp, C.c_float, vp, vp, vp, sz, vp]
+    L.jrr_shape_critic_apply.argtypes = [vp, vp, vp, vp, vp, vp, C.c_float, vp]
     L.jrr_workspace_bytes.argtypes = [vp, i64]
     L.jrr_workspace_bytes.restype = sz
     L.jrr_smpl_forward.argtypes = [vp, i64, vp, vp, C.c_int, vp, vp, vp, sz, vp]

@@ -386,6 +386,49 @@ extern "C" int jrr_regressor_apply(JrrModel* m, float* J17_raw, const float* mas
   return launch_regressor_apply(m, J17_raw, mask, G_accum, adam_m, adam_v, step_count, lr, (cudaStream_t)stream);
 }
 
+// ---- widening row 8f-1: critic training step (optimize.py:276-293) ------------------------------
+extern "C" int jrr_critic_grad_accumulate(JrrModel* m, int64_t B, int64_t B_logical, const float* x6, float target,
+                                          float* G_accum, float* loss_accum, void* ws, size_t ws_bytes, void* stream) {
+  Workspace w;
+  if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
+  if (!m->has_critic) return fail(JRR_ERR_STATE, "jrr_critic_load has not been called");
+  if (!x6 || !G_accum) return fail(JRR_ERR_INVALID, "null argument");
+  if (B_logical < B) return fail(JRR_ERR_INVALID, "B_logical must be >= B");
+  if (B > 16384) return fail(JRR_ERR_INVALID, "at most 16384 poses per critic-gradient call (chunk and accumulate)");
+  return critic_grad_accumulate(m, w, B_logical, x6, target, G_accum, loss_accum, (cudaStream_t)stream);
+}
+
+extern "C" int jrr_critic_apply(JrrModel* m, float* params, const float* G, float* adam_m, float* adam_v,
+                                int32_t* step_count, float lr, void* stream) {
+  if (!m || !params || !G || !adam_m || !adam_v || !step_count) return fail(JRR_ERR_INVALID, "null argument");
+  reset_launch_count();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = launch_adam_flat(params, G, adam_m, adam_v, step_count, lr, JRR_CRITIC_PARAMS, st)) return rc;
+  return critic_load_impl(m, params, st);
+}
+
+extern "C" int jrr_shape_critic_grad_accumulate(JrrModel* m, int64_t B, int64_t B_logical, const float* betas,
+                                                float target, float* G_accum, float* loss_accum, void* ws,
+                                                size_t ws_bytes, void* stream) {
+  Workspace w;
+  if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
+  if (!m->has_shape_critic) return fail(JRR_ERR_STATE, "jrr_shape_critic_load has not been called");
+  if (!betas || !G_accum) return fail(JRR_ERR_INVALID, "null argument");
+  if (B_logical < B) return fail(JRR_ERR_INVALID, "B_logical must be >= B");
+  return shape_critic_grad_accumulate(m, w, B_logical, betas, target, G_accum, loss_accum, (cudaStream_t)stream);
+}
+
+extern "C" int jrr_shape_critic_apply(JrrModel* m, float* params, const float* G, float* adam_m, float* adam_v,
+                                      int32_t* step_count, float lr, void* stream) {
+  if (!m || !params || !G || !adam_m || !adam_v || !step_count) return fail(JRR_ERR_INVALID, "null argument");
+  if (!m->has_shape_critic) return fail(JRR_ERR_STATE, "jrr_shape_critic_load has not been called");
+  reset_launch_count();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = launch_adam_flat(params, G, adam_m, adam_v, step_count, lr, JRR_SHAPE_CRITIC_PARAMS, st)) return rc;
+  JRR_CUDA(cudaMemcpyAsync(m->shape_critic, params, JRR_SHAPE_CRITIC_PARAMS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return JRR_OK;
+}
+
 namespace jrr {
 __global__ void debug_split_kernel(const float* __restrict__ src, int64_t n, float* __restrict__ hi,
                                    float* __restrict__ lo) {

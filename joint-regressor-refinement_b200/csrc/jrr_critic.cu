@@ -7,18 +7,6 @@
 
 namespace jrr {
 
-// offsets into JrrModel::critic_small (floats)
-constexpr int CS_C1W = 0;       // [32][6]
-constexpr int CS_C1B = 192;     // [32]
-constexpr int CS_C2W = 224;     // [32][32]
-constexpr int CS_C2B = 1248;    // [32]
-constexpr int CS_HW = 1280;     // [24][32]
-constexpr int CS_HB = 2048;     // [24]
-constexpr int CS_B1 = 2072;     // [1024]
-constexpr int CS_B2 = 3096;     // [1024]
-constexpr int CS_W3 = 4120;     // [1024]
-constexpr int CS_B3 = 5144;     // [1]
-constexpr int CS_TOTAL = 5145;
 
 __device__ __forceinline__ float tf32_hi_c(float x) {
   uint32_t r;
@@ -79,9 +67,10 @@ constexpr int HEAD_WARPS = 8;
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 critic_head_kernel(const float* __restrict__ cs, const float* __restrict__ h_hi,
                    const float* __restrict__ h_lo, const float* __restrict__ z2_hi,
-                   const float* __restrict__ z2_lo, int64_t B, int64_t BP, float gscale,
+                   const float* __restrict__ z2_lo, int64_t B, int64_t BP, float gscale, float target,
                    float* __restrict__ scores_out, float* __restrict__ dz2_hi,
-                   float* __restrict__ dz2_lo, float* __restrict__ dzj, float* __restrict__ loss_part) {
+                   float* __restrict__ dz2_lo, float* __restrict__ dzj, float* __restrict__ dzg,
+                   float* __restrict__ loss_part) {
   __shared__ float red[HEAD_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * HEAD_WARPS + warp;
@@ -112,15 +101,16 @@ critic_head_kernel(const float* __restrict__ cs, const float* __restrict__ h_hi,
         if (lane == 0) scores_out[b * 25] = sg;
         if (lane < NJ) scores_out[b * 25 + 1 + lane] = sj;
       }
-      float l = (lane < NJ) ? (sj - 1.f) * (sj - 1.f) : 0.f;
-      if (lane == 0) l += (sg - 1.f) * (sg - 1.f);
+      float l = (lane < NJ) ? (sj - target) * (sj - target) : 0.f;
+      if (lane == 0) l += (sg - target) * (sg - target);
       for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
       lsum = l;
     }
     if (dz2_hi != nullptr) {
-      const float dg = (b < B) ? gscale * (sg - 1.f) * sg * (1.f - sg) : 0.f;
-      const float dj = (b < B && lane < NJ) ? gscale * (sj - 1.f) * sj * (1.f - sj) : 0.f;
+      const float dg = (b < B) ? gscale * (sg - target) * sg * (1.f - sg) : 0.f;
+      const float dj = (b < B && lane < NJ) ? gscale * (sj - target) * sj * (1.f - sj) : 0.f;
       if (lane < NJ) dzj[b * NJ + lane] = dj;
+      if (dzg != nullptr && lane == 0) dzg[b] = dg;
 #pragma unroll
       for (int q = 0; q < 32; q++) {
         const int i = lane + 32 * q;
@@ -281,13 +271,13 @@ int launch_critic_pre(const JrrModel* m, const Workspace& w, const float* x6, cu
 }
 
 int launch_critic_head(const JrrModel* m, Workspace& w, int64_t B_logical, float w_pose,
-                       float* scores_out, bool want_grad, cudaStream_t st) {
+                       float* scores_out, bool want_grad, cudaStream_t st, float target, float* dzg) {
   const unsigned nblk = (unsigned)((w.BP + HEAD_WARPS - 1) / HEAD_WARPS);
   const float gscale = w_pose * 2.f / (25.f * (float)B_logical);
   w.n_pose_part = (int)nblk;
   critic_head_kernel<<<nblk, HEAD_WARPS * 32, 0, st>>>(
-      m->critic_small, w.h_hi, w.h_lo, w.z2_hi, w.z2_lo, w.B, w.BP, gscale, scores_out,
-      want_grad ? w.dz2_hi : nullptr, w.dz2_lo, w.dzj, w.loss_part + LOSS_PART_POSE);
+      m->critic_small, w.h_hi, w.h_lo, w.z2_hi, w.z2_lo, w.B, w.BP, gscale, target, scores_out,
+      want_grad ? w.dz2_hi : nullptr, w.dz2_lo, w.dzj, dzg, w.loss_part + LOSS_PART_POSE);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }

@@ -34,6 +34,19 @@ constexpr int MAXCH = 4;            // children per joint supported by the chain
 
 constexpr int C_H = 768;            // critic: 24*32 conv features
 constexpr int C_Z = 1024;
+// offsets into JrrModel::critic_small (floats)
+constexpr int CS_C1W = 0;       // [32][6]
+constexpr int CS_C1B = 192;     // [32]
+constexpr int CS_C2W = 224;     // [32][32]
+constexpr int CS_C2B = 1248;    // [32]
+constexpr int CS_HW = 1280;     // [24][32]
+constexpr int CS_HB = 2048;     // [24]
+constexpr int CS_B1 = 2072;     // [1024]
+constexpr int CS_B2 = 3096;     // [1024]
+constexpr int CS_W3 = 4120;     // [1024]
+constexpr int CS_B3 = 5144;     // [1]
+constexpr int CS_TOTAL = 5145;
+
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -257,11 +270,18 @@ int launch_pose_bwd(const JrrModel* m, const Workspace& w, const float* betas, c
 
 int launch_critic_pre(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st);
 int launch_critic_head(const JrrModel* m, Workspace& w, int64_t B_logical, float w_pose,
-                       float* scores_out, bool want_grad, cudaStream_t st);
+                       float* scores_out, bool want_grad, cudaStream_t st, float target = 1.f, float* dzg = nullptr);
 int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st);
 int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st);
 int launch_critic_post(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st);
 int launch_shape_critic(const JrrModel* m, const Workspace& w, const float* betas, int64_t B_logical, cudaStream_t st);
+int critic_load_impl(JrrModel* m, const float* params, cudaStream_t st);
+int critic_grad_accumulate(JrrModel* m, Workspace& w, int64_t B_logical, const float* x6, float target, float* G_accum,
+                           float* loss_accum, cudaStream_t st);
+int shape_critic_grad_accumulate(JrrModel* m, Workspace& w, int64_t B_logical, const float* betas, float target,
+                                 float* G_accum, float* loss_accum, cudaStream_t st);
+int launch_adam_flat(float* p, const float* g, float* am, float* av, int32_t* step_count, float lr, int64_t n,
+                     cudaStream_t st);
 int launch_shape_critic_scores(const JrrModel* m, int64_t B, const float* betas, float* scores_out, cudaStream_t st);
 
 int launch_loss_finish(const Workspace& w, int64_t B_logical, float w_joint, float w_pose,

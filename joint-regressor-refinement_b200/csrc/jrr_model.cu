@@ -655,7 +655,10 @@ extern "C" int jrr_set_regressor(JrrModel* m, const float* J17_raw, const float*
 extern "C" int jrr_critic_load(JrrModel* m, const float* p, void* stream) {
   if (!m || !p) return fail(JRR_ERR_INVALID, "null argument");
   reset_launch_count();
-  cudaStream_t st = (cudaStream_t)stream;
+  return critic_load_impl(m, p, (cudaStream_t)stream);
+}
+
+int jrr::critic_load_impl(JrrModel* m, const float* p, cudaStream_t st) {
   // state_dict order (see jrr.h)
   const float* c1w = p;               // 192
   const float* c1b = c1w + 192;       // 32

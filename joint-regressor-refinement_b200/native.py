@@ -54,6 +54,29 @@ def flatten_shape_critic_state_dict(sd: dict) -> torch.Tensor:
     return flat
 
 
+CRITIC_KEYS = (["conv_operations.0.weight", "conv_operations.0.bias", "conv_operations.2.weight",
+                "conv_operations.2.bias"]
+               + [f"linears.{i}.{n}" for i in range(24) for n in ("weight", "bias")]
+               + [f"linear_operations.{i}.{n}" for i in (0, 2, 4) for n in ("weight", "bias")])
+CRITIC_SHAPES = ([(32, 6, 1, 1), (32,), (32, 32, 1, 1), (32,)] + [(1, 32), (1,)] * 24
+                 + [(1024, 768), (1024,), (1024, 1024), (1024,), (1, 1024), (1,)])
+SHAPE_CRITIC_KEYS = [f"shape_operations.{i}.{n}" for i in (0, 2, 4) for n in ("weight", "bias")]
+SHAPE_CRITIC_SHAPES = [(10, 10), (10,), (5, 10), (5,), (1, 5), (1,)]
+
+
+def unflatten_state_dict(flat: torch.Tensor, keys, shapes) -> dict:
+    """Inverse of flatten_*_state_dict: flat parameter vector -> state_dict with the reference's keys."""
+    out, o = {}, 0
+    for k, shp in zip(keys, shapes):
+        n = 1
+        for d in shp:
+            n *= d
+        out[k] = flat[o:o + n].reshape(shp).clone()
+        o += n
+    assert o == flat.numel()
+    return out
+
+
 class NativeModel:
     """Device-resident packed body model + regressor + critic (JrrModel*)."""
 
@@ -145,6 +168,24 @@ class NativeModel:
             check(self.L.jrr_shape_critic_forward(self.h, B, _ptr(betas), _ptr(out), _stream()), "jrr_shape_critic_forward")
         self._done()
         return out
+
+    # ------------------------------------------------------------------ critic training (8f-1)
+    def critic_grad_accumulate(self, x6, target, G, loss=None, logical_batch=None, shape=False):
+        """G += d/dparams mean((D(x) - target)^2) over these frames (divisor: logical batch)."""
+        x = _f32c(x6, "x6" if not shape else "betas")
+        B = x.shape[0]
+        ws, wsz = self.workspace(B)
+        fn = self.L.jrr_shape_critic_grad_accumulate if shape else self.L.jrr_critic_grad_accumulate
+        with torch.cuda.device(self.device):
+            check(fn(self.h, B, int(logical_batch or B), _ptr(x), float(target), _ptr(G), _ptr(loss), ws, wsz,
+                     _stream()), "jrr_critic_grad_accumulate")
+        self._done()
+
+    def critic_apply(self, params, G, m, v, t, lr, shape=False):
+        fn = self.L.jrr_shape_critic_apply if shape else self.L.jrr_critic_apply
+        with torch.cuda.device(self.device):
+            check(fn(self.h, _ptr(params), _ptr(G), _ptr(m), _ptr(v), _ptr(t), float(lr), _stream()), "jrr_critic_apply")
+        self._done()
 
     # ------------------------------------------------------------------ SMPL forward / backward
     def smpl_forward(self, betas, pose, kind, want_verts=True, want_joints=True):

@@ -196,6 +196,66 @@ class RegressorRefit:
         return self.J
 
 
+class CriticTrainer:
+    """optimize.py:113-123,276-293: after a batch has been refined, the pose critic (and, when
+    given, the shape critic) take one Adam step on MSE(D(refined), 0) + MSE(D(initial), 1).
+    The flat parameter vectors, Adam moments and step counters live on the device and persist
+    across batches; the model's packed critic copies are refreshed by every step, so the next
+    ``PoseRefiner.refine`` sees the new weights (captured graphs stay valid: same buffers)."""
+
+    def __init__(self, smpl, critic_state_dict, shape_critic_state_dict=None, lr=1e-3, chunk=4096, w_shape=10.0):
+        from .native import flatten_critic_state_dict, flatten_shape_critic_state_dict
+        self.native: NativeModel = smpl.native() if hasattr(smpl, "native") else smpl
+        dev = self.native.device
+        self.lr, self.chunk = float(lr), min(int(chunk), 16384)
+        self.p = flatten_critic_state_dict(critic_state_dict).to(dev).contiguous()
+        self.native.load_critic(critic_state_dict)
+        self.ps = None
+        if shape_critic_state_dict is not None:
+            self.ps = flatten_shape_critic_state_dict(shape_critic_state_dict).to(dev).contiguous()
+            self.native.load_shape_critic(shape_critic_state_dict, w_shape)
+        mk = lambda p: None if p is None else {
+            "m": torch.zeros_like(p), "v": torch.zeros_like(p), "G": torch.zeros_like(p),
+            "t": torch.zeros(1, dtype=torch.int32, device=dev), "loss": torch.zeros(1, device=dev)}
+        self.st, self.sts = mk(self.p), mk(self.ps)
+
+    def _accumulate(self, st, fake, real, LB, shape):
+        st["G"].zero_(); st["loss"].zero_()
+        for x, target in ((fake, 0.0), (real, 1.0)):
+            for lo in range(0, x.shape[0], self.chunk):
+                self.native.critic_grad_accumulate(x[lo:lo + self.chunk], target, st["G"], st["loss"],
+                                                   logical_batch=LB, shape=shape)
+
+    def step(self, x6_refined, x6_initial, betas_refined=None, betas_initial=None, logical_batch=None):
+        """One training step over this rank's frames.  With torch.distributed initialised the gradients
+        are summed over ranks first and `logical_batch` must be the GLOBAL frame count.  Returns
+        (pose critic loss, shape critic loss or None) as device tensors."""
+        N = x6_refined.shape[0]
+        LB = N if logical_batch is None else int(logical_batch)
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        x6f, x6r = x6_refined.detach().reshape(N, 24, 6), x6_initial.detach().reshape(N, 24, 6)
+        self._accumulate(self.st, x6f, x6r, LB, False)
+        if self.ps is not None:
+            self._accumulate(self.sts, betas_refined.detach(), betas_initial.detach(), LB, True)
+        if multi:
+            dist.all_reduce(self.st["G"]); dist.all_reduce(self.st["loss"])
+            if self.ps is not None:
+                dist.all_reduce(self.sts["G"]); dist.all_reduce(self.sts["loss"])
+        self.native.critic_apply(self.p, self.st["G"], self.st["m"], self.st["v"], self.st["t"], self.lr)
+        if self.ps is not None:
+            self.native.critic_apply(self.ps, self.sts["G"], self.sts["m"], self.sts["v"], self.sts["t"], self.lr,
+                                     shape=True)
+        return self.st["loss"], (None if self.ps is None else self.sts["loss"])
+
+    def state_dict(self):
+        from .native import CRITIC_KEYS, CRITIC_SHAPES, unflatten_state_dict
+        return unflatten_state_dict(self.p, CRITIC_KEYS, CRITIC_SHAPES)
+
+    def shape_state_dict(self):
+        from .native import SHAPE_CRITIC_KEYS, SHAPE_CRITIC_SHAPES, unflatten_state_dict
+        return None if self.ps is None else unflatten_state_dict(self.ps, SHAPE_CRITIC_KEYS, SHAPE_CRITIC_SHAPES)
+
+
 def load_j_regressor(path, device="cpu"):
     """``models/retrained_J_Regressor.pt`` (saved from cuda:0, requires_grad, column-major)
     loads unchanged: map_location + detach + contiguous (test.py:46-47 omits map_location)."""

@@ -386,6 +386,48 @@ class RegressorAdam:
         return self.J.detach()
 
 
+# --------------------------------------------------------------------------- optimize.py:276-293
+def critic_train_loss(sd, x6_fake, x6_real, logical_batch=None):
+    """optimize.py:276-281: MSE(D(refined), 0) + MSE(D(initial), 1); both means over B x 25 scores."""
+    LB = x6_fake.shape[0] if logical_batch is None else logical_batch
+    pf, pr = discriminator_forward(sd, x6_fake), discriminator_forward(sd, x6_real)
+    return (pf ** 2).sum() / (LB * 25) + ((pr - 1) ** 2).sum() / (LB * 25)
+
+
+def shape_critic_train_loss(sd, betas_fake, betas_real, logical_batch=None):
+    """optimize.py:286-290: the same for Shape_Discriminator (one score per frame)."""
+    LB = betas_fake.shape[0] if logical_batch is None else logical_batch
+    pf, pr = shape_discriminator_forward(sd, betas_fake), shape_discriminator_forward(sd, betas_real)
+    return (pf ** 2).sum() / LB + ((pr - 1) ** 2).sum() / LB
+
+
+class CriticAdam:
+    """optimize.py:113-123,282-284,291-293: Adam(lr=opt_disc_learning_rate, default 1e-3 at
+    args.py:13) over a discriminator's parameters, state persisting across batches.
+    ``loss_fn(sd, fake, real, logical_batch)`` is critic_train_loss or shape_critic_train_loss."""
+
+    def __init__(self, sd, loss_fn, lr=1e-3):
+        self.sd = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+        self.loss_fn = loss_fn
+        self.opt = torch.optim.Adam(list(self.sd.values()), lr=lr)
+
+    def grad(self, fake, real, logical_batch=None):
+        loss = self.loss_fn(self.sd, fake, real, logical_batch)
+        gs = torch.autograd.grad(loss, list(self.sd.values()))
+        return loss.item(), dict(zip(self.sd.keys(), gs))
+
+    def step(self, fake, real, logical_batch=None):
+        loss, g = self.grad(fake, real, logical_batch)
+        self.opt.zero_grad()
+        for k, v in self.sd.items():
+            v.grad = g[k].clone()
+        self.opt.step()
+        return loss
+
+    def state_dict(self):
+        return {k: v.detach().clone() for k, v in self.sd.items()}
+
+
 def make_gt(smpl, Jraw, true_rotmat, true_betas, gt_noise_mm):
     """Synthetic GT 3-D joints in mm, pelvis-centred."""
     with torch.no_grad():

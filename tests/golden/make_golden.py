@@ -56,6 +56,33 @@ def main():
     np.savez(os.path.join(HERE, "ref_shape_critic_golden.npz"), betas=betas.numpy(),
              shape_scores=S(betas).detach().numpy(),
              **{k.replace(".", "__"): v.detach().numpy() for k, v in S.state_dict().items()})
+    # critic training step, optimize.py:113-123,276-293, run with the reference's own modules:
+    # two Adam(lr=1e-3) steps of MSE(D(fake),0)+MSE(D(real),1) for both discriminators
+    import torch.nn as nn
+    torch.manual_seed(0)
+    D = d.Discriminator()
+    torch.manual_seed(0)
+    S = d.Shape_Discriminator()
+    optD = torch.optim.Adam(D.parameters(), lr=1e-3); optS = torch.optim.Adam(S.parameters(), lr=1e-3)
+    x6_real = x6 + 0.3 * torch.randn(6, 24, 6, generator=g)
+    betas_real = betas + 0.5 * torch.randn(6, 10, generator=g)
+    mse = nn.MSELoss()
+    losses, losses_s = [], []
+    for _ in range(2):
+        pf, pr = D(x6), D(x6_real)
+        l = mse(pf, torch.zeros(pf.shape)) + mse(pr, torch.ones(pf.shape))
+        optD.zero_grad(); l.backward(); optD.step(); losses.append(l.item())
+        pf, pr = S(betas), S(betas_real)
+        l = mse(pf, torch.zeros(pf.shape)) + mse(pr, torch.ones(pf.shape))
+        optS.zero_grad(); l.backward(); optS.step(); losses_s.append(l.item())
+    sdD = D.state_dict()
+    np.savez(os.path.join(HERE, "ref_critic_train_golden.npz"), x6_fake=x6.numpy(), x6_real=x6_real.numpy(),
+             betas_fake=betas.numpy(), betas_real=betas_real.numpy(), losses=np.array(losses), losses_shape=np.array(losses_s),
+             conv0_w=sdD["conv_operations.0.weight"].numpy(), conv2_b=sdD["conv_operations.2.bias"].numpy(),
+             lin3_w=sdD["linears.3.weight"].numpy(), lin3_b=sdD["linears.3.bias"].numpy(),
+             w1_block=sdD["linear_operations.0.weight"][:4, :8].numpy(), b2=sdD["linear_operations.2.bias"].numpy(),
+             w3=sdD["linear_operations.4.weight"].numpy(),
+             **{"shape__" + k.replace(".", "__"): v.detach().numpy() for k, v in S.state_dict().items()})
     print("wrote fixtures; artefact sha256", sha)
 
 

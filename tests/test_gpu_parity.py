@@ -577,3 +577,123 @@ def test_refine_with_shape_term_graph_20_iterations(smpl_tc, jrr, oracle, osmpl3
         assert (be.cpu() - bo).abs().max() < 2e-3
     finally:
         smpl_tc.native().load_shape_critic(None)
+
+
+# ------------------------------------------------------------------ row 8f-1: critic training step
+def _flat_grad(jrr, g):
+    return jrr.native.flatten_critic_state_dict(g)
+
+
+def _kink_free_frames(sd64, n, gen, scale=0.7):
+    """Random rot6d frames none of whose critic pre-activations sits within round-off of a ReLU kink
+    (there fp32 may legitimately take the other branch and a whole gradient row changes by that
+    frame's term, which says nothing about the kernels)."""
+    keep = []
+    while sum(k.shape[0] for k in keep) < n:
+        x = scale * torch.randn(2 * n, 24, 6, generator=gen)
+        xd = x.double()
+        p1 = xd @ sd64["conv_operations.0.weight"].reshape(32, 6).t() + sd64["conv_operations.0.bias"]
+        p2 = torch.relu(p1) @ sd64["conv_operations.2.weight"].reshape(32, 32).t() + sd64["conv_operations.2.bias"]
+        h = torch.relu(p2).reshape(2 * n, 768)
+        a1 = h @ sd64["linear_operations.0.weight"].t() + sd64["linear_operations.0.bias"]
+        a2 = torch.relu(a1) @ sd64["linear_operations.2.weight"].t() + sd64["linear_operations.2.bias"]
+        ok = (a1.abs().min(1).values > 5e-5) & (a2.abs().min(1).values > 5e-5)
+        ok &= (p1.abs().reshape(2 * n, -1).min(1).values > 2e-6) & (p2.abs().reshape(2 * n, -1).min(1).values > 2e-6)
+        keep.append(x[ok])
+    return torch.cat(keep)[:n].contiguous()
+
+
+@pytest.mark.parametrize("n,lb", [(300, 320), (1000, 1000)])
+def test_critic_weight_gradient_matches_fp64_oracle(n, lb, smpl_tc, jrr, oracle, critic_sd):
+    """d/dparams of MSE(D(fake),0) + MSE(D(real),1) (optimize.py:276-281) against fp64 autograd, per tensor."""
+    g = torch.Generator().manual_seed(n)
+    sd64 = {k: v.double() for k, v in critic_sd.items()}
+    fake, real = _kink_free_frames(sd64, n, g), _kink_free_frames(sd64, n, g)
+    A = oracle.CriticAdam(sd64, oracle.critic_train_loss)
+    loss, grads = A.grad(fake.double(), real.double(), lb)
+    nat = smpl_tc.native()
+    nat.load_critic(critic_sd)
+    G = torch.zeros(1840153, device=DEV); L = torch.zeros(1, device=DEV)
+    nat.critic_grad_accumulate(fake.to(DEV), 0.0, G, L, logical_batch=lb)
+    nat.critic_grad_accumulate(real.to(DEV), 1.0, G, L, logical_batch=lb)
+    torch.cuda.synchronize()
+    assert abs(L.item() - loss) / loss < 1e-5
+    got = jrr.native.unflatten_state_dict(G.cpu(), jrr.native.CRITIC_KEYS, jrr.native.CRITIC_SHAPES)
+    worst = 0.0
+    for k, ge in grads.items():
+        err = (got[k].double() - ge).abs().max().item() / max(ge.abs().max().item(), 1e-12)
+        worst = max(worst, err)
+        assert err < 1e-4, (k, err)      # 1-element tensors (head biases) are sums with cancellation: fp32 round-off ~4e-5
+    print(f"critic weight gradient n={n}: worst per-tensor rel err {worst:.2e}")
+    # accumulate semantics / sharding: two shards of `fake` add up to the full call
+    G2 = torch.zeros_like(G); G3 = torch.zeros_like(G)
+    nat.critic_grad_accumulate(fake.to(DEV), 0.0, G2, None, logical_batch=lb)
+    nat.critic_grad_accumulate(fake[:113].to(DEV), 0.0, G3, None, logical_batch=lb)
+    nat.critic_grad_accumulate(fake[113:].to(DEV), 0.0, G3, None, logical_batch=lb)
+    assert (G2 - G3).abs().max().item() < 1e-5 * G2.abs().max().item()
+    # run-to-run identical (no atomics)
+    G4 = torch.zeros_like(G)
+    nat.critic_grad_accumulate(fake.to(DEV), 0.0, G4, None, logical_batch=lb)
+    assert torch.equal(G2, G4)
+
+
+def test_shape_critic_weight_gradient_matches_fp64_oracle(smpl_tc, jrr, oracle):
+    n, lb = 777, 800
+    g = torch.Generator().manual_seed(5)
+    fake = 1.5 * torch.randn(n, 10, generator=g); real = 1.5 * torch.randn(n, 10, generator=g)
+    ssd = oracle.make_shape_critic_state_dict(2)
+    A = oracle.CriticAdam({k: v.double() for k, v in ssd.items()}, oracle.shape_critic_train_loss)
+    loss, grads = A.grad(fake.double(), real.double(), lb)
+    nat = smpl_tc.native()
+    try:
+        nat.load_shape_critic(ssd, 10.0)
+        G = torch.zeros(171, device=DEV); L = torch.zeros(1, device=DEV)
+        nat.critic_grad_accumulate(fake.to(DEV), 0.0, G, L, logical_batch=lb, shape=True)
+        nat.critic_grad_accumulate(real.to(DEV), 1.0, G, L, logical_batch=lb, shape=True)
+        assert abs(L.item() - loss) / loss < 1e-5
+        got = jrr.native.unflatten_state_dict(G.cpu(), jrr.native.SHAPE_CRITIC_KEYS, jrr.native.SHAPE_CRITIC_SHAPES)
+        for k, ge in grads.items():
+            assert (got[k].double() - ge).abs().max().item() / ge.abs().max().item() < 1e-5, k
+    finally:
+        nat.load_shape_critic(None)
+
+
+def test_critic_trainer_three_steps_match_oracle_adam(smpl_tc, jrr, oracle, critic_sd):
+    """CriticTrainer (optimize.py:113-123,276-293) against torch.optim.Adam on the oracle: losses of
+    three consecutive steps (each depends on the previous update), parameters after them, and
+    the packed copies used by the refinement kernels are the updated ones."""
+    n = 512
+    g = torch.Generator().manual_seed(9)
+    fake = 0.7 * torch.randn(n, 24, 6, generator=g); real = 0.7 * torch.randn(n, 24, 6, generator=g)
+    bf = torch.randn(n, 10, generator=g); br = torch.randn(n, 10, generator=g)
+    ssd = oracle.make_shape_critic_state_dict(2)
+    A = oracle.CriticAdam(critic_sd, oracle.critic_train_loss, lr=1e-3)
+    S = oracle.CriticAdam(ssd, oracle.shape_critic_train_loss, lr=1e-3)
+    nat = smpl_tc.native()
+    try:
+        T = jrr.CriticTrainer(smpl_tc, critic_sd, ssd, lr=1e-3, chunk=200)      # ragged chunks
+        for i in range(3):
+            lo, ls = A.step(fake, real), S.step(bf, br)
+            lp, lsh = T.step(fake.to(DEV), real.to(DEV), bf.to(DEV), br.to(DEV))
+            assert abs(lp.item() - lo) / lo < 2e-5, (i, lp.item(), lo)
+            assert abs(lsh.item() - ls) / ls < 2e-5, (i, lsh.item(), ls)
+        sd_o, sd_c = A.state_dict(), T.state_dict()
+        assert list(sd_c.keys()) == list(sd_o.keys())
+        for k in sd_o:
+            assert sd_c[k].shape == sd_o[k].shape
+            d = (sd_c[k].cpu() - sd_o[k]).abs()
+            # Adam moves every weight by ~lr per step whatever |g| is, so round-off (and the odd ReLU branch
+            # flip) shows where |g| ~ 0: mean within 3 % of the 3*lr travelled, max within 2*3*lr
+            assert d.mean().item() < 1e-4 and d.max().item() <= 6.1e-3, (k, d.mean().item(), d.max().item())
+        so, sc = S.state_dict(), T.shape_state_dict()
+        for k in so:
+            assert (sc[k].cpu() - so[k]).abs().max().item() < 1e-5, k
+        # the refinement path now scores with the trained weights
+        x = 0.7 * torch.randn(50, 24, 6)
+        got = nat.critic_forward(x.to(DEV)).cpu()
+        ref = oracle.discriminator_forward(sd_c_cpu := {k: v.cpu() for k, v in sd_c.items()}, x)[..., 0]
+        assert (got - ref).abs().max().item() < 1e-5
+        assert (got - oracle.discriminator_forward(critic_sd, x)[..., 0]).abs().max().item() > 1e-4
+    finally:
+        nat.load_shape_critic(None)
+        nat.load_critic(critic_sd)

@@ -52,6 +52,26 @@ def test_golden_shape_critic(oracle):
     assert np.abs(s.numpy() - z["shape_scores"]).max() < 1e-6
 
 
+def test_golden_critic_training_steps(oracle, critic_sd):
+    """optimize.py:276-293 run with the reference's own modules and torch.optim.Adam (two steps,
+    fixture from make_golden.py) against the oracle's CriticAdam."""
+    z = np.load(os.path.join(GOLDEN, "ref_critic_train_golden.npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    A = oracle.CriticAdam(critic_sd, oracle.critic_train_loss, lr=1e-3)
+    S = oracle.CriticAdam(oracle.make_shape_critic_state_dict(0), oracle.shape_critic_train_loss, lr=1e-3)
+    for i in range(2):
+        assert abs(A.step(t("x6_fake"), t("x6_real")) - z["losses"][i]) < 1e-6
+        assert abs(S.step(t("betas_fake"), t("betas_real")) - z["losses_shape"][i]) < 1e-6
+    sd = A.state_dict()
+    for key, name in (("conv0_w", "conv_operations.0.weight"), ("conv2_b", "conv_operations.2.bias"),
+                      ("lin3_w", "linears.3.weight"), ("lin3_b", "linears.3.bias"),
+                      ("b2", "linear_operations.2.bias"), ("w3", "linear_operations.4.weight")):
+        assert np.abs(sd[name].numpy() - z[key]).max() < 2e-6, name
+    assert np.abs(sd["linear_operations.0.weight"][:4, :8].numpy() - z["w1_block"]).max() < 2e-6
+    for k, v in S.state_dict().items():
+        assert np.abs(v.numpy() - z["shape__" + k.replace(".", "__")]).max() < 2e-6, k
+
+
 def test_golden_regressor_fixture_matches_documented_artefact(J_shipped):
     z = np.load(os.path.join(GOLDEN, "j_regressor_nnz.npz"))
     assert str(z["sha256"]) == "4ea32d1b3b9a135130722218f87eadfcf78321cf2ca6954e14f780eb9b60d079"
