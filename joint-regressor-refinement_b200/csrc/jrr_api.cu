@@ -64,6 +64,10 @@ Workspace carve(const JrrModel* m, int64_t B, void* base) {
   w.dx6c = take(BP * 144);
   w.dbeta_s = take(BP * NB);
   w.shape_part = take(BP / 128 + 64);
+  w.zj = take(BP * NJ);
+  w.zg_part = take(BP * (C_Z / 128));
+  w.dzg = take(BP);
+  w.cmask = reinterpret_cast<uint2*>(take(BP * NJ * 2));
   w.scores = take(BP * 25);
   w.bytes = off;
   return w;
@@ -234,15 +238,17 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   // The critic chain only reads x6 and its own workspace slices, so outside profiling it is
   // forked onto the model's side stream and joins again before the Adam kernel (inside a
   // CUDA-graph capture this becomes a parallel branch of the graph).
+  const bool hf = m->critic_head_fused;      // global head inside the layer-2 GEMM epilogue
   const bool fork = critic && ev == nullptr && m->overlap_critic;
   cudaStream_t cs = fork ? m->side : st;
   if (fork) {
     JRR_CUDA(cudaEventRecord(m->ev_fork, st));
     JRR_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
-    if (int rc = launch_critic_pre(m, w, x6, cs)) return rc;
-    if (int rc = critic_forward_gemms(m, w, cs)) return rc;
-    if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, cs)) return rc;
-    if (int rc = critic_backward_gemms(m, w, cs)) return rc;
+    if (int rc = launch_critic_pre(m, w, x6, cs, hf)) return rc;
+    if (int rc = critic_forward_gemms(m, w, cs, hf)) return rc;
+    if (hf) { if (int rc = launch_critic_head_light(m, w, B_logical, w_pose, cs)) return rc; }
+    else if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, cs)) return rc;
+    if (int rc = critic_backward_gemms(m, w, cs, hf ? w.dzg : nullptr)) return rc;
     if (int rc = launch_critic_post(m, w, x6, cs)) return rc;
     if (shape) if (int rc = launch_shape_critic(m, w, betas, B_logical, cs)) return rc;
     JRR_CUDA(cudaEventRecord(m->ev_join, m->side));
@@ -274,13 +280,16 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   }
   // critic forward + input gradient (inline when profiling or when the fork is disabled)
   const bool inl = critic && !fork;
-  if (inl) if (int rc = launch_critic_pre(m, w, x6, st)) return rc;
+  if (inl) if (int rc = launch_critic_pre(m, w, x6, st, hf)) return rc;
   JRR_MARK();
-  if (inl) if (int rc = critic_forward_gemms(m, w, st)) return rc;
+  if (inl) if (int rc = critic_forward_gemms(m, w, st, hf)) return rc;
   JRR_MARK();
-  if (inl) if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, st)) return rc;
+  if (inl) {
+    if (hf) { if (int rc = launch_critic_head_light(m, w, B_logical, w_pose, st)) return rc; }
+    else if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, st)) return rc;
+  }
   JRR_MARK();
-  if (inl) if (int rc = critic_backward_gemms(m, w, st)) return rc;
+  if (inl) if (int rc = critic_backward_gemms(m, w, st, hf ? w.dzg : nullptr)) return rc;
   JRR_MARK();
   if (inl) if (int rc = launch_critic_post(m, w, x6, st)) return rc;
   if (shape && !fork) if (int rc = launch_shape_critic(m, w, betas, B_logical, st)) return rc;

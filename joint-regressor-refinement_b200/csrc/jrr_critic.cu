@@ -17,14 +17,19 @@ __device__ __forceinline__ float tf32_hi_c(float x) {
 // thread = (pose, joint): conv1x1 6->32, ReLU, conv1x1 32->32, ReLU -> h[b][j*32+c] (hi/lo)
 __global__ void __launch_bounds__(256)
 critic_pre_kernel(const float* __restrict__ cs, const float* __restrict__ x6, int64_t B, int64_t BP,
-                  float* __restrict__ h_hi, float* __restrict__ h_lo) {
+                  float* __restrict__ h_hi, float* __restrict__ h_lo, float* __restrict__ zj_out,
+                  uint2* __restrict__ masks_out) {
   __shared__ float sw[CS_HW];
+  __shared__ float shw[NJ * 33];     // joint-head weights, row stride 33: lanes hold different joints
   for (int i = threadIdx.x; i < CS_HW; i += blockDim.x) sw[i] = cs[i];
+  if (zj_out != nullptr)
+    for (int i = threadIdx.x; i < NJ * 32; i += blockDim.x) shw[(i >> 5) * 33 + (i & 31)] = cs[CS_HW + i];
   __syncthreads();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= BP * NJ) return;
   const int64_t b = idx / NJ;
   float h2[32];
+  uint32_t m1 = 0, m2 = 0;     // ReLU masks of the two convs, reused by critic_post_kernel
   if (b < B) {
     float x[6];
     for (int i = 0; i < 6; i++) x[i] = x6[idx * 6 + i];
@@ -35,6 +40,7 @@ critic_pre_kernel(const float* __restrict__ cs, const float* __restrict__ x6, in
 #pragma unroll
       for (int i = 0; i < 6; i++) a = fmaf(sw[CS_C1W + k * 6 + i], x[i], a);
       h1[k] = fmaxf(a, 0.f);
+      m1 |= (a > 0.f ? 1u : 0u) << k;
     }
 #pragma unroll 4
     for (int c = 0; c < 32; c++) {
@@ -42,10 +48,19 @@ critic_pre_kernel(const float* __restrict__ cs, const float* __restrict__ x6, in
 #pragma unroll
       for (int k = 0; k < 32; k++) a = fmaf(sw[CS_C2W + c * 32 + k], h1[k], a);
       h2[c] = fmaxf(a, 0.f);
+      m2 |= (a > 0.f ? 1u : 0u) << c;
     }
   } else {
 #pragma unroll
     for (int c = 0; c < 32; c++) h2[c] = 0.f;
+  }
+  if (masks_out != nullptr) masks_out[idx] = make_uint2(m1, m2);
+  if (zj_out != nullptr) {   // joint head logit (linears.j), consumed by critic_head_light_kernel
+    const int j = (int)(idx % NJ);
+    float zj = __ldg(cs + CS_HB + j);
+#pragma unroll
+    for (int c = 0; c < 32; c++) zj = fmaf(shw[j * 33 + c], h2[c], zj);
+    zj_out[idx] = zj;
   }
   float4* ph = reinterpret_cast<float4*>(h_hi + idx * 32);
   float4* pl = reinterpret_cast<float4*>(h_lo + idx * 32);
@@ -130,49 +145,80 @@ critic_head_kernel(const float* __restrict__ cs, const float* __restrict__ h_hi,
   }
 }
 
-// thread = (pose, joint): back through the joint head and the two 1x1 convs -> dx6c[b][j*6+i]
+// Refinement-step head when the global head's logit partials come out of the second wide GEMM's
+// epilogue (EPI_BIAS_RELU_HEAD) and the joint logits out of critic_pre: warp = pose, lane < 24 the
+// joint heads, lane 24 the global head.  Writes dL/dlogit (dzj, dzg) and the loss partial.
+__global__ void __launch_bounds__(HEAD_WARPS * 32)
+critic_head_light_kernel(const float* __restrict__ cs, const float* __restrict__ zj, const float* __restrict__ zg_part,
+                         int n_part, int64_t B, int64_t BP, float gscale, float* __restrict__ dzj,
+                         float* __restrict__ dzg, float* __restrict__ loss_part) {
+  __shared__ float red[HEAD_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * HEAD_WARPS + warp;
+  float l = 0.f;
+  if (b < BP) {
+    float z = 0.f;
+    if (lane < NJ) z = zj[b * NJ + lane];
+    else if (lane == NJ) {
+      z = cs[CS_B3];
+      for (int i = 0; i < n_part; i++) z += zg_part[(int64_t)i * BP + b];
+    }
+    const float sg = 1.f / (1.f + expf(-z));
+    const bool on = b < B && lane <= NJ;
+    const float d = on ? gscale * (sg - 1.f) * sg * (1.f - sg) : 0.f;
+    if (lane < NJ) dzj[b * NJ + lane] = d;
+    else if (lane == NJ) dzg[b] = d;
+    l = on ? (sg - 1.f) * (sg - 1.f) : 0.f;
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  }
+  if (lane == 0) red[warp] = l;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < HEAD_WARPS; i++) t += red[i];
+    loss_part[blockIdx.x] = t;
+  }
+}
+
+// thread = (pose, joint): back through the joint head and the two 1x1 convs -> dx6c[b][j*6+i].
+// The ReLU masks come from critic_pre_kernel (no forward recompute).
 __global__ void __launch_bounds__(256)
-critic_post_kernel(const float* __restrict__ cs, const float* __restrict__ x6,
+critic_post_kernel(const float* __restrict__ cs, const uint2* __restrict__ masks,
                    const float* __restrict__ dh, const float* __restrict__ dzj, int64_t B,
                    float* __restrict__ dx6c) {
-  __shared__ float sw[CS_HB];
-  for (int i = threadIdx.x; i < CS_HB; i += blockDim.x) sw[i] = cs[i];
+  __shared__ float sw[CS_HW];
+  __shared__ float shw[NJ * 33];
+  for (int i = threadIdx.x; i < CS_HW; i += blockDim.x) sw[i] = cs[i];
+  for (int i = threadIdx.x; i < NJ * 32; i += blockDim.x) shw[(i >> 5) * 33 + (i & 31)] = cs[CS_HW + i];
   __syncthreads();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * NJ) return;
   const int j = (int)(idx % NJ);
-  float x[6];
-  for (int i = 0; i < 6; i++) x[i] = x6[idx * 6 + i];
-  float h1[32];
-#pragma unroll
-  for (int k = 0; k < 32; k++) {
-    float a = sw[CS_C1B + k];
-#pragma unroll
-    for (int i = 0; i < 6; i++) a = fmaf(sw[CS_C1W + k * 6 + i], x[i], a);
-    h1[k] = fmaxf(a, 0.f);
-  }
+  const uint2 mk = masks[idx];
   const float dj = dzj[idx];
+  float d[32];
+  const float4* dh4 = reinterpret_cast<const float4*>(dh + idx * 32);
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const float4 t = dh4[q];
+    d[4 * q + 0] = t.x; d[4 * q + 1] = t.y; d[4 * q + 2] = t.z; d[4 * q + 3] = t.w;
+  }
+#pragma unroll
+  for (int c = 0; c < 32; c++) d[c] = ((mk.y >> c) & 1u) ? fmaf(dj, shw[j * 33 + c], d[c]) : 0.f;
   float dh1[32];
 #pragma unroll
   for (int k = 0; k < 32; k++) dh1[k] = 0.f;
 #pragma unroll 4
   for (int c = 0; c < 32; c++) {
-    float a = sw[CS_C2B + c];
 #pragma unroll
-    for (int k = 0; k < 32; k++) a = fmaf(sw[CS_C2W + c * 32 + k], h1[k], a);
-    if (a > 0.f) {
-      const float d = dh[idx * 32 + c] + dj * sw[CS_HW + j * 32 + c];
-#pragma unroll
-      for (int k = 0; k < 32; k++) dh1[k] = fmaf(sw[CS_C2W + c * 32 + k], d, dh1[k]);
-    }
+    for (int k = 0; k < 32; k++) dh1[k] = fmaf(sw[CS_C2W + c * 32 + k], d[c], dh1[k]);
   }
   float dx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int k = 0; k < 32; k++) {
-    if (h1[k] > 0.f) {
+    const float t = ((mk.x >> k) & 1u) ? dh1[k] : 0.f;
 #pragma unroll
-      for (int i = 0; i < 6; i++) dx[i] = fmaf(sw[CS_C1W + k * 6 + i], dh1[k], dx[i]);
-    }
+    for (int i = 0; i < 6; i++) dx[i] = fmaf(sw[CS_C1W + k * 6 + i], t, dx[i]);
   }
   for (int i = 0; i < 6; i++) dx6c[idx * 6 + i] = dx[i];
 }
@@ -262,10 +308,20 @@ int launch_shape_critic_scores(const JrrModel* m, int64_t B, const float* betas,
   return JRR_OK;
 }
 
-int launch_critic_pre(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st) {
+int launch_critic_pre(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st, bool want_zj) {
   const int64_t n = w.BP * NJ;
   critic_pre_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->critic_small, x6, w.B, w.BP,
-                                                                w.h_hi, w.h_lo);
+                                                                w.h_hi, w.h_lo, want_zj ? w.zj : nullptr, w.cmask);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+int launch_critic_head_light(const JrrModel* m, Workspace& w, int64_t B_logical, float w_pose, cudaStream_t st) {
+  const unsigned nblk = (unsigned)((w.BP + HEAD_WARPS - 1) / HEAD_WARPS);
+  const float gscale = w_pose * 2.f / (25.f * (float)B_logical);
+  w.n_pose_part = (int)nblk;
+  critic_head_light_kernel<<<nblk, HEAD_WARPS * 32, 0, st>>>(m->critic_small, w.zj, w.zg_part, C_Z / 128, w.B, w.BP,
+                                                            gscale, w.dzj, w.dzg, w.loss_part + LOSS_PART_POSE);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
@@ -284,14 +340,16 @@ int launch_critic_head(const JrrModel* m, Workspace& w, int64_t B_logical, float
 
 int launch_critic_post(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st) {
   const int64_t n = w.B * NJ;
-  critic_post_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->critic_small, x6, w.dh, w.dzj,
+  (void)x6;
+  critic_post_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->critic_small, w.cmask, w.dh, w.dzj,
                                                                  w.B, w.dx6c);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
 
-// The four wide GEMMs around the small kernels.
-int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st) {
+// The four wide GEMMs around the small kernels.  head_fused: the second layer's epilogue also does
+// the global head (logit partials + its masked gradient row), see EPI_BIAS_RELU_HEAD.
+int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, bool head_fused) {
   GemmDesc g{};
   g.A_hi = w.h_hi; g.A_lo = w.h_lo; g.lda = C_H;
   g.B_hi = m->W1_hi; g.B_lo = m->W1_lo; g.ldb = C_H;
@@ -302,12 +360,18 @@ int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st)
   g.A_hi = w.z1_hi; g.A_lo = w.z1_lo; g.lda = C_Z;
   g.B_hi = m->W2_hi; g.B_lo = m->W2_lo; g.ldb = C_Z;
   g.K = C_Z; g.out0 = w.z2_hi; g.out1 = w.z2_lo; g.bias = m->critic_small + CS_B2;
+  if (head_fused) {
+    g.epi = EPI_BIAS_RELU_HEAD;
+    g.out0 = w.dz2_hi; g.out1 = w.dz2_lo;          // (z2 > 0) * w3, the head's gradient row up to dL/dlogit
+    g.vec = m->critic_small + CS_W3; g.out2 = w.zg_part;
+  }
   return launch_gemm(m, g, st);
 }
 
-int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st) {
+int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, const float* rowscale) {
   GemmDesc g{};
-  // dz1 = (dz2 . W2) * [z1 > 0]
+  // dz1 = (dz2 . W2) * [z1 > 0]   (head_fused: dz2 rows still lack their scalar dL/dlogit = rowscale)
+  g.rowscale = rowscale;
   g.A_hi = w.dz2_hi; g.A_lo = w.dz2_lo; g.lda = C_Z;
   g.B_hi = m->W2t_hi; g.B_lo = m->W2t_lo; g.ldb = C_Z;
   g.M = w.BP; g.N = C_Z; g.K = C_Z; g.ksplit = 1; g.epi = EPI_MASK_SPLIT;
@@ -318,7 +382,7 @@ int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st
   g.A_hi = w.dz1_hi; g.A_lo = w.dz1_lo; g.lda = C_Z;
   g.B_hi = m->W1t_hi; g.B_lo = m->W1t_lo; g.ldb = C_Z;
   g.N = C_H; g.K = C_Z; g.epi = EPI_STORE_SPLITK; g.out0 = w.dh; g.out1 = nullptr; g.ldo = C_H;
-  g.mask = nullptr;
+  g.mask = nullptr; g.rowscale = nullptr;
   return launch_gemm(m, g, st);
 }
 

@@ -247,12 +247,10 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
               const f32x2 ww = pk2(wk[k], wk[k]);                                                     \
               o01 = fma2(ww, u01, o01);                                                               \
               o2 = fmaf(wk[k], u2, o2);                                                               \
-              _Pragma("unroll") for (int r = 0; r < 3; r++) {                                         \
-                const float wd = wk[k] * dv[ii][r];                                                   \
-                const f32x2 wdd = pk2(wd, wd);                                                        \
-                dA01[k][r] = fma2(wdd, vp01, dA01[k][r]);                                             \
-                dA23[k][r] = fma2(wdd, vp21, dA23[k][r]);                                             \
-              }                                                                                       \
+              const f32x2 wv01 = mul2(ww, vp01), wv21 = mul2(ww, vp21);                               \
+              dA01[k][0] = fma2(d0, wv01, dA01[k][0]); dA23[k][0] = fma2(d0, wv21, dA23[k][0]);       \
+              dA01[k][1] = fma2(d1, wv01, dA01[k][1]); dA23[k][1] = fma2(d1, wv21, dA23[k][1]);       \
+              dA01[k][2] = fma2(d2, wv01, dA01[k][2]); dA23[k][2] = fma2(d2, wv21, dA23[k][2]);       \
             }                                                                                         \
             upk2(o01, o[ii * 3 + 0], o[ii * 3 + 1]);                                                  \
             o[ii * 3 + 2] = o2;                                                                       \

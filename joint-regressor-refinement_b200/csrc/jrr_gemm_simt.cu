@@ -92,7 +92,7 @@ gemm_simt_kernel(GemmDesc g) {
           g.out0[m * g.ldo + n] = hi;
           g.out1[m * g.ldo + n] = tf32_hi_s(v - hi);
         } else if (EPI == EPI_MASK_SPLIT) {
-          v = g.mask[m * g.ldmask + n] > 0.f ? v : 0.f;
+          v = g.mask[m * g.ldmask + n] > 0.f ? v * (g.rowscale != nullptr ? g.rowscale[m] : 1.f) : 0.f;
           float hi = tf32_hi_s(v);
           g.out0[m * g.ldo + n] = hi;
           g.out1[m * g.ldo + n] = tf32_hi_s(v - hi);

@@ -30,6 +30,9 @@ struct TcParams {
   float* out0; float* out1; int64_t ldo;
   const float* bias;
   const float* mask; int64_t ldmask;
+  const float* rowscale;   // EPI_MASK_SPLIT: multiply row m by rowscale[m] (or nullptr)
+  const float* vec;        // EPI_BIAS_RELU_HEAD: w3[N]
+  float* out2;             // EPI_BIAS_RELU_HEAD: zg_part[n_tile][M]
 };
 
 template <int BN>
@@ -156,12 +159,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       tc_fence_after();
       const int64_t m = (int64_t)mb * BM + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
+      float zsum = 0.f;   // EPI_BIAS_RELU_HEAD: this row's share of the global head's logit
+      float rs = 1.f;
+      if (EPI == EPI_MASK_SPLIT && p.rowscale != nullptr && m < p.M) rs = p.rowscale[m];
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
         float v[32];
         tc_ld32(trow + c * 32, v);
         const int64_t n0 = (int64_t)nb * BN + c * 32;
-        if (EPI == EPI_STORE_T) {
+        if (EPI == EPI_BIAS_RELU_HEAD) {
+          // x = relu(acc + b); logit partial sum x.w3; and the head's masked gradient row
+          // (x > 0 ? w3 : 0) as a tf32 hi/lo pair -- the per-row scalar dL/dlogit is applied by the
+          // EPILOGUE of the backward GEMM (rowscale), so no kernel ever reads the activations back
+          if (m < p.M && n0 < p.N) {
+            float hi[32], lo[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+              const float x = fmaxf(v[i] + __ldg(p.bias + n0 + i), 0.f);
+              const float w = __ldg(p.vec + n0 + i);
+              zsum = fmaf(x, w, zsum);
+              const float wh = tf32_hi_g(w);
+              hi[i] = x > 0.f ? wh : 0.f;
+              lo[i] = x > 0.f ? tf32_hi_g(w - wh) : 0.f;
+            }
+            float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
+            float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+          }
+        } else if (EPI == EPI_STORE_T) {
           // out[n][m]: lanes hold consecutive m -> one 128-byte line per column
           if (m < p.M) {
 #pragma unroll
@@ -175,7 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             for (int i = 0; i < 32; i++) {
               float x = v[i];
               if (EPI == EPI_BIAS_RELU_SPLIT) x = fmaxf(x + __ldg(p.bias + n0 + i), 0.f);
-              else x = (p.mask[m * p.ldmask + n0 + i] > 0.f) ? x : 0.f;
+              else x = (p.mask[m * p.ldmask + n0 + i] > 0.f) ? x * rs : 0.f;
               hi[i] = tf32_hi_g(x);
               lo[i] = tf32_hi_g(x - hi[i]);
             }
@@ -195,6 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
           }
         }
       }
+      if (EPI == EPI_BIAS_RELU_HEAD && m < p.M) p.out2[(int64_t)nb * p.M + m] = zsum;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -263,6 +293,7 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   p.m_tiles = (int)(g.M / BM);
   p.n_tiles = (int)((g.N + BN - 1) / BN);
   p.out0 = g.out0; p.out1 = g.out1; p.ldo = g.ldo; p.bias = g.bias; p.mask = g.mask; p.ldmask = g.ldmask;
+  p.rowscale = g.rowscale; p.vec = g.vec; p.out2 = g.out2;
   auto kern = gemm_tc_kernel<BN, EPI>;
   JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
@@ -285,6 +316,9 @@ int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
       break;
     case EPI_MASK_SPLIT:
       if (g.N % 128 == 0) return launch_tc<128, EPI_MASK_SPLIT>(m, g, st);
+      break;
+    case EPI_BIAS_RELU_HEAD:
+      if (g.N % 128 == 0) return launch_tc<128, EPI_BIAS_RELU_HEAD>(m, g, st);
       break;
     case EPI_STORE_SPLITK:
       if (g.N == 224) return launch_tc<224, EPI_STORE_SPLITK>(m, g, st);

@@ -168,6 +168,7 @@ struct JrrModel {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_critic = true;
+  bool critic_head_fused = true;             // global critic head inside the layer-2 GEMM epilogue (refine step)
   bool fused_fwd = true;   // loss path: skinning + regressor in the blend GEMM's epilogue
   bool fused_bwd = true;   // loss path: skinning backward generates the A operand of the blend-gradient GEMM
   std::vector<void*> allocs;
@@ -207,6 +208,10 @@ struct Workspace {
   float* dx6c;             // [BP][144]  critic grad wrt rot6d
   float* dbeta_s;          // [BP][10]   shape-critic grad wrt betas
   float* shape_part;       // [BP/128]   shape-critic loss partials
+  float* zj;               // [BP][24]   joint-head logits (head-fused critic path)
+  float* zg_part;          // [8][BP]    global-head logit partials per 128-column tile of layer 2
+  float* dzg;              // [BP]       dL/d(global logit)
+  uint2* cmask;            // [BP][24]   ReLU masks of the critic's two 1x1 convs (pre -> post)
   float* scores;           // [BP][25]
   size_t bytes;
 };
@@ -217,7 +222,7 @@ int launch_pose_fwd(const JrrModel* m, int64_t B, int64_t BP, const float* betas
                     int kind, float* AT, float* feat_hi, float* feat_lo, float* Jp, cudaStream_t st);
 
 // C[m][n] = sum_k A[m][k] * B[n][k], operands given as tf32 hi/lo pairs
-enum GemmEpi { EPI_STORE_T = 0, EPI_BIAS_RELU_SPLIT = 1, EPI_MASK_SPLIT = 2, EPI_STORE_SPLITK = 3 };
+enum GemmEpi { EPI_STORE_T = 0, EPI_BIAS_RELU_SPLIT = 1, EPI_MASK_SPLIT = 2, EPI_STORE_SPLITK = 3, EPI_BIAS_RELU_HEAD = 4 };
 struct GemmDesc {
   const float *A_hi, *A_lo; int64_t lda;
   const float *B_hi, *B_lo; int64_t ldb;
@@ -227,6 +232,8 @@ struct GemmDesc {
   float* out0; float* out1; int64_t ldo;   // out (or out_hi/out_lo)
   const float* bias;                       // [N] (EPI_BIAS_RELU_SPLIT)
   const float* mask; int64_t ldmask;       // (EPI_MASK_SPLIT) multiply by (mask>0)
+  const float* rowscale;                   // (EPI_MASK_SPLIT) and by rowscale[m] when given
+  const float* vec; float* out2;           // (EPI_BIAS_RELU_HEAD) w3[N] in, logit partials [N/128][M] out
 };
 int launch_gemm(const JrrModel* m, const GemmDesc& g, cudaStream_t st);
 int launch_gemm_simt(const GemmDesc& g, cudaStream_t st);
@@ -268,11 +275,12 @@ int launch_pose_bwd(const JrrModel* m, const Workspace& w, const float* betas, c
                     float* x6, float* betas_rw, float* adam_m, float* adam_v, int32_t* step_count,
                     float lr, cudaStream_t st);
 
-int launch_critic_pre(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st);
+int launch_critic_pre(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st, bool want_zj = false);
 int launch_critic_head(const JrrModel* m, Workspace& w, int64_t B_logical, float w_pose,
                        float* scores_out, bool want_grad, cudaStream_t st, float target = 1.f, float* dzg = nullptr);
-int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st);
-int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st);
+int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, bool head_fused = false);
+int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, const float* rowscale = nullptr);
+int launch_critic_head_light(const JrrModel* m, Workspace& w, int64_t B_logical, float w_pose, cudaStream_t st);
 int launch_critic_post(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st);
 int launch_shape_critic(const JrrModel* m, const Workspace& w, const float* betas, int64_t B_logical, cudaStream_t st);
 int critic_load_impl(JrrModel* m, const float* params, cudaStream_t st);

@@ -451,7 +451,8 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   if (const char* e = getenv("JRR_FUSED_FWD")) m->fused_fwd = (e[0] != '0');
   if (const char* e = getenv("JRR_FUSED_BWD")) m->fused_bwd = (e[0] != '0');
   if (const char* e = getenv("JRR_COMPACT_ACTIVE")) m->compact_active = (e[0] != '0');
-  if (m->gemm_impl != 0) { m->fused_fwd = false; m->fused_bwd = false; }
+  if (const char* e = getenv("JRR_CRITIC_HEAD_FUSED")) m->critic_head_fused = (e[0] != '0');
+  if (m->gemm_impl != 0) { m->fused_fwd = false; m->fused_bwd = false; m->critic_head_fused = false; }
   // the active-vertex prefix is only walked by the two fused kernels; the stand-alone skinning
   // kernels always process every vertex, so compaction is tied to the fused configuration
   if (!(m->fused_fwd && m->fused_bwd)) m->compact_active = false;

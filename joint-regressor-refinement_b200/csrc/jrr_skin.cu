@@ -189,7 +189,7 @@ skin_fwd_kernel(const VtxRec* __restrict__ vrec, const int* __restrict__ perm,
 // CTA = one pose block of 128.  Phase 1: 8 warps sum the slots row by row (4 independent
 // 128-byte loads per slot and lane, slots unrolled) into smem; phase 2: 128 threads do the
 // per-pose maths; phase 3: all threads write gT coalesced.
-constexpr int LS_THREADS = 256;
+constexpr int LS_THREADS = 512;
 
 // 2-D reprojection of the 17 regressed joints (scripts/renderer.py:35-49 with pytorch3d 0.3.0
 // PerspectiveCameras, R = I, focal 5000/224, principal point 0, 224x224 screen):
@@ -225,18 +225,21 @@ __device__ __forceinline__ void adam_update3(float T[3], const float dT[3], floa
   }
 }
 
+// PPB poses per CTA: 32 (more CTAs in flight; the kernel is latency-bound on the partial-slot loads) or 128
+template <int PPB>
 __global__ void __launch_bounds__(LS_THREADS)
 loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T, int G,
                  const float* __restrict__ gt_mm, int64_t B, int64_t BP, float scale,
                  float* __restrict__ gT, float* __restrict__ joints17_out, float* __restrict__ loss_part,
                  const Proj2D p2d) {
-  __shared__ float sp[NACC][128];
-  __shared__ float red[4], red2[4];
+  constexpr int NC = PPB / 32;
+  __shared__ float sp[NACC][PPB];
+  __shared__ float red[NC], red2[NC];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t b0 = (int64_t)blockIdx.x * 128;
+  const int64_t b0 = (int64_t)blockIdx.x * PPB;
   if (nslots <= 0) {
     // partials written by the fused forward kernel: two per CTA segment of this pose block
-    const int mb = blockIdx.x;
+    const int mb = (int)(b0 / 128);      // the fused forward's 128-pose block
     const int c0 = (int)(((int64_t)mb * n_tiles * G) / T);
     const int c1 = (int)((((int64_t)(mb + 1) * n_tiles - 1) * G) / T);
     nslots = 2 * (c1 - c0 + 1);
@@ -244,28 +247,27 @@ loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T,
   const int64_t slot_stride = (int64_t)NACC * BP;
   for (int a = warp; a < NACC; a += LS_THREADS / 32) {
     const float* src = part + (int64_t)a * BP + b0 + lane;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    int s = 0;
-    for (; s + 4 <= nslots; s += 4) {
-      float v[4][4];
+    float acc[NC];
 #pragma unroll
-      for (int u = 0; u < 4; u++)
+    for (int c = 0; c < NC; c++) acc[c] = 0.f;
+    // 8 slots per round trip (predicated): the kernel is bound by the latency of these loads
+    for (int s = 0; s < nslots; s += 8) {
+      float v[8][NC];
 #pragma unroll
-        for (int c = 0; c < 4; c++) v[u][c] = src[(int64_t)(s + u) * slot_stride + 32 * c];
+      for (int u = 0; u < 8; u++)
 #pragma unroll
-      for (int u = 0; u < 4; u++)
+        for (int c = 0; c < NC; c++) v[u][c] = (s + u < nslots) ? src[(int64_t)(s + u) * slot_stride + 32 * c] : 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; c++) acc[c] += v[u][c];
+      for (int u = 0; u < 8; u++)
+#pragma unroll
+        for (int c = 0; c < NC; c++) acc[c] += v[u][c];
     }
-    for (; s < nslots; s++)
 #pragma unroll
-      for (int c = 0; c < 4; c++) acc[c] += src[(int64_t)s * slot_stride + 32 * c];
-#pragma unroll
-    for (int c = 0; c < 4; c++) sp[a][lane + 32 * c] = acc[c];
+    for (int c = 0; c < NC; c++) sp[a][lane + 32 * c] = acc[c];
   }
   __syncthreads();
   float loss = 0.f, loss2 = 0.f;
-  if (tid < 128) {
+  if (tid < PPB) {
     const int64_t b = b0 + tid;
     float pred[NACC];
 #pragma unroll
@@ -312,14 +314,17 @@ loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T,
     loss += __shfl_xor_sync(0xffffffffu, loss, o);
     loss2 += __shfl_xor_sync(0xffffffffu, loss2, o);
   }
-  if (tid < 128 && lane == 0) { red[warp] = loss; red2[warp] = loss2; }
+  if (tid < PPB && lane == 0) { red[warp] = loss; red2[warp] = loss2; }
   __syncthreads();
   if (tid == 0) {
-    loss_part[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
-    loss_part[LOSS_PART_2D + blockIdx.x] = (red2[0] + red2[1]) + (red2[2] + red2[3]);
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; c++) { t1 += red[c]; t2 += red2[c]; }
+    loss_part[blockIdx.x] = t1;
+    loss_part[LOSS_PART_2D + blockIdx.x] = t2;
   }
-  for (int idx = tid; idx < NACC * 128; idx += LS_THREADS) {
-    const int a = idx >> 7, bl = idx & 127;
+  for (int idx = tid; idx < NACC * PPB; idx += LS_THREADS) {
+    const int a = idx / PPB, bl = idx % PPB;
     gT[(int64_t)a * BP + b0 + bl] = sp[a][bl];
   }
 }
@@ -662,14 +667,14 @@ __global__ void joints49_bwd_kernel(const int* __restrict__ joint_map, const flo
 __global__ void loss_finish_kernel(const float* __restrict__ lp_joint, int n_joint, float sj,
                                    const float* __restrict__ lp_pose, int n_pose, float sp,
                                    const float* __restrict__ lp_2d, float s2, const float* __restrict__ lp_shape,
-                                   float ss, float wj, float wp, float w2, float wsh,
+                                   int n_shape, float ss, float wj, float wp, float w2, float wsh,
                                    float* __restrict__ loss_out, float* __restrict__ loss_accum) {
   // one warp; lane-strided partial sums + xor-shuffle tree: a fixed summation order
   const int lane = threadIdx.x;
   float a = 0.f, p = 0.f, q = 0.f, r = 0.f;
   for (int i = lane; i < n_joint; i += 32) a += lp_joint[i];
   if (wsh != 0.f)
-    for (int i = lane; i < n_joint; i += 32) r += lp_shape[i];
+    for (int i = lane; i < n_shape; i += 32) r += lp_shape[i];
   for (int i = lane; i < n_pose; i += 32) p += lp_pose[i];
   if (w2 != 0.f)
     for (int i = lane; i < n_joint; i += 32) q += lp_2d[i];
@@ -757,14 +762,21 @@ int launch_skin_fwd(const JrrModel* m, const Workspace& w, float* vertices_out, 
   return JRR_OK;
 }
 
+// poses per CTA of the loss-seed kernel: 32 while the partial count fits its 2048-entry region
+static inline int loss_seed_ppb(int64_t BP) { return BP / 32 <= 2048 ? 32 : 128; }
+
 int launch_loss_seed(const JrrModel* m, const Workspace& w, bool fused_partials, const float* gt_mm,
                      int64_t B_logical, float w_joint, float* joints17_out, const Proj2D& p2d, cudaStream_t st) {
-  dim3 grid((unsigned)(w.BP / 128)), block(LS_THREADS);
+  const int ppb = loss_seed_ppb(w.BP);
+  dim3 grid((unsigned)(w.BP / ppb)), block(LS_THREADS);
   const float scale = gt_mm != nullptr ? w_joint * 2.f / (51.f * (float)B_logical) : 0.f;
   const int n_tiles = m->nv_act / 64, T = (int)(w.BP / 128) * n_tiles, G = T < m->num_sms ? T : m->num_sms;
-  loss_seed_kernel<<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, gt_mm, w.B, w.BP, scale,
-                                           gt_mm != nullptr ? w.gT : nullptr, joints17_out,
-                                           w.loss_part, p2d);
+  if (ppb == 32)
+    loss_seed_kernel<32><<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, gt_mm, w.B, w.BP, scale,
+                                                 gt_mm != nullptr ? w.gT : nullptr, joints17_out, w.loss_part, p2d);
+  else
+    loss_seed_kernel<128><<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, gt_mm, w.B, w.BP, scale,
+                                                  gt_mm != nullptr ? w.gT : nullptr, joints17_out, w.loss_part, p2d);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
@@ -823,12 +835,12 @@ int launch_joints49_bwd(const JrrModel* m, const Workspace& w, const float* djoi
 
 int launch_loss_finish(const Workspace& w, int64_t B_logical, float w_joint, float w_pose,
                        bool have_pose, float w_2d, float w_shape, float* loss_out, float* loss_accum, cudaStream_t st) {
-  const int nj = (int)(w.BP / SK_THREADS);
+  const int nj = (int)(w.BP / loss_seed_ppb(w.BP));
   const int np = have_pose ? w.n_pose_part : 0;
   loss_finish_kernel<<<1, 32, 0, st>>>(w.loss_part, nj, 1.f / (51.f * (float)B_logical),
                                        w.loss_part + LOSS_PART_POSE, np, 1.f / (25.f * (float)B_logical),
                                        w.loss_part + LOSS_PART_2D, 1.f / (34.f * (float)B_logical),
-                                       w.shape_part, 1.f / (float)B_logical,
+                                       w.shape_part, (int)(w.BP / 128), 1.f / (float)B_logical,
                                        w_joint, w_pose, w_2d, w_shape, loss_out, loss_accum);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
