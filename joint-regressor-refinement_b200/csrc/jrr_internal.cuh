@@ -77,6 +77,7 @@ struct ChainTab {
   int depth[NJ];
   int child[NJ][MAXCH];  // -1 when absent
   int max_depth;
+  int maxch[NJ];         // by depth d: the largest number of depth-d children any joint has (gather rounds)
 };
 
 // per packed vertex: skinning run record (ELL-4 with register-cached joint slots)

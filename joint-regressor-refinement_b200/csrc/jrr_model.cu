@@ -476,6 +476,12 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
       ct.child[p][c] = j;
     }
   }
+  for (int dd = 0; dd < NJ; dd++) ct.maxch[dd] = 0;
+  for (int j = 0; j < NJ; j++) {
+    int n = 0;
+    for (int c = 0; c < MAXCH; c++) n += ct.child[j][c] >= 0;
+    if (ct.depth[j] + 1 < NJ) ct.maxch[ct.depth[j] + 1] = std::max(ct.maxch[ct.depth[j] + 1], n);
+  }
 
   // ---- host copies the (re)packing needs: joint-set key and <= 4 (joint, weight) pairs per vertex
   m->h_key.assign(V, 0);

@@ -259,7 +259,7 @@ pose_fwd_kernel(const __grid_constant__ ChainTab tab, const float* __restrict__ 
 //   dJp   [BP][72]            d loss / d posed joints (module path only)
 //   dx6c  [BP][144]           critic gradient w.r.t. rot6d (refine path only)
 template <int KIND, bool ADAM>
-__global__ void __launch_bounds__(POSES_PER_CTA * 32)
+__global__ void __launch_bounds__(POSES_PER_CTA * 32, 4)   // <= 64 registers: all 4096 warps of a 4096-pose step in one wave
 pose_bwd_kernel(const __grid_constant__ ChainTab tab, const float* __restrict__ J0,
                 const float* __restrict__ JS, const float* betas /* may alias betas_rw */,
                 const float* pose /* may alias x6_rw */, int64_t B, int64_t BP, const float* __restrict__ dAT,
@@ -298,6 +298,9 @@ pose_bwd_kernel(const __grid_constant__ ChainTab tab, const float* __restrict__ 
   // reverse walk, deepest level first.  A joint at depth d sends its parent
   //   mR = dGR R^T + dGt rel^T (9), mt = dGt (3), mJ = -GRp^T dGt (3)
   const int dep = tab.depth[j];
+  int chl[MAXCH];      // this lane's children, read once (a lane-indexed constant load serialises per address)
+#pragma unroll
+  for (int ci = 0; ci < MAXCH; ci++) chl[ci] = tab.child[j][ci];
   for (int d = tab.max_depth; d >= 1; d--) {
     float msg[15];
     for (int r = 0; r < 3; r++)
@@ -310,16 +313,21 @@ pose_bwd_kernel(const __grid_constant__ ChainTab tab, const float* __restrict__ 
     for (int r = 0; r < 3; r++) { msg[9 + r] = dGt[r]; msg[12 + r] = -gpt[r]; }
     if (act && dep == d)
       for (int c = 0; c < 3; c++) dJr[c] += gpt[c];   // rel_j = Jr_j - Jr_parent
+    const int rounds = tab.maxch[d];   // children of one joint sit in its first slots
+#pragma unroll
     for (int ci = 0; ci < MAXCH; ci++) {
-      int ch = tab.child[j][ci];
-      int src = ch < 0 ? 0 : ch;
-      bool take = act && ch >= 0 && tab.depth[src] == d;
-      for (int i = 0; i < 15; i++) {
-        float v = __shfl_sync(FULL, msg[i], src);
-        if (take) {
-          if (i < 9) dGR[i] += v;
-          else if (i < 12) dGt[i - 9] += v;
-          else dJr[i - 12] += v;
+      if (ci < rounds) {               // uniform
+        const int ch = chl[ci];
+        const int src = ch < 0 ? 0 : ch;
+        const bool take = act && ch >= 0 && dep + 1 == d;   // a child sits one level below its parent
+#pragma unroll
+        for (int i = 0; i < 15; i++) {
+          float v = __shfl_sync(FULL, msg[i], src);
+          if (take) {
+            if (i < 9) dGR[i] += v;
+            else if (i < 12) dGt[i - 9] += v;
+            else dJr[i - 12] += v;
+          }
         }
       }
     }

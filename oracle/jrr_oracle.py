@@ -335,7 +335,7 @@ def camera_fit(smpl, Jraw, x6, betas, gt_j2d, cam, iters=1000, lr=1e-2, logical_
 
 
 def refine_2d(smpl, Jraw, critic_sd, x6, betas, cam, gt_mm, gt_j2d, iters=100, lr=1e-2, w_joint=10000.0,
-              w_pose=10.0, w_2d=0.01, logical_batch=None):
+              w_pose=10.0, w_2d=0.01, logical_batch=None, shape_sd=None, w_shape=10.0):
     """optimize.py:201-202,220-265 with the 3-D joint, pose-critic and 2-D reprojection terms
     (everything except the silhouette render): Adam([pose, orient, betas, cam])."""
     x6 = x6.detach().clone().requires_grad_(True)
@@ -346,7 +346,8 @@ def refine_2d(smpl, Jraw, critic_sd, x6, betas, cam, gt_mm, gt_j2d, iters=100, l
     LB = B if logical_batch is None else logical_batch
     hist = []
     for _ in range(iters):
-        total, jl, pl, pred = refine_loss(smpl, Jraw, critic_sd, x6, betas, gt_mm, w_joint, w_pose, logical_batch)
+        total, jl, pl, pred = refine_loss(smpl, Jraw, critic_sd, x6, betas, gt_mm, w_joint, w_pose, logical_batch,
+                                          shape_sd=shape_sd, w_shape=w_shape)
         l2 = ((gt_j2d - project_2d(pred, cam)) ** 2).sum() / (LB * 17 * 2)
         total = total + w_2d * l2
         opt.zero_grad()

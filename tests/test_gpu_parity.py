@@ -697,3 +697,52 @@ def test_critic_trainer_three_steps_match_oracle_adam(smpl_tc, jrr, oracle, crit
     finally:
         nat.load_shape_critic(None)
         nat.load_critic(critic_sd)
+
+
+# ------------------------------------------------------------------ the whole per-batch loop of optimize.py:150-312
+def test_refinement_loop_two_batches_match_oracle_composition(smpl_tc, jrr, oracle, osmpl32, critic_sd, J_shipped):
+    """camera fit -> refinement with all in-scope terms -> critic + shape-critic training step -> regressor
+    refit, twice (the critics' and the regressor's Adam state persists across batches), against the same
+    sequence composed from the oracle's pieces."""
+    n, cam_it, ref_it = 48, 40, 4
+    ssd = oracle.make_shape_critic_state_dict(5)
+    loop = jrr.RefinementLoop(smpl_tc, J_shipped, critic_sd, ssd, refine_iters=ref_it, cam_iters=cam_it)
+    A = oracle.CriticAdam(critic_sd, oracle.critic_train_loss, lr=1e-3)
+    S = oracle.CriticAdam(ssd, oracle.shape_critic_train_loss, lr=1e-3)
+    RA = oracle.RegressorAdam(J_shipped, lr=1e-2)
+    J_o = J_shipped.clone()
+    try:
+        for bi in range(2):
+            fr, gt2d, cam0 = _cam_problem(jrr, oracle, osmpl32, J_shipped, n, 40 + bi)
+            gt_raw = fr["gt_mm"] + torch.tensor([30.0, -20.0, 10.0])       # not pelvis-centred on input (optimize.py:162)
+            out = loop.run_batch({"orient": fr["x6"][:, :1], "pose": fr["x6"][:, 1:], "betas": fr["betas"],
+                                  "gt_j3d": gt_raw, "gt_j2d": gt2d, "cam": cam0})
+            torch.cuda.synchronize()
+            # ---- oracle composition
+            gt = oracle.move_pelvis(gt_raw)
+            cam_o, _ = oracle.camera_fit(osmpl32, J_o, fr["x6"], fr["betas"], gt2d, cam0, iters=cam_it)
+            x6o, bo, co, hist = oracle.refine_2d(osmpl32, J_o, A.state_dict(), fr["x6"], fr["betas"], cam_o, gt, gt2d,
+                                                 iters=ref_it, shape_sd=S.state_dict(), w_shape=10.0)
+            lc = A.step(x6o, fr["x6"])
+            ls = S.step(bo, fr["betas"])
+            g, lr_ = oracle.regressor_grad(osmpl32, J_o, x6o, bo, gt)
+            J_o = RA.step(g)
+            # ---- compare
+            assert (out["x6"].cpu() - x6o).abs().max().item() < 5e-4, bi
+            assert (out["betas"].cpu() - bo).abs().max().item() < 5e-4, bi
+            assert (out["cam"].cpu() - co).abs().max().item() < 5e-3, bi
+            assert abs(out["refine_loss"][0].item() - hist[-1][0]) / hist[-1][0] < 1e-3, bi
+            assert abs(out["critic_loss"].item() - lc) / lc < 1e-4, (bi, out["critic_loss"].item(), lc)
+            assert abs(out["shape_critic_loss"].item() - ls) / ls < 1e-4, (bi, out["shape_critic_loss"].item(), ls)
+            assert abs(out["refit_loss"].item() - lr_) / lr_ < 1e-3, (bi, out["refit_loss"].item(), lr_)
+            dJ = (loop.refit.J_regressor.cpu() - J_o).abs().max().item()
+            print(f"batch {bi}: critic loss {out['critic_loss'].item():.6f} vs {lc:.6f}; refit loss {out['refit_loss'].item():.3e} "
+                  f"vs {lr_:.3e}; max |dJ| {dJ:.2e}")
+            assert dJ < 1e-4, bi      # north star: regressor weights within 1e-4
+        m0, p0 = loop.evaluate(fr["x6"], fr["betas"], gt_raw)
+        m1, p1 = loop.evaluate(out["x6"], out["betas"], gt_raw)
+        assert m1 < m0
+    finally:
+        smpl_tc.native().load_shape_critic(None)
+        smpl_tc.native().load_critic(critic_sd)
+        smpl_tc.native().set_regressor(J_shipped.to(DEV))
