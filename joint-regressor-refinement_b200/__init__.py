@@ -10,3 +10,5 @@ from .refine import CriticTrainer, PoseRefiner, RegressorRefit, load_j_regressor
 from .smpl import SMPL, SMPLFunction, SMPLOutput  # noqa: F401
 from .utils import evaluate, find_j_reg_mask, find_joints, move_pelvis, rot6d_to_rotmat, set_seed  # noqa: F401
 from .optimize import RefinementLoop  # noqa: F401
+from .data import data_set, write_precomputed  # noqa: F401
+from . import data  # noqa: F401

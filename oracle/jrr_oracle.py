@@ -436,6 +436,35 @@ def make_gt(smpl, Jraw, true_rotmat, true_betas, gt_noise_mm):
         return 1000 * move_pelvis(pred) + gt_noise_mm
 
 
+def load_reference_data_module(root="/root/reference"):
+    """Import the reference's scripts/data.py by path for pinning its crop arithmetic (find_crop,
+    crop_intrinsics, resize_intrinsics).  Its module-level imports of h5py / imageio (image decoding,
+    absent offline and unused by those functions) are satisfied with empty stub modules."""
+    import importlib
+    import os
+    import sys
+    import types
+    if not os.path.isdir(os.path.join(root, "scripts")):
+        return None
+    for m in ("h5py", "imageio"):
+        if m not in sys.modules:
+            try:
+                importlib.import_module(m)
+            except ImportError:
+                sys.modules[m] = types.ModuleType(m)
+    argv = sys.argv
+    sys.argv = ["oracle", "--device", "cpu"]
+    sys.path.insert(0, root)
+    try:
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            return importlib.import_module("scripts.data")
+    finally:
+        sys.argv = argv
+        sys.path.remove(root)
+
+
 def load_reference_modules(root="/root/reference"):
     """Import the reference's own utils / discriminator by path (CPU device) for
     pinning.  Returns (utils, discriminator, eval_utils) or None when the tree is absent."""

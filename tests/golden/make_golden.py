@@ -83,6 +83,24 @@ def main():
              w1_block=sdD["linear_operations.0.weight"][:4, :8].numpy(), b2=sdD["linear_operations.2.bias"].numpy(),
              w3=sdD["linear_operations.4.weight"].numpy(),
              **{"shape__" + k.replace(".", "__"): v.detach().numpy() for k, v in S.state_dict().items()})
+    # crop arithmetic of the data loader (scripts/data.py:123-138,216-270) from the reference's own find_crop
+    rd = O.load_reference_data_module(REF)
+    gb = torch.Generator().manual_seed(77)
+    lo = 100 + 300 * torch.rand(5, 2, generator=gb)
+    hi = lo + 150 + 400 * torch.rand(5, 2, generator=gb)
+    bboxes = torch.stack([lo[:, 0], lo[:, 1], hi[:, 0], hi[:, 1]], dim=1)          # [min_y, min_x, max_y, max_x]
+    intr = torch.zeros(5, 3, 3)
+    intr[:, 0, 0] = 1145 + torch.rand(5, generator=gb); intr[:, 1, 1] = 1144 + torch.rand(5, generator=gb)
+    intr[:, 0, 2] = 500 + 20 * torch.rand(5, generator=gb); intr[:, 1, 2] = 510 + 20 * torch.rand(5, generator=gb)
+    intr[:, 2, 2] = 1
+    _, mnx, mny, sc, intr_out = rd.find_crop(torch.zeros(5, 3, 64, 64), bboxes, intr)
+    j2d = 1000 * torch.rand(5, 17, 2, generator=gb)
+    rep = j2d.clone()                                   # data.py:134-138 on the reference's crop parameters
+    rep[..., 0] -= mnx[:, None]; rep[..., 1] -= mny[:, None]
+    rep /= sc[:, None, None]; rep /= 1000 / 224
+    np.savez(os.path.join(HERE, "ref_data_crop_golden.npz"), bboxes=bboxes.numpy(), intrinsics=intr.numpy(),
+             min_x=mnx.numpy(), min_y=mny.numpy(), scale=sc.numpy(), intrinsics_out=intr_out.numpy(),
+             gt_j2d=j2d.numpy(), gt_j2d_repositioned=rep.numpy())
     print("wrote fixtures; artefact sha256", sha)
 
 

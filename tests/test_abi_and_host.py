@@ -125,3 +125,35 @@ def test_two_rank_refit_allreduce_gloo(tmp_path):
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
+def test_precomputed_split_round_trip(tmp_path, jrr):
+    """The reference's on-disk split layout (scripts/data.py:49-69): write, load, index, batch."""
+    import pytest
+    n = 37
+    g = torch.Generator().manual_seed(0)
+    lo = 100 + 300 * torch.rand(n, 2, generator=g)
+    hi = lo + 200 + 300 * torch.rand(n, 2, generator=g)
+    frames = {
+        "bboxes": torch.stack([lo[:, 0], lo[:, 1], hi[:, 0], hi[:, 1]], dim=1), "betas": torch.randn(n, 10, generator=g),
+        "estimated_translation": torch.randn(n, 3, generator=g), "gt_j2d": 1000 * torch.rand(n, 17, 2, generator=g),
+        "gt_j3d": 500 * torch.randn(n, 17, 3, generator=g), "intrinsics": torch.eye(3).repeat(n, 1, 1),
+        "orient": torch.randn(n, 1, 6, generator=g), "pose": torch.randn(n, 23, 6, generator=g),
+    }
+    root = str(tmp_path)
+    jrr.write_precomputed(root + "/precomputed_val", frames)
+    ds = jrr.data_set("validation", root=root)
+    assert len(ds) == n and len(ds.images) == n
+    item = ds[5]
+    assert set(item) == {"bboxes", "betas", "cam", "gt_j2d", "gt_j3d", "intrinsics", "orient", "pose", "inc_gt"}
+    assert torch.equal(item["pose"], frames["pose"][5]) and torch.equal(item["cam"], frames["estimated_translation"][5])
+    assert item["gt_j2d"].shape == (17, 2) and item["intrinsics"].shape == (3, 3) and bool(item["inc_gt"])
+    seen = 0
+    for b in ds.batches(16):
+        assert b["pose"].shape[1:] == (23, 6) and b["orient"].shape[1:] == (1, 6)
+        seen += b["pose"].shape[0]
+    assert seen == n
+    assert sum(b["pose"].shape[0] for b in ds.batches(16, shuffle=True, seed=1, drop_last=True)) == 32
+    assert torch.equal(ds.batch(slice(3, 9))["gt_j3d"], frames["gt_j3d"][3:9])
+    with pytest.raises(FileNotFoundError):
+        jrr.data_set("train", root=root)

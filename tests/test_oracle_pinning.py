@@ -150,3 +150,31 @@ def test_product_mirrors_match_reference_utils(ref, jrr):
     assert abs(m1 - m2) < 1e-3 and abs(p1 - p2) < 1e-3
     J = torch.randn(17, 6890)
     assert torch.equal(u.find_j_reg_mask(J), jrr.find_j_reg_mask(J))
+
+
+def test_golden_data_crop_arithmetic(jrr):
+    """scripts/data.py find_crop / crop_intrinsics / resize_intrinsics and the 2-D joint repositioning of
+    data_set.__getitem__ (fixture produced by the reference's own find_crop)."""
+    z = np.load(os.path.join(GOLDEN, "ref_data_crop_golden.npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    mnx, mny, sc, _, _ = jrr.data.crop_window(t("bboxes"))
+    assert np.abs(mnx.numpy() - z["min_x"]).max() < 1e-3 and np.abs(mny.numpy() - z["min_y"]).max() < 1e-3
+    assert np.abs(sc.numpy() - z["scale"]).max() < 1e-6
+    assert np.abs(jrr.data.cropped_intrinsics(t("intrinsics"), t("bboxes")).numpy() - z["intrinsics_out"]).max() < 1e-3
+    assert np.abs(jrr.data.reposition_j2d(t("gt_j2d"), t("bboxes")).numpy() - z["gt_j2d_repositioned"]).max() < 1e-3
+
+
+@needs_ref
+def test_live_reference_find_crop(oracle, jrr):
+    rd = oracle.load_reference_data_module()
+    g = torch.Generator().manual_seed(3)
+    lo = 50 + 400 * torch.rand(9, 2, generator=g)
+    hi = lo + 100 + 300 * torch.rand(9, 2, generator=g)
+    bb = torch.stack([lo[:, 0], lo[:, 1], hi[:, 0], hi[:, 1]], dim=1)
+    intr = torch.eye(3).repeat(9, 1, 1)
+    intr[:, 0, 0] = 1100; intr[:, 1, 1] = 1090; intr[:, 0, 2] = 505; intr[:, 1, 2] = 498
+    for size in (224, 256):
+        _, mnx, mny, sc, io = rd.find_crop(torch.zeros(9, 3, 32, 32), bb, intr, img_size=size)
+        a, b, c, _, _ = jrr.data.crop_window(bb)
+        assert torch.allclose(a, mnx, atol=1e-3) and torch.allclose(b, mny, atol=1e-3) and torch.allclose(c, sc)
+        assert torch.allclose(jrr.data.cropped_intrinsics(intr, bb, img_size=size), io, atol=1e-3)
