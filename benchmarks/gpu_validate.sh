@@ -18,3 +18,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:'fused_bwd|fused_fwd|gemm_tc_kernel<128, 1' -s 30 -c 6 -o gpurun_out/r1_prof python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | head -30
 timeout 1500 python benchmarks/sweep.py > gpurun_out/r1_sweep.jsonl 2> gpurun_out/r1_sweep.err; tail -2 gpurun_out/r1_sweep.err
+compute-sanitizer --tool memcheck --print-limit 20 python benchmarks/sanitize.py 2>&1 | grep -E "COMPUTE-SANITIZER|ERROR SUMMARY|Invalid|sanitizer workload|at 0x|Error" | head -40 > gpurun_out/r1_memcheck.txt; tail -2 gpurun_out/r1_memcheck.txt
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29517 benchmarks/multi_gpu_check.py > /dev/null 2>&1 || echo "multi_gpu_check (1 rank) FAILED"
