@@ -459,6 +459,14 @@ extern "C" int jrr_debug_gemm(JrrModel* m, int impl, int64_t M, int64_t N, int64
   if (!m || !A || !B || !C || !scratch) return fail(JRR_ERR_INVALID, "null argument");
   reset_launch_count();
   cudaStream_t st = (cudaStream_t)stream;
+  if (impl == 2) {      // tcgen05 kernel with the in-shared-memory tf32 split (plain fp32 operands)
+    GemmDesc g{};
+    g.smem_split = true;
+    g.A_hi = A; g.lda = K; g.B_hi = B; g.ldb = K;
+    g.M = M; g.N = N; g.K = K; g.ksplit = 1; g.epi = EPI_STORE_SPLITK;
+    g.out0 = C; g.ldo = N;
+    return launch_gemm_tc(m, g, st);
+  }
   float* Ah = scratch;
   float* Al = Ah + M * K;
   float* Bh = Al + M * K;

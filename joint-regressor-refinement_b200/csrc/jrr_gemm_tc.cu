@@ -21,7 +21,8 @@ namespace jrr {
 
 constexpr int BM = 128;
 constexpr int BK = 32;  // fp32 per stage row = 128 bytes = one swizzle atom
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 192;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int TC_THREADS_SS = 320;       // + warps 6-9: in-smem tf32 splitters (SS variant, plain fp32 operands)
 
 struct TcParams {
   int64_t M, N, K;     // K = per-split extent
@@ -46,8 +47,13 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// SS = false: operands arrive pre-split (four TMA tiles per stage).  SS = true: operands are plain
+// fp32 -- TMA brings ONE tile per operand into the stage's "hi" slot, four splitter warps round it to
+// tf32 in place and write the remainder into the "lo" slot (same swizzled positions, so the UMMA
+// descriptors do not change), and every epilogue writes a single fp32 array.  That halves the
+// L2 -> SM operand traffic (which bounds the pre-split 128x128 kernel) and the activations' HBM traffic.
+template <int BN, int EPI, bool SS>
+__global__ void __launch_bounds__(SS ? TC_THREADS_SS : TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                const TcParams p) {
@@ -60,7 +66,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+  uint64_t* ready_bar = bars + 2 * STAGES + 4;   // [STAGES] splitters -> MMA (SS)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (int)(p.K / BK);
@@ -72,7 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAl) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
-    for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 4); }
     for (int s = 0; s < 2; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -98,12 +105,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          mbar_expect_tx(&full_bar[stage], SS ? Cfg::A_BYTES + Cfg::B_BYTES : Cfg::STAGE_BYTES);
           const int kc = (int)(split * p.K) + kb * BK;
           tma_load_2d(&mapAh, &full_bar[stage], sa, kc, mb * BM);
-          tma_load_2d(&mapAl, &full_bar[stage], sa + Cfg::A_BYTES, kc, mb * BM);
+          if (!SS) tma_load_2d(&mapAl, &full_bar[stage], sa + Cfg::A_BYTES, kc, mb * BM);
           tma_load_2d(&mapBh, &full_bar[stage], sa + 2 * Cfg::A_BYTES, kc, nb * BN);
-          tma_load_2d(&mapBl, &full_bar[stage], sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, kc, nb * BN);
+          if (!SS) tma_load_2d(&mapBl, &full_bar[stage], sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, kc, nb * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -124,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
       for (int kb = 0; kb < num_kb; kb++) {
         if (lane == 0) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(SS ? &ready_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t dAh = make_sdesc(sa);
@@ -146,7 +153,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else {
+  } else if (SS && warp >= 6) {
+    // ===================== in-smem tf32 splitters (warps 6..9) =====================
+    const int tid = threadIdx.x - 6 * 32;      // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < num_kb; kb++) {
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+        for (int op = 0; op < 2; op++) {
+          float4* hi4 = reinterpret_cast<float4*>(sa + (op == 0 ? 0 : 2 * Cfg::A_BYTES));
+          float4* lo4 = reinterpret_cast<float4*>(sa + (op == 0 ? Cfg::A_BYTES : 2 * Cfg::A_BYTES + Cfg::B_BYTES));
+          constexpr int N4A = Cfg::A_BYTES / 16, N4B = Cfg::B_BYTES / 16;
+          const int n4 = op == 0 ? N4A : N4B;
+#pragma unroll 4
+          for (int i = tid; i < n4; i += 128) {
+            const float4 x = hi4[i];
+            float4 h, l;
+            split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y);
+            split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+            hi4[i] = h;
+            lo4[i] = l;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 2 && warp < 6) {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
@@ -178,16 +216,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
               const float x = fmaxf(v[i] + __ldg(p.bias + n0 + i), 0.f);
               const float w = __ldg(p.vec + n0 + i);
               zsum = fmaf(x, w, zsum);
-              const float wh = tf32_hi_g(w);
-              hi[i] = x > 0.f ? wh : 0.f;
-              lo[i] = x > 0.f ? tf32_hi_g(w - wh) : 0.f;
+              if (SS) {
+                hi[i] = x > 0.f ? w : 0.f;
+              } else {
+                const float wh = tf32_hi_g(w);
+                hi[i] = x > 0.f ? wh : 0.f;
+                lo[i] = x > 0.f ? tf32_hi_g(w - wh) : 0.f;
+              }
             }
             float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
-            float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-              oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-              ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            for (int i = 0; i < 8; i++) oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            if (!SS) {
+              float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
+#pragma unroll
+              for (int i = 0; i < 8; i++) ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
             }
           }
         } else if (EPI == EPI_STORE_T) {
@@ -205,15 +248,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
               float x = v[i];
               if (EPI == EPI_BIAS_RELU_SPLIT) x = fmaxf(x + __ldg(p.bias + n0 + i), 0.f);
               else x = (p.mask[m * p.ldmask + n0 + i] > 0.f) ? x * rs : 0.f;
-              hi[i] = tf32_hi_g(x);
-              lo[i] = tf32_hi_g(x - hi[i]);
+              if (SS) {
+                hi[i] = x;
+              } else {
+                hi[i] = tf32_hi_g(x);
+                lo[i] = tf32_hi_g(x - hi[i]);
+              }
             }
             float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
-            float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-              oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-              ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            for (int i = 0; i < 8; i++) oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            if (!SS) {
+              float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
+#pragma unroll
+              for (int i = 0; i < 8; i++) ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
             }
           }
         } else {
@@ -279,26 +327,30 @@ int device_num_sms(int device) {
   return cached[device];
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool SS = false>
 static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   CUtensorMap mAh, mAl, mBh, mBl;
   const int64_t Ktot = g.K * g.ksplit;
   if (int rc = make_tensor_map_2d(&mAh, g.A_hi, g.M, Ktot, g.lda, BM)) return rc;
-  if (int rc = make_tensor_map_2d(&mAl, g.A_lo, g.M, Ktot, g.lda, BM)) return rc;
   if (int rc = make_tensor_map_2d(&mBh, g.B_hi, g.N, Ktot, g.ldb, BN)) return rc;
-  if (int rc = make_tensor_map_2d(&mBl, g.B_lo, g.N, Ktot, g.ldb, BN)) return rc;
+  if (SS) {
+    mAl = mAh; mBl = mBh;      // unused by the kernel
+  } else {
+    if (int rc = make_tensor_map_2d(&mAl, g.A_lo, g.M, Ktot, g.lda, BM)) return rc;
+    if (int rc = make_tensor_map_2d(&mBl, g.B_lo, g.N, Ktot, g.ldb, BN)) return rc;
+  }
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.ksplit = g.ksplit;
   p.m_tiles = (int)(g.M / BM);
   p.n_tiles = (int)((g.N + BN - 1) / BN);
   p.out0 = g.out0; p.out1 = g.out1; p.ldo = g.ldo; p.bias = g.bias; p.mask = g.mask; p.ldmask = g.ldmask;
   p.rowscale = g.rowscale; p.vec = g.vec; p.out2 = g.out2;
-  auto kern = gemm_tc_kernel<BN, EPI>;
+  auto kern = gemm_tc_kernel<BN, EPI, SS>;
   JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = std::min(tiles, device_num_sms(m->device));
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
+  kern<<<grid, SS ? TC_THREADS_SS : TC_THREADS, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
@@ -307,6 +359,16 @@ int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   if (g.M % BM != 0 || g.K % BK != 0) return fail(JRR_ERR_INVALID, "tc gemm: M%128 or K%32");
   if (((uintptr_t)g.A_hi | (uintptr_t)g.A_lo | (uintptr_t)g.B_hi | (uintptr_t)g.B_lo) & 15)
     return fail(JRR_ERR_INVALID, "tc gemm: operands must be 16-byte aligned");
+  if (g.smem_split) {      // plain fp32 operands (A_hi / B_hi), tf32 split inside the kernel
+    if (g.N % 128 != 0) return fail(JRR_ERR_INVALID, "tc gemm (smem split): N % 128");
+    switch (g.epi) {
+      case EPI_BIAS_RELU_SPLIT: return launch_tc<128, EPI_BIAS_RELU_SPLIT, true>(m, g, st);
+      case EPI_MASK_SPLIT: return launch_tc<128, EPI_MASK_SPLIT, true>(m, g, st);
+      case EPI_BIAS_RELU_HEAD: return launch_tc<128, EPI_BIAS_RELU_HEAD, true>(m, g, st);
+      case EPI_STORE_SPLITK: return launch_tc<128, EPI_STORE_SPLITK, true>(m, g, st);
+      default: return fail(JRR_ERR_INVALID, "tc gemm (smem split): unsupported epilogue");
+    }
+  }
   switch (g.epi) {
     case EPI_STORE_T:
       if (g.N % 128 == 0) return launch_tc<128, EPI_STORE_T>(m, g, st);
