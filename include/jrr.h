@@ -244,7 +244,7 @@ const char* jrr_step_kernel_name(int i);
 /* Diagnostic: the 3xTF32 GEMM on its own, C[M,N] (row-major) = A[M,K] . B[N,K]^T with fp32
  * inputs that are split into tf32 hi/lo pairs inside the call (scratch = 2*(M+N)*K floats,
  * device).  impl 0 = tcgen05 kernel, 1 = SIMT validation kernel, 2 = tcgen05 kernel that takes the
- * fp32 operands as they are and splits them in shared memory (N%128 == 0).  M%128 == 0, K%32 == 0,
+ * fp32 A as it is and stages its tf32 hi/lo pair through tensor memory (N%128 == 0).  M%128 == 0, K%32 == 0,
  * N%128 == 0 or N == 224.  Used by the kernel-level parity tests and the GEMM roofline
  * micro-benchmark; not on the reference's interface. */
 int jrr_debug_gemm(JrrModel* model, int impl, int64_t M, int64_t N, int64_t K, const float* A,

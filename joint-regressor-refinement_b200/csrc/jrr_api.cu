@@ -459,10 +459,14 @@ extern "C" int jrr_debug_gemm(JrrModel* m, int impl, int64_t M, int64_t N, int64
   if (!m || !A || !B || !C || !scratch) return fail(JRR_ERR_INVALID, "null argument");
   reset_launch_count();
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 2) {      // tcgen05 kernel with the in-shared-memory tf32 split (plain fp32 operands)
+  if (impl == 2) {      // tcgen05 kernel with plain fp32 A staged through tensor memory (B pre-split here)
+    float* Bh2 = scratch;
+    float* Bl2 = Bh2 + N * K;
+    debug_split_kernel<<<(unsigned)((N * K + 255) / 256), 256, 0, st>>>(B, N * K, Bh2, Bl2);
+    JRR_LAUNCH_CHECK();
     GemmDesc g{};
     g.smem_split = true;
-    g.A_hi = A; g.lda = K; g.B_hi = B; g.ldb = K;
+    g.A_hi = A; g.lda = K; g.B_hi = Bh2; g.B_lo = Bl2; g.ldb = K;
     g.M = M; g.N = N; g.K = K; g.ksplit = 1; g.epi = EPI_STORE_SPLITK;
     g.out0 = C; g.ldo = N;
     return launch_gemm_tc(m, g, st);

@@ -356,17 +356,17 @@ int launch_critic_post(const JrrModel* m, const Workspace& w, const float* x6, c
 // The four wide GEMMs around the small kernels.  head_fused: the second layer's epilogue also does
 // the global head (logit partials + its masked gradient row), see EPI_BIAS_RELU_HEAD.
 int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, bool head_fused) {
-  const bool ss = head_fused && m->critic_ss;    // plain fp32 operands, tf32 split inside the GEMM
+  const bool ss = head_fused && m->critic_ss;    // plain fp32 activations, staged through tensor memory by the GEMM
   GemmDesc g{};
   g.smem_split = ss;
   g.A_hi = w.h_hi; g.A_lo = w.h_lo; g.lda = C_H;
-  g.B_hi = ss ? m->W1f : m->W1_hi; g.B_lo = m->W1_lo; g.ldb = C_H;
+  g.B_hi = m->W1_hi; g.B_lo = m->W1_lo; g.ldb = C_H;
   g.M = w.BP; g.N = C_Z; g.K = C_H; g.ksplit = 1; g.epi = EPI_BIAS_RELU_SPLIT;
   g.out0 = w.z1_hi; g.out1 = w.z1_lo; g.ldo = C_Z; g.bias = m->critic_small + CS_B1;
   int rc = launch_gemm(m, g, st);
   if (rc) return rc;
   g.A_hi = w.z1_hi; g.A_lo = w.z1_lo; g.lda = C_Z;
-  g.B_hi = ss ? m->W2f : m->W2_hi; g.B_lo = m->W2_lo; g.ldb = C_Z;
+  g.B_hi = m->W2_hi; g.B_lo = m->W2_lo; g.ldb = C_Z;
   g.K = C_Z; g.out0 = w.z2_hi; g.out1 = w.z2_lo; g.bias = m->critic_small + CS_B2;
   if (head_fused) {
     g.epi = EPI_BIAS_RELU_HEAD;
@@ -383,14 +383,14 @@ int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st
   // dz1 = (dz2 . W2) * [z1 > 0]   (head_fused: dz2 rows still lack their scalar dL/dlogit = rowscale)
   g.rowscale = rowscale;
   g.A_hi = w.dz2_hi; g.A_lo = w.dz2_lo; g.lda = C_Z;
-  g.B_hi = ss ? m->W2tf : m->W2t_hi; g.B_lo = m->W2t_lo; g.ldb = C_Z;
+  g.B_hi = m->W2t_hi; g.B_lo = m->W2t_lo; g.ldb = C_Z;
   g.M = w.BP; g.N = C_Z; g.K = C_Z; g.ksplit = 1; g.epi = EPI_MASK_SPLIT;
   g.out0 = w.dz1_hi; g.out1 = w.dz1_lo; g.ldo = C_Z; g.mask = w.z1_hi; g.ldmask = C_Z;
   int rc = launch_gemm(m, g, st);
   if (rc) return rc;
   // dh = dz1 . W1
   g.A_hi = w.dz1_hi; g.A_lo = w.dz1_lo; g.lda = C_Z;
-  g.B_hi = ss ? m->W1tf : m->W1t_hi; g.B_lo = m->W1t_lo; g.ldb = C_Z;
+  g.B_hi = m->W1t_hi; g.B_lo = m->W1t_lo; g.ldb = C_Z;
   g.N = C_H; g.K = C_Z; g.epi = EPI_STORE_SPLITK; g.out0 = w.dh; g.out1 = nullptr; g.ldo = C_H;
   g.mask = nullptr; g.rowscale = nullptr;
   return launch_gemm(m, g, st);

@@ -22,7 +22,7 @@ namespace jrr {
 constexpr int BM = 128;
 constexpr int BK = 32;  // fp32 per stage row = 128 bytes = one swizzle atom
 constexpr int TC_THREADS = 192;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int TC_THREADS_SS = 320;       // + warps 6-9: in-smem tf32 splitters (SS variant, plain fp32 operands)
+constexpr int TC_THREADS_SS = 320;       // + warps 6-9: A producers of the SS variant (smem fp32 tile -> registers -> TMEM)
 
 struct TcParams {
   int64_t M, N, K;     // K = per-split extent
@@ -31,6 +31,7 @@ struct TcParams {
   float* out0; float* out1; int64_t ldo;
   const float* bias;
   const float* mask; int64_t ldmask;
+  const float* A; int64_t lda;   // SS: plain fp32 A
   const float* rowscale;   // EPI_MASK_SPLIT: multiply row m by rowscale[m] (or nullptr)
   const float* vec;        // EPI_BIAS_RELU_HEAD: w3[N]
   float* out2;             // EPI_BIAS_RELU_HEAD: zg_part[n_tile][M]
@@ -44,24 +45,33 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int A_TMEM_COL = 2 * ACC_STRIDE;   // SS: A staging ring, 64 columns (hi 32 | lo 32) per stage
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGES_SS = 4;                        // SS: [A raw][B_hi][B_lo] = 48 KB at BN = 128
+  static constexpr int STAGE_BYTES_SS = A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES_SS = STAGES_SS * STAGE_BYTES_SS + 1024 + 256;
 };
 
-// SS = false: operands arrive pre-split (four TMA tiles per stage).  SS = true: operands are plain
-// fp32 -- TMA brings ONE tile per operand into the stage's "hi" slot, four splitter warps round it to
-// tf32 in place and write the remainder into the "lo" slot (same swizzled positions, so the UMMA
-// descriptors do not change), and every epilogue writes a single fp32 array.  That halves the
-// L2 -> SM operand traffic (which bounds the pre-split 128x128 kernel) and the activations' HBM traffic.
+// SS = false: both operands arrive pre-split through TMA (four tiles per stage) and are read from
+// shared memory by the tensor core -- at 128x128 tiles the 3xTF32 scheme then reads 24 KB of operands
+// per 8-column K step and is bound by shared-memory bandwidth (~60 % of the tensor peak).
+// SS = true ("A through tensor memory"): A is a plain fp32 activation matrix.  TMA brings ONE raw tile
+// per stage; four producer warps (thread = row = TMEM lane) read their row, make the tf32 hi/lo pair
+// in registers and tcgen05.st it into a TMEM staging ring; the MMAs take A from TMEM and only B (the
+// pre-split weights) from shared memory.  Shared-memory traffic per K block drops from 160 KB to
+// 112 KB, the activations' L2/HBM traffic halves, and every epilogue writes a single fp32 array.
 template <int BN, int EPI, bool SS>
 __global__ void __launch_bounds__(SS ? TC_THREADS_SS : TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                const TcParams p) {
   using Cfg = TcCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGES = SS ? Cfg::STAGES_SS : Cfg::STAGES;
+  constexpr int STAGE_BYTES = SS ? Cfg::STAGE_BYTES_SS : Cfg::STAGE_BYTES;
+  constexpr int B_OFF = SS ? Cfg::A_BYTES : 2 * Cfg::A_BYTES;    // SS: one raw A tile, then B_hi, B_lo
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -85,7 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(Cfg::TMEM_COLS));
+                 "n"(SS ? 512 : Cfg::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -104,13 +114,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         const int mb = r % p.m_tiles, nb = r / p.m_tiles;
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], SS ? Cfg::A_BYTES + Cfg::B_BYTES : Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           const int kc = (int)(split * p.K) + kb * BK;
           tma_load_2d(&mapAh, &full_bar[stage], sa, kc, mb * BM);
           if (!SS) tma_load_2d(&mapAl, &full_bar[stage], sa + Cfg::A_BYTES, kc, mb * BM);
-          tma_load_2d(&mapBh, &full_bar[stage], sa + 2 * Cfg::A_BYTES, kc, nb * BN);
-          if (!SS) tma_load_2d(&mapBl, &full_bar[stage], sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, kc, nb * BN);
+          tma_load_2d(&mapBh, &full_bar[stage], sa + B_OFF, kc, nb * BN);
+          tma_load_2d(&mapBl, &full_bar[stage], sa + B_OFF + Cfg::B_BYTES, kc, nb * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -131,19 +141,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
       for (int kb = 0; kb < num_kb; kb++) {
         if (lane == 0) {
-          mbar_wait(SS ? &ready_bar[stage] : &full_bar[stage], phase);
+          mbar_wait(SS ? &ready_bar[stage] : &full_bar[stage], phase);   // SS: the producers waited for the TMA
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t dAh = make_sdesc(sa);
           const uint64_t dAl = make_sdesc(sa + Cfg::A_BYTES);
-          const uint64_t dBh = make_sdesc(sa + 2 * Cfg::A_BYTES);
-          const uint64_t dBl = make_sdesc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+          const uint64_t dBh = make_sdesc(sa + B_OFF);
+          const uint64_t dBl = make_sdesc(sa + B_OFF + Cfg::B_BYTES);
+          const uint32_t ta = tmem_base + Cfg::A_TMEM_COL + stage * 64;   // SS: hi at +0, lo at +32
 #pragma unroll
           for (int k = 0; k < BK / 8; k++) {
             const uint64_t ko = (uint64_t)(k * 32 >> 4);  // 8 tf32 = 32 bytes along K
-            tc_mma_tf32(d_tmem, dAl + ko, dBh + ko, idesc, (kb | k) != 0);
-            tc_mma_tf32(d_tmem, dAh + ko, dBl + ko, idesc, 1);
-            tc_mma_tf32(d_tmem, dAh + ko, dBh + ko, idesc, 1);
+            if (SS) {
+              tc_mma_tf32_ts(d_tmem, ta + 32 + k * 8, dBh + ko, idesc, (kb | k) != 0);
+              tc_mma_tf32_ts(d_tmem, ta + k * 8, dBl + ko, idesc, 1);
+              tc_mma_tf32_ts(d_tmem, ta + k * 8, dBh + ko, idesc, 1);
+            } else {
+              tc_mma_tf32(d_tmem, dAl + ko, dBh + ko, idesc, (kb | k) != 0);
+              tc_mma_tf32(d_tmem, dAh + ko, dBl + ko, idesc, 1);
+              tc_mma_tf32(d_tmem, dAh + ko, dBh + ko, idesc, 1);
+            }
           }
           tc_commit(&empty_bar[stage]);
           if (kb == num_kb - 1) tc_commit(&tfull_bar[acc]);
@@ -154,31 +171,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (SS && warp >= 6) {
-    // ===================== in-smem tf32 splitters (warps 6..9) =====================
-    const int tid = threadIdx.x - 6 * 32;      // 0..127
+    // ===================== A producers (warps 6..9): global fp32 -> tf32 hi/lo -> TMEM =====================
+    const int q = warp & 3;                      // TMEM lane quarter of this warp
+    const int row = q * 32 + lane;               // A-tile row = TMEM lane
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_TMEM_COL;
+    // The raw fp32 A tile arrives by TMA in the stage's A slot (SWIZZLE_128B: 16-byte chunk c of row r sits
+    // at chunk c ^ (r & 7)); each thread reads its own row, splits it and stores the pair to TMEM.  The
+    // staging slot of a stage is free whenever the stage's smem has been refilled (same MMA commit).
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       for (int kb = 0; kb < num_kb; kb++) {
         mbar_wait(&full_bar[stage], phase);
-        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        const uint8_t* arow = smem + stage * STAGE_BYTES + row * 128;
+        float hi[32], lo[32];
 #pragma unroll
-        for (int op = 0; op < 2; op++) {
-          float4* hi4 = reinterpret_cast<float4*>(sa + (op == 0 ? 0 : 2 * Cfg::A_BYTES));
-          float4* lo4 = reinterpret_cast<float4*>(sa + (op == 0 ? Cfg::A_BYTES : 2 * Cfg::A_BYTES + Cfg::B_BYTES));
-          constexpr int N4A = Cfg::A_BYTES / 16, N4B = Cfg::B_BYTES / 16;
-          const int n4 = op == 0 ? N4A : N4B;
-#pragma unroll 4
-          for (int i = tid; i < n4; i += 128) {
-            const float4 x = hi4[i];
-            float4 h, l;
-            split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y);
-            split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-            hi4[i] = h;
-            lo4[i] = l;
-          }
+        for (int c = 0; c < 8; c++) {
+          const float4 x = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+          split_tf32(x.x, hi[4 * c], lo[4 * c]);
+          split_tf32(x.y, hi[4 * c + 1], lo[4 * c + 1]);
+          split_tf32(x.z, hi[4 * c + 2], lo[4 * c + 2]);
+          split_tf32(x.w, hi[4 * c + 3], lo[4 * c + 3]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_after();
+        tc_st32(trow + stage * 64, hi);
+        tc_st32(trow + stage * 64 + 32, lo);
+        tc_wait_st();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -283,7 +302,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(SS ? 512 : Cfg::TMEM_COLS));
   }
 }
 
@@ -332,13 +351,13 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   CUtensorMap mAh, mAl, mBh, mBl;
   const int64_t Ktot = g.K * g.ksplit;
-  if (int rc = make_tensor_map_2d(&mAh, g.A_hi, g.M, Ktot, g.lda, BM)) return rc;
   if (int rc = make_tensor_map_2d(&mBh, g.B_hi, g.N, Ktot, g.ldb, BN)) return rc;
+  if (int rc = make_tensor_map_2d(&mBl, g.B_lo, g.N, Ktot, g.ldb, BN)) return rc;
+  if (int rc = make_tensor_map_2d(&mAh, g.A_hi, g.M, Ktot, g.lda, BM)) return rc;
   if (SS) {
-    mAl = mAh; mBl = mBh;      // unused by the kernel
+    mAl = mAh;                 // unused by the kernel: one raw fp32 A tile per stage
   } else {
     if (int rc = make_tensor_map_2d(&mAl, g.A_lo, g.M, Ktot, g.lda, BM)) return rc;
-    if (int rc = make_tensor_map_2d(&mBl, g.B_lo, g.N, Ktot, g.ldb, BN)) return rc;
   }
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.ksplit = g.ksplit;
@@ -346,21 +365,23 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   p.n_tiles = (int)((g.N + BN - 1) / BN);
   p.out0 = g.out0; p.out1 = g.out1; p.ldo = g.ldo; p.bias = g.bias; p.mask = g.mask; p.ldmask = g.ldmask;
   p.rowscale = g.rowscale; p.vec = g.vec; p.out2 = g.out2;
+  p.A = g.A_hi; p.lda = g.lda;
   auto kern = gemm_tc_kernel<BN, EPI, SS>;
-  JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  constexpr int smem_bytes = SS ? Cfg::SMEM_BYTES_SS : Cfg::SMEM_BYTES;
+  JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = std::min(tiles, device_num_sms(m->device));
-  kern<<<grid, SS ? TC_THREADS_SS : TC_THREADS, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
+  kern<<<grid, SS ? TC_THREADS_SS : TC_THREADS, smem_bytes, st>>>(mAh, mAl, mBh, mBl, p);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
 
 int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   if (g.M % BM != 0 || g.K % BK != 0) return fail(JRR_ERR_INVALID, "tc gemm: M%128 or K%32");
-  if (((uintptr_t)g.A_hi | (uintptr_t)g.A_lo | (uintptr_t)g.B_hi | (uintptr_t)g.B_lo) & 15)
+  if (((uintptr_t)g.A_hi | (uintptr_t)(g.smem_split ? nullptr : g.A_lo) | (uintptr_t)g.B_hi | (uintptr_t)g.B_lo) & 15)
     return fail(JRR_ERR_INVALID, "tc gemm: operands must be 16-byte aligned");
-  if (g.smem_split) {      // plain fp32 operands (A_hi / B_hi), tf32 split inside the kernel
-    if (g.N % 128 != 0) return fail(JRR_ERR_INVALID, "tc gemm (smem split): N % 128");
+  if (g.smem_split) {      // plain fp32 A (A_hi) through tensor memory, pre-split B
+    if (g.N % 128 != 0 || g.lda % 4 != 0) return fail(JRR_ERR_INVALID, "tc gemm (A through TMEM): N % 128, lda % 4");
     switch (g.epi) {
       case EPI_BIAS_RELU_SPLIT: return launch_tc<128, EPI_BIAS_RELU_SPLIT, true>(m, g, st);
       case EPI_MASK_SPLIT: return launch_tc<128, EPI_MASK_SPLIT, true>(m, g, st);

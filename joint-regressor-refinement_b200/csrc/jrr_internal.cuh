@@ -169,10 +169,8 @@ struct JrrModel {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_critic = true;
-  bool critic_ss = false;                    // JRR_CRITIC_SS=1: critic GEMMs of the refine step take plain fp32 operands and
-                                             // split them in shared memory.  Measured SLOWER (0.28 vs 0.21 ms): the 128x128
-                                             // 3xTF32 tile is bound by shared-memory bandwidth, not by L2 -> SM traffic
-  float *W1f = nullptr, *W2f = nullptr, *W1tf = nullptr, *W2tf = nullptr;   // fp32 critic weights and transposes
+  bool critic_ss = true;                     // critic GEMMs of the refine step: plain fp32 activations staged through tensor
+                                             // memory (JRR_CRITIC_SS=0: pre-split activations through shared memory)
   bool critic_head_fused = true;             // global critic head inside the layer-2 GEMM epilogue (refine step)
   bool fused_fwd = true;   // loss path: skinning + regressor in the blend GEMM's epilogue
   bool fused_bwd = true;   // loss path: skinning backward generates the A operand of the blend-gradient GEMM
@@ -239,8 +237,8 @@ struct GemmDesc {
   const float* mask; int64_t ldmask;       // (EPI_MASK_SPLIT) multiply by (mask>0)
   const float* rowscale;                   // (EPI_MASK_SPLIT) and by rowscale[m] when given
   const float* vec; float* out2;           // (EPI_BIAS_RELU_HEAD) w3[N] in, logit partials [N/128][M] out
-  bool smem_split;                         // operands are plain fp32 in A_hi / B_hi; split to tf32 hi/lo in shared
-                                           // memory by the kernel; *_SPLIT epilogues then write ONE fp32 array (out0)
+  bool smem_split;                         // A is plain fp32 (A_hi): loaded, tf32-split and staged in tensor memory by the
+                                           // kernel (B stays pre-split); *_SPLIT epilogues then write ONE fp32 array (out0)
 };
 int launch_gemm(const JrrModel* m, const GemmDesc& g, cudaStream_t st);
 int launch_gemm_simt(const GemmDesc& g, cudaStream_t st);

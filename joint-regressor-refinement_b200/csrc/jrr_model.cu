@@ -286,14 +286,6 @@ __global__ void split_transpose_kernel(const float* __restrict__ src, int rows, 
   lo[i] = __uint_as_float(q);
 }
 
-__global__ void transpose_plain_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
-  // src [rows][cols] -> dst [cols][rows]
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)rows * cols) return;
-  const int c = (int)(i / rows), r = (int)(i % rows);
-  dst[i] = src[(int64_t)r * cols + c];
-}
-
 // K-range size of the fused backward: the largest of 768/384/192 vertices that still yields >= 9
 // ranges over the active prefix (enough CTAs per 256-pose block), 192 for very sparse regressors
 static int loss_range_size(int n_active) {
@@ -613,10 +605,6 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   if (int rc = dalloc(m, &m->W2_lo, (size_t)C_Z * C_Z)) return rc;
   if (int rc = dalloc(m, &m->W2t_hi, (size_t)C_Z * C_Z)) return rc;
   if (int rc = dalloc(m, &m->W2t_lo, (size_t)C_Z * C_Z)) return rc;
-  if (int rc = dalloc(m, &m->W1f, (size_t)C_Z * C_H)) return rc;
-  if (int rc = dalloc(m, &m->W1tf, (size_t)C_Z * C_H)) return rc;
-  if (int rc = dalloc(m, &m->W2f, (size_t)C_Z * C_Z)) return rc;
-  if (int rc = dalloc(m, &m->W2tf, (size_t)C_Z * C_Z)) return rc;
   JRR_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
   JRR_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   JRR_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
@@ -712,13 +700,6 @@ int jrr::critic_load_impl(JrrModel* m, const float* p, cudaStream_t st) {
   split_transpose_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(W1, C_Z, C_H, m->W1t_hi, m->W1t_lo);
   JRR_LAUNCH_CHECK();
   split_transpose_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(W2, C_Z, C_Z, m->W2t_hi, m->W2t_lo);
-  JRR_LAUNCH_CHECK();
-  // plain fp32 copies for the smem-split GEMM path
-  JRR_CUDA(cudaMemcpyAsync(m->W1f, W1, n1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  JRR_CUDA(cudaMemcpyAsync(m->W2f, W2, n2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  transpose_plain_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(W1, C_Z, C_H, m->W1tf);
-  JRR_LAUNCH_CHECK();
-  transpose_plain_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(W2, C_Z, C_Z, m->W2tf);
   JRR_LAUNCH_CHECK();
   m->has_critic = true;
   return JRR_OK;
