@@ -52,7 +52,7 @@ def hbm_peak():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="c1,c3,c4,cam,c5")
+    ap.add_argument("--only", default="c1,c3,c4,cam,loop,c5")
     ap.add_argument("--frames", type=int, default=312000)
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--max-log2", type=int, default=16)
@@ -190,6 +190,44 @@ def main():
         emit({"config": "camera_fit", "workload": "4096 frames x 1000 Adam iterations on the camera translation "
               "(optimize.py:187-199); one body-model forward, then a per-frame kernel", "ms": round(ms, 3),
               "frame_iterations_per_s": round(B * 1000 / ms * 1e3)})
+
+    if "loop" in only and rank == 0:
+        # the whole per-batch loop of optimize.py:150-312 (minus SPIN inference and the silhouette term) on one
+        # 4096-frame batch: camera fit 1000 it, refinement 100 it with every in-scope term, critic + shape-critic
+        # training step, regressor refit step
+        B = 4096
+        inp = jrr.synthetic.make_pose_inputs(B, 13)
+        x6 = torch.from_numpy(inp["x6"]).to(dev).contiguous()
+        be = torch.from_numpy(inp["betas"]).to(dev).contiguous()
+        gt = 100 * torch.randn(B, 17, 3, device=dev)
+        gt2d = 112 + 40 * torch.randn(B, 17, 2, device=dev)
+        torch.manual_seed(1)
+        ssd = jrr.Shape_Discriminator().state_dict()
+        loop = jrr.RefinementLoop(smpl, J, sd, ssd)
+        cam0 = torch.tensor([0.0, 0.0, 40.0], device=dev).repeat(B, 1)
+        batch = {"orient": x6[:, :1], "pose": x6[:, 1:], "betas": be, "gt_j3d": gt, "gt_j2d": gt2d, "cam": cam0}
+        loop.run_batch(batch)                                           # warm-up (module loading, graphs)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        xs, bs, cs = x6.clone(), be.clone(), cam0.clone()
+        gtc = jrr.move_pelvis(gt)
+        torch.cuda.synchronize()
+        ev[0].record()
+        loop.refiner.fit_camera(xs, bs, gt2d, cs, iters=1000, logical_batch=B)
+        ev[1].record()
+        loop.refiner.refine_2d(xs, bs, cs, gtc, gt2d, iters=100, w_2d=0.01, logical_batch=B)
+        ev[2].record()
+        loop.trainer.step(xs, x6, bs, be, logical_batch=B)
+        ev[3].record()
+        loop.refit.step(xs, bs, gtc, logical_batch=B)
+        ev[4].record()
+        torch.cuda.synchronize()
+        names = ["camera_fit_1000it_ms", "refine_100it_3d+2d+critic+shape_ms", "critic_training_step_ms", "regressor_refit_step_ms"]
+        ms = {n: round(ev[i].elapsed_time(ev[i + 1]), 3) for i, n in enumerate(names)}
+        tot = ev[0].elapsed_time(ev[4])
+        emit({"config": "per_batch_loop", "workload": "optimize.py:150-312 on one 4096-frame batch (no SPIN inference, no "
+              "silhouette term): camera fit, refinement (eager launches: the 2-D variant is not graph-captured), critic + "
+              "shape-critic training step, regressor refit", **ms, "total_ms": round(tot, 3),
+              "frames_per_s": round(B / tot * 1e3, 1)})
 
     if "c5" in only and rank == 0:
         hbm, src = hbm_peak()

@@ -386,7 +386,11 @@ int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
       case EPI_BIAS_RELU_SPLIT: return launch_tc<128, EPI_BIAS_RELU_SPLIT, true>(m, g, st);
       case EPI_MASK_SPLIT: return launch_tc<128, EPI_MASK_SPLIT, true>(m, g, st);
       case EPI_BIAS_RELU_HEAD: return launch_tc<128, EPI_BIAS_RELU_HEAD, true>(m, g, st);
-      case EPI_STORE_SPLITK: return launch_tc<128, EPI_STORE_SPLITK, true>(m, g, st);
+      case EPI_STORE_SPLITK:
+        // N = 768 (the critic's dh): 96-column tiles give 256 tiles = 1.73 waves of 0.75 units instead of
+        // 192 tiles = 1.3 waves of 1 unit on 148 SMs
+        if (g.N == 768 && g.ksplit == 1) return launch_tc<96, EPI_STORE_SPLITK, true>(m, g, st);
+        return launch_tc<128, EPI_STORE_SPLITK, true>(m, g, st);
       default: return fail(JRR_ERR_INVALID, "tc gemm (smem split): unsupported epilogue");
     }
   }
