@@ -174,6 +174,9 @@ def main():
                     help="dense 17x6890 (headline: the full reduction) or the shipped sparse artefact")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-impl", type=int, default=0)
+    ap.add_argument("--loss-path", default="vertex", choices=["vertex", "folded"],
+                    help="vertex: per-vertex fused kernels (blend GEMM + skinning + 17x6890 reduction, the path SURVEY.md 8a "
+                         "names); folded: regressor o skinning o blend operator folded per regressor version (include/jrr.h)")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":
@@ -205,7 +208,9 @@ def main():
     torch.manual_seed(0)
     critic = jrr.Discriminator()                      # default init, frozen
     sd = critic.state_dict()
-    refiner = jrr.PoseRefiner(smpl, J, sd, lr=1e-2, w_joint=10000.0, w_pose=10.0, chunk=B, use_graph=True)
+    refiner = jrr.PoseRefiner(smpl, J, sd, lr=1e-2, w_joint=10000.0, w_pose=10.0, chunk=B, use_graph=True,
+                              loss_path=args.loss_path)
+    folded = args.loss_path == "folded"
     x6_h, be_h, gt_h = make_problem(jrr, smpl, J, B, seed=rank, dev=dev)
     x6_pin, be_pin, gt_pin = x6_h.pin_memory(), be_h.pin_memory(), gt_h.pin_memory()
 
@@ -294,12 +299,24 @@ def main():
     BP = (B + 127) // 128 * 128
     tf32_peak = pk["bf16_sustained"] / 2           # dense TF32 = half the bf16 rate; kernels timed inside a long step
     kern = []
-    fused_fwd = acc.get("skin_fwd", 0.0) < 0.01      # skinning + regressor ran in the GEMM epilogue
-    fused_bwd = acc.get("blend_gemm_bwd", 0.0) < 0.01  # skinning backward generated the GEMM's A operand in smem
+    fused_fwd = not folded and acc.get("skin_fwd", 0.0) < 0.01      # skinning + regressor ran in the GEMM epilogue
+    fused_bwd = not folded and acc.get("blend_gemm_bwd", 0.0) < 0.01  # skinning backward generated the GEMM's A operand in smem
     for name, ms in acc.items():
         if ms <= 0 or (fused_fwd and name == "skin_fwd") or (fused_bwd and name == "blend_gemm_bwd"):
             continue
+        if folded and name in ("skin_fwd", "skin_bwd", "dA_reduce"):
+            continue                                     # empty event intervals on the folded path
         e = {"name": name, "ms": round(ms, 4)}
+        if folded and name in ("blend_gemm_fwd", "blend_gemm_bwd", "loss_seed"):
+            e["name"] = {"blend_gemm_fwd": "folded_gemm_fwd(Q=feat.T^T,N=1224)", "blend_gemm_bwd": "folded_gemm_bwd(dfeat=dQ.T,K=1224)",
+                         "loss_seed": "folded_seed(joints+loss+dA+dQ)"}[name]
+            if name != "loss_seed":
+                fl = 3 * 2.0 * B * 1224 * 218
+                e.update(bound="tensor", achieved=fl / (ms * 1e-3) / 1e12, peak=tf32_peak, unit="TFLOP/s")
+                e["frac"] = round(e["achieved"] / e["peak"], 4)
+                e["achieved"] = round(e["achieved"], 2)
+            kern.append(e)
+            continue
         if name == "blend_gemm_fwd" and fused_fwd:
             e["name"] = "fused_fwd(blend_gemm+skinning+regressor)"
         if name == "skin_bwd" and fused_bwd:
@@ -346,7 +363,8 @@ def main():
                     "share_of_step": round(dom["ms"] / step_ms_prof, 3),
                     "peak_source": pk["source"] + (" bf16_sustained/2 (dense TF32)" if dom["bound"] == "tensor" else " hbm copy")}
     pose_steps_per_s = value / world
-    whole = {"tensor_frac_3xtf32": round(3 * F_GEMM * pose_steps_per_s / (tf32_peak * 1e12), 4),
+    f_gemm = F_GEMM if not folded else 2.0 * (2 * 1224 * 218 + 2 * (768 * 1024 + 1024 * 1024))
+    whole = {"tensor_frac_3xtf32": round(3 * f_gemm * pose_steps_per_s / (tf32_peak * 1e12), 4),
              "hbm_frac_algorithmic": round(ALG_BYTES_PER_POSE_STEP * pose_steps_per_s / (pk["hbm_gbs"] * 1e9), 6),
              "useful_tflops": round(F_USEFUL * pose_steps_per_s / 1e12, 2)}
 
@@ -368,6 +386,37 @@ def main():
     refit_ms = {"accumulate": round(ev[0].elapsed_time(ev[1]), 3), "allreduce": round(ev[1].elapsed_time(ev[2]), 3),
                 "apply": round(ev[2].elapsed_time(ev[3]), 3), "allreduce_bytes": 17 * 6890 * 4 + 4}
 
+    # ---------------------------------------------------------------- the other loss-path formulation, same run
+    other = "folded" if not folded else "vertex"
+    refiner.native.set_loss_path(other)
+    refiner.set_regressor(J)
+    st["x6"].copy_(x6_pin); st["betas"].copy_(be_pin)
+    refiner._run_chunk(st, W, B)                      # re-captures the graph for this path
+    g2 = st["graph"]
+    st["x6"].copy_(x6_pin); st["betas"].copy_(be_pin)
+    st["m"].zero_(); st["v"].zero_(); st["t"].zero_()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(K):
+        g2.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    with torch.no_grad():
+        Rg = jrr.rot6d_to_rotmat(st["x6"].reshape(-1, 6)).view(-1, 24, 3, 3)
+        mp2, _ = jrr.evaluate(jrr.find_joints(smpl, st["betas"], Rg[:, :1], Rg[:, 1:], J.to(dev)), st["gt"])
+    other_path = {"loss_path": other, "value": world * B * K / (t2.item() * 1e-3), "unit": UNIT,
+                  "ms_per_step": t2.item() / K, "mpjpe_after_mm": round(float(mp2), 3),
+                  "gpu_launches": refiner.launches_per_step * K,
+                  "note": "same workload, inputs and iteration count through the other formulation of the loss path "
+                          "(python bench.py --loss-path " + other + " makes it the headline)"}
+    refiner.native.set_loss_path(args.loss_path)
+    refiner.set_regressor(J)
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         rate, ms_cpu, cores = cpu_reference_rate(1024, 6, 1)
@@ -379,7 +428,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": B, "regressor": args.regressor,
+            "config": {"workload": WORKLOAD, "frames_per_gpu": B, "regressor": args.regressor, "loss_path": args.loss_path,
                        "parallelism": f"frame-shard x{world}, no data-path collective",
                        "l2": "per-step working set ~1.2 GB of intermediates per GPU, larger than the 126 MB L2",
                        "graph": "one CUDA graph per step, replayed", "gemm": "tcgen05 3xTF32" if args.gemm_impl == 0 else "simt"},
@@ -391,6 +440,7 @@ def main():
             "quality": {"mpjpe_initial_mm": round(float(mp0), 3), "mpjpe_after_mm": round(float(mpjpe), 3),
                         "pa_mpjpe_after_mm": round(float(pampjpe), 3), "iterations": K},
             "refit_ms": refit_ms,
+            "other_loss_path": other_path,
             "cpu_baseline": cpu,
         }
         emit(out)

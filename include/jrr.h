@@ -89,6 +89,19 @@ int jrr_model_destroy(JrrModel* model);
  * be NULL (== all ones, which is what utils.py:182-187 returns). */
 int jrr_set_regressor(JrrModel* model, const float* J17_raw, const float* mask, void* stream);
 
+/* Loss-path formulation used by jrr_refine_step / jrr_refine_step_2d (the results are the same function
+ * of the inputs; see DESIGN.md "folded loss path"):
+ *   JRR_LOSS_PATH_VERTEX  per-vertex: blend GEMM [B,224]x[224,20736] with skinning and the 17x6890
+ *                         regressor reduction fused into it, and the mirrored backward (default)
+ *   JRR_LOSS_PATH_FOLDED  the constant linear maps between blend features and regressed joints
+ *                         (regressor o skinning weights o blend matrix) are folded once per regressor
+ *                         version into T[24*17*3, 224]; a step then runs two N = 1224 GEMMs and a per-frame
+ *                         contraction with the joint transforms instead of any per-vertex work.
+ * Re-folds inside jrr_set_regressor / jrr_regressor_apply while selected. */
+#define JRR_LOSS_PATH_VERTEX 0
+#define JRR_LOSS_PATH_FOLDED 1
+int jrr_set_loss_path(JrrModel* model, int mode, void* stream);
+
 /* replaces: Discriminator.__init__/load_state_dict (scripts/discriminator.py:7-30).
  * `params` is DEVICE fp32, the state_dict tensors flattened and concatenated in this order:
  * conv_operations.0.weight[32,6] .bias[32] conv_operations.2.weight[32,32] .bias[32]

@@ -19,7 +19,7 @@ EXPORTS = [
     "jrr_regressor_grad_accumulate", "jrr_regressor_apply", "jrr_last_launch_count",
     "jrr_debug_gemm", "jrr_refine_step_profiled", "jrr_step_kernel_name", "jrr_camera_fit", "jrr_refine_step_2d", "jrr_evaluate",
     "jrr_shape_critic_load", "jrr_shape_critic_forward", "jrr_critic_grad_accumulate", "jrr_critic_apply",
-    "jrr_shape_critic_grad_accumulate", "jrr_shape_critic_apply",
+    "jrr_shape_critic_grad_accumulate", "jrr_shape_critic_apply", "jrr_set_loss_path",
 ]
 
 
@@ -55,6 +55,7 @@ def lib():
     L.jrr_model_destroy.argtypes = [vp]
     L.jrr_set_regressor.argtypes = [vp, vp, vp, vp]
     L.jrr_critic_load.argtypes = [vp, vp, vp]
+    L.jrr_set_loss_path.argtypes = [vp, C.c_int, vp]
     L.jrr_shape_critic_load.argtypes = [vp, vp, C.c_float, vp]
     L.jrr_shape_critic_forward.argtypes = [vp, i64, vp, vp, vp]
     L.jrr_critic_grad_accumulate.argtypes = [vp, i64, i64, vp, C.c_float, vp, vp, vp, sz, vp]

@@ -224,6 +224,7 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   Workspace w;
   if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
   if (!m->has_regressor) return fail(JRR_ERR_STATE, "jrr_set_regressor has not been called");
+  if (m->folded && !m->T_hi) return fail(JRR_ERR_STATE, "folded loss path selected before a regressor was set");
   if (!x6 || !betas || !gt_mm || !adam_m || !adam_v || !step_count) return fail(JRR_ERR_INVALID, "null argument");
   if (B_logical < B) return fail(JRR_ERR_INVALID, "B_logical must be >= B");
   const bool critic = w_pose != 0.f;
@@ -254,29 +255,62 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
     JRR_CUDA(cudaEventRecord(m->ev_join, m->side));
   }
   JRR_MARK();
-  // forward: chain | blend GEMM with the skinning + 17x6890 regressor epilogue | loss seed
-  // (events: pose_fwd | blend_gemm_fwd [fused: the whole forward] | skin_fwd [fused: empty])
-  if (int rc = loss_forward(m, w, betas, x6, JRR_POSE_ROT6D, 1, w.vpT, st, ev ? &ev[1] : nullptr, ev ? &ev[2] : nullptr)) return rc;
-  mark = 3;
-  JRR_MARK();
-  if (int rc = launch_loss_seed(m, w, m->fused_fwd, gt_mm, B_logical, w_joint, nullptr, p2d, st)) return rc;
-  JRR_MARK();
-  // backward: regressor-transpose seed + skinning | dA reduction | blend GEMM
-  // (events: skin_bwd [fused: skinning backward + blend-gradient GEMM] | dA_reduce | blend_gemm_bwd [fused: empty])
-  if (m->fused_bwd) {
-    w.ksplit = m->nsplit_act;
-    if (int rc = launch_fused_bwd(m, w, st)) return rc;
+  if (m->folded) {
+    // folded loss path: chain | Q = feat . T^T | per-frame joints + loss seed + dA + dQ | dfeat = dQ . T (split-K)
+    // (events: pose_fwd | blend_gemm_fwd [the N = 1224 GEMM] | skin_fwd [empty] | loss_seed [folded seed] |
+    //  skin_bwd [empty] | dA_reduce [empty] | blend_gemm_bwd [the K = 1280 GEMM])
+    if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, x6, JRR_POSE_ROT6D, w.AT, w.feat_hi, w.feat_lo, nullptr, st)) return rc;
     JRR_MARK();
-    if (int rc = launch_dA_reduce(m, w, true, st)) return rc;
+    {
+      GemmDesc g{};
+      g.A_hi = w.feat_hi; g.A_lo = w.feat_lo; g.lda = KA;
+      g.B_hi = m->T_hi; g.B_lo = m->T_lo; g.ldb = KA;
+      g.M = w.BP; g.N = FOLD_NP; g.K = KA; g.ksplit = 1; g.epi = EPI_STORE_T;
+      g.out0 = w.vpT; g.ldo = w.BP;
+      if (int rc = launch_gemm(m, g, st)) return rc;
+    }
     JRR_MARK();
+    JRR_MARK();
+    if (int rc = launch_folded_seed(m, w, gt_mm, B_logical, w_joint, nullptr, p2d, st)) return rc;
+    JRR_MARK();
+    JRR_MARK();
+    JRR_MARK();
+    {
+      w.ksplit = (w.BP / 128) * 4 >= m->num_sms ? 4 : 8;
+      GemmDesc g{};
+      g.A_hi = w.dvp_hi; g.A_lo = w.dvp_lo; g.lda = FOLD_NP;
+      g.B_hi = m->Tt_hi; g.B_lo = m->Tt_lo; g.ldb = FOLD_NP;
+      g.M = w.BP; g.N = KA; g.K = FOLD_NP / w.ksplit; g.ksplit = w.ksplit; g.epi = EPI_STORE_SPLITK;
+      g.k_valid = FOLD_N;                      // the seed kernel writes 1224 columns per row; TMA zero-fills the K padding
+      g.out0 = w.dfeat; g.ldo = KA;
+      if (int rc = launch_gemm(m, g, st)) return rc;
+    }
     JRR_MARK();
   } else {
-    if (int rc = launch_skin_bwd(m, w, nullptr, true, false, st)) return rc;
+  // forward: chain | blend GEMM with the skinning + 17x6890 regressor epilogue | loss seed
+    // (events: pose_fwd | blend_gemm_fwd [fused: the whole forward] | skin_fwd [fused: empty])
+    if (int rc = loss_forward(m, w, betas, x6, JRR_POSE_ROT6D, 1, w.vpT, st, ev ? &ev[1] : nullptr, ev ? &ev[2] : nullptr)) return rc;
+    mark = 3;
     JRR_MARK();
-    if (int rc = launch_dA_reduce(m, w, false, st)) return rc;
+    if (int rc = launch_loss_seed(m, w, m->fused_fwd, gt_mm, B_logical, w_joint, nullptr, p2d, st)) return rc;
     JRR_MARK();
-    if (int rc = blend_backward_gemm(m, w, st)) return rc;
-    JRR_MARK();
+    // backward: regressor-transpose seed + skinning | dA reduction | blend GEMM
+    // (events: skin_bwd [fused: skinning backward + blend-gradient GEMM] | dA_reduce | blend_gemm_bwd [fused: empty])
+    if (m->fused_bwd) {
+      w.ksplit = m->nsplit_act;
+      if (int rc = launch_fused_bwd(m, w, st)) return rc;
+      JRR_MARK();
+      if (int rc = launch_dA_reduce(m, w, true, st)) return rc;
+      JRR_MARK();
+      JRR_MARK();
+    } else {
+      if (int rc = launch_skin_bwd(m, w, nullptr, true, false, st)) return rc;
+      JRR_MARK();
+      if (int rc = launch_dA_reduce(m, w, false, st)) return rc;
+      JRR_MARK();
+      if (int rc = blend_backward_gemm(m, w, st)) return rc;
+      JRR_MARK();
+    }
   }
   // critic forward + input gradient (inline when profiling or when the fork is disabled)
   const bool inl = critic && !fork;

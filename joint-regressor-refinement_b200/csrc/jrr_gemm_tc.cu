@@ -353,11 +353,12 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   const int64_t Ktot = g.K * g.ksplit;
   if (int rc = make_tensor_map_2d(&mBh, g.B_hi, g.N, Ktot, g.ldb, BN)) return rc;
   if (int rc = make_tensor_map_2d(&mBl, g.B_lo, g.N, Ktot, g.ldb, BN)) return rc;
-  if (int rc = make_tensor_map_2d(&mAh, g.A_hi, g.M, Ktot, g.lda, BM)) return rc;
+  const int64_t Ka = g.k_valid > 0 ? g.k_valid : Ktot;      // columns of A that exist; TMA zero-fills beyond
+  if (int rc = make_tensor_map_2d(&mAh, g.A_hi, g.M, Ka, g.lda, BM)) return rc;
   if (SS) {
     mAl = mAh;                 // unused by the kernel: one raw fp32 A tile per stage
   } else {
-    if (int rc = make_tensor_map_2d(&mAl, g.A_lo, g.M, Ktot, g.lda, BM)) return rc;
+    if (int rc = make_tensor_map_2d(&mAl, g.A_lo, g.M, Ka, g.lda, BM)) return rc;
   }
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.ksplit = g.ksplit;

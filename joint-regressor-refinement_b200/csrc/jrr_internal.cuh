@@ -98,8 +98,10 @@ struct VtxRec {
 };
 static_assert(sizeof(VtxRec) == 112, "VtxRec tiles are staged as float4");
 constexpr int REC_WORDS = 28;
-constexpr int LOSS_PART_POSE = 4096;  // offset of the critic partials inside Workspace::loss_part
-constexpr int LOSS_PART_2D = 2048;    // offset of the 2-D reprojection partials (<= 2048 pose blocks per call)
+constexpr int FOLD_N = 24 * 17 * 3;      // rows of the folded operator T: (joint j, regressor row i, coordinate c)
+constexpr int FOLD_NP = 1280;            // ... padded to the GEMM tile
+constexpr int LOSS_PART_POSE = 16384; // offset of the critic partials inside Workspace::loss_part
+constexpr int LOSS_PART_2D = 8192;    // offset of the 2-D reprojection partials (<= 8192 pose blocks of 32 per call)
 constexpr int64_t MAX_POSES_PER_CALL = 262144;
 
 // sparse rows (CSR over ORIGINAL vertex ids) for the joints49 path
@@ -172,6 +174,12 @@ struct JrrModel {
   bool critic_ss = true;                     // critic GEMMs of the refine step: plain fp32 activations staged through tensor
                                              // memory (JRR_CRITIC_SS=0: pre-split activations through shared memory)
   bool critic_head_fused = true;             // global critic head inside the layer-2 GEMM epilogue (refine step)
+  // folded loss path (jrr_set_loss_path): T = Jhat o skinning weights o blend matrix, per regressor version
+  bool folded = false;
+  float *T_hi = nullptr, *T_lo = nullptr;    // [FOLD_NP][KA]   forward B operand
+  float *Tt_hi = nullptr, *Tt_lo = nullptr;  // [KA][FOLD_NP]   backward B operand
+  float* Tc = nullptr;                       // [24][17]        sum_v Jhat_iv w_vj
+  double* fold_part = nullptr;               // scratch of fold_kernel
   bool fused_fwd = true;   // loss path: skinning + regressor in the blend GEMM's epilogue
   bool fused_bwd = true;   // loss path: skinning backward generates the A operand of the blend-gradient GEMM
   std::vector<void*> allocs;
@@ -195,6 +203,7 @@ struct Workspace {
   float* dAT;       // [288][BP]
   float* dfeat;     // [ksplit][BP][224]
   int ksplit;       // split-K factor of the backward blend GEMM for this batch
+  int n_joint_part; // number of joint-loss partials the last seed kernel wrote
   float* dJp;       // [BP][72]    grad wrt posed joints (module path)
   float* Jp;        // [BP][72]    posed joints
   float* d30T;      // [90][BP]    joints49 gradient gathered onto picks / extra rows
@@ -237,6 +246,7 @@ struct GemmDesc {
   const float* mask; int64_t ldmask;       // (EPI_MASK_SPLIT) multiply by (mask>0)
   const float* rowscale;                   // (EPI_MASK_SPLIT) and by rowscale[m] when given
   const float* vec; float* out2;           // (EPI_BIAS_RELU_HEAD) w3[N] in, logit partials [N/128][M] out
+  int64_t k_valid;                         // > 0: only the first k_valid columns of A exist (TMA zero-fills the rest of K)
   bool smem_split;                         // A is plain fp32 (A_hi): loaded, tf32-split and staged in tensor memory by the
                                            // kernel (B stays pre-split); *_SPLIT epilogues then write ONE fp32 array (out0)
 };
@@ -257,7 +267,10 @@ struct Proj2D {
   float lr = 0.f;
   float scale = 0.f;             // w_2d * 2 / (34 * B_logical)
 };
-int launch_loss_seed(const JrrModel* m, const Workspace& w, bool fused_partials, const float* gt_mm,
+int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int64_t B_logical, float w_joint,
+                       float* joints17_out, const Proj2D& p2d, cudaStream_t st);
+int launch_fold(JrrModel* m, cudaStream_t st);
+int launch_loss_seed(const JrrModel* m, Workspace& w, bool fused_partials, const float* gt_mm,
                      int64_t B_logical, float w_joint, float* joints17_out, const Proj2D& p2d, cudaStream_t st);
 int launch_camera_fit(const Workspace& w, const float* joints17, const float* gt2d, float* cam, int iters, float lr,
                       int64_t B_logical, float* loss_out, cudaStream_t st);

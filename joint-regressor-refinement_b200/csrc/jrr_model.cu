@@ -252,7 +252,82 @@ int launch_regressor_apply(JrrModel* m, float* Jraw, const float* mask, const fl
   JRR_LAUNCH_CHECK();
   bump_kernel<<<1, 1, 0, st>>>(step_count);
   JRR_LAUNCH_CHECK();
-  return launch_regressor_normalise(m, Jraw, mask, st);
+  if (int rc = launch_regressor_normalise(m, Jraw, mask, st)) return rc;
+  return m->folded ? launch_fold(m, st) : JRR_OK;
+}
+
+// --------------------------------------------------------------------- folded loss-path operator
+// T[(j,i,c)][k] = sum_v Jhat_iv w_vj P[3v+c][k],  c_ji = sum_v Jhat_iv w_vj   (see folded_seed_kernel).
+// grid (17 regressor rows, 4 = three coordinates + the homogeneous one, FOLD_CH vertex chunks), thread = k;
+// double accumulators in shared memory, fixed summation order (chunk partials reduced in order).
+constexpr int FOLD_CH = 8;
+__global__ void __launch_bounds__(KA)
+fold_kernel(const VtxRec* __restrict__ vrec, const float* __restrict__ Pt_hi, const float* __restrict__ Pt_lo,
+            double* __restrict__ part) {
+  __shared__ double acc[NJ * KA];
+  const int i = blockIdx.x, c = blockIdx.y, ch = blockIdx.z, k = threadIdx.x;
+  for (int e = k; e < NJ * KA; e += KA) acc[e] = 0.0;
+  __syncthreads();                 // (each thread only ever touches column k, the barrier is for the zeroing loop)
+  const int per = VP / FOLD_CH;
+  for (int pi = ch * per; pi < (ch + 1) * per; pi++) {
+    const float jh = vrec[pi].jh[i];
+    if (jh == 0.f) continue;       // uniform: vertices outside the regressor row's support
+    const uint32_t meta = vrec[pi].meta;
+    double p;
+    if (c < 3) p = (double)Pt_hi[(int64_t)(3 * pi + c) * KA + k] + (double)Pt_lo[(int64_t)(3 * pi + c) * KA + k];
+    else p = k == 0 ? 1.0 : 0.0;
+#pragma unroll
+    for (int s4 = 0; s4 < 4; s4++) {
+      const float w = vrec[pi].w[s4];
+      if (w != 0.f) acc[((meta >> (5 * s4)) & 31u) * KA + k] += (double)w * (double)jh * p;
+    }
+  }
+  double* out = part + ((int64_t)(ch * NH + i) * 4 + c) * (NJ * KA);
+  for (int j = 0; j < NJ; j++) out[j * KA + k] = acc[j * KA + k];
+}
+
+__global__ void fold_finish_kernel(const double* __restrict__ part, float* __restrict__ T_hi, float* __restrict__ T_lo,
+                                   float* __restrict__ Tt_hi, float* __restrict__ Tt_lo, float* __restrict__ Tc) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (int64_t)FOLD_N * KA) {
+    const int n = (int)(idx / KA), k = (int)(idx % KA);
+    const int c = n % 3, i = (n / 3) % NH, j = n / (3 * NH);
+    double a = 0.0;
+    for (int ch = 0; ch < FOLD_CH; ch++) a += part[((int64_t)(ch * NH + i) * 4 + c) * (NJ * KA) + j * KA + k];
+    const float x = (float)a;
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    const float hi = __uint_as_float(r);
+    const float d = x - hi;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
+    const float lo = __uint_as_float(r);
+    T_hi[idx] = hi;
+    T_lo[idx] = lo;
+    Tt_hi[(int64_t)k * FOLD_NP + n] = hi;
+    Tt_lo[(int64_t)k * FOLD_NP + n] = lo;
+  } else if (idx < (int64_t)FOLD_N * KA + NJ * NH) {
+    const int e = (int)(idx - (int64_t)FOLD_N * KA), j = e / NH, i = e % NH;
+    double a = 0.0;
+    for (int ch = 0; ch < FOLD_CH; ch++) a += part[((int64_t)(ch * NH + i) * 4 + 3) * (NJ * KA) + j * KA];
+    Tc[e] = (float)a;
+  }
+}
+
+int launch_fold(JrrModel* m, cudaStream_t st) {
+  if (!m->T_hi) {
+    if (int rc = dalloc(m, &m->T_hi, (size_t)FOLD_NP * KA)) return rc;      // zero-filled: the padding rows stay zero
+    if (int rc = dalloc(m, &m->T_lo, (size_t)FOLD_NP * KA)) return rc;
+    if (int rc = dalloc(m, &m->Tt_hi, (size_t)FOLD_NP * KA)) return rc;
+    if (int rc = dalloc(m, &m->Tt_lo, (size_t)FOLD_NP * KA)) return rc;
+    if (int rc = dalloc(m, &m->Tc, (size_t)NJ * NH)) return rc;
+    if (int rc = dalloc(m, &m->fold_part, (size_t)FOLD_CH * NH * 4 * NJ * KA)) return rc;
+  }
+  fold_kernel<<<dim3(NH, 4, FOLD_CH), KA, 0, st>>>(m->vrec, m->Pt_hi, m->Pt_lo, m->fold_part);
+  JRR_LAUNCH_CHECK();
+  const int64_t n = (int64_t)FOLD_N * KA + NJ * NH;
+  fold_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->fold_part, m->T_hi, m->T_lo, m->Tt_hi, m->Tt_lo, m->Tc);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
 }
 
 // --------------------------------------------------------------------- critic load kernels
@@ -453,6 +528,7 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   if (const char* e = getenv("JRR_COMPACT_ACTIVE")) m->compact_active = (e[0] != '0');
   if (const char* e = getenv("JRR_CRITIC_HEAD_FUSED")) m->critic_head_fused = (e[0] != '0');
   if (const char* e = getenv("JRR_CRITIC_SS")) m->critic_ss = (e[0] != '0');
+  if (const char* e = getenv("JRR_LOSS_PATH")) m->folded = (e[0] == 'f' || e[0] == '1') && m->gemm_impl == 0;
   if (m->gemm_impl != 0) { m->fused_fwd = false; m->fused_bwd = false; m->critic_head_fused = false; }
   if (!m->critic_head_fused) m->critic_ss = false;
   // the active-vertex prefix is only walked by the two fused kernels; the stand-alone skinning
@@ -658,7 +734,8 @@ extern "C" int jrr_set_regressor(JrrModel* m, const float* J17_raw, const float*
       if (int rc = build_packing(m, act)) return rc;
     }
   }
-  return launch_regressor_normalise(m, J17_raw, mask, st);
+  if (int rc = launch_regressor_normalise(m, J17_raw, mask, st)) return rc;
+  return m->folded ? launch_fold(m, st) : JRR_OK;
 }
 
 extern "C" int jrr_critic_load(JrrModel* m, const float* p, void* stream) {
@@ -718,5 +795,15 @@ extern "C" int jrr_shape_critic_load(JrrModel* m, const float* p, float w_shape,
                            (cudaStream_t)stream));
   m->has_shape_critic = true;
   m->w_shape = w_shape;
+  return JRR_OK;
+}
+
+extern "C" int jrr_set_loss_path(JrrModel* m, int mode, void* stream) {
+  if (!m) return fail(JRR_ERR_INVALID, "null argument");
+  if (mode != JRR_LOSS_PATH_VERTEX && mode != JRR_LOSS_PATH_FOLDED) return fail(JRR_ERR_INVALID, "unknown loss path");
+  if (mode == JRR_LOSS_PATH_FOLDED && m->gemm_impl != 0) return fail(JRR_ERR_INVALID, "the folded loss path needs the tcgen05 GEMM");
+  reset_launch_count();
+  m->folded = mode == JRR_LOSS_PATH_FOLDED;
+  if (m->folded && m->has_regressor) return launch_fold(m, (cudaStream_t)stream);
   return JRR_OK;
 }

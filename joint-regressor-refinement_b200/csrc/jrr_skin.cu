@@ -329,6 +329,155 @@ loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T,
   }
 }
 
+// ---------------------------------------------------------------------------- folded loss path
+// The regressed joints are linear in the blended vertices and the blended vertices are linear in the
+// blend features, with the joint transforms as the only pose-dependent factors in between:
+//   joints17_i(b) = sum_j  A_j^R(b) . (T_ji . feat_b)  +  A_j^t(b) . c_ji
+//   T_ji[c][k] = sum_v Jhat_iv w_vj P[3v+c][k]   (3 x 224),    c_ji = sum_v Jhat_iv w_vj
+// T and c depend on the model and the regressor only (fold_kernel, once per regressor version), so
+// the whole per-vertex pass (blend GEMM N = 20736, skinning, 17x6890 reduction and their backward)
+// becomes Q = feat . T^T (N = 1224), this kernel, and dfeat = dQ . T.  Thread = pose:
+//   forward   pred_i = sum_j A_j^R q_ji + A_j^t c_ji            (q from QT, pose-contiguous)
+//   loss      exactly loss_seed_kernel's (pelvis-centred MSE seed, optional 2-D term + camera Adam)
+//   backward  dA_j^R = sum_i g_i (x) q_ji,  dA_j^t = sum_i g_i c_ji,  dq_ji = A_j^R^T g_i
+// dQ rows leave through shared memory so that each pose's 51 values per joint are written contiguously.
+// Work split: 32 poses per CTA (lane = pose, so every load/store of the pose-contiguous arrays is one
+// 128-byte line), 4 warps x 6 joints each; the partial joints meet in shared memory in a fixed order.
+constexpr int FS_POSES = 32;
+constexpr int FS_WARPS = 4;
+constexpr int FS_JPW = NJ / FS_WARPS;          // 6 joints per warp
+constexpr int FS_LD = 53;                      // dq staging row (odd: conflict-free transposed access)
+__global__ void __launch_bounds__(FS_WARPS * 32)
+folded_seed_kernel(const float* __restrict__ QT, const float* __restrict__ AT, const float* __restrict__ Tc,
+                   const float* __restrict__ gt_mm, int64_t B, int64_t BP, float scale, const Proj2D p2d,
+                   float* __restrict__ loss_part, float* __restrict__ joints17_out, float* __restrict__ dAT,
+                   float* __restrict__ dQ_hi, float* __restrict__ dQ_lo) {
+  __shared__ float sTc[NJ * NH];
+  __shared__ float sbuf[FS_WARPS * FS_POSES * FS_LD];    // forward: partial joints [warp][51][32]; backward: dq staging
+  __shared__ float sg[NACC * FS_POSES];                  // joints, then the loss seed g, [a][pose]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t b0 = (int64_t)blockIdx.x * FS_POSES, b = b0 + lane;
+  for (int i = tid; i < NJ * NH; i += FS_WARPS * 32) sTc[i] = Tc[i];
+  __syncthreads();
+  {
+    float pred[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; a++) pred[a] = 0.f;
+#pragma unroll 1
+    for (int jj = 0; jj < FS_JPW; jj++) {
+      const int j = warp * FS_JPW + jj;
+      float A[12];
+#pragma unroll
+      for (int e = 0; e < 12; e++) A[e] = AT[(int64_t)(j * 12 + e) * BP + b];
+      const float* q = QT + (int64_t)(j * NH * 3) * BP + b;
+#pragma unroll
+      for (int i = 0; i < NH; i++) {
+        const float q0 = q[(int64_t)(i * 3 + 0) * BP], q1 = q[(int64_t)(i * 3 + 1) * BP], q2 = q[(int64_t)(i * 3 + 2) * BP];
+        const float tc = sTc[j * NH + i];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+          pred[i * 3 + r] += fmaf(A[r * 4 + 0], q0, fmaf(A[r * 4 + 1], q1, fmaf(A[r * 4 + 2], q2, A[r * 4 + 3] * tc)));
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NACC; a++) sbuf[(warp * NACC + a) * FS_POSES + lane] = pred[a];
+  }
+  __syncthreads();
+  for (int a = warp; a < NACC; a += FS_WARPS) {
+    float t = sbuf[a * FS_POSES + lane];
+#pragma unroll
+    for (int w2 = 1; w2 < FS_WARPS; w2++) t += sbuf[(w2 * NACC + a) * FS_POSES + lane];
+    sg[a * FS_POSES + lane] = t;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float pred[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; a++) pred[a] = sg[a * FS_POSES + lane];
+    if (b < B && joints17_out != nullptr) {
+#pragma unroll
+      for (int a = 0; a < NACC; a++) joints17_out[b * NACC + a] = pred[a];
+    }
+    if (dAT != nullptr) {
+      float g[NACC];
+      float loss = 0.f, loss2 = 0.f;
+      float sum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int a = 0; a < NACC; a++) {
+        float d = 0.f;
+        if (b < B) d = (pred[a] - pred[a % 3]) - gt_mm[b * NACC + a] / 1000.f;
+        loss += d * d;
+        g[a] = scale * d;
+        sum[a % 3] += g[a];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) g[c] -= sum[c];
+      if (p2d.gt2d != nullptr) {
+        if (b < B) {
+          float Tcam[3], dT[3] = {0.f, 0.f, 0.f}, m3[3], v3[3];
+#pragma unroll
+          for (int c = 0; c < 3; c++) { Tcam[c] = p2d.cam[b * 3 + c]; m3[c] = p2d.cam_m[b * 3 + c]; v3[c] = p2d.cam_v[b * 3 + c]; }
+          loss2 = proj2d_grad(pred, Tcam, p2d.gt2d + b * 34, p2d.scale, g, dT);
+          adam_update3(Tcam, dT, m3, v3, *p2d.step_count + 1, p2d.lr);
+#pragma unroll
+          for (int c = 0; c < 3; c++) { p2d.cam[b * 3 + c] = Tcam[c]; p2d.cam_m[b * 3 + c] = m3[c]; p2d.cam_v[b * 3 + c] = v3[c]; }
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        loss += __shfl_xor_sync(0xffffffffu, loss, o);
+        loss2 += __shfl_xor_sync(0xffffffffu, loss2, o);
+      }
+      if (lane == 0) { loss_part[blockIdx.x] = loss; loss_part[LOSS_PART_2D + blockIdx.x] = loss2; }
+#pragma unroll
+      for (int a = 0; a < NACC; a++) sg[a * FS_POSES + lane] = g[a];
+    }
+  }
+  if (dAT == nullptr) return;      // joints only (uniform)
+  __syncthreads();
+  float* sdq = sbuf + warp * FS_POSES * FS_LD;
+#pragma unroll 1
+  for (int jj = 0; jj < FS_JPW; jj++) {
+    const int j = warp * FS_JPW + jj;
+    float A[12], dA[12];
+#pragma unroll
+    for (int e = 0; e < 12; e++) { A[e] = AT[(int64_t)(j * 12 + e) * BP + b]; dA[e] = 0.f; }
+    const float* q = QT + (int64_t)(j * NH * 3) * BP + b;
+#pragma unroll
+    for (int i = 0; i < NH; i++) {
+      const float q0 = q[(int64_t)(i * 3 + 0) * BP], q1 = q[(int64_t)(i * 3 + 1) * BP], q2 = q[(int64_t)(i * 3 + 2) * BP];
+      const float tc = sTc[j * NH + i];
+      const float g0 = sg[(i * 3 + 0) * FS_POSES + lane], g1 = sg[(i * 3 + 1) * FS_POSES + lane], g2 = sg[(i * 3 + 2) * FS_POSES + lane];
+      dA[0] = fmaf(g0, q0, dA[0]); dA[1] = fmaf(g0, q1, dA[1]); dA[2] = fmaf(g0, q2, dA[2]); dA[3] = fmaf(g0, tc, dA[3]);
+      dA[4] = fmaf(g1, q0, dA[4]); dA[5] = fmaf(g1, q1, dA[5]); dA[6] = fmaf(g1, q2, dA[6]); dA[7] = fmaf(g1, tc, dA[7]);
+      dA[8] = fmaf(g2, q0, dA[8]); dA[9] = fmaf(g2, q1, dA[9]); dA[10] = fmaf(g2, q2, dA[10]); dA[11] = fmaf(g2, tc, dA[11]);
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+        sdq[lane * FS_LD + i * 3 + c] = fmaf(A[c], g0, fmaf(A[4 + c], g1, A[8 + c] * g2));
+    }
+#pragma unroll
+    for (int e = 0; e < 12; e++) dAT[(int64_t)(j * 12 + e) * BP + b] = dA[e];
+    __syncwarp();
+    // each pose's 51 values of this joint are contiguous in its dQ row (K-major A operand of the second GEMM)
+#pragma unroll 4
+    for (int p = 0; p < FS_POSES; p++) {
+      const int64_t o = (b0 + p) * FOLD_NP + j * NACC;
+      {
+        const float x = sdq[p * FS_LD + lane];
+        const float hi = tf32_hi_k(x);
+        dQ_hi[o + lane] = hi;
+        dQ_lo[o + lane] = tf32_hi_k(x - hi);
+      }
+      if (lane < NACC - 32) {
+        const float x = sdq[p * FS_LD + 32 + lane];
+        const float hi = tf32_hi_k(x);
+        dQ_hi[o + 32 + lane] = hi;
+        dQ_lo[o + 32 + lane] = tf32_hi_k(x - hi);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------------------- backward
 // dv_i = Jhat^T g (USE_G) + dvertices (USE_DV, natural layout staged through smem) +
 //        picks / extra-regressor rows of the joints49 gradient (USE_X)
@@ -762,12 +911,13 @@ int launch_skin_fwd(const JrrModel* m, const Workspace& w, float* vertices_out, 
   return JRR_OK;
 }
 
-// poses per CTA of the loss-seed kernel: 32 while the partial count fits its 2048-entry region
-static inline int loss_seed_ppb(int64_t BP) { return BP / 32 <= 2048 ? 32 : 128; }
+// poses per CTA of the loss-seed kernel: 32 while the partial count fits its region of the partial buffer
+static inline int loss_seed_ppb(int64_t BP) { return BP / 32 <= LOSS_PART_2D ? 32 : 128; }
 
-int launch_loss_seed(const JrrModel* m, const Workspace& w, bool fused_partials, const float* gt_mm,
+int launch_loss_seed(const JrrModel* m, Workspace& w, bool fused_partials, const float* gt_mm,
                      int64_t B_logical, float w_joint, float* joints17_out, const Proj2D& p2d, cudaStream_t st) {
   const int ppb = loss_seed_ppb(w.BP);
+  w.n_joint_part = (int)(w.BP / ppb);
   dim3 grid((unsigned)(w.BP / ppb)), block(LS_THREADS);
   const float scale = gt_mm != nullptr ? w_joint * 2.f / (51.f * (float)B_logical) : 0.f;
   const int n_tiles = m->nv_act / 64, T = (int)(w.BP / 128) * n_tiles, G = T < m->num_sms ? T : m->num_sms;
@@ -833,9 +983,22 @@ int launch_joints49_bwd(const JrrModel* m, const Workspace& w, const float* djoi
   return JRR_OK;
 }
 
+// Folded loss path: joints (+ loss seed, dA, dQ when gt_mm is given) from Q = feat . T^T.
+int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int64_t B_logical, float w_joint,
+                       float* joints17_out, const Proj2D& p2d, cudaStream_t st) {
+  const float scale = gt_mm != nullptr ? w_joint * 2.f / (51.f * (float)B_logical) : 0.f;
+  const bool grad = gt_mm != nullptr;
+  w.n_joint_part = (int)(w.BP / FS_POSES);
+  folded_seed_kernel<<<(unsigned)(w.BP / FS_POSES), FS_WARPS * 32, 0, st>>>(
+      w.vpT, w.AT, m->Tc, gt_mm, w.B, w.BP, scale, p2d, w.loss_part, joints17_out, grad ? w.dAT : nullptr,
+      grad ? w.dvp_hi : nullptr, grad ? w.dvp_lo : nullptr);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
 int launch_loss_finish(const Workspace& w, int64_t B_logical, float w_joint, float w_pose,
                        bool have_pose, float w_2d, float w_shape, float* loss_out, float* loss_accum, cudaStream_t st) {
-  const int nj = (int)(w.BP / loss_seed_ppb(w.BP));
+  const int nj = w.n_joint_part;
   const int np = have_pose ? w.n_pose_part : 0;
   loss_finish_kernel<<<1, 32, 0, st>>>(w.loss_part, nj, 1.f / (51.f * (float)B_logical),
                                        w.loss_part + LOSS_PART_POSE, np, 1.f / (25.f * (float)B_logical),

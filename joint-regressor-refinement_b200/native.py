@@ -149,6 +149,15 @@ class NativeModel:
             check(self.L.jrr_critic_load(self.h, _ptr(flat), _stream()), "jrr_critic_load")
             torch.cuda.current_stream().synchronize()   # `flat` may be freed after return
 
+    def set_loss_path(self, mode: str):
+        """'vertex' (per-vertex fused kernels, default) or 'folded' (regressor o skinning o blend operator
+        folded once per regressor version; see include/jrr.h)."""
+        code = {"vertex": 0, "folded": 1}[mode]
+        with torch.cuda.device(self.device):
+            check(self.L.jrr_set_loss_path(self.h, code, _stream()), "jrr_set_loss_path")
+        self.loss_path = mode
+        self.regressor_version = getattr(self, "regressor_version", 0) + 1     # captured graphs hold the old launch sequence
+
     def load_shape_critic(self, state_dict, w_shape: float = 10.0):
         """Shape_Discriminator weights (scripts/discriminator.py:57-74) + the weight of its loss
         term (optimize.py:253).  ``state_dict=None`` switches the term off."""

@@ -28,7 +28,7 @@ from .utils import evaluate, move_pelvis
 class RefinementLoop:
     def __init__(self, smpl, J_regressor, critic_state_dict, shape_critic_state_dict=None, mask=None,
                  lr=1e-2, disc_lr=1e-3, j_reg_lr=1e-2, refine_iters=100, cam_iters=1000,
-                 w_joint=10000.0, w_pose=10.0, w_shape=10.0, w_2d=0.01, chunk=4096):
+                 w_joint=10000.0, w_pose=10.0, w_shape=10.0, w_2d=0.01, chunk=4096, loss_path=None):
         self.native = smpl.native() if hasattr(smpl, "native") else smpl
         self.device = self.native.device
         self.refine_iters, self.cam_iters, self.w_2d = int(refine_iters), int(cam_iters), float(w_2d)
@@ -37,7 +37,7 @@ class RefinementLoop:
         self.refit = RegressorRefit(smpl, J_regressor, mask=mask, lr=j_reg_lr, chunk=chunk)
         self.refiner = PoseRefiner(smpl, self.refit.J_regressor, critic_state_dict, mask=mask, lr=lr, w_joint=w_joint,
                                    w_pose=w_pose, chunk=chunk, shape_critic_state_dict=shape_critic_state_dict,
-                                   w_shape=w_shape)
+                                   w_shape=w_shape, loss_path=loss_path)
         self.trainer = CriticTrainer(smpl, critic_state_dict, shape_critic_state_dict, lr=disc_lr, chunk=chunk,
                                      w_shape=w_shape)
         self.has_shape = shape_critic_state_dict is not None

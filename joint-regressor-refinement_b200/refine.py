@@ -26,13 +26,15 @@ def shard_range(n_frames: int, rank: int, world: int):
 class PoseRefiner:
     def __init__(self, smpl, J_regressor, critic_state_dict=None, mask=None, lr=1e-2,
                  w_joint=10000.0, w_pose=10.0, chunk=4096, use_graph=True, shape_critic_state_dict=None,
-                 w_shape=10.0):
+                 w_shape=10.0, loss_path=None):
         self.native: NativeModel = smpl.native() if hasattr(smpl, "native") else smpl
         self.device = self.native.device
         self.lr, self.w_joint = float(lr), float(w_joint)
         self.w_pose = float(w_pose) if critic_state_dict is not None else 0.0
         self.chunk = int(chunk)
         self.use_graph = use_graph
+        if loss_path is not None:
+            self.native.set_loss_path(loss_path)
         self.set_regressor(J_regressor, mask)
         if critic_state_dict is not None:
             self.native.load_critic(critic_state_dict)

@@ -761,3 +761,94 @@ def test_refinement_loop_two_batches_match_oracle_composition(smpl_tc, jrr, orac
         smpl_tc.native().load_shape_critic(None)
         smpl_tc.native().load_critic(critic_sd)
         smpl_tc.native().set_regressor(J_shipped.to(DEV))
+
+
+# ------------------------------------------------------------------ folded loss path (jrr_set_loss_path)
+@pytest.mark.parametrize("which", ["shipped", "dense"])
+def test_folded_loss_path_single_step(which, smpl_tc, jrr, oracle, osmpl64, critic_sd, J_shipped, J_dense):
+    """One Adam step through the folded operator T = Jhat o skinning o blend: gradients against the fp64
+    oracle and against the per-vertex kernels; same losses."""
+    J = J_shipped if which == "shipped" else J_dense
+    n = 300
+    fr = make_frames(jrr, oracle, oracle.OracleSMPL(jrr.synthetic.make_smpl_model(0)), J, n, 61)
+    sd64 = {k: v.double() for k, v in critic_sd.items()}
+    x6 = fr["x6"].double().requires_grad_(True)
+    be = fr["betas"].double().requires_grad_(True)
+    total, jl, pl, _ = oracle.refine_loss(osmpl64, J.double(), sd64, x6, be, fr["gt_mm"].double())
+    total.backward()
+    gall = torch.cat([x6.grad.reshape(n, 144), be.grad], dim=1)
+    res = {}
+    try:
+        for path in ("vertex", "folded"):
+            ref = jrr.PoseRefiner(smpl_tc, J, critic_sd, use_graph=False, loss_path=path)
+            st = ref._buffers(n)
+            st["x6"].copy_(fr["x6"]); st["betas"].copy_(fr["betas"]); st["gt"].copy_(fr["gt_mm"])
+            ref._run_chunk(st, 1, n)
+            torch.cuda.synchronize()
+            res[path] = (st["m"].cpu().double() * 10, st["loss"].cpu().double(), ref.launches_per_step)
+    finally:
+        smpl_tc.native().set_loss_path("vertex")
+    gf, lf, nf = res["folded"]
+    gv, lv, nv = res["vertex"]
+    err_o = (gf - gall).abs().max().item() / gall.abs().max().item()
+    err_v = (gf - gv).abs().max().item() / gv.abs().max().item()
+    print(f"[{which}] folded path: gradient rel err vs fp64 oracle {err_o:.2e}, vs per-vertex kernels {err_v:.2e}; "
+          f"launches per step {nf} vs {nv}")
+    assert err_o < 1e-4 and err_v < 2e-5
+    assert abs(lf[1] - jl.item()) / jl.item() < 1e-5 and abs(lf[0] - total.item()) / total.item() < 1e-5
+    assert abs(lf[0] - lv[0]) / lv[0] < 1e-6
+
+
+def test_folded_loss_path_100_iterations_and_all_terms(smpl_tc, jrr, oracle, osmpl32, critic_sd, J_shipped, frames64):
+    fr = frames64
+    x6o, bo, hist = _oracle_refine(oracle, osmpl32, J_shipped, critic_sd, fr, 100)
+    try:
+        ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, loss_path="folded")
+        x6 = fr["x6"].to(DEV).clone(); be = fr["betas"].to(DEV).clone()
+        loss = ref.refine(x6, be, fr["gt_mm"].to(DEV), iters=100)
+        pred_o = oracle.find_joints(osmpl32, bo, *(lambda R: (R[:, :1], R[:, 1:]))(oracle.rot6d_to_rotmat(x6o.reshape(-1, 6)).view(-1, 24, 3, 3)), J_shipped)
+        m_o, _ = oracle.evaluate(pred_o, fr["gt_mm"])
+        R = oracle.rot6d_to_rotmat(x6.cpu().reshape(-1, 6)).view(-1, 24, 3, 3)
+        m_c, _ = oracle.evaluate(oracle.find_joints(osmpl32, be.cpu(), R[:, :1], R[:, 1:], J_shipped), fr["gt_mm"])
+        print(f"folded path, 100 iterations: MPJPE oracle {m_o:.4f} mm, cuda {m_c:.4f} mm")
+        assert abs(m_o - m_c) < 0.01
+        assert abs(loss[0].item() - hist[-1][0]) / hist[-1][0] < 1e-3
+        # 2-D term + camera group + shape critic through the folded seed kernel
+        fr2, gt2d, cam0 = _cam_problem(jrr, oracle, osmpl32, J_shipped, 40, 9)
+        ssd = oracle.make_shape_critic_state_dict(5)
+        x6o, bo, co, hist = oracle.refine_2d(osmpl32, J_shipped, critic_sd, fr2["x6"], fr2["betas"], cam0, fr2["gt_mm"], gt2d,
+                                             iters=3, shape_sd=ssd, w_shape=10.0)
+        ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, use_graph=False, shape_critic_state_dict=ssd, loss_path="folded")
+        x6, be, cam = fr2["x6"].to(DEV).clone(), fr2["betas"].to(DEV).clone(), cam0.to(DEV).clone()
+        loss = ref.refine_2d(x6, be, cam, fr2["gt_mm"].to(DEV), gt2d.to(DEV), iters=3)
+        assert (x6.cpu() - x6o).abs().max().item() < 2e-4 and (be.cpu() - bo).abs().max().item() < 2e-4
+        assert (cam.cpu() - co).abs().max().item() < 2e-4
+        assert abs(loss[0].item() - hist[-1][0]) / hist[-1][0] < 1e-4
+    finally:
+        smpl_tc.native().load_shape_critic(None)
+        smpl_tc.native().set_loss_path("vertex")
+
+
+def test_folded_loss_path_follows_the_refit(smpl_tc, jrr, oracle, osmpl32, critic_sd, J_shipped):
+    """The folded operator is rebuilt inside jrr_regressor_apply / jrr_set_regressor: the whole per-batch loop on
+    the folded path against the oracle composition (second batch runs with the refitted regressor)."""
+    n, ref_it = 48, 4
+    loop = jrr.RefinementLoop(smpl_tc, J_shipped, critic_sd, None, refine_iters=ref_it, loss_path="folded")
+    A = oracle.CriticAdam(critic_sd, oracle.critic_train_loss, lr=1e-3)
+    RA = oracle.RegressorAdam(J_shipped, lr=1e-2)
+    J_o = J_shipped.clone()
+    try:
+        for bi in range(2):
+            fr = make_frames(jrr, oracle, osmpl32, J_shipped, n, 70 + bi)
+            out = loop.run_batch({"orient": fr["x6"][:, :1], "pose": fr["x6"][:, 1:], "betas": fr["betas"], "gt_j3d": fr["gt_mm"]})
+            x6o, bo, hist = oracle.refine(osmpl32, J_o, A.state_dict(), fr["x6"], fr["betas"], oracle.move_pelvis(fr["gt_mm"]), iters=ref_it)
+            A.step(x6o, fr["x6"])
+            g, _ = oracle.regressor_grad(osmpl32, J_o, x6o, bo, oracle.move_pelvis(fr["gt_mm"]))
+            J_o = RA.step(g)
+            assert (out["x6"].cpu() - x6o).abs().max().item() < 5e-4, bi
+            assert abs(out["refine_loss"][0].item() - hist[-1][0]) / hist[-1][0] < 1e-3, bi
+            assert (loop.refit.J_regressor.cpu() - J_o).abs().max().item() < 1e-4, bi
+    finally:
+        smpl_tc.native().set_loss_path("vertex")
+        smpl_tc.native().load_critic(critic_sd)
+        smpl_tc.native().set_regressor(J_shipped.to(DEV))
