@@ -174,7 +174,7 @@ def main():
                     help="dense 17x6890 (headline: the full reduction) or the shipped sparse artefact")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-impl", type=int, default=0)
-    ap.add_argument("--loss-path", default="vertex", choices=["vertex", "folded"],
+    ap.add_argument("--loss-path", default="folded", choices=["vertex", "folded"],
                     help="vertex: per-vertex fused kernels (blend GEMM + skinning + 17x6890 reduction, the path SURVEY.md 8a "
                          "names); folded: regressor o skinning o blend operator folded per regressor version (include/jrr.h)")
     args = ap.parse_args()
@@ -351,9 +351,13 @@ def main():
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["dram_bytes_per_launch"]
         if dom is not None and B == FRAMES and args.regressor == "dense":
-            key = "fused_bwd_kernel" if dom["name"].startswith("fused_bwd") else \
-                  "fused_fwd_kernel" if dom["name"].startswith("fused_fwd") else None
-            traffic = tj.get(key) if key else None
+            # the kernel group's launches as named in the ncu capture (sum of their DRAM bytes)
+            group = {"fused_bwd": ["fused_bwd_kernel"], "fused_fwd": ["fused_fwd_kernel<1>"],
+                     "critic_gemm_fwd": ["gemm_tc_kernel<128, 1, 1>", "gemm_tc_kernel<128, 4, 1>"],
+                     "critic_gemm_bwd": ["gemm_tc_kernel<128, 2, 1>", "gemm_tc_kernel<96, 3, 1>"]}
+            names = next((v for k, v in group.items() if dom["name"].startswith(k)), None)
+            if names and all(n in tj for n in names):
+                traffic = sum(tj[n] for n in names)
     except Exception:
         traffic = None
     roofline = None
@@ -388,6 +392,7 @@ def main():
 
     # ---------------------------------------------------------------- the other loss-path formulation, same run
     other = "folded" if not folded else "vertex"
+    main_launches = refiner.launches_per_step
     refiner.native.set_loss_path(other)
     refiner.set_regressor(J)
     st["x6"].copy_(x6_pin); st["betas"].copy_(be_pin)
@@ -435,7 +440,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K + 12,
                     "note": "one user call: pinned-host x6/betas/gt -> device, K steps (loss read back every step), refined x6/betas -> pinned host"},
-            "gpu_launches": refiner.launches_per_step * K,
+            "gpu_launches": main_launches * K,
             "roofline": roofline, "kernels": kern, "whole_step": whole,
             "quality": {"mpjpe_initial_mm": round(float(mp0), 3), "mpjpe_after_mm": round(float(mpjpe), 3),
                         "pa_mpjpe_after_mm": round(float(pampjpe), 3), "iterations": K},

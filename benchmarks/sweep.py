@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--frames", type=int, default=312000)
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--max-log2", type=int, default=16)
+    ap.add_argument("--loss-path", default="folded", choices=["vertex", "folded"])
     args = ap.parse_args()
     only = set(args.only.split(","))
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -118,7 +119,7 @@ def main():
         x6 = torch.from_numpy(inp["x6"]).to(dev).contiguous()
         be = torch.from_numpy(inp["betas"]).to(dev).contiguous()
         del R, tb
-        refiner = jrr.PoseRefiner(smpl, J, sd, chunk=4096)
+        refiner = jrr.PoseRefiner(smpl, J, sd, chunk=4096, loss_path=args.loss_path)
 
         def mpjpe():
             tot, cnt = 0.0, 0
@@ -147,7 +148,7 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             mp1 = mpjpe()
             emit({"config": "C3", "workload": f"{args.frames} frames x {args.iters} Adam iterations, chunk 4096 (ragged tail), "
-                  f"frame-sharded over {world} GPU(s), no collective", "n_gpus": world, "seconds": round(t.item() / 1e3, 3),
+                  f"frame-sharded over {world} GPU(s), no collective", "loss_path": args.loss_path, "n_gpus": world, "seconds": round(t.item() / 1e3, 3),
                   "pose_steps_per_s": round(args.frames * args.iters / (t.item() / 1e3), 1),
                   "mpjpe_before_mm_rank0": round(mp0, 3), "mpjpe_after_mm_rank0": round(mp1, 3)})
         if "c4" in only:
@@ -203,7 +204,7 @@ def main():
         gt2d = 112 + 40 * torch.randn(B, 17, 2, device=dev)
         torch.manual_seed(1)
         ssd = jrr.Shape_Discriminator().state_dict()
-        loop = jrr.RefinementLoop(smpl, J, sd, ssd)
+        loop = jrr.RefinementLoop(smpl, J, sd, ssd, loss_path=args.loss_path)
         cam0 = torch.tensor([0.0, 0.0, 40.0], device=dev).repeat(B, 1)
         batch = {"orient": x6[:, :1], "pose": x6[:, 1:], "betas": be, "gt_j3d": gt, "gt_j2d": gt2d, "cam": cam0}
         loop.run_batch(batch)                                           # warm-up (module loading, graphs)
@@ -226,7 +227,7 @@ def main():
         tot = ev[0].elapsed_time(ev[4])
         emit({"config": "per_batch_loop", "workload": "optimize.py:150-312 on one 4096-frame batch (no SPIN inference, no "
               "silhouette term): camera fit, refinement (eager launches: the 2-D variant is not graph-captured), critic + "
-              "shape-critic training step, regressor refit", **ms, "total_ms": round(tot, 3),
+              "shape-critic training step, regressor refit", "loss_path": args.loss_path, **ms, "total_ms": round(tot, 3),
               "frames_per_s": round(B / tot * 1e3, 1)})
 
     if "c5" in only and rank == 0:

@@ -68,6 +68,8 @@ Workspace carve(const JrrModel* m, int64_t B, void* base) {
   w.zg_part = take(BP * (C_Z / 128));
   w.dzg = take(BP);
   w.cmask = reinterpret_cast<uint2*>(take(BP * NJ * 2));
+  w.gx6 = take(BP * 144);
+  w.gbetas = take(BP * NB);
   w.scores = take(BP * 25);
   w.bytes = off;
   return w;
@@ -328,13 +330,21 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   if (inl) if (int rc = launch_critic_post(m, w, x6, st)) return rc;
   if (shape && !fork) if (int rc = launch_shape_critic(m, w, betas, B_logical, st)) return rc;
   JRR_MARK();
+  // With the critic on its own branch, the chain backward does not have to wait for it: it leaves the
+  // parameter gradients in the workspace and an element-wise Adam kernel runs after the join.
+  const bool split = fork && m->split_adam;
+  if (split)
+    if (int rc = launch_pose_bwd(m, w, betas, x6, JRR_POSE_ROT6D, false, false, false, w.gbetas, w.gx6, nullptr, nullptr,
+                                 nullptr, nullptr, nullptr, 0.f, st)) return rc;
   if (fork) JRR_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
   if (loss_out)
     if (int rc = launch_loss_finish(w, B_logical, w_joint, w_pose, critic, w_2d, shape ? m->w_shape : 0.f, loss_out, nullptr, st)) return rc;
   JRR_MARK();
   // chain backward + Adam
-  if (int rc = launch_pose_bwd(m, w, betas, x6, JRR_POSE_ROT6D, false, critic, shape, nullptr, nullptr, x6, betas,
-                               adam_m, adam_v, step_count, lr, st)) return rc;
+  if (split) {
+    if (int rc = launch_adam_params(w, critic, shape, x6, betas, adam_m, adam_v, step_count, lr, st)) return rc;
+  } else if (int rc = launch_pose_bwd(m, w, betas, x6, JRR_POSE_ROT6D, false, critic, shape, nullptr, nullptr, x6, betas,
+                                      adam_m, adam_v, step_count, lr, st)) return rc;
   JRR_MARK();
 #undef JRR_MARK
   return JRR_OK;

@@ -171,6 +171,7 @@ struct JrrModel {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_critic = true;
+  bool split_adam = true;                    // chain backward beside the critic branch, element-wise Adam after the join
   bool critic_ss = true;                     // critic GEMMs of the refine step: plain fp32 activations staged through tensor
                                              // memory (JRR_CRITIC_SS=0: pre-split activations through shared memory)
   bool critic_head_fused = true;             // global critic head inside the layer-2 GEMM epilogue (refine step)
@@ -224,6 +225,8 @@ struct Workspace {
   float* zg_part;          // [8][BP]    global-head logit partials per 128-column tile of layer 2
   float* dzg;              // [BP]       dL/d(global logit)
   uint2* cmask;            // [BP][24]   ReLU masks of the critic's two 1x1 convs (pre -> post)
+  float* gx6;              // [BP][144]  parameter gradients of the chain backward (split-Adam schedule)
+  float* gbetas;           // [BP][10]
   float* scores;           // [BP][25]
   size_t bytes;
 };
@@ -270,6 +273,8 @@ struct Proj2D {
 int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int64_t B_logical, float w_joint,
                        float* joints17_out, const Proj2D& p2d, cudaStream_t st);
 int launch_fold(JrrModel* m, cudaStream_t st);
+int launch_adam_params(const Workspace& w, bool use_critic, bool use_shape, float* x6, float* betas, float* adam_m,
+                       float* adam_v, int32_t* step_count, float lr, cudaStream_t st);
 int launch_loss_seed(const JrrModel* m, Workspace& w, bool fused_partials, const float* gt_mm,
                      int64_t B_logical, float w_joint, float* joints17_out, const Proj2D& p2d, cudaStream_t st);
 int launch_camera_fit(const Workspace& w, const float* joints17, const float* gt2d, float* cam, int iters, float lr,

@@ -528,6 +528,7 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   if (const char* e = getenv("JRR_COMPACT_ACTIVE")) m->compact_active = (e[0] != '0');
   if (const char* e = getenv("JRR_CRITIC_HEAD_FUSED")) m->critic_head_fused = (e[0] != '0');
   if (const char* e = getenv("JRR_CRITIC_SS")) m->critic_ss = (e[0] != '0');
+  if (const char* e = getenv("JRR_SPLIT_ADAM")) m->split_adam = (e[0] != '0');
   if (const char* e = getenv("JRR_LOSS_PATH")) m->folded = (e[0] == 'f' || e[0] == '1') && m->gemm_impl == 0;
   if (m->gemm_impl != 0) { m->fused_fwd = false; m->fused_bwd = false; m->critic_head_fused = false; }
   if (!m->critic_head_fused) m->critic_ss = false;

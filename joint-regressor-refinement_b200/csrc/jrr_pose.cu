@@ -403,7 +403,53 @@ pose_bwd_kernel(const __grid_constant__ ChainTab tab, const float* __restrict__ 
 
 __global__ void bump_step_kernel(int32_t* step_count) { *step_count += 1; }
 
+// Adam step on the parameter gradients left by pose_bwd_kernel<ROT6D, false> plus the critics' input
+// gradients: lets the chain backward run beside the critic branch, only this element-wise kernel
+// waits for it.  Same arithmetic, in the same order, as the fused Adam of pose_bwd_kernel.
+__global__ void __launch_bounds__(256)
+adam_params_kernel(const float* __restrict__ gx6, const float* __restrict__ gbetas, const float* __restrict__ dx6c,
+                   const float* __restrict__ dbeta_s, int64_t B, float* __restrict__ x6, float* __restrict__ betas,
+                   float* __restrict__ adam_m, float* __restrict__ adam_v, const int32_t* __restrict__ step_count,
+                   float lr) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * NPARAM) return;
+  const int64_t b = idx / NPARAM;
+  const int p = (int)(idx - b * NPARAM);
+  float g;
+  float* prm;
+  if (p < 144) {
+    g = gx6[b * 144 + p] + (dx6c != nullptr ? dx6c[b * 144 + p] : 0.f);
+    prm = x6 + b * 144 + p;
+  } else {
+    g = gbetas[b * NB + (p - 144)];
+    if (dbeta_s != nullptr) g += dbeta_s[b * NB + (p - 144)];
+    prm = betas + b * NB + (p - 144);
+  }
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  const int t = *step_count + 1;
+  const float bc2s = (float)sqrt(1.0 - pow(0.999, (double)t));
+  const float step = (float)((double)lr / (1.0 - pow(0.9, (double)t)));
+  const float m = b1 * adam_m[idx] + (1.f - b1) * g;
+  const float v = b2 * adam_v[idx] + (1.f - b2) * g * g;
+  adam_m[idx] = m;
+  adam_v[idx] = v;
+  const float denom = sqrtf(v) / bc2s + eps;
+  *prm = *prm - step * (m / denom);
+}
+
 // ---- host wrappers ---------------------------------------------------------------------------
+int launch_adam_params(const Workspace& w, bool use_critic, bool use_shape, float* x6, float* betas, float* adam_m,
+                       float* adam_v, int32_t* step_count, float lr, cudaStream_t st) {
+  const int64_t n = w.B * NPARAM;
+  adam_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.gx6, w.gbetas, use_critic ? w.dx6c : nullptr,
+                                                                 use_shape ? w.dbeta_s : nullptr, w.B, x6, betas, adam_m,
+                                                                 adam_v, step_count, lr);
+  JRR_LAUNCH_CHECK();
+  bump_step_kernel<<<1, 1, 0, st>>>(step_count);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
 int launch_pose_fwd(const JrrModel* m, int64_t B, int64_t BP, const float* betas, const float* pose,
                     int kind, float* AT, float* feat_hi, float* feat_lo, float* Jp, cudaStream_t st) {
   dim3 grid((unsigned)(BP / POSES_PER_CTA)), block(POSES_PER_CTA * 32);

@@ -60,42 +60,43 @@ def launches():
 
 
 def top_kernels():
-    rep = os.path.join(SRC, f"{TAG}_prof.ncu-rep")
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-    ki = hdr.index("Kernel Name")
-    out = ["ncu --set full --clock-control none --import-source on -k regex:'fused_bwd|fused_fwd|gemm_tc_kernel<128, 1' "
-           "-s 30 -c 6 python bench.py --steps 3 --warmup 3 --no-cpu-baseline",
-           "(first captured launch of each kernel; B = 4096 poses, dense 17x6890 regressor; times under ncu are cold-cache and serialised)", ""]
-    seen = set()
-    for r in rows[2:]:
-        name = short(r[ki])
-        if name in seen:
-            continue
-        seen.add(name)
-        out.append(f"== {name}")
-        for w in WANT:
-            if w in hdr:
-                i = hdr.index(w)
-                out.append(f"   {w:95s} {r[i]:>18s} {units[i]}")
-        out.append("")
-    open(os.path.join(DST, f"{TAG}_ncu_top_kernels.txt"), "w").write("\n".join(out))
-    # per-launch DRAM traffic of each captured kernel, read by bench.py for roofline.traffic
     import json
+    out = ["ncu --set full --clock-control none --import-source on -k regex:'folded_seed|gemm_tc_kernel' -s 42 -c 14 "
+           "python bench.py --steps 3 --warmup 3 --no-cpu-baseline",
+           "ncu --set full ... -k regex:'fused_bwd|fused_fwd' -s 30 -c 4 python bench.py --loss-path vertex --steps 3 --warmup 3 --no-cpu-baseline",
+           "(first captured launch of each kernel; B = 4096 poses, dense 17x6890 regressor; times under ncu are cold-cache and serialised)", ""]
     traffic = {}
-    ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    for r in rows[2:]:
-        name = short(r[ki]).split("<")[0]
-        if name not in traffic:
+    for tag in (f"{TAG}_prof", f"{TAG}_prof_vertex"):
+        rep = os.path.join(SRC, tag + ".ncu-rep")
+        if not os.path.exists(rep):
+            continue
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        ki = hdr.index("Kernel Name")
+        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        seen = set()
+        for r in rows[2:]:
+            name = short(r[ki])
+            if name in seen:
+                continue
+            seen.add(name)
+            out.append(f"== {name}")
+            for w in WANT:
+                if w in hdr:
+                    i = hdr.index(w)
+                    out.append(f"   {w:95s} {r[i]:>18s} {units[i]}")
+            out.append("")
+            # per-launch DRAM traffic of each captured kernel, read by bench.py for roofline.traffic
             traffic[name] = float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
+    open(os.path.join(DST, f"{TAG}_ncu_top_kernels.txt"), "w").write("\n".join(out))
     json.dump({"source": f"profiles/{TAG}_ncu_top_kernels.txt (ncu --set full, B = 4096, dense regressor)",
                "dram_bytes_per_launch": traffic}, open(os.path.join(DST, "ncu_traffic.json"), "w"), indent=1)
 
 
 def main():
-    for f in (f"{TAG}_bench.json", f"{TAG}_bench_shipped.json", f"{TAG}_bench_reference.json", f"{TAG}_gpu_tests.txt",
+    for f in (f"{TAG}_bench.json", f"{TAG}_bench_vertex.json", f"{TAG}_bench_shipped.json", f"{TAG}_bench_reference.json", f"{TAG}_gpu_tests.txt",
               f"{TAG}_sweep.jsonl", f"{TAG}_memcheck.txt", f"{TAG}_bench_2gpu.json"):
         p = os.path.join(SRC, f)
         if os.path.exists(p):
