@@ -183,11 +183,16 @@ __global__ void sum_scale_add_kernel(const float* __restrict__ parts, int n, flo
 __global__ void __launch_bounds__(256)
 adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ am, float* __restrict__ av,
                  const int32_t* __restrict__ step_count, float lr, int64_t n) {
+  __shared__ float s_bc[2];      // double-precision bias corrections, once per block
+  if (threadIdx.x == 0) {
+    const int t = *step_count + 1;
+    s_bc[0] = (float)sqrt(1.0 - pow(0.999, (double)t));
+    s_bc[1] = (float)((double)lr / (1.0 - pow(0.9, (double)t)));
+  }
+  __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int t = *step_count + 1;
-  const float bc2s = (float)sqrt(1.0 - pow(0.999, (double)t));
-  const float step = (float)((double)lr / (1.0 - pow(0.9, (double)t)));
+  const float bc2s = s_bc[0], step = s_bc[1];
   const float gi = g[i];
   const float m = 0.9f * am[i] + 0.1f * gi;
   const float v = 0.999f * av[i] + 0.001f * gi * gi;

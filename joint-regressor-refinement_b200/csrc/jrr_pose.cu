@@ -411,6 +411,14 @@ adam_params_kernel(const float* __restrict__ gx6, const float* __restrict__ gbet
                    const float* __restrict__ dbeta_s, int64_t B, float* __restrict__ x6, float* __restrict__ betas,
                    float* __restrict__ adam_m, float* __restrict__ adam_v, const int32_t* __restrict__ step_count,
                    float lr) {
+  // bias corrections in double like torch.optim.Adam's Python scalars: once per block, not per element
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const int t0 = *step_count + 1;
+    s_bc[0] = (float)sqrt(1.0 - pow(0.999, (double)t0));
+    s_bc[1] = (float)((double)lr / (1.0 - pow(0.9, (double)t0)));
+  }
+  __syncthreads();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * NPARAM) return;
   const int64_t b = idx / NPARAM;
@@ -426,9 +434,7 @@ adam_params_kernel(const float* __restrict__ gx6, const float* __restrict__ gbet
     prm = betas + b * NB + (p - 144);
   }
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
-  const int t = *step_count + 1;
-  const float bc2s = (float)sqrt(1.0 - pow(0.999, (double)t));
-  const float step = (float)((double)lr / (1.0 - pow(0.9, (double)t)));
+  const float bc2s = s_bc[0], step = s_bc[1];
   const float m = b1 * adam_m[idx] + (1.f - b1) * g;
   const float v = b2 * adam_v[idx] + (1.f - b2) * g * g;
   adam_m[idx] = m;
