@@ -19,9 +19,16 @@ __global__ void __launch_bounds__(256)
 critic_pre_kernel(const float* __restrict__ cs, const float* __restrict__ x6, int64_t B, int64_t BP,
                   float* __restrict__ h_hi, float* __restrict__ h_lo, float* __restrict__ zj_out,
                   uint2* __restrict__ masks_out) {
-  __shared__ float sw[CS_HW];
+  // conv weights TRANSPOSED in shared memory ([input][output]): the inner loops then run over 32 independent
+  // accumulators (one broadcast LDS.128 feeds four of them) instead of one 32-deep dependent chain per output;
+  // every output still sums bias, k = 0, 1, ... in the same order
+  __shared__ __align__(16) float sw1t[6 * 32];
+  __shared__ __align__(16) float sw2t[32 * 32];
+  __shared__ float sb[64];
   __shared__ float shw[NJ * 33];     // joint-head weights, row stride 33: lanes hold different joints
-  for (int i = threadIdx.x; i < CS_HW; i += blockDim.x) sw[i] = cs[i];
+  for (int i = threadIdx.x; i < 192; i += blockDim.x) sw1t[(i % 6) * 32 + i / 6] = cs[CS_C1W + i];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sw2t[(i & 31) * 32 + (i >> 5)] = cs[CS_C2W + i];
+  if (threadIdx.x < 32) { sb[threadIdx.x] = cs[CS_C1B + threadIdx.x]; sb[32 + threadIdx.x] = cs[CS_C2B + threadIdx.x]; }
   if (zj_out != nullptr)
     for (int i = threadIdx.x; i < NJ * 32; i += blockDim.x) shw[(i >> 5) * 33 + (i & 31)] = cs[CS_HW + i];
   __syncthreads();
@@ -35,20 +42,26 @@ critic_pre_kernel(const float* __restrict__ cs, const float* __restrict__ x6, in
     for (int i = 0; i < 6; i++) x[i] = x6[idx * 6 + i];
     float h1[32];
 #pragma unroll
+    for (int k = 0; k < 32; k++) h1[k] = sb[k];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int k = 0; k < 32; k++) h1[k] = fmaf(sw1t[i * 32 + k], x[i], h1[k]);
+#pragma unroll
     for (int k = 0; k < 32; k++) {
-      float a = sw[CS_C1B + k];
-#pragma unroll
-      for (int i = 0; i < 6; i++) a = fmaf(sw[CS_C1W + k * 6 + i], x[i], a);
-      h1[k] = fmaxf(a, 0.f);
-      m1 |= (a > 0.f ? 1u : 0u) << k;
+      m1 |= (h1[k] > 0.f ? 1u : 0u) << k;
+      h1[k] = fmaxf(h1[k], 0.f);
     }
-#pragma unroll 4
-    for (int c = 0; c < 32; c++) {
-      float a = sw[CS_C2B + c];
 #pragma unroll
-      for (int k = 0; k < 32; k++) a = fmaf(sw[CS_C2W + c * 32 + k], h1[k], a);
-      h2[c] = fmaxf(a, 0.f);
-      m2 |= (a > 0.f ? 1u : 0u) << c;
+    for (int c = 0; c < 32; c++) h2[c] = sb[32 + c];
+#pragma unroll
+    for (int k = 0; k < 32; k++)
+#pragma unroll
+      for (int c = 0; c < 32; c++) h2[c] = fmaf(sw2t[k * 32 + c], h1[k], h2[c]);
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+      m2 |= (h2[c] > 0.f ? 1u : 0u) << c;
+      h2[c] = fmaxf(h2[c], 0.f);
     }
   } else {
 #pragma unroll
