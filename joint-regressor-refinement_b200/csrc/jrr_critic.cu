@@ -376,8 +376,10 @@ int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st,
   g.B_hi = m->W1_hi; g.B_lo = m->W1_lo; g.ldb = C_H;
   g.M = w.BP; g.N = C_Z; g.K = C_H; g.ksplit = 1; g.epi = EPI_BIAS_RELU_SPLIT;
   g.out0 = w.z1_hi; g.out1 = w.z1_lo; g.ldo = C_Z; g.bias = m->critic_small + CS_B1;
+  g.mask_bits_out = ss ? w.zmask : nullptr;      // layer-1 ReLU mask for the backward epilogue
   int rc = launch_gemm(m, g, st);
   if (rc) return rc;
+  g.mask_bits_out = nullptr;
   g.A_hi = w.z1_hi; g.A_lo = w.z1_lo; g.lda = C_Z;
   g.B_hi = m->W2_hi; g.B_lo = m->W2_lo; g.ldb = C_Z;
   g.K = C_Z; g.out0 = w.z2_hi; g.out1 = w.z2_lo; g.bias = m->critic_small + CS_B2;
@@ -399,8 +401,10 @@ int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st
   g.B_hi = m->W2t_hi; g.B_lo = m->W2t_lo; g.ldb = C_Z;
   g.M = w.BP; g.N = C_Z; g.K = C_Z; g.ksplit = 1; g.epi = EPI_MASK_SPLIT;
   g.out0 = w.dz1_hi; g.out1 = w.dz1_lo; g.ldo = C_Z; g.mask = w.z1_hi; g.ldmask = C_Z;
+  g.mask_bits = ss ? w.zmask : nullptr;
   int rc = launch_gemm(m, g, st);
   if (rc) return rc;
+  g.mask_bits = nullptr;
   // dh = dz1 . W1
   g.A_hi = w.dz1_hi; g.A_lo = w.dz1_lo; g.lda = C_Z;
   g.B_hi = m->W1t_hi; g.B_lo = m->W1t_lo; g.ldb = C_Z;

@@ -31,6 +31,7 @@ struct TcParams {
   float* out0; float* out1; int64_t ldo;
   const float* bias;
   const float* mask; int64_t ldmask;
+  const uint32_t* mask_bits; uint32_t* mask_bits_out;   // ReLU masks as bits [M][N/32]
   const float* A; int64_t lda;   // SS: plain fp32 A
   const float* rowscale;   // EPI_MASK_SPLIT: multiply row m by rowscale[m] (or nullptr)
   const float* vec;        // EPI_BIAS_RELU_HEAD: w3[N]
@@ -262,11 +263,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         } else if (EPI == EPI_BIAS_RELU_SPLIT || EPI == EPI_MASK_SPLIT) {
           if (m < p.M && n0 < p.N) {
             float hi[32], lo[32];
+            // ReLU masks can travel as one bit per element (row m, word n0 / 32) between the layer's forward
+            // epilogue and the backward epilogue, instead of re-reading the fp32 activations
+            uint32_t bits = 0;
+            if (EPI == EPI_MASK_SPLIT && p.mask_bits != nullptr) bits = p.mask_bits[m * (p.N >> 5) + (n0 >> 5)];
 #pragma unroll
             for (int i = 0; i < 32; i++) {
               float x = v[i];
-              if (EPI == EPI_BIAS_RELU_SPLIT) x = fmaxf(x + __ldg(p.bias + n0 + i), 0.f);
-              else x = (p.mask[m * p.ldmask + n0 + i] > 0.f) ? x * rs : 0.f;
+              if (EPI == EPI_BIAS_RELU_SPLIT) {
+                x = fmaxf(x + __ldg(p.bias + n0 + i), 0.f);
+                bits |= (x > 0.f ? 1u : 0u) << i;
+              } else if (p.mask_bits != nullptr) {
+                x = ((bits >> i) & 1u) ? x * rs : 0.f;
+              } else {
+                x = (p.mask[m * p.ldmask + n0 + i] > 0.f) ? x * rs : 0.f;
+              }
               if (SS) {
                 hi[i] = x;
               } else {
@@ -274,6 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                 lo[i] = tf32_hi_g(x - hi[i]);
               }
             }
+            if (EPI == EPI_BIAS_RELU_SPLIT && p.mask_bits_out != nullptr) p.mask_bits_out[m * (p.N >> 5) + (n0 >> 5)] = bits;
             float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
 #pragma unroll
             for (int i = 0; i < 8; i++) oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
@@ -367,6 +379,7 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   p.out0 = g.out0; p.out1 = g.out1; p.ldo = g.ldo; p.bias = g.bias; p.mask = g.mask; p.ldmask = g.ldmask;
   p.rowscale = g.rowscale; p.vec = g.vec; p.out2 = g.out2;
   p.A = g.A_hi; p.lda = g.lda;
+  p.mask_bits = g.mask_bits; p.mask_bits_out = g.mask_bits_out;
   auto kern = gemm_tc_kernel<BN, EPI, SS>;
   constexpr int smem_bytes = SS ? Cfg::SMEM_BYTES_SS : Cfg::SMEM_BYTES;
   JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

@@ -225,6 +225,7 @@ struct Workspace {
   float* zg_part;          // [8][BP]    global-head logit partials per 128-column tile of layer 2
   float* dzg;              // [BP]       dL/d(global logit)
   uint2* cmask;            // [BP][24]   ReLU masks of the critic's two 1x1 convs (pre -> post)
+  uint32_t* zmask;         // [BP][32]   ReLU mask bits of the critic's first wide layer
   float* gx6;              // [BP][144]  parameter gradients of the chain backward (split-Adam schedule)
   float* gbetas;           // [BP][10]
   float* scores;           // [BP][25]
@@ -249,6 +250,8 @@ struct GemmDesc {
   const float* mask; int64_t ldmask;       // (EPI_MASK_SPLIT) multiply by (mask>0)
   const float* rowscale;                   // (EPI_MASK_SPLIT) and by rowscale[m] when given
   const float* vec; float* out2;           // (EPI_BIAS_RELU_HEAD) w3[N] in, logit partials [N/128][M] out
+  const uint32_t* mask_bits;               // (EPI_MASK_SPLIT) ReLU mask as bits [M][N/32] instead of `mask`
+  uint32_t* mask_bits_out;                 // (EPI_BIAS_RELU_SPLIT) also emit the ReLU mask as bits [M][N/32]
   int64_t k_valid;                         // > 0: only the first k_valid columns of A exist (TMA zero-fills the rest of K)
   bool smem_split;                         // A is plain fp32 (A_hi): loaded, tf32-split and staged in tensor memory by the
                                            // kernel (B stays pre-split); *_SPLIT epilogues then write ONE fp32 array (out0)
