@@ -169,7 +169,7 @@ struct JrrModel {
   float w_shape = 0.f;                       // weight of the shape-critic term in the refinement loss (optimize.py:253: 10)
   // the critic chain of a refinement step runs on a forked side stream (joins before Adam)
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_seed = nullptr, ev_join2 = nullptr;
   bool overlap_critic = true;
   bool split_adam = true;                    // chain backward beside the critic branch, element-wise Adam after the join
   bool critic_ss = true;                     // critic GEMMs of the refine step: plain fp32 activations staged through tensor

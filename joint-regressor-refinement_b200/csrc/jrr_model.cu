@@ -512,6 +512,8 @@ extern "C" int jrr_model_destroy(JrrModel* m) {
   if (m->side) cudaStreamDestroy(m->side);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
+  if (m->ev_seed) cudaEventDestroy(m->ev_seed);
+  if (m->ev_join2) cudaEventDestroy(m->ev_join2);
   delete m;
   return JRR_OK;
 }
@@ -685,6 +687,8 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   JRR_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
   JRR_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   JRR_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+  JRR_CUDA(cudaEventCreateWithFlags(&m->ev_seed, cudaEventDisableTiming));
+  JRR_CUDA(cudaEventCreateWithFlags(&m->ev_join2, cudaEventDisableTiming));
   JRR_CUDA(cudaDeviceSynchronize());
   return JRR_OK;
 }
