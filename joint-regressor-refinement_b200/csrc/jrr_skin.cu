@@ -342,19 +342,20 @@ loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T,
 //   backward  dA_j^R = sum_i g_i (x) q_ji,  dA_j^t = sum_i g_i c_ji,  dq_ji = A_j^R^T g_i
 // dQ rows leave through shared memory so that each pose's 51 values per joint are written contiguously.
 // Work split: 32 poses per CTA (lane = pose, so every load/store of the pose-contiguous arrays is one
-// 128-byte line), 4 warps x 6 joints each; the partial joints meet in shared memory in a fixed order.
+// 128-byte line), 8 warps x 3 joints each; the partial joints meet in shared memory in a fixed order.
 constexpr int FS_POSES = 32;
-constexpr int FS_WARPS = 4;
-constexpr int FS_JPW = NJ / FS_WARPS;          // 6 joints per warp
+constexpr int FS_WARPS = 8;
+constexpr int FS_JPW = NJ / FS_WARPS;          // 3 joints per warp
 constexpr int FS_LD = 53;                      // dq staging row (odd: conflict-free transposed access)
 __global__ void __launch_bounds__(FS_WARPS * 32)
 folded_seed_kernel(const float* __restrict__ QT, const float* __restrict__ AT, const float* __restrict__ Tc,
                    const float* __restrict__ gt_mm, int64_t B, int64_t BP, float scale, const Proj2D p2d,
                    float* __restrict__ loss_part, float* __restrict__ joints17_out, float* __restrict__ dAT,
                    float* __restrict__ dQ_hi, float* __restrict__ dQ_lo) {
-  __shared__ float sTc[NJ * NH];
-  __shared__ float sbuf[FS_WARPS * FS_POSES * FS_LD];    // forward: partial joints [warp][51][32]; backward: dq staging
-  __shared__ float sg[NACC * FS_POSES];                  // joints, then the loss seed g, [a][pose]
+  extern __shared__ float fs_smem[];
+  float* sbuf = fs_smem;                                   // forward: partial joints [warp][51][32]; backward: dq staging
+  float* sg = sbuf + FS_WARPS * FS_POSES * FS_LD;          // joints, then the loss seed g, [a][pose]
+  float* sTc = sg + NACC * FS_POSES;                       // [24][17]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b0 = (int64_t)blockIdx.x * FS_POSES, b = b0 + lane;
   for (int i = tid; i < NJ * NH; i += FS_WARPS * 32) sTc[i] = Tc[i];
@@ -989,7 +990,9 @@ int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int6
   const float scale = gt_mm != nullptr ? w_joint * 2.f / (51.f * (float)B_logical) : 0.f;
   const bool grad = gt_mm != nullptr;
   w.n_joint_part = (int)(w.BP / FS_POSES);
-  folded_seed_kernel<<<(unsigned)(w.BP / FS_POSES), FS_WARPS * 32, 0, st>>>(
+  constexpr int smem = (FS_WARPS * FS_POSES * FS_LD + NACC * FS_POSES + NJ * NH) * (int)sizeof(float);
+  JRR_CUDA(cudaFuncSetAttribute(folded_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  folded_seed_kernel<<<(unsigned)(w.BP / FS_POSES), FS_WARPS * 32, smem, st>>>(
       w.vpT, w.AT, m->Tc, gt_mm, w.B, w.BP, scale, p2d, w.loss_part, joints17_out, grad ? w.dAT : nullptr,
       grad ? w.dvp_hi : nullptr, grad ? w.dvp_lo : nullptr);
   JRR_LAUNCH_CHECK();
