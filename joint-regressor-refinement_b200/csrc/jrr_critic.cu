@@ -329,7 +329,7 @@ int launch_shape_critic_scores(const JrrModel* m, int64_t B, const float* betas,
 int launch_critic_pre(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st, bool want_zj) {
   const int64_t n = w.BP * NJ;
   critic_pre_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->critic_small, x6, w.B, w.BP,
-                                                                w.h_hi, (want_zj && m->critic_ss) ? nullptr : w.h_lo,
+                                                                w.h_hi, (want_zj && m->critic_ts) ? nullptr : w.h_lo,
                                                                 want_zj ? w.zj : nullptr, w.cmask);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
@@ -369,14 +369,14 @@ int launch_critic_post(const JrrModel* m, const Workspace& w, const float* x6, c
 // The four wide GEMMs around the small kernels.  head_fused: the second layer's epilogue also does
 // the global head (logit partials + its masked gradient row), see EPI_BIAS_RELU_HEAD.
 int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, bool head_fused) {
-  const bool ss = head_fused && m->critic_ss;    // plain fp32 activations, staged through tensor memory by the GEMM
+  const bool ts = head_fused && m->critic_ts;    // plain fp32 activations, staged through tensor memory by the GEMM
   GemmDesc g{};
-  g.smem_split = ss;
+  g.a_via_tmem = ts;
   g.A_hi = w.h_hi; g.A_lo = w.h_lo; g.lda = C_H;
   g.B_hi = m->W1_hi; g.B_lo = m->W1_lo; g.ldb = C_H;
   g.M = w.BP; g.N = C_Z; g.K = C_H; g.ksplit = 1; g.epi = EPI_BIAS_RELU_SPLIT;
   g.out0 = w.z1_hi; g.out1 = w.z1_lo; g.ldo = C_Z; g.bias = m->critic_small + CS_B1;
-  g.mask_bits_out = ss ? w.zmask : nullptr;      // layer-1 ReLU mask for the backward epilogue
+  g.mask_bits_out = ts ? w.zmask : nullptr;      // layer-1 ReLU mask for the backward epilogue
   int rc = launch_gemm(m, g, st);
   if (rc) return rc;
   g.mask_bits_out = nullptr;
@@ -392,16 +392,16 @@ int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st,
 }
 
 int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, const float* rowscale) {
-  const bool ss = rowscale != nullptr && m->critic_ss;
+  const bool ts = rowscale != nullptr && m->critic_ts;
   GemmDesc g{};
-  g.smem_split = ss;
+  g.a_via_tmem = ts;
   // dz1 = (dz2 . W2) * [z1 > 0]   (head_fused: dz2 rows still lack their scalar dL/dlogit = rowscale)
   g.rowscale = rowscale;
   g.A_hi = w.dz2_hi; g.A_lo = w.dz2_lo; g.lda = C_Z;
   g.B_hi = m->W2t_hi; g.B_lo = m->W2t_lo; g.ldb = C_Z;
   g.M = w.BP; g.N = C_Z; g.K = C_Z; g.ksplit = 1; g.epi = EPI_MASK_SPLIT;
   g.out0 = w.dz1_hi; g.out1 = w.dz1_lo; g.ldo = C_Z; g.mask = w.z1_hi; g.ldmask = C_Z;
-  g.mask_bits = ss ? w.zmask : nullptr;
+  g.mask_bits = ts ? w.zmask : nullptr;
   int rc = launch_gemm(m, g, st);
   if (rc) return rc;
   g.mask_bits = nullptr;

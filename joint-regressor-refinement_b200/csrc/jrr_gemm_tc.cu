@@ -22,7 +22,7 @@ namespace jrr {
 constexpr int BM = 128;
 constexpr int BK = 32;  // fp32 per stage row = 128 bytes = one swizzle atom
 constexpr int TC_THREADS = 192;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int TC_THREADS_SS = 320;       // + warps 6-9: A producers of the SS variant (smem fp32 tile -> registers -> TMEM)
+constexpr int TC_THREADS_TS = 320;       // + warps 6-9: A producers of the TS variant (smem fp32 tile -> registers -> TMEM)
 
 struct TcParams {
   int64_t M, N, K;     // K = per-split extent
@@ -32,7 +32,7 @@ struct TcParams {
   const float* bias;
   const float* mask; int64_t ldmask;
   const uint32_t* mask_bits; uint32_t* mask_bits_out;   // ReLU masks as bits [M][N/32]
-  const float* A; int64_t lda;   // SS: plain fp32 A
+  const float* A; int64_t lda;   // TS: plain fp32 A
   const float* rowscale;   // EPI_MASK_SPLIT: multiply row m by rowscale[m] (or nullptr)
   const float* vec;        // EPI_BIAS_RELU_HEAD: w3[N]
   float* out2;             // EPI_BIAS_RELU_HEAD: zg_part[n_tile][M]
@@ -46,30 +46,30 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int A_TMEM_COL = 2 * ACC_STRIDE;   // SS: A staging ring, 64 columns (hi 32 | lo 32) per stage
+  static constexpr int A_TMEM_COL = 2 * ACC_STRIDE;   // TS: A staging ring, 64 columns (hi 32 | lo 32) per stage
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int STAGES_SS = 4;                        // SS: [A raw][B_hi][B_lo] = 48 KB at BN = 128
-  static constexpr int STAGE_BYTES_SS = A_BYTES + 2 * B_BYTES;
-  static constexpr int SMEM_BYTES_SS = STAGES_SS * STAGE_BYTES_SS + 1024 + 256;
+  static constexpr int STAGES_TS = 4;                        // TS: [A raw][B_hi][B_lo] = 48 KB at BN = 128
+  static constexpr int STAGE_BYTES_TS = A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES_TS = STAGES_TS * STAGE_BYTES_TS + 1024 + 256;
 };
 
-// SS = false: both operands arrive pre-split through TMA (four tiles per stage) and are read from
+// TS = false: both operands arrive pre-split through TMA (four tiles per stage) and are read from
 // shared memory by the tensor core -- at 128x128 tiles the 3xTF32 scheme then reads 24 KB of operands
 // per 8-column K step and is bound by shared-memory bandwidth (~60 % of the tensor peak).
-// SS = true ("A through tensor memory"): A is a plain fp32 activation matrix.  TMA brings ONE raw tile
+// TS = true ("A through tensor memory"): A is a plain fp32 activation matrix.  TMA brings ONE raw tile
 // per stage; four producer warps (thread = row = TMEM lane) read their row, make the tf32 hi/lo pair
 // in registers and tcgen05.st it into a TMEM staging ring; the MMAs take A from TMEM and only B (the
 // pre-split weights) from shared memory.  Shared-memory traffic per K block drops from 160 KB to
 // 112 KB, the activations' L2/HBM traffic halves, and every epilogue writes a single fp32 array.
-template <int BN, int EPI, bool SS>
-__global__ void __launch_bounds__(SS ? TC_THREADS_SS : TC_THREADS, 1)
+template <int BN, int EPI, bool TS>
+__global__ void __launch_bounds__(TS ? TC_THREADS_TS : TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                const TcParams p) {
   using Cfg = TcCfg<BN>;
-  constexpr int STAGES = SS ? Cfg::STAGES_SS : Cfg::STAGES;
-  constexpr int STAGE_BYTES = SS ? Cfg::STAGE_BYTES_SS : Cfg::STAGE_BYTES;
-  constexpr int B_OFF = SS ? Cfg::A_BYTES : 2 * Cfg::A_BYTES;    // SS: one raw A tile, then B_hi, B_lo
+  constexpr int STAGES = TS ? Cfg::STAGES_TS : Cfg::STAGES;
+  constexpr int STAGE_BYTES = TS ? Cfg::STAGE_BYTES_TS : Cfg::STAGE_BYTES;
+  constexpr int B_OFF = TS ? Cfg::A_BYTES : 2 * Cfg::A_BYTES;    // TS: one raw A tile, then B_hi, B_lo
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -77,7 +77,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint64_t* ready_bar = bars + 2 * STAGES + 4;   // [STAGES] splitters -> MMA (SS)
+  uint64_t* ready_bar = bars + 2 * STAGES + 4;   // [STAGES] splitters -> MMA (TS)
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,7 +96,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(SS ? 512 : Cfg::TMEM_COLS));
+                 "n"(TS ? 512 : Cfg::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -119,7 +119,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           const int kc = (int)(split * p.K) + kb * BK;
           tma_load_2d(&mapAh, &full_bar[stage], sa, kc, mb * BM);
-          if (!SS) tma_load_2d(&mapAl, &full_bar[stage], sa + Cfg::A_BYTES, kc, mb * BM);
+          if (!TS) tma_load_2d(&mapAl, &full_bar[stage], sa + Cfg::A_BYTES, kc, mb * BM);
           tma_load_2d(&mapBh, &full_bar[stage], sa + B_OFF, kc, nb * BN);
           tma_load_2d(&mapBl, &full_bar[stage], sa + B_OFF + Cfg::B_BYTES, kc, nb * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -142,18 +142,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
       for (int kb = 0; kb < num_kb; kb++) {
         if (lane == 0) {
-          mbar_wait(SS ? &ready_bar[stage] : &full_bar[stage], phase);   // SS: the producers waited for the TMA
+          mbar_wait(TS ? &ready_bar[stage] : &full_bar[stage], phase);   // TS: the producers waited for the TMA
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t dAh = make_sdesc(sa);
           const uint64_t dAl = make_sdesc(sa + Cfg::A_BYTES);
           const uint64_t dBh = make_sdesc(sa + B_OFF);
           const uint64_t dBl = make_sdesc(sa + B_OFF + Cfg::B_BYTES);
-          const uint32_t ta = tmem_base + Cfg::A_TMEM_COL + stage * 64;   // SS: hi at +0, lo at +32
+          const uint32_t ta = tmem_base + Cfg::A_TMEM_COL + stage * 64;   // TS: hi at +0, lo at +32
 #pragma unroll
           for (int k = 0; k < BK / 8; k++) {
             const uint64_t ko = (uint64_t)(k * 32 >> 4);  // 8 tf32 = 32 bytes along K
-            if (SS) {
+            if (TS) {
               tc_mma_tf32_ts(d_tmem, ta + 32 + k * 8, dBh + ko, idesc, (kb | k) != 0);
               tc_mma_tf32_ts(d_tmem, ta + k * 8, dBl + ko, idesc, 1);
               tc_mma_tf32_ts(d_tmem, ta + k * 8, dBh + ko, idesc, 1);
@@ -171,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (SS && warp >= 6) {
+  } else if (TS && warp >= 6) {
     // ===================== A producers (warps 6..9): global fp32 -> tf32 hi/lo -> TMEM =====================
     const int q = warp & 3;                      // TMEM lane quarter of this warp
     const int row = q * 32 + lane;               // A-tile row = TMEM lane
@@ -236,7 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
               const float x = fmaxf(v[i] + __ldg(p.bias + n0 + i), 0.f);
               const float w = __ldg(p.vec + n0 + i);
               zsum = fmaf(x, w, zsum);
-              if (SS) {
+              if (TS) {
                 hi[i] = x > 0.f ? w : 0.f;
               } else {
                 const float wh = tf32_hi_g(w);
@@ -247,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
 #pragma unroll
             for (int i = 0; i < 8; i++) oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            if (!SS) {
+            if (!TS) {
               float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
 #pragma unroll
               for (int i = 0; i < 8; i++) ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
@@ -278,7 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
               } else {
                 x = (p.mask[m * p.ldmask + n0 + i] > 0.f) ? x * rs : 0.f;
               }
-              if (SS) {
+              if (TS) {
                 hi[i] = x;
               } else {
                 hi[i] = tf32_hi_g(x);
@@ -289,7 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
 #pragma unroll
             for (int i = 0; i < 8; i++) oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            if (!SS) {
+            if (!TS) {
               float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
 #pragma unroll
               for (int i = 0; i < 8; i++) ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
@@ -314,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(SS ? 512 : Cfg::TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TS ? 512 : Cfg::TMEM_COLS));
   }
 }
 
@@ -358,7 +358,7 @@ int device_num_sms(int device) {
   return cached[device];
 }
 
-template <int BN, int EPI, bool SS = false>
+template <int BN, int EPI, bool TS = false>
 static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   CUtensorMap mAh, mAl, mBh, mBl;
@@ -367,7 +367,7 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   if (int rc = make_tensor_map_2d(&mBl, g.B_lo, g.N, Ktot, g.ldb, BN)) return rc;
   const int64_t Ka = g.k_valid > 0 ? g.k_valid : Ktot;      // columns of A that exist; TMA zero-fills beyond
   if (int rc = make_tensor_map_2d(&mAh, g.A_hi, g.M, Ka, g.lda, BM)) return rc;
-  if (SS) {
+  if (TS) {
     mAl = mAh;                 // unused by the kernel: one raw fp32 A tile per stage
   } else {
     if (int rc = make_tensor_map_2d(&mAl, g.A_lo, g.M, Ka, g.lda, BM)) return rc;
@@ -380,21 +380,21 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   p.rowscale = g.rowscale; p.vec = g.vec; p.out2 = g.out2;
   p.A = g.A_hi; p.lda = g.lda;
   p.mask_bits = g.mask_bits; p.mask_bits_out = g.mask_bits_out;
-  auto kern = gemm_tc_kernel<BN, EPI, SS>;
-  constexpr int smem_bytes = SS ? Cfg::SMEM_BYTES_SS : Cfg::SMEM_BYTES;
+  auto kern = gemm_tc_kernel<BN, EPI, TS>;
+  constexpr int smem_bytes = TS ? Cfg::SMEM_BYTES_TS : Cfg::SMEM_BYTES;
   JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = std::min(tiles, device_num_sms(m->device));
-  kern<<<grid, SS ? TC_THREADS_SS : TC_THREADS, smem_bytes, st>>>(mAh, mAl, mBh, mBl, p);
+  kern<<<grid, TS ? TC_THREADS_TS : TC_THREADS, smem_bytes, st>>>(mAh, mAl, mBh, mBl, p);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
 
 int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   if (g.M % BM != 0 || g.K % BK != 0) return fail(JRR_ERR_INVALID, "tc gemm: M%128 or K%32");
-  if (((uintptr_t)g.A_hi | (uintptr_t)(g.smem_split ? nullptr : g.A_lo) | (uintptr_t)g.B_hi | (uintptr_t)g.B_lo) & 15)
+  if (((uintptr_t)g.A_hi | (uintptr_t)(g.a_via_tmem ? nullptr : g.A_lo) | (uintptr_t)g.B_hi | (uintptr_t)g.B_lo) & 15)
     return fail(JRR_ERR_INVALID, "tc gemm: operands must be 16-byte aligned");
-  if (g.smem_split) {      // plain fp32 A (A_hi) through tensor memory, pre-split B
+  if (g.a_via_tmem) {      // plain fp32 A (A_hi) through tensor memory, pre-split B
     if (g.N % 128 != 0 || g.lda % 4 != 0) return fail(JRR_ERR_INVALID, "tc gemm (A through TMEM): N % 128, lda % 4");
     switch (g.epi) {
       case EPI_BIAS_RELU_SPLIT: return launch_tc<128, EPI_BIAS_RELU_SPLIT, true>(m, g, st);
@@ -405,7 +405,7 @@ int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
         // 192 tiles = 1.3 waves of 1 unit on 148 SMs
         if (g.N == 768 && g.ksplit == 1) return launch_tc<96, EPI_STORE_SPLITK, true>(m, g, st);
         return launch_tc<128, EPI_STORE_SPLITK, true>(m, g, st);
-      default: return fail(JRR_ERR_INVALID, "tc gemm (smem split): unsupported epilogue");
+      default: return fail(JRR_ERR_INVALID, "tc gemm (A through TMEM): unsupported epilogue");
     }
   }
   switch (g.epi) {

@@ -172,8 +172,8 @@ struct JrrModel {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_seed = nullptr, ev_join2 = nullptr;
   bool overlap_critic = true;
   bool split_adam = true;                    // chain backward beside the critic branch, element-wise Adam after the join
-  bool critic_ss = true;                     // critic GEMMs of the refine step: plain fp32 activations staged through tensor
-                                             // memory (JRR_CRITIC_SS=0: pre-split activations through shared memory)
+  bool critic_ts = true;                     // critic GEMMs of the refine step: plain fp32 activations staged through tensor
+                                             // memory (JRR_CRITIC_TS=0: pre-split activations through shared memory)
   bool critic_head_fused = true;             // global critic head inside the layer-2 GEMM epilogue (refine step)
   // folded loss path (jrr_set_loss_path): T = Jhat o skinning weights o blend matrix, per regressor version
   bool folded = false;
@@ -253,7 +253,7 @@ struct GemmDesc {
   const uint32_t* mask_bits;               // (EPI_MASK_SPLIT) ReLU mask as bits [M][N/32] instead of `mask`
   uint32_t* mask_bits_out;                 // (EPI_BIAS_RELU_SPLIT) also emit the ReLU mask as bits [M][N/32]
   int64_t k_valid;                         // > 0: only the first k_valid columns of A exist (TMA zero-fills the rest of K)
-  bool smem_split;                         // A is plain fp32 (A_hi): loaded, tf32-split and staged in tensor memory by the
+  bool a_via_tmem;                         // A is plain fp32 (A_hi): loaded, tf32-split and staged in tensor memory by the
                                            // kernel (B stays pre-split); *_SPLIT epilogues then write ONE fp32 array (out0)
 };
 int launch_gemm(const JrrModel* m, const GemmDesc& g, cudaStream_t st);

@@ -57,8 +57,8 @@ def test_gemm_tcgen05_3xtf32_vs_fp64(smpl_tc, shape):
 
 
 @pytest.mark.parametrize("shape", [(128, 128, 32), (256, 256, 224), (384, 1024, 768), (4096, 1024, 1024), (512, 768, 1024)])
-def test_gemm_tcgen05_smem_split_vs_fp64(smpl_tc, shape):
-    """The variant that takes plain fp32 operands and makes the tf32 hi/lo pairs in shared memory."""
+def test_gemm_tcgen05_a_through_tmem_vs_fp64(smpl_tc, shape):
+    """The variant that takes a plain fp32 A, splits it in registers and feeds the MMAs from tensor memory."""
     M, N, K = shape
     g = torch.Generator(device="cpu").manual_seed(M + N + K + 1)
     A = torch.randn(M, K, generator=g).to(DEV)
@@ -66,7 +66,7 @@ def test_gemm_tcgen05_smem_split_vs_fp64(smpl_tc, shape):
     C = smpl_tc.native().debug_gemm(A, B, impl=2)
     torch.cuda.synchronize()
     err = rel(C, A.double() @ B.double().t())
-    print(f"tcgen05 3xTF32 smem-split {shape}: rel err {err:.2e}")
+    print(f"tcgen05 3xTF32 A-through-TMEM {shape}: rel err {err:.2e}")
     assert err < 1e-5
     assert torch.equal(C, smpl_tc.native().debug_gemm(A, B, impl=2))
 
