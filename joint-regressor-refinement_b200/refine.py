@@ -26,13 +26,17 @@ def shard_range(n_frames: int, rank: int, world: int):
 class PoseRefiner:
     def __init__(self, smpl, J_regressor, critic_state_dict=None, mask=None, lr=1e-2,
                  w_joint=10000.0, w_pose=10.0, chunk=4096, use_graph=True, shape_critic_state_dict=None,
-                 w_shape=10.0, loss_path=None):
+                 w_shape=10.0, loss_path=None, steps_per_graph=10):
         self.native: NativeModel = smpl.native() if hasattr(smpl, "native") else smpl
         self.device = self.native.device
         self.lr, self.w_joint = float(lr), float(w_joint)
         self.w_pose = float(w_pose) if critic_state_dict is not None else 0.0
         self.chunk = int(chunk)
         self.use_graph = use_graph
+        # iterations captured per CUDA graph: > 1 removes the launch gap between consecutive replays (the step
+        # counter of the Adam bias correction lives on the device, so a multi-step graph is exact); the loss
+        # buffer then holds the last captured step's values
+        self.steps_per_graph = max(1, int(steps_per_graph))
         if loss_path is not None:
             self.native.set_loss_path(loss_path)
         self.set_regressor(J_regressor, mask)
@@ -76,23 +80,37 @@ class PoseRefiner:
                 self._step(st, LB)
             self.launches_per_step = self.native.launches
             return
-        if st["graph"] is None or st["LB"] != LB or st.get("ver") != getattr(self.native, "regressor_version", 0):
-            # warm-up outside capture (module loading, attribute calls), on a side stream
-            keep = [st[k].clone() for k in ("x6", "betas", "m", "v", "t")]
-            s = torch.cuda.Stream(device=self.device)
-            s.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(s):
-                self._step(st, LB)
-            torch.cuda.current_stream(self.device).wait_stream(s)
-            self.launches_per_step = self.native.launches
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._step(st, LB)
-            for k, v in zip(("x6", "betas", "m", "v", "t"), keep):
-                st[k].copy_(v)
-            st["graph"], st["LB"], st["ver"] = g, LB, getattr(self.native, "regressor_version", 0)
+        ver = getattr(self.native, "regressor_version", 0)
+        if st["graph"] is None or st["LB"] != LB or st.get("ver") != ver:
+            st["graphs"] = {}
+            st["graph"], st["LB"], st["ver"] = self._capture(st, LB, 1), LB, ver
+            st["graphs"][1] = st["graph"]
+        u = self.steps_per_graph
+        if u > 1 and iters >= u:
+            if u not in st["graphs"]:
+                st["graphs"][u] = self._capture(st, LB, u)
+            for _ in range(iters // u):
+                st["graphs"][u].replay()
+            iters -= (iters // u) * u
         for _ in range(iters):
             st["graph"].replay()
+
+    def _capture(self, st, LB, n_steps):
+        # warm-up outside capture (module loading, attribute calls), on a side stream
+        keep = [st[k].clone() for k in ("x6", "betas", "m", "v", "t")]
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self._step(st, LB)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        self.launches_per_step = self.native.launches
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n_steps):
+                self._step(st, LB)
+        for k, v in zip(("x6", "betas", "m", "v", "t"), keep):
+            st[k].copy_(v)
+        return g
 
     def fit_camera(self, x6, betas, gt_j2d, cam, iters=1000, lr=1e-2, logical_batch=None):
         """optimize.py:187-199: camera-only Adam against the 2-D joints; `cam` [N,3] updated in place.
