@@ -852,3 +852,21 @@ def test_folded_loss_path_follows_the_refit(smpl_tc, jrr, oracle, osmpl32, criti
         smpl_tc.native().set_loss_path("vertex")
         smpl_tc.native().load_critic(critic_sd)
         smpl_tc.native().set_regressor(J_shipped.to(DEV))
+
+
+@pytest.mark.parametrize("path", ["vertex", "folded"])
+def test_multi_step_graph_is_bit_identical(path, smpl_tc, jrr, critic_sd, J_shipped, frames64):
+    """10 Adam iterations captured in one CUDA graph (device-side step counter) give exactly the bits of
+    ten replays of the one-step graph and of eager launches."""
+    fr = frames64
+    res = []
+    try:
+        for kw in (dict(use_graph=False), dict(steps_per_graph=1), dict(steps_per_graph=10)):
+            ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, loss_path=path, **kw)
+            x6 = fr["x6"].to(DEV).clone(); be = fr["betas"].to(DEV).clone()
+            loss = ref.refine(x6, be, fr["gt_mm"].to(DEV), iters=23).clone()      # 2 x 10-step graph + 3 single steps
+            res.append((x6.clone(), be.clone(), loss))
+    finally:
+        smpl_tc.native().set_loss_path("vertex")
+    for x6, be, loss in res[1:]:
+        assert torch.equal(x6, res[0][0]) and torch.equal(be, res[0][1]) and torch.equal(loss, res[0][2])
