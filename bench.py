@@ -381,7 +381,9 @@ def main():
     f_gemm = F_GEMM if not folded else 2.0 * (2 * 1224 * 218 + 2 * (768 * 1024 + 1024 * 1024))
     whole = {"tensor_frac_3xtf32": round(3 * f_gemm * pose_steps_per_s / (tf32_peak * 1e12), 4),
              "hbm_frac_algorithmic": round(ALG_BYTES_PER_POSE_STEP * pose_steps_per_s / (pk["hbm_gbs"] * 1e9), 6),
-             "useful_tflops": round(F_USEFUL * pose_steps_per_s / 1e12, 2)}
+             "useful_tflops": round((F_USEFUL if not folded else f_gemm + 2 * 24 * 17 * 33) * pose_steps_per_s / 1e12, 2),
+             "flops_per_pose_step": "per-vertex formulation (SURVEY.md 8d)" if not folded else
+                                    "folded formulation: two N=1224 GEMMs + critic GEMMs + the per-frame joint contraction"}
 
     # ---------------------------------------------------------------- regressor refit (C4), untimed extra
     refit = jrr.RegressorRefit(smpl, J, lr=1e-2, chunk=B)
