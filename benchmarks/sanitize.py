@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Workload for `compute-sanitizer --tool memcheck python benchmarks/sanitize.py` (small batches, every
-entry point of include/jrr.h once, ragged sizes).  Prints "sanitizer workload done"."""
+entry point of include/jrr.h once, both loss-path formulations, ragged sizes).  Prints "sanitizer workload done"."""
 import os
 import sys
 
@@ -27,15 +27,19 @@ for J in (shipped_regressor(), torch.rand(17, 6890) + 0.01):
                    global_orient=R[:, :1], pose2rot=False)
         (out.vertices.sum() + out.joints.sum()).backward()
         gt = 1000 * jrr.move_pelvis(jrr.find_joints(smpl, be, R[:, :1], R[:, 1:], J.to(dev))) + 5 * torch.randn(n, 17, 3, device=dev)
-        loop = jrr.RefinementLoop(smpl, J, sd, ssd, refine_iters=2, cam_iters=3)
         cam = torch.tensor([0.0, 0.0, 40.0], device=dev).repeat(n, 1)
         gt2d = 112 + 20 * torch.randn(n, 17, 2, device=dev)
-        for use2d in (True, False):
-            b = {"orient": x6[:, :1], "pose": x6[:, 1:], "betas": be, "gt_j3d": gt}
-            if use2d:
-                b.update(gt_j2d=gt2d, cam=cam)
-            res = loop.run_batch(b)
-        loop.evaluate(res["x6"], res["betas"], gt)
+        for path in ("vertex", "folded"):
+            loop = jrr.RefinementLoop(smpl, J, sd, ssd, refine_iters=2, cam_iters=3, loss_path=path)
+            for use2d in (True, False):
+                b = {"orient": x6[:, :1], "pose": x6[:, 1:], "betas": be, "gt_j3d": gt}
+                if use2d:
+                    b.update(gt_j2d=gt2d, cam=cam)
+                res = loop.run_batch(b)
+            loop.evaluate(res["x6"], res["betas"], gt)
+            # graph-captured refinement, 10 iterations per graph
+            jrr.PoseRefiner(smpl, J, sd, loss_path=path).refine(x6.clone(), be.clone(), gt, iters=12)
+        smpl.native().set_loss_path("vertex")
         jrr.Discriminator().to(dev).bind(smpl.native())(x6)
         jrr.Shape_Discriminator().to(dev).bind(smpl.native())(be)
         smpl.native().load_shape_critic(None)
