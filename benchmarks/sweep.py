@@ -226,7 +226,7 @@ def main():
         ms = {n: round(ev[i].elapsed_time(ev[i + 1]), 3) for i, n in enumerate(names)}
         tot = ev[0].elapsed_time(ev[4])
         emit({"config": "per_batch_loop", "workload": "optimize.py:150-312 on one 4096-frame batch (no SPIN inference, no "
-              "silhouette term): camera fit, refinement (eager launches: the 2-D variant is not graph-captured), critic + "
+              "silhouette term): camera fit, refinement (CUDA graphs of 10 iterations), critic + "
               "shape-critic training step, regressor refit", "loss_path": args.loss_path, **ms, "total_ms": round(tot, 3),
               "frames_per_s": round(B / tot * 1e3, 1)})
 

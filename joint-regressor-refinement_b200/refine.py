@@ -53,8 +53,8 @@ class PoseRefiner:
         for st in getattr(self, "_bufs", {}).values():     # captured graphs hold the old packing's launch shapes
             st["graph"] = None
 
-    def _buffers(self, B):
-        st = self._bufs.get(B)
+    def _buffers(self, B, two_d=False):
+        st = self._bufs.get((B, two_d))
         if st is None:
             dev = self.device
             st = {
@@ -64,23 +64,33 @@ class PoseRefiner:
                 "t": torch.zeros(1, dtype=torch.int32, device=dev),
                 "loss": torch.zeros(5, device=dev), "graph": None, "LB": None,
             }
-            self._bufs[B] = st
+            if two_d:       # 2-D reprojection term: camera translation as a fourth Adam group
+                st.update(cam=torch.zeros(B, 3, device=dev), cm=torch.zeros(B, 3, device=dev),
+                          cv=torch.zeros(B, 3, device=dev), gt2d=torch.zeros(B, 17, 2, device=dev), w_2d=0.01)
+            self._bufs[(B, two_d)] = st
         return st
 
+    _STATE = ("x6", "betas", "m", "v", "t", "cam", "cm", "cv")      # what a step mutates (restored after a capture warm-up)
+
     def _step(self, st, LB):
-        self.native.refine_step(st["x6"], st["betas"], st["gt"], st["m"], st["v"], st["t"], self.lr,
-                                self.w_joint, self.w_pose, logical_batch=LB, loss_out=st["loss"])
+        if "cam" in st:
+            self.native.refine_step_2d(st["x6"], st["betas"], st["gt"], st["gt2d"], st["cam"], st["m"], st["v"], st["cm"],
+                                       st["cv"], st["t"], self.lr, self.w_joint, self.w_pose, st["w_2d"],
+                                       logical_batch=LB, loss_out=st["loss"])
+        else:
+            self.native.refine_step(st["x6"], st["betas"], st["gt"], st["m"], st["v"], st["t"], self.lr,
+                                    self.w_joint, self.w_pose, logical_batch=LB, loss_out=st["loss"])
 
     def _run_chunk(self, st, iters, LB):
-        st["m"].zero_()
-        st["v"].zero_()
-        st["t"].zero_()
+        for k in ("m", "v", "t", "cm", "cv"):
+            if k in st:
+                st[k].zero_()
         if not self.use_graph:
             for _ in range(iters):
                 self._step(st, LB)
             self.launches_per_step = self.native.launches
             return
-        ver = getattr(self.native, "regressor_version", 0)
+        ver = (getattr(self.native, "regressor_version", 0), st.get("w_2d"))     # w_2d is baked into a captured launch
         if st["graph"] is None or st["LB"] != LB or st.get("ver") != ver:
             st["graphs"] = {}
             st["graph"], st["LB"], st["ver"] = self._capture(st, LB, 1), LB, ver
@@ -97,7 +107,8 @@ class PoseRefiner:
 
     def _capture(self, st, LB, n_steps):
         # warm-up outside capture (module loading, attribute calls), on a side stream
-        keep = [st[k].clone() for k in ("x6", "betas", "m", "v", "t")]
+        names = [k for k in self._STATE if k in st]
+        keep = [st[k].clone() for k in names]
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
@@ -108,7 +119,7 @@ class PoseRefiner:
         with torch.cuda.graph(g):
             for _ in range(n_steps):
                 self._step(st, LB)
-        for k, v in zip(("x6", "betas", "m", "v", "t"), keep):
+        for k, v in zip(names, keep):
             st[k].copy_(v)
         return g
 
@@ -127,24 +138,27 @@ class PoseRefiner:
 
     def refine_2d(self, x6, betas, cam, gt_mm, gt_j2d, iters=100, w_2d=0.01, logical_batch=None):
         """`refine` with the 2-D reprojection term and the camera as a fourth Adam group
-        (optimize.py:201-202,231-233,252-253).  Eager launches (no graph); x6/betas/cam in place."""
+        (optimize.py:201-202,231-233,252-253); x6 / betas / cam are updated in place.  Same chunking and
+        CUDA-graph replay as `refine`."""
         N = x6.shape[0]
-        loss = torch.zeros(5, device=self.device)
+        last = None
         with torch.cuda.device(self.device):
             for lo in range(0, N, self.chunk):
                 hi = min(N, lo + self.chunk)
                 B = hi - lo
-                LB = B if logical_batch is None else logical_batch
-                xs, bs, cs = x6[lo:hi].reshape(B, 24, 6).contiguous(), betas[lo:hi].contiguous(), cam[lo:hi].contiguous()
-                m = torch.zeros(B, 154, device=self.device); v = torch.zeros_like(m)
-                cm = torch.zeros(B, 3, device=self.device); cv = torch.zeros_like(cm)
-                t = torch.zeros(1, dtype=torch.int32, device=self.device)
-                for _ in range(iters):
-                    self.native.refine_step_2d(xs, bs, gt_mm[lo:hi].contiguous(), gt_j2d[lo:hi].contiguous(), cs, m, v,
-                                               cm, cv, t, self.lr, self.w_joint, self.w_pose, w_2d,
-                                               logical_batch=LB, loss_out=loss)
-                x6[lo:hi].copy_(xs.view_as(x6[lo:hi])); betas[lo:hi].copy_(bs); cam[lo:hi].copy_(cs)
-        return loss
+                st = self._buffers(B, two_d=True)
+                st["x6"].copy_(x6[lo:hi].reshape(B, 24, 6), non_blocking=True)
+                st["betas"].copy_(betas[lo:hi], non_blocking=True)
+                st["cam"].copy_(cam[lo:hi], non_blocking=True)
+                st["gt"].copy_(gt_mm[lo:hi].reshape(B, 17, 3), non_blocking=True)
+                st["gt2d"].copy_(gt_j2d[lo:hi].reshape(B, 17, 2), non_blocking=True)
+                st["w_2d"] = float(w_2d)
+                self._run_chunk(st, iters, B if logical_batch is None else logical_batch)
+                x6[lo:hi].copy_(st["x6"].view_as(x6[lo:hi]), non_blocking=True)
+                betas[lo:hi].copy_(st["betas"], non_blocking=True)
+                cam[lo:hi].copy_(st["cam"], non_blocking=True)
+                last = st["loss"]
+        return last
 
     def refine(self, x6, betas, gt_mm, iters=100, logical_batch=None):
         """In-place refinement of x6 [N,24,6] / betas [N,10] against gt_mm [N,17,3] (mm,
