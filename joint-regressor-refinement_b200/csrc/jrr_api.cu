@@ -73,6 +73,7 @@ Workspace carve(const JrrModel* m, int64_t B, void* base) {
   w.zmask = reinterpret_cast<uint32_t*>(take(BP * (C_Z / 32)));
   w.gx6 = take(BP * 144);
   w.gbetas = take(BP * NB);
+  w.adam_coef = take(64);
   w.scores = take(BP * 25);
   w.bytes = off;
   return w;
@@ -260,6 +261,8 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
     JRR_CUDA(cudaEventRecord(m->ev_join, m->side));
   }
   JRR_MARK();
+  if (fork && m->split_adam)
+    if (int rc = launch_adam_coef(w, step_count, lr, st)) return rc;
   if (m->folded) {
     // folded loss path: chain | Q = feat . T^T | per-frame joints + loss seed + dA + dQ | dfeat = dQ . T (split-K)
     // (events: pose_fwd | blend_gemm_fwd [the N = 1224 GEMM] | skin_fwd [empty] | loss_seed [folded seed] |

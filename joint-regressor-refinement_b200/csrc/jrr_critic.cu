@@ -15,7 +15,8 @@ __device__ __forceinline__ float tf32_hi_c(float x) {
 }
 
 // thread = (pose, joint): conv1x1 6->32, ReLU, conv1x1 32->32, ReLU -> h[b][j*32+c] (hi/lo)
-__global__ void __launch_bounds__(256)
+// (<= 85 registers: three CTAs per SM, so the 384 CTAs of a 4096-frame step are one wave, not 1.3)
+__global__ void __launch_bounds__(256, 3)
 critic_pre_kernel(const float* __restrict__ cs, const float* __restrict__ x6, int64_t B, int64_t BP,
                   float* __restrict__ h_hi, float* __restrict__ h_lo, float* __restrict__ zj_out,
                   uint2* __restrict__ masks_out) {

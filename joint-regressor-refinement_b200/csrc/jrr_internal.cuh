@@ -228,6 +228,7 @@ struct Workspace {
   uint32_t* zmask;         // [BP][32]   ReLU mask bits of the critic's first wide layer
   float* gx6;              // [BP][144]  parameter gradients of the chain backward (split-Adam schedule)
   float* gbetas;           // [BP][10]
+  float* adam_coef;        // [2]        this step's Adam bias corrections (adam_coef_kernel)
   float* scores;           // [BP][25]
   size_t bytes;
 };
@@ -276,6 +277,7 @@ struct Proj2D {
 int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int64_t B_logical, float w_joint,
                        float* joints17_out, const Proj2D& p2d, cudaStream_t st);
 int launch_fold(JrrModel* m, cudaStream_t st);
+int launch_adam_coef(const Workspace& w, const int32_t* step_count, float lr, cudaStream_t st);
 int launch_adam_params(const Workspace& w, bool use_critic, bool use_shape, float* x6, float* betas, float* adam_m,
                        float* adam_v, int32_t* step_count, float lr, cudaStream_t st);
 int launch_loss_seed(const JrrModel* m, Workspace& w, bool fused_partials, const float* gt_mm,

@@ -409,16 +409,7 @@ __global__ void bump_step_kernel(int32_t* step_count) { *step_count += 1; }
 __global__ void __launch_bounds__(256)
 adam_params_kernel(const float* __restrict__ gx6, const float* __restrict__ gbetas, const float* __restrict__ dx6c,
                    const float* __restrict__ dbeta_s, int64_t B, float* __restrict__ x6, float* __restrict__ betas,
-                   float* __restrict__ adam_m, float* __restrict__ adam_v, const int32_t* __restrict__ step_count,
-                   float lr) {
-  // bias corrections in double like torch.optim.Adam's Python scalars: once per block, not per element
-  __shared__ float s_bc[2];
-  if (threadIdx.x == 0) {
-    const int t0 = *step_count + 1;
-    s_bc[0] = (float)sqrt(1.0 - pow(0.999, (double)t0));
-    s_bc[1] = (float)((double)lr / (1.0 - pow(0.9, (double)t0)));
-  }
-  __syncthreads();
+                   float* __restrict__ adam_m, float* __restrict__ adam_v, const float* __restrict__ coef) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * NPARAM) return;
   const int64_t b = idx / NPARAM;
@@ -434,7 +425,7 @@ adam_params_kernel(const float* __restrict__ gx6, const float* __restrict__ gbet
     prm = betas + b * NB + (p - 144);
   }
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
-  const float bc2s = s_bc[0], step = s_bc[1];
+  const float bc2s = coef[0], step = coef[1];      // adam_coef_kernel
   const float m = b1 * adam_m[idx] + (1.f - b1) * g;
   const float v = b2 * adam_v[idx] + (1.f - b2) * g * g;
   adam_m[idx] = m;
@@ -443,13 +434,28 @@ adam_params_kernel(const float* __restrict__ gx6, const float* __restrict__ gbet
   *prm = *prm - step * (m / denom);
 }
 
+// Bias corrections of this step in double, like torch.optim.Adam's Python scalars (a double-precision pow is a
+// few microseconds of dependent latency: one thread does it early in the step, off the critical path).
+__global__ void adam_coef_kernel(const int32_t* __restrict__ step_count, float lr, float* __restrict__ coef) {
+  const int t = *step_count + 1;
+  coef[0] = (float)sqrt(1.0 - pow(0.999, (double)t));
+  coef[1] = (float)((double)lr / (1.0 - pow(0.9, (double)t)));
+}
+
+int launch_adam_coef(const Workspace& w, const int32_t* step_count, float lr, cudaStream_t st) {
+  adam_coef_kernel<<<1, 1, 0, st>>>(step_count, lr, w.adam_coef);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
 // ---- host wrappers ---------------------------------------------------------------------------
 int launch_adam_params(const Workspace& w, bool use_critic, bool use_shape, float* x6, float* betas, float* adam_m,
                        float* adam_v, int32_t* step_count, float lr, cudaStream_t st) {
   const int64_t n = w.B * NPARAM;
   adam_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.gx6, w.gbetas, use_critic ? w.dx6c : nullptr,
                                                                  use_shape ? w.dbeta_s : nullptr, w.B, x6, betas, adam_m,
-                                                                 adam_v, step_count, lr);
+                                                                 adam_v, w.adam_coef);
+  (void)lr;
   JRR_LAUNCH_CHECK();
   bump_step_kernel<<<1, 1, 0, st>>>(step_count);
   JRR_LAUNCH_CHECK();
