@@ -37,7 +37,7 @@ class PoseRefiner:
         # counter of the Adam bias correction lives on the device, so a multi-step graph is exact); the loss
         # buffer then holds the last captured step's values
         self.steps_per_graph = max(1, int(steps_per_graph))
-        if loss_path is not None:
+        if loss_path is not None:          # a property of the shared native model: the last refiner to set it wins
             self.native.set_loss_path(loss_path)
         self.set_regressor(J_regressor, mask)
         if critic_state_dict is not None:
