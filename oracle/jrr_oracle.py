@@ -185,6 +185,38 @@ def evaluate(pred_j3ds: torch.Tensor, target_j3ds: torch.Tensor):
     return mpjpe, pa
 
 
+# --------------------------------------------------------------------------- folded loss-path operator
+def fold_operator(smpl, J_regressor, mask=None):
+    """The constant linear maps between blend features and regressed joints, folded:
+    T[j,i,c,k] = sum_v Jhat[i,v] W[v,j] P[v,c,k],  c[j,i] = sum_v Jhat[i,v] W[v,j], with P the augmented blend matrix
+    [posedirs(207) | shapedirs(10) | v_template(1)] per vertex coordinate.  Checker for fold_kernel and a statement
+    of why the folded formulation is the same function (tests/test_oracle.py::test_folded_operator_is_exact)."""
+    Jh = normalise_regressor(J_regressor, mask).to(smpl.dtype)
+    V = smpl.v_template.shape[0]
+    P = torch.cat([smpl.posedirs.t().reshape(V, 3, 207), smpl.shapedirs.reshape(V, 3, 10),
+                   smpl.v_template.reshape(V, 3, 1)], dim=2)                     # [V,3,218]
+    JW = torch.einsum('iv,vj->jiv', Jh, smpl.lbs_weights)                       # [24,17,V]
+    return torch.einsum('jiv,vck->jick', JW, P), JW.sum(-1)
+
+
+def find_joints_folded(smpl, betas, rot_mats, T, c):
+    """joints17_i = sum_j A_j^R (T_ji feat) + A_j^t c_ji with A_j the relative joint transforms of lbs()."""
+    B = rot_mats.shape[0]
+    dt = rot_mats.dtype
+    v_shaped = smpl.v_template[None] + torch.einsum('bl,vkl->bvk', betas, smpl.shapedirs)
+    J = torch.einsum('jv,bvk->bjk', smpl.J_regressor, v_shaped)
+    GR, Gt = [rot_mats[:, 0]], [J[:, 0]]
+    for j in range(1, smpl.parents.shape[0]):
+        p = int(smpl.parents[j])
+        GR.append(GR[p] @ rot_mats[:, j])
+        Gt.append((GR[p] @ (J[:, j] - J[:, p])[..., None])[..., 0] + Gt[p])
+    GR, Gt = torch.stack(GR, 1), torch.stack(Gt, 1)
+    At = Gt - (GR @ J[..., None])[..., 0]
+    feat = torch.cat([(rot_mats[:, 1:] - torch.eye(3, dtype=dt)).reshape(B, 207), betas, torch.ones(B, 1, dtype=dt)], 1)
+    q = torch.einsum('jick,bk->bjic', T, feat)
+    return torch.einsum('bjrc,bjic->bir', GR, q) + torch.einsum('bjr,ji->bir', At, c)
+
+
 # --------------------------------------------------------------------------- scripts/discriminator.py
 def discriminator_forward(sd: dict, rot6d: torch.Tensor) -> torch.Tensor:
     """scripts/discriminator.py:32-54 as a function of the module's state_dict

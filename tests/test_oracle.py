@@ -119,3 +119,17 @@ def test_shape_term_shards_and_gradient(oracle, osmpl64, J_shipped, jrr):
     assert abs(sum(parts) - full.item()) < 1e-12
     assert (torch.cat(grads) - g_full).abs().max() < 1e-14
     assert g_full.abs().max() > 1e-4      # the default-init network is not dead on N(0,1) betas
+
+
+def test_folded_operator_is_exact(oracle, osmpl64, J_shipped, jrr):
+    """The folded formulation (regressor o skinning o blend operator) is the same function as
+    find_joints on the per-vertex body model: fp64 agreement to round-off, for a sparse and a dense regressor."""
+    g = torch.Generator().manual_seed(8)
+    R = oracle.rot6d_to_rotmat(torch.randn(7 * 24, 6, generator=g).double()).view(7, 24, 3, 3)
+    b = torch.randn(7, 10, generator=g).double()
+    for J in (J_shipped.double(), torch.from_numpy(jrr.synthetic.make_dense_regressor(0)).double()):
+        ref = oracle.find_joints(osmpl64, b, R[:, :1], R[:, 1:], J)
+        T, c = oracle.fold_operator(osmpl64, J)
+        assert T.shape == (24, 17, 3, 218) and c.shape == (24, 17)
+        got = oracle.find_joints_folded(osmpl64, b, R, T, c)
+        assert (got - ref).abs().max().item() < 1e-12
