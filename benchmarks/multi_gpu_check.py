@@ -22,11 +22,12 @@ import jrr_b200 as jrr  # noqa: E402
 from conftest import shipped_regressor  # noqa: E402
 
 N, BATCH, ITERS = 1536, 768, 5
+LOSS_PATH = sys.argv[1] if len(sys.argv) > 1 else "folded"      # 'folded' (bench default) or 'vertex'
 
 
 def run(model, dev, J, sd, ssd, frames, gt):
     smpl = jrr.SMPL(model_dict=model, create_transl=False).to(dev)
-    loop = jrr.RefinementLoop(smpl, J, sd, ssd, refine_iters=ITERS)
+    loop = jrr.RefinementLoop(smpl, J, sd, ssd, refine_iters=ITERS, loss_path=LOSS_PATH)
     fr = {"orient": frames["x6"][:, :1], "pose": frames["x6"][:, 1:], "betas": frames["betas"], "gt_j3d": gt}
     hist = loop.run(fr, batch_size=BATCH)
     torch.cuda.synchronize()
@@ -78,7 +79,7 @@ def main():
     ok = ok and all(abs(a - b) / abs(b) < 1e-4 for a, b in zip(lcw + lrw, lc1 + lr1))
     if rank == 0:
         os.write(real_stdout, (json.dumps({
-            "check": "multi_gpu_equality", "world": world, "frames": N, "global_batch": BATCH, "refine_iters": ITERS,
+            "check": "multi_gpu_equality", "loss_path": LOSS_PATH, "world": world, "frames": N, "global_batch": BATCH, "refine_iters": ITERS,
             "max_abs_diff": {"J_regressor": dJ, "critic_params_max": dp_max, "critic_params_mean": dp_mean,
                              "shape_critic_params": dps, "refined_x6": dx},
             "critic_loss": {"sharded": lcw, "single": lc1}, "refit_loss": {"sharded": lrw, "single": lr1},
