@@ -269,17 +269,31 @@ fold_kernel(const VtxRec* __restrict__ vrec, const float* __restrict__ Pt_hi, co
   for (int e = k; e < NJ * KA; e += KA) acc[e] = 0.0;
   __syncthreads();                 // (each thread only ever touches column k, the barrier is for the zeroing loop)
   const int per = VP / FOLD_CH;
-  for (int pi = ch * per; pi < (ch + 1) * per; pi++) {
-    const float jh = vrec[pi].jh[i];
-    if (jh == 0.f) continue;       // uniform: vertices outside the regressor row's support
-    const uint32_t meta = vrec[pi].meta;
-    double p;
-    if (c < 3) p = (double)Pt_hi[(int64_t)(3 * pi + c) * KA + k] + (double)Pt_lo[(int64_t)(3 * pi + c) * KA + k];
-    else p = k == 0 ? 1.0 : 0.0;
+  // four vertices per round trip: their blend-matrix rows are loaded before any of them is accumulated (the loop
+  // is a chain of dependent global-load latencies otherwise); accumulation order stays vertex by vertex
+  for (int p0 = ch * per; p0 < (ch + 1) * per; p0 += 4) {
+    float jh[4], w[4][4];
+    uint32_t meta[4];
+    double p[4];
 #pragma unroll
-    for (int s4 = 0; s4 < 4; s4++) {
-      const float w = vrec[pi].w[s4];
-      if (w != 0.f) acc[((meta >> (5 * s4)) & 31u) * KA + k] += (double)w * (double)jh * p;
+    for (int u = 0; u < 4; u++) {
+      const int pi = p0 + u;
+      jh[u] = vrec[pi].jh[i];
+      meta[u] = vrec[pi].meta;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; s4++) w[u][s4] = vrec[pi].w[s4];
+      p[u] = 0.0;
+      if (jh[u] != 0.f) {          // uniform: vertices outside the regressor row's support are skipped
+        if (c < 3) p[u] = (double)Pt_hi[(int64_t)(3 * pi + c) * KA + k] + (double)Pt_lo[(int64_t)(3 * pi + c) * KA + k];
+        else p[u] = k == 0 ? 1.0 : 0.0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (jh[u] == 0.f) continue;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; s4++)
+        if (w[u][s4] != 0.f) acc[((meta[u] >> (5 * s4)) & 31u) * KA + k] += (double)w[u][s4] * (double)jh[u] * p[u];
     }
   }
   double* out = part + ((int64_t)(ch * NH + i) * 4 + c) * (NJ * KA);
