@@ -53,7 +53,9 @@ def launches():
     with open(os.path.join(DST, f"{TAG}_launches_summary.txt"), "w") as f:
         f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline\n")
         f.write("(cold-cache, serialised per-launch times: compare SHARES, not absolutes; the command also runs set-up,\n"
-                " warm-up, the end-to-end leg, the profiled steps and the refit, so library kernels of those appear too)\n\n")
+                " warm-up, the end-to-end leg, the profiled steps, the other loss-path formulation and the refit, so their kernels\n"
+                " appear too: fold_kernel runs once per regressor version -- here at every set_regressor of the set-up and quality\n"
+                " checks, never inside a timed step; fused_fwd/fused_bwd/loss_seed belong to the per-vertex formulation)\n\n")
         f.write(f"{'kernel':62s} {'launches':>8s} {'total_us':>10s} {'avg_us':>9s} {'share':>7s}\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k[:62]:62s} {n:8d} {t:10.1f} {t / n:9.2f} {100 * t / tot:6.2f}%\n")
