@@ -59,6 +59,24 @@ def launches():
         f.write(f"{'kernel':62s} {'launches':>8s} {'total_us':>10s} {'avg_us':>9s} {'share':>7s}\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k[:62]:62s} {n:8d} {t:10.1f} {t / n:9.2f} {100 * t / tot:6.2f}%\n")
+        # shares WITHIN one refinement step of the headline (folded) formulation: one launch of each kernel per step,
+        # average per-launch time from the list above -- the number to hold against bench.py's roofline.share_of_step
+        step = ["pose_fwd_kernel<2>", "gemm_tc_kernel<128, 0, 0>", "folded_seed_kernel", "gemm_tc_kernel<224, 3, 0>",
+                "pose_bwd_kernel<2, 0>", "critic_pre_kernel", "gemm_tc_kernel<128, 1, 1>", "gemm_tc_kernel<128, 4, 1>",
+                "critic_head_light_kernel", "gemm_tc_kernel<128, 2, 1>", "gemm_tc_kernel<96, 3, 1>", "critic_post_kernel",
+                "loss_finish_kernel", "adam_coef_kernel", "adam_params_kernel", "bump_step_kernel"]
+        have = [(k, agg[k][1] / agg[k][0]) for k in step if k in agg]
+        if have:
+            st = sum(t for _, t in have)
+            f.write(f"\none folded refinement step = {len(have)} launches, {st:.1f} us serialised under ncu\n")
+            for k, t in sorted(have, key=lambda kv: -kv[1]):
+                f.write(f"{k[:62]:62s} {1:8d} {t:10.1f} {t:9.2f} {100 * t / st:6.2f}%\n")
+            grp = {"critic_gemm_fwd": ["gemm_tc_kernel<128, 1, 1>", "gemm_tc_kernel<128, 4, 1>"],
+                   "critic_gemm_bwd": ["gemm_tc_kernel<128, 2, 1>", "gemm_tc_kernel<96, 3, 1>"]}
+            d = dict(have)
+            for g, ks in grp.items():
+                if all(k in d for k in ks):
+                    f.write(f"{g + ' (bench.py kernel group)':62s} {len(ks):8d} {sum(d[k] for k in ks):10.1f} {'':9s} {100 * sum(d[k] for k in ks) / st:6.2f}%\n")
 
 
 def top_kernels():
