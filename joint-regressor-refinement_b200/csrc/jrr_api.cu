@@ -253,10 +253,16 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
     JRR_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
     if (int rc = launch_critic_pre(m, w, x6, cs, hf)) return rc;
     if (int rc = critic_forward_gemms(m, w, cs, hf)) return rc;
-    if (hf) { if (int rc = launch_critic_head_light(m, w, B_logical, w_pose, cs)) return rc; }
-    else if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, cs)) return rc;
-    if (int rc = critic_backward_gemms(m, w, cs, hf ? w.dzg : nullptr)) return rc;
-    if (int rc = launch_critic_post(m, w, x6, cs)) return rc;
+    const bool hl = hf && m->critic_headless;      // no head kernel on the chain
+    if (hl) {
+      if (int rc = critic_backward_gemms(m, w, cs, nullptr, w_pose * 2.f / (25.f * (float)B_logical))) return rc;
+      if (int rc = launch_critic_post(m, w, x6, cs, true, B_logical, w_pose)) return rc;
+    } else {
+      if (hf) { if (int rc = launch_critic_head_light(m, w, B_logical, w_pose, cs)) return rc; }
+      else if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, cs)) return rc;
+      if (int rc = critic_backward_gemms(m, w, cs, hf ? w.dzg : nullptr)) return rc;
+      if (int rc = launch_critic_post(m, w, x6, cs)) return rc;
+    }
     if (shape) if (int rc = launch_shape_critic(m, w, betas, B_logical, cs)) return rc;
     JRR_CUDA(cudaEventRecord(m->ev_join, m->side));
   }
@@ -328,14 +334,16 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   JRR_MARK();
   if (inl) if (int rc = critic_forward_gemms(m, w, st, hf)) return rc;
   JRR_MARK();
-  if (inl) {
+  const bool hl_inl = hf && m->critic_headless;
+  if (inl && !hl_inl) {
     if (hf) { if (int rc = launch_critic_head_light(m, w, B_logical, w_pose, st)) return rc; }
     else if (int rc = launch_critic_head(m, w, B_logical, w_pose, nullptr, true, st)) return rc;
   }
   JRR_MARK();
-  if (inl) if (int rc = critic_backward_gemms(m, w, st, hf ? w.dzg : nullptr)) return rc;
+  if (inl) if (int rc = critic_backward_gemms(m, w, st, hl_inl ? nullptr : (hf ? w.dzg : nullptr),
+                                              hl_inl ? w_pose * 2.f / (25.f * (float)B_logical) : 0.f)) return rc;
   JRR_MARK();
-  if (inl) if (int rc = launch_critic_post(m, w, x6, st)) return rc;
+  if (inl) if (int rc = launch_critic_post(m, w, x6, st, hl_inl, B_logical, w_pose)) return rc;
   if (shape && !fork) if (int rc = launch_shape_critic(m, w, betas, B_logical, st)) return rc;
   JRR_MARK();
   // With the critic on its own branch, the chain backward does not have to wait for it: it leaves the

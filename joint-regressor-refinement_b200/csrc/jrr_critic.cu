@@ -204,17 +204,47 @@ critic_head_light_kernel(const float* __restrict__ cs, const float* __restrict__
 __global__ void __launch_bounds__(256)
 critic_post_kernel(const float* __restrict__ cs, const uint2* __restrict__ masks,
                    const float* __restrict__ dh, const float* __restrict__ dzj, int64_t B,
-                   float* __restrict__ dx6c) {
+                   float* __restrict__ dx6c, const float* __restrict__ zj, const float* __restrict__ zg_part,
+                   int n_part, int64_t BP, float gscale, float* __restrict__ loss_part) {
   __shared__ float sw[CS_HW];
   __shared__ float shw[NJ * 33];
+  __shared__ float red[8];
   for (int i = threadIdx.x; i < CS_HW; i += blockDim.x) sw[i] = cs[i];
   for (int i = threadIdx.x; i < NJ * 32; i += blockDim.x) shw[(i >> 5) * 33 + (i & 31)] = cs[CS_HW + i];
   __syncthreads();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * NJ) return;
+  const bool live = idx < B * NJ;
   const int j = (int)(idx % NJ);
+  float dj = 0.f;
+  if (zj != nullptr) {
+    // head-less chain: the joint heads' sigmoid / loss / dL/dlogit happen here (and the global head's loss term
+    // on the joint-0 thread of every frame); the global head's dL/dlogit is applied inside the backward GEMM
+    float l = 0.f;
+    if (live) {
+      const float sj = 1.f / (1.f + expf(-zj[idx]));
+      dj = gscale * (sj - 1.f) * sj * (1.f - sj);
+      l = (sj - 1.f) * (sj - 1.f);
+      if (j == 0) {
+        const int64_t b = idx / NJ;
+        float z = cs[CS_B3];
+        for (int i = 0; i < n_part; i++) z += zg_part[(int64_t)i * BP + b];
+        const float sg = 1.f / (1.f + expf(-z));
+        l += (sg - 1.f) * (sg - 1.f);
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
+      loss_part[blockIdx.x] = t;
+    }
+  } else if (live) {
+    dj = dzj[idx];
+  }
+  if (!live) return;
   const uint2 mk = masks[idx];
-  const float dj = dzj[idx];
   float d[32];
   const float4* dh4 = reinterpret_cast<const float4*>(dh + idx * 32);
 #pragma unroll
@@ -358,11 +388,15 @@ int launch_critic_head(const JrrModel* m, Workspace& w, int64_t B_logical, float
   return JRR_OK;
 }
 
-int launch_critic_post(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st) {
+int launch_critic_post(const JrrModel* m, Workspace& w, const float* x6, cudaStream_t st, bool with_head,
+                       int64_t B_logical, float w_pose) {
   const int64_t n = w.B * NJ;
   (void)x6;
-  critic_post_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->critic_small, w.cmask, w.dh, w.dzj,
-                                                                 w.B, w.dx6c);
+  const unsigned nblk = (unsigned)((n + 255) / 256);
+  if (with_head) w.n_pose_part = (int)nblk;
+  critic_post_kernel<<<nblk, 256, 0, st>>>(m->critic_small, w.cmask, w.dh, w.dzj, w.B, w.dx6c,
+                                           with_head ? w.zj : nullptr, w.zg_part, C_Z / 128, w.BP,
+                                           w_pose * 2.f / (25.f * (float)B_logical), w.loss_part + LOSS_PART_POSE);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
@@ -392,12 +426,18 @@ int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st,
   return launch_gemm(m, g, st);
 }
 
-int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, const float* rowscale) {
-  const bool ts = rowscale != nullptr && m->critic_ts;
+int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, const float* rowscale,
+                          float headless_gscale) {
+  const bool ts = (rowscale != nullptr || headless_gscale != 0.f) && m->critic_ts;
   GemmDesc g{};
   g.a_via_tmem = ts;
-  // dz1 = (dz2 . W2) * [z1 > 0]   (head_fused: dz2 rows still lack their scalar dL/dlogit = rowscale)
+  // dz1 = (dz2 . W2) * [z1 > 0]   (head_fused: dz2 rows still lack their scalar dL/dlogit = rowscale; head-less:
+  // the epilogue derives that scalar from the logit partials itself)
   g.rowscale = rowscale;
+  if (headless_gscale != 0.f) {
+    g.logit_part = w.zg_part; g.n_logit_part = C_Z / 128; g.logit_bias = m->critic_small + CS_B3;
+    g.logit_gscale = headless_gscale; g.rows_valid = w.B;
+  }
   g.A_hi = w.dz2_hi; g.A_lo = w.dz2_lo; g.lda = C_Z;
   g.B_hi = m->W2t_hi; g.B_lo = m->W2t_lo; g.ldb = C_Z;
   g.M = w.BP; g.N = C_Z; g.K = C_Z; g.ksplit = 1; g.epi = EPI_MASK_SPLIT;
@@ -410,7 +450,7 @@ int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st
   g.A_hi = w.dz1_hi; g.A_lo = w.dz1_lo; g.lda = C_Z;
   g.B_hi = m->W1t_hi; g.B_lo = m->W1t_lo; g.ldb = C_Z;
   g.N = C_H; g.K = C_Z; g.epi = EPI_STORE_SPLITK; g.out0 = w.dh; g.out1 = nullptr; g.ldo = C_H;
-  g.mask = nullptr; g.rowscale = nullptr;
+  g.mask = nullptr; g.rowscale = nullptr; g.logit_part = nullptr;
   return launch_gemm(m, g, st);
 }
 

@@ -32,6 +32,7 @@ struct TcParams {
   const float* bias;
   const float* mask; int64_t ldmask;
   const uint32_t* mask_bits; uint32_t* mask_bits_out;   // ReLU masks as bits [M][N/32]
+  const float* logit_part; int n_logit_part; const float* logit_bias; float logit_gscale; int64_t rows_valid;
   const float* A; int64_t lda;   // TS: plain fp32 A
   const float* rowscale;   // EPI_MASK_SPLIT: multiply row m by rowscale[m] (or nullptr)
   const float* vec;        // EPI_BIAS_RELU_HEAD: w3[N]
@@ -220,6 +221,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       float zsum = 0.f;   // EPI_BIAS_RELU_HEAD: this row's share of the global head's logit
       float rs = 1.f;
       if (EPI == EPI_MASK_SPLIT && p.rowscale != nullptr && m < p.M) rs = p.rowscale[m];
+      if (EPI == EPI_MASK_SPLIT && p.logit_part != nullptr && m < p.M) {
+        // dL/dlogit of the global critic head for this row, from the forward epilogue's logit partials
+        float z = __ldg(p.logit_bias);
+        for (int i = 0; i < p.n_logit_part; i++) z += p.logit_part[(int64_t)i * p.M + m];
+        const float sg = 1.f / (1.f + expf(-z));
+        rs = m < p.rows_valid ? p.logit_gscale * (sg - 1.f) * sg * (1.f - sg) : 0.f;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
         float v[32];
@@ -380,6 +388,8 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   p.rowscale = g.rowscale; p.vec = g.vec; p.out2 = g.out2;
   p.A = g.A_hi; p.lda = g.lda;
   p.mask_bits = g.mask_bits; p.mask_bits_out = g.mask_bits_out;
+  p.logit_part = g.logit_part; p.n_logit_part = g.n_logit_part; p.logit_bias = g.logit_bias;
+  p.logit_gscale = g.logit_gscale; p.rows_valid = g.rows_valid;
   auto kern = gemm_tc_kernel<BN, EPI, TS>;
   constexpr int smem_bytes = TS ? Cfg::SMEM_BYTES_TS : Cfg::SMEM_BYTES;
   JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

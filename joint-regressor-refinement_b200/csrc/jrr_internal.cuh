@@ -174,6 +174,7 @@ struct JrrModel {
   bool split_adam = true;                    // chain backward beside the critic branch, element-wise Adam after the join
   bool critic_ts = true;                     // critic GEMMs of the refine step: plain fp32 activations staged through tensor
                                              // memory (JRR_CRITIC_TS=0: pre-split activations through shared memory)
+  bool critic_headless = true;               // no head kernel: dL/dlogit inside the backward GEMM, joint heads in critic_post
   bool critic_head_fused = true;             // global critic head inside the layer-2 GEMM epilogue (refine step)
   // folded loss path (jrr_set_loss_path): T = Jhat o skinning weights o blend matrix, per regressor version
   bool folded = false;
@@ -253,6 +254,9 @@ struct GemmDesc {
   const float* vec; float* out2;           // (EPI_BIAS_RELU_HEAD) w3[N] in, logit partials [N/128][M] out
   const uint32_t* mask_bits;               // (EPI_MASK_SPLIT) ReLU mask as bits [M][N/32] instead of `mask`
   uint32_t* mask_bits_out;                 // (EPI_BIAS_RELU_SPLIT) also emit the ReLU mask as bits [M][N/32]
+  const float* logit_part; int n_logit_part; const float* logit_bias; float logit_gscale; int64_t rows_valid;
+                                           // (EPI_MASK_SPLIT) row scale = gscale * (s - 1) s (1 - s), s = sigmoid(bias +
+                                           // sum of the row's logit partials), zero for rows >= rows_valid
   int64_t k_valid;                         // > 0: only the first k_valid columns of A exist (TMA zero-fills the rest of K)
   bool a_via_tmem;                         // A is plain fp32 (A_hi): loaded, tf32-split and staged in tensor memory by the
                                            // kernel (B stays pre-split); *_SPLIT epilogues then write ONE fp32 array (out0)
@@ -307,9 +311,11 @@ int launch_critic_pre(const JrrModel* m, const Workspace& w, const float* x6, cu
 int launch_critic_head(const JrrModel* m, Workspace& w, int64_t B_logical, float w_pose,
                        float* scores_out, bool want_grad, cudaStream_t st, float target = 1.f, float* dzg = nullptr);
 int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, bool head_fused = false);
-int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, const float* rowscale = nullptr);
+int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, const float* rowscale = nullptr,
+                          float headless_gscale = 0.f);
 int launch_critic_head_light(const JrrModel* m, Workspace& w, int64_t B_logical, float w_pose, cudaStream_t st);
-int launch_critic_post(const JrrModel* m, const Workspace& w, const float* x6, cudaStream_t st);
+int launch_critic_post(const JrrModel* m, Workspace& w, const float* x6, cudaStream_t st, bool with_head = false,
+                       int64_t B_logical = 1, float w_pose = 0.f);
 int launch_shape_critic(const JrrModel* m, const Workspace& w, const float* betas, int64_t B_logical, cudaStream_t st);
 int critic_load_impl(JrrModel* m, const float* params, cudaStream_t st);
 int critic_grad_accumulate(JrrModel* m, Workspace& w, int64_t B_logical, const float* x6, float target, float* G_accum,

@@ -545,9 +545,11 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   if (const char* e = getenv("JRR_CRITIC_HEAD_FUSED")) m->critic_head_fused = (e[0] != '0');
   if (const char* e = getenv("JRR_CRITIC_TS")) m->critic_ts = (e[0] != '0');
   if (const char* e = getenv("JRR_SPLIT_ADAM")) m->split_adam = (e[0] != '0');
+  if (const char* e = getenv("JRR_CRITIC_HEADLESS")) m->critic_headless = (e[0] != '0');
   if (const char* e = getenv("JRR_LOSS_PATH")) m->folded = (e[0] == 'f' || e[0] == '1') && m->gemm_impl == 0;
   if (m->gemm_impl != 0) { m->fused_fwd = false; m->fused_bwd = false; m->critic_head_fused = false; }
   if (!m->critic_head_fused) m->critic_ts = false;
+  if (!m->critic_ts) m->critic_headless = false;
   // the active-vertex prefix is only walked by the two fused kernels; the stand-alone skinning
   // kernels always process every vertex, so compaction is tied to the fused configuration
   if (!(m->fused_fwd && m->fused_bwd)) m->compact_active = false;
