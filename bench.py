@@ -315,6 +315,8 @@ def main():
     for name, ms in acc.items():
         if ms <= 0 or (fused_fwd and name == "skin_fwd") or (fused_bwd and name == "blend_gemm_bwd"):
             continue
+        if name == "critic_head" and ms < 0.004:
+            continue                                     # head-less chain: an empty event interval
         if folded and name in ("skin_fwd", "skin_bwd", "dA_reduce"):
             continue                                     # empty event intervals on the folded path
         e = {"name": name, "ms": round(ms, 4)}
