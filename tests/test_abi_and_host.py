@@ -127,6 +127,46 @@ def test_two_rank_refit_allreduce_gloo(tmp_path):
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
 
 
+_WORKER_CRITIC = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import jrr_b200 as jrr
+from oracle import jrr_oracle as O
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+g = torch.Generator().manual_seed(3)
+n = 14
+fake = 0.7 * torch.randn(n, 24, 6, generator=g, dtype=torch.float64)
+real = 0.7 * torch.randn(n, 24, 6, generator=g, dtype=torch.float64)
+sd = {{k: v.double() for k, v in O.make_critic_state_dict(0).items()}}
+A = O.CriticAdam(sd, O.critic_train_loss, lr=1e-3)
+lo, hi = jrr.shard_range(n, rank, world)
+loss, grads = A.grad(fake[lo:hi], real[lo:hi], logical_batch=n)          # this rank's frames, GLOBAL divisor
+flat = torch.cat([grads[k].reshape(-1) for k in A.sd])                   # the 7.36 MB flat gradient of the C ABI
+l = torch.tensor([loss], dtype=torch.float64)
+dist.all_reduce(flat); dist.all_reduce(l)
+lf, gf = A.grad(fake, real)
+ff = torch.cat([gf[k].reshape(-1) for k in A.sd])
+assert flat.numel() == 1840153
+assert torch.allclose(flat, ff, atol=1e-13), (flat - ff).abs().max()
+assert abs(l.item() - lf) < 1e-13
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_critic_gradient_allreduce_gloo(tmp_path):
+    """world_size-2 gloo run of the critic training step's data flow (optimize.py:276-284 sharded): per-rank
+    gradient of MSE(D(fake),0)+MSE(D(real),1) with the GLOBAL divisor -> all-reduce == full-batch gradient."""
+    script = tmp_path / "worker_critic.py"
+    script.write_text(_WORKER_CRITIC.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29518", WORLD_SIZE="2", OMP_NUM_THREADS="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
 def test_precomputed_split_round_trip(tmp_path, jrr):
     """The reference's on-disk split layout (scripts/data.py:49-69): write, load, index, batch."""
     import pytest
