@@ -6,7 +6,7 @@ from . import utils  # noqa: F401
 from ._lib import JrrError, LIB_PATH  # noqa: F401
 from .discriminator import Discriminator, Shape_Discriminator  # noqa: F401
 from .native import NativeModel, flatten_critic_state_dict  # noqa: F401
-from .refine import CriticTrainer, PoseRefiner, RegressorRefit, load_j_regressor, save_j_regressor, shard_range  # noqa: F401
+from .refine import CriticTrainer, PoseRefiner, RegressorRefit, export_normalised_regressor, load_j_regressor, save_j_regressor, shard_range  # noqa: F401
 from .smpl import SMPL, SMPLFunction, SMPLOutput  # noqa: F401
 from .utils import evaluate, find_j_reg_mask, find_joints, move_pelvis, rot6d_to_rotmat, set_seed  # noqa: F401
 from .optimize import RefinementLoop  # noqa: F401

@@ -1,8 +1,21 @@
 """Pose critic with the reference's parameter layout (``scripts/discriminator.py:7-54``):
 ``conv_operations.{0,2}``, ``linears.{0..23}``, ``linear_operations.{0,2,4}`` -- a reference
 ``state_dict`` loads unchanged.  ``forward`` runs the CUDA kernels (fused 1x1 convs + heads,
-3xTF32 tensor-core GEMMs for 768->1024->1024).  The input gradient used by the refinement
-loop lives inside ``jrr_refine_step``; this module's forward is inference-only."""
+3xTF32 tensor-core GEMMs for 768->1024->1024).
+
+Limits of the drop-in (what differs from the reference ``nn.Module``):
+
+* ``forward`` is INFERENCE ONLY: the input is detached and no autograd graph is built, neither to
+  the input nor to the parameters.  The two gradients the reference loop takes through this
+  module live in the C ABI instead: the input gradient of ``MSE(D(x), 1)`` inside
+  ``jrr_refine_step`` (``PoseRefiner``), the parameter gradient of ``MSE(D(fake),0)+MSE(D(real),1)``
+  in ``jrr_critic_grad_accumulate`` / ``jrr_critic_apply`` (``CriticTrainer``).
+* ``bind(smpl.native())`` must be called first (the kernels need the device model); until then
+  ``forward`` raises.  There is no PyTorch or CPU path.
+* A bound module's ``forward`` writes ITS parameters into the native model's single critic slot
+  whenever they changed, replacing whatever is there -- including weights a ``CriticTrainer`` on
+  the same model has trained.  To score with the trained weights, load
+  ``CriticTrainer.state_dict()`` into the module first (or call ``native.critic_forward``)."""
 from __future__ import annotations
 
 import torch

@@ -108,6 +108,14 @@ class NativeModel:
         self._ws = None
         self._ws_B = 0
         self.launches = 0
+        # generation counters captured CUDA graphs are keyed on (refine.py): the workspace pointer, the
+        # regressor / packing, and everything else a captured launch sequence bakes in (loss path, shape critic)
+        self.ws_generation = 0
+        self.regressor_version = 0
+        self.config_generation = 0
+        # who set the current regressor: (J tensor, mask tensor, J._version) -- holders re-assert theirs
+        # (PoseRefiner / RegressorRefit) and utils.find_joints restores it after a call with another J
+        self._reg = None
 
     def __del__(self):
         try:
@@ -124,6 +132,7 @@ class NativeModel:
             self._ws = None
             self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
             self._ws_B = B
+            self.ws_generation += 1      # graphs that captured the old pointer must be re-captured
         off = (-self._ws.data_ptr()) % 256
         return C.c_void_p(self._ws.data_ptr() + off), C.c_size_t(self._ws.numel() - off)
 
@@ -141,7 +150,16 @@ class NativeModel:
         # the packed vertex order (and with it the workspace layout) may have been rebuilt
         self._ws = None
         self._ws_B = 0
-        self.regressor_version = getattr(self, "regressor_version", 0) + 1
+        self.regressor_version += 1
+        self._reg = (J17_raw, mask, J17_raw._version)
+
+    def holds_regressor(self, J17_raw, mask=None) -> bool:
+        """True when the model's normalised regressor was built from exactly this tensor (same storage, not
+        modified through torch since) and mask."""
+        r = self._reg
+        return (r is not None and r[0].data_ptr() == J17_raw.data_ptr() and r[0].device == J17_raw.device
+                and r[2] == J17_raw._version
+                and ((r[1] is None) == (mask is None)) and (mask is None or r[1].data_ptr() == mask.data_ptr()))
 
     def load_critic(self, state_dict: dict):
         flat = flatten_critic_state_dict(state_dict).to(self.device)
@@ -156,11 +174,12 @@ class NativeModel:
         with torch.cuda.device(self.device):
             check(self.L.jrr_set_loss_path(self.h, code, _stream()), "jrr_set_loss_path")
         self.loss_path = mode
-        self.regressor_version = getattr(self, "regressor_version", 0) + 1     # captured graphs hold the old launch sequence
+        self.config_generation += 1     # captured graphs hold the old launch sequence
 
     def load_shape_critic(self, state_dict, w_shape: float = 10.0):
         """Shape_Discriminator weights (scripts/discriminator.py:57-74) + the weight of its loss
         term (optimize.py:253).  ``state_dict=None`` switches the term off."""
+        self.config_generation += 1     # whether the term runs and its weight are baked into captured launches
         with torch.cuda.device(self.device):
             if state_dict is None:
                 check(self.L.jrr_shape_critic_load(self.h, None, 0.0, _stream()), "jrr_shape_critic_load")

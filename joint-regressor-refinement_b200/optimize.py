@@ -62,7 +62,13 @@ class RefinementLoop:
         x6_init, betas_init = x6.clone(), betas.clone()          # spin_pred_pose / spin_pred_betas
         out = {}
         use_2d = "gt_j2d" in batch and batch["gt_j2d"] is not None
-        if use_2d:
+        if n == 0:
+            # a rank whose shard of a short last batch is empty: no local kernels, but it still takes part in the
+            # all-reduces of the critic and regressor steps (zero gradient, zero loss) so the others do not block
+            out["refine_loss"] = torch.zeros(5, device=dev)
+            if use_2d:
+                out["cam"] = batch["cam"].to(dev).float().reshape(0, 3)
+        elif use_2d:
             gt2d = batch["gt_j2d"].to(dev).float().contiguous()
             cam = batch["cam"].to(dev).float().contiguous().clone()
             self.refiner.fit_camera(x6, betas, gt2d, cam, iters=self.cam_iters, logical_batch=LB)
@@ -71,7 +77,8 @@ class RefinementLoop:
             out["cam"] = cam
         else:
             loss = self.refiner.refine(x6, betas, gt, iters=self.refine_iters, logical_batch=LB)
-        out["refine_loss"] = loss.clone()
+        if n > 0:
+            out["refine_loss"] = loss.clone()
         lp, ls = self.trainer.step(x6, x6_init, betas if self.has_shape else None,
                                    betas_init if self.has_shape else None, logical_batch=LB)
         out["critic_loss"], out["shape_critic_loss"] = lp.clone(), (None if ls is None else ls.clone())

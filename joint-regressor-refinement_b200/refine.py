@@ -49,9 +49,17 @@ class PoseRefiner:
         self.launches_per_step = 0
 
     def set_regressor(self, J_regressor, mask=None):
-        self.native.set_regressor(J_regressor.to(self.device), None if mask is None else mask.to(self.device))
-        for st in getattr(self, "_bufs", {}).values():     # captured graphs hold the old packing's launch shapes
-            st["graph"] = None
+        # the refiner keeps its regressor and re-asserts it when somebody else (another refiner, a refit on
+        # another tensor, utils.find_joints with another J) has replaced the shared model's copy meanwhile
+        # (a device tensor is kept as it is, not copied: a refiner given RegressorRefit.J_regressor follows the refit's
+        # in-place updates and the two never displace each other)
+        self._J = J_regressor.detach().to(self.device)
+        self._mask = None if mask is None else mask.detach().to(self.device)
+        self._ensure_regressor()
+
+    def _ensure_regressor(self):
+        if not self.native.holds_regressor(self._J, self._mask):
+            self.native.set_regressor(self._J, self._mask)     # bumps regressor_version: graphs are re-captured
 
     def _buffers(self, B, two_d=False):
         st = self._bufs.get((B, two_d))
@@ -81,20 +89,32 @@ class PoseRefiner:
             self.native.refine_step(st["x6"], st["betas"], st["gt"], st["m"], st["v"], st["t"], self.lr,
                                     self.w_joint, self.w_pose, logical_batch=LB, loss_out=st["loss"])
 
-    def _run_chunk(self, st, iters, LB):
+    def _run_chunk(self, st, iters, LB, loss_history=None):
         for k in ("m", "v", "t", "cm", "cv"):
             if k in st:
                 st[k].zero_()
         if not self.use_graph:
-            for _ in range(iters):
+            for i in range(iters):
                 self._step(st, LB)
+                if loss_history is not None:
+                    loss_history[i].copy_(st["loss"], non_blocking=True)
             self.launches_per_step = self.native.launches
             return
-        ver = (getattr(self.native, "regressor_version", 0), st.get("w_2d"))     # w_2d is baked into a captured launch
+        # everything a captured launch sequence bakes in: the packing / regressor version, the workspace pointer,
+        # the loss path and shape-critic switch of the shared model, and the scalar arguments of the step
+        nat = self.native
+        nat.workspace(st["x6"].shape[0])      # grow (and bump the generation) BEFORE comparing, not inside the capture
+        ver = (nat.regressor_version, nat.ws_generation, nat.config_generation, st.get("w_2d"), self.lr, self.w_joint,
+               self.w_pose)
         if st["graph"] is None or st["LB"] != LB or st.get("ver") != ver:
             st["graphs"] = {}
             st["graph"], st["LB"], st["ver"] = self._capture(st, LB, 1), LB, ver
             st["graphs"][1] = st["graph"]
+        if loss_history is not None:       # the caller reads every iteration's loss: one-step graph + an async copy each
+            for i in range(iters):
+                st["graph"].replay()
+                loss_history[i].copy_(st["loss"], non_blocking=True)
+            return
         u = self.steps_per_graph
         if u > 1 and iters >= u:
             if u not in st["graphs"]:
@@ -127,6 +147,7 @@ class PoseRefiner:
         """optimize.py:187-199: camera-only Adam against the 2-D joints; `cam` [N,3] updated in place.
         One body-model forward per chunk (the joints do not depend on the camera)."""
         N = x6.shape[0]
+        self._ensure_regressor()
         with torch.cuda.device(self.device):
             for lo in range(0, N, self.chunk):
                 hi = min(N, lo + self.chunk)
@@ -142,6 +163,7 @@ class PoseRefiner:
         CUDA-graph replay as `refine`."""
         N = x6.shape[0]
         last = None
+        self._ensure_regressor()
         with torch.cuda.device(self.device):
             for lo in range(0, N, self.chunk):
                 hi = min(N, lo + self.chunk)
@@ -160,15 +182,22 @@ class PoseRefiner:
                 last = st["loss"]
         return last
 
-    def refine(self, x6, betas, gt_mm, iters=100, logical_batch=None):
+    def refine(self, x6, betas, gt_mm, iters=100, logical_batch=None, loss_history=None):
         """In-place refinement of x6 [N,24,6] / betas [N,10] against gt_mm [N,17,3] (mm,
         pelvis-centred).  Frames are processed in chunks of ``chunk``; each chunk is one
         reference "batch" (fresh Adam state; its size is the divisor of the mean losses unless
         ``logical_batch`` is given).  Returns the last iteration's [total, joint, pose, 2d, shape] loss
-        of the last chunk (device tensor)."""
+        of the last chunk (device tensor).
+
+        The tensors may live on the device or in (pinned) host memory: every chunk is copied into the
+        refiner's static device buffers, refined there and copied back, all asynchronously on the current
+        stream.  ``loss_history`` [iters,5] (device or pinned host) receives every iteration's loss terms of
+        the last chunk -- the per-iteration read-out of optimize.py:255-261 without a host sync (it costs the
+        multi-step graphs: iterations are then replayed one at a time)."""
         N = x6.shape[0]
         x6v, bv, gv = x6.view(N, 24, 6), betas.view(N, 10), gt_mm.view(N, 17, 3)
         last = None
+        self._ensure_regressor()
         with torch.cuda.device(self.device):
             for lo in range(0, N, self.chunk):
                 hi = min(N, lo + self.chunk)
@@ -177,7 +206,7 @@ class PoseRefiner:
                 st["x6"].copy_(x6v[lo:hi], non_blocking=True)
                 st["betas"].copy_(bv[lo:hi], non_blocking=True)
                 st["gt"].copy_(gv[lo:hi], non_blocking=True)
-                self._run_chunk(st, iters, B if logical_batch is None else logical_batch)
+                self._run_chunk(st, iters, B if logical_batch is None else logical_batch, loss_history)
                 x6v[lo:hi].copy_(st["x6"], non_blocking=True)
                 bv[lo:hi].copy_(st["betas"], non_blocking=True)
                 last = st["loss"]
@@ -202,13 +231,29 @@ class RegressorRefit:
         self.chunk = int(chunk)
         self.native.set_regressor(self.J, self.mask)
 
+    def _ensure_regressor(self):
+        # jrr_regressor_grad_accumulate / jrr_regressor_apply read the model's normalised copy: it must be the one
+        # built from THIS raw regressor
+        if not self.native.holds_regressor(self.J, self.mask):
+            self.native.set_regressor(self.J, self.mask)
+
+    def reset(self, J_regressor):
+        """Start over from `J_regressor` (values copied into the tensor this refit owns, Adam state zeroed)."""
+        self.J.copy_(J_regressor.detach().to(self.J.device).float())
+        self.m.zero_(); self.v.zero_(); self.t.zero_()
+        self.native.set_regressor(self.J, self.mask)
+
     def accumulate(self, x6, betas, gt_mm, logical_batch=None):
-        """G += dL/dJhat over these frames (L = MSE with divisor 51*logical_batch)."""
+        """G += dL/dJhat over these frames (L = MSE with divisor 51*logical_batch).  The frames may live on the
+        device or in (pinned) host memory; host chunks are uploaded asynchronously on the current stream."""
+        self._ensure_regressor()
         N = x6.shape[0]
         LB = N if logical_batch is None else int(logical_batch)
+        dev = self.native.device
+        up = lambda t: t if t.is_cuda else t.to(dev, non_blocking=True)
         for lo in range(0, N, self.chunk):
             hi = min(N, lo + self.chunk)
-            self.native.regressor_grad_accumulate(x6[lo:hi], betas[lo:hi], gt_mm[lo:hi], self.G, self.loss,
+            self.native.regressor_grad_accumulate(up(x6[lo:hi]), up(betas[lo:hi]), up(gt_mm[lo:hi]), self.G, self.loss,
                                                   logical_batch=LB)
 
     def step(self, x6=None, betas=None, gt_mm=None, logical_batch=None):
@@ -222,6 +267,7 @@ class RegressorRefit:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.G, op=dist.ReduceOp.SUM)
             dist.all_reduce(self.loss, op=dist.ReduceOp.SUM)
+        self._ensure_regressor()
         self.native.regressor_apply(self.J, self.mask, self.G, self.m, self.v, self.t, self.lr)
         return self.loss
 
@@ -300,3 +346,27 @@ def load_j_regressor(path, device="cpu"):
 def save_j_regressor(J, path):
     """Plain ``torch.save(tensor)`` so the artefact stays loadable by test.py:46-47."""
     torch.save(J.detach().clone(), path)
+
+
+def export_normalised_regressor(J, path=None, device=None):
+    """The regressor in the form VIBE / MEVA consume it (test.py:206-208,255-256,272-273: ``nn.ReLU()(J)`` divided by
+    its row sums, handed to ``model(image, J_regressor=...)``): returns relu(J) / rowsum, [17,6890] fp32 contiguous;
+    with ``path`` it is also written with plain ``torch.save(tensor)`` (the artefact's own format, see
+    ``save_j_regressor``).  ``J`` may be the raw tensor, a path to ``retrained_J_Regressor.pt`` or a ``RegressorRefit``.
+    The mask of utils.py:182-187 is all ones and therefore not applied.  A row without a positive entry would divide
+    by zero in the reference (NaN row); here that is an error."""
+    if isinstance(J, (str, bytes)) or hasattr(J, "__fspath__"):
+        J = load_j_regressor(J)
+    elif hasattr(J, "J_regressor"):
+        J = J.J_regressor
+    Jn = torch.relu(J.detach().float())
+    s = Jn.sum(dim=1, keepdim=True)
+    if bool((s <= 0).any()):
+        raise ValueError("export_normalised_regressor: a regressor row has no positive entry (the reference's "
+                         "normalisation, utils.py:91-92 / test.py:207-208, would produce NaN)")
+    Jn = (Jn / s).contiguous()
+    if device is not None:
+        Jn = Jn.to(device)
+    if path is not None:
+        torch.save(Jn.detach().cpu().clone(), path)
+    return Jn

@@ -116,6 +116,12 @@ class SMPL(nn.Module):
         self.register_buffer("faces_tensor", torch.as_tensor(np.asarray(md["faces"], dtype=np.int64)))
         self.faces = np.asarray(md["faces"])
         self.joint_map = torch.as_tensor(np.asarray(md["joint_map"], dtype=np.int64))
+        # smpl.py:75-76 regresses the 9 extra joints from the TRANSLATED vertices, so `transl` reaches them scaled by
+        # their regressor row sums (1 only when the rows are normalised); the other 45 joints get it unscaled
+        jm = np.asarray(md["joint_map"], dtype=np.int64)
+        rs = np.asarray(md["J_regressor_extra"], dtype=np.float64).sum(axis=1)
+        self.register_buffer("_transl_scale", torch.as_tensor(
+            np.where(jm >= 45, rs[np.clip(jm - 45, 0, len(rs) - 1)], 1.0).astype(np.float32)), persistent=False)
         # smplx default parameters (batch_size rows)
         self.betas = nn.Parameter(torch.zeros(batch_size, 10))
         self.global_orient = nn.Parameter(torch.zeros(batch_size, 3))
@@ -158,7 +164,7 @@ class SMPL(nn.Module):
             if transl.shape[0] != B:
                 transl = transl.expand(B, -1)
             verts = verts + transl[:, None]
-            joints = joints + transl[:, None]
+            joints = joints + transl[:, None] * self._transl_scale[None, :, None]
         return SMPLOutput(vertices=verts if return_verts else None, joints=joints, betas=betas,
                           global_orient=global_orient, body_pose=body_pose,
                           full_pose=full if return_full_pose else None)

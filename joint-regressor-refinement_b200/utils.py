@@ -40,14 +40,25 @@ def find_joints(smpl, shape, orient, pose, J_regressor, mask=None, return_verts=
         pred = torch.matmul(Jn.to(verts.device)[None], verts)
         return (pred, verts) if return_verts else pred
     native = smpl.native()
-    # like the reference (utils.py:87-92) the regressor is re-normalised on every call: three
-    # tiny kernels; the refinement loop itself normalises once per regressor version
-    native.set_regressor(J_regressor.to(native.device), None if mask is None else mask.to(native.device))
+    # The reference's find_joints is stateless (utils.py:87-92 re-normalises on every call); the CUDA model keeps
+    # ONE normalised regressor, shared with PoseRefiner / RegressorRefit.  When this call's J is not the one the
+    # model holds it is installed for the call and the previous one is put back afterwards, so a comparison run
+    # with another regressor does not change what the refinement loop optimises against.
+    J = J_regressor.detach().to(native.device)
+    m = None if mask is None else mask.detach().to(native.device)
+    prev = None
+    if not native.holds_regressor(J, m):
+        prev = native._reg
+        native.set_regressor(J, m)
     B = max(shape.shape[0], pose.shape[0])
     full = torch.cat([orient.reshape(-1, 1, 3, 3).expand(B, -1, -1, -1),
                       pose.reshape(-1, 23, 3, 3).expand(B, -1, -1, -1)], dim=1).reshape(B, 24, 9)
     betas = shape if shape.shape[0] == B else shape.expand(B, -1)
-    return native.find_joints(betas, full, POSE_ROTMAT)
+    try:
+        return native.find_joints(betas, full, POSE_ROTMAT)
+    finally:
+        if prev is not None:
+            native.set_regressor(prev[0], prev[1])
 
 
 def move_pelvis(j3ds: torch.Tensor) -> torch.Tensor:

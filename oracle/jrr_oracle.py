@@ -52,7 +52,7 @@ def lbs(betas, rot_mats, v_template, shapedirs, posedirs, J_regressor, parents, 
     # 2. rest joints
     J = torch.einsum('jv,bvk->bjk', J_regressor, v_shaped)
     # 3. pose blend (joint-major, row-major 3x3)
-    eye = torch.eye(3, dtype=dtype)
+    eye = torch.eye(3, dtype=dtype, device=rot_mats.device)
     pose_feature = (rot_mats[:, 1:] - eye).reshape(B, -1)
     v_posed = v_shaped + (pose_feature @ posedirs).view(B, -1, 3)
     # 4. kinematic chain
@@ -77,18 +77,18 @@ class OracleSMPL:
     ``smpl(betas=, body_pose=, global_orient=, pose2rot=)`` -> object with ``.vertices``
     [B,6890,3] and ``.joints`` [B,49,3]."""
 
-    def __init__(self, model: dict, dtype=torch.float32):
+    def __init__(self, model: dict, dtype=torch.float32, device="cpu"):
         self.dtype = dtype
-        t = lambda k: torch.as_tensor(model[k]).to(dtype)
+        t = lambda k: torch.as_tensor(model[k]).to(device=device, dtype=dtype)
         self.v_template = t("v_template")
         self.shapedirs = t("shapedirs")
         self.posedirs = t("posedirs")
         self.J_regressor = t("J_regressor")
         self.lbs_weights = t("lbs_weights")
         self.J_regressor_extra = t("J_regressor_extra")
-        self.parents = torch.as_tensor(model["parents"]).long()
-        self.joint_map = torch.as_tensor(model["joint_map"]).long()
-        self.vertex_picks = torch.as_tensor(model["vertex_picks"]).long()
+        self.parents = torch.as_tensor(model["parents"]).long()          # host: the chain loop indexes it
+        self.joint_map = torch.as_tensor(model["joint_map"]).long().to(device)
+        self.vertex_picks = torch.as_tensor(model["vertex_picks"]).long().to(device)
 
     def __call__(self, betas=None, body_pose=None, global_orient=None, transl=None,
                  return_verts=True, return_full_pose=False, pose2rot=True, **kwargs):
@@ -301,7 +301,7 @@ def refine_loss(smpl, Jraw, critic_sd, x6, betas, gt_mm, w_joint=10000.0, w_pose
     LB = B if logical_batch is None else logical_batch
     joint_loss = (diff ** 2).sum() / (LB * 17 * 3)
     total = w_joint * joint_loss
-    pose_loss = torch.zeros((), dtype=x6.dtype)
+    pose_loss = torch.zeros((), dtype=x6.dtype, device=x6.device)
     if critic_sd is not None and w_pose != 0:
         sig = discriminator_forward(critic_sd, x6)
         pose_loss = ((sig - 1) ** 2).sum() / (LB * 25)

@@ -2,6 +2,10 @@
 (run in the build container, where /root/reference exists):
 
   j_regressor_nnz.npz   the 107 non-zeros of models/retrained_J_Regressor.pt (+ its sha256)
+  retrained_J_Regressor.pt   the artefact itself, byte for byte (469 240 B of weights saved from cuda:0,
+                        requires_grad, column-major): /root/reference does not exist on the GPU box, and
+                        "loads unchanged" can only be shown on the real bytes (bench.py --regressor shipped
+                        and the loader tests read it through jrr_b200.load_j_regressor)
   ref_utils_golden.npz  inputs/outputs of the reference's rot6d_to_rotmat, move_pelvis,
                         find_joints (on the oracle SMPL), evaluate, Discriminator.forward,
                         computed by importing /root/reference/scripts/{utils,discriminator}.py
@@ -28,6 +32,8 @@ def main():
     art = os.path.join(REF, "models", "retrained_J_Regressor.pt")
     sha = hashlib.sha256(open(art, "rb").read()).hexdigest()
     J = torch.load(art, map_location="cpu", weights_only=True).detach().contiguous()
+    import shutil
+    shutil.copyfile(art, os.path.join(HERE, "retrained_J_Regressor.pt"))
     r, c = torch.nonzero(J, as_tuple=True)
     np.savez(os.path.join(HERE, "j_regressor_nnz.npz"), row=r.numpy().astype(np.int32),
              col=c.numpy().astype(np.int32), val=J[r, c].numpy(), sha256=np.array(sha))

@@ -207,7 +207,7 @@ def test_bench_reference_arm_prints_one_contract_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--frames", "512"],
                        capture_output=True, text=True, timeout=300, cwd=root)
     assert r.returncode == 0, r.stderr[-500:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -216,4 +216,31 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "refine_step_poses_per_sec" and d["unit"] == "poses/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["config"]["frames_per_gpu"] == 512 and d["config"]["regressor"] == "dense"      # same keys as the CUDA arm's config
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_export_normalised_regressor_round_trip(tmp_path, jrr, oracle, J_shipped):
+    """the pre-normalised form VIBE / MEVA take (test.py:206-208: ReLU, divide by the row sums) --
+    values against the pinned oracle normalisation, file round trip in the artefact's torch.save format, and the
+    consumer's own normalisation applied on top is the identity (so handing either form to test.py is safe)."""
+    import torch
+    p = tmp_path / "J_regressor_normalised.pt"
+    Jn = jrr.export_normalised_regressor(J_shipped, str(p))
+    assert Jn.shape == (17, 6890) and Jn.is_contiguous() and Jn.dtype == torch.float32
+    assert torch.equal(Jn, oracle.normalise_regressor(J_shipped, oracle.find_j_reg_mask(J_shipped)))
+    assert torch.allclose(Jn.sum(1), torch.ones(17), atol=1e-6) and (Jn >= 0).all()
+    assert (Jn[J_shipped <= 0] == 0).all()
+    back = jrr.load_j_regressor(str(p))
+    assert torch.equal(back, Jn)
+    again = torch.relu(back) / torch.relu(back).sum(1, keepdim=True)          # test.py:206-208 on the exported file
+    assert (again - Jn).abs().max() < 1e-7
+    # accepts the artefact path directly
+    raw = tmp_path / "raw.pt"
+    jrr.save_j_regressor(J_shipped, str(raw))
+    assert torch.equal(jrr.export_normalised_regressor(str(raw)), Jn)
+    bad = J_shipped.clone()
+    bad[3] = -bad[3].abs()
+    import pytest
+    with pytest.raises(ValueError, match="no positive entry"):
+        jrr.export_normalised_regressor(bad)

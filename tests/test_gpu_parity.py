@@ -870,3 +870,234 @@ def test_multi_step_graph_is_bit_identical(path, smpl_tc, jrr, critic_sd, J_ship
         smpl_tc.native().set_loss_path("vertex")
     for x6, be, loss in res[1:]:
         assert torch.equal(x6, res[0][0]) and torch.equal(be, res[0][1]) and torch.equal(loss, res[0][2])
+
+
+# ------------------------------------------------------------------ the configuration bench.py headlines
+# (C2: 4096 frames, DENSE 17x6890 regressor, loss 10000*joint + 10*critic, both formulations of the loss path) against
+# the oracle itself -- the loop of optimize.py:220-265.  Frames couple only through the divisors of the two mean
+# losses, so the oracle runs in chunks with logical_batch = 4096 (tests/test_oracle.py::test_shards_reproduce_...).
+BENCH_B = 4096
+
+
+def _frames_chunked(jrr, oracle, osmpl, J, n, seed, chunk=512):
+    inp = jrr.synthetic.make_pose_inputs(n, seed)
+    t = {k: torch.from_numpy(v) for k, v in inp.items()}
+    t["gt_mm"] = torch.cat([oracle.make_gt(osmpl, J, t["true_rotmat"][lo:lo + chunk], t["true_betas"][lo:lo + chunk],
+                                           t["gt_noise"][lo:lo + chunk]) for lo in range(0, n, chunk)])
+    return t
+
+
+@pytest.fixture(scope="module")
+def bench_frames(jrr, oracle, osmpl32, J_dense):
+    return _frames_chunked(jrr, oracle, osmpl32, J_dense, BENCH_B, 0)
+
+
+@pytest.fixture(scope="module")
+def bench_oracle_fp64_step(oracle, osmpl64, J_dense, critic_sd, bench_frames):
+    """fp64 oracle losses and gradient [4096,154] of ONE iteration on the bench inputs."""
+    fr, n, chunk = bench_frames, BENCH_B, 512
+    sd64 = {k: v.double() for k, v in critic_sd.items()}
+    tot = jl = pl = 0.0
+    grads = []
+    for lo in range(0, n, chunk):
+        x6 = fr["x6"][lo:lo + chunk].double().requires_grad_(True)
+        be = fr["betas"][lo:lo + chunk].double().requires_grad_(True)
+        t, j, p, _ = oracle.refine_loss(osmpl64, J_dense.double(), sd64, x6, be, fr["gt_mm"][lo:lo + chunk].double(),
+                                        logical_batch=n)
+        t.backward()
+        tot, jl, pl = tot + t.item(), jl + j.item(), pl + p.item()
+        grads.append(torch.cat([x6.grad.reshape(-1, 144), be.grad], dim=1))
+    return tot, jl, pl, torch.cat(grads)
+
+
+@pytest.mark.parametrize("path", ["folded", "vertex"])
+def test_bench_config_one_step_vs_fp64_oracle(path, smpl_tc, jrr, critic_sd, J_dense, bench_frames, bench_oracle_fp64_step):
+    """B = 4096, dense regressor, one Adam iteration from zero state: the three losses within 1e-5 relative and the
+    gradient (Adam's first moment after one step is 0.1*g) within 1e-4 of its max against the fp64 oracle."""
+    fr = bench_frames
+    tot, jl, pl, gall = bench_oracle_fp64_step
+    try:
+        ref = jrr.PoseRefiner(smpl_tc, J_dense, critic_sd, use_graph=False, loss_path=path, chunk=BENCH_B)
+        st = ref._buffers(BENCH_B)
+        st["x6"].copy_(fr["x6"]); st["betas"].copy_(fr["betas"]); st["gt"].copy_(fr["gt_mm"])
+        ref._run_chunk(st, 1, BENCH_B)
+        torch.cuda.synchronize()
+    finally:
+        smpl_tc.native().set_loss_path("vertex")
+    loss = st["loss"].cpu().double()
+    m = st["m"].cpu().double() * 10
+    err = (m - gall).abs().max().item() / gall.abs().max().item()
+    print(f"[{path}] B=4096 dense: loss {loss[0].item():.6f} vs fp64 oracle {tot:.6f}; joint {loss[1].item():.4e} vs {jl:.4e}; "
+          f"pose {loss[2].item():.6f} vs {pl:.6f}; gradient rel err {err:.2e}")
+    assert abs(loss[0].item() - tot) / tot < 1e-5
+    assert abs(loss[1].item() - jl) / jl < 1e-5
+    assert abs(loss[2].item() - pl) / pl < 1e-5
+    assert err < 1e-4
+
+
+@pytest.mark.parametrize("path", ["folded", "vertex"])
+def test_bench_config_10_iterations_vs_fp32_oracle(path, smpl_tc, jrr, oracle, osmpl32, critic_sd, J_dense, bench_frames):
+    """B = 4096, dense regressor, 10 Adam iterations through the replayed CUDA graph against the fp32 oracle's
+    trajectory (torch.optim.Adam): per-iteration loss, refined parameters."""
+    fr, n, chunk = bench_frames, BENCH_B, 512
+    xs, bs, hist = [], [], None
+    for lo in range(0, n, chunk):
+        x6o, bo, h = oracle.refine(osmpl32, J_dense, critic_sd, fr["x6"][lo:lo + chunk], fr["betas"][lo:lo + chunk],
+                                   fr["gt_mm"][lo:lo + chunk], iters=10, logical_batch=n)
+        xs.append(x6o); bs.append(bo)
+        h = torch.tensor(h, dtype=torch.float64)
+        hist = h if hist is None else hist + h
+    x6o, bo = torch.cat(xs), torch.cat(bs)
+    try:
+        ref = jrr.PoseRefiner(smpl_tc, J_dense, critic_sd, use_graph=True, loss_path=path, chunk=BENCH_B, steps_per_graph=5)
+        x6, be = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+        loss = ref.refine(x6, be, fr["gt_mm"].to(DEV), iters=10).cpu()
+    finally:
+        smpl_tc.native().set_loss_path("vertex")
+    dx, db = (x6.cpu() - x6o).abs(), (be.cpu() - bo).abs()
+    moved = (x6o - fr["x6"]).abs().mean().item()
+    print(f"[{path}] B=4096 dense, 10 iterations: final loss {loss[0].item():.6f} vs oracle {hist[-1, 0].item():.6f}; "
+          f"max |dx6| {dx.max().item():.2e} mean {dx.mean().item():.2e} (mean travel {moved:.2e}); max |dbetas| {db.max().item():.2e}")
+    assert abs(loss[0].item() - hist[-1, 0].item()) / hist[-1, 0].item() < 1e-4
+    assert abs(loss[1].item() - hist[-1, 1].item()) / hist[-1, 1].item() < 1e-4
+    assert dx.mean().item() < 1e-5 and db.mean().item() < 1e-5
+    # Adam divides by sqrt(v): where a gradient is ~0 round-off decides the sign of a lr-sized move, so the worst
+    # element is bounded by a few steps of lr, not by the arithmetic's precision
+    assert dx.max().item() < 2e-3 and db.max().item() < 2e-3
+
+
+def test_dense_regressor_100_iterations_both_paths(smpl_tc, jrr, oracle, osmpl32, critic_sd, J_dense):
+    """256 frames x 100 Adam iterations with the DENSE 17x6890 regressor (the reduction bench.py headlines), both
+    formulations: refined MPJPE within 0.01 mm of the oracle's, and the recorded bound on the parameter distance."""
+    n = 256
+    fr = _frames_chunked(jrr, oracle, osmpl32, J_dense, n, 5)
+    x6o, bo, hist = oracle.refine(osmpl32, J_dense, critic_sd, fr["x6"], fr["betas"], fr["gt_mm"], iters=100)
+    Ro = oracle.rot6d_to_rotmat(x6o.reshape(-1, 6)).view(-1, 24, 3, 3)
+    mp_o, pa_o = oracle.evaluate(oracle.find_joints(osmpl32, bo, Ro[:, :1], Ro[:, 1:], J_dense), fr["gt_mm"])
+    R0 = oracle.rot6d_to_rotmat(fr["x6"].reshape(-1, 6)).view(-1, 24, 3, 3)
+    mp_0, _ = oracle.evaluate(oracle.find_joints(osmpl32, fr["betas"], R0[:, :1], R0[:, 1:], J_dense), fr["gt_mm"])
+    try:
+        for path in ("folded", "vertex"):
+            ref = jrr.PoseRefiner(smpl_tc, J_dense, critic_sd, loss_path=path)
+            x6, be = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+            loss = ref.refine(x6, be, fr["gt_mm"].to(DEV), iters=100)
+            R = oracle.rot6d_to_rotmat(x6.cpu().reshape(-1, 6)).view(-1, 24, 3, 3)
+            mp_c, pa_c = oracle.evaluate(oracle.find_joints(osmpl32, be.cpu(), R[:, :1], R[:, 1:], J_dense), fr["gt_mm"])
+            dx = (x6.cpu() - x6o).abs()
+            print(f"[{path}] dense, 256 frames x 100 iterations: MPJPE {mp_0:.3f} -> oracle {mp_o:.4f} / cuda {mp_c:.4f} mm, "
+                  f"PA {pa_o:.4f} / {pa_c:.4f}; loss {hist[-1][0]:.6f} / {loss[0].item():.6f}; max |dx6| {dx.max().item():.2e} "
+                  f"mean {dx.mean().item():.2e}")
+            assert mp_c < mp_0
+            assert abs(mp_c - mp_o) < 0.01 and abs(pa_c - pa_o) < 0.01
+            assert abs(loss[0].item() - hist[-1][0]) / hist[-1][0] < 1e-3
+            assert dx.max().item() < 5e-3 and dx.mean().item() < 5e-5
+    finally:
+        smpl_tc.native().set_loss_path("vertex")
+
+
+def test_shipped_100_iterations_records_parameter_distance(smpl_tc, jrr, oracle, osmpl32, critic_sd, J_shipped, frames64):
+    """The bound test_refine_100_iterations_mpjpe only printed (round 1: 2.9e-4), asserted so a regression shows."""
+    fr = frames64
+    x6o, bo, _ = oracle.refine(osmpl32, J_shipped, critic_sd, fr["x6"], fr["betas"], fr["gt_mm"], iters=100)
+    ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd)
+    x6, be = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+    ref.refine(x6, be, fr["gt_mm"].to(DEV), iters=100)
+    d = (x6.cpu() - x6o).abs()
+    print(f"shipped, 64 frames x 100 iterations: max |dx6| {d.max().item():.2e} mean {d.mean().item():.2e}; "
+          f"max |dbetas| {(be.cpu() - bo).abs().max().item():.2e}")
+    assert d.max().item() < 1.5e-3 and d.mean().item() < 2e-5
+    assert (be.cpu() - bo).abs().max().item() < 1.5e-3
+
+
+# ------------------------------------------------------------------ advisor findings of round 1
+def test_workspace_growth_recaptures_graphs(smpl_tc, jrr, critic_sd, J_shipped, frames64):
+    """A captured graph bakes the workspace pointer in; a later call with a larger batch reallocates the shared
+    workspace.  The refiner must notice (generation counter) and re-capture instead of replaying into freed memory."""
+    fr = frames64
+    nat = smpl_tc.native()
+    gt = fr["gt_mm"].to(DEV)
+    ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, use_graph=True)
+    xa, ba = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+    ref.refine(xa, ba, gt, iters=7)
+    gen = nat.ws_generation
+    big = jrr.synthetic.make_pose_inputs(1500, 3)
+    R = torch.from_numpy(big["true_rotmat"]).to(DEV)
+    out = smpl_tc(betas=torch.from_numpy(big["true_betas"]).to(DEV), body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False)
+    junk = [torch.full((1 << 22,), float("nan"), device=DEV) for _ in range(8)]      # re-use of the freed block would show
+    assert nat.ws_generation > gen
+    xb, bb = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+    ref.refine(xb, bb, gt, iters=7)
+    torch.cuda.synchronize()
+    assert torch.equal(xa, xb) and torch.equal(ba, bb)
+    assert all(torch.isnan(j).all() for j in junk) and torch.isfinite(out.vertices).all()
+
+
+def test_find_joints_with_another_regressor_leaves_the_loop_alone(smpl_tc, jrr, oracle, osmpl32, critic_sd, J_shipped, J_dense, frames64):
+    """utils.find_joints is stateless in the reference: calling it with another regressor in between (e.g. to compare
+    the initial regressor with the retrained one) must not change what PoseRefiner / RegressorRefit work against."""
+    fr = frames64
+    gt = fr["gt_mm"].to(DEV)
+    R = fr["true_rotmat"].to(DEV)
+    b = fr["true_betas"].to(DEV)
+    ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd)
+    refit = jrr.RegressorRefit(smpl_tc, J_shipped, lr=1e-2)
+    xa, ba = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+    ref.refine(xa, ba, gt, iters=5)
+    Ja = jrr.RegressorRefit(smpl_tc, J_shipped, lr=1e-2)
+    la = Ja.step(xa, ba, gt).item()
+    # interleave a foreign regressor
+    ref2 = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd)
+    xb, bb = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+    with torch.no_grad():
+        other = jrr.find_joints(smpl_tc, b, R[:, :1], R[:, 1:], J_dense.to(DEV))
+    expect = oracle.find_joints(osmpl32, fr["true_betas"], fr["true_rotmat"][:, :1], fr["true_rotmat"][:, 1:], J_dense)
+    assert rel(other, expect) < 1e-5
+    ref2.refine(xb, bb, gt, iters=5)
+    with torch.no_grad():
+        jrr.find_joints(smpl_tc, b, R[:, :1], R[:, 1:], J_dense.to(DEV))
+    lb = refit.step(xb, bb, gt).item()
+    assert torch.equal(xa, xb) and torch.equal(ba, bb)
+    assert la == lb and torch.equal(Ja.J_regressor, refit.J_regressor)
+
+
+def test_changed_scalars_and_shape_critic_invalidate_graphs(smpl_tc, jrr, oracle, critic_sd, J_shipped, frames64):
+    """lr / loss weights / the shape-critic switch are baked into captured launches: changing them after a capture
+    must take effect (graph key), exactly as on the eager path."""
+    fr = frames64
+    gt = fr["gt_mm"].to(DEV)
+
+    def run(refiner):
+        x, b = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+        refiner.refine(x, b, gt, iters=3)
+        return x, b
+    g = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, use_graph=True, steps_per_graph=1)
+    e = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, use_graph=False)
+    run(g)
+    g.lr = e.lr = 3e-3
+    g.w_joint = e.w_joint = 5000.0
+    xg, bg = run(g); xe, be_ = run(e)
+    assert torch.equal(xg, xe) and torch.equal(bg, be_)
+    try:
+        smpl_tc.native().load_shape_critic(oracle.make_shape_critic_state_dict(5), 10.0)
+        xg2, bg2 = run(g); xe2, be2 = run(e)
+        assert torch.equal(xg2, xe2) and torch.equal(bg2, be2) and not torch.equal(bg2, bg)
+    finally:
+        smpl_tc.native().load_shape_critic(None)
+
+
+def test_transl_reaches_unnormalised_extra_joints(jrr, model, oracle):
+    """smpl.py:75-76 regresses the 9 extra joints from the TRANSLATED vertices: with J_regressor_extra rows that do not
+    sum to 1 the translation arrives scaled by the row sum (advisor finding, round 1)."""
+    md = dict(model)
+    ex = model["J_regressor_extra"].copy()
+    ex[2] *= 1.7
+    ex[5] *= 0.4
+    md["J_regressor_extra"] = ex
+    m = jrr.SMPL(model_dict=md, batch_size=3, create_transl=True).to(DEV)
+    o = oracle.OracleSMPL(md)
+    g = torch.Generator().manual_seed(1)
+    betas, go, bp = torch.randn(3, 10, generator=g), torch.randn(3, 3, generator=g), 0.2 * torch.randn(3, 69, generator=g)
+    tr = torch.randn(3, 3, generator=g)
+    out = m(betas=betas.to(DEV), global_orient=go.to(DEV), body_pose=bp.to(DEV), transl=tr.to(DEV))
+    ref = o(betas=betas, global_orient=go, body_pose=bp, transl=tr)
+    assert rel(out.joints, ref.joints) < 1e-5 and rel(out.vertices, ref.vertices) < 1e-5

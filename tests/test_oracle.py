@@ -133,3 +133,30 @@ def test_folded_operator_is_exact(oracle, osmpl64, J_shipped, jrr):
         assert T.shape == (24, 17, 3, 218) and c.shape == (24, 17)
         got = oracle.find_joints_folded(osmpl64, b, R, T, c)
         assert (got - ref).abs().max().item() < 1e-12
+
+
+def test_independent_lbs_statement_agrees(oracle, osmpl64, model, jrr):
+    """oracle.lbs vs the second statement written from the SMPL paper (oracle/lbs_independent.py: NumPy
+    per-vertex loops, matrix-exponential rotations, inverted rest-pose transforms; no shared code).  The smplx
+    boundary cannot be pinned offline; two independent formulations agreeing is what can be shown instead."""
+    from oracle import lbs_independent as I2
+    inp = jrr.synthetic.make_pose_inputs(2, 123)
+    g = torch.Generator().manual_seed(7)
+    aa = torch.cat([torch.randn(2, 1, 3, generator=g, dtype=torch.float64),
+                    0.4 * torch.randn(2, 23, 3, generator=g, dtype=torch.float64)], dim=1)
+    betas = torch.from_numpy(inp["true_betas"]).double()
+    out = osmpl64(betas=betas, body_pose=aa[:, 1:].reshape(2, 69), global_orient=aa[:, 0], pose2rot=True)
+    for b in range(2):
+        rot = np.stack([I2.rotation_from_axis_angle(aa[b, k].numpy()) for k in range(24)])
+        verts, pj = I2.smpl_forward_one(model, betas[b].numpy(), rot)
+        j49 = I2.joints49_one(model, verts, pj)
+        ev = np.abs(verts - out.vertices[b].numpy()).max() / np.abs(verts).max()
+        ej = np.abs(j49 - out.joints[b].numpy()).max() / np.abs(j49).max()
+        # smplx's Rodrigues adds 1e-8 inside the norm: the two rotations differ by ~1e-8 relative
+        assert ev < 5e-8 and ej < 5e-8, (ev, ej)
+    # rotation matrices handed over directly (pose2rot=False, the refinement loop's call): no Rodrigues in between
+    R = torch.from_numpy(inp["true_rotmat"]).double()
+    out = osmpl64(betas=betas, body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False)
+    verts, pj = I2.smpl_forward_one(model, betas[0].numpy(), R[0].numpy())
+    assert np.abs(verts - out.vertices[0].numpy()).max() < 1e-12
+    assert np.abs(I2.joints49_one(model, verts, pj) - out.joints[0].numpy()).max() < 1e-12

@@ -178,3 +178,16 @@ def test_live_reference_find_crop(oracle, jrr):
         a, b, c, _, _ = jrr.data.crop_window(bb)
         assert torch.allclose(a, mnx, atol=1e-3) and torch.allclose(b, mny, atol=1e-3) and torch.allclose(c, sc)
         assert torch.allclose(jrr.data.cropped_intrinsics(intr, bb, img_size=size), io, atol=1e-3)
+
+
+def test_committed_artefact_bytes_load_unchanged(jrr, J_shipped):
+    """tests/golden/retrained_J_Regressor.pt is the reference artefact byte for byte (make_golden.py), so this runs on
+    the GPU box too, where /root/reference is absent: cuda:0 device tag, requires_grad and stride (1,17) all go through
+    load_j_regressor (test.py:46-47 loads it without map_location and needs a GPU for that)."""
+    path = os.path.join(GOLDEN, "retrained_J_Regressor.pt")
+    assert hashlib.sha256(open(path, "rb").read()).hexdigest() == \
+        "4ea32d1b3b9a135130722218f87eadfcf78321cf2ca6954e14f780eb9b60d079"
+    J = jrr.load_j_regressor(path)
+    assert J.shape == (17, 6890) and J.is_contiguous() and not J.requires_grad and J.dtype == torch.float32
+    assert torch.equal(J, J_shipped)
+    assert int((J != 0).sum()) == 107 and int((J > 0).sum()) == 62
