@@ -537,6 +537,7 @@ extern "C" int jrr_debug_gemm(JrrModel* m, int impl, int64_t M, int64_t N, int64
     JRR_LAUNCH_CHECK();
     GemmDesc g{};
     g.a_via_tmem = true;
+    g.probe_env = true;
     g.A_hi = A; g.lda = K; g.B_hi = Bh2; g.B_lo = Bl2; g.ldb = K;
     g.M = M; g.N = N; g.K = K; g.ksplit = 1; g.epi = EPI_STORE_SPLITK;
     g.out0 = C; g.ldo = N;

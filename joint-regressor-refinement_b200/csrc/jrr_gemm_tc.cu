@@ -37,6 +37,9 @@ struct TcParams {
   const float* rowscale;   // EPI_MASK_SPLIT: multiply row m by rowscale[m] (or nullptr)
   const float* vec;        // EPI_BIAS_RELU_HEAD: w3[N]
   float* out2;             // EPI_BIAS_RELU_HEAD: zg_part[n_tile][M]
+  int probe;               // diagnostic only (JRR_GEMM_PROBE, benchmarks/gemm_probe.py): bit 0 = MMAs do not wait for the
+                           // A producers (garbage A; shows the loop's pace without the smem->TMEM staging chain),
+                           // bit 1 = skip the A_hi.B_lo MMA, bit 2 = skip the A_lo.B_hi MMA as well (results wrong)
 };
 
 template <int BN>
@@ -143,7 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
       for (int kb = 0; kb < num_kb; kb++) {
         if (lane == 0) {
-          mbar_wait(TS ? &ready_bar[stage] : &full_bar[stage], phase);   // TS: the producers waited for the TMA
+          mbar_wait((TS && !(p.probe & 1)) ? &ready_bar[stage] : &full_bar[stage], phase);   // TS: the producers waited for the TMA
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t dAh = make_sdesc(sa);
@@ -154,7 +157,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / 8; k++) {
             const uint64_t ko = (uint64_t)(k * 32 >> 4);  // 8 tf32 = 32 bytes along K
-            if (TS) {
+            if (TS && p.probe) {
+              if (!(p.probe & 4)) tc_mma_tf32_ts(d_tmem, ta + 32 + k * 8, dBh + ko, idesc, 1);
+              if (!(p.probe & 2)) tc_mma_tf32_ts(d_tmem, ta + k * 8, dBl + ko, idesc, 1);
+              tc_mma_tf32_ts(d_tmem, ta + k * 8, dBh + ko, idesc, 1);
+            } else if (TS) {
               tc_mma_tf32_ts(d_tmem, ta + 32 + k * 8, dBh + ko, idesc, (kb | k) != 0);
               tc_mma_tf32_ts(d_tmem, ta + k * 8, dBl + ko, idesc, 1);
               tc_mma_tf32_ts(d_tmem, ta + k * 8, dBh + ko, idesc, 1);
@@ -172,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (TS && warp >= 6) {
+  } else if (TS && warp >= 6 && !(p.probe & 1)) {
     // ===================== A producers (warps 6..9): global fp32 -> tf32 hi/lo -> TMEM =====================
     const int q = warp & 3;                      // TMEM lane quarter of this warp
     const int row = q * 32 + lane;               // A-tile row = TMEM lane
@@ -395,8 +402,17 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = std::min(tiles, device_num_sms(m->device));
-  kern<<<grid, TS ? TC_THREADS_TS : TC_THREADS, smem_bytes, st>>>(mAh, mAl, mBh, mBl, p);
-  JRR_LAUNCH_CHECK();
+  int reps = 1;
+  if (g.probe_env) {       // jrr_debug_gemm only: diagnostic knobs for benchmarks/gemm_probe.py
+    const char* e = getenv("JRR_GEMM_PROBE");
+    p.probe = e ? atoi(e) : 0;
+    e = getenv("JRR_GEMM_PROBE_REPS");
+    reps = e ? std::max(1, atoi(e)) : 1;
+  }
+  for (int r = 0; r < reps; r++) {
+    kern<<<grid, TS ? TC_THREADS_TS : TC_THREADS, smem_bytes, st>>>(mAh, mAl, mBh, mBl, p);
+    JRR_LAUNCH_CHECK();
+  }
   return JRR_OK;
 }
 

@@ -258,6 +258,7 @@ struct GemmDesc {
                                            // (EPI_MASK_SPLIT) row scale = gscale * (s - 1) s (1 - s), s = sigmoid(bias +
                                            // sum of the row's logit partials), zero for rows >= rows_valid
   int64_t k_valid;                         // > 0: only the first k_valid columns of A exist (TMA zero-fills the rest of K)
+  bool probe_env;                          // jrr_debug_gemm: honour the JRR_GEMM_PROBE* diagnostic environment knobs
   bool a_via_tmem;                         // A is plain fp32 (A_hi): loaded, tf32-split and staged in tensor memory by the
                                            // kernel (B stays pre-split); *_SPLIT epilogues then write ONE fp32 array (out0)
 };
