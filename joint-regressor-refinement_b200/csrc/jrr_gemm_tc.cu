@@ -57,6 +57,106 @@ struct TcCfg {
   static constexpr int SMEM_BYTES_TS = STAGES_TS * STAGE_BYTES_TS + 1024 + 256;
 };
 
+// One accumulator row (thread = row m = TMEM lane, BN columns starting at TMEM address `trow`) through the fused epilogue.
+template <int BN, int EPI, bool TS>
+__device__ __forceinline__ void tc_epilogue_row(const TcParams& p, const uint32_t trow, const int64_t m, const int nb,
+                                                const int split) {
+  float zsum = 0.f;   // EPI_BIAS_RELU_HEAD: this row's share of the global head's logit
+  float rs = 1.f;
+  if (EPI == EPI_MASK_SPLIT && p.rowscale != nullptr && m < p.M) rs = p.rowscale[m];
+  if (EPI == EPI_MASK_SPLIT && p.logit_part != nullptr && m < p.M) {
+    // dL/dlogit of the global critic head for this row, from the forward epilogue's logit partials
+    float z = __ldg(p.logit_bias);
+    for (int i = 0; i < p.n_logit_part; i++) z += p.logit_part[(int64_t)i * p.M + m];
+    const float sg = 1.f / (1.f + expf(-z));
+    rs = m < p.rows_valid ? p.logit_gscale * (sg - 1.f) * sg * (1.f - sg) : 0.f;
+  }
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; c++) {
+    float v[32];
+    tc_ld32(trow + c * 32, v);
+    const int64_t n0 = (int64_t)nb * BN + c * 32;
+    if (EPI == EPI_BIAS_RELU_HEAD) {
+      // x = relu(acc + b); logit partial sum x.w3; and the head's masked gradient row
+      // (x > 0 ? w3 : 0) as a tf32 hi/lo pair -- the per-row scalar dL/dlogit is applied by the
+      // EPILOGUE of the backward GEMM (rowscale), so no kernel ever reads the activations back
+      if (m < p.M && n0 < p.N) {
+        float hi[32], lo[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const float x = fmaxf(v[i] + __ldg(p.bias + n0 + i), 0.f);
+          const float w = __ldg(p.vec + n0 + i);
+          zsum = fmaf(x, w, zsum);
+          if (TS) {
+            hi[i] = x > 0.f ? w : 0.f;
+          } else {
+            const float wh = tf32_hi_g(w);
+            hi[i] = x > 0.f ? wh : 0.f;
+            lo[i] = x > 0.f ? tf32_hi_g(w - wh) : 0.f;
+          }
+        }
+        float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+        if (!TS) {
+          float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
+#pragma unroll
+          for (int i = 0; i < 8; i++) ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+        }
+      }
+    } else if (EPI == EPI_STORE_T) {
+      // out[n][m]: lanes hold consecutive m -> one 128-byte line per column
+      if (m < p.M) {
+#pragma unroll
+        for (int i = 0; i < 32; i++)
+          if (n0 + i < p.N) p.out0[(n0 + i) * p.ldo + m] = v[i];
+      }
+    } else if (EPI == EPI_BIAS_RELU_SPLIT || EPI == EPI_MASK_SPLIT) {
+      if (m < p.M && n0 < p.N) {
+        float hi[32], lo[32];
+        // ReLU masks can travel as one bit per element (row m, word n0 / 32) between the layer's forward
+        // epilogue and the backward epilogue, instead of re-reading the fp32 activations
+        uint32_t bits = 0;
+        if (EPI == EPI_MASK_SPLIT && p.mask_bits != nullptr) bits = p.mask_bits[m * (p.N >> 5) + (n0 >> 5)];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          float x = v[i];
+          if (EPI == EPI_BIAS_RELU_SPLIT) {
+            x = fmaxf(x + __ldg(p.bias + n0 + i), 0.f);
+            bits |= (x > 0.f ? 1u : 0u) << i;
+          } else if (p.mask_bits != nullptr) {
+            x = ((bits >> i) & 1u) ? x * rs : 0.f;
+          } else {
+            x = (p.mask[m * p.ldmask + n0 + i] > 0.f) ? x * rs : 0.f;
+          }
+          if (TS) {
+            hi[i] = x;
+          } else {
+            hi[i] = tf32_hi_g(x);
+            lo[i] = tf32_hi_g(x - hi[i]);
+          }
+        }
+        if (EPI == EPI_BIAS_RELU_SPLIT && p.mask_bits_out != nullptr) p.mask_bits_out[m * (p.N >> 5) + (n0 >> 5)] = bits;
+        float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+        if (!TS) {
+          float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
+#pragma unroll
+          for (int i = 0; i < 8; i++) ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+        }
+      }
+    } else {
+      if (m < p.M && n0 < p.N) {
+        float4* o = reinterpret_cast<float4*>(p.out0 + ((int64_t)split * p.M + m) * p.ldo + n0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+  }
+  if (EPI == EPI_BIAS_RELU_HEAD && m < p.M) p.out2[(int64_t)nb * p.M + m] = zsum;
+}
+
 // TS = false: both operands arrive pre-split through TMA (four tiles per stage) and are read from
 // shared memory by the tensor core -- at 128x128 tiles the 3xTF32 scheme then reads 24 KB of operands
 // per 8-column K step and is bound by shared-memory bandwidth (~60 % of the tensor peak).
@@ -120,12 +220,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const bool skip_bl = TS && (p.probe & 8);      // diagnostic: do not load B_lo (the MMAs then read stale smem)
+          mbar_expect_tx(&full_bar[stage], skip_bl ? STAGE_BYTES - Cfg::B_BYTES : STAGE_BYTES);
           const int kc = (int)(split * p.K) + kb * BK;
           tma_load_2d(&mapAh, &full_bar[stage], sa, kc, mb * BM);
           if (!TS) tma_load_2d(&mapAl, &full_bar[stage], sa + Cfg::A_BYTES, kc, mb * BM);
           tma_load_2d(&mapBh, &full_bar[stage], sa + B_OFF, kc, nb * BN);
-          tma_load_2d(&mapBl, &full_bar[stage], sa + B_OFF + Cfg::B_BYTES, kc, nb * BN);
+          if (!skip_bl) tma_load_2d(&mapBl, &full_bar[stage], sa + B_OFF + Cfg::B_BYTES, kc, nb * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -225,100 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       tc_fence_after();
       const int64_t m = (int64_t)mb * BM + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
-      float zsum = 0.f;   // EPI_BIAS_RELU_HEAD: this row's share of the global head's logit
-      float rs = 1.f;
-      if (EPI == EPI_MASK_SPLIT && p.rowscale != nullptr && m < p.M) rs = p.rowscale[m];
-      if (EPI == EPI_MASK_SPLIT && p.logit_part != nullptr && m < p.M) {
-        // dL/dlogit of the global critic head for this row, from the forward epilogue's logit partials
-        float z = __ldg(p.logit_bias);
-        for (int i = 0; i < p.n_logit_part; i++) z += p.logit_part[(int64_t)i * p.M + m];
-        const float sg = 1.f / (1.f + expf(-z));
-        rs = m < p.rows_valid ? p.logit_gscale * (sg - 1.f) * sg * (1.f - sg) : 0.f;
-      }
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; c++) {
-        float v[32];
-        tc_ld32(trow + c * 32, v);
-        const int64_t n0 = (int64_t)nb * BN + c * 32;
-        if (EPI == EPI_BIAS_RELU_HEAD) {
-          // x = relu(acc + b); logit partial sum x.w3; and the head's masked gradient row
-          // (x > 0 ? w3 : 0) as a tf32 hi/lo pair -- the per-row scalar dL/dlogit is applied by the
-          // EPILOGUE of the backward GEMM (rowscale), so no kernel ever reads the activations back
-          if (m < p.M && n0 < p.N) {
-            float hi[32], lo[32];
-#pragma unroll
-            for (int i = 0; i < 32; i++) {
-              const float x = fmaxf(v[i] + __ldg(p.bias + n0 + i), 0.f);
-              const float w = __ldg(p.vec + n0 + i);
-              zsum = fmaf(x, w, zsum);
-              if (TS) {
-                hi[i] = x > 0.f ? w : 0.f;
-              } else {
-                const float wh = tf32_hi_g(w);
-                hi[i] = x > 0.f ? wh : 0.f;
-                lo[i] = x > 0.f ? tf32_hi_g(w - wh) : 0.f;
-              }
-            }
-            float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
-#pragma unroll
-            for (int i = 0; i < 8; i++) oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            if (!TS) {
-              float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
-#pragma unroll
-              for (int i = 0; i < 8; i++) ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-            }
-          }
-        } else if (EPI == EPI_STORE_T) {
-          // out[n][m]: lanes hold consecutive m -> one 128-byte line per column
-          if (m < p.M) {
-#pragma unroll
-            for (int i = 0; i < 32; i++)
-              if (n0 + i < p.N) p.out0[(n0 + i) * p.ldo + m] = v[i];
-          }
-        } else if (EPI == EPI_BIAS_RELU_SPLIT || EPI == EPI_MASK_SPLIT) {
-          if (m < p.M && n0 < p.N) {
-            float hi[32], lo[32];
-            // ReLU masks can travel as one bit per element (row m, word n0 / 32) between the layer's forward
-            // epilogue and the backward epilogue, instead of re-reading the fp32 activations
-            uint32_t bits = 0;
-            if (EPI == EPI_MASK_SPLIT && p.mask_bits != nullptr) bits = p.mask_bits[m * (p.N >> 5) + (n0 >> 5)];
-#pragma unroll
-            for (int i = 0; i < 32; i++) {
-              float x = v[i];
-              if (EPI == EPI_BIAS_RELU_SPLIT) {
-                x = fmaxf(x + __ldg(p.bias + n0 + i), 0.f);
-                bits |= (x > 0.f ? 1u : 0u) << i;
-              } else if (p.mask_bits != nullptr) {
-                x = ((bits >> i) & 1u) ? x * rs : 0.f;
-              } else {
-                x = (p.mask[m * p.ldmask + n0 + i] > 0.f) ? x * rs : 0.f;
-              }
-              if (TS) {
-                hi[i] = x;
-              } else {
-                hi[i] = tf32_hi_g(x);
-                lo[i] = tf32_hi_g(x - hi[i]);
-              }
-            }
-            if (EPI == EPI_BIAS_RELU_SPLIT && p.mask_bits_out != nullptr) p.mask_bits_out[m * (p.N >> 5) + (n0 >> 5)] = bits;
-            float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
-#pragma unroll
-            for (int i = 0; i < 8; i++) oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            if (!TS) {
-              float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
-#pragma unroll
-              for (int i = 0; i < 8; i++) ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-            }
-          }
-        } else {
-          if (m < p.M && n0 < p.N) {
-            float4* o = reinterpret_cast<float4*>(p.out0 + ((int64_t)split * p.M + m) * p.ldo + n0);
-#pragma unroll
-            for (int i = 0; i < 8; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-        }
-      }
-      if (EPI == EPI_BIAS_RELU_HEAD && m < p.M) p.out2[(int64_t)nb * p.M + m] = zsum;
+      tc_epilogue_row<BN, EPI, TS>(p, trow, m, nb, split);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -330,6 +338,200 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TS ? 512 : Cfg::TMEM_COLS));
+  }
+}
+
+
+// ------------------------------------------------------------------------------ two row blocks per CTA (critic layers)
+// Measured on the B200 (benchmarks/gemm_probe.py, profiles/r2_gemm_probe.jsonl): the 128x128 A-through-TMEM kernel above
+// runs at ~1600 cycles per 32-column K block whether it issues 3, 2 or 1 MMA per 8-column step -- it is paced by
+// operand delivery (48 KB of TMA boxes per K block and SM, ~30 B/clk/SM), not by the tensor pipe (768 cycles) and not by
+// the A staging chain.  This variant halves the weight traffic per unit of work: a CTA owns TWO 128-row blocks of the same
+// 128-column panel, so one [B_hi | B_lo] stage (32 KB) feeds 24 MMAs instead of 12 -- 64 KB of operands per 2 units
+// instead of 96 KB.  TMEM: two accumulators (columns 0 / 128) + a 2-slot staging ring of {A0 hi, A0 lo, A1 hi, A1 lo}
+// (columns 256 + 128 * slot).  The accumulators are single-buffered; the exposed epilogue (two warp quads, one per
+// accumulator) is ~4 % of a tile.  Warps: 0 TMA, 1 MMA, 2-5 epilogue of block 0, 6-9 A producers, 10-13 epilogue of block 1.
+constexpr int TS2_THREADS = 448;
+constexpr int TS2_STAGES = 3;
+constexpr int TS2_SLOTS = 2;
+template <int BN>
+struct Ts2Cfg {
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES = TS2_STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int ACC_STRIDE = 128;
+  static constexpr int RING_COL = 256;
+  static constexpr int SLOT_COLS = 128;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(TS2_THREADS, 1)
+gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+                const __grid_constant__ CUtensorMap mapBl, const TcParams p) {
+  using Cfg = Ts2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + TS2_STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                               // [STAGES]  TMA -> producers, MMA
+  uint64_t* empty_bar = bars + TS2_STAGES;                 // [STAGES]  MMA commit -> TMA
+  uint64_t* ready_bar = bars + 2 * TS2_STAGES;             // [SLOTS]   producers -> MMA
+  uint64_t* afree_bar = bars + 2 * TS2_STAGES + TS2_SLOTS; // [SLOTS]   MMA commit -> producers
+  uint64_t* tfull_bar = bars + 2 * TS2_STAGES + 2 * TS2_SLOTS;   // [1]  MMA commit -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 1;                    // [1]  epilogue (8 warps) -> MMA
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (int)(p.K / BK);
+  const int tiles_mn = p.m_tiles * p.n_tiles;              // m_tiles counts 256-row tiles here
+  const int num_tiles = tiles_mn * p.ksplit;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
+    for (int s = 0; s < TS2_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < TS2_SLOTS; s++) { mbar_init(&ready_bar[s], 4); mbar_init(&afree_bar[s], 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int r = t % tiles_mn;
+        const int mb = r % p.m_tiles, nb = r / p.m_tiles;
+        const int row0 = mb * 2 * BM;
+        // an odd number of 128-row blocks: the last tile's second block re-reads the first (its rows are never stored)
+        const int row1 = (row0 + BM < (int)p.M) ? row0 + BM : row0;
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int kc = (int)(split * p.K) + kb * BK;
+          tma_load_2d(&mapA, &full_bar[stage], sa, kc, row0);
+          tma_load_2d(&mapA, &full_bar[stage], sa + Cfg::A_BYTES, kc, row1);
+          tma_load_2d(&mapBh, &full_bar[stage], sa + 2 * Cfg::A_BYTES, kc, nb * BN);
+          tma_load_2d(&mapBl, &full_bar[stage], sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, kc, nb * BN);
+          if (++stage == TS2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(BM >> 4) << 24);
+    int stage = 0, slot = 0;
+    uint32_t phase = 0, sphase = 0, acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      if (lane == 0) mbar_wait(tempty_bar, acc_phase ^ 1);
+      __syncwarp();
+      tc_fence_after();
+      for (int kb = 0; kb < num_kb; kb++) {
+        if (lane == 0) {
+          mbar_wait(&full_bar[stage], phase);        // the weights of this stage (the producers waited for it too)
+          mbar_wait(&ready_bar[slot], sphase);       // both A blocks staged in tensor memory
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t dBh = make_sdesc(sa + 2 * Cfg::A_BYTES);
+          const uint64_t dBl = make_sdesc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+          const uint32_t ring = tmem_base + Cfg::RING_COL + slot * Cfg::SLOT_COLS;
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            const uint32_t d_tmem = tmem_base + i * Cfg::ACC_STRIDE;
+            const uint32_t ta = ring + i * 64;           // hi at +0, lo at +32
+#pragma unroll
+            for (int k = 0; k < BK / 8; k++) {
+              const uint64_t ko = (uint64_t)(k * 32 >> 4);
+              tc_mma_tf32_ts(d_tmem, ta + 32 + k * 8, dBh + ko, idesc, (kb | k) != 0);
+              tc_mma_tf32_ts(d_tmem, ta + k * 8, dBl + ko, idesc, 1);
+              tc_mma_tf32_ts(d_tmem, ta + k * 8, dBh + ko, idesc, 1);
+            }
+          }
+          tc_commit(&empty_bar[stage]);
+          tc_commit(&afree_bar[slot]);
+          if (kb == num_kb - 1) tc_commit(tfull_bar);
+        }
+        __syncwarp();
+        if (++stage == TS2_STAGES) { stage = 0; phase ^= 1; }
+        if (++slot == TS2_SLOTS) { slot = 0; sphase ^= 1; }
+      }
+      acc_phase ^= 1;
+    }
+  } else if (warp >= 6 && warp < 10) {
+    // ===================== A producers: smem fp32 rows -> tf32 hi/lo -> TMEM staging ring =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::RING_COL;
+    int stage = 0, slot = 0;
+    uint32_t phase = 0, sphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < num_kb; kb++) {
+        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&afree_bar[slot], sphase ^ 1);       // the MMAs that read this slot two K blocks ago have completed
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const uint8_t* arow = smem + stage * Cfg::STAGE_BYTES + i * Cfg::A_BYTES + row * 128;
+          float hi[32], lo[32];
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            const float4 x = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+            split_tf32(x.x, hi[4 * c], lo[4 * c]);
+            split_tf32(x.y, hi[4 * c + 1], lo[4 * c + 1]);
+            split_tf32(x.z, hi[4 * c + 2], lo[4 * c + 2]);
+            split_tf32(x.w, hi[4 * c + 3], lo[4 * c + 3]);
+          }
+          tc_st32(trow + slot * Cfg::SLOT_COLS + i * 64, hi);
+          tc_st32(trow + slot * Cfg::SLOT_COLS + i * 64 + 32, lo);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready_bar[slot]);
+        if (++stage == TS2_STAGES) { stage = 0; phase ^= 1; }
+        if (++slot == TS2_SLOTS) { slot = 0; sphase ^= 1; }
+      }
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue: warps 2-5 row block 0, warps 10-13 row block 1 =====================
+    const int q = warp & 3;
+    const int blk = warp >= 10 ? 1 : 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int split = t / tiles_mn;
+      const int r = t % tiles_mn;
+      const int mb = r % p.m_tiles, nb = r / p.m_tiles;
+      mbar_wait(tfull_bar, acc_phase);
+      tc_fence_after();
+      // rows past M (the duplicated block of an odd last tile, or padding) fall out through the m < p.M guards
+      const int64_t m = (int64_t)mb * 2 * BM + blk * BM + q * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + blk * Cfg::ACC_STRIDE;
+      tc_epilogue_row<BN, EPI, true>(p, trow, m, nb, split);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+      acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
 
@@ -401,19 +603,67 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   constexpr int smem_bytes = TS ? Cfg::SMEM_BYTES_TS : Cfg::SMEM_BYTES;
   JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
-  const int grid = std::min(tiles, device_num_sms(m->device));
+  int grid_override = 0;
   int reps = 1;
   if (g.probe_env) {       // jrr_debug_gemm only: diagnostic knobs for benchmarks/gemm_probe.py
     const char* e = getenv("JRR_GEMM_PROBE");
     p.probe = e ? atoi(e) : 0;
     e = getenv("JRR_GEMM_PROBE_REPS");
     reps = e ? std::max(1, atoi(e)) : 1;
+    e = getenv("JRR_GEMM_PROBE_GRID");
+    if (e && atoi(e) > 0) grid_override = atoi(e);
   }
+  const int grid = std::min(tiles, grid_override > 0 ? grid_override : device_num_sms(m->device));
   for (int r = 0; r < reps; r++) {
     kern<<<grid, TS ? TC_THREADS_TS : TC_THREADS, smem_bytes, st>>>(mAh, mAl, mBh, mBl, p);
     JRR_LAUNCH_CHECK();
   }
   return JRR_OK;
+}
+
+
+template <int BN, int EPI>
+static int launch_ts2(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
+  using Cfg = Ts2Cfg<BN>;
+  CUtensorMap mA, mBh, mBl;
+  const int64_t Ktot = g.K * g.ksplit;
+  if (int rc = make_tensor_map_2d(&mBh, g.B_hi, g.N, Ktot, g.ldb, BN)) return rc;
+  if (int rc = make_tensor_map_2d(&mBl, g.B_lo, g.N, Ktot, g.ldb, BN)) return rc;
+  const int64_t Ka = g.k_valid > 0 ? g.k_valid : Ktot;
+  if (int rc = make_tensor_map_2d(&mA, g.A_hi, g.M, Ka, g.lda, BM)) return rc;
+  TcParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K; p.ksplit = g.ksplit;
+  p.m_tiles = (int)((g.M + 2 * BM - 1) / (2 * BM));
+  p.n_tiles = (int)((g.N + BN - 1) / BN);
+  p.out0 = g.out0; p.out1 = g.out1; p.ldo = g.ldo; p.bias = g.bias; p.mask = g.mask; p.ldmask = g.ldmask;
+  p.rowscale = g.rowscale; p.vec = g.vec; p.out2 = g.out2;
+  p.A = g.A_hi; p.lda = g.lda;
+  p.mask_bits = g.mask_bits; p.mask_bits_out = g.mask_bits_out;
+  p.logit_part = g.logit_part; p.n_logit_part = g.n_logit_part; p.logit_bias = g.logit_bias;
+  p.logit_gscale = g.logit_gscale; p.rows_valid = g.rows_valid;
+  auto kern = gemm_ts2_kernel<BN, EPI>;
+  JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
+  int reps = 1;
+  if (g.probe_env) {
+    const char* e = getenv("JRR_GEMM_PROBE_REPS");
+    reps = e ? std::max(1, atoi(e)) : 1;
+  }
+  const int grid = std::min(tiles, device_num_sms(m->device));
+  for (int r = 0; r < reps; r++) {
+    kern<<<grid, TS2_THREADS, Cfg::SMEM_BYTES, st>>>(mA, mBh, mBl, p);
+    JRR_LAUNCH_CHECK();
+  }
+  return JRR_OK;
+}
+
+static bool use_ts2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JRR_GEMM_TS2");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
@@ -422,6 +672,18 @@ int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
     return fail(JRR_ERR_INVALID, "tc gemm: operands must be 16-byte aligned");
   if (g.a_via_tmem) {      // plain fp32 A (A_hi) through tensor memory, pre-split B
     if (g.N % 128 != 0 || g.lda % 4 != 0) return fail(JRR_ERR_INVALID, "tc gemm (A through TMEM): N % 128, lda % 4");
+    if (g.M >= 2 * BM && use_ts2() && !(g.probe_env && getenv("JRR_GEMM_PROBE_TS1"))) {
+      // two 128-row blocks per CTA: half the weight traffic per MMA (see gemm_ts2_kernel)
+      switch (g.epi) {
+        case EPI_BIAS_RELU_SPLIT: return launch_ts2<128, EPI_BIAS_RELU_SPLIT>(m, g, st);
+        case EPI_MASK_SPLIT: return launch_ts2<128, EPI_MASK_SPLIT>(m, g, st);
+        case EPI_BIAS_RELU_HEAD: return launch_ts2<128, EPI_BIAS_RELU_HEAD>(m, g, st);
+        case EPI_STORE_SPLITK:
+          if (g.N == 768 && g.ksplit == 1) return launch_ts2<96, EPI_STORE_SPLITK>(m, g, st);
+          return launch_ts2<128, EPI_STORE_SPLITK>(m, g, st);
+        default: break;
+      }
+    }
     switch (g.epi) {
       case EPI_BIAS_RELU_SPLIT: return launch_tc<128, EPI_BIAS_RELU_SPLIT, true>(m, g, st);
       case EPI_MASK_SPLIT: return launch_tc<128, EPI_MASK_SPLIT, true>(m, g, st);

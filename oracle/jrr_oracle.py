@@ -239,6 +239,27 @@ def discriminator_forward(sd: dict, rot6d: torch.Tensor) -> torch.Tensor:
     return torch.sigmoid(torch.cat([zg, zj], dim=1))[..., None]
 
 
+def critic_kink_frames(sd: dict, rot6d: torch.Tensor, tol_wide: float = 5e-7, tol_conv: float = 1e-7) -> torch.Tensor:
+    """Frames [B] (bool) one of whose ReLU pre-activations in the pose critic lies within fp32 round-off of zero.
+    There an fp32 evaluation (any fp32 evaluation: these kernels, or the reference itself in torch fp32) may take the
+    other branch of that ReLU than the fp64 oracle does, which changes that frame's critic gradient by one unit's
+    whole contribution (~1e-3 relative) and says nothing about the arithmetic.  Gradient comparisons against the fp64
+    oracle are asserted tightly on the other frames and loosely on these (about 1 % of random frames).
+    Tolerances: the two wide layers run as 3xTF32 tensor-core GEMMs whose accumulation truncates -- measured absolute
+    error of a pre-activation ~2.5e-7 at K = 1024 (values ~0.03), observed flips at |a| = 6e-8 and 1e-7; torch's own
+    fp32 evaluation flips below ~2e-8.  The 1x1 convs are plain fp32 FMAs (error ~1e-8)."""
+    x = rot6d.double()
+    B = x.shape[0]
+    g = lambda k: sd[k].double()
+    p1 = x @ g("conv_operations.0.weight").reshape(32, 6).t() + g("conv_operations.0.bias")
+    p2 = torch.relu(p1) @ g("conv_operations.2.weight").reshape(32, 32).t() + g("conv_operations.2.bias")
+    h = torch.relu(p2).reshape(B, 768)
+    a1 = h @ g("linear_operations.0.weight").t() + g("linear_operations.0.bias")
+    a2 = torch.relu(a1) @ g("linear_operations.2.weight").t() + g("linear_operations.2.bias")
+    return ((a1.abs().min(1).values < tol_wide) | (a2.abs().min(1).values < tol_wide)
+            | (p1.abs().reshape(B, -1).min(1).values < tol_conv) | (p2.abs().reshape(B, -1).min(1).values < tol_conv))
+
+
 def make_critic_state_dict(seed: int = 0) -> dict:
     """Default-init ``Discriminator()`` parameters under torch.manual_seed(seed), built
     from the same nn layers in the same construction order as discriminator.py:14-30 so

@@ -911,7 +911,7 @@ def bench_oracle_fp64_step(oracle, osmpl64, J_dense, critic_sd, bench_frames):
 
 
 @pytest.mark.parametrize("path", ["folded", "vertex"])
-def test_bench_config_one_step_vs_fp64_oracle(path, smpl_tc, jrr, critic_sd, J_dense, bench_frames, bench_oracle_fp64_step):
+def test_bench_config_one_step_vs_fp64_oracle(path, smpl_tc, jrr, oracle, critic_sd, J_dense, bench_frames, bench_oracle_fp64_step):
     """B = 4096, dense regressor, one Adam iteration from zero state: the three losses within 1e-5 relative and the
     gradient (Adam's first moment after one step is 0.1*g) within 1e-4 of its max against the fp64 oracle."""
     fr = bench_frames
@@ -926,13 +926,18 @@ def test_bench_config_one_step_vs_fp64_oracle(path, smpl_tc, jrr, critic_sd, J_d
         smpl_tc.native().set_loss_path("vertex")
     loss = st["loss"].cpu().double()
     m = st["m"].cpu().double() * 10
-    err = (m - gall).abs().max().item() / gall.abs().max().item()
+    # frames with a critic pre-activation within fp32 round-off of a ReLU kink may take the other branch than fp64 does
+    # (one unit's whole contribution, ~1e-3 of that frame's critic gradient): tight bound on the rest, loose on those
+    kink = oracle.critic_kink_frames(critic_sd, fr["x6"])
+    d = (m - gall).abs().max(1).values / gall.abs().max().item()
+    err, err_kink = d[~kink].max().item(), (d[kink].max().item() if kink.any() else 0.0)
     print(f"[{path}] B=4096 dense: loss {loss[0].item():.6f} vs fp64 oracle {tot:.6f}; joint {loss[1].item():.4e} vs {jl:.4e}; "
-          f"pose {loss[2].item():.6f} vs {pl:.6f}; gradient rel err {err:.2e}")
+          f"pose {loss[2].item():.6f} vs {pl:.6f}; gradient rel err {err:.2e} ({int(kink.sum())} ReLU-kink frames: {err_kink:.2e})")
     assert abs(loss[0].item() - tot) / tot < 1e-5
     assert abs(loss[1].item() - jl) / jl < 1e-5
     assert abs(loss[2].item() - pl) / pl < 1e-5
     assert err < 1e-4
+    assert int(kink.sum()) < BENCH_B // 50 and err_kink < 2e-3
 
 
 @pytest.mark.parametrize("path", ["folded", "vertex"])
