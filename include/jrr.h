@@ -263,6 +263,13 @@ const char* jrr_step_kernel_name(int i);
 int jrr_debug_gemm(JrrModel* model, int impl, int64_t M, int64_t N, int64_t K, const float* A,
                    const float* B, float* C, float* scratch, void* stream);
 
+/* Diagnostic (benchmarks/tma_probe.py): raw TMA tile-load rate.  `grid` CTAs each stream `iters` stages of `boxes` 2-D
+ * boxes ([box_rows] x 32 fp32, SWIZZLE_128B) of the DEVICE matrix src[rows][cols] through a ring of `stages` stages; a consumer
+ * lane frees every stage as soon as it has landed (after `dwell_ns`).  shared_tiles != 0: all CTAs read the same tiles.
+ * Not on the reference's interface. */
+int jrr_debug_tma_probe(const float* src, int64_t rows, int64_t cols, int box_rows, int boxes, int stages, int shared_tiles,
+                        int iters, int grid, int dwell_ns, void* stream);
+
 /* number of kernels the last call of the named entry point enqueued (bench.py's
  * gpu_launches claim is counted, not guessed) */
 int64_t jrr_last_launch_count(void);
