@@ -447,6 +447,21 @@ extern "C" int jrr_regressor_grad_accumulate(JrrModel* m, int64_t B, int64_t B_l
   if (!x6 || !betas || !gt_mm || !G_accum) return fail(JRR_ERR_INVALID, "null argument");
   if (B_logical < B) return fail(JRR_ERR_INVALID, "B_logical must be >= B");
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool folded_refit = [] { const char* e = getenv("JRR_FOLDED_REFIT"); return !(e && e[0] == '0'); }();
+  if (m->folded && m->T_hi && folded_refit && m->gemm_impl == 0) {
+    // folded form: chain | Q = feat . T^T | per-frame seed | G += unfold(dQ^T . feat, dc)   (jrr_model.cu)
+    if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, x6, JRR_POSE_ROT6D, w.AT, w.feat_hi, w.feat_lo, nullptr, st)) return rc;
+    GemmDesc g{};
+    g.A_hi = w.feat_hi; g.A_lo = w.feat_lo; g.lda = KA;
+    g.B_hi = m->T_hi; g.B_lo = m->T_lo; g.ldb = KA;
+    g.M = w.BP; g.N = FOLD_NP; g.K = KA; g.ksplit = 1; g.epi = EPI_STORE_T;
+    g.out0 = w.vpT; g.ldo = w.BP;
+    if (int rc = launch_gemm(m, g, st)) return rc;
+    if (int rc = regressor_accumulate_folded(m, w, gt_mm, B_logical, G_accum, st)) return rc;
+    if (loss_accum)
+      if (int rc = launch_loss_finish(w, B_logical, 1.f, 0.f, false, 0.f, 0.f, nullptr, loss_accum, st)) return rc;
+    return JRR_OK;
+  }
   // skinned vertices kept pose-contiguous in the (otherwise idle) dvp_hi buffer
   float* vT = w.dvp_hi;
   if (int rc = loss_forward(m, w, betas, x6, JRR_POSE_ROT6D, 2, vT, st, nullptr, nullptr)) return rc;

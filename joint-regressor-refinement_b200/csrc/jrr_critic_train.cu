@@ -290,11 +290,14 @@ shape_grad_finish_kernel(const float* __restrict__ partial, int nblk, float* __r
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-static int transpose(const float* src, int64_t rows, int cols, float* dst, cudaStream_t st) {
+int launch_transpose(const float* src, int64_t rows, int cols, float* dst, cudaStream_t st) {
   dim3 grid((unsigned)(cols / 32), (unsigned)(rows / 32));
   transpose_kernel<<<grid, 256, 0, st>>>(src, rows, cols, dst);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
+}
+static int transpose(const float* src, int64_t rows, int cols, float* dst, cudaStream_t st) {
+  return launch_transpose(src, rows, cols, dst, st);
 }
 
 static int colsum(const float* hi, const float* lo, const float* rowscale, int64_t rows, int cols, float* partial,

@@ -37,6 +37,7 @@ struct TcParams {
   const float* rowscale;   // EPI_MASK_SPLIT: multiply row m by rowscale[m] (or nullptr)
   const float* vec;        // EPI_BIAS_RELU_HEAD: w3[N]
   float* out2;             // EPI_BIAS_RELU_HEAD: zg_part[n_tile][M]
+  long long* prof;         // diagnostic only (jrr_debug_gemm + JRR_GEMM_PROF): per-CTA role timers, 16 counters each
   int probe;               // diagnostic only (JRR_GEMM_PROBE, benchmarks/gemm_probe.py): bit 0 = MMAs do not wait for the
                            // A producers (garbage A; shows the loop's pace without the smem->TMEM staging chain),
                            // bit 1 = skip the A_hi.B_lo MMA, bit 2 = skip the A_lo.B_hi MMA as well (results wrong)
@@ -365,6 +366,18 @@ struct Ts2Cfg {
   static constexpr int SLOT_COLS = 128;
 };
 
+// role timers of the diagnostic build path (p.prof != nullptr): cycles spent inside the named wait
+#define JRR_TIMED_WAIT(slot, stmt)                                   \
+  do {                                                               \
+    if (p.prof) {                                                    \
+      const long long _t0 = clock64();                               \
+      stmt;                                                          \
+      tacc[slot] += clock64() - _t0;                                 \
+    } else {                                                         \
+      stmt;                                                          \
+    }                                                                \
+  } while (0)
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(TS2_THREADS, 1)
 gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
@@ -382,6 +395,8 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long tacc[4] = {0, 0, 0, 0};
+  const long long t_start = clock64();
   const int num_kb = (int)(p.K / BK);
   const int tiles_mn = p.m_tiles * p.n_tiles;              // m_tiles counts 256-row tiles here
   const int num_tiles = tiles_mn * p.ksplit;
@@ -418,7 +433,7 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // an odd number of 128-row blocks: the last tile's second block re-reads the first (its rows are never stored)
         const int row1 = (row0 + BM < (int)p.M) ? row0 + BM : row0;
         for (int kb = 0; kb < num_kb; kb++) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          JRR_TIMED_WAIT(0, mbar_wait(&empty_bar[stage], phase ^ 1));
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int kc = (int)(split * p.K) + kb * BK;
@@ -429,6 +444,7 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           if (++stage == TS2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.prof) { p.prof[blockIdx.x * 16 + 0] = tacc[0]; p.prof[blockIdx.x * 16 + 1] = clock64() - t_start; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -437,13 +453,13 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     int stage = 0, slot = 0;
     uint32_t phase = 0, sphase = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      if (lane == 0) mbar_wait(tempty_bar, acc_phase ^ 1);
+      if (lane == 0) JRR_TIMED_WAIT(0, mbar_wait(tempty_bar, acc_phase ^ 1));
       __syncwarp();
       tc_fence_after();
       for (int kb = 0; kb < num_kb; kb++) {
         if (lane == 0) {
-          mbar_wait(&full_bar[stage], phase);        // the weights of this stage (the producers waited for it too)
-          mbar_wait(&ready_bar[slot], sphase);       // both A blocks staged in tensor memory
+          JRR_TIMED_WAIT(1, mbar_wait(&full_bar[stage], phase));        // the weights of this stage (the producers waited for it too)
+          JRR_TIMED_WAIT(2, mbar_wait(&ready_bar[slot], sphase));       // both A blocks staged in tensor memory
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t dBh = make_sdesc(sa + 2 * Cfg::A_BYTES);
@@ -471,6 +487,10 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
       acc_phase ^= 1;
     }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 16 + 2] = tacc[0]; p.prof[blockIdx.x * 16 + 3] = tacc[1]; p.prof[blockIdx.x * 16 + 4] = tacc[2];
+      p.prof[blockIdx.x * 16 + 5] = clock64() - t_start;
+    }
   } else if (warp >= 6 && warp < 10) {
     // ===================== A producers: smem fp32 rows -> tf32 hi/lo -> TMEM staging ring =====================
     const int q = warp & 3;
@@ -480,8 +500,8 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint32_t phase = 0, sphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       for (int kb = 0; kb < num_kb; kb++) {
-        mbar_wait(&full_bar[stage], phase);
-        mbar_wait(&afree_bar[slot], sphase ^ 1);       // the MMAs that read this slot two K blocks ago have completed
+        JRR_TIMED_WAIT(0, mbar_wait(&full_bar[stage], phase));
+        JRR_TIMED_WAIT(1, mbar_wait(&afree_bar[slot], sphase ^ 1));       // the MMAs that read this slot two K blocks ago have completed
         tc_fence_after();
 #pragma unroll
         for (int i = 0; i < 2; i++) {
@@ -506,6 +526,9 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (++slot == TS2_SLOTS) { slot = 0; sphase ^= 1; }
       }
     }
+    if (p.prof && warp == 6 && lane == 0) {
+      p.prof[blockIdx.x * 16 + 6] = tacc[0]; p.prof[blockIdx.x * 16 + 7] = tacc[1]; p.prof[blockIdx.x * 16 + 8] = clock64() - t_start;
+    }
   } else if (warp >= 2) {
     // ===================== epilogue: warps 2-5 row block 0, warps 10-13 row block 1 =====================
     const int q = warp & 3;
@@ -515,7 +538,7 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const int split = t / tiles_mn;
       const int r = t % tiles_mn;
       const int mb = r % p.m_tiles, nb = r / p.m_tiles;
-      mbar_wait(tfull_bar, acc_phase);
+      JRR_TIMED_WAIT(0, mbar_wait(tfull_bar, acc_phase));
       tc_fence_after();
       // rows past M (the duplicated block of an odd last tile, or padding) fall out through the m < p.M guards
       const int64_t m = (int64_t)mb * 2 * BM + blk * BM + q * 32 + lane;
@@ -526,6 +549,7 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       if (lane == 0) mbar_arrive(tempty_bar);
       acc_phase ^= 1;
     }
+    if (p.prof && warp == 2 && lane == 0) { p.prof[blockIdx.x * 16 + 9] = tacc[0]; p.prof[blockIdx.x * 16 + 10] = clock64() - t_start; }
   }
 
   tc_fence_before();
@@ -641,6 +665,10 @@ static int launch_ts2(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   p.mask_bits = g.mask_bits; p.mask_bits_out = g.mask_bits_out;
   p.logit_part = g.logit_part; p.n_logit_part = g.n_logit_part; p.logit_bias = g.logit_bias;
   p.logit_gscale = g.logit_gscale; p.rows_valid = g.rows_valid;
+  if (g.probe_env) {        // jrr_debug_gemm only: JRR_GEMM_PROF = device address (decimal) of 16 int64 counters per CTA
+    const char* e = getenv("JRR_GEMM_PROF");
+    p.prof = e ? (long long*)strtoull(e, nullptr, 10) : nullptr;
+  }
   auto kern = gemm_ts2_kernel<BN, EPI>;
   JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int tiles = p.m_tiles * p.n_tiles * p.ksplit;

@@ -280,7 +280,11 @@ struct Proj2D {
   float scale = 0.f;             // w_2d * 2 / (34 * B_logical)
 };
 int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int64_t B_logical, float w_joint,
-                       float* joints17_out, const Proj2D& p2d, cudaStream_t st);
+                       float* joints17_out, const Proj2D& p2d, cudaStream_t st, float* dc_part = nullptr);
+// regressor refit through the folded operator (jrr_model.cu): G += unfold(dT, dc)
+int regressor_accumulate_folded(const JrrModel* m, Workspace& w, const float* gt_mm, int64_t B_logical, float* G_accum,
+                                cudaStream_t st);
+int launch_transpose(const float* src, int64_t rows, int cols, float* dst, cudaStream_t st);
 int launch_fold(JrrModel* m, cudaStream_t st);
 int launch_adam_coef(const Workspace& w, const int32_t* step_count, float lr, cudaStream_t st);
 int launch_adam_params(const Workspace& w, bool use_critic, bool use_shape, float* x6, float* betas, float* adam_m,

@@ -256,6 +256,112 @@ int launch_regressor_apply(JrrModel* m, float* Jraw, const float* mask, const fl
   return m->folded ? launch_fold(m, st) : JRR_OK;
 }
 
+// --------------------------------------------------------------------- regressor refit through the folded operator
+// The refit gradient G_iv = d loss / d Jhat_iv = sum_b g~_b,i . V_b,v needs the skinned vertices of every frame in its
+// literal form.  But V is linear in the blend features with the joint transforms as the only pose-dependent factors -- the
+// same structure fold_kernel exploits -- so G is the ADJOINT of the fold applied to small per-batch sums:
+//   dT_ji[c][f] = sum_b (A_j^R(b)^T g~_b,i)[c] feat_b[f]      (= dQ^T . feat: one [1224 x B] x [B x 224] GEMM, K = batch)
+//   dc_ji       = sum_b g~_b,i . A_j^t(b)                      (24 x 17 sums, per-CTA partials of the seed kernel)
+//   G_iv        = sum_j w_vj ( <dT_ji, P_v> + dc_ji )          (U = dT . P^T: one [408 x 672] x [672 x 6912] GEMM + a gather)
+// with dQ, g~ from folded_seed_kernel (weight 1).  No per-vertex work per frame, no vertices in memory: 4096 frames cost two
+// small tensor-core GEMMs instead of a blend GEMM, a 339 MB vertex store and its re-read.  (optimize.py:300-309)
+constexpr int UNF_M = 512;                 // (j,i) rows of the unfold GEMM, 408 padded to the 128-row tile
+constexpr int UNF_K = 3 * KA;              // 672: (coordinate, feature)
+constexpr int DT_KSPLIT = 8;
+
+__global__ void dT_finish_kernel(const float* __restrict__ part, float* __restrict__ hi, float* __restrict__ lo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= UNF_M * UNF_K) return;
+  float a = 0.f;
+  if (idx < FOLD_N * KA)
+    for (int s = 0; s < DT_KSPLIT; s++) a += part[(int64_t)s * FOLD_NP * KA + idx];      // fixed order
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+  const float h = __uint_as_float(r);
+  const float d = a - h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
+  hi[idx] = h;
+  lo[idx] = __uint_as_float(r);
+}
+
+__global__ void dc_reduce_kernel(const float* __restrict__ part, int nblk, float* __restrict__ dc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= NJ * NH) return;
+  float a = 0.f;
+  for (int b = 0; b < nblk; b++) a += part[(int64_t)b * (NJ * NH) + e];
+  dc[e] = a;
+}
+
+// G[i][perm[p]] += sum_slots w_p,slot ( U[(j_slot, i)][p] + dc[j_slot][i] ), packed vertex p (thread), regressor row i (blockIdx.y)
+__global__ void __launch_bounds__(256)
+unfold_gather_kernel(const VtxRec* __restrict__ vrec, const int* __restrict__ perm, const float* __restrict__ U,
+                     const float* __restrict__ dc, int nv, float* __restrict__ G) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (p >= nv) return;
+  const int v = perm[p];
+  if (v < 0) return;
+  const uint32_t meta = vrec[p].meta;
+  float a = 0.f;
+#pragma unroll
+  for (int s4 = 0; s4 < 4; s4++) {
+    const float wgt = vrec[p].w[s4];
+    if (wgt != 0.f) {
+      const int j = (meta >> (5 * s4)) & 31u;
+      a = fmaf(wgt, U[(int64_t)(j * NH + i) * VP + p] + dc[j * NH + i], a);
+    }
+  }
+  G[i * V + v] += a;
+}
+
+int regressor_accumulate_folded(const JrrModel* m, Workspace& w, const float* gt_mm, int64_t B_logical, float* G_accum,
+                                cudaStream_t st) {
+  const int64_t BP = w.BP;
+  // scratch in the (idle) blend-gradient buffers: [dQ | dQ^T | feat^T | ...] hi in dvp_hi, lo in dvp_lo
+  float* dQT_hi = w.dvp_hi + BP * FOLD_NP;
+  float* dQT_lo = w.dvp_lo + BP * FOLD_NP;
+  float* fT_hi = w.dvp_hi + 2 * BP * FOLD_NP;
+  float* fT_lo = w.dvp_lo + 2 * BP * FOLD_NP;
+  float* dT_part = w.dvp_hi + 2 * BP * FOLD_NP + BP * KA;                  // [DT_KSPLIT][1280][224]
+  float* u = w.dvp_lo + 2 * BP * FOLD_NP + BP * KA;
+  float* dTs_hi = u; u += UNF_M * UNF_K;
+  float* dTs_lo = u; u += UNF_M * UNF_K;
+  float* U = u;      u += (int64_t)UNF_M * VP;
+  float* dc_part = u; u += (BP / 32) * (NJ * NH);
+  float* dc = u;      u += 512;
+  if ((u - w.dvp_lo) > (int64_t)NP * BP || (dT_part + (int64_t)DT_KSPLIT * FOLD_NP * KA - w.dvp_hi) > (int64_t)NP * BP)
+    return fail(JRR_ERR_WORKSPACE, "folded refit scratch does not fit the workspace");
+  // per-frame joints, loss, seed g~ (weight 1), dQ = A^R^T g~ and the dc partials
+  if (int rc = launch_folded_seed(m, w, gt_mm, B_logical, 1.f, nullptr, Proj2D{}, st, dc_part)) return rc;
+  if (int rc = launch_transpose(w.dvp_hi, BP, FOLD_NP, dQT_hi, st)) return rc;
+  if (int rc = launch_transpose(w.dvp_lo, BP, FOLD_NP, dQT_lo, st)) return rc;
+  if (int rc = launch_transpose(w.feat_hi, BP, KA, fT_hi, st)) return rc;
+  if (int rc = launch_transpose(w.feat_lo, BP, KA, fT_lo, st)) return rc;
+  {
+    GemmDesc g{};                       // dT[(j,i,c)][f] = sum_b dQ^T[(j,i,c)][b] feat^T[f][b]
+    g.A_hi = dQT_hi; g.A_lo = dQT_lo; g.lda = BP;
+    g.B_hi = fT_hi; g.B_lo = fT_lo; g.ldb = BP;
+    g.M = FOLD_NP; g.N = KA; g.K = BP / DT_KSPLIT; g.ksplit = DT_KSPLIT; g.epi = EPI_STORE_SPLITK;
+    g.out0 = dT_part; g.ldo = KA;
+    if (int rc = launch_gemm(m, g, st)) return rc;
+  }
+  dT_finish_kernel<<<(UNF_M * UNF_K + 255) / 256, 256, 0, st>>>(dT_part, dTs_hi, dTs_lo);
+  JRR_LAUNCH_CHECK();
+  dc_reduce_kernel<<<(NJ * NH + 127) / 128, 128, 0, st>>>(dc_part, (int)(BP / 32), dc);
+  JRR_LAUNCH_CHECK();
+  const int nv = (int)round_up(m->nv_act, 128);
+  {
+    GemmDesc g{};                       // U[(j,i)][p] = < dT_ji, P_p >  over (c,f) = 672
+    g.A_hi = dTs_hi; g.A_lo = dTs_lo; g.lda = UNF_K;
+    g.B_hi = m->Pt_hi; g.B_lo = m->Pt_lo; g.ldb = UNF_K;
+    g.M = UNF_M; g.N = nv; g.K = UNF_K; g.ksplit = 1; g.epi = EPI_STORE_SPLITK;
+    g.out0 = U; g.ldo = VP;
+    if (int rc = launch_gemm(m, g, st)) return rc;
+  }
+  unfold_gather_kernel<<<dim3((unsigned)((m->nv_act + 255) / 256), NH), 256, 0, st>>>(m->vrec, m->perm, U, dc, m->nv_act, G_accum);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
 // --------------------------------------------------------------------- folded loss-path operator
 // T[(j,i,c)][k] = sum_v Jhat_iv w_vj P[3v+c][k],  c_ji = sum_v Jhat_iv w_vj   (see folded_seed_kernel).
 // grid (17 regressor rows, 4 = three coordinates + the homogeneous one, FOLD_CH vertex chunks), thread = k;

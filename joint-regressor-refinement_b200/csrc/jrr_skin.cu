@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
 folded_seed_kernel(const float* __restrict__ QT, const float* __restrict__ AT, const float* __restrict__ Tc,
                    const float* __restrict__ gt_mm, int64_t B, int64_t BP, float scale, const Proj2D p2d,
                    float* __restrict__ loss_part, float* __restrict__ joints17_out, float* __restrict__ dAT,
-                   float* __restrict__ dQ_hi, float* __restrict__ dQ_lo) {
+                   float* __restrict__ dQ_hi, float* __restrict__ dQ_lo, float* __restrict__ dc_part) {
   extern __shared__ float fs_smem[];
   float* sbuf = fs_smem;                                   // forward: partial joints [warp][51][32]; backward: dq staging
   float* sg = sbuf + FS_WARPS * FS_POSES * FS_LD;          // joints, then the loss seed g, [a][pose]
@@ -454,6 +454,12 @@ folded_seed_kernel(const float* __restrict__ QT, const float* __restrict__ AT, c
 #pragma unroll
       for (int c = 0; c < 3; c++)
         sdq[lane * FS_LD + i * 3 + c] = fmaf(A[c], g0, fmaf(A[4 + c], g1, A[8 + c] * g2));
+      if (dc_part != nullptr) {
+        // regressor refit (folded form): d loss / d c_ji = sum_b g_i . A_j^t, this CTA's 32 poses (uniform branch)
+        float t = fmaf(g0, A[3], fmaf(g1, A[7], g2 * A[11]));
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) dc_part[(int64_t)blockIdx.x * (NJ * NH) + j * NH + i] = t;
+      }
     }
 #pragma unroll
     for (int e = 0; e < 12; e++) dAT[(int64_t)(j * 12 + e) * BP + b] = dA[e];
@@ -986,7 +992,7 @@ int launch_joints49_bwd(const JrrModel* m, const Workspace& w, const float* djoi
 
 // Folded loss path: joints (+ loss seed, dA, dQ when gt_mm is given) from Q = feat . T^T.
 int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int64_t B_logical, float w_joint,
-                       float* joints17_out, const Proj2D& p2d, cudaStream_t st) {
+                       float* joints17_out, const Proj2D& p2d, cudaStream_t st, float* dc_part) {
   const float scale = gt_mm != nullptr ? w_joint * 2.f / (51.f * (float)B_logical) : 0.f;
   const bool grad = gt_mm != nullptr;
   w.n_joint_part = (int)(w.BP / FS_POSES);
@@ -994,7 +1000,7 @@ int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int6
   JRR_CUDA(cudaFuncSetAttribute(folded_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   folded_seed_kernel<<<(unsigned)(w.BP / FS_POSES), FS_WARPS * 32, smem, st>>>(
       w.vpT, w.AT, m->Tc, gt_mm, w.B, w.BP, scale, p2d, w.loss_part, joints17_out, grad ? w.dAT : nullptr,
-      grad ? w.dvp_hi : nullptr, grad ? w.dvp_lo : nullptr);
+      grad ? w.dvp_hi : nullptr, grad ? w.dvp_lo : nullptr, grad ? dc_part : nullptr);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }

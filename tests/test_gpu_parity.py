@@ -1113,3 +1113,49 @@ def test_transl_reaches_unnormalised_extra_joints(jrr, model, oracle):
     out = m(betas=betas.to(DEV), global_orient=go.to(DEV), body_pose=bp.to(DEV), transl=tr.to(DEV))
     ref = o(betas=betas, global_orient=go, body_pose=bp, transl=tr)
     assert rel(out.joints, ref.joints) < 1e-5 and rel(out.vertices, ref.vertices) < 1e-5
+
+
+@pytest.mark.parametrize("which", ["shipped", "dense"])
+def test_regressor_refit_through_the_folded_operator(which, smpl_tc, jrr, oracle, osmpl64, J_shipped, J_dense, frames64):
+    """With the folded loss path selected the refit gradient is the adjoint of the fold applied to two small GEMMs
+    (G_iv = sum_j w_vj (<dT_ji, P_v> + dc_ji), csrc/jrr_model.cu) instead of a pass over the skinned vertices: same G as
+    the per-vertex accumulation and as fp64 autograd, same three Adam steps as the oracle (ragged chunks: 48 + 16)."""
+    J = J_shipped if which == "shipped" else J_dense
+    fr = frames64
+    x6, be, gt = fr["x6"].to(DEV), fr["betas"].to(DEV), fr["gt_mm"].to(DEV)
+    nat = smpl_tc.native()
+    try:
+        G = {}
+        for path in ("vertex", "folded"):
+            nat.set_loss_path(path)
+            refit = jrr.RegressorRefit(smpl_tc, J, lr=1e-2, chunk=48)
+            refit.accumulate(x6, be, gt)
+            torch.cuda.synchronize()
+            G[path] = (refit.G.clone(), refit.loss.clone(), nat.launches)
+        # fp64 oracle: dL/dJhat by autograd through find_joints with an already-normalised regressor
+        Jn = oracle.normalise_regressor(J.double()).requires_grad_(True)
+        R = oracle.rot6d_to_rotmat(fr["x6"].double().reshape(-1, 6)).view(-1, 24, 3, 3)
+        verts = osmpl64(global_orient=R[:, :1], body_pose=R[:, 1:], betas=fr["betas"].double(), pose2rot=False).vertices
+        pred = torch.einsum('jv,bvk->bjk', Jn, verts)
+        loss = ((oracle.move_pelvis(pred) - fr["gt_mm"].double() / 1000) ** 2).sum() / (64 * 51)
+        loss.backward()
+        act = (oracle.normalise_regressor(J) != 0).any(0)              # columns that can receive gradient
+        ref = Jn.grad[:, act]
+        ev = (G["vertex"][0].cpu().double()[:, act] - ref).abs().max().item() / ref.abs().max().item()
+        ef = (G["folded"][0].cpu().double()[:, act] - ref).abs().max().item() / ref.abs().max().item()
+        print(f"[{which}] refit gradient vs fp64 oracle: per-vertex {ev:.2e}, folded {ef:.2e}; loss {G['folded'][1].item():.6e} / "
+              f"{G['vertex'][1].item():.6e} / {loss.item():.6e}; launches {G['folded'][2]} vs {G['vertex'][2]}")
+        assert ev < 1e-4 and ef < 1e-4
+        assert abs(G["folded"][1].item() - loss.item()) / loss.item() < 1e-5
+        # three Adam steps on the folded path against the oracle optimiser
+        refit = jrr.RegressorRefit(smpl_tc, J, lr=1e-2, chunk=48)
+        opt = oracle.RegressorAdam(J.double(), lr=1e-2)
+        for it in range(3):
+            g64, l64 = oracle.regressor_grad(osmpl64, opt.J.detach(), fr["x6"].double(), fr["betas"].double(), fr["gt_mm"].double())
+            Jo = opt.step(g64)
+            l = refit.step(x6, be, gt)
+            d = (refit.J_regressor.cpu().double() - Jo).abs().max().item()
+            assert abs(l.item() - l64) / l64 < 1e-4 and d < 1e-4, (it, l.item(), l64, d)
+        assert torch.equal(refit.J_regressor.cpu()[J <= 0], J[J <= 0])
+    finally:
+        nat.set_loss_path("vertex")
