@@ -270,6 +270,10 @@ int jrr_debug_gemm(JrrModel* model, int impl, int64_t M, int64_t N, int64_t K, c
 int jrr_debug_tma_probe(const float* src, int64_t rows, int64_t cols, int box_rows, int boxes, int stages, int shared_tiles,
                         int iters, int grid, int dwell_ns, void* stream);
 
+/* Diagnostic (benchmarks/gemm_prof.py): role timers (cycles each warp role of the critic GEMM kernel spends waiting) of the
+ * next launches are written to consecutive [148][16] int64 slots of the DEVICE buffer `base`; base == NULL switches it off. */
+int jrr_debug_set_gemm_prof(long long* base, int slots);
+
 /* number of kernels the last call of the named entry point enqueued (bench.py's
  * gpu_launches claim is counted, not guessed) */
 int64_t jrr_last_launch_count(void);

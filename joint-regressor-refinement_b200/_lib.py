@@ -19,7 +19,7 @@ EXPORTS = [
     "jrr_regressor_grad_accumulate", "jrr_regressor_apply", "jrr_last_launch_count",
     "jrr_debug_gemm", "jrr_refine_step_profiled", "jrr_step_kernel_name", "jrr_camera_fit", "jrr_refine_step_2d", "jrr_evaluate",
     "jrr_shape_critic_load", "jrr_shape_critic_forward", "jrr_critic_grad_accumulate", "jrr_critic_apply",
-    "jrr_shape_critic_grad_accumulate", "jrr_shape_critic_apply", "jrr_set_loss_path", "jrr_debug_tma_probe",
+    "jrr_shape_critic_grad_accumulate", "jrr_shape_critic_apply", "jrr_set_loss_path", "jrr_debug_tma_probe", "jrr_debug_set_gemm_prof",
 ]
 
 
@@ -79,6 +79,7 @@ def lib():
     L.jrr_refine_step_2d.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, sz, vp]
     L.jrr_evaluate.argtypes = [i64, vp, vp, vp, vp, vp, sz, vp]
     L.jrr_debug_gemm.argtypes = [vp, C.c_int, i64, i64, i64, vp, vp, vp, vp, vp]
+    L.jrr_debug_set_gemm_prof.argtypes = [vp, C.c_int]
     L.jrr_debug_tma_probe.argtypes = [vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -58,10 +58,39 @@ struct TcCfg {
   static constexpr int SMEM_BYTES_TS = STAGES_TS * STAGE_BYTES_TS + 1024 + 256;
 };
 
+// 32 consecutive outputs of row m.  Direct form: eight 16-byte stores per thread -- the 32 lanes of a warp hold 32
+// different rows, so every store instruction touches 32 lines (measured: 8192 LSU wavefronts per 256x128 tile, ~9400
+// exposed cycles at the end of every critic GEMM).  Staged form (`stage` != nullptr): the warp writes its 32x32 block into a
+// SWIZZLE_128B shared-memory box (conflict-free per quarter warp) and one lane hands it to the TMA store unit, which writes
+// full 128-byte rows and clips rows past M; `row0` = first row of the warp's block (all 32 rows are in or out together).
+__device__ __forceinline__ void tc_store_row32(float* out, int64_t ldo, int64_t m, int64_t n0, const float* x,
+                                               float* stage, const CUtensorMap* mapO, int64_t row0, int lane) {
+  if (stage == nullptr) {
+    float4* o = reinterpret_cast<float4*>(out + m * ldo + n0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+    return;
+  }
+  if (lane == 0) tma_store_wait_read();          // the previous block has left the staging box
+  __syncwarp();
+  uint8_t* rowp = reinterpret_cast<uint8_t*>(stage) + lane * 128;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    *reinterpret_cast<float4*>(rowp + ((i ^ (lane & 7)) << 4)) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(mapO, stage, (int)n0, (int)row0);
+    tma_store_commit();
+  }
+}
+
 // One accumulator row (thread = row m = TMEM lane, BN columns starting at TMEM address `trow`) through the fused epilogue.
 template <int BN, int EPI, bool TS>
 __device__ __forceinline__ void tc_epilogue_row(const TcParams& p, const uint32_t trow, const int64_t m, const int nb,
-                                                const int split) {
+                                                const int split, float* stage = nullptr, const CUtensorMap* mapO = nullptr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = m - lane;
   float zsum = 0.f;   // EPI_BIAS_RELU_HEAD: this row's share of the global head's logit
   float rs = 1.f;
   if (EPI == EPI_MASK_SPLIT && p.rowscale != nullptr && m < p.M) rs = p.rowscale[m];
@@ -96,14 +125,8 @@ __device__ __forceinline__ void tc_epilogue_row(const TcParams& p, const uint32_
             lo[i] = x > 0.f ? tf32_hi_g(w - wh) : 0.f;
           }
         }
-        float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
-#pragma unroll
-        for (int i = 0; i < 8; i++) oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-        if (!TS) {
-          float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
-#pragma unroll
-          for (int i = 0; i < 8; i++) ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-        }
+        tc_store_row32(p.out0, p.ldo, m, n0, hi, TS ? stage : nullptr, mapO, row0, lane);
+        if (!TS) tc_store_row32(p.out1, p.ldo, m, n0, lo, nullptr, nullptr, row0, lane);
       }
     } else if (EPI == EPI_STORE_T) {
       // out[n][m]: lanes hold consecutive m -> one 128-byte line per column
@@ -138,21 +161,13 @@ __device__ __forceinline__ void tc_epilogue_row(const TcParams& p, const uint32_
           }
         }
         if (EPI == EPI_BIAS_RELU_SPLIT && p.mask_bits_out != nullptr) p.mask_bits_out[m * (p.N >> 5) + (n0 >> 5)] = bits;
-        float4* oh = reinterpret_cast<float4*>(p.out0 + m * p.ldo + n0);
-#pragma unroll
-        for (int i = 0; i < 8; i++) oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-        if (!TS) {
-          float4* ol = reinterpret_cast<float4*>(p.out1 + m * p.ldo + n0);
-#pragma unroll
-          for (int i = 0; i < 8; i++) ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-        }
+        tc_store_row32(p.out0, p.ldo, m, n0, hi, TS ? stage : nullptr, mapO, row0, lane);
+        if (!TS) tc_store_row32(p.out1, p.ldo, m, n0, lo, nullptr, nullptr, row0, lane);
       }
     } else {
-      if (m < p.M && n0 < p.N) {
-        float4* o = reinterpret_cast<float4*>(p.out0 + ((int64_t)split * p.M + m) * p.ldo + n0);
-#pragma unroll
-        for (int i = 0; i < 8; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      }
+      // split-K partial s lives at rows [s*M, (s+1)*M) of the output (the store map of the staged form spans ksplit*M rows)
+      if (m < p.M && n0 < p.N)
+        tc_store_row32(p.out0, p.ldo, (int64_t)split * p.M + m, n0, v, stage, mapO, (int64_t)split * p.M + row0, lane);
     }
   }
   if (EPI == EPI_BIAS_RELU_HEAD && m < p.M) p.out2[(int64_t)nb * p.M + m] = zsum;
@@ -355,12 +370,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
 constexpr int TS2_THREADS = 448;
 constexpr int TS2_STAGES = 3;
 constexpr int TS2_SLOTS = 2;
+constexpr int TS2_STORE_BYTES = 8 * 4096;   // one 32x32 fp32 staging box per epilogue warp (TMA store)
 template <int BN>
 struct Ts2Cfg {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int SMEM_BYTES = TS2_STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = TS2_STAGES * STAGE_BYTES + TS2_STORE_BYTES + 1024 + 256;
   static constexpr int ACC_STRIDE = 128;
   static constexpr int RING_COL = 256;
   static constexpr int SLOT_COLS = 128;
@@ -381,11 +397,12 @@ struct Ts2Cfg {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(TS2_THREADS, 1)
 gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
-                const __grid_constant__ CUtensorMap mapBl, const TcParams p) {
+                const __grid_constant__ CUtensorMap mapBl, const __grid_constant__ CUtensorMap mapO, const TcParams p) {
   using Cfg = Ts2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + TS2_STAGES * Cfg::STAGE_BYTES);
+  uint8_t* store_smem = smem + TS2_STAGES * Cfg::STAGE_BYTES;        // [8 epilogue warps][4 KB], 1024-byte aligned
+  uint64_t* bars = (uint64_t*)(store_smem + TS2_STORE_BYTES);
   uint64_t* full_bar = bars;                               // [STAGES]  TMA -> producers, MMA
   uint64_t* empty_bar = bars + TS2_STAGES;                 // [STAGES]  MMA commit -> TMA
   uint64_t* ready_bar = bars + 2 * TS2_STAGES;             // [SLOTS]   producers -> MMA
@@ -395,7 +412,7 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long tacc[4] = {0, 0, 0, 0};
+  long long tacc[6] = {0, 0, 0, 0, 0, 0};
   const long long t_start = clock64();
   const int num_kb = (int)(p.K / BK);
   const int tiles_mn = p.m_tiles * p.n_tiles;              // m_tiles counts 256-row tiles here
@@ -405,6 +422,7 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapO) : "memory");
     for (int s = 0; s < TS2_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < TS2_SLOTS; s++) { mbar_init(&ready_bar[s], 4); mbar_init(&afree_bar[s], 1); }
     mbar_init(tfull_bar, 1);
@@ -435,10 +453,13 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int kb = 0; kb < num_kb; kb++) {
           JRR_TIMED_WAIT(0, mbar_wait(&empty_bar[stage], phase ^ 1));
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const bool skip_a = (p.probe & 4) != 0;       // diagnostic: no A tiles (the producers then stage zeros)
+          mbar_expect_tx(&full_bar[stage], skip_a ? 2 * Cfg::B_BYTES : Cfg::STAGE_BYTES);
           const int kc = (int)(split * p.K) + kb * BK;
-          tma_load_2d(&mapA, &full_bar[stage], sa, kc, row0);
-          tma_load_2d(&mapA, &full_bar[stage], sa + Cfg::A_BYTES, kc, row1);
+          if (!skip_a) {
+            tma_load_2d(&mapA, &full_bar[stage], sa, kc, row0);
+            tma_load_2d(&mapA, &full_bar[stage], sa + Cfg::A_BYTES, kc, row1);
+          }
           tma_load_2d(&mapBh, &full_bar[stage], sa + 2 * Cfg::A_BYTES, kc, nb * BN);
           tma_load_2d(&mapBl, &full_bar[stage], sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, kc, nb * BN);
           if (++stage == TS2_STAGES) { stage = 0; phase ^= 1; }
@@ -447,49 +468,72 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       if (p.prof) { p.prof[blockIdx.x * 16 + 0] = tacc[0]; p.prof[blockIdx.x * 16 + 1] = clock64() - t_start; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (one lane) =====================
+    // Measured with the role timers (benchmarks/gemm_prof.py): tcgen05.mma issue blocks the lane at the pipe's pace
+    // (~64 cycles per 128x128x8 MMA: the queue is shallow), so every cycle this lane spends between two K blocks --
+    // barrier probes, fences, descriptor arithmetic -- is a cycle the tensor pipe drains and idles.  Hence: the next K
+    // block's "staged" barrier is probed while this block's last MMAs are still queued, the stage's own TMA barrier is not
+    // waited for again (the A producers waited for it before they arrived on `ready`), and the other 31 lanes stay out
+    // of the loop.
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)(BM >> 4) << 24);
-    int stage = 0, slot = 0;
-    uint32_t phase = 0, sphase = 0, acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      if (lane == 0) JRR_TIMED_WAIT(0, mbar_wait(tempty_bar, acc_phase ^ 1));
-      __syncwarp();
-      tc_fence_after();
-      for (int kb = 0; kb < num_kb; kb++) {
-        if (lane == 0) {
-          JRR_TIMED_WAIT(1, mbar_wait(&full_bar[stage], phase));        // the weights of this stage (the producers waited for it too)
-          JRR_TIMED_WAIT(2, mbar_wait(&ready_bar[slot], sphase));       // both A blocks staged in tensor memory
+    if (lane == 0) {
+      int stage = 0, slot = 0;
+      uint32_t sphase = 0, acc_phase = 0;
+      bool staged = false;              // ready_bar[slot] of the K block about to be issued is known to have completed
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        JRR_TIMED_WAIT(0, mbar_wait(tempty_bar, acc_phase ^ 1));
+        for (int kb = 0; kb < num_kb; kb++) {
+          if (!staged) JRR_TIMED_WAIT(2, mbar_wait(&ready_bar[slot], sphase));
           tc_fence_after();
+          const long long t_issue0 = p.prof ? clock64() : 0;
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t dBh = make_sdesc(sa + 2 * Cfg::A_BYTES);
           const uint64_t dBl = make_sdesc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
           const uint32_t ring = tmem_base + Cfg::RING_COL + slot * Cfg::SLOT_COLS;
+          const int nslot = slot + 1 == TS2_SLOTS ? 0 : slot + 1;
+          const uint32_t nphase = slot + 1 == TS2_SLOTS ? sphase ^ 1 : sphase;
+          const int nrep = (p.probe & 8) ? 2 : ((p.probe & 16) ? 0 : 1);    // diagnostic: every MMA twice / no MMAs at all
+          for (int rep = 0; rep < nrep; rep++) {
 #pragma unroll
-          for (int i = 0; i < 2; i++) {
-            const uint32_t d_tmem = tmem_base + i * Cfg::ACC_STRIDE;
-            const uint32_t ta = ring + i * 64;           // hi at +0, lo at +32
+            for (int i = 0; i < 2; i++) {
+              const uint32_t d_tmem = tmem_base + i * Cfg::ACC_STRIDE;
+              const uint32_t ta = ring + i * 64;           // hi at +0, lo at +32
 #pragma unroll
-            for (int k = 0; k < BK / 8; k++) {
-              const uint64_t ko = (uint64_t)(k * 32 >> 4);
-              tc_mma_tf32_ts(d_tmem, ta + 32 + k * 8, dBh + ko, idesc, (kb | k) != 0);
-              tc_mma_tf32_ts(d_tmem, ta + k * 8, dBl + ko, idesc, 1);
-              tc_mma_tf32_ts(d_tmem, ta + k * 8, dBh + ko, idesc, 1);
+              for (int k = 0; k < BK / 8; k++) {
+                const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                tc_mma_tf32_ts(d_tmem, ta + 32 + k * 8, dBh + ko, idesc, (kb | k) != 0);
+                tc_mma_tf32_ts(d_tmem, ta + k * 8, dBl + ko, idesc, 1);
+                tc_mma_tf32_ts(d_tmem, ta + k * 8, dBh + ko, idesc, 1);
+              }
             }
           }
-          tc_commit(&empty_bar[stage]);
-          tc_commit(&afree_bar[slot]);
+          if (p.prof) tacc[4] += clock64() - t_issue0;
+          // ONE commit per K block (it releases the smem stage to the TMA lane and, two K blocks later, the staging slot
+          // to the A producers), issued before the probe below so the release is not delayed
+          if (p.prof && (p.probe & 64)) {
+            JRR_TIMED_WAIT(5, tc_commit(&empty_bar[stage]));
+          } else {
+            tc_commit(&empty_bar[stage]);
+          }
           if (kb == num_kb - 1) tc_commit(tfull_bar);
+          // probe the next K block's barrier while the MMAs above are still executing
+          if (p.prof && (p.probe & 128)) {
+            JRR_TIMED_WAIT(3, staged = mbar_try(&ready_bar[nslot], nphase));
+          } else {
+            staged = mbar_try(&ready_bar[nslot], nphase);
+          }
+          if (++stage == TS2_STAGES) stage = 0;
+          slot = nslot;
+          sphase = nphase;
         }
-        __syncwarp();
-        if (++stage == TS2_STAGES) { stage = 0; phase ^= 1; }
-        if (++slot == TS2_SLOTS) { slot = 0; sphase ^= 1; }
+        acc_phase ^= 1;
       }
-      acc_phase ^= 1;
-    }
-    if (p.prof && lane == 0) {
-      p.prof[blockIdx.x * 16 + 2] = tacc[0]; p.prof[blockIdx.x * 16 + 3] = tacc[1]; p.prof[blockIdx.x * 16 + 4] = tacc[2];
-      p.prof[blockIdx.x * 16 + 5] = clock64() - t_start;
+      if (p.prof) {
+        p.prof[blockIdx.x * 16 + 2] = tacc[0]; p.prof[blockIdx.x * 16 + 3] = 0; p.prof[blockIdx.x * 16 + 4] = tacc[2];
+        p.prof[blockIdx.x * 16 + 5] = clock64() - t_start;
+        p.prof[blockIdx.x * 16 + 11] = tacc[3]; p.prof[blockIdx.x * 16 + 12] = tacc[4]; p.prof[blockIdx.x * 16 + 13] = tacc[5];
+      }
     }
   } else if (warp >= 6 && warp < 10) {
     // ===================== A producers: smem fp32 rows -> tf32 hi/lo -> TMEM staging ring =====================
@@ -497,11 +541,15 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int row = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::RING_COL;
     int stage = 0, slot = 0;
-    uint32_t phase = 0, sphase = 0;
+    uint32_t phase = 0;
+    int n = 0;                        // running K-block count of this CTA
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      for (int kb = 0; kb < num_kb; kb++) {
+      for (int kb = 0; kb < num_kb; kb++, n++) {
         JRR_TIMED_WAIT(0, mbar_wait(&full_bar[stage], phase));
-        JRR_TIMED_WAIT(1, mbar_wait(&afree_bar[slot], sphase ^ 1));       // the MMAs that read this slot two K blocks ago have completed
+        // the MMAs that read this staging slot belong to K block n - 2; their completion is completion (n-2)/3 of the
+        // empty barrier of stage (n-2) % 3 (it cannot run a phase ahead: its next completion needs K block n + 1 staged)
+        if (n >= TS2_SLOTS)
+          JRR_TIMED_WAIT(1, mbar_wait(&empty_bar[(n - TS2_SLOTS) % TS2_STAGES], (uint32_t)(((n - TS2_SLOTS) / TS2_STAGES) & 1)));
         tc_fence_after();
 #pragma unroll
         for (int i = 0; i < 2; i++) {
@@ -509,7 +557,8 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           float hi[32], lo[32];
 #pragma unroll
           for (int c = 0; c < 8; c++) {
-            const float4 x = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+            float4 x = make_float4(1.f, 2.f, 3.f, 4.f);
+            if (!(p.probe & 6)) x = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));   // (diagnostic: no smem read)
             split_tf32(x.x, hi[4 * c], lo[4 * c]);
             split_tf32(x.y, hi[4 * c + 1], lo[4 * c + 1]);
             split_tf32(x.z, hi[4 * c + 2], lo[4 * c + 2]);
@@ -523,7 +572,7 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready_bar[slot]);
         if (++stage == TS2_STAGES) { stage = 0; phase ^= 1; }
-        if (++slot == TS2_SLOTS) { slot = 0; sphase ^= 1; }
+        if (++slot == TS2_SLOTS) slot = 0;
       }
     }
     if (p.prof && warp == 6 && lane == 0) {
@@ -533,6 +582,7 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     // ===================== epilogue: warps 2-5 row block 0, warps 10-13 row block 1 =====================
     const int q = warp & 3;
     const int blk = warp >= 10 ? 1 : 0;
+    float* my_stage = p.probe & 32 ? nullptr : reinterpret_cast<float*>(store_smem + (blk * 4 + q) * 4096);   // (probe 32: direct stores)
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int split = t / tiles_mn;
@@ -543,12 +593,13 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       // rows past M (the duplicated block of an odd last tile, or padding) fall out through the m < p.M guards
       const int64_t m = (int64_t)mb * 2 * BM + blk * BM + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + blk * Cfg::ACC_STRIDE;
-      tc_epilogue_row<BN, EPI, true>(p, trow, m, nb, split);
+      tc_epilogue_row<BN, EPI, true>(p, trow, m, nb, split, my_stage, &mapO);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar);
       acc_phase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all();       // every bulk store of this lane has landed before the CTA retires
     if (p.prof && warp == 2 && lane == 0) { p.prof[blockIdx.x * 16 + 9] = tacc[0]; p.prof[blockIdx.x * 16 + 10] = clock64() - t_start; }
   }
 
@@ -646,6 +697,10 @@ static int launch_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
 }
 
 
+// diagnostic (benchmarks/gemm_prof.py): role timers of every gemm_ts2_kernel launch go to consecutive 148x16 slots
+static long long* g_prof_base = nullptr;
+static int g_prof_slots = 0, g_prof_next = 0;
+
 template <int BN, int EPI>
 static int launch_ts2(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   using Cfg = Ts2Cfg<BN>;
@@ -655,6 +710,8 @@ static int launch_ts2(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   if (int rc = make_tensor_map_2d(&mBl, g.B_lo, g.N, Ktot, g.ldb, BN)) return rc;
   const int64_t Ka = g.k_valid > 0 ? g.k_valid : Ktot;
   if (int rc = make_tensor_map_2d(&mA, g.A_hi, g.M, Ka, g.lda, BM)) return rc;
+  CUtensorMap mO;                  // epilogue store boxes: 32 rows x 32 columns of out0 (split-K partials stacked along rows)
+  if (int rc = make_tensor_map_2d(&mO, g.out0, g.M * g.ksplit, g.N, g.ldo, 32)) return rc;
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.ksplit = g.ksplit;
   p.m_tiles = (int)((g.M + 2 * BM - 1) / (2 * BM));
@@ -668,6 +725,12 @@ static int launch_ts2(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   if (g.probe_env) {        // jrr_debug_gemm only: JRR_GEMM_PROF = device address (decimal) of 16 int64 counters per CTA
     const char* e = getenv("JRR_GEMM_PROF");
     p.prof = e ? (long long*)strtoull(e, nullptr, 10) : nullptr;
+    e = getenv("JRR_GEMM_PROBE");
+    p.probe = e ? atoi(e) : 0;
+  }
+  if (g_prof_base != nullptr && g_prof_slots > 0) {
+    p.prof = g_prof_base + (int64_t)(g_prof_next % g_prof_slots) * 148 * 16;
+    g_prof_next++;
   }
   auto kern = gemm_ts2_kernel<BN, EPI>;
   JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -679,11 +742,18 @@ static int launch_ts2(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   }
   const int grid = std::min(tiles, device_num_sms(m->device));
   for (int r = 0; r < reps; r++) {
-    kern<<<grid, TS2_THREADS, Cfg::SMEM_BYTES, st>>>(mA, mBh, mBl, p);
+    kern<<<grid, TS2_THREADS, Cfg::SMEM_BYTES, st>>>(mA, mBh, mBl, mO, p);
     JRR_LAUNCH_CHECK();
   }
   return JRR_OK;
 }
+
+}  // namespace jrr
+extern "C" int jrr_debug_set_gemm_prof(long long* base, int slots) {
+  jrr::g_prof_base = base; jrr::g_prof_slots = slots; jrr::g_prof_next = 0;
+  return JRR_OK;
+}
+namespace jrr {
 
 static bool use_ts2() {
   static int v = -1;
@@ -707,7 +777,9 @@ int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
         case EPI_MASK_SPLIT: return launch_ts2<128, EPI_MASK_SPLIT>(m, g, st);
         case EPI_BIAS_RELU_HEAD: return launch_ts2<128, EPI_BIAS_RELU_HEAD>(m, g, st);
         case EPI_STORE_SPLITK:
-          if (g.N == 768 && g.ksplit == 1) return launch_ts2<96, EPI_STORE_SPLITK>(m, g, st);
+          // (a 96-column panel buys nothing here: measured ~58 cycles per tcgen05.mma at N = 96 against ~60 at N = 128 --
+          //  below 128 columns the instruction time does not shrink with N -- so N = 768 runs as 6 x 16 = 96 CTAs of
+          //  256 x 128 and leaves the other SMs to the concurrent branch of the step)
           return launch_ts2<128, EPI_STORE_SPLITK>(m, g, st);
         default: break;
       }
