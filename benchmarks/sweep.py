@@ -20,13 +20,17 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import jrr_b200 as jrr  # noqa: E402
-from conftest import shipped_regressor  # noqa: E402
+from bench import load_regressor  # noqa: E402
+
+
+def shipped_regressor():
+    """the reference artefact through the product loader (reference tree, else its byte copy under tests/golden/)"""
+    return load_regressor("shipped")
 
 
 def cuda_time(fn, warm=3, reps=10):

@@ -157,6 +157,19 @@ extern "C" int jrr_smpl_forward(JrrModel* m, int64_t B, const float* betas, cons
   if (!betas || !pose) return fail(JRR_ERR_INVALID, "null input");
   if (!vertices_out && !joints49_out) return fail(JRR_ERR_INVALID, "no output requested");
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool fused_module = [] { const char* e = getenv("JRR_FUSED_MODULE"); return !(e && e[0] == '0'); }();
+  if (m->gemm_impl == 0 && m->fused_fwd && fused_module) {
+    // chain | blend GEMM with the skinning epilogue over EVERY packed vertex (pose-contiguous store) | un-packing to the
+    // model's vertex order with coalesced reads and writes | 49 joints gathered from the packed vertices
+    if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, pose, kind, w.AT, w.feat_hi, w.feat_lo,
+                                 joints49_out ? w.Jp : nullptr, st)) return rc;
+    if (int rc = launch_fused_fwd(m, w, 2, w.vpT, st, true)) return rc;
+    if (vertices_out)
+      if (int rc = launch_unpack_vertices(m, w, w.vpT, vertices_out, st)) return rc;
+    if (joints49_out)
+      if (int rc = launch_joints49_fwd_packed(m, w, w.vpT, joints49_out, st)) return rc;
+    return JRR_OK;
+  }
   if (int rc = forward_common(m, w, betas, pose, kind, joints49_out != nullptr, st)) return rc;
   // joints49 reads vertices: use caller's buffer, else scratch (dvp_hi is [BP][NP] >= [B][6890][3])
   float* verts = vertices_out ? vertices_out : w.dvp_hi;

@@ -353,13 +353,14 @@ int fused_fwd_slots(int64_t BP, int num_sms) {
   return 2 * worst;
 }
 
-int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store, float* vT_out, cudaStream_t st) {
+int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store, float* vT_out, cudaStream_t st, bool all_vertices) {
   CUtensorMap mAh, mAl, mBh, mBl;
   if (int rc = make_tensor_map_2d(&mAh, w.feat_hi, w.BP, KA, KA, FBM)) return rc;
   if (int rc = make_tensor_map_2d(&mAl, w.feat_lo, w.BP, KA, KA, FBM)) return rc;
   if (int rc = make_tensor_map_2d(&mBh, m->Pt_hi, NP, KA, KA, FBN)) return rc;
   if (int rc = make_tensor_map_2d(&mBl, m->Pt_lo, NP, KA, KA, FBN)) return rc;
-  const int m_tiles = (int)(w.BP / FBM), n_tiles = m->nv_act / FV;   // only the active vertex prefix
+  // loss path: only the active vertex prefix; module path (all_vertices): every packed vertex
+  const int m_tiles = (int)(w.BP / FBM), n_tiles = (all_vertices ? VP : m->nv_act) / FV;
   const int T = m_tiles * n_tiles, G = std::min(T, m->num_sms);
 #define JRR_FF(S)                                                                                   \
   do {                                                                                              \

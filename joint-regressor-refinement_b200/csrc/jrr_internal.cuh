@@ -128,6 +128,7 @@ struct JrrModel {
   jrr::VtxRec* vrec = nullptr;               // [VP]  forward ranges (VS_F)
   jrr::VtxRec* vrec_b = nullptr;             // [VP]  backward ranges (VS_B): reload/first flags differ
   int* perm = nullptr;                       // [VP] packed index -> original vertex id (-1 = padding)
+  int* inv_perm = nullptr;                   // [V]  original vertex id -> packed index
   int* vx_src = nullptr;                     // joints49 sources per vertex (see VtxRec)
   float* vx_coef = nullptr;
   int n_flush = 0;                           // dA flush events per pose (all ranges)
@@ -296,7 +297,10 @@ int launch_camera_fit(const Workspace& w, const float* joints17, const float* gt
 // fused blend GEMM + skinning + regressor partial sums (jrr_fused_fwd.cu)
 int fused_fwd_slots(int64_t BP, int num_sms);
 int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store /*0 none, 1 vp, 2 skinned v*/,
-                     float* vT_out, cudaStream_t st);
+                     float* vT_out, cudaStream_t st, bool all_vertices = false);
+// packed pose-contiguous vertices vT [3*VP][BP] -> natural order [B][6890][3] (module path)
+int launch_unpack_vertices(const JrrModel* m, const Workspace& w, const float* vT, float* vertices_out, cudaStream_t st);
+int launch_joints49_fwd_packed(const JrrModel* m, const Workspace& w, const float* vT, float* joints49_out, cudaStream_t st);
 // fused skinning backward + transpose-side blend GEMM (jrr_fused_bwd.cu); writes dfeat[NSPLIT_B] and dAflush
 int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st);
 int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_g,

@@ -597,6 +597,12 @@ int build_packing(JrrModel* m, const std::vector<uint8_t>& active) {
     return fail(JRR_ERR_INVALID, "flush list overflow");
 
   JRR_CUDA(cudaMemcpy(m->perm, perm.data(), sizeof(int) * VP, cudaMemcpyHostToDevice));
+  {
+    std::vector<int> inv(V, 0);
+    for (int i = 0; i < VP; i++)
+      if (perm[i] >= 0) inv[perm[i]] = i;
+    JRR_CUDA(cudaMemcpy(m->inv_perm, inv.data(), sizeof(int) * V, cudaMemcpyHostToDevice));
+  }
   JRR_CUDA(cudaMemcpy(m->vrec, rec_f.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
   JRR_CUDA(cudaMemcpy(m->vrec_b, rec_b.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
   if (!vx_src.empty()) {
@@ -779,6 +785,7 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
 
   // ---- device buffers of the packing (filled by build_packing; sizes do not depend on the order)
   if (int rc = dalloc(m, &m->perm, VP)) return rc;
+  if (int rc = dalloc(m, &m->inv_perm, V)) return rc;
   if (int rc = dalloc(m, &m->vrec, VP)) return rc;
   if (int rc = dalloc(m, &m->vrec_b, VP)) return rc;
   if (int rc = dalloc(m, &m->flush_ptr, NJ + 1)) return rc;

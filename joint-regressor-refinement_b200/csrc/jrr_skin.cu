@@ -769,6 +769,89 @@ dA_reduce_kernel(const int* __restrict__ flush_ptr, const int* __restrict__ flus
   for (int e = 0; e < 12; e++) dAT[(int64_t)(k * 12 + e) * BP + b] = acc[e];
 }
 
+// ----------------------------------------------------------------------- module path: vertex un-packing
+// The fused forward leaves the skinned vertices packed (sorted by joint set) and pose-contiguous, vT[3p+c][b]: that is the
+// layout in which a warp of 32 poses writes full 128-byte lines.  The drop-in returns [B][6890][3] in the model's own vertex
+// order.  This kernel walks the NATURAL order: a CTA takes 32 poses x 32 consecutive vertices, GATHERS their three rows each
+// through inv_perm (every read is one full line of 32 poses), transposes in shared memory and writes 384 contiguous bytes per
+// pose -- both directions fully coalesced, which a scatter by `perm` from the packed side cannot be (12-byte pieces).
+constexpr int UP_V = 64;
+__global__ void __launch_bounds__(256)
+unpack_vertices_kernel(const int* __restrict__ inv_perm, const float* __restrict__ vT, int64_t B, int64_t BP,
+                       float* __restrict__ out) {
+  __shared__ float tile[UP_V * 3][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v0 = blockIdx.x * UP_V;
+  const int64_t b0 = (int64_t)blockIdx.y * 32;
+  constexpr int RPW = UP_V * 3 / 8;               // 24 rows per warp: all gathers of a warp are in flight together
+  float x[RPW];
+#pragma unroll
+  for (int i = 0; i < RPW; i++) {
+    const int r = warp + 8 * i;
+    const int v = v0 + r / 3;
+    x[i] = v < V ? vT[(int64_t)(3 * __ldg(inv_perm + v) + r % 3) * BP + b0 + lane] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < RPW; i++) tile[warp + 8 * i][lane] = x[i];
+  __syncthreads();
+  const int nv = min(UP_V, V - v0) * 3;          // floats of this vertex group per pose
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int pp = warp + 8 * q;
+    const int64_t b = b0 + pp;
+    if (b >= B) continue;
+    float* o = out + b * (int64_t)(V * 3) + (int64_t)v0 * 3;
+#pragma unroll
+    for (int j = 0; j < UP_V * 3 / 32; j++) {
+      const int e = j * 32 + lane;
+      if (e < nv) o[e] = tile[e][pp];
+    }
+  }
+}
+
+int launch_unpack_vertices(const JrrModel* m, const Workspace& w, const float* vT, float* vertices_out, cudaStream_t st) {
+  dim3 grid((V + UP_V - 1) / UP_V, (unsigned)((w.B + 31) / 32));
+  unpack_vertices_kernel<<<grid, 256, 0, st>>>(m->inv_perm, vT, w.B, w.BP, vertices_out);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+// joints49 straight from the packed pose-contiguous vertices (same arithmetic as joints49_fwd_kernel)
+__global__ void joints49_fwd_packed_kernel(const int* __restrict__ joint_map, const int* __restrict__ picks, Csr extra,
+                                           const int* __restrict__ inv_perm, const float* __restrict__ Jp,
+                                           const float* __restrict__ vT, int64_t B, int64_t BP, float* __restrict__ joints49) {
+  // thread = (output joint o, pose b) with b fastest: the reads of one vertex row are pose-contiguous
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= BP * JRR_NUM_OUT_JOINTS) return;
+  const int o = (int)(idx / BP);
+  const int64_t b = idx % BP;
+  if (b >= B) return;
+  const int src = joint_map[o];
+  float out[3] = {0.f, 0.f, 0.f};
+  if (src < NJ) {
+    for (int c = 0; c < 3; c++) out[c] = Jp[b * 72 + src * 3 + c];
+  } else if (src < NJ + JRR_NUM_PICKS) {
+    const int p = inv_perm[picks[src - NJ]];
+    for (int c = 0; c < 3; c++) out[c] = vT[(int64_t)(3 * p + c) * BP + b];
+  } else {
+    const int e = src - NJ - JRR_NUM_PICKS;
+    for (int q = extra.ptr[e]; q < extra.ptr[e + 1]; q++) {
+      const int p = inv_perm[extra.col[q]];
+      const float cf = extra.val[q];
+      for (int c = 0; c < 3; c++) out[c] = fmaf(cf, vT[(int64_t)(3 * p + c) * BP + b], out[c]);
+    }
+  }
+  for (int c = 0; c < 3; c++) joints49[(b * JRR_NUM_OUT_JOINTS + o) * 3 + c] = out[c];
+}
+
+int launch_joints49_fwd_packed(const JrrModel* m, const Workspace& w, const float* vT, float* joints49_out, cudaStream_t st) {
+  const int64_t n = w.BP * JRR_NUM_OUT_JOINTS;
+  joints49_fwd_packed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->joint_map, m->picks, m->extra, m->inv_perm, w.Jp,
+                                                                         vT, w.B, w.BP, joints49_out);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
 // ----------------------------------------------------------------------- joints49 (module)
 // smplx vertex_joint_selector + scripts/smpl.py:75-78
 __global__ void joints49_fwd_kernel(const int* __restrict__ joint_map, const int* __restrict__ picks,
