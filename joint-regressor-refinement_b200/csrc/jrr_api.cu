@@ -187,8 +187,25 @@ extern "C" int jrr_smpl_backward(JrrModel* m, int64_t B, const float* betas, con
   if (!betas || !pose || !dbetas_out || !dpose_out) return fail(JRR_ERR_INVALID, "null argument");
   if (!dvertices && !djoints49) return fail(JRR_ERR_INVALID, "no upstream gradient given");
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = forward_common(m, w, betas, pose, kind, false, st)) return rc;
   const bool use_x = djoints49 != nullptr;
+  static const bool fused_module = [] { const char* e = getenv("JRR_FUSED_MODULE"); return !(e && e[0] == '0'); }();
+  if (m->gemm_impl == 0 && m->fused_fwd && m->fused_bwd && fused_module) {
+    // recompute: chain | blend GEMM + skinning (stores the blended vertices, pose-contiguous) ; then
+    // joints49 gradient -> its sources | re-pack d vertices | skinning backward generating the A operand of the
+    // blend-gradient GEMM (d blended vertices never reach memory) | dA reduction | chain backward
+    if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, pose, kind, w.AT, w.feat_hi, w.feat_lo, nullptr, st)) return rc;
+    if (int rc = launch_fused_fwd(m, w, 1, w.vpT, st, true)) return rc;
+    if (use_x)
+      if (int rc = launch_joints49_bwd(m, w, djoints49, st)) return rc;
+    float* dvT = w.dvp_hi;
+    if (int rc = launch_pack_dvertices(m, w, dvertices, use_x, dvT, st)) return rc;
+    w.ksplit = NSPLIT_B;
+    if (int rc = launch_fused_bwd(m, w, st, dvT)) return rc;
+    if (int rc = launch_dA_reduce(m, w, false, st)) return rc;
+    return launch_pose_bwd(m, w, betas, pose, kind, use_x, false, false, dbetas_out, dpose_out, nullptr, nullptr,
+                           nullptr, nullptr, nullptr, 0.f, st);
+  }
+  if (int rc = forward_common(m, w, betas, pose, kind, false, st)) return rc;
   if (use_x)
     if (int rc = launch_joints49_bwd(m, w, djoints49, st)) return rc;
   if (int rc = launch_skin_bwd(m, w, dvertices, false, use_x, st)) return rc;

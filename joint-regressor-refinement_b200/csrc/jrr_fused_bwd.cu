@@ -39,6 +39,10 @@ constexpr int GB_REC_F4 = 32 * REC_WORDS / 4;    // vertex records per 32-vertex
 constexpr int GB_SMEM = 2 * GB_A_STAGE + GB_P_BYTES + 2 * GB_REC_F4 * 16 + 1024 + 256;
 constexpr int GB_TMEM_COLS = 512;                // accumulators at columns 0 and 256
 
+// USE_DV = false: loss path, the vertex gradient is generated as dv = Jhat^T g (gT: the loss seed).
+// USE_DV = true: module path (autograd backward of SMPL.forward), dv is READ from dvT [3*VP][BP] -- the caller's
+// d loss / d vertices re-packed pose-contiguous, with the joints49 contributions already added (pack_dvertices_kernel).
+template <bool USE_DV>
 __global__ void __launch_bounds__(GB_THREADS, 1)
 fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ CUtensorMap mapPl,
                  const VtxRec* __restrict__ vrec, const int* __restrict__ range_flush_base,
@@ -149,15 +153,17 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
       const int i0 = ks * vs;
       float* flush_dst = dAflush + (int64_t)range_flush_base[ks] * 12 * BP + b;
 
-      f32x2 gp[3][9];
+      f32x2 gp[USE_DV ? 1 : 3][USE_DV ? 1 : 9];
+      if (!USE_DV) {
 #pragma unroll
-      for (int p = 0; p < 9; p++)
+        for (int p = 0; p < 9; p++)
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const float lo = gT[(int64_t)((2 * p) * 3 + c) * BP + b];
-          const float hi = (2 * p + 1 < NH) ? gT[(int64_t)((2 * p + 1) * 3 + c) * BP + b] : 0.f;
-          gp[c][p] = pk2(lo, hi);
-        }
+          for (int c = 0; c < 3; c++) {
+            const float lo = gT[(int64_t)((2 * p) * 3 + c) * BP + b];
+            const float hi = (2 * p + 1 < NH) ? gT[(int64_t)((2 * p + 1) * 3 + c) * BP + b] : 0.f;
+            gp[USE_DV ? 0 : c][USE_DV ? 0 : p] = pk2(lo, hi);
+          }
+      }
       f32x2 AR01[4][3], dA01[4][3], dA23[4][3];
       float AR2[4][3];
 #pragma unroll
@@ -175,6 +181,12 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
       float nx[12];
 #pragma unroll
       for (int q = 0; q < 12; q++) { nx[q] = *vsrc; vsrc += BP; }
+      const float* dsrc = gT + (int64_t)(3 * i0) * BP + b;     // USE_DV: gT is dvT, walked like vpT
+      float dnx[USE_DV ? 12 : 1];
+      if (USE_DV) {
+#pragma unroll
+        for (int q = 0; q < 12; q++) { dnx[USE_DV ? q : 0] = *dsrc; dsrc += BP; }
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // (nothing of this item is queued yet)
 
       const int NT = vs / 32;         // record tiles per item (24 / 12 / 6)
@@ -191,9 +203,18 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
           float cur[12];
 #pragma unroll
           for (int q = 0; q < 12; q++) cur[q] = nx[q];
+          float dcur[USE_DV ? 12 : 1];
+          if (USE_DV) {
+#pragma unroll
+            for (int q = 0; q < 12; q++) dcur[USE_DV ? q : 0] = dnx[USE_DV ? q : 0];
+          }
           if (g + 1 < NT * 8) {
 #pragma unroll
             for (int q = 0; q < 12; q++) { nx[q] = *vsrc; vsrc += BP; }
+            if (USE_DV) {
+#pragma unroll
+              for (int q = 0; q < 12; q++) { dnx[USE_DV ? q : 0] = *dsrc; dsrc += BP; }
+            }
           }
           const float4* rh = rt + (sub * 4) * 7;
           float4 r0[4];
@@ -210,7 +231,12 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
           float dv[4][3];
 #pragma unroll
           for (int ii = 0; ii < 4; ii++) { dv[ii][0] = 0.f; dv[ii][1] = 0.f; dv[ii][2] = 0.f; }
-          if ((many >> 24) & 1u) {
+          if (USE_DV) {
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+              for (int c = 0; c < 3; c++) dv[ii][c] = dcur[USE_DV ? ii * 3 + c : 0];
+          } else if ((many >> 24) & 1u) {
 #pragma unroll
             for (int ii = 0; ii < 4; ii++) {
               f32x2 a[3] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
@@ -220,8 +246,8 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
                 const f32x2 ja = pk2(tt.x, tt.y), jb = pk2(tt.z, tt.w);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                  if (2 * qq < 9) a[c] = fma2(ja, gp[c][2 * qq], a[c]);
-                  if (2 * qq + 1 < 9) a[c] = fma2(jb, gp[c][2 * qq + 1], a[c]);
+                  if (2 * qq < 9) a[c] = fma2(ja, gp[USE_DV ? 0 : c][USE_DV ? 0 : 2 * qq], a[c]);
+                  if (2 * qq + 1 < 9) a[c] = fma2(jb, gp[USE_DV ? 0 : c][USE_DV ? 0 : 2 * qq + 1], a[c]);
                 }
               }
 #pragma unroll
@@ -365,17 +391,28 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap mapPh, const __grid_constan
   }
 }
 
-int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st) {
+int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st, const float* dvT) {
   if (w.BP % GB_POSES != 0) return fail(JRR_ERR_INVALID, "fused backward needs BP % 256 == 0");
   CUtensorMap mPh, mPl;
   if (int rc = make_tensor_map_2d(&mPh, m->P_hi, KA, NP, NP, KA)) return rc;
   if (int rc = make_tensor_map_2d(&mPl, m->P_lo, KA, NP, NP, KA)) return rc;
+  if (dvT != nullptr) {
+    // module path: every packed vertex in 768-vertex ranges (the records / flush lists of the module backward)
+    const int nsplit = NSPLIT_B;
+    const int n_items = (int)(w.BP / GB_POSES) * nsplit;
+    const int grid = std::min(n_items, m->num_sms);
+    JRR_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM));
+    fused_bwd_kernel<true><<<grid, GB_THREADS, GB_SMEM, st>>>(mPh, mPl, m->vrec_b, m->range_flush_base, w.AT, w.vpT, dvT,
+                                                              w.BP, n_items, nsplit, VS_B, w.dfeat, w.dAflush);
+    JRR_LAUNCH_CHECK();
+    return JRR_OK;
+  }
   const int nsplit = m->nsplit_act;      // K ranges of the active vertex prefix
   const int n_items = (int)(w.BP / GB_POSES) * nsplit;
   const int grid = std::min(n_items, m->num_sms);
-  JRR_CUDA(cudaFuncSetAttribute(fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM));
-  fused_bwd_kernel<<<grid, GB_THREADS, GB_SMEM, st>>>(mPh, mPl, m->vrec_l, m->range_flush_base_l, w.AT, w.vpT, w.gT,
-                                                      w.BP, n_items, nsplit, m->vs_l, w.dfeat, w.dAflush);
+  JRR_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM));
+  fused_bwd_kernel<false><<<grid, GB_THREADS, GB_SMEM, st>>>(mPh, mPl, m->vrec_l, m->range_flush_base_l, w.AT, w.vpT, w.gT,
+                                                             w.BP, n_items, nsplit, m->vs_l, w.dfeat, w.dAflush);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }

@@ -302,7 +302,10 @@ int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store /*0 none, 
 int launch_unpack_vertices(const JrrModel* m, const Workspace& w, const float* vT, float* vertices_out, cudaStream_t st);
 int launch_joints49_fwd_packed(const JrrModel* m, const Workspace& w, const float* vT, float* joints49_out, cudaStream_t st);
 // fused skinning backward + transpose-side blend GEMM (jrr_fused_bwd.cu); writes dfeat[NSPLIT_B] and dAflush
-int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st);
+int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st, const float* dvT = nullptr);
+// natural-order d loss / d vertices [B][6890][3] (may be NULL) + the joints49 gradient on its vertex-borne sources (d30T,
+// may be unused) -> packed pose-contiguous dvT [3*VP][BP] for the fused backward
+int launch_pack_dvertices(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_x, float* dvT, cudaStream_t st);
 int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_g,
                     bool use_x, cudaStream_t st);
 int launch_dA_reduce(const JrrModel* m, const Workspace& w, bool loss_path_lists, cudaStream_t st);

@@ -816,6 +816,57 @@ int launch_unpack_vertices(const JrrModel* m, const Workspace& w, const float* v
   return JRR_OK;
 }
 
+// Inverse of unpack_vertices_kernel for the module backward: the caller's d loss / d vertices [B][6890][3] is read in the
+// natural order (coalesced, 768 bytes per pose), transposed in shared memory and written as full pose-contiguous lines
+// into the packed layout dvT[3p+c][b] the fused backward walks.  The joints49 gradient that reaches vertices (21 vertex
+// picks, 9 extra-regressor rows; d30T from joints49_bwd_kernel) is added here, so the backward kernel needs no special case.
+__global__ void __launch_bounds__(256)
+pack_dvertices_kernel(const int* __restrict__ inv_perm, const VtxRec* __restrict__ vrec, const int* __restrict__ vx_src,
+                      const float* __restrict__ vx_coef, const float* __restrict__ dverts, const float* __restrict__ d30T,
+                      int64_t B, int64_t BP, float* __restrict__ dvT) {
+  __shared__ float tile[UP_V * 3][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v0 = blockIdx.x * UP_V;
+  const int64_t b0 = (int64_t)blockIdx.y * 32;
+  const int nv = min(UP_V, V - v0) * 3;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int pp = warp + 8 * q;
+    const int64_t b = b0 + pp;
+    const float* src = dverts != nullptr ? dverts + b * (int64_t)(V * 3) + (int64_t)v0 * 3 : nullptr;
+#pragma unroll
+    for (int j = 0; j < UP_V * 3 / 32; j++) {
+      const int e = j * 32 + lane;
+      tile[e][pp] = (src != nullptr && b < B && e < nv) ? src[e] : 0.f;
+    }
+  }
+  __syncthreads();
+  constexpr int RPW = UP_V * 3 / 8;
+#pragma unroll 4
+  for (int i = 0; i < RPW; i++) {
+    const int r = warp + 8 * i;
+    const int v = v0 + r / 3, c = r % 3;
+    if (v >= V) continue;
+    const int p = __ldg(inv_perm + v);
+    float x = tile[r][lane];
+    if (d30T != nullptr) {
+      const int xp = vrec[p].xptr, xc = vrec[p].xcnt;
+      for (int q = 0; q < xc; q++) x = fmaf(vx_coef[xp + q], d30T[(int64_t)(vx_src[xp + q] * 3 + c) * BP + b0 + lane], x);
+    }
+    dvT[(int64_t)(3 * p + c) * BP + b0 + lane] = x;
+  }
+}
+
+int launch_pack_dvertices(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_x, float* dvT, cudaStream_t st) {
+  // the 22 padding vertices sit at the end of the packed order: their rows must be finite (their weights are zero)
+  JRR_CUDA(cudaMemsetAsync(dvT + (int64_t)(3 * V) * w.BP, 0, sizeof(float) * (size_t)(3 * (VP - V)) * w.BP, st));
+  dim3 grid((V + UP_V - 1) / UP_V, (unsigned)(w.BP / 32));
+  pack_dvertices_kernel<<<grid, 256, 0, st>>>(m->inv_perm, m->vrec_b, m->vx_src, m->vx_coef, dvertices, use_x ? w.d30T : nullptr,
+                                              w.B, w.BP, dvT);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
 // joints49 straight from the packed pose-contiguous vertices (same arithmetic as joints49_fwd_kernel)
 __global__ void joints49_fwd_packed_kernel(const int* __restrict__ joint_map, const int* __restrict__ picks, Csr extra,
                                            const int* __restrict__ inv_perm, const float* __restrict__ Jp,
