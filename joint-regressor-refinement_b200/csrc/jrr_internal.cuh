@@ -183,6 +183,7 @@ struct JrrModel {
   float *Tt_hi = nullptr, *Tt_lo = nullptr;  // [KA][FOLD_NP]   backward B operand
   float* Tc = nullptr;                       // [24][17]        sum_v Jhat_iv w_vj
   double* fold_part = nullptr;               // scratch of fold_kernel
+  double* fold_wj = nullptr;                 // [17][VP][4] w * Jhat in double (fold_prep_kernel)
   bool fused_fwd = true;   // loss path: skinning + regressor in the blend GEMM's epilogue
   bool fused_bwd = true;   // loss path: skinning backward generates the A operand of the blend-gradient GEMM
   std::vector<void*> allocs;

@@ -366,42 +366,76 @@ int regressor_accumulate_folded(const JrrModel* m, Workspace& w, const float* gt
 // T[(j,i,c)][k] = sum_v Jhat_iv w_vj P[3v+c][k],  c_ji = sum_v Jhat_iv w_vj   (see folded_seed_kernel).
 // grid (17 regressor rows, 4 = three coordinates + the homogeneous one, FOLD_CH vertex chunks), thread = k;
 // double accumulators in shared memory, fixed summation order (chunk partials reduced in order).
-constexpr int FOLD_CH = 8;
+constexpr int FOLD_CH = VP / VS_F;          // 12 chunks = the forward record ranges (a range start reloads all four slots)
+
+// wj[i][p][slot] = w_p,slot * Jhat_i,p in double (exact: 24 + 24 significand bits), once per regressor version -- the fold
+// kernel's 224 threads per CTA would otherwise each redo these conversions and products for every vertex
+__global__ void fold_prep_kernel(const VtxRec* __restrict__ vrec, double* __restrict__ wj) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NH * VP) return;
+  const int i = idx / VP, p = idx % VP;
+  const double jh = (double)vrec[p].jh[i];
+#pragma unroll
+  for (int s4 = 0; s4 < 4; s4++) wj[(int64_t)idx * 4 + s4] = (double)vrec[p].w[s4] * jh;
+}
+
 __global__ void __launch_bounds__(KA)
-fold_kernel(const VtxRec* __restrict__ vrec, const float* __restrict__ Pt_hi, const float* __restrict__ Pt_lo,
-            double* __restrict__ part) {
+fold_kernel(const VtxRec* __restrict__ vrec, const double* __restrict__ wj, const float* __restrict__ Pt_hi,
+            const float* __restrict__ Pt_lo, double* __restrict__ part) {
+  // Packed vertices are sorted by joint set, so a record slot keeps its joint over long runs: each thread keeps the four
+  // slots' running sums in REGISTERS (four independent double chains) and adds them to the per-joint shared-memory
+  // accumulators only when a slot's joint changes (the records' reload bits: ~190 times over the whole model) -- the
+  // first version updated the shared accumulators for every (vertex, slot), one dependent shared-memory round trip each
+  // (0.46 ms).  Same fp64 arithmetic; groups of four vertices without a slot change take a branch-free path.
   __shared__ double acc[NJ * KA];
   const int i = blockIdx.x, c = blockIdx.y, ch = blockIdx.z, k = threadIdx.x;
   for (int e = k; e < NJ * KA; e += KA) acc[e] = 0.0;
   __syncthreads();                 // (each thread only ever touches column k, the barrier is for the zeroing loop)
-  const int per = VP / FOLD_CH;
-  // four vertices per round trip: their blend-matrix rows are loaded before any of them is accumulated (the loop
-  // is a chain of dependent global-load latencies otherwise); accumulation order stays vertex by vertex
-  for (int p0 = ch * per; p0 < (ch + 1) * per; p0 += 4) {
-    float jh[4], w[4][4];
-    uint32_t meta[4];
+  double run[4] = {0.0, 0.0, 0.0, 0.0};
+  int jcur[4] = {0, 0, 0, 0};
+  const int p0 = ch * VS_F;
+  const double2* wj2 = reinterpret_cast<const double2*>(wj + ((int64_t)i * VP + p0) * 4);
+#pragma unroll 1
+  for (int q0 = 0; q0 < VS_F; q0 += 4) {
+    uint32_t meta[4], many = 0;
     double p[4];
+    double2 wa[4], wb[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int pi = p0 + u;
-      jh[u] = vrec[pi].jh[i];
+    for (int u = 0; u < 4; u++) {       // four vertices' loads in flight together
+      const int pi = p0 + q0 + u;
       meta[u] = vrec[pi].meta;
+      many |= meta[u];
+      wa[u] = __ldg(wj2 + (q0 + u) * 2);
+      wb[u] = __ldg(wj2 + (q0 + u) * 2 + 1);
+      if (c < 3) p[u] = (double)__ldg(Pt_hi + (int64_t)(3 * pi + c) * KA + k) + (double)__ldg(Pt_lo + (int64_t)(3 * pi + c) * KA + k);
+      else p[u] = k == 0 ? 1.0 : 0.0;
+    }
+    if (!((many >> 20) & 0xFu)) {       // no slot changes inside the group (uniform)
 #pragma unroll
-      for (int s4 = 0; s4 < 4; s4++) w[u][s4] = vrec[pi].w[s4];
-      p[u] = 0.0;
-      if (jh[u] != 0.f) {          // uniform: vertices outside the regressor row's support are skipped
-        if (c < 3) p[u] = (double)Pt_hi[(int64_t)(3 * pi + c) * KA + k] + (double)Pt_lo[(int64_t)(3 * pi + c) * KA + k];
-        else p[u] = k == 0 ? 1.0 : 0.0;
+      for (int u = 0; u < 4; u++) {
+        run[0] = fma(wa[u].x, p[u], run[0]);
+        run[1] = fma(wa[u].y, p[u], run[1]);
+        run[2] = fma(wb[u].x, p[u], run[2]);
+        run[3] = fma(wb[u].y, p[u], run[3]);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const double wv[4] = {wa[u].x, wa[u].y, wb[u].x, wb[u].y};
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+          if ((meta[u] >> (20 + s4)) & 1u) {          // the slot changes its joint before this vertex (uniform)
+            acc[jcur[s4] * KA + k] += run[s4];
+            run[s4] = 0.0;
+            jcur[s4] = (meta[u] >> (5 * s4)) & 31u;
+          }
+          run[s4] = fma(wv[s4], p[u], run[s4]);
+        }
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (jh[u] == 0.f) continue;
-#pragma unroll
-      for (int s4 = 0; s4 < 4; s4++)
-        if (w[u][s4] != 0.f) acc[((meta[u] >> (5 * s4)) & 31u) * KA + k] += (double)w[u][s4] * (double)jh[u] * p[u];
-    }
   }
+#pragma unroll
+  for (int s4 = 0; s4 < 4; s4++) acc[jcur[s4] * KA + k] += run[s4];
   double* out = part + ((int64_t)(ch * NH + i) * 4 + c) * (NJ * KA);
   for (int j = 0; j < NJ; j++) out[j * KA + k] = acc[j * KA + k];
 }
@@ -441,8 +475,11 @@ int launch_fold(JrrModel* m, cudaStream_t st) {
     if (int rc = dalloc(m, &m->Tt_lo, (size_t)FOLD_NP * KA)) return rc;
     if (int rc = dalloc(m, &m->Tc, (size_t)NJ * NH)) return rc;
     if (int rc = dalloc(m, &m->fold_part, (size_t)FOLD_CH * NH * 4 * NJ * KA)) return rc;
+    if (int rc = dalloc(m, &m->fold_wj, (size_t)NH * VP * 4)) return rc;
   }
-  fold_kernel<<<dim3(NH, 4, FOLD_CH), KA, 0, st>>>(m->vrec, m->Pt_hi, m->Pt_lo, m->fold_part);
+  fold_prep_kernel<<<(NH * VP + 255) / 256, 256, 0, st>>>(m->vrec, m->fold_wj);
+  JRR_LAUNCH_CHECK();
+  fold_kernel<<<dim3(NH, 4, FOLD_CH), KA, 0, st>>>(m->vrec, m->fold_wj, m->Pt_hi, m->Pt_lo, m->fold_part);
   JRR_LAUNCH_CHECK();
   const int64_t n = (int64_t)FOLD_N * KA + NJ * NH;
   fold_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->fold_part, m->T_hi, m->T_lo, m->Tt_hi, m->Tt_lo, m->Tc);

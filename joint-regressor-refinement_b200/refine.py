@@ -80,14 +80,15 @@ class PoseRefiner:
 
     _STATE = ("x6", "betas", "m", "v", "t", "cam", "cm", "cv")      # what a step mutates (restored after a capture warm-up)
 
-    def _step(self, st, LB):
+    def _step(self, st, LB, loss=None):
+        loss = st["loss"] if loss is None else loss
         if "cam" in st:
             self.native.refine_step_2d(st["x6"], st["betas"], st["gt"], st["gt2d"], st["cam"], st["m"], st["v"], st["cm"],
                                        st["cv"], st["t"], self.lr, self.w_joint, self.w_pose, st["w_2d"],
-                                       logical_batch=LB, loss_out=st["loss"])
+                                       logical_batch=LB, loss_out=loss)
         else:
             self.native.refine_step(st["x6"], st["betas"], st["gt"], st["m"], st["v"], st["t"], self.lr,
-                                    self.w_joint, self.w_pose, logical_batch=LB, loss_out=st["loss"])
+                                    self.w_joint, self.w_pose, logical_batch=LB, loss_out=loss)
 
     def _run_chunk(self, st, iters, LB, loss_history=None):
         for k in ("m", "v", "t", "cm", "cv"):
@@ -110,20 +111,24 @@ class PoseRefiner:
             st["graphs"] = {}
             st["graph"], st["LB"], st["ver"] = self._capture(st, LB, 1), LB, ver
             st["graphs"][1] = st["graph"]
-        if loss_history is not None:       # the caller reads every iteration's loss: one-step graph + an async copy each
-            for i in range(iters):
-                st["graph"].replay()
-                loss_history[i].copy_(st["loss"], non_blocking=True)
-            return
+        # every captured iteration of the u-step graph writes its loss terms to its own row of st["loss_hist"], so a
+        # caller that reads every iteration's loss (loss_history) still gets the multi-step graphs: one asynchronous copy
+        # of u rows per replay instead of a one-step replay + copy per iteration
         u = self.steps_per_graph
+        done = 0
         if u > 1 and iters >= u:
             if u not in st["graphs"]:
                 st["graphs"][u] = self._capture(st, LB, u)
             for _ in range(iters // u):
                 st["graphs"][u].replay()
-            iters -= (iters // u) * u
-        for _ in range(iters):
+                if loss_history is not None:
+                    loss_history[done:done + u].copy_(st["loss_hist"][u], non_blocking=True)
+                done += u
+            st["loss"].copy_(st["loss_hist"][u][u - 1])
+        for i in range(done, iters):
             st["graph"].replay()
+            if loss_history is not None:
+                loss_history[i].copy_(st["loss"], non_blocking=True)
 
     def _capture(self, st, LB, n_steps):
         # warm-up outside capture (module loading, attribute calls), on a side stream
@@ -135,10 +140,12 @@ class PoseRefiner:
             self._step(st, LB)
         torch.cuda.current_stream(self.device).wait_stream(s)
         self.launches_per_step = self.native.launches
+        if n_steps > 1:      # one loss row per captured iteration (kept per graph length: a captured graph holds its pointers)
+            st.setdefault("loss_hist", {}).setdefault(n_steps, torch.zeros(n_steps, 5, device=self.device))
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for _ in range(n_steps):
-                self._step(st, LB)
+            for i in range(n_steps):
+                self._step(st, LB, None if n_steps == 1 else st["loss_hist"][n_steps][i])
         for k, v in zip(names, keep):
             st[k].copy_(v)
         return g

@@ -1159,3 +1159,27 @@ def test_regressor_refit_through_the_folded_operator(which, smpl_tc, jrr, oracle
         assert torch.equal(refit.J_regressor.cpu()[J <= 0], J[J <= 0])
     finally:
         nat.set_loss_path("vertex")
+
+
+def test_loss_history_through_multi_step_graphs(smpl_tc, jrr, critic_sd, J_shipped, frames64):
+    """`refine(loss_history=...)`: every iteration's five loss terms, identical whether the iterations run eagerly, as
+    one-step graph replays or inside 10-step graphs (each captured iteration writes its own row), into device or pinned
+    host memory; the refined parameters are the same bits as without the read-out."""
+    fr = frames64
+    gt = fr["gt_mm"].to(DEV)
+    out = []
+    for kw, pinned in ((dict(use_graph=False), False), (dict(steps_per_graph=1), False), (dict(steps_per_graph=10), True)):
+        ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, **kw)
+        x6, be = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+        hist = torch.zeros(23, 5).pin_memory() if pinned else torch.zeros(23, 5, device=DEV)
+        last = ref.refine(x6, be, gt, iters=23, loss_history=hist).clone()
+        torch.cuda.synchronize()
+        out.append((x6.clone(), hist.cpu().clone(), last.cpu()))
+    for x6, hist, last in out[1:]:
+        assert torch.equal(x6, out[0][0]) and torch.equal(hist, out[0][1]) and torch.equal(last, out[0][2])
+    h = out[0][1]
+    assert torch.equal(h[-1], out[0][2]) and (h[:, 0] > 0).all() and h[-1, 1] < h[0, 1]      # the joint term decreases
+    ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, steps_per_graph=10)
+    x6, be = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone()
+    ref.refine(x6, be, gt, iters=23)
+    assert torch.equal(x6, out[0][0])
