@@ -14,7 +14,7 @@ smpl = jrr.SMPL(model_dict=jrr.synthetic.make_smpl_model(0), create_transl=False
 nat = smpl.native()
 names = ["tma.wait_empty", "tma.total", "mma.wait_tempty", "mma.wait_full", "mma.wait_ready", "mma.total",
          "prod.wait_full", "prod.wait_afree", "prod.total", "epi.wait_tfull", "epi.total", "mma.fence", "mma.issue", "mma.commit"]
-for M, N, K, probe in [(4096, 1024, 1024, 0), (4096, 1024, 1024, 64), (4096, 1024, 1024, 128), (4096, 1024, 1024, 32)]:
+for M, N, K, probe in [(4096, 1024, 1024, 0), (4096, 1024, 768, 0)]:
     os.environ["JRR_GEMM_PROBE"] = str(probe)
     A = torch.randn(M, K, device=dev)
     B = torch.randn(N, K, device=dev)
