@@ -25,12 +25,13 @@ Workspace carve(const JrrModel* m, int64_t B, void* base) {
   w.feat_hi = take(BP * KA);
   w.feat_lo = take(BP * KA);
   w.vpT = take((size_t)NP * BP);
-  w.part = take((size_t)std::max(NSPLIT, fused_fwd_slots(w.BP, m->num_sms)) * NACC * BP);
+  w.part_stride = (int64_t)std::max(NSPLIT, fused_fwd_slots(w.BP, m->num_sms)) * NACC * (int64_t)BP;
+  w.part = take((size_t)w.part_stride * m->n_pass);
   w.gT = take(NACC * BP);
   w.pred = take(BP * NACC);
   w.dvp_hi = take(BP * (size_t)NP);
   w.dvp_lo = take(BP * (size_t)NP);
-  w.dAflush = take((size_t)std::max(m->n_flush, m->n_flush_l) * 12 * BP);
+  w.dAflush = take((size_t)m->flush_off[m->n_pass] * 12 * BP);
   w.dAT = take(288 * BP);
   w.dfeat = take((size_t)KSPLIT_MAX * BP * KA);
   {
@@ -108,6 +109,42 @@ static int forward_common(const JrrModel* m, const Workspace& w, const float* be
   return blend_forward_gemm(m, w, st);
 }
 
+// The fused forward once per skinning pass (models with more than four weights per vertex; SMPL: one pass).  Pass p > 0
+// re-runs the blend GEMM with the vertex's next four weights: its regressor partial sums go to their own region of
+// `part` (loss_seed adds the regions), skinned vertices are ADDED to the stored ones, blended vertices are not re-stored.
+static int fused_fwd_all_passes(const JrrModel* cm, const Workspace& w, int store, float* out, cudaStream_t st, bool all_vertices) {
+  JrrModel* m = const_cast<JrrModel*>(cm);
+  int rc = JRR_OK;
+  for (int p = 0; p < m->n_pass && rc == JRR_OK; p++) {
+    m->select_pass(p);
+    const int sp = p == 0 ? store : (store == 2 ? 3 : 0);
+    rc = launch_fused_fwd(m, w, sp, out, st, all_vertices);
+  }
+  m->select_pass(0);
+  return rc;
+}
+
+// The fused backward once per skinning pass: split-K partials of pass p go to slots [p*nsplit, (p+1)*nsplit) of dfeat, its dA
+// flush events to their own region, and the dA reduction of pass p > 0 accumulates.  Sets w.ksplit for the chain backward.
+static int fused_bwd_all_passes(const JrrModel* cm, Workspace& w, cudaStream_t st, const float* dvT, cudaEvent_t* ev_mid) {
+  JrrModel* m = const_cast<JrrModel*>(cm);
+  const int nsplit = dvT != nullptr ? NSPLIT_B : m->nsplit_act;
+  if (nsplit * m->n_pass > KSPLIT_MAX) return fail(JRR_ERR_INVALID, "too many skinning passes for the split-K workspace");
+  int rc = JRR_OK;
+  for (int p = 0; p < m->n_pass && rc == JRR_OK; p++) {
+    m->select_pass(p);
+    rc = launch_fused_bwd(m, w, st, dvT);
+  }
+  if (ev_mid && rc == JRR_OK) { cudaError_t e = cudaEventRecord(*ev_mid, st); if (e != cudaSuccess) rc = fail(JRR_ERR_CUDA, cudaGetErrorString(e)); }
+  for (int p = 0; p < m->n_pass && rc == JRR_OK; p++) {
+    m->select_pass(p);
+    rc = launch_dA_reduce(m, w, dvT == nullptr, st);
+  }
+  m->select_pass(0);
+  w.ksplit = nsplit * m->n_pass;
+  return rc;
+}
+
 // Forward of the loss path up to the regressor partial sums.  store: 0 nothing, 1 blended
 // vertices vp -> out (pose-contiguous, the backward needs them), 2 skinned vertices -> out.
 static int loss_forward(const JrrModel* m, const Workspace& w, const float* betas, const float* pose, int kind,
@@ -116,7 +153,7 @@ static int loss_forward(const JrrModel* m, const Workspace& w, const float* beta
   if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, pose, kind, w.AT, w.feat_hi, w.feat_lo, nullptr, st)) return rc;
   if (ev_after_pose) JRR_CUDA(cudaEventRecord(*ev_after_pose, st));
   if (m->fused_fwd) {
-    if (int rc = launch_fused_fwd(m, w, store, out, st)) return rc;
+    if (int rc = fused_fwd_all_passes(m, w, store, out, st, false)) return rc;
     if (ev_after_gemm) JRR_CUDA(cudaEventRecord(*ev_after_gemm, st));
     return JRR_OK;
   }
@@ -163,13 +200,14 @@ extern "C" int jrr_smpl_forward(JrrModel* m, int64_t B, const float* betas, cons
     // model's vertex order with coalesced reads and writes | 49 joints gathered from the packed vertices
     if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, pose, kind, w.AT, w.feat_hi, w.feat_lo,
                                  joints49_out ? w.Jp : nullptr, st)) return rc;
-    if (int rc = launch_fused_fwd(m, w, 2, w.vpT, st, true)) return rc;
+    if (int rc = fused_fwd_all_passes(m, w, 2, w.vpT, st, true)) return rc;
     if (vertices_out)
       if (int rc = launch_unpack_vertices(m, w, w.vpT, vertices_out, st)) return rc;
     if (joints49_out)
       if (int rc = launch_joints49_fwd_packed(m, w, w.vpT, joints49_out, st)) return rc;
     return JRR_OK;
   }
+  if (m->n_pass > 1) return fail(JRR_ERR_STATE, "models with more than 4 skinning weights per vertex need the fused kernels");
   if (int rc = forward_common(m, w, betas, pose, kind, joints49_out != nullptr, st)) return rc;
   // joints49 reads vertices: use caller's buffer, else scratch (dvp_hi is [BP][NP] >= [B][6890][3])
   float* verts = vertices_out ? vertices_out : w.dvp_hi;
@@ -194,17 +232,16 @@ extern "C" int jrr_smpl_backward(JrrModel* m, int64_t B, const float* betas, con
     // joints49 gradient -> its sources | re-pack d vertices | skinning backward generating the A operand of the
     // blend-gradient GEMM (d blended vertices never reach memory) | dA reduction | chain backward
     if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, pose, kind, w.AT, w.feat_hi, w.feat_lo, nullptr, st)) return rc;
-    if (int rc = launch_fused_fwd(m, w, 1, w.vpT, st, true)) return rc;
+    if (int rc = launch_fused_fwd(m, w, 1, w.vpT, st, true)) return rc;      // (the blended vertices do not depend on the pass)
     if (use_x)
       if (int rc = launch_joints49_bwd(m, w, djoints49, st)) return rc;
     float* dvT = w.dvp_hi;
     if (int rc = launch_pack_dvertices(m, w, dvertices, use_x, dvT, st)) return rc;
-    w.ksplit = NSPLIT_B;
-    if (int rc = launch_fused_bwd(m, w, st, dvT)) return rc;
-    if (int rc = launch_dA_reduce(m, w, false, st)) return rc;
+    if (int rc = fused_bwd_all_passes(m, w, st, dvT, nullptr)) return rc;
     return launch_pose_bwd(m, w, betas, pose, kind, use_x, false, false, dbetas_out, dpose_out, nullptr, nullptr,
                            nullptr, nullptr, nullptr, 0.f, st);
   }
+  if (m->n_pass > 1) return fail(JRR_ERR_STATE, "models with more than 4 skinning weights per vertex need the fused kernels");
   if (int rc = forward_common(m, w, betas, pose, kind, false, st)) return rc;
   if (use_x)
     if (int rc = launch_joints49_bwd(m, w, djoints49, st)) return rc;
@@ -343,10 +380,8 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
     // backward: regressor-transpose seed + skinning | dA reduction | blend GEMM
     // (events: skin_bwd [fused: skinning backward + blend-gradient GEMM] | dA_reduce | blend_gemm_bwd [fused: empty])
     if (m->fused_bwd) {
-      w.ksplit = m->nsplit_act;
-      if (int rc = launch_fused_bwd(m, w, st)) return rc;
-      JRR_MARK();
-      if (int rc = launch_dA_reduce(m, w, true, st)) return rc;
+      if (int rc = fused_bwd_all_passes(m, w, st, nullptr, ev ? &ev[mark] : nullptr)) return rc;   // (event: end of the fused kernels)
+      mark += 1;
       JRR_MARK();
       JRR_MARK();
     } else {

@@ -45,7 +45,7 @@ constexpr int F_SMEM_BYTES = F_STAGES * F_STAGE_BYTES + 2 * F_REC_F4 * 16 + 1024
 __host__ __device__ inline int fused_tile_begin(int c, int T, int G) { return (int)(((int64_t)c * T + G - 1) / G); }
 __host__ __device__ inline int fused_cta_of_tile(int t, int T, int G) { return (int)(((int64_t)t * G) / T); }
 
-enum { FSTORE_NONE = 0, FSTORE_VP = 1, FSTORE_V = 2 };
+enum { FSTORE_NONE = 0, FSTORE_VP = 1, FSTORE_V = 2, FSTORE_V_ADD = 3 /* later skinning passes: added to the stored vertices */ };
 
 template <int STORE>
 __global__ void __launch_bounds__(F_THREADS, 1)
@@ -277,6 +277,14 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
           for (int ii = 0; ii < 4; ii++)
 #pragma unroll
             for (int r = 0; r < 3; r++) { *vout = v[ii][r]; vout += BP; }
+        } else if (STORE == FSTORE_V_ADD) {
+          float old[12];
+#pragma unroll
+          for (int e = 0; e < 12; e++) old[e] = vout[(int64_t)e * BP];
+#pragma unroll
+          for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+            for (int r = 0; r < 3; r++) { *vout = old[ii * 3 + r] + v[ii][r]; vout += BP; }
         }
         // ---- 17x6890 regressor reduction (zero columns contribute zeros; skipped per group)
         if (any_col) {
@@ -367,11 +375,12 @@ int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store, float* vT
     auto kern = fused_fwd_kernel<S>;                                                                \
     JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES)); \
     kern<<<G, F_THREADS, F_SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, m->vrec, w.AT, w.BP, m_tiles, n_tiles, \
-                                             vT_out, w.part);                                      \
+                                             vT_out, w.part + (int64_t)m->cur_pass * w.part_stride);  \
   } while (0)
   if (store == FSTORE_NONE) JRR_FF(FSTORE_NONE);
   else if (store == FSTORE_VP) JRR_FF(FSTORE_VP);
-  else JRR_FF(FSTORE_V);
+  else if (store == FSTORE_V) JRR_FF(FSTORE_V);
+  else JRR_FF(FSTORE_V_ADD);
 #undef JRR_FF
   JRR_LAUNCH_CHECK();
   return JRR_OK;

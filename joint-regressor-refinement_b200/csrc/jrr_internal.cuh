@@ -114,6 +114,21 @@ struct Csr {
 
 }  // namespace jrr
 
+namespace jrr {
+// Record tables of one skinning PASS.  A vertex with more than four skinning weights (SMPL has at most four; the C ABI
+// takes any dense [6890,24]) is handled by running the same kernels again with the vertex's next four weights: every
+// output of the skinning kernels is linear in the weights, so passes simply add up (regressor partial sums, stored
+// vertices, blend-gradient partials, joint-transform gradients, the folded operator).  Pass 0 lives in JrrModel's own fields.
+struct PassTab {
+  VtxRec *vrec = nullptr, *vrec_b = nullptr, *vrec_l = nullptr;
+  int *flush_ptr = nullptr, *flush_idx = nullptr, *range_flush_base = nullptr;
+  int n_flush = 0;
+  int *flush_ptr_l = nullptr, *flush_idx_l = nullptr, *range_flush_base_l = nullptr;
+  int n_flush_l = 0;
+};
+constexpr int MAX_PASS = 6;      // 24 weights per vertex
+}  // namespace jrr
+
 struct JrrModel {
   int device = 0;
   int gemm_impl = 0;
@@ -186,6 +201,18 @@ struct JrrModel {
   double* fold_wj = nullptr;                 // [17][VP][4] w * Jhat in double (fold_prep_kernel)
   bool fused_fwd = true;   // loss path: skinning + regressor in the blend GEMM's epilogue
   bool fused_bwd = true;   // loss path: skinning backward generates the A operand of the blend-gradient GEMM
+  // skinning passes (see PassTab): n_pass = ceil(max non-zeros per lbs_weights row / 4)
+  int n_pass = 1, cur_pass = 0;
+  jrr::PassTab passes[jrr::MAX_PASS];        // [0] mirrors the fields above
+  int flush_off[jrr::MAX_PASS + 1] = {0};    // offset (in flush events) of each pass inside Workspace::dAflush
+  void select_pass(int p) {                  // point the table fields at pass p (launches capture them by value)
+    const jrr::PassTab& t = passes[p];
+    vrec = t.vrec; vrec_b = t.vrec_b; vrec_l = t.vrec_l;
+    flush_ptr = t.flush_ptr; flush_idx = t.flush_idx; range_flush_base = t.range_flush_base; n_flush = t.n_flush;
+    flush_ptr_l = t.flush_ptr_l; flush_idx_l = t.flush_idx_l; range_flush_base_l = t.range_flush_base_l; n_flush_l = t.n_flush_l;
+    n_flush_act = t.n_flush_l;
+    cur_pass = p;
+  }
   std::vector<void*> allocs;
 };
 
@@ -198,7 +225,8 @@ struct Workspace {
   float* feat_hi;   // [BP][224]
   float* feat_lo;
   float* vpT;       // [NP][BP]    posed-blend vertices, pose contiguous
-  float* part;      // [NSPLIT][51][BP] regressor partial sums
+  float* part;      // [n_pass][slots][51][BP] regressor partial sums (one region per skinning pass)
+  int64_t part_stride;   // floats per pass region
   float* gT;        // [51][BP]    loss seed (pelvis adjusted)
   float* pred;      // [BP][51]
   float* dvp_hi;    // [BP][NP]

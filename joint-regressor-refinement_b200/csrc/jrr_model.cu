@@ -229,8 +229,11 @@ int launch_regressor_normalise(JrrModel* m, const float* Jraw, const float* mask
   JRR_LAUNCH_CHECK();
   reg_normalise_kernel<<<(NH * V + 255) / 256, 256, 0, st>>>(Jraw, mask, m->rowsum, m->Jhat);
   JRR_LAUNCH_CHECK();
-  reg_records_kernel<<<(VP + 255) / 256, 256, 0, st>>>(m->Jhat, m->perm, m->vrec, m->vrec_b, m->vrec_l);
-  JRR_LAUNCH_CHECK();
+  for (int pass = 0; pass < m->n_pass; pass++) {      // the regressor column rides in every pass's records
+    const PassTab& t = m->passes[pass];
+    reg_records_kernel<<<(VP + 255) / 256, 256, 0, st>>>(m->Jhat, m->perm, t.vrec, t.vrec_b, t.vrec_l);
+    JRR_LAUNCH_CHECK();
+  }
   m->has_regressor = true;
   return JRR_OK;
 }
@@ -357,8 +360,10 @@ int regressor_accumulate_folded(const JrrModel* m, Workspace& w, const float* gt
     g.out0 = U; g.ldo = VP;
     if (int rc = launch_gemm(m, g, st)) return rc;
   }
-  unfold_gather_kernel<<<dim3((unsigned)((m->nv_act + 255) / 256), NH), 256, 0, st>>>(m->vrec, m->perm, U, dc, m->nv_act, G_accum);
-  JRR_LAUNCH_CHECK();
+  for (int pass = 0; pass < m->n_pass; pass++) {
+    unfold_gather_kernel<<<dim3((unsigned)((m->nv_act + 255) / 256), NH), 256, 0, st>>>(m->passes[pass].vrec, m->perm, U, dc, m->nv_act, G_accum);
+    JRR_LAUNCH_CHECK();
+  }
   return JRR_OK;
 }
 
@@ -381,7 +386,7 @@ __global__ void fold_prep_kernel(const VtxRec* __restrict__ vrec, double* __rest
 
 __global__ void __launch_bounds__(KA)
 fold_kernel(const VtxRec* __restrict__ vrec, const double* __restrict__ wj, const float* __restrict__ Pt_hi,
-            const float* __restrict__ Pt_lo, double* __restrict__ part) {
+            const float* __restrict__ Pt_lo, double* __restrict__ part, int accumulate) {
   // Packed vertices are sorted by joint set, so a record slot keeps its joint over long runs: each thread keeps the four
   // slots' running sums in REGISTERS (four independent double chains) and adds them to the per-joint shared-memory
   // accumulators only when a slot's joint changes (the records' reload bits: ~190 times over the whole model) -- the
@@ -437,7 +442,7 @@ fold_kernel(const VtxRec* __restrict__ vrec, const double* __restrict__ wj, cons
 #pragma unroll
   for (int s4 = 0; s4 < 4; s4++) acc[jcur[s4] * KA + k] += run[s4];
   double* out = part + ((int64_t)(ch * NH + i) * 4 + c) * (NJ * KA);
-  for (int j = 0; j < NJ; j++) out[j * KA + k] = acc[j * KA + k];
+  for (int j = 0; j < NJ; j++) out[j * KA + k] = accumulate ? out[j * KA + k] + acc[j * KA + k] : acc[j * KA + k];
 }
 
 __global__ void fold_finish_kernel(const double* __restrict__ part, float* __restrict__ T_hi, float* __restrict__ T_lo,
@@ -477,10 +482,13 @@ int launch_fold(JrrModel* m, cudaStream_t st) {
     if (int rc = dalloc(m, &m->fold_part, (size_t)FOLD_CH * NH * 4 * NJ * KA)) return rc;
     if (int rc = dalloc(m, &m->fold_wj, (size_t)NH * VP * 4)) return rc;
   }
-  fold_prep_kernel<<<(NH * VP + 255) / 256, 256, 0, st>>>(m->vrec, m->fold_wj);
-  JRR_LAUNCH_CHECK();
-  fold_kernel<<<dim3(NH, 4, FOLD_CH), KA, 0, st>>>(m->vrec, m->fold_wj, m->Pt_hi, m->Pt_lo, m->fold_part);
-  JRR_LAUNCH_CHECK();
+  for (int pass = 0; pass < m->n_pass; pass++) {      // linear in the skinning weights: passes add up in the fp64 partials
+    const PassTab& t = m->passes[pass];
+    fold_prep_kernel<<<(NH * VP + 255) / 256, 256, 0, st>>>(t.vrec, m->fold_wj);
+    JRR_LAUNCH_CHECK();
+    fold_kernel<<<dim3(NH, 4, FOLD_CH), KA, 0, st>>>(t.vrec, m->fold_wj, m->Pt_hi, m->Pt_lo, m->fold_part, pass > 0 ? 1 : 0);
+    JRR_LAUNCH_CHECK();
+  }
   const int64_t n = (int64_t)FOLD_N * KA + NJ * NH;
   fold_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->fold_part, m->T_hi, m->T_lo, m->Tt_hi, m->Tt_lo, m->Tc);
   JRR_LAUNCH_CHECK();
@@ -562,14 +570,18 @@ int build_packing(JrrModel* m, const std::vector<uint8_t>& active) {
       for (auto& e : m->h_vx[perm[i]]) { vx_src.push_back(e.first); vx_coef.push_back(e.second); }
     xcnt[i] = (int)vx_src.size() - xptr[i];
   }
-  auto build = [&](int VS, std::vector<VtxRec>& rec, std::vector<int>* flush_joint, std::vector<int>* range_base) {
+  auto build = [&](int pass, int VS, std::vector<VtxRec>& rec, std::vector<int>* flush_joint, std::vector<int>* range_base) {
     rec.assign(VP, VtxRec{});
     int cur[4] = {0, 0, 0, 0};
     for (int i = 0; i < VP; i++) {
       const bool first = (i % VS) == 0;
       if (first && range_base) (*range_base)[i / VS] = (int)flush_joint->size();
-      static const std::vector<std::pair<int, float>> none;
-      const std::vector<std::pair<int, float>>& nz = perm[i] >= 0 ? m->h_lbs[perm[i]] : none;
+      // this pass's (up to four) weights of the vertex: entries [4*pass, 4*pass + 4) of its list
+      std::vector<std::pair<int, float>> nz;
+      if (perm[i] >= 0) {
+        const auto& all = m->h_lbs[perm[i]];
+        for (size_t e = (size_t)4 * pass; e < all.size() && e < (size_t)4 * pass + 4; e++) nz.push_back(all[e]);
+      }
       int nj[4];
       float nw[4] = {0.f, 0.f, 0.f, 0.f};
       bool used[4] = {false, false, false, false};
@@ -597,27 +609,15 @@ int build_packing(JrrModel* m, const std::vector<uint8_t>& active) {
         cur[k] = nj[k];
       }
       if (first) meta |= 1u << 25;
-      if (xcnt[i] > 0) meta |= 1u << 26;
+      if (xcnt[i] > 0 && pass == 0) meta |= 1u << 26;
       rec[i].meta = meta;
       for (int k = 0; k < 4; k++) rec[i].w[k] = nw[k];
       rec[i].xptr = xptr[i];
-      rec[i].xcnt = xcnt[i];
+      rec[i].xcnt = pass == 0 ? xcnt[i] : 0;
       if (flush_joint && (i % VS) == VS - 1)
         for (int k = 0; k < 4; k++) flush_joint->push_back(cur[k]);
     }
   };
-  std::vector<VtxRec> rec_f, rec_b, rec_l;
-  std::vector<int> flush_joint, range_base(NSPLIT_B + 1), flush_joint_l, range_base_l(VP / 192 + 1, 0);
-  build(VS_F, rec_f, nullptr, nullptr);
-  build(VS_B, rec_b, &flush_joint, &range_base);            // module backward: every vertex, 768-vertex ranges
-  build(m->vs_l, rec_l, &flush_joint_l, &range_base_l);     // fused backward: vs_l-vertex ranges
-  range_base[NSPLIT_B] = (int)flush_joint.size();
-  m->n_flush = (int)flush_joint.size();
-  // the fused backward only walks the active ranges: its flush ids are a prefix
-  flush_joint_l.resize(range_base_l[m->nsplit_act] ? range_base_l[m->nsplit_act] : flush_joint_l.size());
-  if (m->nsplit_act * m->vs_l >= VP) flush_joint_l.resize(flush_joint_l.size());
-  m->n_flush_l = (int)flush_joint_l.size();
-  m->n_flush_act = m->n_flush_l;
   // CSR joint -> flush ids (ids ascend inside a joint's list)
   auto csr = [](const std::vector<int>& fj, std::vector<int>& fptr, std::vector<int>& fidx) {
     fptr.assign(NJ + 1, 0);
@@ -627,12 +627,6 @@ int build_packing(JrrModel* m, const std::vector<uint8_t>& active) {
     std::vector<int> fill(fptr.begin(), fptr.end() - 1);
     for (int f = 0; f < (int)fj.size(); f++) fidx[fill[fj[f]]++] = f;
   };
-  std::vector<int> fptr, fidx, fptr_l, fidx_l;
-  csr(flush_joint, fptr, fidx);
-  csr(flush_joint_l, fptr_l, fidx_l);
-  if (fidx.size() > (size_t)4 * VP + 4 * NSPLIT_B || fidx_l.size() > (size_t)4 * VP + 4 * 36)
-    return fail(JRR_ERR_INVALID, "flush list overflow");
-
   JRR_CUDA(cudaMemcpy(m->perm, perm.data(), sizeof(int) * VP, cudaMemcpyHostToDevice));
   {
     std::vector<int> inv(V, 0);
@@ -640,19 +634,40 @@ int build_packing(JrrModel* m, const std::vector<uint8_t>& active) {
       if (perm[i] >= 0) inv[perm[i]] = i;
     JRR_CUDA(cudaMemcpy(m->inv_perm, inv.data(), sizeof(int) * V, cudaMemcpyHostToDevice));
   }
-  JRR_CUDA(cudaMemcpy(m->vrec, rec_f.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
-  JRR_CUDA(cudaMemcpy(m->vrec_b, rec_b.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
   if (!vx_src.empty()) {
     JRR_CUDA(cudaMemcpy(m->vx_src, vx_src.data(), sizeof(int) * vx_src.size(), cudaMemcpyHostToDevice));
     JRR_CUDA(cudaMemcpy(m->vx_coef, vx_coef.data(), sizeof(float) * vx_coef.size(), cudaMemcpyHostToDevice));
   }
-  JRR_CUDA(cudaMemcpy(m->flush_ptr, fptr.data(), sizeof(int) * (NJ + 1), cudaMemcpyHostToDevice));
-  if (!fidx.empty()) JRR_CUDA(cudaMemcpy(m->flush_idx, fidx.data(), sizeof(int) * fidx.size(), cudaMemcpyHostToDevice));
-  JRR_CUDA(cudaMemcpy(m->range_flush_base, range_base.data(), sizeof(int) * (NSPLIT_B + 1), cudaMemcpyHostToDevice));
-  JRR_CUDA(cudaMemcpy(m->vrec_l, rec_l.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
-  JRR_CUDA(cudaMemcpy(m->flush_ptr_l, fptr_l.data(), sizeof(int) * (NJ + 1), cudaMemcpyHostToDevice));
-  if (!fidx_l.empty()) JRR_CUDA(cudaMemcpy(m->flush_idx_l, fidx_l.data(), sizeof(int) * fidx_l.size(), cudaMemcpyHostToDevice));
-  JRR_CUDA(cudaMemcpy(m->range_flush_base_l, range_base_l.data(), sizeof(int) * 37, cudaMemcpyHostToDevice));
+  m->flush_off[0] = 0;
+  for (int pass = 0; pass < m->n_pass; pass++) {
+    PassTab& t = m->passes[pass];
+    std::vector<VtxRec> rec_f, rec_b, rec_l;
+    std::vector<int> flush_joint, range_base(NSPLIT_B + 1), flush_joint_l, range_base_l(VP / 192 + 1, 0);
+    build(pass, VS_F, rec_f, nullptr, nullptr);
+    build(pass, VS_B, rec_b, &flush_joint, &range_base);            // module backward: every vertex, 768-vertex ranges
+    build(pass, m->vs_l, rec_l, &flush_joint_l, &range_base_l);     // fused backward: vs_l-vertex ranges
+    range_base[NSPLIT_B] = (int)flush_joint.size();
+    t.n_flush = (int)flush_joint.size();
+    // the fused backward only walks the active ranges: its flush ids are a prefix
+    flush_joint_l.resize(range_base_l[m->nsplit_act] ? range_base_l[m->nsplit_act] : flush_joint_l.size());
+    t.n_flush_l = (int)flush_joint_l.size();
+    std::vector<int> fptr, fidx, fptr_l, fidx_l;
+    csr(flush_joint, fptr, fidx);
+    csr(flush_joint_l, fptr_l, fidx_l);
+    if (fidx.size() > (size_t)4 * VP + 4 * NSPLIT_B || fidx_l.size() > (size_t)4 * VP + 4 * 36)
+      return fail(JRR_ERR_INVALID, "flush list overflow");
+    JRR_CUDA(cudaMemcpy(t.vrec, rec_f.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
+    JRR_CUDA(cudaMemcpy(t.vrec_b, rec_b.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
+    JRR_CUDA(cudaMemcpy(t.flush_ptr, fptr.data(), sizeof(int) * (NJ + 1), cudaMemcpyHostToDevice));
+    if (!fidx.empty()) JRR_CUDA(cudaMemcpy(t.flush_idx, fidx.data(), sizeof(int) * fidx.size(), cudaMemcpyHostToDevice));
+    JRR_CUDA(cudaMemcpy(t.range_flush_base, range_base.data(), sizeof(int) * (NSPLIT_B + 1), cudaMemcpyHostToDevice));
+    JRR_CUDA(cudaMemcpy(t.vrec_l, rec_l.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
+    JRR_CUDA(cudaMemcpy(t.flush_ptr_l, fptr_l.data(), sizeof(int) * (NJ + 1), cudaMemcpyHostToDevice));
+    if (!fidx_l.empty()) JRR_CUDA(cudaMemcpy(t.flush_idx_l, fidx_l.data(), sizeof(int) * fidx_l.size(), cudaMemcpyHostToDevice));
+    JRR_CUDA(cudaMemcpy(t.range_flush_base_l, range_base_l.data(), sizeof(int) * 37, cudaMemcpyHostToDevice));
+    m->flush_off[pass + 1] = m->flush_off[pass] + std::max(t.n_flush, t.n_flush_l);
+  }
+  m->select_pass(0);
   const int64_t n = (int64_t)KA * NP;
   repack_blend_kernel<<<(unsigned)((n + 255) / 256), 256>>>(m->Pn, m->perm, m->P_hi, m->P_lo, m->Pt_hi, m->Pt_lo);
   JRR_CUDA(cudaGetLastError());
@@ -738,10 +753,16 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
       const float x = d->lbs_weights_host[(size_t)v * NJ + j];
       if (x != 0.f) { k |= 1u << j; m->h_lbs[v].push_back({j, x}); }
     }
-    if (m->h_lbs[v].size() > 4)
-      return fail(JRR_ERR_INVALID, "lbs_weights row with more than 4 non-zeros is not supported by this build");
+    // largest weights first: pass 0 then carries most of every vertex (and a 4-weight model is exactly one pass)
+    std::stable_sort(m->h_lbs[v].begin(), m->h_lbs[v].end(),
+                     [](const std::pair<int, float>& a, const std::pair<int, float>& b) { return std::fabs(a.second) > std::fabs(b.second); });
+    m->n_pass = std::max(m->n_pass, (int)(m->h_lbs[v].size() + 3) / 4);
     m->h_key[v] = k;
   }
+  if (m->n_pass > 1 && m->gemm_impl != 0)
+    return fail(JRR_ERR_INVALID, "lbs_weights rows with more than 4 non-zeros need the tensor-core build (gemm_impl 0): "
+                                 "the SIMT validation kernels are single-pass");
+  if (m->n_pass > 1) { m->fused_fwd = true; m->fused_bwd = true; }      // the unfused validation kernels are single-pass
 
   // ---- natural-order master of the augmented blend matrix [224][3*6890] (rows: posedirs, shapedirs^T, template)
   {
@@ -823,15 +844,20 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   // ---- device buffers of the packing (filled by build_packing; sizes do not depend on the order)
   if (int rc = dalloc(m, &m->perm, VP)) return rc;
   if (int rc = dalloc(m, &m->inv_perm, V)) return rc;
-  if (int rc = dalloc(m, &m->vrec, VP)) return rc;
-  if (int rc = dalloc(m, &m->vrec_b, VP)) return rc;
-  if (int rc = dalloc(m, &m->flush_ptr, NJ + 1)) return rc;
-  if (int rc = dalloc(m, &m->flush_idx, (size_t)4 * VP + 4 * NSPLIT_B)) return rc;
-  if (int rc = dalloc(m, &m->range_flush_base, NSPLIT_B + 1)) return rc;
-  if (int rc = dalloc(m, &m->vrec_l, VP)) return rc;
-  if (int rc = dalloc(m, &m->flush_ptr_l, NJ + 1)) return rc;
-  if (int rc = dalloc(m, &m->flush_idx_l, (size_t)4 * VP + 4 * 36)) return rc;
-  if (int rc = dalloc(m, &m->range_flush_base_l, 37)) return rc;
+  if (m->n_pass > MAX_PASS) return fail(JRR_ERR_INVALID, "more than 24 skinning weights per vertex");
+  for (int pass = 0; pass < m->n_pass; pass++) {
+    PassTab& t = m->passes[pass];
+    if (int rc = dalloc(m, &t.vrec, VP)) return rc;
+    if (int rc = dalloc(m, &t.vrec_b, VP)) return rc;
+    if (int rc = dalloc(m, &t.flush_ptr, NJ + 1)) return rc;
+    if (int rc = dalloc(m, &t.flush_idx, (size_t)4 * VP + 4 * NSPLIT_B)) return rc;
+    if (int rc = dalloc(m, &t.range_flush_base, NSPLIT_B + 1)) return rc;
+    if (int rc = dalloc(m, &t.vrec_l, VP)) return rc;
+    if (int rc = dalloc(m, &t.flush_ptr_l, NJ + 1)) return rc;
+    if (int rc = dalloc(m, &t.flush_idx_l, (size_t)4 * VP + 4 * 36)) return rc;
+    if (int rc = dalloc(m, &t.range_flush_base_l, 37)) return rc;
+  }
+  m->select_pass(0);
   if (int rc = dalloc(m, &m->active_dev, V)) return rc;
   if (int rc = build_packing(m, std::vector<uint8_t>(V, 1))) return rc;
 

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(LS_THREADS)
 loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T, int G,
                  const float* __restrict__ gt_mm, int64_t B, int64_t BP, float scale,
                  float* __restrict__ gT, float* __restrict__ joints17_out, float* __restrict__ loss_part,
-                 const Proj2D p2d) {
+                 const Proj2D p2d, int n_pass, int64_t pass_stride) {
   constexpr int NC = PPB / 32;
   __shared__ float sp[NACC][PPB];
   __shared__ float red[NC], red2[NC];
@@ -246,21 +246,23 @@ loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T,
   }
   const int64_t slot_stride = (int64_t)NACC * BP;
   for (int a = warp; a < NACC; a += LS_THREADS / 32) {
-    const float* src = part + (int64_t)a * BP + b0 + lane;
     float acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) acc[c] = 0.f;
-    // 8 slots per round trip (predicated): the kernel is bound by the latency of these loads
-    for (int s = 0; s < nslots; s += 8) {
-      float v[8][NC];
+    for (int ps = 0; ps < n_pass; ps++) {          // one region of partial sums per skinning pass (SMPL: one)
+      const float* src = part + ps * pass_stride + (int64_t)a * BP + b0 + lane;
+      // 8 slots per round trip (predicated): the kernel is bound by the latency of these loads
+      for (int s = 0; s < nslots; s += 8) {
+        float v[8][NC];
 #pragma unroll
-      for (int u = 0; u < 8; u++)
+        for (int u = 0; u < 8; u++)
 #pragma unroll
-        for (int c = 0; c < NC; c++) v[u][c] = (s + u < nslots) ? src[(int64_t)(s + u) * slot_stride + 32 * c] : 0.f;
+          for (int c = 0; c < NC; c++) v[u][c] = (s + u < nslots) ? src[(int64_t)(s + u) * slot_stride + 32 * c] : 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; u++)
+        for (int u = 0; u < 8; u++)
 #pragma unroll
-        for (int c = 0; c < NC; c++) acc[c] += v[u][c];
+          for (int c = 0; c < NC; c++) acc[c] += v[u][c];
+      }
     }
 #pragma unroll
     for (int c = 0; c < NC; c++) sp[a][lane + 32 * c] = acc[c];
@@ -751,7 +753,7 @@ skin_bwd_kernel(const VtxRec* __restrict__ vrec, const int* __restrict__ perm,
 // dAT[k][e][b] = sum over the flush events of joint k (fixed order)
 __global__ void __launch_bounds__(SK_THREADS)
 dA_reduce_kernel(const int* __restrict__ flush_ptr, const int* __restrict__ flush_idx, int flush_limit,
-                 const float* __restrict__ dAflush, int64_t BP, float* __restrict__ dAT) {
+                 const float* __restrict__ dAflush, int64_t BP, float* __restrict__ dAT, int accumulate) {
   const int64_t b = (int64_t)blockIdx.x * SK_THREADS + threadIdx.x;
   const int k = blockIdx.y;
   float acc[12];
@@ -766,7 +768,10 @@ dA_reduce_kernel(const int* __restrict__ flush_ptr, const int* __restrict__ flus
     for (int e = 0; e < 12; e++) acc[e] += src[(int64_t)e * BP];
   }
 #pragma unroll
-  for (int e = 0; e < 12; e++) dAT[(int64_t)(k * 12 + e) * BP + b] = acc[e];
+  for (int e = 0; e < 12; e++) {
+    float* d = dAT + (int64_t)(k * 12 + e) * BP + b;
+    *d = accumulate ? *d + acc[e] : acc[e];      // (later skinning passes add to the first)
+  }
 }
 
 // ----------------------------------------------------------------------- module path: vertex un-packing
@@ -1064,10 +1069,12 @@ int launch_loss_seed(const JrrModel* m, Workspace& w, bool fused_partials, const
   const int n_tiles = m->nv_act / 64, T = (int)(w.BP / 128) * n_tiles, G = T < m->num_sms ? T : m->num_sms;
   if (ppb == 32)
     loss_seed_kernel<32><<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, gt_mm, w.B, w.BP, scale,
-                                                 gt_mm != nullptr ? w.gT : nullptr, joints17_out, w.loss_part, p2d);
+                                                 gt_mm != nullptr ? w.gT : nullptr, joints17_out, w.loss_part, p2d,
+                                                 fused_partials ? m->n_pass : 1, w.part_stride);
   else
     loss_seed_kernel<128><<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, gt_mm, w.B, w.BP, scale,
-                                                  gt_mm != nullptr ? w.gT : nullptr, joints17_out, w.loss_part, p2d);
+                                                  gt_mm != nullptr ? w.gT : nullptr, joints17_out, w.loss_part, p2d,
+                                                  fused_partials ? m->n_pass : 1, w.part_stride);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
@@ -1098,10 +1105,12 @@ int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertice
 
 int launch_dA_reduce(const JrrModel* m, const Workspace& w, bool loss_path_lists, cudaStream_t st) {
   dim3 grid((unsigned)(w.BP / SK_THREADS), NJ), block(SK_THREADS);
+  const float* src = w.dAflush + (int64_t)m->flush_off[m->cur_pass] * 12 * w.BP;      // this pass's flush region
+  const int acc = m->cur_pass > 0 ? 1 : 0;
   if (loss_path_lists)
-    dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr_l, m->flush_idx_l, m->n_flush_l, w.dAflush, w.BP, w.dAT);
+    dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr_l, m->flush_idx_l, m->n_flush_l, src, w.BP, w.dAT, acc);
   else
-    dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr, m->flush_idx, m->n_flush, w.dAflush, w.BP, w.dAT);
+    dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr, m->flush_idx, m->n_flush, src, w.BP, w.dAT, acc);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }

@@ -85,10 +85,12 @@ def _sparse_rows(rng, targets, verts, nnz):
     return out
 
 
-def make_smpl_model(seed: int = 0) -> dict:
+def make_smpl_model(seed: int = 0, skin_weights_per_vertex: int = 4) -> dict:
     """Random-init SMPL of the canonical shape.  Returns float32/int64 numpy arrays with
     the smplx buffer names: v_template, shapedirs, posedirs, J_regressor, parents,
-    lbs_weights, faces, J_regressor_extra, joint_map, vertex_picks."""
+    lbs_weights, faces, J_regressor_extra, joint_map, vertex_picks.
+    ``skin_weights_per_vertex`` (SMPL: 4) sets the non-zeros of every ``lbs_weights`` row; larger values
+    exercise the multi-pass skinning of models that are not 4-sparse."""
     rng = np.random.default_rng(seed)
     # vertices are generated bone by bone so that neighbouring ids are spatial
     # neighbours, as in the real SMPL mesh
@@ -116,9 +118,9 @@ def make_smpl_model(seed: int = 0) -> dict:
 
     J_regressor = _sparse_rows(rng, _REST, v_template, 32)
 
-    # exactly 4 non-zeros per vertex: softmax(-distance) over the 4 nearest joints
+    # exactly 4 (default) non-zeros per vertex: softmax(-distance) over the nearest joints
     dist = np.linalg.norm(v_template[:, None, :] - _REST[None, :, :], axis=2)
-    near = np.argsort(dist, axis=1, kind="stable")[:, :4]
+    near = np.argsort(dist, axis=1, kind="stable")[:, :skin_weights_per_vertex]
     logits = -np.take_along_axis(dist, near, axis=1) / 0.05
     logits -= logits.max(axis=1, keepdims=True)
     w4 = np.exp(logits)

@@ -404,14 +404,101 @@ def test_errors_are_loud(smpl_tc, jrr, critic_sd, J_shipped):
         fresh.refine_step(x6, be, gt, mm, mm.clone(), t, 1e-2, 1e4, 10.0)
 
 
-def test_model_with_five_weights_per_vertex_is_rejected(jrr, model):
-    bad = dict(model)
-    w = model["lbs_weights"].copy()
-    w[0, :] = 0
-    w[0, :5] = 0.2
-    bad["lbs_weights"] = w
-    with pytest.raises(jrr.JrrError, match="more than 4"):
-        jrr.SMPL(model_dict=bad, create_transl=False).to(DEV).native()
+# ------------------------------------------------------------------ models that are not 4-sparse
+@pytest.fixture(scope="module")
+def model6(jrr):
+    """Every vertex skinned to SIX joints: two skinning passes (4 + 2 weights) through the same kernels."""
+    m = jrr.synthetic.make_smpl_model(0, skin_weights_per_vertex=6)
+    assert ((m["lbs_weights"] != 0).sum(1) == 6).all()
+    return m
+
+
+@pytest.fixture(scope="module")
+def smpl6(jrr, model6):
+    return jrr.SMPL(model_dict=model6, create_transl=False).to(DEV)
+
+
+def test_six_weight_model_forward_and_backward(smpl6, model6, jrr, oracle):
+    """SMPL.forward / backward of a 6-weights-per-vertex model against the fp64 oracle (dense skinning weights there)."""
+    o64 = oracle.OracleSMPL(model6, torch.float64)
+    B = 70
+    inp = jrr.synthetic.make_pose_inputs(B, 31)
+    R = torch.from_numpy(inp["true_rotmat"]); betas = torch.from_numpy(inp["true_betas"])
+    g = torch.Generator().manual_seed(2)
+    wv, wj = torch.randn(B, 6890, 3, generator=g), torch.randn(B, 49, 3, generator=g)
+
+    def run(fn, dt, dev):
+        b = betas.to(dev, dt).requires_grad_(True)
+        o = R[:, :1].contiguous().to(dev, dt).requires_grad_(True)
+        p = R[:, 1:].contiguous().to(dev, dt).requires_grad_(True)
+        out = fn(betas=b, body_pose=p, global_orient=o, pose2rot=False)
+        ((out.vertices * wv.to(dev, dt)).sum() + (out.joints * wj.to(dev, dt)).sum()).backward()
+        return out, b.grad, o.grad, p.grad
+    ro, rb, rg, rp = run(o64, torch.float64, "cpu")
+    co, cb, cg, cp = run(smpl6, torch.float32, DEV)
+    ev, ej = rel(co.vertices, ro.vertices), rel(co.joints, ro.joints)
+    eb, eo, ep = rel(cb, rb), rel(cg, rg), rel(cp, rp)
+    print(f"6-weight model: vertices {ev:.2e} joints {ej:.2e}; dbetas {eb:.2e} dorient {eo:.2e} dpose {ep:.2e}")
+    assert ev < 1e-5 and ej < 1e-5
+    assert eb < 1e-4 and eo < 1e-4 and ep < 1e-4
+    # and it differs from truncating every vertex to its four largest weights (the check is not vacuous)
+    m4 = dict(model6)
+    w = model6["lbs_weights"].copy()
+    idx = np.argsort(-w, axis=1)[:, 4:]
+    np.put_along_axis(w, idx, 0.0, axis=1)
+    m4["lbs_weights"] = w
+    t = oracle.OracleSMPL(m4, torch.float64)(betas=betas.double(), body_pose=R[:, 1:].double(), global_orient=R[:, :1].double(), pose2rot=False)
+    assert rel(t.vertices, ro.vertices) > 1e-3
+
+
+@pytest.mark.parametrize("which", ["shipped", "dense"])
+def test_six_weight_model_refine_and_refit(which, smpl6, model6, jrr, oracle, critic_sd, J_shipped, J_dense):
+    """The refinement step (both loss-path formulations) and the regressor refit (both forms) on the 6-weight model:
+    find_joints, one-step losses and gradients, and the refit gradient against the fp64 oracle."""
+    J = J_shipped if which == "shipped" else J_dense
+    o32, o64 = oracle.OracleSMPL(model6), oracle.OracleSMPL(model6, torch.float64)
+    n = 150
+    fr = make_frames(jrr, oracle, o32, J, n, 77)
+    R = fr["true_rotmat"]
+    ref_j = oracle.find_joints(o64, fr["true_betas"].double(), R[:, :1].double(), R[:, 1:].double(), J.double())
+    with torch.no_grad():
+        got_j = jrr.find_joints(smpl6, fr["true_betas"].to(DEV), R[:, :1].to(DEV), R[:, 1:].to(DEV), J.to(DEV))
+    assert rel(got_j, ref_j) < 1e-5
+    sd64 = {k: v.double() for k, v in critic_sd.items()}
+    x6 = fr["x6"].double().requires_grad_(True)
+    be = fr["betas"].double().requires_grad_(True)
+    total, jl, pl, _ = oracle.refine_loss(o64, J.double(), sd64, x6, be, fr["gt_mm"].double())
+    total.backward()
+    gall = torch.cat([x6.grad.reshape(n, 144), be.grad], dim=1)
+    kink = oracle.critic_kink_frames(critic_sd, fr["x6"])
+    gJ, lJ = oracle.regressor_grad(o64, J.double(), fr["x6"].double(), fr["betas"].double(), fr["gt_mm"].double())
+    nat = smpl6.native()
+    try:
+        for path in ("vertex", "folded"):
+            ref = jrr.PoseRefiner(smpl6, J, critic_sd, use_graph=False, loss_path=path)
+            st = ref._buffers(n)
+            st["x6"].copy_(fr["x6"]); st["betas"].copy_(fr["betas"]); st["gt"].copy_(fr["gt_mm"])
+            ref._run_chunk(st, 1, n)
+            torch.cuda.synchronize()
+            loss = st["loss"].cpu().double()
+            d = ((st["m"].cpu().double() * 10 - gall).abs().max(1).values / gall.abs().max())[~kink]
+            print(f"[{which}/{path}] 6-weight model: loss {loss[0].item():.6f} vs {total.item():.6f}; gradient rel err {d.max().item():.2e}")
+            assert abs(loss[0].item() - total.item()) / total.item() < 1e-5 and abs(loss[1].item() - jl.item()) / jl.item() < 1e-5
+            assert d.max().item() < 1e-4
+            refit = jrr.RegressorRefit(smpl6, J, lr=1e-2, chunk=100)          # ragged chunks: 100 + 50
+            opt = oracle.RegressorAdam(J.double(), lr=1e-2)
+            Jo = opt.step(gJ)
+            l = refit.step(fr["x6"].to(DEV), fr["betas"].to(DEV), fr["gt_mm"].to(DEV))
+            dJ = (refit.J_regressor.cpu().double() - Jo).abs().max().item()
+            print(f"[{which}/{path}] 6-weight model refit: loss {l.item():.6e} vs {lJ:.6e}; max |dJ| {dJ:.2e}")
+            assert abs(l.item() - lJ) / lJ < 1e-4 and dJ < 1e-4
+    finally:
+        nat.set_loss_path("vertex")
+
+
+def test_more_than_24_weights_or_simt_build_is_rejected(jrr, model6):
+    with pytest.raises(jrr.JrrError, match="tensor-core build"):
+        jrr.SMPL(model_dict=model6, create_transl=False, gemm_impl=1).to(DEV).native()
 
 
 def test_transl_and_default_parameters(smpl_tc, jrr, model, osmpl32):
