@@ -419,8 +419,8 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
                                  nullptr, nullptr, nullptr, 0.f, st)) return rc;
   // The loss read-out does not feed the update: with the fork it runs on the critic's stream (after the
   // seed kernel's partials, ev_seed) beside the Adam kernel, and the step ends when both have.
-  // (measured bimodal, 0.303 / 0.335 ms against a steady 0.318 ms inline, so it is off unless JRR_FINISH_ASIDE=1)
-  static const bool aside_on = [] { const char* e = getenv("JRR_FINISH_ASIDE"); return e && e[0] == '1'; }();
+  // (round 2, K = 100, two runs each: 0.2866 / 0.2873 ms against 0.2902 / 0.2900 ms inline; JRR_FINISH_ASIDE=0 switches it off)
+  static const bool aside_on = [] { const char* e = getenv("JRR_FINISH_ASIDE"); return !(e && e[0] == '0'); }();
   const bool finish_aside = aside_on && split && loss_out != nullptr;
   if (finish_aside) {
     JRR_CUDA(cudaStreamWaitEvent(m->side, m->ev_seed, 0));
