@@ -244,3 +244,23 @@ def test_export_normalised_regressor_round_trip(tmp_path, jrr, oracle, J_shipped
     import pytest
     with pytest.raises(ValueError, match="no positive entry"):
         jrr.export_normalised_regressor(bad)
+
+
+def test_bench_chunking_and_regressor_loading_helpers():
+    """bench.py's host helpers: balanced chunks (sizes differ by at most one, all frames covered) and the shipped
+    artefact through the product loader (byte copy under tests/golden when /root/reference is absent)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for n, c in ((312000, 4096), (39000, 4096), (4096, 4096), (5, 4096), (8193, 4096)):
+        ch = bench.balanced_chunks(n, c)
+        sizes = [b - a for a, b in ch]
+        assert ch[0][0] == 0 and ch[-1][1] == n and all(ch[i][1] == ch[i + 1][0] for i in range(len(ch) - 1))
+        assert max(sizes) <= c and max(sizes) - min(sizes) <= 1
+    assert bench.balanced_chunks(39000, 4096)[0] == (0, 3900)
+    J = bench.load_regressor("shipped")
+    assert tuple(J.shape) == (17, 6890) and int((J != 0).sum()) == 107
+    assert tuple(bench.load_regressor("dense").shape) == (17, 6890)

@@ -160,3 +160,23 @@ def test_independent_lbs_statement_agrees(oracle, osmpl64, model, jrr):
     verts, pj = I2.smpl_forward_one(model, betas[0].numpy(), R[0].numpy())
     assert np.abs(verts - out.vertices[0].numpy()).max() < 1e-12
     assert np.abs(I2.joints49_one(model, verts, pj) - out.joints[0].numpy()).max() < 1e-12
+
+
+def test_critic_kink_frames_flags_exactly_the_frames_near_a_relu_kink(oracle, critic_sd):
+    """The helper behind the gradient-parity tests: a frame whose layer-2 pre-activation is moved onto a ReLU kink is
+    flagged, its neighbours are not, and on random frames the flagged share stays ~1 %."""
+    g = torch.Generator().manual_seed(11)
+    x = 0.7 * torch.randn(400, 24, 6, generator=g)
+    base = oracle.critic_kink_frames(critic_sd, x)
+    assert base.float().mean().item() < 0.05
+    # shift the bias of unit 7 of the second wide layer so that frame 3's pre-activation there is 1e-8
+    sd = {k: v.clone().double() for k, v in critic_sd.items()}
+    xd = x.double()
+    h = torch.relu(torch.relu(xd @ sd["conv_operations.0.weight"].reshape(32, 6).t() + sd["conv_operations.0.bias"])
+                   @ sd["conv_operations.2.weight"].reshape(32, 32).t() + sd["conv_operations.2.bias"]).reshape(400, 768)
+    a1 = torch.relu(h @ sd["linear_operations.0.weight"].t() + sd["linear_operations.0.bias"])
+    a2 = a1 @ sd["linear_operations.2.weight"].t() + sd["linear_operations.2.bias"]
+    sd["linear_operations.2.bias"][7] -= a2[3, 7] - 1e-8
+    flagged = oracle.critic_kink_frames(sd, x)
+    assert bool(flagged[3])
+    assert int((flagged & ~base).sum()) <= 3      # moving one bias puts (almost) only frame 3 on a kink
