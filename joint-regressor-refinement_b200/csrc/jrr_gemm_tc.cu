@@ -610,6 +610,206 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------ CTA pairs (critic layers)
+// The two-row-block kernel above still reads 96 KB of weights from shared memory per K block next to 64 KB of TMA
+// writes and 32 KB of producer reads: 192 KB per 1536 MMA cycles = the whole 128 B/clk of the SM's shared memory, so the
+// tensor pipe waits on it (~59 % busy in steady state).  Here two CTAs of a cluster (the two SMs of a TPC) run ONE
+// tcgen05.mma.cta_group::2 of 256 rows x BN columns per K step: every CTA stages its own 128 activation rows in its own
+// tensor memory and holds only HALF of the weight panel (BN/2 rows) in shared memory -- the tensor cores of the pair
+// share the halves -- so per K block and SM the shared memory sees 48 KB of TMA writes + 48 KB of MMA reads + 16 KB of
+// producer reads = 112 KB per 1536 cycles, and L2 delivers 48 KB instead of 64 KB.
+//   rank 0 = leader (issues every MMA, owns the `ready` / `tempty` barriers both CTAs arrive on), rank 1 = peer.
+//   warps (both CTAs): 0 TMA (own A rows, own half of B_hi / B_lo -> own smem, own `full` barrier), 6-9 A producers
+//   (wait for the own `full`, split, tcgen05.st into the own staging ring, arrive on the LEADER's `ready`), 2-5 / 10-13
+//   epilogue of the own 128 rows (column halves), 1 = MMA lane (leader only).  Completion of the MMAs is multicast to the
+//   `empty` (smem stage + staging slot free) and `tfull` (accumulator complete) barriers of both CTAs.
+//   TMEM per CTA: accumulator 128 lanes x BN columns at column 0, staging ring {hi 32 | lo 32} x 4 slots at column 256.
+constexpr int PAIR_THREADS = 448;
+constexpr int PAIR_STAGES = 4;
+constexpr int PAIR_STORE_BYTES = 8 * 4096;
+template <int BN>
+struct PairCfg {
+  static constexpr int HB = BN / 2;                 // weight rows (output columns) held by one CTA
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int B_BYTES = HB * BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES = PAIR_STAGES * STAGE_BYTES + PAIR_STORE_BYTES + 1024 + 256;
+  static constexpr int RING_COL = 256;
+  static_assert(BN % 32 == 0 && BN <= 256 && B_BYTES % 1024 == 0, "pair tile width");
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+                 const __grid_constant__ CUtensorMap mapBl, const __grid_constant__ CUtensorMap mapO, const TcParams p) {
+  using Cfg = PairCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // (the dynamic shared memory window starts at the same offset in both CTAs, so the aligned layouts coincide)
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* store_smem = smem + PAIR_STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = (uint64_t*)(store_smem + PAIR_STORE_BYTES);
+  uint64_t* full_bar = bars;                          // [STAGES] own TMA -> own A producers
+  uint64_t* empty_bar = bars + PAIR_STAGES;           // [STAGES] MMA commit (multicast) -> own TMA lane
+  uint64_t* ready_bar = bars + 2 * PAIR_STAGES;       // [STAGES] A producers of both CTAs -> MMA lane (leader's copy)
+  uint64_t* tfull_bar = bars + 3 * PAIR_STAGES;       // [1] MMA commit (multicast) -> own epilogue
+  uint64_t* tempty_bar = tfull_bar + 1;               // [1] epilogue warps of both CTAs -> MMA lane (leader's copy)
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_kb = (int)(p.K / BK);
+  const int tiles_mn = p.m_tiles * p.n_tiles;         // m_tiles counts 256-row pair tiles
+  const int num_tiles = tiles_mn * p.ksplit;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapO) : "memory");
+    for (int s = 0; s < PAIR_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 8); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 16);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised and both allocations are done before anything remote
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (each CTA feeds its own shared memory) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int split = t / tiles_mn;
+        const int r = t % tiles_mn;
+        const int mb = r % p.m_tiles, nb = r / p.m_tiles;
+        int rowA = mb * 2 * BM + (int)rank * BM;
+        if (rowA >= (int)p.M) rowA -= BM;      // odd number of 128-row blocks: the peer re-reads the leader's (never stored)
+        const int rowB = nb * BN + (int)rank * Cfg::HB;
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int kc = (int)(split * p.K) + kb * BK;
+          tma_load_2d(&mapA, &full_bar[stage], sa, kc, rowA);
+          tma_load_2d(&mapBh, &full_bar[stage], sa + Cfg::A_BYTES, kc, rowB);
+          tma_load_2d(&mapBl, &full_bar[stage], sa + Cfg::A_BYTES + Cfg::B_BYTES, kc, rowB);
+          if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      // the last commits still arrive on this CTA's `empty` barriers: wait for them before the CTA may retire
+      for (int s = 0; s < PAIR_STAGES; s++) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one lane of the leader CTA) =====================
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)((2 * BM) >> 4) << 24);
+    if (rank == 0 && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool staged = false;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        mbar_wait(tempty_bar, acc_phase ^ 1);
+        for (int kb = 0; kb < num_kb; kb++) {
+          if (!staged) mbar_wait(&ready_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t dBh = make_sdesc(sa + Cfg::A_BYTES);
+          const uint64_t dBl = make_sdesc(sa + Cfg::A_BYTES + Cfg::B_BYTES);
+          const uint32_t ta = tmem_base + Cfg::RING_COL + stage * 64;     // hi at +0, lo at +32
+#pragma unroll
+          for (int k = 0; k < BK / 8; k++) {
+            const uint64_t ko = (uint64_t)(k * 32 >> 4);
+            tc_mma_tf32_ts_pair(tmem_base, ta + 32 + k * 8, dBh + ko, idesc, (kb | k) != 0);
+            tc_mma_tf32_ts_pair(tmem_base, ta + k * 8, dBl + ko, idesc, 1);
+            tc_mma_tf32_ts_pair(tmem_base, ta + k * 8, dBh + ko, idesc, 1);
+          }
+          tc_commit_pair(&empty_bar[stage]);
+          if (kb == num_kb - 1) tc_commit_pair(tfull_bar);
+          const int nstage = stage + 1 == PAIR_STAGES ? 0 : stage + 1;
+          const uint32_t nphase = stage + 1 == PAIR_STAGES ? phase ^ 1 : phase;
+          staged = mbar_try(&ready_bar[nstage], nphase);     // probed while the MMAs above are still queued
+          stage = nstage;
+          phase = nphase;
+        }
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 6 && warp < 10) {
+    // ===================== A producers: own smem fp32 rows -> tf32 hi/lo -> own TMEM staging ring =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::RING_COL;
+    const uint32_t ready_leader = map_to_cta(ready_bar, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      for (int kb = 0; kb < num_kb; kb++) {
+        // `full` of this stage follows the `empty` commit of the MMAs that read staging slot `stage` four K blocks ago
+        mbar_wait(&full_bar[stage], phase);
+        const uint8_t* arow = smem + stage * Cfg::STAGE_BYTES + row * 128;
+        float hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const float4 x = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+          split_tf32(x.x, hi[4 * c], lo[4 * c]);
+          split_tf32(x.y, hi[4 * c + 1], lo[4 * c + 1]);
+          split_tf32(x.z, hi[4 * c + 2], lo[4 * c + 2]);
+          split_tf32(x.w, hi[4 * c + 3], lo[4 * c + 3]);
+        }
+        tc_fence_after();
+        tc_st32(trow + stage * 64, hi);
+        tc_st32(trow + stage * 64 + 32, lo);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ready_leader + stage * 8);
+        if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue: warps 2-5 columns [0, BN/2), warps 10-13 columns [BN/2, BN) of the own rows ==========
+    const int q = warp & 3;
+    const int half = warp >= 10 ? 1 : 0;
+    float* my_stage = reinterpret_cast<float*>(store_smem + (half * 4 + q) * 4096);
+    const uint32_t tempty_leader = map_to_cta(tempty_bar, 0);
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int split = t / tiles_mn;
+      const int r = t % tiles_mn;
+      const int mb = r % p.m_tiles, nb = r / p.m_tiles;
+      mbar_wait(tfull_bar, acc_phase);
+      tc_fence_after();
+      const int64_t m = (int64_t)mb * 2 * BM + (int64_t)rank * BM + q * 32 + lane;   // rows past M fall out through the guards
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + half * Cfg::HB;
+      tc_epilogue_row<Cfg::HB, EPI, true>(p, trow, m, nb * 2 + half, split, my_stage, &mapO);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader);
+      acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's shared / tensor memory stays alive until the leader's last MMA has used it
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 // ------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -765,12 +965,71 @@ static int launch_ts2(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   return JRR_OK;
 }
 
+// CTA-pair kernel: grid = 2 x min(pair tiles, SM pairs); the static cluster dimension keeps a pair on one TPC
+template <int BN, int EPI>
+static int launch_pair(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
+  using Cfg = PairCfg<BN>;
+  CUtensorMap mA, mBh, mBl, mO;
+  const int64_t Ktot = g.K * g.ksplit;
+  if (int rc = make_tensor_map_2d(&mBh, g.B_hi, g.N, Ktot, g.ldb, Cfg::HB)) return rc;
+  if (int rc = make_tensor_map_2d(&mBl, g.B_lo, g.N, Ktot, g.ldb, Cfg::HB)) return rc;
+  const int64_t Ka = g.k_valid > 0 ? g.k_valid : Ktot;
+  if (int rc = make_tensor_map_2d(&mA, g.A_hi, g.M, Ka, g.lda, BM)) return rc;
+  if (int rc = make_tensor_map_2d(&mO, g.out0, g.M * g.ksplit, g.N, g.ldo, 32)) return rc;
+  TcParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K; p.ksplit = g.ksplit;
+  p.m_tiles = (int)((g.M + 2 * BM - 1) / (2 * BM));
+  p.n_tiles = (int)(g.N / BN);
+  p.out0 = g.out0; p.out1 = g.out1; p.ldo = g.ldo; p.bias = g.bias; p.mask = g.mask; p.ldmask = g.ldmask;
+  p.rowscale = g.rowscale; p.vec = g.vec; p.out2 = g.out2;
+  p.A = g.A_hi; p.lda = g.lda;
+  p.mask_bits = g.mask_bits; p.mask_bits_out = g.mask_bits_out;
+  p.logit_part = g.logit_part; p.n_logit_part = g.n_logit_part; p.logit_bias = g.logit_bias;
+  p.logit_gscale = g.logit_gscale; p.rows_valid = g.rows_valid;
+  auto kern = gemm_pair_kernel<BN, EPI>;
+  JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
+  int reps = 1;
+  if (g.probe_env) {
+    const char* e = getenv("JRR_GEMM_PROBE_REPS");
+    reps = e ? std::max(1, atoi(e)) : 1;
+  }
+  const int pairs = std::min(tiles, device_num_sms(m->device) / 2);
+  for (int r = 0; r < reps; r++) {
+    kern<<<2 * pairs, PAIR_THREADS, Cfg::SMEM_BYTES, st>>>(mA, mBh, mBl, mO, p);
+    JRR_LAUNCH_CHECK();
+  }
+  return JRR_OK;
+}
+
+template <int BN>
+static int launch_pair_epi(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
+  switch (g.epi) {
+    case EPI_BIAS_RELU_SPLIT: return launch_pair<BN, EPI_BIAS_RELU_SPLIT>(m, g, st);
+    case EPI_MASK_SPLIT: return launch_pair<BN, EPI_MASK_SPLIT>(m, g, st);
+    case EPI_BIAS_RELU_HEAD: return launch_pair<BN, EPI_BIAS_RELU_HEAD>(m, g, st);
+    case EPI_STORE_SPLITK: return launch_pair<BN, EPI_STORE_SPLITK>(m, g, st);
+    default: return fail(JRR_ERR_INVALID, "tc gemm (CTA pairs): unsupported epilogue");
+  }
+}
+
 }  // namespace jrr
 extern "C" int jrr_debug_set_gemm_prof(long long* base, int slots) {
   jrr::g_prof_base = base; jrr::g_prof_slots = slots; jrr::g_prof_next = 0;
   return JRR_OK;
 }
 namespace jrr {
+
+// JRR_GEMM_PAIR: 0 = never, 1 (default) = CTA pairs for the A-through-TMEM GEMMs with M >= 256 and N % 256 == 0
+// (N = 768 as 192-column pair tiles: 64 tiles of 0.75 units instead of 48 of 1), 2 = 256-column tiles for N = 768 too
+static int pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JRR_GEMM_PAIR");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
 
 static bool use_ts2() {
   static int v = -1;
@@ -787,6 +1046,10 @@ int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
     return fail(JRR_ERR_INVALID, "tc gemm: operands must be 16-byte aligned");
   if (g.a_via_tmem) {      // plain fp32 A (A_hi) through tensor memory, pre-split B
     if (g.N % 128 != 0 || g.lda % 4 != 0) return fail(JRR_ERR_INVALID, "tc gemm (A through TMEM): N % 128, lda % 4");
+    if (g.M >= 2 * BM && pair_mode() > 0 && !(g.probe_env && getenv("JRR_GEMM_PROBE_TS1"))) {
+      if (g.N == 768 && pair_mode() == 1) return launch_pair_epi<192>(m, g, st);
+      if (g.N % 256 == 0) return launch_pair_epi<256>(m, g, st);
+    }
     if (g.M >= 2 * BM && use_ts2() && !(g.probe_env && getenv("JRR_GEMM_PROBE_TS1"))) {
       // two 128-row blocks per CTA: half the weight traffic per MMA (see gemm_ts2_kernel)
       switch (g.epi) {
