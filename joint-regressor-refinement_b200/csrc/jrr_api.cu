@@ -340,10 +340,13 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
     // folded loss path: chain | Q = feat . T^T | per-frame joints + loss seed + dA + dQ | dfeat = dQ . T (split-K)
     // (events: pose_fwd | blend_gemm_fwd [the N = 1224 GEMM] | skin_fwd [empty] | loss_seed [folded seed] |
     //  skin_bwd [empty] | dA_reduce [empty] | blend_gemm_bwd [the K = 1280 GEMM])
-    if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, x6, JRR_POSE_ROT6D, w.AT, w.feat_hi, w.feat_lo, nullptr, st)) return rc;
+    // fold_ts: features and dQ stay plain fp32 (half the bytes) and both GEMMs run on CTA pairs, A through tensor memory
+    const bool fts = m->fold_ts && m->gemm_impl == 0 && w.BP >= 256;
+    if (int rc = launch_pose_fwd(m, w.B, w.BP, betas, x6, JRR_POSE_ROT6D, w.AT, w.feat_hi, fts ? nullptr : w.feat_lo, nullptr, st)) return rc;
     JRR_MARK();
     {
       GemmDesc g{};
+      g.a_via_tmem = fts;
       g.A_hi = w.feat_hi; g.A_lo = w.feat_lo; g.lda = KA;
       g.B_hi = m->T_hi; g.B_lo = m->T_lo; g.ldb = KA;
       g.M = w.BP; g.N = FOLD_NP; g.K = KA; g.ksplit = 1; g.epi = EPI_STORE_T;
@@ -352,7 +355,7 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
     }
     JRR_MARK();
     JRR_MARK();
-    if (int rc = launch_folded_seed(m, w, gt_mm, B_logical, w_joint, nullptr, p2d, st)) return rc;
+    if (int rc = launch_folded_seed(m, w, gt_mm, B_logical, w_joint, nullptr, p2d, st, nullptr, fts)) return rc;
     if (fork) JRR_CUDA(cudaEventRecord(m->ev_seed, st));
     JRR_MARK();
     JRR_MARK();
@@ -360,6 +363,7 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
     {
       w.ksplit = (w.BP / 128) * 4 >= m->num_sms ? 4 : 8;
       GemmDesc g{};
+      g.a_via_tmem = fts;
       g.A_hi = w.dvp_hi; g.A_lo = w.dvp_lo; g.lda = FOLD_NP;
       g.B_hi = m->Tt_hi; g.B_lo = m->Tt_lo; g.ldb = FOLD_NP;
       g.M = w.BP; g.N = KA; g.K = FOLD_NP / w.ksplit; g.ksplit = w.ksplit; g.epi = EPI_STORE_SPLITK;

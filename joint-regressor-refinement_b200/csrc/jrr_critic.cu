@@ -257,8 +257,8 @@ critic_post_kernel(const float* __restrict__ cs, const uint2* __restrict__ masks
   float dh1[32];
 #pragma unroll
   for (int k = 0; k < 32; k++) dh1[k] = 0.f;
-#pragma unroll 4
-  for (int c = 0; c < 32; c++) {
+#pragma unroll
+  for (int c = 0; c < 32; c++) {           // (fully unrolled: a partial unroll indexes d[] dynamically and spills it)
 #pragma unroll
     for (int k = 0; k < 32; k++) dh1[k] = fmaf(sw[CS_C2W + c * 32 + k], d[c], dh1[k]);
   }

@@ -85,10 +85,12 @@ __device__ __forceinline__ void tc_store_row32(float* out, int64_t ldo, int64_t 
   }
 }
 
-// One accumulator row (thread = row m = TMEM lane, BN columns starting at TMEM address `trow`) through the fused epilogue.
+// One accumulator row (thread = row m = TMEM lane, BN columns starting at TMEM address `trow`, output columns starting at
+// `n_base`) through the fused epilogue.
 template <int BN, int EPI, bool TS>
-__device__ __forceinline__ void tc_epilogue_row(const TcParams& p, const uint32_t trow, const int64_t m, const int nb,
+__device__ __forceinline__ void tc_epilogue_row(const TcParams& p, const uint32_t trow, const int64_t m, const int64_t n_base,
                                                 const int split, float* stage = nullptr, const CUtensorMap* mapO = nullptr) {
+  static_assert(BN % 32 == 0, "epilogue rows are processed 32 columns at a time");
   const int lane = threadIdx.x & 31;
   const int64_t row0 = m - lane;
   float zsum = 0.f;   // EPI_BIAS_RELU_HEAD: this row's share of the global head's logit
@@ -105,7 +107,7 @@ __device__ __forceinline__ void tc_epilogue_row(const TcParams& p, const uint32_
   for (int c = 0; c < BN / 32; c++) {
     float v[32];
     tc_ld32(trow + c * 32, v);
-    const int64_t n0 = (int64_t)nb * BN + c * 32;
+    const int64_t n0 = n_base + c * 32;
     if (EPI == EPI_BIAS_RELU_HEAD) {
       // x = relu(acc + b); logit partial sum x.w3; and the head's masked gradient row
       // (x > 0 ? w3 : 0) as a tf32 hi/lo pair -- the per-row scalar dL/dlogit is applied by the
@@ -170,7 +172,7 @@ __device__ __forceinline__ void tc_epilogue_row(const TcParams& p, const uint32_
         tc_store_row32(p.out0, p.ldo, (int64_t)split * p.M + m, n0, v, stage, mapO, (int64_t)split * p.M + row0, lane);
     }
   }
-  if (EPI == EPI_BIAS_RELU_HEAD && m < p.M) p.out2[(int64_t)nb * p.M + m] = zsum;
+  if (EPI == EPI_BIAS_RELU_HEAD && m < p.M) p.out2[(n_base / 128) * p.M + m] = zsum;   // one logit partial per 128 columns (callers use BN = 128 here)
 }
 
 // TS = false: both operands arrive pre-split through TMA (four tiles per stage) and are read from
@@ -342,7 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       tc_fence_after();
       const int64_t m = (int64_t)mb * BM + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
-      tc_epilogue_row<BN, EPI, TS>(p, trow, m, nb, split);
+      tc_epilogue_row<BN, EPI, TS>(p, trow, m, (int64_t)nb * BN, split);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -593,7 +595,7 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       // rows past M (the duplicated block of an odd last tile, or padding) fall out through the m < p.M guards
       const int64_t m = (int64_t)mb * 2 * BM + blk * BM + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + blk * Cfg::ACC_STRIDE;
-      tc_epilogue_row<BN, EPI, true>(p, trow, m, nb, split, my_stage, &mapO);
+      tc_epilogue_row<BN, EPI, true>(p, trow, m, (int64_t)nb * BN, split, my_stage, &mapO);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar);
@@ -635,6 +637,8 @@ struct PairCfg {
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
   static constexpr int SMEM_BYTES = PAIR_STAGES * STAGE_BYTES + PAIR_STORE_BYTES + 1024 + 256;
   static constexpr int RING_COL = 256;
+  static constexpr int E0 = ((HB + 31) / 32) * 32;  // accumulator columns drained by epilogue warps 2-5 ...
+  static constexpr int E1 = BN - E0;                // ... and by warps 10-13
   static_assert(BN % 32 == 0 && BN <= 256 && B_BYTES % 1024 == 0, "pair tile width");
 };
 
@@ -779,7 +783,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
     }
   } else if (warp >= 2) {
-    // ===================== epilogue: warps 2-5 columns [0, BN/2), warps 10-13 columns [BN/2, BN) of the own rows ==========
+    // ===================== epilogue: warps 2-5 columns [0, E0), warps 10-13 columns [E0, BN) of the own rows ==========
     const int q = warp & 3;
     const int half = warp >= 10 ? 1 : 0;
     float* my_stage = reinterpret_cast<float*>(store_smem + (half * 4 + q) * 4096);
@@ -792,8 +796,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_wait(tfull_bar, acc_phase);
       tc_fence_after();
       const int64_t m = (int64_t)mb * 2 * BM + (int64_t)rank * BM + q * 32 + lane;   // rows past M fall out through the guards
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + half * Cfg::HB;
-      tc_epilogue_row<Cfg::HB, EPI, true>(p, trow, m, nb * 2 + half, split, my_stage, &mapO);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + half * Cfg::E0;
+      if (half == 0) tc_epilogue_row<Cfg::E0, EPI, true>(p, trow, m, (int64_t)nb * BN, split, my_stage, &mapO);
+      else tc_epilogue_row<Cfg::E1, EPI, true>(p, trow, m, (int64_t)nb * BN + Cfg::E0, split, my_stage, &mapO);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader);
@@ -979,13 +984,15 @@ static int launch_pair(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.ksplit = g.ksplit;
   p.m_tiles = (int)((g.M + 2 * BM - 1) / (2 * BM));
-  p.n_tiles = (int)(g.N / BN);
+  p.n_tiles = (int)((g.N + BN - 1) / BN);      // a last partial tile: TMA zero-fills the missing weight rows, stores are clipped
   p.out0 = g.out0; p.out1 = g.out1; p.ldo = g.ldo; p.bias = g.bias; p.mask = g.mask; p.ldmask = g.ldmask;
   p.rowscale = g.rowscale; p.vec = g.vec; p.out2 = g.out2;
   p.A = g.A_hi; p.lda = g.lda;
   p.mask_bits = g.mask_bits; p.mask_bits_out = g.mask_bits_out;
   p.logit_part = g.logit_part; p.n_logit_part = g.n_logit_part; p.logit_bias = g.logit_bias;
   p.logit_gscale = g.logit_gscale; p.rows_valid = g.rows_valid;
+  if (EPI == EPI_BIAS_RELU_HEAD && (Cfg::E0 != 128 || Cfg::E1 != 128))
+    return fail(JRR_ERR_INVALID, "tc gemm (CTA pairs): the fused head needs 128-column epilogue parts");
   auto kern = gemm_pair_kernel<BN, EPI>;
   JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
@@ -1045,7 +1052,16 @@ int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   if (((uintptr_t)g.A_hi | (uintptr_t)(g.a_via_tmem ? nullptr : g.A_lo) | (uintptr_t)g.B_hi | (uintptr_t)g.B_lo) & 15)
     return fail(JRR_ERR_INVALID, "tc gemm: operands must be 16-byte aligned");
   if (g.a_via_tmem) {      // plain fp32 A (A_hi) through tensor memory, pre-split B
-    if (g.N % 128 != 0 || g.lda % 4 != 0) return fail(JRR_ERR_INVALID, "tc gemm (A through TMEM): N % 128, lda % 4");
+    if (g.lda % 4 != 0) return fail(JRR_ERR_INVALID, "tc gemm (A through TMEM): lda % 4");
+    // the two small GEMMs of the folded loss path (CTA pairs only)
+    if (g.epi == EPI_STORE_T && g.M >= 2 * BM) {
+      static const int bn = [] { const char* e = getenv("JRR_FOLD_BN"); return e ? atoi(e) : 256; }();
+      if (bn == 128) return launch_pair<128, EPI_STORE_T>(m, g, st);
+      if (bn == 192) return launch_pair<192, EPI_STORE_T>(m, g, st);
+      return launch_pair<256, EPI_STORE_T>(m, g, st);
+    }
+    if (g.epi == EPI_STORE_SPLITK && g.N == 224 && g.M >= 2 * BM) return launch_pair<224, EPI_STORE_SPLITK>(m, g, st);
+    if (g.N % 128 != 0) return fail(JRR_ERR_INVALID, "tc gemm (A through TMEM): N % 128");
     if (g.M >= 2 * BM && pair_mode() > 0 && !(g.probe_env && getenv("JRR_GEMM_PROBE_TS1"))) {
       if (g.N == 768 && pair_mode() == 1) return launch_pair_epi<192>(m, g, st);
       if (g.N % 256 == 0) return launch_pair_epi<256>(m, g, st);

@@ -188,6 +188,7 @@ struct JrrModel {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_seed = nullptr, ev_join2 = nullptr;
   bool overlap_critic = true;
   bool split_adam = true;                    // chain backward beside the critic branch, element-wise Adam after the join
+  bool fold_ts = true;                       // folded loss path of the refine step: plain fp32 features / dQ, CTA-pair GEMMs
   bool critic_ts = true;                     // critic GEMMs of the refine step: plain fp32 activations staged through tensor
                                              // memory (JRR_CRITIC_TS=0: pre-split activations through shared memory)
   bool critic_headless = true;               // no head kernel: dL/dlogit inside the backward GEMM, joint heads in critic_post
@@ -310,7 +311,8 @@ struct Proj2D {
   float scale = 0.f;             // w_2d * 2 / (34 * B_logical)
 };
 int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int64_t B_logical, float w_joint,
-                       float* joints17_out, const Proj2D& p2d, cudaStream_t st, float* dc_part = nullptr);
+                       float* joints17_out, const Proj2D& p2d, cudaStream_t st, float* dc_part = nullptr,
+                       bool plain_dq = false);
 // regressor refit through the folded operator (jrr_model.cu): G += unfold(dT, dc)
 int regressor_accumulate_folded(const JrrModel* m, Workspace& w, const float* gt_mm, int64_t B_logical, float* G_accum,
                                 cudaStream_t st);

@@ -708,6 +708,7 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   if (const char* e = getenv("JRR_COMPACT_ACTIVE")) m->compact_active = (e[0] != '0');
   if (const char* e = getenv("JRR_CRITIC_HEAD_FUSED")) m->critic_head_fused = (e[0] != '0');
   if (const char* e = getenv("JRR_CRITIC_TS")) m->critic_ts = (e[0] != '0');
+  if (const char* e = getenv("JRR_FOLD_TS")) m->fold_ts = (e[0] != '0');
   if (const char* e = getenv("JRR_SPLIT_ADAM")) m->split_adam = (e[0] != '0');
   if (const char* e = getenv("JRR_CRITIC_HEADLESS")) m->critic_headless = (e[0] != '0');
   if (const char* e = getenv("JRR_LOSS_PATH")) m->folded = (e[0] == 'f' || e[0] == '1') && m->gemm_impl == 0;

@@ -236,6 +236,7 @@ pose_fwd_kernel(const __grid_constant__ ChainTab tab, const float* __restrict__ 
   if (b < BP) {
     for (int i = lane; i < KA; i += 32) {
       float f = sF[warp][i];
+      if (feat_lo == nullptr) { feat_hi[b * KA + i] = f; continue; }     // plain fp32 (A-through-TMEM GEMM)
       float hi = tf32_hi(f);
       feat_hi[b * KA + i] = hi;
       feat_lo[b * KA + i] = tf32_hi(f - hi);

@@ -470,6 +470,11 @@ folded_seed_kernel(const float* __restrict__ QT, const float* __restrict__ AT, c
 #pragma unroll 4
     for (int p = 0; p < FS_POSES; p++) {
       const int64_t o = (b0 + p) * FOLD_NP + j * NACC;
+      if (dQ_lo == nullptr) {        // plain fp32 rows: the GEMM splits them on their way into tensor memory (uniform)
+        dQ_hi[o + lane] = sdq[p * FS_LD + lane];
+        if (lane < NACC - 32) dQ_hi[o + 32 + lane] = sdq[p * FS_LD + 32 + lane];
+        continue;
+      }
       {
         const float x = sdq[p * FS_LD + lane];
         const float hi = tf32_hi_k(x);
@@ -1135,7 +1140,7 @@ int launch_joints49_bwd(const JrrModel* m, const Workspace& w, const float* djoi
 
 // Folded loss path: joints (+ loss seed, dA, dQ when gt_mm is given) from Q = feat . T^T.
 int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int64_t B_logical, float w_joint,
-                       float* joints17_out, const Proj2D& p2d, cudaStream_t st, float* dc_part) {
+                       float* joints17_out, const Proj2D& p2d, cudaStream_t st, float* dc_part, bool plain_dq) {
   const float scale = gt_mm != nullptr ? w_joint * 2.f / (51.f * (float)B_logical) : 0.f;
   const bool grad = gt_mm != nullptr;
   w.n_joint_part = (int)(w.BP / FS_POSES);
@@ -1143,7 +1148,7 @@ int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int6
   JRR_CUDA(cudaFuncSetAttribute(folded_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   folded_seed_kernel<<<(unsigned)(w.BP / FS_POSES), FS_WARPS * 32, smem, st>>>(
       w.vpT, w.AT, m->Tc, gt_mm, w.B, w.BP, scale, p2d, w.loss_part, joints17_out, grad ? w.dAT : nullptr,
-      grad ? w.dvp_hi : nullptr, grad ? w.dvp_lo : nullptr, grad ? dc_part : nullptr);
+      grad ? w.dvp_hi : nullptr, (grad && !plain_dq) ? w.dvp_lo : nullptr, grad ? dc_part : nullptr);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
