@@ -318,6 +318,11 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   if (fork) {
     JRR_CUDA(cudaEventRecord(m->ev_fork, st));
     JRR_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+  }
+  static const int dbg_skip_c = [] { const char* e = getenv("JRR_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
+  if (fork && (dbg_skip_c & 2)) {
+    JRR_CUDA(cudaEventRecord(m->ev_join, m->side));
+  } else if (fork) {
     if (int rc = launch_critic_pre(m, w, x6, cs, hf)) return rc;
     if (int rc = critic_forward_gemms(m, w, cs, hf)) return rc;
     const bool hl = hf && m->critic_headless;      // no head kernel on the chain
@@ -336,7 +341,13 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   JRR_MARK();
   if (fork && m->split_adam)
     if (int rc = launch_adam_coef(w, step_count, lr, st)) return rc;
-  if (m->folded) {
+  // diagnostic only (benchmarks/step_breakdown.py): JRR_DEBUG_SKIP bit 0 = leave out the loss-path kernels of the main
+  // branch (results meaningless), bit 1 = leave out the critic chain -- what each branch costs the step when it runs alone
+  static const int dbg_skip = [] { const char* e = getenv("JRR_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
+  if (dbg_skip & 1) {
+    if (fork) JRR_CUDA(cudaEventRecord(m->ev_seed, st));
+    for (int i = 0; i < 7; i++) JRR_MARK();
+  } else if (m->folded) {
     // folded loss path: chain | Q = feat . T^T | per-frame joints + loss seed + dA + dQ | dfeat = dQ . T (split-K)
     // (events: pose_fwd | blend_gemm_fwd [the N = 1224 GEMM] | skin_fwd [empty] | loss_seed [folded seed] |
     //  skin_bwd [empty] | dA_reduce [empty] | blend_gemm_bwd [the K = 1280 GEMM])
@@ -361,7 +372,8 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
     JRR_MARK();
     JRR_MARK();
     {
-      w.ksplit = (w.BP / 128) * 4 >= m->num_sms ? 4 : 8;
+      // (CTA pairs: 256-row tiles, one wave of BP / 256 * 4 tiles up to 4736 frames)
+      w.ksplit = (fts || (w.BP / 128) * 4 >= m->num_sms) ? 4 : 8;
       GemmDesc g{};
       g.a_via_tmem = fts;
       g.A_hi = w.dvp_hi; g.A_lo = w.dvp_lo; g.lda = FOLD_NP;
@@ -418,7 +430,7 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   // With the critic on its own branch, the chain backward does not have to wait for it: it leaves the
   // parameter gradients in the workspace and an element-wise Adam kernel runs after the join.
   const bool split = fork && m->split_adam;
-  if (split)
+  if (split && !(dbg_skip & 1))
     if (int rc = launch_pose_bwd(m, w, betas, x6, JRR_POSE_ROT6D, false, false, false, w.gbetas, w.gx6, nullptr, nullptr,
                                  nullptr, nullptr, nullptr, 0.f, st)) return rc;
   // The loss read-out does not feed the update: with the fork it runs on the critic's stream (after the

@@ -627,7 +627,12 @@ gemm_ts2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 //   `empty` (smem stage + staging slot free) and `tfull` (accumulator complete) barriers of both CTAs.
 //   TMEM per CTA: accumulator 128 lanes x BN columns at column 0, staging ring {hi 32 | lo 32} x 4 slots at column 256.
 constexpr int PAIR_THREADS = 448;
-constexpr int PAIR_STAGES = 4;
+// Footprint: the pair kernel leaves room on its SMs for one CTA of the step's small kernels (pose chain, critic_pre / post:
+// 256 threads x <= 96 registers, <= 17 KB of shared memory), which are latency-bound and would otherwise queue for the 20 SMs
+// the 64 pairs of a 4096-frame GEMM do not use: 88 registers per thread (448 x 88 = 39 424 of 65 536; the epilogues spill
+// 4-12 bytes) and <= 194 KB of shared memory (three operand stages at 256 columns).
+constexpr int PAIR_MAXREG = 88;
+constexpr int PAIR_SMEM_BUDGET = 194 * 1024;
 constexpr int PAIR_STORE_BYTES = 8 * 4096;
 template <int BN>
 struct PairCfg {
@@ -635,7 +640,8 @@ struct PairCfg {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = HB * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
-  static constexpr int SMEM_BYTES = PAIR_STAGES * STAGE_BYTES + PAIR_STORE_BYTES + 1024 + 256;
+  static constexpr int STAGES = (4 * STAGE_BYTES + PAIR_STORE_BYTES + 1024 + 256 <= PAIR_SMEM_BUDGET) ? 4 : 3;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PAIR_STORE_BYTES + 1024 + 256;
   static constexpr int RING_COL = 256;
   static constexpr int E0 = ((HB + 31) / 32) * 32;  // accumulator columns drained by epilogue warps 2-5 ...
   static constexpr int E1 = BN - E0;                // ... and by warps 10-13
@@ -643,23 +649,25 @@ struct PairCfg {
 };
 
 template <int BN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(PAIR_MAXREG)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
                  const __grid_constant__ CUtensorMap mapBl, const __grid_constant__ CUtensorMap mapO, const TcParams p) {
   using Cfg = PairCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // (the dynamic shared memory window starts at the same offset in both CTAs, so the aligned layouts coincide)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* store_smem = smem + PAIR_STAGES * Cfg::STAGE_BYTES;
+  uint8_t* store_smem = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = (uint64_t*)(store_smem + PAIR_STORE_BYTES);
   uint64_t* full_bar = bars;                          // [STAGES] own TMA -> own A producers
-  uint64_t* empty_bar = bars + PAIR_STAGES;           // [STAGES] MMA commit (multicast) -> own TMA lane
-  uint64_t* ready_bar = bars + 2 * PAIR_STAGES;       // [STAGES] A producers of both CTAs -> MMA lane (leader's copy)
-  uint64_t* tfull_bar = bars + 3 * PAIR_STAGES;       // [1] MMA commit (multicast) -> own epilogue
+  uint64_t* empty_bar = bars + Cfg::STAGES;           // [STAGES] MMA commit (multicast) -> own TMA lane
+  uint64_t* ready_bar = bars + 2 * Cfg::STAGES;       // [STAGES] A producers of both CTAs -> MMA lane (leader's copy)
+  uint64_t* tfull_bar = bars + 3 * Cfg::STAGES;       // [1] MMA commit (multicast) -> own epilogue
   uint64_t* tempty_bar = tfull_bar + 1;               // [1] epilogue warps of both CTAs -> MMA lane (leader's copy)
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_entry = clock64();       // (role time stamps of the diagnostic path, p.prof != nullptr: cycles since entry)
+#define JRR_STAMP(slot) do { if (p.prof) p.prof[blockIdx.x * 16 + (slot)] = clock64() - t_entry; } while (0)
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int num_kb = (int)(p.K / BK);
@@ -671,7 +679,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapO) : "memory");
-    for (int s = 0; s < PAIR_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 8); }
+    for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 8); }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -685,6 +693,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   cluster_sync_all();          // both CTAs' barriers are initialised and both allocations are done before anything remote
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) JRR_STAMP(1);        // prologue done
 
   if (warp == 0) {
     // ===================== TMA producer (each CTA feeds its own shared memory) =====================
@@ -706,13 +715,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tma_load_2d(&mapA, &full_bar[stage], sa, kc, rowA);
           tma_load_2d(&mapBh, &full_bar[stage], sa + Cfg::A_BYTES, kc, rowB);
           tma_load_2d(&mapBl, &full_bar[stage], sa + Cfg::A_BYTES + Cfg::B_BYTES, kc, rowB);
-          if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+          if (t == pair && kb == 0) JRR_STAMP(2);      // first stage issued
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
       // the last commits still arrive on this CTA's `empty` barriers: wait for them before the CTA may retire
-      for (int s = 0; s < PAIR_STAGES; s++) {
+      for (int s = 0; s < Cfg::STAGES; s++) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -728,6 +738,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         for (int kb = 0; kb < num_kb; kb++) {
           if (!staged) mbar_wait(&ready_bar[stage], phase);
           tc_fence_after();
+          if (t == pair && kb == 0) JRR_STAMP(4);      // first K block staged in both CTAs
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t dBh = make_sdesc(sa + Cfg::A_BYTES);
           const uint64_t dBl = make_sdesc(sa + Cfg::A_BYTES + Cfg::B_BYTES);
@@ -740,9 +751,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             tc_mma_tf32_ts_pair(tmem_base, ta + k * 8, dBh + ko, idesc, 1);
           }
           tc_commit_pair(&empty_bar[stage]);
-          if (kb == num_kb - 1) tc_commit_pair(tfull_bar);
-          const int nstage = stage + 1 == PAIR_STAGES ? 0 : stage + 1;
-          const uint32_t nphase = stage + 1 == PAIR_STAGES ? phase ^ 1 : phase;
+          if (kb == num_kb - 1) { tc_commit_pair(tfull_bar); if (t == pair) JRR_STAMP(5); }   // all MMAs of the first tile issued
+          const int nstage = stage + 1 == Cfg::STAGES ? 0 : stage + 1;
+          const uint32_t nphase = stage + 1 == Cfg::STAGES ? phase ^ 1 : phase;
           staged = mbar_try(&ready_bar[nstage], nphase);     // probed while the MMAs above are still queued
           stage = nstage;
           phase = nphase;
@@ -762,6 +773,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       for (int kb = 0; kb < num_kb; kb++) {
         // `full` of this stage follows the `empty` commit of the MMAs that read staging slot `stage` four K blocks ago
         mbar_wait(&full_bar[stage], phase);
+        if (t == pair && kb == 0 && warp == 6 && lane == 0) JRR_STAMP(3);    // first operands landed
         const uint8_t* arow = smem + stage * Cfg::STAGE_BYTES + row * 128;
         float hi[32], lo[32];
 #pragma unroll
@@ -779,7 +791,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(ready_leader + stage * 8);
-        if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 2) {
@@ -795,6 +807,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int mb = r % p.m_tiles, nb = r / p.m_tiles;
       mbar_wait(tfull_bar, acc_phase);
       tc_fence_after();
+      if (t == pair && warp == 2 && lane == 0) JRR_STAMP(6);                 // accumulator complete
       const int64_t m = (int64_t)mb * 2 * BM + (int64_t)rank * BM + q * 32 + lane;   // rows past M fall out through the guards
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + half * Cfg::E0;
       if (half == 0) tc_epilogue_row<Cfg::E0, EPI, true>(p, trow, m, (int64_t)nb * BN, split, my_stage, &mapO);
@@ -802,9 +815,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader);
+      if (t == pair && warp == 2 && lane == 0) JRR_STAMP(7);                 // epilogue of the first tile issued
       acc_phase ^= 1;
     }
     if (lane == 0) tma_store_wait_all();
+    if (warp == 2 && lane == 0) JRR_STAMP(8);                                // stores landed
   }
 
   tc_fence_before();
@@ -813,6 +828,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
+  if (threadIdx.x == 32) JRR_STAMP(9);       // teardown done
+#undef JRR_STAMP
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -1000,6 +1017,10 @@ static int launch_pair(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   if (g.probe_env) {
     const char* e = getenv("JRR_GEMM_PROBE_REPS");
     reps = e ? std::max(1, atoi(e)) : 1;
+  }
+  if (g_prof_base != nullptr && g_prof_slots > 0) {      // diagnostic (benchmarks/gemm_prof.py): 16 stamps per CTA and launch
+    p.prof = g_prof_base + (int64_t)(g_prof_next % g_prof_slots) * 148 * 16;
+    g_prof_next++;
   }
   const int pairs = std::min(tiles, device_num_sms(m->device) / 2);
   for (int r = 0; r < reps; r++) {

@@ -356,6 +356,46 @@ int launch_critic_head(const JrrModel* m, Workspace& w, int64_t B_logical, float
 int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, bool head_fused = false);
 int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st, const float* rowscale = nullptr,
                           float headless_gscale = 0.f);
+// the loss read-out {total, joint, pose, 2d, shape} from the per-CTA partials (loss_finish_kernel)
+struct LossFinishArgs {
+  const float* lp_joint; int n_joint; float sj;
+  const float* lp_pose; int n_pose; float sp;
+  const float* lp_2d; float s2;
+  const float* lp_shape; int n_shape; float ss;
+  float wj, wp, w2, wsh;
+  float* loss_out; float* loss_accum;
+};
+// one warp; lane-strided partial sums + xor-shuffle tree: a fixed summation order
+__device__ __forceinline__ void loss_finish_warp(const LossFinishArgs& a, const int lane) {
+  float sa = 0.f, p = 0.f, q = 0.f, r = 0.f;
+  for (int i = lane; i < a.n_joint; i += 32) sa += __ldcg(a.lp_joint + i);
+  if (a.wsh != 0.f)
+    for (int i = lane; i < a.n_shape; i += 32) r += __ldcg(a.lp_shape + i);
+  for (int i = lane; i < a.n_pose; i += 32) p += __ldcg(a.lp_pose + i);
+  if (a.w2 != 0.f)
+    for (int i = lane; i < a.n_joint; i += 32) q += __ldcg(a.lp_2d + i);
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    p += __shfl_xor_sync(0xffffffffu, p, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+    r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  if (lane != 0) return;
+  sa *= a.sj;
+  p *= a.sp;
+  q *= a.s2;
+  r *= a.ss;
+  if (a.loss_out != nullptr) {
+    a.loss_out[0] = a.wj * sa + a.wp * p + a.w2 * q + a.wsh * r;
+    a.loss_out[1] = sa;
+    a.loss_out[2] = p;
+    a.loss_out[3] = q;
+    a.loss_out[4] = r;
+  }
+  if (a.loss_accum != nullptr) a.loss_accum[0] += sa;
+}
+LossFinishArgs make_loss_finish_args(const Workspace& w, int64_t B_logical, float w_joint, float w_pose, bool have_pose,
+                                     float w_2d, float w_shape, float* loss_out, float* loss_accum);
 int launch_critic_head_light(const JrrModel* m, Workspace& w, int64_t B_logical, float w_pose, cudaStream_t st);
 int launch_critic_post(const JrrModel* m, Workspace& w, const float* x6, cudaStream_t st, bool with_head = false,
                        int64_t B_logical = 1, float w_pose = 0.f);

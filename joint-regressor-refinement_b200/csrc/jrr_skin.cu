@@ -386,6 +386,7 @@ folded_seed_kernel(const float* __restrict__ QT, const float* __restrict__ AT, c
     for (int a = 0; a < NACC; a++) sbuf[(warp * NACC + a) * FS_POSES + lane] = pred[a];
   }
   __syncthreads();
+  // joints (fixed-order sum of the eight partial sets), spread over the warps: warp w owns components a = w, w + 8, ...
   for (int a = warp; a < NACC; a += FS_WARPS) {
     float t = sbuf[a * FS_POSES + lane];
 #pragma unroll
@@ -393,29 +394,61 @@ folded_seed_kernel(const float* __restrict__ QT, const float* __restrict__ AT, c
     sg[a * FS_POSES + lane] = t;
   }
   __syncthreads();
-  if (warp == 0) {
-    float pred[NACC];
-#pragma unroll
-    for (int a = 0; a < NACC; a++) pred[a] = sg[a * FS_POSES + lane];
-    if (b < B && joints17_out != nullptr) {
-#pragma unroll
-      for (int a = 0; a < NACC; a++) joints17_out[b * NACC + a] = pred[a];
+  if (joints17_out != nullptr) {       // [32 poses][51] is one contiguous block of the output: coalesced
+    for (int e = tid; e < FS_POSES * NACC; e += FS_WARPS * 32) {
+      const int p = e / NACC, a = e - p * NACC;
+      if (b0 + p < B) joints17_out[b0 * NACC + e] = sg[a * FS_POSES + p];
     }
-    if (dAT != nullptr) {
-      float g[NACC];
-      float loss = 0.f, loss2 = 0.f;
-      float sum[3] = {0.f, 0.f, 0.f};
+  }
+  if (dAT != nullptr) {
+    // Loss seed on all warps (it was one warp's serial section -- 51 strided loads, 51 divisions -- with the other seven
+    // parked at the barrier: 44 % of the kernel's warp time).  Thread (w, pose) handles a = w, w + 8, ...; the ground
+    // truth block [32][51] is contiguous and comes in through shared memory; pelvis sums and the loss meet in shared memory
+    // in a fixed order.
+    float* sgt = sbuf;                                      // [32][51] (the partial joints are consumed)
+    float* ssum = sbuf + FS_POSES * NACC;                   // [8 warps][3][32]
+    float* sred = ssum + FS_WARPS * 3 * FS_POSES;           // [8] loss
+    float* spred = sred + 32;                               // [51][32] the joints, kept for the 2-D term
+    for (int e = tid; e < FS_POSES * NACC; e += FS_WARPS * 32)
+      sgt[e] = (b0 + e / NACC < B) ? gt_mm[b0 * NACC + e] : 0.f;
+    __syncthreads();
+    float loss = 0.f;
+    float sum[3] = {0.f, 0.f, 0.f};
+    float dloc[(NACC + FS_WARPS - 1) / FS_WARPS];
 #pragma unroll
-      for (int a = 0; a < NACC; a++) {
-        float d = 0.f;
-        if (b < B) d = (pred[a] - pred[a % 3]) - gt_mm[b * NACC + a] / 1000.f;
-        loss += d * d;
-        g[a] = scale * d;
-        sum[a % 3] += g[a];
-      }
+    for (int k = 0; k < (NACC + FS_WARPS - 1) / FS_WARPS; k++) {
+      const int a = warp + k * FS_WARPS;
+      float d = 0.f;
+      if (a < NACC && b < B) d = (sg[a * FS_POSES + lane] - sg[(a % 3) * FS_POSES + lane]) - sgt[lane * NACC + a] / 1000.f;
+      if (a < NACC && p2d.gt2d != nullptr) spred[a * FS_POSES + lane] = sg[a * FS_POSES + lane];
+      loss += d * d;
+      dloc[k] = scale * d;
+      if (a < NACC) sum[a % 3] += dloc[k];
+    }
+    __syncthreads();                                         // every warp has read the joints it needs from sg
 #pragma unroll
-      for (int c = 0; c < 3; c++) g[c] -= sum[c];
-      if (p2d.gt2d != nullptr) {
+    for (int k = 0; k < (NACC + FS_WARPS - 1) / FS_WARPS; k++) {
+      const int a = warp + k * FS_WARPS;
+      if (a < NACC) sg[a * FS_POSES + lane] = dloc[k];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) ssum[(warp * 3 + c) * FS_POSES + lane] = sum[c];
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if (lane == 0) sred[warp] = loss;
+    __syncthreads();
+    if (warp < 3) {                                          // pelvis adjustment g[c] -= sum over all components of g[. % 3 == c]
+      float t = ssum[warp * FS_POSES + lane];
+#pragma unroll
+      for (int w2 = 1; w2 < FS_WARPS; w2++) t += ssum[(w2 * 3 + warp) * FS_POSES + lane];
+      sg[warp * FS_POSES + lane] -= t;
+    }
+    float loss2 = 0.f;
+    if (p2d.gt2d != nullptr) {                               // 2-D reprojection term + camera Adam: one warp, whole poses
+      __syncthreads();
+      if (warp == 0) {
+        float pred[NACC], g[NACC];
+#pragma unroll
+        for (int a = 0; a < NACC; a++) { pred[a] = spred[a * FS_POSES + lane]; g[a] = sg[a * FS_POSES + lane]; }
         if (b < B) {
           float Tcam[3], dT[3] = {0.f, 0.f, 0.f}, m3[3], v3[3];
 #pragma unroll
@@ -425,14 +458,17 @@ folded_seed_kernel(const float* __restrict__ QT, const float* __restrict__ AT, c
 #pragma unroll
           for (int c = 0; c < 3; c++) { p2d.cam[b * 3 + c] = Tcam[c]; p2d.cam_m[b * 3 + c] = m3[c]; p2d.cam_v[b * 3 + c] = v3[c]; }
         }
-      }
-      for (int o = 16; o > 0; o >>= 1) {
-        loss += __shfl_xor_sync(0xffffffffu, loss, o);
-        loss2 += __shfl_xor_sync(0xffffffffu, loss2, o);
-      }
-      if (lane == 0) { loss_part[blockIdx.x] = loss; loss_part[LOSS_PART_2D + blockIdx.x] = loss2; }
+        for (int o = 16; o > 0; o >>= 1) loss2 += __shfl_xor_sync(0xffffffffu, loss2, o);
 #pragma unroll
-      for (int a = 0; a < NACC; a++) sg[a * FS_POSES + lane] = g[a];
+        for (int a = 0; a < NACC; a++) sg[a * FS_POSES + lane] = g[a];
+      }
+    }
+    if (tid == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < FS_WARPS; w2++) t += sred[w2];
+      loss_part[blockIdx.x] = t;
+      loss_part[LOSS_PART_2D + blockIdx.x] = loss2;
     }
   }
   if (dAT == nullptr) return;      // joints only (uniform)
@@ -964,40 +1000,7 @@ __global__ void joints49_bwd_kernel(const int* __restrict__ joint_map, const flo
 }
 
 // ---------------------------------------------------------------------------- loss finish
-__global__ void loss_finish_kernel(const float* __restrict__ lp_joint, int n_joint, float sj,
-                                   const float* __restrict__ lp_pose, int n_pose, float sp,
-                                   const float* __restrict__ lp_2d, float s2, const float* __restrict__ lp_shape,
-                                   int n_shape, float ss, float wj, float wp, float w2, float wsh,
-                                   float* __restrict__ loss_out, float* __restrict__ loss_accum) {
-  // one warp; lane-strided partial sums + xor-shuffle tree: a fixed summation order
-  const int lane = threadIdx.x;
-  float a = 0.f, p = 0.f, q = 0.f, r = 0.f;
-  for (int i = lane; i < n_joint; i += 32) a += lp_joint[i];
-  if (wsh != 0.f)
-    for (int i = lane; i < n_shape; i += 32) r += lp_shape[i];
-  for (int i = lane; i < n_pose; i += 32) p += lp_pose[i];
-  if (w2 != 0.f)
-    for (int i = lane; i < n_joint; i += 32) q += lp_2d[i];
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    p += __shfl_xor_sync(0xffffffffu, p, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
-    r += __shfl_xor_sync(0xffffffffu, r, o);
-  }
-  if (lane != 0) return;
-  a *= sj;
-  p *= sp;
-  q *= s2;
-  r *= ss;
-  if (loss_out != nullptr) {
-    loss_out[0] = wj * a + wp * p + w2 * q + wsh * r;
-    loss_out[1] = a;
-    loss_out[2] = p;
-    loss_out[3] = q;
-    loss_out[4] = r;
-  }
-  if (loss_accum != nullptr) loss_accum[0] += a;
-}
+__global__ void loss_finish_kernel(const LossFinishArgs a) { loss_finish_warp(a, threadIdx.x); }
 
 // ---------------------------------------------------------------------------- camera fit
 // optimize.py:187-199: Adam(lr) on the camera translation alone against the 2-D joints.  The 3-D
@@ -1153,15 +1156,22 @@ int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int6
   return JRR_OK;
 }
 
+LossFinishArgs make_loss_finish_args(const Workspace& w, int64_t B_logical, float w_joint, float w_pose, bool have_pose,
+                                     float w_2d, float w_shape, float* loss_out, float* loss_accum) {
+  LossFinishArgs a{};
+  a.lp_joint = w.loss_part; a.n_joint = w.n_joint_part; a.sj = 1.f / (51.f * (float)B_logical);
+  a.lp_pose = w.loss_part + LOSS_PART_POSE; a.n_pose = have_pose ? w.n_pose_part : 0; a.sp = 1.f / (25.f * (float)B_logical);
+  a.lp_2d = w.loss_part + LOSS_PART_2D; a.s2 = 1.f / (34.f * (float)B_logical);
+  a.lp_shape = w.shape_part; a.n_shape = (int)(w.BP / 128); a.ss = 1.f / (float)B_logical;
+  a.wj = w_joint; a.wp = w_pose; a.w2 = w_2d; a.wsh = w_shape;
+  a.loss_out = loss_out; a.loss_accum = loss_accum;
+  return a;
+}
+
 int launch_loss_finish(const Workspace& w, int64_t B_logical, float w_joint, float w_pose,
                        bool have_pose, float w_2d, float w_shape, float* loss_out, float* loss_accum, cudaStream_t st) {
-  const int nj = w.n_joint_part;
-  const int np = have_pose ? w.n_pose_part : 0;
-  loss_finish_kernel<<<1, 32, 0, st>>>(w.loss_part, nj, 1.f / (51.f * (float)B_logical),
-                                       w.loss_part + LOSS_PART_POSE, np, 1.f / (25.f * (float)B_logical),
-                                       w.loss_part + LOSS_PART_2D, 1.f / (34.f * (float)B_logical),
-                                       w.shape_part, (int)(w.BP / 128), 1.f / (float)B_logical,
-                                       w_joint, w_pose, w_2d, w_shape, loss_out, loss_accum);
+  loss_finish_kernel<<<1, 32, 0, st>>>(make_loss_finish_args(w, B_logical, w_joint, w_pose, have_pose, w_2d, w_shape,
+                                                            loss_out, loss_accum));
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
