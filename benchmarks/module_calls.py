@@ -1,0 +1,24 @@
+#!/usr/bin/env python
+"""Workload for an ncu launch list of the drop-in module path: SMPL forward and backward at B = 1, 256, 4096."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import jrr_b200 as jrr  # noqa: E402
+
+dev = torch.device("cuda", 0)
+smpl = jrr.SMPL(model_dict=jrr.synthetic.make_smpl_model(0), create_transl=False).to(dev)
+nat = smpl.native()
+base = jrr.synthetic.make_pose_inputs(4096, 7)
+for B in (4096, 256, 1):
+    full = torch.from_numpy(base["true_rotmat"])[:B].reshape(B, 24, 9).to(dev).contiguous()
+    b = torch.from_numpy(base["true_betas"])[:B].to(dev).contiguous()
+    dv = torch.randn(B, 6890, 3, device=dev)
+    dj = torch.randn(B, 49, 3, device=dev)
+    for _ in range(2):
+        nat.smpl_forward(b, full, 0, True, True)
+        nat.smpl_backward(b, full, 0, dv, dj)
+    torch.cuda.synchronize()
+    print("B", B, "done", flush=True)

@@ -299,6 +299,8 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   if (!m->has_regressor) return fail(JRR_ERR_STATE, "jrr_set_regressor has not been called");
   if (m->folded && !m->T_hi) return fail(JRR_ERR_STATE, "folded loss path selected before a regressor was set");
   if (!x6 || !betas || !gt_mm || !adam_m || !adam_v || !step_count) return fail(JRR_ERR_INVALID, "null argument");
+  if (((uintptr_t)x6 | (uintptr_t)betas | (uintptr_t)adam_m | (uintptr_t)adam_v) & 7)
+    return fail(JRR_ERR_INVALID, "x6 / betas / adam_m / adam_v must be 8-byte aligned");
   if (B_logical < B) return fail(JRR_ERR_INVALID, "B_logical must be >= B");
   const bool critic = w_pose != 0.f;
   if (critic && !m->has_critic) return fail(JRR_ERR_STATE, "w_pose != 0 but jrr_critic_load has not been called");

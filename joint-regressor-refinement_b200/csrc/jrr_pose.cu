@@ -410,29 +410,49 @@ __global__ void bump_step_kernel(int32_t* step_count) { *step_count += 1; }
 __global__ void __launch_bounds__(256)
 adam_params_kernel(const float* __restrict__ gx6, const float* __restrict__ gbetas, const float* __restrict__ dx6c,
                    const float* __restrict__ dbeta_s, int64_t B, float* __restrict__ x6, float* __restrict__ betas,
-                   float* __restrict__ adam_m, float* __restrict__ adam_v, const float* __restrict__ coef) {
+                   float* __restrict__ adam_m, float* __restrict__ adam_v, const float* __restrict__ coef,
+                   int32_t* __restrict__ step_count) {
+  // thread = two consecutive parameters of one pose (NPARAM and 144 are even: a pair never straddles rot6d / betas or
+  // two poses, and every array is 8-byte aligned at it): half the threads, twice the bytes in flight per thread
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * NPARAM) return;
-  const int64_t b = idx / NPARAM;
-  const int p = (int)(idx - b * NPARAM);
-  float g;
-  float* prm;
+  // the step counter advances here (nothing in this kernel reads it: the bias corrections of this step are in `coef`), not
+  // in a one-thread kernel of its own at the very end of the step
+  if (idx == 0) step_count[0] += 1;
+  constexpr int HP = NPARAM / 2;
+  if (idx >= B * HP) return;
+  const int64_t b = idx / HP;
+  const int p = 2 * (int)(idx - b * HP);
+  float2 g;
+  float2* prm;
   if (p < 144) {
-    g = gx6[b * 144 + p] + (dx6c != nullptr ? dx6c[b * 144 + p] : 0.f);
-    prm = x6 + b * 144 + p;
+    g = *reinterpret_cast<const float2*>(gx6 + b * 144 + p);
+    if (dx6c != nullptr) {
+      const float2 c = *reinterpret_cast<const float2*>(dx6c + b * 144 + p);
+      g.x += c.x; g.y += c.y;
+    }
+    prm = reinterpret_cast<float2*>(x6 + b * 144 + p);
   } else {
-    g = gbetas[b * NB + (p - 144)];
-    if (dbeta_s != nullptr) g += dbeta_s[b * NB + (p - 144)];
-    prm = betas + b * NB + (p - 144);
+    g = *reinterpret_cast<const float2*>(gbetas + b * NB + (p - 144));
+    if (dbeta_s != nullptr) {
+      const float2 c = *reinterpret_cast<const float2*>(dbeta_s + b * NB + (p - 144));
+      g.x += c.x; g.y += c.y;
+    }
+    prm = reinterpret_cast<float2*>(betas + b * NB + (p - 144));
   }
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
   const float bc2s = coef[0], step = coef[1];      // adam_coef_kernel
-  const float m = b1 * adam_m[idx] + (1.f - b1) * g;
-  const float v = b2 * adam_v[idx] + (1.f - b2) * g * g;
-  adam_m[idx] = m;
-  adam_v[idx] = v;
-  const float denom = sqrtf(v) / bc2s + eps;
-  *prm = *prm - step * (m / denom);
+  float2* pm = reinterpret_cast<float2*>(adam_m + b * NPARAM + p);
+  float2* pv = reinterpret_cast<float2*>(adam_v + b * NPARAM + p);
+  float2 m = *pm, v = *pv, x = *prm;
+  m.x = b1 * m.x + (1.f - b1) * g.x;
+  m.y = b1 * m.y + (1.f - b1) * g.y;
+  v.x = b2 * v.x + (1.f - b2) * g.x * g.x;
+  v.y = b2 * v.y + (1.f - b2) * g.y * g.y;
+  *pm = m;
+  *pv = v;
+  x.x = x.x - step * (m.x / (sqrtf(v.x) / bc2s + eps));
+  x.y = x.y - step * (m.y / (sqrtf(v.y) / bc2s + eps));
+  *prm = x;
 }
 
 // Bias corrections of this step in double, like torch.optim.Adam's Python scalars (a double-precision pow is a
@@ -452,13 +472,11 @@ int launch_adam_coef(const Workspace& w, const int32_t* step_count, float lr, cu
 // ---- host wrappers ---------------------------------------------------------------------------
 int launch_adam_params(const Workspace& w, bool use_critic, bool use_shape, float* x6, float* betas, float* adam_m,
                        float* adam_v, int32_t* step_count, float lr, cudaStream_t st) {
-  const int64_t n = w.B * NPARAM;
+  const int64_t n = w.B * (NPARAM / 2);
   adam_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.gx6, w.gbetas, use_critic ? w.dx6c : nullptr,
                                                                  use_shape ? w.dbeta_s : nullptr, w.B, x6, betas, adam_m,
-                                                                 adam_v, w.adam_coef);
+                                                                 adam_v, w.adam_coef, step_count);
   (void)lr;
-  JRR_LAUNCH_CHECK();
-  bump_step_kernel<<<1, 1, 0, st>>>(step_count);
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }
