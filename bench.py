@@ -680,7 +680,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu": B, "regressor": args.regressor, "loss_path": args.loss_path,
                        "parallelism": f"frame-shard x{world}, no data-path collective in `value` (the refit all-reduce is in e2e and secondary.c3_strong)",
-                       "l2": "per-step working set ~1.2 GB of intermediates per GPU, larger than the 126 MB L2",
+                       "l2": ("one folded step touches ~190 MB per GPU (activations 120 MB, split weights 33 MB, Q / dQ 42 MB)"
+                              if folded else "one per-vertex step touches ~1.2 GB of intermediates per GPU") + ": larger than the 126 MB L2",
                        "graph": f"PoseRefiner.refine: CUDA graph of {U} step(s) replayed (value); one-step graph with the loss copied back per step (e2e)",
                        "gemm": "tcgen05 3xTF32" if args.gemm_impl == 0 else "simt"},
             "clocks": clocks,

@@ -1,24 +1,27 @@
 # Regenerates everything under profiles/ on a B200 (run through gpurun from the repo root):
-#   gpurun --timeout 1800 -- "bash benchmarks/gpu_validate.sh"   then copy gpurun_out/r1_* to profiles/
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -4 | tee gpurun_out/r1_gpu_tests_tail.txt
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 -s 2>&1 | grep -E "^\[|MPJPE|refit|gradient rel|tcgen05 3xTF32|passed|failed" > gpurun_out/r1_gpu_tests.txt
-python bench.py > gpurun_out/r1_bench.json 2> gpurun_out/r1_bench.err; tail -2 gpurun_out/r1_bench.err
-python bench.py --loss-path vertex --no-cpu-baseline > gpurun_out/r1_bench_vertex.json 2>> gpurun_out/r1_bench.err
-python bench.py --regressor shipped --no-cpu-baseline > gpurun_out/r1_bench_shipped.json 2>> gpurun_out/r1_bench.err
-python bench.py --impl reference --steps 20 --warmup 2 > gpurun_out/r1_bench_reference.json 2>> gpurun_out/r1_bench.err
-python - <<'PY'
-import json
-for f in ("r1_bench","r1_bench_vertex","r1_bench_shipped"):
-    d=json.load(open(f"gpurun_out/{f}.json"))
-    print(f, d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'], d['roofline'])
+#   gpurun --timeout 2400 -- "bash benchmarks/gpu_validate.sh r2"   then   python profiles/summarize.py r2
+T=${1:-r2}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 -s 2>&1 | grep -E "^\[|MPJPE|refit|gradient rel|tcgen05 3xTF32|passed|failed|rel err|max \|" > gpurun_out/${T}_gpu_tests.txt; tail -1 gpurun_out/${T}_gpu_tests.txt
+python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; tail -2 gpurun_out/${T}_bench.err
+python bench.py --loss-path vertex --no-cpu-baseline --no-secondary > gpurun_out/${T}_bench_vertex.json 2>> gpurun_out/${T}_bench.err
+python bench.py --regressor shipped --no-cpu-baseline --no-secondary > gpurun_out/${T}_bench_shipped.json 2>> gpurun_out/${T}_bench.err
+python bench.py --impl reference --steps 20 --warmup 2 > gpurun_out/${T}_bench_reference.json 2>> gpurun_out/${T}_bench.err
+python - $T <<'PY'
+import json,sys
+T=sys.argv[1]
+for f in ("bench","bench_vertex","bench_shipped"):
+    d=json.loads(open(f"gpurun_out/{T}_{f}.json").read().strip().splitlines()[-1])
+    print(f, round(d['value']), d['ms_per_step'], round(d['e2e']['value']), d['gpu_launches'], d['roofline'].get('kernel'), d['roofline'].get('frac'), d['whole_step'].get('tensor_frac_3xtf32'))
     print([(k['name'][:14],k['ms'],k.get('frac')) for k in d['kernels']])
-    print(d['quality'], d['refit_ms'], d['clocks'], d.get('cpu_baseline'))
-print(open("gpurun_out/r1_bench_reference.json").read()[:300])
+print(open(f"gpurun_out/{T}_bench_reference.json").read()[:300])
 PY
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r1_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'folded_seed|gemm_tc_kernel' -s 42 -c 14 -o gpurun_out/r1_prof python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'fused_bwd|fused_fwd' -s 30 -c 4 -o gpurun_out/r1_prof_vertex python bench.py --loss-path vertex --steps 3 --warmup 3 --no-cpu-baseline >> gpurun_out/ncu_full.log 2>&1
-ls -la gpurun_out | head -30
-timeout 1500 python benchmarks/sweep.py > gpurun_out/r1_sweep.jsonl 2> gpurun_out/r1_sweep.err; tail -2 gpurun_out/r1_sweep.err
-compute-sanitizer --tool memcheck --print-limit 20 python benchmarks/sanitize.py 2>&1 | grep -E "COMPUTE-SANITIZER|ERROR SUMMARY|Invalid|sanitizer workload|at 0x|Error" | head -40 > gpurun_out/r1_memcheck.txt; tail -2 gpurun_out/r1_memcheck.txt
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29517 benchmarks/multi_gpu_check.py > /dev/null 2>&1 || echo "multi_gpu_check (1 rank) FAILED"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/ncu_bench.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'gemm_pair|folded_seed|critic_pre|critic_post|pose_fwd|pose_bwd|adam_params' -s 60 -c 26 -f -o gpurun_out/${T}_prof python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'fused_bwd|fused_fwd' -s 30 -c 4 -f -o gpurun_out/${T}_prof_vertex python bench.py --loss-path vertex --steps 3 --warmup 3 --no-cpu-baseline --no-secondary >> gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out/${T}_prof*.ncu-rep
+timeout 300 python benchmarks/gemm_pair_check.py > gpurun_out/${T}_gemm_pair_check.jsonl 2>/dev/null
+timeout 300 python benchmarks/gemm_prof.py > gpurun_out/${T}_gemm_role_stamps.jsonl 2>/dev/null
+for s in 0 1 2 3; do JRR_DEBUG_SKIP=$s timeout 200 python benchmarks/step_breakdown.py; done > gpurun_out/${T}_step_breakdown.jsonl 2>/dev/null
+JRR_OVERLAP_CRITIC=0 timeout 200 python benchmarks/step_breakdown.py >> gpurun_out/${T}_step_breakdown.jsonl 2>/dev/null
+compute-sanitizer --tool memcheck --print-limit 20 python benchmarks/sanitize.py 2>&1 | grep -E "COMPUTE-SANITIZER|ERROR SUMMARY|Invalid|sanitizer workload|at 0x|Error" | head -40 > gpurun_out/${T}_memcheck.txt; tail -2 gpurun_out/${T}_memcheck.txt

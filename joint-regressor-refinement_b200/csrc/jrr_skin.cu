@@ -931,11 +931,30 @@ __global__ void joints49_fwd_packed_kernel(const int* __restrict__ joint_map, co
     const int p = inv_perm[picks[src - NJ]];
     for (int c = 0; c < 3; c++) out[c] = vT[(int64_t)(3 * p + c) * BP + b];
   } else {
+    // eight entries at a time: their index -> permutation -> vertex loads are three dependent round trips per BATCH, not per
+    // entry (a row of J_regressor_extra was a 16-deep chain of them: 21 us even for one pose); the sum keeps its order
     const int e = src - NJ - JRR_NUM_PICKS;
-    for (int q = extra.ptr[e]; q < extra.ptr[e + 1]; q++) {
-      const int p = inv_perm[extra.col[q]];
-      const float cf = extra.val[q];
-      for (int c = 0; c < 3; c++) out[c] = fmaf(cf, vT[(int64_t)(3 * p + c) * BP + b], out[c]);
+    const int q1 = extra.ptr[e + 1];
+    for (int q = extra.ptr[e]; q < q1; q += 8) {
+      int p[8];
+      float cf[8], v[8][3];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const bool on = q + u < q1;
+        cf[u] = on ? extra.val[q + u] : 0.f;
+        p[u] = on ? extra.col[q + u] : extra.col[q];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) p[u] = inv_perm[p[u]];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) v[u][c] = vT[(int64_t)(3 * p[u] + c) * BP + b];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        if (q + u < q1)
+#pragma unroll
+          for (int c = 0; c < 3; c++) out[c] = fmaf(cf[u], v[u][c], out[c]);
     }
   }
   for (int c = 0; c < 3; c++) joints49[(b * JRR_NUM_OUT_JOINTS + o) * 3 + c] = out[c];

@@ -51,7 +51,8 @@ def launches():
         a[1] += t
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(DST, f"{TAG}_launches_summary.txt"), "w") as f:
-        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline\n")
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
+                + (" --no-secondary" if TAG != "r1" else "") + "\n")
         f.write("(cold-cache, serialised per-launch times: compare SHARES, not absolutes; the command also runs set-up,\n"
                 " warm-up, the end-to-end leg, the profiled steps, the other loss-path formulation and the refit, so their kernels\n"
                 " appear too: fold_kernel runs once per regressor version -- here at every set_regressor of the set-up and quality\n"
@@ -65,14 +66,21 @@ def launches():
                 "pose_bwd_kernel<2, 0>", "critic_pre_kernel", "gemm_tc_kernel<128, 1, 1>", "gemm_tc_kernel<128, 4, 1>",
                 "critic_head_light_kernel", "gemm_tc_kernel<128, 2, 1>", "gemm_tc_kernel<96, 3, 1>", "critic_post_kernel",
                 "loss_finish_kernel", "adam_coef_kernel", "adam_params_kernel", "bump_step_kernel"]
+        grp = {"critic_gemm_fwd": ["gemm_tc_kernel<128, 1, 1>", "gemm_tc_kernel<128, 4, 1>"],
+               "critic_gemm_bwd": ["gemm_tc_kernel<128, 2, 1>", "gemm_tc_kernel<96, 3, 1>"]}
+        if any(k.startswith("gemm_pair_kernel") for k in agg):      # round 2: every GEMM of the step on CTA pairs
+            step = ["pose_fwd_kernel<2>", "gemm_pair_kernel<256, 0>", "folded_seed_kernel", "gemm_pair_kernel<224, 3>",
+                    "pose_bwd_kernel<2, 0>", "critic_pre_kernel", "gemm_pair_kernel<256, 1>", "gemm_pair_kernel<256, 4>",
+                    "gemm_pair_kernel<256, 2>", "gemm_pair_kernel<192, 3>", "critic_post_kernel", "loss_finish_kernel",
+                    "adam_coef_kernel", "adam_params_kernel"]
+            grp = {"critic_gemm_fwd": ["gemm_pair_kernel<256, 1>", "gemm_pair_kernel<256, 4>"],
+                   "critic_gemm_bwd": ["gemm_pair_kernel<256, 2>", "gemm_pair_kernel<192, 3>"]}
         have = [(k, agg[k][1] / agg[k][0]) for k in step if k in agg]
         if have:
             st = sum(t for _, t in have)
             f.write(f"\none folded refinement step = {len(have)} launches, {st:.1f} us serialised under ncu\n")
             for k, t in sorted(have, key=lambda kv: -kv[1]):
                 f.write(f"{k[:62]:62s} {1:8d} {t:10.1f} {t:9.2f} {100 * t / st:6.2f}%\n")
-            grp = {"critic_gemm_fwd": ["gemm_tc_kernel<128, 1, 1>", "gemm_tc_kernel<128, 4, 1>"],
-                   "critic_gemm_bwd": ["gemm_tc_kernel<128, 2, 1>", "gemm_tc_kernel<96, 3, 1>"]}
             d = dict(have)
             for g, ks in grp.items():
                 if all(k in d for k in ks):
@@ -82,7 +90,9 @@ def launches():
 def top_kernels():
     import json
     out = ["ncu --set full --clock-control none --import-source on -k regex:'folded_seed|gemm_tc_kernel' -s 42 -c 14 "
-           "python bench.py --steps 3 --warmup 3 --no-cpu-baseline",
+           "python bench.py --steps 3 --warmup 3 --no-cpu-baseline" if TAG == "r1" else
+           "ncu --set full --clock-control none --import-source on -k regex:'gemm_pair|folded_seed|critic_pre|critic_post|pose_fwd|"
+           "pose_bwd|adam_params' -s 60 -c 26 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary",
            "ncu --set full ... -k regex:'fused_bwd|fused_fwd' -s 30 -c 4 python bench.py --loss-path vertex --steps 3 --warmup 3 --no-cpu-baseline",
            "(first captured launch of each kernel; B = 4096 poses, dense 17x6890 regressor; times under ncu are cold-cache and serialised)", ""]
     traffic = {}
@@ -117,7 +127,9 @@ def top_kernels():
 
 def main():
     for f in (f"{TAG}_bench.json", f"{TAG}_bench_vertex.json", f"{TAG}_bench_shipped.json", f"{TAG}_bench_reference.json", f"{TAG}_gpu_tests.txt",
-              f"{TAG}_sweep.jsonl", f"{TAG}_memcheck.txt", f"{TAG}_bench_2gpu.json"):
+              f"{TAG}_sweep.jsonl", f"{TAG}_memcheck.txt", f"{TAG}_bench_2gpu.json", f"{TAG}_bench_8gpu.json", f"{TAG}_launches.csv",
+              f"{TAG}_gemm_pair_check.jsonl", f"{TAG}_gemm_role_stamps.jsonl", f"{TAG}_step_breakdown.jsonl",
+              f"{TAG}_multi_gpu_check_2.json", f"{TAG}_multi_gpu_check_8.json", f"{TAG}_module_launches.csv"):
         p = os.path.join(SRC, f)
         if os.path.exists(p):
             shutil.copy(p, os.path.join(DST, f))
