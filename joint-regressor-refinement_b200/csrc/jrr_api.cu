@@ -72,6 +72,7 @@ Workspace carve(const JrrModel* m, int64_t B, void* base) {
   w.dzg = take(BP);
   w.cmask = reinterpret_cast<uint2*>(take(BP * NJ * 2));
   w.zmask = reinterpret_cast<uint32_t*>(take(BP * (C_Z / 32)));
+  w.zmask2 = reinterpret_cast<uint32_t*>(take(BP * (C_Z / 32)));
   w.gx6 = take(BP * 144);
   w.gbetas = take(BP * NB);
   w.adam_coef = take(64);

@@ -422,6 +422,8 @@ int critic_forward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st,
     g.epi = EPI_BIAS_RELU_HEAD;
     g.out0 = w.dz2_hi; g.out1 = w.dz2_lo;          // (z2 > 0) * w3, the head's gradient row up to dL/dlogit
     g.vec = m->critic_small + CS_W3; g.out2 = w.zg_part;
+    // ... or only the mask z2 > 0 as bits, when the backward GEMM can take it as a 0/1 operand against diag(w3) W2
+    if (ts && gemm_pair_bits_available(m, w.BP)) g.mask_bits_out = w.zmask2;
   }
   return launch_gemm(m, g, st);
 }
@@ -440,12 +442,17 @@ int critic_backward_gemms(const JrrModel* m, const Workspace& w, cudaStream_t st
   }
   g.A_hi = w.dz2_hi; g.A_lo = w.dz2_lo; g.lda = C_Z;
   g.B_hi = m->W2t_hi; g.B_lo = m->W2t_lo; g.ldb = C_Z;
+  if (ts && gemm_pair_bits_available(m, w.BP)) {     // (the forward wrote the mask bits, see critic_forward_gemms)
+    g.a_bits = w.zmask2;
+    g.B_hi = m->W2tw_hi; g.B_lo = m->W2tw_lo;
+  }
   g.M = w.BP; g.N = C_Z; g.K = C_Z; g.ksplit = 1; g.epi = EPI_MASK_SPLIT;
   g.out0 = w.dz1_hi; g.out1 = w.dz1_lo; g.ldo = C_Z; g.mask = w.z1_hi; g.ldmask = C_Z;
   g.mask_bits = ts ? w.zmask : nullptr;
   int rc = launch_gemm(m, g, st);
   if (rc) return rc;
   g.mask_bits = nullptr;
+  g.a_bits = nullptr;
   // dh = dz1 . W1
   g.A_hi = w.dz1_hi; g.A_lo = w.dz1_lo; g.lda = C_Z;
   g.B_hi = m->W1t_hi; g.B_lo = m->W1t_lo; g.ldb = C_Z;

@@ -37,6 +37,7 @@ struct TcParams {
   const float* rowscale;   // EPI_MASK_SPLIT: multiply row m by rowscale[m] (or nullptr)
   const float* vec;        // EPI_BIAS_RELU_HEAD: w3[N]
   float* out2;             // EPI_BIAS_RELU_HEAD: zg_part[n_tile][M]
+  const uint32_t* a_bits;  // CTA-pair kernel, ABITS: the 0/1 A operand as bits [M][K_total / 32]
   long long* prof;         // diagnostic only (jrr_debug_gemm + JRR_GEMM_PROF): per-CTA role timers, 16 counters each
   int probe;               // diagnostic only (JRR_GEMM_PROBE, benchmarks/gemm_probe.py): bit 0 = MMAs do not wait for the
                            // A producers (garbage A; shows the loop's pace without the smem->TMEM staging chain),
@@ -112,7 +113,20 @@ __device__ __forceinline__ void tc_epilogue_row(const TcParams& p, const uint32_
       // x = relu(acc + b); logit partial sum x.w3; and the head's masked gradient row
       // (x > 0 ? w3 : 0) as a tf32 hi/lo pair -- the per-row scalar dL/dlogit is applied by the
       // EPILOGUE of the backward GEMM (rowscale), so no kernel ever reads the activations back
-      if (m < p.M && n0 < p.N) {
+      if (TS && p.mask_bits_out != nullptr) {
+        // the consumer of this layer's gradient row (x > 0 ? w3 : 0) takes the ReLU MASK as a 0/1 operand against
+        // diag(w3) W2 (a_bits): one bit per element leaves instead of a 4-byte value
+        if (m < p.M && n0 < p.N) {
+          uint32_t bits = 0;
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const float x = fmaxf(v[i] + __ldg(p.bias + n0 + i), 0.f);
+            zsum = fmaf(x, __ldg(p.vec + n0 + i), zsum);
+            bits |= (x > 0.f ? 1u : 0u) << i;
+          }
+          p.mask_bits_out[m * (p.N >> 5) + (n0 >> 5)] = bits;
+        }
+      } else if (m < p.M && n0 < p.N) {
         float hi[32], lo[32];
 #pragma unroll
         for (int i = 0; i < 32; i++) {
@@ -634,10 +648,10 @@ constexpr int PAIR_THREADS = 448;
 constexpr int PAIR_MAXREG = 88;
 constexpr int PAIR_SMEM_BUDGET = 194 * 1024;
 constexpr int PAIR_STORE_BYTES = 8 * 4096;
-template <int BN>
+template <int BN, bool ABITS = false>
 struct PairCfg {
   static constexpr int HB = BN / 2;                 // weight rows (output columns) held by one CTA
-  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int A_BYTES = ABITS ? 0 : BM * BK * 4;     // (ABITS: the producers expand mask bits, no A tile in smem)
   static constexpr int B_BYTES = HB * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (4 * STAGE_BYTES + PAIR_STORE_BYTES + 1024 + 256 <= PAIR_SMEM_BUDGET) ? 4 : 3;
@@ -648,11 +662,15 @@ struct PairCfg {
   static_assert(BN % 32 == 0 && BN <= 256 && B_BYTES % 1024 == 0, "pair tile width");
 };
 
-template <int BN, int EPI>
+// ABITS: the A operand is a 0/1 matrix given as bits (TcParams::a_bits; the layer-2 backward of the critic reads the ReLU mask
+// against diag(w3) W2): exact in tf32, so every K step is two MMAs (A . B_hi + A . B_lo) instead of three, the A tile does
+// not travel through TMA at all -- a producer thread loads ONE word per K block and row -- and the layer that produces the
+// mask writes 512 KB of bits instead of 16.8 MB of fp32 values.
+template <int BN, int EPI, bool ABITS = false>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(PAIR_MAXREG)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
                  const __grid_constant__ CUtensorMap mapBl, const __grid_constant__ CUtensorMap mapO, const TcParams p) {
-  using Cfg = PairCfg<BN>;
+  using Cfg = PairCfg<BN, ABITS>;
   extern __shared__ uint8_t smem_raw[];
   // (the dynamic shared memory window starts at the same offset in both CTAs, so the aligned layouts coincide)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -712,7 +730,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int kc = (int)(split * p.K) + kb * BK;
-          tma_load_2d(&mapA, &full_bar[stage], sa, kc, rowA);
+          if (!ABITS) tma_load_2d(&mapA, &full_bar[stage], sa, kc, rowA);
           tma_load_2d(&mapBh, &full_bar[stage], sa + Cfg::A_BYTES, kc, rowB);
           tma_load_2d(&mapBl, &full_bar[stage], sa + Cfg::A_BYTES + Cfg::B_BYTES, kc, rowB);
           if (t == pair && kb == 0) JRR_STAMP(2);      // first stage issued
@@ -746,8 +764,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / 8; k++) {
             const uint64_t ko = (uint64_t)(k * 32 >> 4);
-            tc_mma_tf32_ts_pair(tmem_base, ta + 32 + k * 8, dBh + ko, idesc, (kb | k) != 0);
-            tc_mma_tf32_ts_pair(tmem_base, ta + k * 8, dBl + ko, idesc, 1);
+            if (!ABITS) tc_mma_tf32_ts_pair(tmem_base, ta + 32 + k * 8, dBh + ko, idesc, (kb | k) != 0);
+            tc_mma_tf32_ts_pair(tmem_base, ta + k * 8, dBl + ko, idesc, ABITS ? (uint32_t)((kb | k) != 0) : 1u);
             tc_mma_tf32_ts_pair(tmem_base, ta + k * 8, dBh + ko, idesc, 1);
           }
           tc_commit_pair(&empty_bar[stage]);
@@ -770,6 +788,30 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
+      if (ABITS) {
+        // 0/1 operand: one word of mask bits per K block and row, expanded to 32 exact tf32 values (no lo half)
+        const int split = t / tiles_mn, mb = (t % tiles_mn) % p.m_tiles;
+        const int64_t m = (int64_t)mb * 2 * BM + (int64_t)rank * BM + row;
+        const uint32_t* wrow = p.a_bits + (m < p.M ? m : 0) * (int64_t)(p.K * p.ksplit / BK) + (int64_t)split * num_kb;
+        uint32_t word = m < p.M ? wrow[0] : 0u;
+        for (int kb = 0; kb < num_kb; kb++) {
+          const uint32_t next = (m < p.M && kb + 1 < num_kb) ? wrow[kb + 1] : 0u;     // in flight across the wait below
+          mbar_wait(&full_bar[stage], phase);      // the weights landed; the staging slot's previous readers are done
+          if (t == pair && kb == 0 && warp == 6 && lane == 0) JRR_STAMP(3);
+          float hi[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) hi[i] = ((word >> i) & 1u) ? 1.f : 0.f;
+          tc_fence_after();
+          tc_st32(trow + stage * 64, hi);
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(ready_leader + stage * 8);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          word = next;
+        }
+        continue;
+      }
       for (int kb = 0; kb < num_kb; kb++) {
         // `full` of this stage follows the `empty` commit of the MMAs that read staging slot `stage` four K blocks ago
         mbar_wait(&full_bar[stage], phase);
@@ -988,15 +1030,16 @@ static int launch_ts2(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
 }
 
 // CTA-pair kernel: grid = 2 x min(pair tiles, SM pairs); the static cluster dimension keeps a pair on one TPC
-template <int BN, int EPI>
+template <int BN, int EPI, bool ABITS = false>
 static int launch_pair(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
-  using Cfg = PairCfg<BN>;
+  using Cfg = PairCfg<BN, ABITS>;
   CUtensorMap mA, mBh, mBl, mO;
   const int64_t Ktot = g.K * g.ksplit;
   if (int rc = make_tensor_map_2d(&mBh, g.B_hi, g.N, Ktot, g.ldb, Cfg::HB)) return rc;
   if (int rc = make_tensor_map_2d(&mBl, g.B_lo, g.N, Ktot, g.ldb, Cfg::HB)) return rc;
   const int64_t Ka = g.k_valid > 0 ? g.k_valid : Ktot;
-  if (int rc = make_tensor_map_2d(&mA, g.A_hi, g.M, Ka, g.lda, BM)) return rc;
+  if (ABITS) mA = mBh;       // (unused: the A operand comes from a_bits)
+  else if (int rc = make_tensor_map_2d(&mA, g.A_hi, g.M, Ka, g.lda, BM)) return rc;
   if (int rc = make_tensor_map_2d(&mO, g.out0, g.M * g.ksplit, g.N, g.ldo, 32)) return rc;
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.ksplit = g.ksplit;
@@ -1010,7 +1053,8 @@ static int launch_pair(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
   p.logit_gscale = g.logit_gscale; p.rows_valid = g.rows_valid;
   if (EPI == EPI_BIAS_RELU_HEAD && (Cfg::E0 != 128 || Cfg::E1 != 128))
     return fail(JRR_ERR_INVALID, "tc gemm (CTA pairs): the fused head needs 128-column epilogue parts");
-  auto kern = gemm_pair_kernel<BN, EPI>;
+  p.a_bits = g.a_bits;
+  auto kern = gemm_pair_kernel<BN, EPI, ABITS>;
   JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
   int reps = 1;
@@ -1059,6 +1103,11 @@ static int pair_mode() {
   return v;
 }
 
+bool gemm_pair_bits_available(const JrrModel* m, int64_t M) {
+  static const bool on = [] { const char* e = getenv("JRR_CRITIC_BITS"); return !(e && e[0] == '0'); }();
+  return on && m->gemm_impl == 0 && pair_mode() > 0 && M >= 2 * BM;
+}
+
 static bool use_ts2() {
   static int v = -1;
   if (v < 0) {
@@ -1082,6 +1131,11 @@ int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st) {
       return launch_pair<256, EPI_STORE_T>(m, g, st);
     }
     if (g.epi == EPI_STORE_SPLITK && g.N == 224 && g.M >= 2 * BM) return launch_pair<224, EPI_STORE_SPLITK>(m, g, st);
+    if (g.a_bits != nullptr) {
+      if (!gemm_pair_bits_available(m, g.M) || g.epi != EPI_MASK_SPLIT || g.N % 256 != 0 || g.ksplit != 1)
+        return fail(JRR_ERR_INVALID, "tc gemm: a 0/1 A operand needs the CTA-pair kernel (mask epilogue, N % 256 == 0)");
+      return launch_pair<256, EPI_MASK_SPLIT, true>(m, g, st);
+    }
     if (g.N % 128 != 0) return fail(JRR_ERR_INVALID, "tc gemm (A through TMEM): N % 128");
     if (g.M >= 2 * BM && pair_mode() > 0 && !(g.probe_env && getenv("JRR_GEMM_PROBE_TS1"))) {
       if (g.N == 768 && pair_mode() == 1) return launch_pair_epi<192>(m, g, st);

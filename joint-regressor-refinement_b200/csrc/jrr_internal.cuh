@@ -179,6 +179,7 @@ struct JrrModel {
   float *W2_hi = nullptr, *W2_lo = nullptr;    // [1024][1024]
   float *W1t_hi = nullptr, *W1t_lo = nullptr;  // [768][1024]
   float *W2t_hi = nullptr, *W2t_lo = nullptr;  // [1024][1024]
+  float *W2tw_hi = nullptr, *W2tw_lo = nullptr;  // [1024][1024]  (diag(w3) W2)^T: the backward of layer 2 with a 0/1 A operand
   bool has_critic = false;
   float* shape_critic = nullptr;             // 171 floats: shape_operations.{0,2,4} weight/bias (discriminator.py:57-74)
   bool has_shape_critic = false;
@@ -258,6 +259,7 @@ struct Workspace {
   float* dzg;              // [BP]       dL/d(global logit)
   uint2* cmask;            // [BP][24]   ReLU masks of the critic's two 1x1 convs (pre -> post)
   uint32_t* zmask;         // [BP][32]   ReLU mask bits of the critic's first wide layer
+  uint32_t* zmask2;        // [BP][32]   ... of the second (the A operand of the layer-2 backward GEMM, bit-packed)
   float* gx6;              // [BP][144]  parameter gradients of the chain backward (split-Adam schedule)
   float* gbetas;           // [BP][10]
   float* adam_coef;        // [2]        this step's Adam bias corrections (adam_coef_kernel)
@@ -288,6 +290,9 @@ struct GemmDesc {
   const float* logit_part; int n_logit_part; const float* logit_bias; float logit_gscale; int64_t rows_valid;
                                            // (EPI_MASK_SPLIT) row scale = gscale * (s - 1) s (1 - s), s = sigmoid(bias +
                                            // sum of the row's logit partials), zero for rows >= rows_valid
+  const uint32_t* a_bits;                  // (CTA-pair kernel) A is a 0/1 matrix given as bits [M][K/32] (bit k%32 of word k/32): exact
+                                           // in tf32, so the A_lo . B_hi product is dropped -- two MMAs per K step instead of three,
+                                           // no A tile through TMA
   int64_t k_valid;                         // > 0: only the first k_valid columns of A exist (TMA zero-fills the rest of K)
   bool probe_env;                          // jrr_debug_gemm: honour the JRR_GEMM_PROBE* diagnostic environment knobs
   bool a_via_tmem;                         // A is plain fp32 (A_hi): loaded, tf32-split and staged in tensor memory by the
@@ -296,6 +301,7 @@ struct GemmDesc {
 int launch_gemm(const JrrModel* m, const GemmDesc& g, cudaStream_t st);
 int launch_gemm_simt(const GemmDesc& g, cudaStream_t st);
 int launch_gemm_tc(const JrrModel* m, const GemmDesc& g, cudaStream_t st);
+bool gemm_pair_bits_available(const JrrModel* m, int64_t M);   // the 0/1-A variant of the CTA-pair kernel can run
 
 int launch_skin_fwd(const JrrModel* m, const Workspace& w, float* vertices_out, float* vT_out,
                     bool want_part, cudaStream_t st);

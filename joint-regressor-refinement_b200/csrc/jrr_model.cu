@@ -511,13 +511,15 @@ __global__ void split_kernel(const float* __restrict__ src, int64_t n, float* __
 }
 
 __global__ void split_transpose_kernel(const float* __restrict__ src, int rows, int cols,
-                                       float* __restrict__ hi, float* __restrict__ lo) {
-  // src [rows][cols] -> hi/lo [cols][rows]
+                                       float* __restrict__ hi, float* __restrict__ lo,
+                                       const float* __restrict__ row_scale = nullptr) {
+  // src [rows][cols] (row r optionally scaled by row_scale[r]) -> hi/lo [cols][rows]
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows * cols) return;
   const int c = (int)(i / rows), r = (int)(i % rows);
   uint32_t q;
   float x = src[(int64_t)r * cols + c];
+  if (row_scale != nullptr) x *= row_scale[r];
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(x));
   float h = __uint_as_float(q);
   hi[i] = h;
@@ -877,6 +879,8 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   if (int rc = dalloc(m, &m->W2_lo, (size_t)C_Z * C_Z)) return rc;
   if (int rc = dalloc(m, &m->W2t_hi, (size_t)C_Z * C_Z)) return rc;
   if (int rc = dalloc(m, &m->W2t_lo, (size_t)C_Z * C_Z)) return rc;
+  if (int rc = dalloc(m, &m->W2tw_hi, (size_t)C_Z * C_Z)) return rc;
+  if (int rc = dalloc(m, &m->W2tw_lo, (size_t)C_Z * C_Z)) return rc;
   JRR_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
   JRR_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   JRR_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
@@ -975,6 +979,9 @@ int jrr::critic_load_impl(JrrModel* m, const float* p, cudaStream_t st) {
   split_transpose_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(W1, C_Z, C_H, m->W1t_hi, m->W1t_lo);
   JRR_LAUNCH_CHECK();
   split_transpose_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(W2, C_Z, C_Z, m->W2t_hi, m->W2t_lo);
+  JRR_LAUNCH_CHECK();
+  // (diag(w3) W2)^T: with it the layer-2 backward reads the ReLU mask itself as its A operand (critic_backward_gemms)
+  split_transpose_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(W2, C_Z, C_Z, m->W2tw_hi, m->W2tw_lo, w3);
   JRR_LAUNCH_CHECK();
   m->has_critic = true;
   return JRR_OK;
