@@ -309,7 +309,7 @@ def median_ms(fn, torch, warm=3, reps=10):
     return ts[len(ts) // 2]
 
 
-def kernel_table(acc, folded, B, pk):
+def kernel_table(acc, folded, B, pk, l2_bwd_products=3):
     """Per kernel-group times of jrr_refine_step_profiled -> roofline entries.  Groups are timed in isolation
     (events between serialised launches), so tensor-bound ones are quoted against the BURST peak."""
     tf32_burst = pk["bf16_burst"] / 2
@@ -341,6 +341,8 @@ def kernel_table(acc, folded, B, pk):
                 e["name"] = "fused_bwd(skinning_bwd+blend_gemm_bwd)"
         elif name in ("critic_gemm_fwd", "critic_gemm_bwd", "critic_chain"):
             fl = 3 * B * F_CRITIC_DIR * (2 if name == "critic_chain" else 1)
+            if name != "critic_gemm_fwd":        # the layer-2 backward may issue two products per K step (0/1 operand)
+                fl -= (3 - l2_bwd_products) * B * 2.0 * 1024 * 1024
         elif name == "skin_fwd":
             by = 4.0 * B * (20670 + 288 + 51)
         elif name == "skin_bwd":
@@ -594,7 +596,8 @@ def main():
         if i >= 2:
             for k, v in ms.items():
                 acc[k] = acc.get(k, 0.0) + v / P
-    kern = kernel_table(acc, folded, B, pk)
+    l2p = refiner.native.critic_layer2_bwd_products(B)
+    kern = kernel_table(acc, folded, B, pk, l2p)
     step_ms_prof = sum(e["ms"] for e in kern)
     dom = next((e for e in kern if "achieved" in e), None)
     roofline = None
@@ -609,8 +612,14 @@ def main():
     tf32_sus = pk["bf16_sustained"] / 2               # the whole step runs inside a long replay: sustained peak
     pose_steps_per_s = value / world
     f_gemm = F_GEMM if not folded else 2.0 * (2 * 1224 * 218) + 2 * F_CRITIC_DIR
-    whole = {"tensor_frac_3xtf32": round(3 * f_gemm * pose_steps_per_s / (tf32_sus * 1e12), 4),
-             "tensor_frac_3xtf32_vs_burst": round(3 * f_gemm * pose_steps_per_s / (pk["bf16_burst"] / 2 * 1e12), 4),
+    issued = 3 * f_gemm - (3 - l2p) * 2.0 * 1024 * 1024           # tensor-core FLOPs actually issued per pose-step
+    whole = {"tensor_frac_3xtf32": round(issued * pose_steps_per_s / (tf32_sus * 1e12), 4),
+             "tensor_frac_3xtf32_vs_burst": round(issued * pose_steps_per_s / (pk["bf16_burst"] / 2 * 1e12), 4),
+             "issued_gflop_per_step": round(issued * B / 1e9, 2),
+             # the same results through the generic three-product scheme everywhere (what round 1 issued): the step's
+             # rate of 3xTF32-equivalent work -- not a utilisation figure, the issued one above is
+             "tensor_frac_generic_3xtf32_work": round(3 * f_gemm * pose_steps_per_s / (tf32_sus * 1e12), 4),
+             "critic_layer2_bwd_products_per_k_step": l2p,
              "peak_tflops_tf32_sustained": tf32_sus,
              "hbm_frac_algorithmic": round(ALG_BYTES_PER_POSE_STEP * pose_steps_per_s / (pk["hbm_gbs"] * 1e9), 6),
              "useful_tflops": round((F_USEFUL if not folded else f_gemm + 2 * 24 * 17 * 33) * pose_steps_per_s / 1e12, 2),

@@ -274,6 +274,11 @@ int jrr_debug_tma_probe(const float* src, int64_t rows, int64_t cols, int box_ro
  * next launches are written to consecutive [148][16] int64 slots of the DEVICE buffer `base`; base == NULL switches it off. */
 int jrr_debug_set_gemm_prof(long long* base, int slots);
 
+/* Measurement aid (bench.py's FLOP accounting; no reference counterpart): tensor-core products issued per K step by the
+ * backward GEMM of the critic's second wide layer in a refinement step over B frames -- 2 when it takes the ReLU mask as a
+ * 0/1 operand against diag(w3) W2 (exact in tf32, see csrc/jrr_critic.cu), 3 for the generic 3xTF32 scheme. */
+int jrr_critic_layer2_bwd_products(const JrrModel* model, int64_t B);
+
 /* number of kernels the last call of the named entry point enqueued (bench.py's
  * gpu_launches claim is counted, not guessed) */
 int64_t jrr_last_launch_count(void);

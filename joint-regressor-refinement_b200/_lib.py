@@ -20,6 +20,7 @@ EXPORTS = [
     "jrr_debug_gemm", "jrr_refine_step_profiled", "jrr_step_kernel_name", "jrr_camera_fit", "jrr_refine_step_2d", "jrr_evaluate",
     "jrr_shape_critic_load", "jrr_shape_critic_forward", "jrr_critic_grad_accumulate", "jrr_critic_apply",
     "jrr_shape_critic_grad_accumulate", "jrr_shape_critic_apply", "jrr_set_loss_path", "jrr_debug_tma_probe", "jrr_debug_set_gemm_prof",
+    "jrr_critic_layer2_bwd_products",
 ]
 
 
@@ -56,6 +57,7 @@ def lib():
     L.jrr_set_regressor.argtypes = [vp, vp, vp, vp]
     L.jrr_critic_load.argtypes = [vp, vp, vp]
     L.jrr_set_loss_path.argtypes = [vp, C.c_int, vp]
+    L.jrr_critic_layer2_bwd_products.argtypes = [vp, C.c_int64]
     L.jrr_shape_critic_load.argtypes = [vp, vp, C.c_float, vp]
     L.jrr_shape_critic_forward.argtypes = [vp, i64, vp, vp, vp]
     L.jrr_critic_grad_accumulate.argtypes = [vp, i64, i64, vp, C.c_float, vp, vp, vp, sz, vp]

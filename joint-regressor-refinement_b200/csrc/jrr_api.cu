@@ -497,6 +497,12 @@ extern "C" int jrr_camera_fit(JrrModel* m, int64_t B, int64_t B_logical, const f
   return launch_camera_fit(w, w.pred, gt_j2d, cam, iters, lr, B_logical, loss_out, st);
 }
 
+extern "C" int jrr_critic_layer2_bwd_products(const JrrModel* m, int64_t B) {
+  if (!m || B <= 0) return 3;
+  const bool ts = m->critic_head_fused && m->critic_ts;
+  return (ts && gemm_pair_bits_available(m, round_up(B, 256))) ? 2 : 3;
+}
+
 extern "C" const char* jrr_step_kernel_name(int i) {
   return (i >= 0 && i < JRR_STEP_KERNELS) ? kStepKernelNames[i] : nullptr;
 }

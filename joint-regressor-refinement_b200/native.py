@@ -175,6 +175,10 @@ class NativeModel:
             check(self.L.jrr_critic_load(self.h, _ptr(flat), _stream()), "jrr_critic_load")
             torch.cuda.current_stream().synchronize()   # `flat` may be freed after return
 
+    def critic_layer2_bwd_products(self, B: int) -> int:
+        """Tensor-core products per K step of the critic's layer-2 backward GEMM in a refinement step (2 or 3)."""
+        return int(self.L.jrr_critic_layer2_bwd_products(self.h, int(B)))
+
     def set_loss_path(self, mode: str):
         """'vertex' (per-vertex fused kernels, default) or 'folded' (regressor o skinning o blend operator
         folded once per regressor version; see include/jrr.h)."""
