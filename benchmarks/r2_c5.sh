@@ -1,0 +1,13 @@
+# module path: parity tests, then the C5 sweep rows (forward / forward+backward per batch size)
+timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 2>&1 | tail -4
+python - <<'PY'
+import json, sys, os
+sys.path.insert(0, os.getcwd())
+import torch, bench
+import jrr_b200 as jrr
+dev = torch.device("cuda", 0)
+smpl = jrr.SMPL(model_dict=jrr.synthetic.make_smpl_model(0), create_transl=False).to(dev)
+pk = bench.load_peaks() if hasattr(bench, "load_peaks") else None
+rows = bench.run_c5(jrr, smpl, dev, pk or {"bf16_burst": 1638.9, "hbm_gbs": 6555.5}, [1, 16, 256, 1024, 4096])
+for r in rows: print(json.dumps(r))
+PY

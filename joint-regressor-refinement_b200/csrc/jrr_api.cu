@@ -129,7 +129,8 @@ static int fused_fwd_all_passes(const JrrModel* cm, const Workspace& w, int stor
 // flush events to their own region, and the dA reduction of pass p > 0 accumulates.  Sets w.ksplit for the chain backward.
 static int fused_bwd_all_passes(const JrrModel* cm, Workspace& w, cudaStream_t st, const float* dvT, cudaEvent_t* ev_mid) {
   JrrModel* m = const_cast<JrrModel*>(cm);
-  const int nsplit = dvT != nullptr ? NSPLIT_B : m->nsplit_act;
+  const bool small = dvT != nullptr && module_small_ranges(m, w.BP);
+  const int nsplit = dvT != nullptr ? (small ? NSPLIT_S : NSPLIT_B) : m->nsplit_act;
   if (nsplit * m->n_pass > KSPLIT_MAX) return fail(JRR_ERR_INVALID, "too many skinning passes for the split-K workspace");
   int rc = JRR_OK;
   for (int p = 0; p < m->n_pass && rc == JRR_OK; p++) {
@@ -139,7 +140,7 @@ static int fused_bwd_all_passes(const JrrModel* cm, Workspace& w, cudaStream_t s
   if (ev_mid && rc == JRR_OK) { cudaError_t e = cudaEventRecord(*ev_mid, st); if (e != cudaSuccess) rc = fail(JRR_ERR_CUDA, cudaGetErrorString(e)); }
   for (int p = 0; p < m->n_pass && rc == JRR_OK; p++) {
     m->select_pass(p);
-    rc = launch_dA_reduce(m, w, dvT == nullptr, st);
+    rc = launch_dA_reduce(m, w, dvT == nullptr ? 1 : (small ? 2 : 0), st);
   }
   m->select_pass(0);
   w.ksplit = nsplit * m->n_pass;
@@ -247,7 +248,7 @@ extern "C" int jrr_smpl_backward(JrrModel* m, int64_t B, const float* betas, con
   if (use_x)
     if (int rc = launch_joints49_bwd(m, w, djoints49, st)) return rc;
   if (int rc = launch_skin_bwd(m, w, dvertices, false, use_x, st)) return rc;
-  if (int rc = launch_dA_reduce(m, w, false, st)) return rc;
+  if (int rc = launch_dA_reduce(m, w, 0, st)) return rc;
   if (int rc = blend_backward_gemm(m, w, st)) return rc;
   return launch_pose_bwd(m, w, betas, pose, kind, use_x, false, false, dbetas_out, dpose_out, nullptr, nullptr,
                          nullptr, nullptr, nullptr, 0.f, st);
@@ -406,7 +407,7 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
     } else {
       if (int rc = launch_skin_bwd(m, w, nullptr, true, false, st)) return rc;
       JRR_MARK();
-      if (int rc = launch_dA_reduce(m, w, false, st)) return rc;
+      if (int rc = launch_dA_reduce(m, w, 0, st)) return rc;
       JRR_MARK();
       if (int rc = blend_backward_gemm(m, w, st)) return rc;
       JRR_MARK();

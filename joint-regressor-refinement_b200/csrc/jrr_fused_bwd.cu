@@ -397,17 +397,20 @@ int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st, con
   if (int rc = make_tensor_map_2d(&mPh, m->P_hi, KA, NP, NP, KA)) return rc;
   if (int rc = make_tensor_map_2d(&mPl, m->P_lo, KA, NP, NP, KA)) return rc;
   // skinning pass p: its split-K partials follow those of the earlier passes, its dA flush events have their own region
-  const int ns_p = dvT != nullptr ? NSPLIT_B : m->nsplit_act;
+  const bool small = dvT != nullptr && module_small_ranges(m, w.BP);
+  const int ns_p = dvT != nullptr ? (small ? NSPLIT_S : NSPLIT_B) : m->nsplit_act;
   float* dfeat_p = w.dfeat + (int64_t)m->cur_pass * ns_p * w.BP * KA;
   float* flush_p = w.dAflush + (int64_t)m->flush_off[m->cur_pass] * 12 * w.BP;
   if (dvT != nullptr) {
     // module path: every packed vertex in 768-vertex ranges (the records / flush lists of the module backward)
-    const int nsplit = NSPLIT_B;
+    // (a batch of <= 1024 poses has at most four 256-pose blocks: 192-vertex ranges give it 36 items per block instead of 9)
+    const int nsplit = small ? NSPLIT_S : NSPLIT_B;
     const int n_items = (int)(w.BP / GB_POSES) * nsplit;
     const int grid = std::min(n_items, m->num_sms);
     JRR_CUDA(cudaFuncSetAttribute(fused_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM));
-    fused_bwd_kernel<true><<<grid, GB_THREADS, GB_SMEM, st>>>(mPh, mPl, m->vrec_b, m->range_flush_base, w.AT, w.vpT, dvT,
-                                                              w.BP, n_items, nsplit, VS_B, dfeat_p, flush_p);
+    fused_bwd_kernel<true><<<grid, GB_THREADS, GB_SMEM, st>>>(mPh, mPl, small ? m->vrec_s : m->vrec_b,
+                                                              small ? m->range_flush_base_s : m->range_flush_base, w.AT, w.vpT, dvT,
+                                                              w.BP, n_items, nsplit, small ? VS_S : VS_B, dfeat_p, flush_p);
     JRR_LAUNCH_CHECK();
     return JRR_OK;
   }

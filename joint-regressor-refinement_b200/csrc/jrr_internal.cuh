@@ -28,6 +28,8 @@ constexpr int VS_F = 576;           // packed vertices per CTA range, forward sk
 constexpr int NSPLIT = VP / VS_F;   // 12 regressor partial sums per pose
 constexpr int VS_B = 768;           // packed vertices per CTA range, backward skinning
 constexpr int NSPLIT_B = VP / VS_B; // 9
+constexpr int VS_S = 192;           // ... of the module backward on small batches (more CTAs per 256-pose block)
+constexpr int NSPLIT_S = VP / VS_S; // 36
 constexpr int KSPLIT_MAX = 36;      // split-K of the backward blend GEMM: 6, 9, 12 or 18 (chosen per batch to fill whole waves)
 constexpr int NPARAM = 154;         // 144 rot6d + 10 betas per pose
 constexpr int MAXCH = 4;            // children per joint supported by the chain kernels
@@ -125,6 +127,10 @@ struct PassTab {
   int n_flush = 0;
   int *flush_ptr_l = nullptr, *flush_idx_l = nullptr, *range_flush_base_l = nullptr;
   int n_flush_l = 0;
+  // module backward on small batches: every vertex in 192-vertex ranges (36 K ranges per 256-pose block instead of 9)
+  VtxRec* vrec_s = nullptr;
+  int *flush_ptr_s = nullptr, *flush_idx_s = nullptr, *range_flush_base_s = nullptr;
+  int n_flush_s = 0;
 };
 constexpr int MAX_PASS = 6;      // 24 weights per vertex
 }  // namespace jrr
@@ -156,6 +162,9 @@ struct JrrModel {
   int* flush_ptr_l = nullptr;                // [25]
   int* flush_idx_l = nullptr;
   int* range_flush_base_l = nullptr;         // [37]
+  jrr::VtxRec* vrec_s = nullptr;             // [VP] records with 192-vertex range boundaries (module backward, small batches)
+  int *flush_ptr_s = nullptr, *flush_idx_s = nullptr, *range_flush_base_s = nullptr;
+  int n_flush_s = 0;
   bool compact_active = true;                // pack vertices with a non-zero regressor column first
   uint8_t* active_dev = nullptr;             // [V] scratch of jrr_set_regressor
   std::vector<uint8_t> packed_active;        // support the current packing was built for
@@ -212,6 +221,7 @@ struct JrrModel {
     vrec = t.vrec; vrec_b = t.vrec_b; vrec_l = t.vrec_l;
     flush_ptr = t.flush_ptr; flush_idx = t.flush_idx; range_flush_base = t.range_flush_base; n_flush = t.n_flush;
     flush_ptr_l = t.flush_ptr_l; flush_idx_l = t.flush_idx_l; range_flush_base_l = t.range_flush_base_l; n_flush_l = t.n_flush_l;
+    vrec_s = t.vrec_s; flush_ptr_s = t.flush_ptr_s; flush_idx_s = t.flush_idx_s; range_flush_base_s = t.range_flush_base_s; n_flush_s = t.n_flush_s;
     n_flush_act = t.n_flush_l;
     cur_pass = p;
   }
@@ -345,7 +355,9 @@ int launch_fused_bwd(const JrrModel* m, const Workspace& w, cudaStream_t st, con
 int launch_pack_dvertices(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_x, float* dvT, cudaStream_t st);
 int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertices, bool use_g,
                     bool use_x, cudaStream_t st);
-int launch_dA_reduce(const JrrModel* m, const Workspace& w, bool loss_path_lists, cudaStream_t st);
+// module backward: 192-vertex K ranges when the batch has too few 256-pose blocks to fill the GPU with 768-vertex ones
+inline bool module_small_ranges(const JrrModel* m, int64_t BP) { return m->n_pass == 1 && BP <= 1024; }
+int launch_dA_reduce(const JrrModel* m, const Workspace& w, int lists /* 0 module (768), 1 loss path, 2 module (192) */, cudaStream_t st);
 int launch_joints49_fwd(const JrrModel* m, const Workspace& w, const float* vertices,
                         float* joints49_out, cudaStream_t st);
 int launch_joints49_bwd(const JrrModel* m, const Workspace& w, const float* djoints49,

@@ -643,19 +643,25 @@ int build_packing(JrrModel* m, const std::vector<uint8_t>& active) {
   m->flush_off[0] = 0;
   for (int pass = 0; pass < m->n_pass; pass++) {
     PassTab& t = m->passes[pass];
-    std::vector<VtxRec> rec_f, rec_b, rec_l;
+    std::vector<VtxRec> rec_f, rec_b, rec_l, rec_s;
     std::vector<int> flush_joint, range_base(NSPLIT_B + 1), flush_joint_l, range_base_l(VP / 192 + 1, 0);
+    std::vector<int> flush_joint_s, range_base_s(NSPLIT_S + 1, 0);
     build(pass, VS_F, rec_f, nullptr, nullptr);
     build(pass, VS_B, rec_b, &flush_joint, &range_base);            // module backward: every vertex, 768-vertex ranges
     build(pass, m->vs_l, rec_l, &flush_joint_l, &range_base_l);     // fused backward: vs_l-vertex ranges
+    build(pass, VS_S, rec_s, &flush_joint_s, &range_base_s);        // module backward, small batches: every vertex, 192-vertex ranges
+    range_base_s[NSPLIT_S] = (int)flush_joint_s.size();
+    t.n_flush_s = (int)flush_joint_s.size();
     range_base[NSPLIT_B] = (int)flush_joint.size();
     t.n_flush = (int)flush_joint.size();
     // the fused backward only walks the active ranges: its flush ids are a prefix
     flush_joint_l.resize(range_base_l[m->nsplit_act] ? range_base_l[m->nsplit_act] : flush_joint_l.size());
     t.n_flush_l = (int)flush_joint_l.size();
-    std::vector<int> fptr, fidx, fptr_l, fidx_l;
+    std::vector<int> fptr, fidx, fptr_l, fidx_l, fptr_s, fidx_s;
     csr(flush_joint, fptr, fidx);
     csr(flush_joint_l, fptr_l, fidx_l);
+    csr(flush_joint_s, fptr_s, fidx_s);
+    if (fidx_s.size() > (size_t)4 * VP + 4 * NSPLIT_S) return fail(JRR_ERR_INVALID, "flush list overflow");
     if (fidx.size() > (size_t)4 * VP + 4 * NSPLIT_B || fidx_l.size() > (size_t)4 * VP + 4 * 36)
       return fail(JRR_ERR_INVALID, "flush list overflow");
     JRR_CUDA(cudaMemcpy(t.vrec, rec_f.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
@@ -667,7 +673,11 @@ int build_packing(JrrModel* m, const std::vector<uint8_t>& active) {
     JRR_CUDA(cudaMemcpy(t.flush_ptr_l, fptr_l.data(), sizeof(int) * (NJ + 1), cudaMemcpyHostToDevice));
     if (!fidx_l.empty()) JRR_CUDA(cudaMemcpy(t.flush_idx_l, fidx_l.data(), sizeof(int) * fidx_l.size(), cudaMemcpyHostToDevice));
     JRR_CUDA(cudaMemcpy(t.range_flush_base_l, range_base_l.data(), sizeof(int) * 37, cudaMemcpyHostToDevice));
-    m->flush_off[pass + 1] = m->flush_off[pass] + std::max(t.n_flush, t.n_flush_l);
+    JRR_CUDA(cudaMemcpy(t.vrec_s, rec_s.data(), sizeof(VtxRec) * VP, cudaMemcpyHostToDevice));
+    JRR_CUDA(cudaMemcpy(t.flush_ptr_s, fptr_s.data(), sizeof(int) * (NJ + 1), cudaMemcpyHostToDevice));
+    if (!fidx_s.empty()) JRR_CUDA(cudaMemcpy(t.flush_idx_s, fidx_s.data(), sizeof(int) * fidx_s.size(), cudaMemcpyHostToDevice));
+    JRR_CUDA(cudaMemcpy(t.range_flush_base_s, range_base_s.data(), sizeof(int) * (NSPLIT_S + 1), cudaMemcpyHostToDevice));
+    m->flush_off[pass + 1] = m->flush_off[pass] + std::max(std::max(t.n_flush, t.n_flush_l), t.n_flush_s);
   }
   m->select_pass(0);
   const int64_t n = (int64_t)KA * NP;
@@ -859,6 +869,10 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
     if (int rc = dalloc(m, &t.flush_ptr_l, NJ + 1)) return rc;
     if (int rc = dalloc(m, &t.flush_idx_l, (size_t)4 * VP + 4 * 36)) return rc;
     if (int rc = dalloc(m, &t.range_flush_base_l, 37)) return rc;
+    if (int rc = dalloc(m, &t.vrec_s, VP)) return rc;
+    if (int rc = dalloc(m, &t.flush_ptr_s, NJ + 1)) return rc;
+    if (int rc = dalloc(m, &t.flush_idx_s, (size_t)4 * VP + 4 * NSPLIT_S)) return rc;
+    if (int rc = dalloc(m, &t.range_flush_base_s, NSPLIT_S + 1)) return rc;
   }
   m->select_pass(0);
   if (int rc = dalloc(m, &m->active_dev, V)) return rc;

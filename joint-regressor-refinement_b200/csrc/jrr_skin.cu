@@ -1130,12 +1130,14 @@ int launch_skin_bwd(const JrrModel* m, const Workspace& w, const float* dvertice
   return JRR_OK;
 }
 
-int launch_dA_reduce(const JrrModel* m, const Workspace& w, bool loss_path_lists, cudaStream_t st) {
+int launch_dA_reduce(const JrrModel* m, const Workspace& w, int lists, cudaStream_t st) {
   dim3 grid((unsigned)(w.BP / SK_THREADS), NJ), block(SK_THREADS);
   const float* src = w.dAflush + (int64_t)m->flush_off[m->cur_pass] * 12 * w.BP;      // this pass's flush region
   const int acc = m->cur_pass > 0 ? 1 : 0;
-  if (loss_path_lists)
+  if (lists == 1)
     dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr_l, m->flush_idx_l, m->n_flush_l, src, w.BP, w.dAT, acc);
+  else if (lists == 2)
+    dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr_s, m->flush_idx_s, m->n_flush_s, src, w.BP, w.dAT, acc);
   else
     dA_reduce_kernel<<<grid, block, 0, st>>>(m->flush_ptr, m->flush_idx, m->n_flush, src, w.BP, w.dAT, acc);
   JRR_LAUNCH_CHECK();
