@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Workload for an ncu launch list of the drop-in module path: SMPL forward and backward at B = 1, 256, 4096."""
+"""Workload for an ncu launch list of the drop-in module path: SMPL forward and backward at B = 1, 8, 256, 4096."""
 import os
 import sys
 
@@ -12,7 +12,7 @@ dev = torch.device("cuda", 0)
 smpl = jrr.SMPL(model_dict=jrr.synthetic.make_smpl_model(0), create_transl=False).to(dev)
 nat = smpl.native()
 base = jrr.synthetic.make_pose_inputs(4096, 7)
-for B in (4096, 256, 1):
+for B in (4096, 256, 8, 1):
     full = torch.from_numpy(base["true_rotmat"])[:B].reshape(B, 24, 9).to(dev).contiguous()
     b = torch.from_numpy(base["true_betas"])[:B].to(dev).contiguous()
     dv = torch.randn(B, 6890, 3, device=dev)

@@ -197,6 +197,11 @@ extern "C" int jrr_smpl_forward(JrrModel* m, int64_t B, const float* betas, cons
   if (!vertices_out && !joints49_out) return fail(JRR_ERR_INVALID, "no output requested");
   cudaStream_t st = (cudaStream_t)stream;
   static const bool fused_module = [] { const char* e = getenv("JRR_FUSED_MODULE"); return !(e && e[0] == '0'); }();
+  if (smpl_small_fwd_available(m, B)) {
+    // a handful of poses: chain, blend, skinning, vertex store and the 49 joints in ONE launch (warp per vertex)
+    // (joints49 reads the stored vertices: the caller's buffer, else scratch -- dvp_hi is [BP][NP] >= [B][6890][3])
+    return launch_smpl_small_fwd(m, B, betas, pose, kind, vertices_out ? vertices_out : w.dvp_hi, joints49_out, st);
+  }
   if (m->gemm_impl == 0 && m->fused_fwd && fused_module) {
     // chain | blend GEMM with the skinning epilogue over EVERY packed vertex (pose-contiguous store) | un-packing to the
     // model's vertex order with coalesced reads and writes | 49 joints gathered from the packed vertices

@@ -47,7 +47,12 @@ __host__ __device__ inline int fused_cta_of_tile(int t, int T, int G) { return (
 
 enum { FSTORE_NONE = 0, FSTORE_VP = 1, FSTORE_V = 2, FSTORE_V_ADD = 3 /* later skinning passes: added to the stored vertices */ };
 
-template <int STORE>
+// MODE (module path, which walks EVERY packed vertex and has no use for the regressor sums): F_FULL = skinning + 17x6890
+// reduction (loss path); F_SKIN = skinning only (SMPL.forward: the skinned vertices are the output); F_BLEND = neither
+// (the recomputation inside SMPL.backward needs the blended vertices only: the epilogue is a plain store).
+enum { F_FULL = 0, F_SKIN = 1, F_BLEND = 2 };
+
+template <int STORE, int MODE>
 __global__ void __launch_bounds__(F_THREADS, 1)
 fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                  const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
@@ -225,8 +230,8 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
           meta[0] = (meta[0] & ~(0xFu << 20)) | need;
           many = meta[0] | meta[1] | meta[2] | meta[3];
         }
-        const bool any_reload = (many >> 20) & 0xFu;
-        const bool any_col = (many >> 24) & 1u;
+        const bool any_reload = MODE != F_BLEND && ((many >> 20) & 0xFu);
+        const bool any_col = MODE == F_FULL && ((many >> 24) & 1u);
         float v[4][3];
         // ---- skinning.  Fast path: no slot changes inside the group -> branch-free, the four
         // vertices interleave in the instruction stream.
@@ -247,7 +252,9 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
           upk2(v01, v[ii][0], v[ii][1]);                                                            \
           v[ii][2] = v2;                                                                            \
         }
-        if (!any_reload) {
+        if (MODE == F_BLEND) {
+          // (nothing to skin)
+        } else if (!any_reload) {
 #pragma unroll
           for (int ii = 0; ii < 4; ii++) JRR_SKIN_VERTEX(ii)
         } else {
@@ -313,7 +320,12 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       // per-CTA partial sums leave when the pose block changes (or the CTA runs out of tiles)
-      if (!has_next || (t + 1) / n_tiles != mb) {
+      if (MODE != F_FULL) {
+        if (!has_next || (t + 1) / n_tiles != mb) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) cached_joint[k] = -1;
+        }
+      } else if (!has_next || (t + 1) / n_tiles != mb) {
 #pragma unroll
         for (int k = 0; k < 4; k++) cached_joint[k] = -1;   // next tile belongs to other poses
         const int seg = blockIdx.x - fused_cta_of_tile(mb * n_tiles, T, G);
@@ -370,18 +382,24 @@ int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store, float* vT
   // loss path: only the active vertex prefix; module path (all_vertices): every packed vertex
   const int m_tiles = (int)(w.BP / FBM), n_tiles = (all_vertices ? VP : m->nv_act) / FV;
   const int T = m_tiles * n_tiles, G = std::min(T, m->num_sms);
-#define JRR_FF(S)                                                                                   \
+#define JRR_FFM(S, MD)                                                                              \
   do {                                                                                              \
-    auto kern = fused_fwd_kernel<S>;                                                                \
+    auto kern = fused_fwd_kernel<S, MD>;                                                            \
     JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES)); \
     kern<<<G, F_THREADS, F_SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, m->vrec, w.AT, w.BP, m_tiles, n_tiles, \
                                              vT_out, w.part + (int64_t)m->cur_pass * w.part_stride);  \
   } while (0)
-  if (store == FSTORE_NONE) JRR_FF(FSTORE_NONE);
-  else if (store == FSTORE_VP) JRR_FF(FSTORE_VP);
-  else if (store == FSTORE_V) JRR_FF(FSTORE_V);
-  else JRR_FF(FSTORE_V_ADD);
-#undef JRR_FF
+  if (all_vertices) {
+    // module path: no regressor sums; the recomputation of SMPL.backward (blended vertices out) does not skin either
+    if (store == FSTORE_VP) JRR_FFM(FSTORE_VP, F_BLEND);
+    else if (store == FSTORE_V) JRR_FFM(FSTORE_V, F_SKIN);
+    else if (store == FSTORE_V_ADD) JRR_FFM(FSTORE_V_ADD, F_SKIN);
+    else return fail(JRR_ERR_INVALID, "fused forward over every vertex needs an output");
+  } else if (store == FSTORE_NONE) JRR_FFM(FSTORE_NONE, F_FULL);
+  else if (store == FSTORE_VP) JRR_FFM(FSTORE_VP, F_FULL);
+  else if (store == FSTORE_V) JRR_FFM(FSTORE_V, F_FULL);
+  else JRR_FFM(FSTORE_V_ADD, F_FULL);
+#undef JRR_FFM
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }

@@ -177,6 +177,7 @@ struct JrrModel {
   jrr::Csr extra;                            // [9] rows over original vertex ids
   int* picks = nullptr;                      // [21]
   int* joint_map = nullptr;                  // [49]
+  unsigned* small_counter = nullptr;         // block counter of the single-launch small-batch forward (self-resetting)
   // regressor (normalised), refreshed by jrr_set_regressor / jrr_regressor_apply
   float* Jhat = nullptr;                     // [17][V]   original vertex order
   float* rowsum = nullptr;                   // [17]
@@ -341,6 +342,10 @@ int launch_loss_seed(const JrrModel* m, Workspace& w, bool fused_partials, const
                      int64_t B_logical, float w_joint, float* joints17_out, const Proj2D& p2d, cudaStream_t st);
 int launch_camera_fit(const Workspace& w, const float* joints17, const float* gt2d, float* cam, int iters, float lr,
                       int64_t B_logical, float* loss_out, cudaStream_t st);
+// whole module forward of a small batch (<= 32 poses, 4 weights per vertex) in one launch (jrr_pose.cu)
+bool smpl_small_fwd_available(const JrrModel* m, int64_t B);
+int launch_smpl_small_fwd(const JrrModel* m, int64_t B, const float* betas, const float* pose, int kind,
+                          float* vertices, float* joints49, cudaStream_t st);
 // fused blend GEMM + skinning + regressor partial sums (jrr_fused_fwd.cu)
 int fused_fwd_slots(int64_t BP, int num_sms);
 int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store /*0 none, 1 vp, 2 skinned v*/,

@@ -857,6 +857,7 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
   // ---- device buffers of the packing (filled by build_packing; sizes do not depend on the order)
   if (int rc = dalloc(m, &m->perm, VP)) return rc;
   if (int rc = dalloc(m, &m->inv_perm, V)) return rc;
+  if (int rc = dalloc(m, &m->small_counter, 1)) return rc;
   if (m->n_pass > MAX_PASS) return fail(JRR_ERR_INVALID, "more than 24 skinning weights per vertex");
   for (int pass = 0; pass < m->n_pass; pass++) {
     PassTab& t = m->passes[pass];

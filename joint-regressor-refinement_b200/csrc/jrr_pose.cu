@@ -6,6 +6,8 @@
 // smplx.lbs.{batch_rodrigues, vertices2joints, batch_rigid_transform} reached through
 // scripts/smpl.py:72-74, their autograd backward (scripts/optimize.py:264) and
 // torch.optim.Adam.step (scripts/optimize.py:201-202,265).
+#include <cstdlib>
+
 #include "jrr_internal.cuh"
 
 namespace jrr {
@@ -465,6 +467,206 @@ __global__ void adam_coef_kernel(const int32_t* __restrict__ step_count, float l
 
 int launch_adam_coef(const Workspace& w, const int32_t* step_count, float lr, cudaStream_t st) {
   adam_coef_kernel<<<1, 1, 0, st>>>(step_count, lr, w.adam_coef);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
+// ---- small batches: the whole module forward in ONE launch -------------------------------------
+// Up to SMALL_MAX (<= 32: lane = pose when skinning) poses the tensor-core path pads the batch to a 128-row tile and a single epilogue lane skins every
+// vertex of the pose (26 us at one pose) behind three more launches.  Here every block repeats the kinematic chain of the
+// batch (warp per pose, cheap) into shared memory, then WARP = PACKED VERTEX: the lanes stream the vertex's three rows of
+// the augmented blend matrix (K contiguous, hi + lo = the fp32 weights to 2^-22) with 16-byte loads, all twelve of them in
+// flight at once, contract them with the features of four poses at a time, butterfly-reduce, and lanes 0..3 skin the
+// vertex for their pose and store it in the model's vertex order.  The blend matrix is read once per block whatever the
+// batch.  The block that finishes last (device counter, self-resetting) gathers the 49 joints from the stored vertices.
+// Replaces smplx.lbs.lbs + vertex_joint_selector + scripts/smpl.py:75-78 for B <= SMALL_MAX.
+constexpr int SMALL_MAX = 8;        // beyond this the tensor-core path is faster (measured: 44 us at 4 poses, 67 us at 64)
+constexpr int SMALL_WARPS = 8;
+constexpr int SMALL_CHUNK = 4;      // poses contracted per pass over the register-held weights
+
+template <int KIND>
+__global__ void __launch_bounds__(SMALL_WARPS * 32, 2)
+smpl_small_fwd_kernel(const __grid_constant__ ChainTab tab, const float* __restrict__ J0, const float* __restrict__ JS,
+                      const float* __restrict__ betas, const float* __restrict__ pose, int B, int BS /* B rounded up to 4 */,
+                      const float* __restrict__ Pt_hi, const float* __restrict__ Pt_lo, const VtxRec* __restrict__ vrec,
+                      const int* __restrict__ perm, const int* __restrict__ joint_map, const int* __restrict__ picks,
+                      Csr extra, float* __restrict__ vertices, float* __restrict__ joints49, unsigned* __restrict__ counter) {
+  extern __shared__ float small_smem[];
+  float* sA = small_smem;                    // [288][BS]
+  float* sF = sA + NJ * 12 * BS;             // [BS][224]
+  float* sJp = sF + BS * KA;                 // [BS][72]
+  __shared__ int s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const bool tail = lane < (KA - 128) / 4;     // lanes that own a second 16-byte piece of a 224-float row
+  const int gw = blockIdx.x * SMALL_WARPS + warp, GW = gridDim.x * SMALL_WARPS;
+  // the three blend-matrix rows of packed vertex i, this lane's K slice (hi + lo): issued before they are needed
+  float p[3][8];
+  auto load_rows = [&](int i) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const int64_t row = (int64_t)(3 * i + c) * KA;
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(Pt_hi + row) + lane);
+      const float4 l0 = __ldg(reinterpret_cast<const float4*>(Pt_lo + row) + lane);
+      float4 h1 = make_float4(0.f, 0.f, 0.f, 0.f), l1 = h1;
+      if (tail) {
+        h1 = __ldg(reinterpret_cast<const float4*>(Pt_hi + row + 128) + lane);
+        l1 = __ldg(reinterpret_cast<const float4*>(Pt_lo + row + 128) + lane);
+      }
+      p[c][0] = h0.x + l0.x; p[c][1] = h0.y + l0.y; p[c][2] = h0.z + l0.z; p[c][3] = h0.w + l0.w;
+      p[c][4] = h1.x + l1.x; p[c][5] = h1.y + l1.y; p[c][6] = h1.z + l1.z; p[c][7] = h1.w + l1.w;
+    }
+  };
+  if (gw < VP) load_rows(gw);                  // in flight while the chain runs
+
+  // ---- kinematic chain of every pose of the batch (warp per pose, lane = joint)
+  for (int b = warp; b < BS; b += SMALL_WARPS) {
+    const bool valid = b < B;
+    const int j = lane < NJ ? lane : NJ - 1;
+    float beta[NB];
+    for (int l = 0; l < NB; l++) beta[l] = valid ? betas[b * NB + l] : 0.f;
+    float raw[9], R[9], Jr[3], GR[9], Gt[3], GRp[9], rel[3];
+    decode_rot<KIND>(pose, b, j, valid, raw, R);
+    rest_joint(J0, JS, beta, j, Jr);
+    chain_forward(tab, j, R, Jr, GR, Gt, GRp, rel);
+    for (int i = lane; i < KA; i += 32) sF[b * KA + i] = 0.f;
+    __syncwarp();
+    if (lane < NJ) {
+      for (int r = 0; r < 3; r++) {
+        const float t = Gt[r] - (GR[r * 3 + 0] * Jr[0] + GR[r * 3 + 1] * Jr[1] + GR[r * 3 + 2] * Jr[2]);
+        sA[(lane * 12 + r * 4 + 0) * BS + b] = GR[r * 3 + 0];
+        sA[(lane * 12 + r * 4 + 1) * BS + b] = GR[r * 3 + 1];
+        sA[(lane * 12 + r * 4 + 2) * BS + b] = GR[r * 3 + 2];
+        sA[(lane * 12 + r * 4 + 3) * BS + b] = t;
+        sJp[b * 72 + lane * 3 + r] = Gt[r];
+      }
+      if (lane >= 1)
+        for (int i = 0; i < 9; i++) sF[b * KA + (lane - 1) * 9 + i] = R[i] - ((i % 4 == 0) ? 1.f : 0.f);
+    }
+    if (lane < NB) sF[b * KA + FEAT_BETA + lane] = beta[lane];
+    if (lane == 0) sF[b * KA + FEAT_ONE] = 1.f;
+  }
+  __syncthreads();
+
+  // ---- warp = packed vertex
+  for (int i = gw; i < VP; i += GW) {
+    if (i != gw) load_rows(i);
+    const int vid = perm[i];
+    if (vid < 0) continue;                     // padding (warp-uniform)
+    const VtxRec* rec = vrec + i;
+    const uint32_t meta = __ldg(&rec->meta);
+    float wk[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) wk[k] = __ldg(&rec->w[k]);
+
+    // blended vertex of pose b lands in lane b
+    float x = 0.f, y = 0.f, z = 0.f;
+    for (int b0 = 0; b0 < BS; b0 += SMALL_CHUNK) {
+      float acc[SMALL_CHUNK][3];
+#pragma unroll
+      for (int bb = 0; bb < SMALL_CHUNK; bb++) {
+        const float4 f0 = *reinterpret_cast<const float4*>(sF + (b0 + bb) * KA + 4 * lane);
+        float4 f1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tail) f1 = *reinterpret_cast<const float4*>(sF + (b0 + bb) * KA + 128 + 4 * lane);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          float a = p[c][0] * f0.x;
+          a = fmaf(p[c][1], f0.y, a); a = fmaf(p[c][2], f0.z, a); a = fmaf(p[c][3], f0.w, a);
+          a = fmaf(p[c][4], f1.x, a); a = fmaf(p[c][5], f1.y, a); a = fmaf(p[c][6], f1.z, a); a = fmaf(p[c][7], f1.w, a);
+          acc[bb][c] = a;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int bb = 0; bb < SMALL_CHUNK; bb++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) acc[bb][c] += __shfl_xor_sync(FULL, acc[bb][c], o);
+#pragma unroll
+      for (int bb = 0; bb < SMALL_CHUNK; bb++)
+        if (lane == b0 + bb) { x = acc[bb][0]; y = acc[bb][1]; z = acc[bb][2]; }
+    }
+    if (lane < B) {
+      const int b = lane;
+      float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float* a = sA + (int)((meta >> (5 * k)) & 31u) * 12 * BS + b;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          const float yk = fmaf(a[(r * 4 + 2) * BS], z, fmaf(a[(r * 4 + 1) * BS], y, fmaf(a[(r * 4 + 0) * BS], x, a[(r * 4 + 3) * BS])));
+          v[r] = fmaf(wk[k], yk, v[r]);
+        }
+      }
+      float* dst = vertices + ((int64_t)b * V + vid) * 3;
+      dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2];
+    }
+  }
+  if (joints49 == nullptr) return;
+
+  // ---- the block that finishes last gathers the 49 joints (24 posed joints, 21 vertex picks, 9 extra-regressor rows)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // posed joints and vertex picks: one thread per (pose, joint), every dependent load chain in flight at once
+  for (int t = threadIdx.x; t < B * JRR_NUM_OUT_JOINTS; t += SMALL_WARPS * 32) {
+    const int b = t / JRR_NUM_OUT_JOINTS, src = joint_map[t % JRR_NUM_OUT_JOINTS];
+    if (src >= NJ + JRR_NUM_PICKS) continue;
+    float* dst = joints49 + (int64_t)t * 3;
+    if (src < NJ) {
+      for (int c = 0; c < 3; c++) dst[c] = sJp[b * 72 + src * 3 + c];
+    } else {
+      const float* vsrc = vertices + ((int64_t)b * V + picks[src - NJ]) * 3;
+      for (int c = 0; c < 3; c++) dst[c] = __ldcg(vsrc + c);
+    }
+  }
+  // extra-regressor rows: one warp per (pose, row), lanes stride the row's non-zeros, fixed-order butterfly
+  for (int task = warp; task < B * JRR_NUM_OUT_JOINTS; task += SMALL_WARPS) {
+    const int b = task / JRR_NUM_OUT_JOINTS, src = joint_map[task % JRR_NUM_OUT_JOINTS];
+    if (src < NJ + JRR_NUM_PICKS) continue;
+    const int e = src - NJ - JRR_NUM_PICKS;
+    const float* vb = vertices + (int64_t)b * V * 3;
+    float out[3] = {0.f, 0.f, 0.f};
+    for (int q = extra.ptr[e] + lane; q < extra.ptr[e + 1]; q += 32) {
+      const int v = extra.col[q];
+      const float cf = extra.val[q];
+      for (int c = 0; c < 3; c++) out[c] = fmaf(cf, __ldcg(vb + v * 3 + c), out[c]);
+    }
+    for (int sft = 16; sft > 0; sft >>= 1)
+      for (int c = 0; c < 3; c++) out[c] += __shfl_xor_sync(FULL, out[c], sft);
+    if (lane < 3) joints49[(int64_t)task * 3 + lane] = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+bool smpl_small_fwd_available(const JrrModel* m, int64_t B) {
+  static const bool on = [] { const char* e = getenv("JRR_SMALL_FWD"); return !(e && e[0] == '0'); }();
+  return on && B <= SMALL_MAX && m->n_pass == 1 && m->gemm_impl == 0 && m->small_counter != nullptr;
+}
+
+int launch_smpl_small_fwd(const JrrModel* m, int64_t B, const float* betas, const float* pose, int kind,
+                          float* vertices, float* joints49, cudaStream_t st) {
+  const int BS = (int)round_up(B, SMALL_CHUNK);
+  const size_t smem = (size_t)(NJ * 12 * BS + BS * KA + BS * 72) * sizeof(float);
+  const int grid = 2 * m->num_sms;
+#define JRR_SF(KIND)                                                                                               \
+  do {                                                                                                             \
+    auto kern = smpl_small_fwd_kernel<KIND>;                                                                       \
+    JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+    kern<<<grid, SMALL_WARPS * 32, smem, st>>>(m->chain, m->J0, m->JS, betas, pose, (int)B, BS, m->Pt_hi, m->Pt_lo, \
+                                               m->passes[0].vrec, m->perm, m->joint_map, m->picks, m->extra, vertices, \
+                                               joints49, m->small_counter);                                       \
+  } while (0)
+  switch (kind) {
+    case JRR_POSE_ROTMAT: JRR_SF(JRR_POSE_ROTMAT); break;
+    case JRR_POSE_AXIS_ANGLE: JRR_SF(JRR_POSE_AXIS_ANGLE); break;
+    case JRR_POSE_ROT6D: JRR_SF(JRR_POSE_ROT6D); break;
+    default: return fail(JRR_ERR_INVALID, "unknown pose kind");
+  }
+#undef JRR_SF
   JRR_LAUNCH_CHECK();
   return JRR_OK;
 }

@@ -124,6 +124,36 @@ def test_smpl_ragged_batch_and_beta_broadcast(smpl_tc, osmpl32, jrr):
     assert rel(out.vertices, ref.vertices) < 1e-5 and rel(out.joints, ref.joints) < 1e-5
 
 
+@pytest.mark.parametrize("B", [1, 3, 4, 5, 8, 9])
+def test_smpl_small_batch_single_launch_forward(B, smpl_tc, osmpl64, jrr):
+    """Up to 8 poses SMPL.forward is ONE launch (warp per vertex, csrc/jrr_pose.cu smpl_small_fwd_kernel); 9 poses take
+    the tensor-core path.  All three rotation formats, vertices + 49 joints vs the fp64 oracle, joints-only calls, and a
+    second call (the device counter that elects the joint-gathering block resets itself)."""
+    inp = jrr.synthetic.make_pose_inputs(64, 21)
+    R = torch.from_numpy(inp["true_rotmat"][:B])
+    betas = torch.from_numpy(inp["true_betas"][:B])
+    nat = smpl_tc.native()
+    ref = osmpl64(betas=betas.double(), body_pose=R[:, 1:].double(), global_orient=R[:, :1].double(), pose2rot=False)
+    for rep_ in range(2):
+        out = smpl_tc(betas=betas.to(DEV), body_pose=R[:, 1:].to(DEV), global_orient=R[:, :1].to(DEV), pose2rot=False)
+        assert nat.launches == (1 if B <= 8 else 4), nat.launches
+        ev, ej = rel(out.vertices, ref.vertices), rel(out.joints, ref.joints)
+        assert ev < 1e-5 and ej < 1e-5, (ev, ej)
+    print(f"[small forward B={B}] vertices rel {ev:.2e} joints rel {ej:.2e} launches {nat.launches}")
+    # joints only (no vertex buffer from the caller), rot6d input
+    x6 = torch.from_numpy(inp["x6"][:B])
+    R6 = jrr.rot6d_to_rotmat(x6.reshape(-1, 6)).reshape(B, 24, 3, 3)
+    ref6 = osmpl64(betas=betas.double(), body_pose=R6[:, 1:].double(), global_orient=R6[:, :1].double(), pose2rot=False)
+    _, j6 = nat.smpl_forward(betas.to(DEV), x6.to(DEV).reshape(B, 24, 6), 2, False, True)
+    assert rel(j6, ref6.joints) < 1e-5
+    # axis-angle
+    g = torch.Generator().manual_seed(5)
+    go, bp = torch.randn(B, 3, generator=g), 0.3 * torch.randn(B, 69, generator=g)
+    refa = osmpl64(betas=betas.double(), global_orient=go.double(), body_pose=bp.double(), pose2rot=True)
+    outa = smpl_tc(betas=betas.to(DEV), global_orient=go.to(DEV), body_pose=bp.to(DEV), pose2rot=True)
+    assert rel(outa.vertices, refa.vertices) < 1e-5 and rel(outa.joints, refa.joints) < 1e-5
+
+
 # ------------------------------------------------------------------ SMPL backward
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("pose2rot", [False, True])
