@@ -25,7 +25,7 @@ Workspace carve(const JrrModel* m, int64_t B, void* base) {
   w.feat_hi = take(BP * KA);
   w.feat_lo = take(BP * KA);
   w.vpT = take((size_t)NP * BP);
-  w.part_stride = (int64_t)std::max(NSPLIT, fused_fwd_slots(w.BP, m->num_sms)) * NACC * (int64_t)BP;
+  w.part_stride = (int64_t)std::max(NSPLIT, fused_fwd_slots(m, w.BP)) * NACC * (int64_t)BP;
   w.part = take((size_t)w.part_stride * m->n_pass);
   w.gT = take(NACC * BP);
   w.pred = take(BP * NACC);

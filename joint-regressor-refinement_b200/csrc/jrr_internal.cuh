@@ -347,7 +347,9 @@ bool smpl_small_fwd_available(const JrrModel* m, int64_t B);
 int launch_smpl_small_fwd(const JrrModel* m, int64_t B, const float* betas, const float* pose, int kind,
                           float* vertices, float* joints49, cudaStream_t st);
 // fused blend GEMM + skinning + regressor partial sums (jrr_fused_fwd.cu)
-int fused_fwd_slots(int64_t BP, int num_sms);
+struct FusedSched { int n_tiles, T, G, mdiv; };   // see jrr_fused_fwd.cu
+FusedSched fused_fwd_sched(const JrrModel* m, int64_t BP, int nv);
+int fused_fwd_slots(const JrrModel* m, int64_t BP);
 int launch_fused_fwd(const JrrModel* m, const Workspace& w, int store /*0 none, 1 vp, 2 skinned v*/,
                      float* vT_out, cudaStream_t st, bool all_vertices = false);
 // packed pose-contiguous vertices vT [3*VP][BP] -> natural order [B][6890][3] (module path)

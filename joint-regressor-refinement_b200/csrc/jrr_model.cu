@@ -369,7 +369,7 @@ int regressor_accumulate_folded(const JrrModel* m, Workspace& w, const float* gt
 
 // --------------------------------------------------------------------- folded loss-path operator
 // T[(j,i,c)][k] = sum_v Jhat_iv w_vj P[3v+c][k],  c_ji = sum_v Jhat_iv w_vj   (see folded_seed_kernel).
-// grid (17 regressor rows, 4 = three coordinates + the homogeneous one, FOLD_CH vertex chunks), thread = k;
+// grid (17 regressor rows in groups of FOLD_R, 4 = three coordinates + the homogeneous one, FOLD_CH vertex chunks), thread = k;
 // double accumulators in shared memory, fixed summation order (chunk partials reduced in order).
 constexpr int FOLD_CH = VP / VS_F;          // 12 chunks = the forward record ranges (a range start reloads all four slots)
 
@@ -384,65 +384,97 @@ __global__ void fold_prep_kernel(const VtxRec* __restrict__ vrec, double* __rest
   for (int s4 = 0; s4 < 4; s4++) wj[(int64_t)idx * 4 + s4] = (double)vrec[p].w[s4] * jh;
 }
 
+constexpr int FOLD_R = 3;                   // regressor rows per CTA: the blend-matrix rows are read 6 times instead of 17
+constexpr int FOLD_SMEM = FOLD_R * NJ * KA * (int)sizeof(double);   // 129 KB
+
 __global__ void __launch_bounds__(KA)
 fold_kernel(const VtxRec* __restrict__ vrec, const double* __restrict__ wj, const float* __restrict__ Pt_hi,
             const float* __restrict__ Pt_lo, double* __restrict__ part, int accumulate) {
   // Packed vertices are sorted by joint set, so a record slot keeps its joint over long runs: each thread keeps the four
-  // slots' running sums in REGISTERS (four independent double chains) and adds them to the per-joint shared-memory
+  // slots' running sums in REGISTERS (independent double chains) and adds them to the per-joint shared-memory
   // accumulators only when a slot's joint changes (the records' reload bits: ~190 times over the whole model) -- the
   // first version updated the shared accumulators for every (vertex, slot), one dependent shared-memory round trip each
   // (0.46 ms).  Same fp64 arithmetic; groups of four vertices without a slot change take a branch-free path.
-  __shared__ double acc[NJ * KA];
-  const int i = blockIdx.x, c = blockIdx.y, ch = blockIdx.z, k = threadIdx.x;
-  for (int e = k; e < NJ * KA; e += KA) acc[e] = 0.0;
+  // A CTA folds FOLD_R regressor rows at once (the kernel was bound by re-reading the blend matrix from L2 once per row:
+  // 17 x 37 MB per fold, 0.27 ms).
+  extern __shared__ double fold_acc[];          // [FOLD_R][NJ * KA]
+  const int i0 = blockIdx.x * FOLD_R, c = blockIdx.y, ch = blockIdx.z, k = threadIdx.x;
+  for (int e = k; e < FOLD_R * NJ * KA; e += KA) fold_acc[e] = 0.0;
   __syncthreads();                 // (each thread only ever touches column k, the barrier is for the zeroing loop)
-  double run[4] = {0.0, 0.0, 0.0, 0.0};
+  double run[FOLD_R][4];
+#pragma unroll
+  for (int r = 0; r < FOLD_R; r++)
+#pragma unroll
+    for (int s4 = 0; s4 < 4; s4++) run[r][s4] = 0.0;
   int jcur[4] = {0, 0, 0, 0};
   const int p0 = ch * VS_F;
-  const double2* wj2 = reinterpret_cast<const double2*>(wj + ((int64_t)i * VP + p0) * 4);
+  const double2* wj2[FOLD_R];
+#pragma unroll
+  for (int r = 0; r < FOLD_R; r++)
+    wj2[r] = reinterpret_cast<const double2*>(wj + ((int64_t)min(i0 + r, NH - 1) * VP + p0) * 4);
 #pragma unroll 1
   for (int q0 = 0; q0 < VS_F; q0 += 4) {
     uint32_t meta[4], many = 0;
     double p[4];
-    double2 wa[4], wb[4];
+    double2 wa[FOLD_R][4], wb[FOLD_R][4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {       // four vertices' loads in flight together
       const int pi = p0 + q0 + u;
       meta[u] = vrec[pi].meta;
       many |= meta[u];
-      wa[u] = __ldg(wj2 + (q0 + u) * 2);
-      wb[u] = __ldg(wj2 + (q0 + u) * 2 + 1);
+#pragma unroll
+      for (int r = 0; r < FOLD_R; r++) {
+        wa[r][u] = __ldg(wj2[r] + (q0 + u) * 2);
+        wb[r][u] = __ldg(wj2[r] + (q0 + u) * 2 + 1);
+      }
       if (c < 3) p[u] = (double)__ldg(Pt_hi + (int64_t)(3 * pi + c) * KA + k) + (double)__ldg(Pt_lo + (int64_t)(3 * pi + c) * KA + k);
       else p[u] = k == 0 ? 1.0 : 0.0;
     }
     if (!((many >> 20) & 0xFu)) {       // no slot changes inside the group (uniform)
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        run[0] = fma(wa[u].x, p[u], run[0]);
-        run[1] = fma(wa[u].y, p[u], run[1]);
-        run[2] = fma(wb[u].x, p[u], run[2]);
-        run[3] = fma(wb[u].y, p[u], run[3]);
-      }
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int r = 0; r < FOLD_R; r++) {
+          run[r][0] = fma(wa[r][u].x, p[u], run[r][0]);
+          run[r][1] = fma(wa[r][u].y, p[u], run[r][1]);
+          run[r][2] = fma(wb[r][u].x, p[u], run[r][2]);
+          run[r][3] = fma(wb[r][u].y, p[u], run[r][3]);
+        }
     } else {
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const double wv[4] = {wa[u].x, wa[u].y, wb[u].x, wb[u].y};
 #pragma unroll
         for (int s4 = 0; s4 < 4; s4++) {
           if ((meta[u] >> (20 + s4)) & 1u) {          // the slot changes its joint before this vertex (uniform)
-            acc[jcur[s4] * KA + k] += run[s4];
-            run[s4] = 0.0;
+#pragma unroll
+            for (int r = 0; r < FOLD_R; r++) {
+              fold_acc[(r * NJ + jcur[s4]) * KA + k] += run[r][s4];
+              run[r][s4] = 0.0;
+            }
             jcur[s4] = (meta[u] >> (5 * s4)) & 31u;
           }
-          run[s4] = fma(wv[s4], p[u], run[s4]);
+        }
+#pragma unroll
+        for (int r = 0; r < FOLD_R; r++) {
+          run[r][0] = fma(wa[r][u].x, p[u], run[r][0]);
+          run[r][1] = fma(wa[r][u].y, p[u], run[r][1]);
+          run[r][2] = fma(wb[r][u].x, p[u], run[r][2]);
+          run[r][3] = fma(wb[r][u].y, p[u], run[r][3]);
         }
       }
     }
   }
 #pragma unroll
-  for (int s4 = 0; s4 < 4; s4++) acc[jcur[s4] * KA + k] += run[s4];
-  double* out = part + ((int64_t)(ch * NH + i) * 4 + c) * (NJ * KA);
-  for (int j = 0; j < NJ; j++) out[j * KA + k] = accumulate ? out[j * KA + k] + acc[j * KA + k] : acc[j * KA + k];
+  for (int r = 0; r < FOLD_R; r++)
+#pragma unroll
+    for (int s4 = 0; s4 < 4; s4++) fold_acc[(r * NJ + jcur[s4]) * KA + k] += run[r][s4];
+#pragma unroll
+  for (int r = 0; r < FOLD_R; r++) {
+    if (i0 + r >= NH) break;
+    double* out = part + ((int64_t)(ch * NH + i0 + r) * 4 + c) * (NJ * KA);
+    for (int j = 0; j < NJ; j++)
+      out[j * KA + k] = accumulate ? out[j * KA + k] + fold_acc[(r * NJ + j) * KA + k] : fold_acc[(r * NJ + j) * KA + k];
+  }
 }
 
 __global__ void fold_finish_kernel(const double* __restrict__ part, float* __restrict__ T_hi, float* __restrict__ T_lo,
@@ -486,7 +518,8 @@ int launch_fold(JrrModel* m, cudaStream_t st) {
     const PassTab& t = m->passes[pass];
     fold_prep_kernel<<<(NH * VP + 255) / 256, 256, 0, st>>>(t.vrec, m->fold_wj);
     JRR_LAUNCH_CHECK();
-    fold_kernel<<<dim3(NH, 4, FOLD_CH), KA, 0, st>>>(t.vrec, m->fold_wj, m->Pt_hi, m->Pt_lo, m->fold_part, pass > 0 ? 1 : 0);
+    JRR_CUDA(cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FOLD_SMEM));
+    fold_kernel<<<dim3((NH + FOLD_R - 1) / FOLD_R, 4, FOLD_CH), KA, FOLD_SMEM, st>>>(t.vrec, m->fold_wj, m->Pt_hi, m->Pt_lo, m->fold_part, pass > 0 ? 1 : 0);
     JRR_LAUNCH_CHECK();
   }
   const int64_t n = (int64_t)FOLD_N * KA + NJ * NH;

@@ -228,7 +228,7 @@ __device__ __forceinline__ void adam_update3(float T[3], const float dT[3], floa
 // PPB poses per CTA: 32 (more CTAs in flight; the kernel is latency-bound on the partial-slot loads) or 128
 template <int PPB>
 __global__ void __launch_bounds__(LS_THREADS)
-loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T, int G,
+loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T, int G, int mdiv,
                  const float* __restrict__ gt_mm, int64_t B, int64_t BP, float scale,
                  float* __restrict__ gT, float* __restrict__ joints17_out, float* __restrict__ loss_part,
                  const Proj2D p2d, int n_pass, int64_t pass_stride) {
@@ -239,7 +239,7 @@ loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T,
   const int64_t b0 = (int64_t)blockIdx.x * PPB;
   if (nslots <= 0) {
     // partials written by the fused forward kernel: two per CTA segment of this pose block
-    const int mb = (int)(b0 / 128);      // the fused forward's 128-pose block
+    const int mb = (int)(b0 / 128) / mdiv;      // the fused forward's tile row: a 128-pose block, or a CTA pair's two
     const int c0 = (int)(((int64_t)mb * n_tiles * G) / T);
     const int c1 = (int)((((int64_t)(mb + 1) * n_tiles - 1) * G) / T);
     nslots = 2 * (c1 - c0 + 1);
@@ -1093,13 +1093,14 @@ int launch_loss_seed(const JrrModel* m, Workspace& w, bool fused_partials, const
   w.n_joint_part = (int)(w.BP / ppb);
   dim3 grid((unsigned)(w.BP / ppb)), block(LS_THREADS);
   const float scale = gt_mm != nullptr ? w_joint * 2.f / (51.f * (float)B_logical) : 0.f;
-  const int n_tiles = m->nv_act / 64, T = (int)(w.BP / 128) * n_tiles, G = T < m->num_sms ? T : m->num_sms;
+  const FusedSched sc = fused_fwd_sched(m, w.BP, m->nv_act);
+  const int n_tiles = sc.n_tiles, T = sc.T, G = sc.G;
   if (ppb == 32)
-    loss_seed_kernel<32><<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, gt_mm, w.B, w.BP, scale,
+    loss_seed_kernel<32><<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, sc.mdiv, gt_mm, w.B, w.BP, scale,
                                                  gt_mm != nullptr ? w.gT : nullptr, joints17_out, w.loss_part, p2d,
                                                  fused_partials ? m->n_pass : 1, w.part_stride);
   else
-    loss_seed_kernel<128><<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, gt_mm, w.B, w.BP, scale,
+    loss_seed_kernel<128><<<grid, block, 0, st>>>(w.part, fused_partials ? 0 : NSPLIT, n_tiles, T, G, sc.mdiv, gt_mm, w.B, w.BP, scale,
                                                   gt_mm != nullptr ? w.gT : nullptr, joints17_out, w.loss_part, p2d,
                                                   fused_partials ? m->n_pass : 1, w.part_stride);
   JRR_LAUNCH_CHECK();

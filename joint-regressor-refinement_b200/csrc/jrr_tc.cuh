@@ -178,6 +178,17 @@ __device__ __forceinline__ void tc_mma_tf32_ts_pair(uint32_t d_tmem, uint32_t a_
       "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ... both operands from shared memory: A = 128 rows per CTA, B = N/2 rows per CTA, same descriptor offsets in both CTAs
+__device__ __forceinline__ void tc_mma_tf32_ss_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // 32 consecutive 32-bit columns of this thread's TMEM lane <- registers
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const float v[32]) {
   asm volatile(
