@@ -226,6 +226,37 @@ int jrr_shape_critic_apply(JrrModel* model, float* params, const float* G, float
 int jrr_evaluate(int64_t B, const float* pred_j3d, const float* target_j3d_mm, float* out_mm,
                  float* per_frame_mm, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Gradients of loss terms computed OUTSIDE jrr_refine_step / jrr_refine_step_2d -- the silhouette term of
+ * optimize.py:234-236,252-253, i.e. jrr_silhouette_backward chained through jrr_smpl_backward(kind = ROT6D) -- are added to
+ * the step's own parameter gradients before the Adam update (optimize.py:252-253,263-265: one optimiser step on the sum of
+ * the terms).  dx6 [B,24,6], dbetas [B,10], dcam [B,3] (used by jrr_refine_step_2d only); any may be NULL; the pointers are
+ * read by every later step until cleared with three NULLs.  8-byte aligned. */
+int jrr_set_external_gradient(JrrModel* model, const float* dx6, const float* dbetas, const float* dcam);
+
+/* --- widening row "silhouette term"  ------------------------------------------
+ * replaces: Mesh_Renderer.forward (scripts/mesh_renderer.py:23-79: pytorch3d 0.3.0 MeshRasterizer(blur_radius=0,
+ * faces_per_pixel=1) + SoftSilhouetteShader(sigma=1e-4) behind PerspectiveCameras(T=cam, focal_length=5000/image_size)),
+ * render_mesh (scripts/optimize.py:77-85: x, y flipped and the vertices scaled by 2 inside) and the MSELoss against the
+ * Mask R-CNN silhouette (optimize.py:234-236), with its backward to the vertices and the camera translation.
+ * vertices [B,V,3]: with flip_scale != 0 the body model's output (render_mesh's x, y flip and scale by 2 happen inside),
+ * with flip_scale == 0 a ready mesh (what Mesh_Renderer.forward receives); cam [B,3]; faces [F,3] int32;
+ * alpha_out [B,S,S] (channel 3 of the reference's [B,4,S,S] image; row 0 = top), pix_to_face_out [B,S,S] (-1 = background).
+ * target [B,S,S] + loss_out DEVICE float[1] (optional, together): mean((alpha - target)^2) over B_logical*S*S elements.
+ * The backward takes either d loss / d alpha (dalpha) or, with dalpha == NULL, the MSE target (gradient of
+ * loss_weight * that mean); it reads the projected vertices the forward left in the workspace, so it must follow the
+ * forward of the same inputs on the same workspace (one backward per forward: it reuses that buffer).  vert_face_ptr [V+1] / vert_face_idx: CSR vertex -> (face*3 + corner).
+ * dcam_out [B,3] may be NULL.  All pointers DEVICE. */
+size_t jrr_silhouette_workspace_bytes(int64_t B, int64_t V, int64_t F, int image_size);
+int jrr_silhouette_forward(int64_t B, const float* vertices, int64_t V, const float* cam, const int32_t* faces, int64_t F,
+                           int image_size, float focal, float sigma, int flip_scale, const float* target, int64_t B_logical,
+                           float* alpha_out, int32_t* pix_to_face_out, float* loss_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int jrr_silhouette_backward(int64_t B, const float* vertices, int64_t V, const float* cam, const int32_t* faces, int64_t F,
+                            const int32_t* vert_face_ptr, const int32_t* vert_face_idx, int image_size, float focal,
+                            float sigma, int flip_scale, const float* alpha, const int32_t* pix_to_face, const float* dalpha,
+                            const float* target, int64_t B_logical, float loss_weight, float* dvertices_out,
+                            float* dcam_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* replaces: the forward/backward half of the regressor refit, optimize.py:300-309
  * (find_joints on detached refined poses, move_pelvis + MSELoss, backward to J_regressor).
  * Accumulates G += dL/dJhat (17x6890, gradient w.r.t. the NORMALISED regressor) and

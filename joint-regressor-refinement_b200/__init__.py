@@ -12,3 +12,4 @@ from .utils import evaluate, find_j_reg_mask, find_joints, move_pelvis, rot6d_to
 from .optimize import RefinementLoop  # noqa: F401
 from .data import data_set, write_precomputed  # noqa: F401
 from . import data  # noqa: F401
+from .mesh_renderer import Mesh_Renderer, SilhouetteFunction, load_obj_faces, render_mesh, silhouette_mse  # noqa: F401

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjrr.so")
 SOURCES = ["jrr_model.cu", "jrr_api.cu", "jrr_pose.cu", "jrr_skin.cu", "jrr_critic.cu", "jrr_critic_train.cu",
-           "jrr_gemm_simt.cu", "jrr_gemm_tc.cu", "jrr_fused_fwd.cu", "jrr_fused_bwd.cu", "jrr_eval.cu", "jrr_probe.cu"]
+           "jrr_gemm_simt.cu", "jrr_gemm_tc.cu", "jrr_fused_fwd.cu", "jrr_fused_bwd.cu", "jrr_eval.cu", "jrr_probe.cu", "jrr_silhouette.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -20,7 +20,7 @@ EXPORTS = [
     "jrr_debug_gemm", "jrr_refine_step_profiled", "jrr_step_kernel_name", "jrr_camera_fit", "jrr_refine_step_2d", "jrr_evaluate",
     "jrr_shape_critic_load", "jrr_shape_critic_forward", "jrr_critic_grad_accumulate", "jrr_critic_apply",
     "jrr_shape_critic_grad_accumulate", "jrr_shape_critic_apply", "jrr_set_loss_path", "jrr_debug_tma_probe", "jrr_debug_set_gemm_prof",
-    "jrr_critic_layer2_bwd_products",
+    "jrr_critic_layer2_bwd_products", "jrr_silhouette_workspace_bytes", "jrr_silhouette_forward", "jrr_silhouette_backward", "jrr_set_external_gradient",
 ]
 
 
@@ -80,6 +80,12 @@ def lib():
     L.jrr_camera_fit.argtypes = [vp, i64, i64, vp, vp, vp, vp, C.c_int, f32, vp, vp, sz, vp]
     L.jrr_refine_step_2d.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, sz, vp]
     L.jrr_evaluate.argtypes = [i64, vp, vp, vp, vp, vp, sz, vp]
+    L.jrr_set_external_gradient.argtypes = [vp, vp, vp, vp]
+    L.jrr_silhouette_workspace_bytes.argtypes = [i64, i64, i64, C.c_int]
+    L.jrr_silhouette_workspace_bytes.restype = sz
+    L.jrr_silhouette_forward.argtypes = [i64, vp, i64, vp, vp, i64, C.c_int, f32, f32, C.c_int, vp, i64, vp, vp, vp, vp, sz, vp]
+    L.jrr_silhouette_backward.argtypes = [i64, vp, i64, vp, vp, i64, vp, vp, C.c_int, f32, f32, C.c_int, vp, vp, vp, vp, i64, f32,
+                                          vp, vp, vp, sz, vp]
     L.jrr_debug_gemm.argtypes = [vp, C.c_int, i64, i64, i64, vp, vp, vp, vp, vp]
     L.jrr_debug_set_gemm_prof.argtypes = [vp, C.c_int]
     L.jrr_debug_tma_probe.argtypes = [vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]

@@ -438,7 +438,9 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   JRR_MARK();
   // With the critic on its own branch, the chain backward does not have to wait for it: it leaves the
   // parameter gradients in the workspace and an element-wise Adam kernel runs after the join.
-  const bool split = fork && m->split_adam;
+  // (external gradients -- jrr_set_external_gradient -- are added by the element-wise Adam kernel, whatever the branches)
+  const bool ext = m->ext_dx6 != nullptr || m->ext_dbetas != nullptr;
+  const bool split = (fork && m->split_adam) || ext;
   if (split && !(dbg_skip & 1))
     if (int rc = launch_pose_bwd(m, w, betas, x6, JRR_POSE_ROT6D, false, false, false, w.gbetas, w.gx6, nullptr, nullptr,
                                  nullptr, nullptr, nullptr, 0.f, st)) return rc;
@@ -446,7 +448,7 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   // seed kernel's partials, ev_seed) beside the Adam kernel, and the step ends when both have.
   // (round 2, K = 100, two runs each: 0.2866 / 0.2873 ms against 0.2902 / 0.2900 ms inline; JRR_FINISH_ASIDE=0 switches it off)
   static const bool aside_on = [] { const char* e = getenv("JRR_FINISH_ASIDE"); return !(e && e[0] == '0'); }();
-  const bool finish_aside = aside_on && split && loss_out != nullptr;
+  const bool finish_aside = aside_on && fork && m->split_adam && loss_out != nullptr;
   if (finish_aside) {
     JRR_CUDA(cudaStreamWaitEvent(m->side, m->ev_seed, 0));
     if (int rc = launch_loss_finish(w, B_logical, w_joint, w_pose, critic, w_2d, shape ? m->w_shape : 0.f, loss_out, nullptr, m->side)) return rc;
@@ -458,12 +460,21 @@ static int refine_step_impl(JrrModel* m, int64_t B, int64_t B_logical, float* x6
   JRR_MARK();
   // chain backward + Adam
   if (split) {
-    if (int rc = launch_adam_params(w, critic, shape, x6, betas, adam_m, adam_v, step_count, lr, st)) return rc;
+    if (int rc = launch_adam_params(w, critic, shape, x6, betas, adam_m, adam_v, step_count, lr, st, m->ext_dx6, m->ext_dbetas)) return rc;
     if (finish_aside) JRR_CUDA(cudaStreamWaitEvent(st, m->ev_join2, 0));
   } else if (int rc = launch_pose_bwd(m, w, betas, x6, JRR_POSE_ROT6D, false, critic, shape, nullptr, nullptr, x6, betas,
                                       adam_m, adam_v, step_count, lr, st)) return rc;
   JRR_MARK();
 #undef JRR_MARK
+  return JRR_OK;
+}
+
+extern "C" int jrr_set_external_gradient(JrrModel* m, const float* dx6, const float* dbetas, const float* dcam) {
+  if (!m) return fail(JRR_ERR_INVALID, "null model");
+  if (((uintptr_t)dx6 | (uintptr_t)dbetas) & 7) return fail(JRR_ERR_INVALID, "external gradients must be 8-byte aligned");
+  m->ext_dx6 = dx6;
+  m->ext_dbetas = dbetas;
+  m->ext_dcam = dcam;
   return JRR_OK;
 }
 
@@ -484,6 +495,7 @@ extern "C" int jrr_refine_step_2d(JrrModel* m, int64_t B, int64_t B_logical, flo
   p2d.gt2d = gt_j2d; p2d.cam = cam; p2d.cam_m = cam_adam_m; p2d.cam_v = cam_adam_v;
   p2d.step_count = step_count; p2d.lr = lr;
   p2d.scale = w_2d * 2.f / (34.f * (float)B_logical);
+  p2d.dcam_ext = m ? m->ext_dcam : nullptr;
   return refine_step_impl(m, B, B_logical, x6, betas, gt_mm, adam_m, adam_v, step_count, lr, w_joint, w_pose,
                           loss_out, ws, ws_bytes, (cudaStream_t)stream, nullptr, p2d, w_2d);
 }

@@ -177,6 +177,9 @@ struct JrrModel {
   jrr::Csr extra;                            // [9] rows over original vertex ids
   int* picks = nullptr;                      // [21]
   int* joint_map = nullptr;                  // [49]
+  // gradients of loss terms computed OUTSIDE the refinement step (the silhouette term: rasteriser + module backward), added
+  // to the step's own parameter gradients before Adam (jrr_set_external_gradient; NULL = none)
+  const float *ext_dx6 = nullptr, *ext_dbetas = nullptr, *ext_dcam = nullptr;
   unsigned* small_counter = nullptr;         // block counter of the single-launch small-batch forward (self-resetting)
   // regressor (normalised), refreshed by jrr_set_regressor / jrr_regressor_apply
   float* Jhat = nullptr;                     // [17][V]   original vertex order
@@ -326,6 +329,7 @@ struct Proj2D {
   const int32_t* step_count = nullptr;
   float lr = 0.f;
   float scale = 0.f;             // w_2d * 2 / (34 * B_logical)
+  const float* dcam_ext = nullptr;   // [B,3] camera gradient of an external loss term, added before the camera's Adam step
 };
 int launch_folded_seed(const JrrModel* m, Workspace& w, const float* gt_mm, int64_t B_logical, float w_joint,
                        float* joints17_out, const Proj2D& p2d, cudaStream_t st, float* dc_part = nullptr,
@@ -337,7 +341,8 @@ int launch_transpose(const float* src, int64_t rows, int cols, float* dst, cudaS
 int launch_fold(JrrModel* m, cudaStream_t st);
 int launch_adam_coef(const Workspace& w, const int32_t* step_count, float lr, cudaStream_t st);
 int launch_adam_params(const Workspace& w, bool use_critic, bool use_shape, float* x6, float* betas, float* adam_m,
-                       float* adam_v, int32_t* step_count, float lr, cudaStream_t st);
+                       float* adam_v, int32_t* step_count, float lr, cudaStream_t st, const float* ext_dx6 = nullptr,
+                       const float* ext_dbetas = nullptr);
 int launch_loss_seed(const JrrModel* m, Workspace& w, bool fused_partials, const float* gt_mm,
                      int64_t B_logical, float w_joint, float* joints17_out, const Proj2D& p2d, cudaStream_t st);
 int launch_camera_fit(const Workspace& w, const float* joints17, const float* gt2d, float* cam, int iters, float lr,

@@ -411,7 +411,8 @@ __global__ void bump_step_kernel(int32_t* step_count) { *step_count += 1; }
 // waits for it.  Same arithmetic, in the same order, as the fused Adam of pose_bwd_kernel.
 __global__ void __launch_bounds__(256)
 adam_params_kernel(const float* __restrict__ gx6, const float* __restrict__ gbetas, const float* __restrict__ dx6c,
-                   const float* __restrict__ dbeta_s, int64_t B, float* __restrict__ x6, float* __restrict__ betas,
+                   const float* __restrict__ dbeta_s, const float* __restrict__ ext_dx6,
+                   const float* __restrict__ ext_dbetas, int64_t B, float* __restrict__ x6, float* __restrict__ betas,
                    float* __restrict__ adam_m, float* __restrict__ adam_v, const float* __restrict__ coef,
                    int32_t* __restrict__ step_count) {
   // thread = two consecutive parameters of one pose (NPARAM and 144 are even: a pair never straddles rot6d / betas or
@@ -432,11 +433,19 @@ adam_params_kernel(const float* __restrict__ gx6, const float* __restrict__ gbet
       const float2 c = *reinterpret_cast<const float2*>(dx6c + b * 144 + p);
       g.x += c.x; g.y += c.y;
     }
+    if (ext_dx6 != nullptr) {
+      const float2 c = *reinterpret_cast<const float2*>(ext_dx6 + b * 144 + p);
+      g.x += c.x; g.y += c.y;
+    }
     prm = reinterpret_cast<float2*>(x6 + b * 144 + p);
   } else {
     g = *reinterpret_cast<const float2*>(gbetas + b * NB + (p - 144));
     if (dbeta_s != nullptr) {
       const float2 c = *reinterpret_cast<const float2*>(dbeta_s + b * NB + (p - 144));
+      g.x += c.x; g.y += c.y;
+    }
+    if (ext_dbetas != nullptr) {
+      const float2 c = *reinterpret_cast<const float2*>(ext_dbetas + b * NB + (p - 144));
       g.x += c.x; g.y += c.y;
     }
     prm = reinterpret_cast<float2*>(betas + b * NB + (p - 144));
@@ -673,10 +682,11 @@ int launch_smpl_small_fwd(const JrrModel* m, int64_t B, const float* betas, cons
 
 // ---- host wrappers ---------------------------------------------------------------------------
 int launch_adam_params(const Workspace& w, bool use_critic, bool use_shape, float* x6, float* betas, float* adam_m,
-                       float* adam_v, int32_t* step_count, float lr, cudaStream_t st) {
+                       float* adam_v, int32_t* step_count, float lr, cudaStream_t st, const float* ext_dx6,
+                       const float* ext_dbetas) {
   const int64_t n = w.B * (NPARAM / 2);
   adam_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.gx6, w.gbetas, use_critic ? w.dx6c : nullptr,
-                                                                 use_shape ? w.dbeta_s : nullptr, w.B, x6, betas, adam_m,
+                                                                 use_shape ? w.dbeta_s : nullptr, ext_dx6, ext_dbetas, w.B, x6, betas, adam_m,
                                                                  adam_v, w.adam_coef, step_count);
   (void)lr;
   JRR_LAUNCH_CHECK();

@@ -297,6 +297,7 @@ loss_seed_kernel(const float* __restrict__ part, int nslots, int n_tiles, int T,
         float l2 = 0.f;
         if (b < B) {
           float Tc[3], dT[3] = {0.f, 0.f, 0.f}, m3[3], v3[3];
+          if (p2d.dcam_ext != nullptr) { dT[0] = p2d.dcam_ext[b * 3 + 0]; dT[1] = p2d.dcam_ext[b * 3 + 1]; dT[2] = p2d.dcam_ext[b * 3 + 2]; }
 #pragma unroll
           for (int c = 0; c < 3; c++) { Tc[c] = p2d.cam[b * 3 + c]; m3[c] = p2d.cam_m[b * 3 + c]; v3[c] = p2d.cam_v[b * 3 + c]; }
           l2 = proj2d_grad(pred, Tc, p2d.gt2d + b * 34, p2d.scale, g, dT);
@@ -451,6 +452,7 @@ folded_seed_kernel(const float* __restrict__ QT, const float* __restrict__ AT, c
         for (int a = 0; a < NACC; a++) { pred[a] = spred[a * FS_POSES + lane]; g[a] = sg[a * FS_POSES + lane]; }
         if (b < B) {
           float Tcam[3], dT[3] = {0.f, 0.f, 0.f}, m3[3], v3[3];
+          if (p2d.dcam_ext != nullptr) { dT[0] = p2d.dcam_ext[b * 3 + 0]; dT[1] = p2d.dcam_ext[b * 3 + 1]; dT[2] = p2d.dcam_ext[b * 3 + 2]; }
 #pragma unroll
           for (int c = 0; c < 3; c++) { Tcam[c] = p2d.cam[b * 3 + c]; m3[c] = p2d.cam_m[b * 3 + c]; v3[c] = p2d.cam_v[b * 3 + c]; }
           loss2 = proj2d_grad(pred, Tcam, p2d.gt2d + b * 34, p2d.scale, g, dT);

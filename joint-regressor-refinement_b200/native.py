@@ -340,6 +340,12 @@ class NativeModel:
                   "jrr_refine_step_2d")
         self._done()
 
+    def set_external_gradient(self, dx6=None, dbetas=None, dcam=None):
+        """Gradients of loss terms computed outside the refinement step (the silhouette term), added before Adam by
+        every later refine_step / refine_step_2d until cleared (call without arguments)."""
+        self._ext = (dx6, dbetas, dcam)        # keep the tensors alive while the library holds their pointers
+        check(self.L.jrr_set_external_gradient(self.h, _ptr(dx6), _ptr(dbetas), _ptr(dcam)), "jrr_set_external_gradient")
+
     def regressor_grad_accumulate(self, x6, betas, gt_mm, G_accum, loss_accum, logical_batch=None):
         B = x6.shape[0]
         LB = B if logical_batch is None else int(logical_batch)

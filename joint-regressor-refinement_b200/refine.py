@@ -189,6 +189,52 @@ class PoseRefiner:
                 last = st["loss"]
         return last
 
+    def refine_silhouette(self, x6, betas, cam, gt_mm, gt_j2d, mask, renderer, iters=100, w_2d=0.01, w_sil=100.0,
+                          logical_batch=None):
+        """`refine_2d` plus the silhouette term of optimize.py:234-236,252-253 (`silhouette*100`): every iteration renders
+        the current mesh (`renderer`: a jrr_b200.Mesh_Renderer; module forward -> rasteriser), takes the gradient of
+        `w_sil * MSE(render, mask)` back through the rasteriser and the body model (module backward) and hands it to the
+        fused step as an external gradient, so ONE Adam step is taken on the sum of all terms like the reference's
+        `opt_loss.backward(); optimizer.step()`.  mask [N,1,S,S] or [N,S,S].  Returns (step losses, silhouette loss) of the
+        last iteration.  Eager launches (the silhouette branch costs a full body-model forward + backward per iteration,
+        ~1.2 ms per 4096 frames, so the graph replay of `refine` would not pay here)."""
+        from ._lib import POSE_ROT6D
+        from .mesh_renderer import silhouette_mse
+        N = x6.shape[0]
+        S = renderer.image_size
+        last, last_s = None, None
+        self._ensure_regressor()
+        nat = self.native
+        with torch.cuda.device(self.device):
+            for lo in range(0, N, self.chunk):
+                hi = min(N, lo + self.chunk)
+                B = hi - lo
+                LB = B if logical_batch is None else logical_batch
+                st = self._buffers(B, two_d=True)
+                st["x6"].copy_(x6[lo:hi].reshape(B, 24, 6), non_blocking=True)
+                st["betas"].copy_(betas[lo:hi], non_blocking=True)
+                st["cam"].copy_(cam[lo:hi], non_blocking=True)
+                st["gt"].copy_(gt_mm[lo:hi].reshape(B, 17, 3), non_blocking=True)
+                st["gt2d"].copy_(gt_j2d[lo:hi].reshape(B, 17, 2), non_blocking=True)
+                st["w_2d"] = float(w_2d)
+                tgt = mask[lo:hi].reshape(B, S, S).to(self.device, torch.float32).contiguous()
+                for k in ("m", "v", "t", "cm", "cv"):
+                    st[k].zero_()
+                try:
+                    for _ in range(iters):
+                        verts, _ = nat.smpl_forward(st["betas"], st["x6"], POSE_ROT6D, True, False)
+                        last_s, dverts, dcam, _ = silhouette_mse(renderer, verts, st["cam"], tgt, LB, w_sil)
+                        dbetas, dx6 = nat.smpl_backward(st["betas"], st["x6"], POSE_ROT6D, dverts, None)
+                        nat.set_external_gradient(dx6, dbetas, dcam)
+                        self._step(st, LB)
+                finally:
+                    nat.set_external_gradient()
+                x6[lo:hi].copy_(st["x6"].view_as(x6[lo:hi]), non_blocking=True)
+                betas[lo:hi].copy_(st["betas"], non_blocking=True)
+                cam[lo:hi].copy_(st["cam"], non_blocking=True)
+                last = st["loss"]
+        return last, last_s
+
     def refine(self, x6, betas, gt_mm, iters=100, logical_batch=None, loss_history=None):
         """In-place refinement of x6 [N,24,6] / betas [N,10] against gt_mm [N,17,3] (mm,
         pelvis-centred).  Frames are processed in chunks of ``chunk``; each chunk is one

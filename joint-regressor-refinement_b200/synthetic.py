@@ -154,6 +154,19 @@ def make_smpl_model(seed: int = 0, skin_weights_per_vertex: int = 4) -> dict:
     }
 
 
+def make_local_faces(v_template: np.ndarray, n_faces: int = 13776) -> np.ndarray:
+    """A surface-like triangle soup for the silhouette term: the model's own ``faces`` are random vertex triples (nothing on
+    the hot path reads them), which would be body-sized triangles.  Here every vertex spans triangles with its nearest
+    neighbours (2 per vertex: neighbours 3-4 and 7-8), so faces are a few centimetres across like SMPL's 13 776."""
+    from scipy.spatial import cKDTree
+    v = np.asarray(v_template, dtype=np.float64)
+    _, nb = cKDTree(v).query(v, k=9)
+    a = np.stack([nb[:, 0], nb[:, 3], nb[:, 4]], axis=1)
+    b = np.stack([nb[:, 0], nb[:, 7], nb[:, 8]], axis=1)
+    faces = np.concatenate([a, b], axis=0)
+    return np.ascontiguousarray(faces[:n_faces], dtype=np.int64)
+
+
 def make_dense_regressor(seed: int = 0) -> np.ndarray:
     """Dense 17x6890 raw regressor |N(0,1)| (exercises the dense reduction)."""
     rng = np.random.default_rng(seed + 7919)

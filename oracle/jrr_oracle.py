@@ -388,9 +388,10 @@ def camera_fit(smpl, Jraw, x6, betas, gt_j2d, cam, iters=1000, lr=1e-2, logical_
 
 
 def refine_2d(smpl, Jraw, critic_sd, x6, betas, cam, gt_mm, gt_j2d, iters=100, lr=1e-2, w_joint=10000.0,
-              w_pose=10.0, w_2d=0.01, logical_batch=None, shape_sd=None, w_shape=10.0):
-    """optimize.py:201-202,220-265 with the 3-D joint, pose-critic and 2-D reprojection terms
-    (everything except the silhouette render): Adam([pose, orient, betas, cam])."""
+              w_pose=10.0, w_2d=0.01, logical_batch=None, shape_sd=None, w_shape=10.0, silhouette=None):
+    """optimize.py:201-202,220-265 with the 3-D joint, pose-critic and 2-D reprojection terms:
+    Adam([pose, orient, betas, cam]).  ``silhouette`` = dict(faces, target [B,S,S], S, weight=100, pix_to_face=None) adds
+    the silhouette term of optimize.py:234-236,252 through oracle/silhouette_oracle.py."""
     x6 = x6.detach().clone().requires_grad_(True)
     betas = betas.detach().clone().requires_grad_(True)
     cam = cam.detach().clone().requires_grad_(True)
@@ -403,6 +404,14 @@ def refine_2d(smpl, Jraw, critic_sd, x6, betas, cam, gt_mm, gt_j2d, iters=100, l
                                           shape_sd=shape_sd, w_shape=w_shape)
         l2 = ((gt_j2d - project_2d(pred, cam)) ** 2).sum() / (LB * 17 * 2)
         total = total + w_2d * l2
+        if silhouette is not None:
+            from . import silhouette_oracle
+            R = rot6d_to_rotmat(x6.reshape(-1, 6)).view(B, 24, 3, 3)
+            verts = smpl(betas=betas, body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False).vertices
+            ls, _, _ = silhouette_oracle.silhouette_loss(verts, cam, silhouette["faces"], silhouette["target"],
+                                                         silhouette["S"], logical_batch=LB,
+                                                         pix_to_face=silhouette.get("pix_to_face"))
+            total = total + silhouette.get("weight", 100.0) * ls
         opt.zero_grad()
         total.backward()
         opt.step()
