@@ -432,6 +432,41 @@ def run_c3(jrr, smpl, J, sd, args, dev, rank, world, timer):
     return c3, c4
 
 
+def run_silhouette(jrr, smpl, J, sd, dev, n=1024, S=224):
+    """Widening row 8f-4: the silhouette term at the reference's image size (optimize.py:111: 224) -- rasteriser forward and
+    backward alone, and one whole refinement iteration with every term of optimize.py:252-253 (3-D joints, pose critic,
+    2-D reprojection, silhouette) through PoseRefiner.refine_silhouette."""
+    import torch
+    inp = jrr.synthetic.make_pose_inputs(n, 5)
+    R = torch.from_numpy(inp["true_rotmat"]).to(dev)
+    betas = torch.from_numpy(inp["true_betas"]).to(dev)
+    faces = jrr.synthetic.make_local_faces(smpl._model_np["v_template"])
+    rend = jrr.Mesh_Renderer(image_size=S, faces=faces)
+    cam = torch.tensor([0.0, 0.4, 5000.0 / S * 2.3], device=dev).repeat(n, 1).contiguous()
+    verts = smpl(betas=betas, body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False).vertices.contiguous()
+    mask = (torch.rand(n, 1, S, S, device=dev) > 0.5).float()
+    from jrr_b200.mesh_renderer import _backward, _forward
+    mesh = rend.mesh(6890, dev)
+    tgt = mask[:, 0].contiguous()
+    f_ms = median_ms(lambda: _forward(mesh, verts, cam, S, True, tgt, n), torch, reps=10)
+    alpha, p2f, _ = _forward(mesh, verts, cam, S, True, tgt, n)
+    b_ms = median_ms(lambda: _backward(mesh, verts, cam, S, True, alpha, p2f, target=tgt, logical_batch=n, weight=100.0), torch, reps=10)
+    ref = jrr.PoseRefiner(smpl, J, sd, chunk=n, use_graph=False)
+    x6 = torch.from_numpy(inp["x6"]).to(dev).reshape(n, 24, 6).contiguous()
+    gt = torch.zeros(n, 17, 3, device=dev)          # (timing only: the targets do not change the work)
+    gt2d = torch.full((n, 17, 2), 112.0, device=dev)
+    xw, bw, cw = x6.clone(), betas.clone(), cam.clone()
+    it_ms = median_ms(lambda: ref.refine_silhouette(xw, bw, cw, gt, gt2d, mask, rend, iters=4), torch, warm=1, reps=3) / 4
+    covered = (p2f >= 0).float().mean().item()
+    del ref
+    return {"frames": n, "image_size": S, "faces": int(faces.shape[0]), "covered_pixel_fraction": round(covered, 4),
+            "raster_fwd_ms": round(f_ms, 3), "raster_bwd_ms": round(b_ms, 3),
+            "refine_iteration_all_terms_ms": round(it_ms, 3),
+            "frames_per_s_all_terms": round(n / (it_ms * 1e-3)),
+            "note": "synthetic triangle soup (2 local triangles per vertex); the iteration = module forward + rasteriser + "
+                    "rasteriser backward + module backward + the fused refinement step with the 2-D term"}
+
+
 def run_c5(jrr, smpl, dev, pk, sizes):
     """C5: the drop-in module itself -- SMPL forward (vertices + 49 joints out) and forward+backward, rotation-matrix
     inputs, through NativeModel.smpl_forward / smpl_backward (what SMPLFunction calls)."""
@@ -672,6 +707,8 @@ def main():
         c3["vs_device_resident_step_rate"] = round(c3["pose_steps_per_s"] / value, 4)
         c5 = run_c5(jrr, smpl, dev, pk, [1, 16, 256, 4096, 65536])
         secondary = {"c3_strong": c3, "c4_refit": c4, "c5_smpl_module": c5}
+        if rank == 0:
+            secondary["silhouette_term"] = run_silhouette(jrr, smpl, J0, sd, dev)
 
     cpu = eager_ref = None
     if rank == 0 and not args.no_cpu_baseline:

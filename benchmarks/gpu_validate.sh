@@ -19,6 +19,8 @@ PY
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'gemm_pair|folded_seed|critic_pre|critic_post|pose_fwd|pose_bwd|adam_params' -s 60 -c 26 -f -o gpurun_out/${T}_prof python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'fused_bwd|fused_fwd' -s 30 -c 4 -f -o gpurun_out/${T}_prof_vertex python bench.py --loss-path vertex --steps 3 --warmup 3 --no-cpu-baseline --no-secondary >> gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'fused_fwd|fused_bwd|smpl_small' -c 14 -f -o gpurun_out/${T}_prof_module python benchmarks/module_calls.py >> gpurun_out/ncu_full.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_module_launches.csv python benchmarks/module_calls.py > gpurun_out/${T}_module.log 2>&1
 ls -la gpurun_out/${T}_prof*.ncu-rep
 timeout 300 python benchmarks/gemm_pair_check.py > gpurun_out/${T}_gemm_pair_check.jsonl 2>/dev/null
 timeout 300 python benchmarks/gemm_prof.py > gpurun_out/${T}_gemm_role_stamps.jsonl 2>/dev/null

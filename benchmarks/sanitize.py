@@ -43,5 +43,21 @@ for J in (shipped_regressor(), torch.rand(17, 6890) + 0.01):
         jrr.Discriminator().to(dev).bind(smpl.native())(x6)
         jrr.Shape_Discriminator().to(dev).bind(smpl.native())(be)
         smpl.native().load_shape_critic(None)
+# single-launch small-batch forward (all three rotation formats) and the silhouette term
+for n in (1, 7):
+    inp = jrr.synthetic.make_pose_inputs(n, 4)
+    x6, be = torch.from_numpy(inp["x6"]).to(dev), torch.from_numpy(inp["betas"]).to(dev)
+    R = torch.from_numpy(inp["true_rotmat"]).to(dev)
+    smpl(betas=be, body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False)
+    smpl(betas=be, body_pose=torch.randn(n, 69, device=dev), global_orient=torch.randn(n, 3, device=dev))
+    smpl.native().smpl_forward(be, x6.reshape(n, 24, 6).contiguous(), 2, False, True)
+    rend = jrr.Mesh_Renderer(image_size=40, faces=jrr.synthetic.make_local_faces(model["v_template"]))
+    cam = torch.tensor([0.0, 0.4, 5000.0 / 40 * 2.3], device=dev).repeat(n, 1)
+    bq = be.clone().requires_grad_(True)
+    img = jrr.render_mesh(smpl, rend, bq, R[:, :1], R[:, 1:], {"cam": cam})
+    torch.nn.functional.mse_loss(img, torch.rand_like(img)).backward()
+    gt = torch.zeros(n, 17, 3, device=dev)
+    jrr.PoseRefiner(smpl, shipped_regressor(), sd, use_graph=False).refine_silhouette(
+        x6.clone(), be.clone(), cam.clone(), gt, torch.full((n, 17, 2), 112.0, device=dev), torch.rand(n, 1, 40, 40, device=dev), rend, iters=2)
 torch.cuda.synchronize()
 print("sanitizer workload done")

@@ -3,9 +3,10 @@
 ``{bboxes,betas,estimated_translation,gt_j2d,gt_j3d,intrinsics,orient,pose}.pt`` (tensors, frame-major)
 and ``{images,pixel_annotations}.pkl`` (python lists).  This module reads the TENSOR fields and
 applies the per-frame crop arithmetic of ``data_set.__getitem__`` / ``find_crop``
-(``data.py:140-158,216-270``); decoding the Human3.6M frames and Mask R-CNN masks (imageio, h5py,
-the differentiable image sampler) feeds only the SPIN network and the silhouette term, both outside
-the hot path, so ``image`` / ``mask_rcnn`` / ``spin_image`` are not produced.
+(``data.py:140-158,216-270``).  The Mask R-CNN silhouettes the silhouette term compares against (``mask_rcnn`` / ``valid``,
+data.py:113-131) are produced when a decoder is available: ``imageio`` as in the reference when it is installed, else a
+``mask_loader(path) -> [H,W] array`` given by the caller (the mask path is derived from the frame path exactly as
+data.py:115-116).  The RGB crops (``image`` / ``spin_image``) feed only the SPIN network (out of scope) and are not produced.
 
 Host-side only (plain torch on CPU tensors): the product's device work starts at
 ``RefinementLoop.run_batch``.
@@ -76,7 +77,14 @@ class data_set(Dataset):
     """``scripts.data.data_set`` for the tensor fields.  ``set`` = "train" reads
     ``<root>/precomputed_train/``, anything else ``<root>/precomputed_val/`` (data.py:31-35)."""
 
-    def __init__(self, set, root="data/human3.6m"):
+    def __init__(self, set, root="data/human3.6m", mask_loader=None):
+        self.mask_loader = mask_loader
+        if mask_loader is None:
+            try:
+                import imageio            # the reference's decoder (data.py:6,118-119); not part of this image
+                self.mask_loader = imageio.imread
+            except ImportError:
+                pass
         self.location = os.path.join(root, "precomputed_train" if set == "train" else "precomputed_val")
         for name in TENSOR_FILES:
             path = os.path.join(self.location, name + ".pt")
@@ -107,6 +115,23 @@ class data_set(Dataset):
             "intrinsics": cropped_intrinsics(self.intrinsics[idx].float(), bb),
             "orient": self.orient[idx].float(), "pose": self.pose[idx].float(), "inc_gt": self.inc_gt[idx],
         }
+
+    def masks(self, index):
+        """``mask_rcnn`` [n,1,H,W] in [0,1] and ``valid`` [n] of data.py:113-131 for the given frames: the mask file is the
+        frame's path with ``imageSequence`` replaced by ``maskSequence``; ``valid`` is read BEFORE the top-left 2x2 pixels
+        are cleared, like the reference."""
+        if self.mask_loader is None or self.images is None:
+            raise RuntimeError("no mask decoder: install imageio or pass mask_loader=, and provide images.pkl")
+        idx = torch.as_tensor(index, dtype=torch.long).reshape(-1).tolist()
+        out = []
+        for i in idx:
+            head, tail = self.images[i].split("imageSequence")[:2]
+            m = torch.as_tensor(self.mask_loader(f"{head}maskSequence{tail}"))
+            out.append(m.to(torch.uint8).float().unsqueeze(0) / 255.0)
+        mask = torch.stack(out)
+        valid = mask[:, 0, 0, 0] != 0
+        mask[:, :, :2, :2] = 0
+        return mask, valid
 
     def __getitem__(self, index):
         return {k: v[0] for k, v in self.batch([int(index)]).items()}

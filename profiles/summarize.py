@@ -94,10 +94,11 @@ def top_kernels():
            "ncu --set full --clock-control none --import-source on -k regex:'gemm_pair|folded_seed|critic_pre|critic_post|pose_fwd|"
            "pose_bwd|adam_params' -s 60 -c 26 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary",
            "ncu --set full ... -k regex:'fused_bwd|fused_fwd' -s 30 -c 4 python bench.py --loss-path vertex --steps 3 --warmup 3 --no-cpu-baseline",
+           "ncu --set full ... -k regex:'fused_fwd|fused_bwd|smpl_small' -c 14 python benchmarks/module_calls.py   (module path: SMPL.forward / backward at 4096, 256, 8 poses)",
            "(first captured launch of each kernel; B = 4096 poses, dense 17x6890 regressor; times under ncu are cold-cache and serialised)", ""]
     traffic = {}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    for tag in (f"{TAG}_prof", f"{TAG}_prof_vertex"):
+    for tag in (f"{TAG}_prof", f"{TAG}_prof_vertex", f"{TAG}_prof_module"):
         rep = os.path.join(SRC, tag + ".ncu-rep")
         if not os.path.exists(rep):
             continue

@@ -197,6 +197,24 @@ def test_precomputed_split_round_trip(tmp_path, jrr):
     assert torch.equal(ds.batch(slice(3, 9))["gt_j3d"], frames["gt_j3d"][3:9])
     with pytest.raises(FileNotFoundError):
         jrr.data_set("train", root=root)
+    # Mask R-CNN silhouettes (data.py:113-131): path derived from the frame path, /255, `valid` read before the top-left
+    # 2x2 pixels are cleared
+    import numpy as np
+    names = [f"{root}/S9/imageSequence/cam0/frame_{i:06d}.npy" for i in range(n)]
+    jrr.write_precomputed(root + "/precomputed_val", frames, images=names)
+    os.makedirs(f"{root}/S9/maskSequence/cam0", exist_ok=True)
+    rng = np.random.default_rng(0)
+    raw = (rng.random((n, 8, 8)) > 0.5).astype(np.uint8) * 255
+    for i in range(n):
+        np.save(f"{root}/S9/maskSequence/cam0/frame_{i:06d}.npy", raw[i])
+    ds = jrr.data_set("validation", root=root, mask_loader=np.load)
+    mask, valid = ds.masks([3, 0, 36])
+    assert mask.shape == (3, 1, 8, 8) and mask.max().item() == 1.0
+    assert valid.tolist() == [bool(raw[i, 0, 0]) for i in (3, 0, 36)]
+    assert mask[:, :, :2, :2].abs().max().item() == 0
+    expect = torch.from_numpy(raw[[3, 0, 36]]).float() / 255
+    expect[:, :2, :2] = 0
+    assert torch.equal(mask[:, 0], expect)
 
 
 def test_bench_reference_arm_prints_one_contract_line():
