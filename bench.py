@@ -440,7 +440,7 @@ def run_silhouette(jrr, smpl, J, sd, dev, n=1024, S=224):
     inp = jrr.synthetic.make_pose_inputs(n, 5)
     R = torch.from_numpy(inp["true_rotmat"]).to(dev)
     betas = torch.from_numpy(inp["true_betas"]).to(dev)
-    faces = jrr.synthetic.make_local_faces(smpl._model_np["v_template"])
+    faces = jrr.synthetic.make_local_faces(smpl._model_np["v_template"], lbs_weights=smpl._model_np["lbs_weights"])
     rend = jrr.Mesh_Renderer(image_size=S, faces=faces)
     cam = torch.tensor([0.0, 0.4, 5000.0 / S * 2.3], device=dev).repeat(n, 1).contiguous()
     verts = smpl(betas=betas, body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False).vertices.contiguous()

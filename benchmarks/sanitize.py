@@ -51,7 +51,7 @@ for n in (1, 7):
     smpl(betas=be, body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False)
     smpl(betas=be, body_pose=torch.randn(n, 69, device=dev), global_orient=torch.randn(n, 3, device=dev))
     smpl.native().smpl_forward(be, x6.reshape(n, 24, 6).contiguous(), 2, False, True)
-    rend = jrr.Mesh_Renderer(image_size=40, faces=jrr.synthetic.make_local_faces(model["v_template"]))
+    rend = jrr.Mesh_Renderer(image_size=40, faces=jrr.synthetic.make_local_faces(model["v_template"], lbs_weights=model["lbs_weights"]))
     cam = torch.tensor([0.0, 0.4, 5000.0 / 40 * 2.3], device=dev).repeat(n, 1)
     bq = be.clone().requires_grad_(True)
     img = jrr.render_mesh(smpl, rend, bq, R[:, :1], R[:, 1:], {"cam": cam})

@@ -226,6 +226,14 @@ int jrr_shape_critic_apply(JrrModel* model, float* params, const float* G, float
 int jrr_evaluate(int64_t B, const float* pred_j3d, const float* target_j3d_mm, float* out_mm,
                  float* per_frame_mm, void* scratch, size_t scratch_bytes, void* stream);
 
+/* replaces: the autograd backward of utils.find_joints (scripts/utils.py:85-103) w.r.t. the body-model inputs, as reached
+ * when a caller differentiates a loss on the regressed joints itself (renderer.py:27-28 -> optimize.py:193-199,231-233):
+ * djoints17 [B,17,3] -> dbetas_out [B,10], dpose_out (layout of `pose`).  The regressor is the one jrr_set_regressor holds
+ * (its own gradient is the refit's: jrr_regressor_grad_accumulate).  Recomputes the forward. */
+int jrr_find_joints_backward(JrrModel* model, int64_t B, const float* betas, const float* pose, int kind,
+                             const float* djoints17, float* dbetas_out, float* dpose_out, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* Gradients of loss terms computed OUTSIDE jrr_refine_step / jrr_refine_step_2d -- the silhouette term of
  * optimize.py:234-236,252-253, i.e. jrr_silhouette_backward chained through jrr_smpl_backward(kind = ROT6D) -- are added to
  * the step's own parameter gradients before the Adam update (optimize.py:252-253,263-265: one optimiser step on the sum of

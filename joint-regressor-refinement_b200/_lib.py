@@ -20,7 +20,7 @@ EXPORTS = [
     "jrr_debug_gemm", "jrr_refine_step_profiled", "jrr_step_kernel_name", "jrr_camera_fit", "jrr_refine_step_2d", "jrr_evaluate",
     "jrr_shape_critic_load", "jrr_shape_critic_forward", "jrr_critic_grad_accumulate", "jrr_critic_apply",
     "jrr_shape_critic_grad_accumulate", "jrr_shape_critic_apply", "jrr_set_loss_path", "jrr_debug_tma_probe", "jrr_debug_set_gemm_prof",
-    "jrr_critic_layer2_bwd_products", "jrr_silhouette_workspace_bytes", "jrr_silhouette_forward", "jrr_silhouette_backward", "jrr_set_external_gradient",
+    "jrr_critic_layer2_bwd_products", "jrr_silhouette_workspace_bytes", "jrr_silhouette_forward", "jrr_silhouette_backward", "jrr_set_external_gradient", "jrr_find_joints_backward",
 ]
 
 
@@ -69,6 +69,7 @@ def lib():
     L.jrr_smpl_forward.argtypes = [vp, i64, vp, vp, C.c_int, vp, vp, vp, sz, vp]
     L.jrr_smpl_backward.argtypes = [vp, i64, vp, vp, C.c_int, vp, vp, vp, vp, vp, sz, vp]
     L.jrr_find_joints.argtypes = [vp, i64, vp, vp, C.c_int, vp, vp, sz, vp]
+    L.jrr_find_joints_backward.argtypes = [vp, i64, vp, vp, C.c_int, vp, vp, vp, vp, sz, vp]
     L.jrr_critic_forward.argtypes = [vp, i64, vp, vp, vp, sz, vp]
     L.jrr_refine_step.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, sz, vp]
     L.jrr_regressor_grad_accumulate.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, sz, vp]

@@ -270,6 +270,29 @@ extern "C" int jrr_find_joints(JrrModel* m, int64_t B, const float* betas, const
   return launch_loss_seed(m, w, m->fused_fwd, nullptr, 1, 0.f, joints17_out, Proj2D{}, st);
 }
 
+extern "C" int jrr_find_joints_backward(JrrModel* m, int64_t B, const float* betas, const float* pose, int kind,
+                                        const float* djoints17, float* dbetas_out, float* dpose_out, void* ws,
+                                        size_t ws_bytes, void* stream) {
+  Workspace w;
+  if (int rc = check_common(m, B, ws, ws_bytes, &w)) return rc;
+  if (!m->has_regressor) return fail(JRR_ERR_STATE, "jrr_set_regressor has not been called");
+  if (!betas || !pose || !djoints17 || !dbetas_out || !dpose_out) return fail(JRR_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  // recompute the forward (blended vertices kept for the backward), seed the skinning backward with the caller's gradient
+  if (int rc = loss_forward(m, w, betas, pose, kind, 1, w.vpT, st, nullptr, nullptr)) return rc;
+  if (int rc = launch_seed_from_dpred(w, djoints17, st)) return rc;
+  if (m->fused_bwd) {
+    if (int rc = fused_bwd_all_passes(m, w, st, nullptr, nullptr)) return rc;
+  } else {
+    if (m->n_pass > 1) return fail(JRR_ERR_STATE, "models with more than 4 skinning weights per vertex need the fused kernels");
+    if (int rc = launch_skin_bwd(m, w, nullptr, true, false, st)) return rc;
+    if (int rc = launch_dA_reduce(m, w, 0, st)) return rc;
+    if (int rc = blend_backward_gemm(m, w, st)) return rc;
+  }
+  return launch_pose_bwd(m, w, betas, pose, kind, false, false, false, dbetas_out, dpose_out, nullptr, nullptr, nullptr,
+                         nullptr, nullptr, 0.f, st);
+}
+
 extern "C" int jrr_critic_forward(JrrModel* m, int64_t B, const float* rot6d, float* scores_out, void* ws,
                                   size_t ws_bytes, void* stream) {
   Workspace w;

@@ -345,6 +345,7 @@ int launch_adam_params(const Workspace& w, bool use_critic, bool use_shape, floa
                        const float* ext_dbetas = nullptr);
 int launch_loss_seed(const JrrModel* m, Workspace& w, bool fused_partials, const float* gt_mm,
                      int64_t B_logical, float w_joint, float* joints17_out, const Proj2D& p2d, cudaStream_t st);
+int launch_seed_from_dpred(const Workspace& w, const float* dpred, cudaStream_t st);
 int launch_camera_fit(const Workspace& w, const float* joints17, const float* gt2d, float* cam, int iters, float lr,
                       int64_t B_logical, float* loss_out, cudaStream_t st);
 // whole module forward of a small batch (<= 32 poses, 4 weights per vertex) in one launch (jrr_pose.cu)

@@ -1089,6 +1089,23 @@ int launch_skin_fwd(const JrrModel* m, const Workspace& w, float* vertices_out, 
 // poses per CTA of the loss-seed kernel: 32 while the partial count fits its region of the partial buffer
 static inline int loss_seed_ppb(int64_t BP) { return BP / 32 <= LOSS_PART_2D ? 32 : 128; }
 
+// upstream gradient of the 17 regressed joints [B,17,3] -> the pose-contiguous seed gT [51][BP] the skinning backward reads
+// (rows of padding poses are zero): the backward of find_joints on its own (jrr_find_joints_backward)
+__global__ void seed_from_dpred_kernel(const float* __restrict__ dpred, int64_t B, int64_t BP, float* __restrict__ gT) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NACC * BP) return;
+  const int a = (int)(idx / BP);
+  const int64_t b = idx % BP;
+  gT[idx] = b < B ? dpred[b * NACC + a] : 0.f;
+}
+
+int launch_seed_from_dpred(const Workspace& w, const float* dpred, cudaStream_t st) {
+  const int64_t n = NACC * w.BP;
+  seed_from_dpred_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dpred, w.B, w.BP, w.gT);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
 int launch_loss_seed(const JrrModel* m, Workspace& w, bool fused_partials, const float* gt_mm,
                      int64_t B_logical, float w_joint, float* joints17_out, const Proj2D& p2d, cudaStream_t st) {
   const int ppb = loss_seed_ppb(w.BP);

@@ -273,6 +273,18 @@ class NativeModel:
         self._done()
         return out
 
+    def find_joints_backward(self, betas, pose, kind, djoints):
+        B = pose.shape[0]
+        betas, pose, dj = _f32c(betas, "betas"), _f32c(pose, "pose"), _f32c(djoints, "djoints17")
+        dbetas = torch.empty(B, 10, device=self.device)
+        dpose = torch.empty_like(pose)
+        ws, wsz = self.workspace(B)
+        with self._on_device():
+            check(self.L.jrr_find_joints_backward(self.h, B, _ptr(betas), _ptr(pose), kind, _ptr(dj), _ptr(dbetas),
+                                                  _ptr(dpose), ws, wsz, _stream()), "jrr_find_joints_backward")
+        self._done()
+        return dbetas, dpose
+
     def critic_forward(self, rot6d):
         B = rot6d.shape[0]
         x = _f32c(rot6d, "rot6d")

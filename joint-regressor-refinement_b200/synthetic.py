@@ -154,13 +154,26 @@ def make_smpl_model(seed: int = 0, skin_weights_per_vertex: int = 4) -> dict:
     }
 
 
-def make_local_faces(v_template: np.ndarray, n_faces: int = 13776) -> np.ndarray:
+def make_local_faces(v_template: np.ndarray, n_faces: int = 13776, lbs_weights: np.ndarray | None = None) -> np.ndarray:
     """A surface-like triangle soup for the silhouette term: the model's own ``faces`` are random vertex triples (nothing on
     the hot path reads them), which would be body-sized triangles.  Here every vertex spans triangles with its nearest
-    neighbours (2 per vertex: neighbours 3-4 and 7-8), so faces are a few centimetres across like SMPL's 13 776."""
+    neighbours (2 per vertex: neighbours 3-4 and 7-8), so faces are a few centimetres across like SMPL's 13 776.  With
+    ``lbs_weights`` the neighbours are taken among the vertices of the same body part (dominant skinning joint), so no face
+    bridges two parts that merely touch in the rest pose (hand / thigh, arm / torso) and stretches across the image once
+    the body is posed -- a real mesh has no such faces."""
     from scipy.spatial import cKDTree
     v = np.asarray(v_template, dtype=np.float64)
-    _, nb = cKDTree(v).query(v, k=9)
+    n = v.shape[0]
+    part = np.zeros(n, dtype=np.int64) if lbs_weights is None else np.asarray(lbs_weights).argmax(axis=1)
+    nb = np.zeros((n, 9), dtype=np.int64)
+    _, nb_all = cKDTree(v).query(v, k=9)
+    for p in np.unique(part):
+        idx = np.nonzero(part == p)[0]
+        if idx.size < 9:
+            nb[idx] = nb_all[idx]           # (a part too small for its own neighbourhood)
+            continue
+        _, loc = cKDTree(v[idx]).query(v[idx], k=9)
+        nb[idx] = idx[loc]
     a = np.stack([nb[:, 0], nb[:, 3], nb[:, 4]], axis=1)
     b = np.stack([nb[:, 0], nb[:, 7], nb[:, 8]], axis=1)
     faces = np.concatenate([a, b], axis=0)

@@ -28,11 +28,55 @@ def find_j_reg_mask(j_reg: torch.Tensor) -> torch.Tensor:
     return torch.ones_like(j_reg)
 
 
+class _RegressorInstalled:
+    """The CUDA model keeps ONE normalised regressor, shared with PoseRefiner / RegressorRefit; the reference's find_joints
+    is stateless (utils.py:87-92 re-normalises on every call).  When a call's J is not the one the model holds it is
+    installed for the call and the previous one is put back afterwards, so a comparison run with another regressor does
+    not change what the refinement loop optimises against."""
+
+    def __init__(self, native, J, mask):
+        self.native, self.J, self.mask, self.prev = native, J, mask, None
+
+    def __enter__(self):
+        if not self.native.holds_regressor(self.J, self.mask):
+            self.prev = self.native._reg
+            self.native.set_regressor(self.J, self.mask)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            self.native.set_regressor(self.prev[0], self.prev[1])
+        return False
+
+
+class FindJointsFunction(torch.autograd.Function):
+    """(betas [B,10], rotations [B,24,9]) -> joints17 [B,17,3] through the fused loss-path kernels; the backward
+    (jrr_find_joints_backward) gives the gradients w.r.t. betas and the rotation matrices.  The regressor is a constant
+    here (its own gradient is the refit's business: RegressorRefit / the eager path of find_joints)."""
+
+    @staticmethod
+    def forward(ctx, betas, full, native, J, mask):
+        betas, full = betas.float().contiguous(), full.float().contiguous()
+        with _RegressorInstalled(native, J, mask):
+            out = native.find_joints(betas, full, POSE_ROTMAT)
+        ctx.save_for_backward(betas, full)
+        ctx.native, ctx.J, ctx.mask = native, J, mask
+        return out
+
+    @staticmethod
+    def backward(ctx, dpred):
+        betas, full = ctx.saved_tensors
+        with _RegressorInstalled(ctx.native, ctx.J, ctx.mask):
+            dbetas, dfull = ctx.native.find_joints_backward(betas, full, POSE_ROTMAT, dpred)
+        return dbetas, dfull, None, None, None
+
+
 def find_joints(smpl, shape, orient, pose, J_regressor, mask=None, return_verts=False):
-    """scripts/utils.py:85-103: regressed 17 joints [B,17,3] (and optionally the vertices)."""
+    """scripts/utils.py:85-103: regressed 17 joints [B,17,3] (and optionally the vertices).  Differentiable w.r.t. the
+    body-model inputs through the fused kernels; only when the REGRESSOR itself requires grad (or the vertices are asked
+    for) does it compose the module forward with a torch contraction like the reference."""
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad for t in (shape, orient, pose, J_regressor))
-    if return_verts or needs_grad:
+    if return_verts or (needs_grad and J_regressor.requires_grad):
         J = J_regressor * mask if mask is not None else J_regressor
         Jn = torch.relu(J)
         Jn = Jn / Jn.sum(dim=1, keepdim=True)
@@ -40,25 +84,16 @@ def find_joints(smpl, shape, orient, pose, J_regressor, mask=None, return_verts=
         pred = torch.matmul(Jn.to(verts.device)[None], verts)
         return (pred, verts) if return_verts else pred
     native = smpl.native()
-    # The reference's find_joints is stateless (utils.py:87-92 re-normalises on every call); the CUDA model keeps
-    # ONE normalised regressor, shared with PoseRefiner / RegressorRefit.  When this call's J is not the one the
-    # model holds it is installed for the call and the previous one is put back afterwards, so a comparison run
-    # with another regressor does not change what the refinement loop optimises against.
     J = J_regressor.detach().to(native.device)
     m = None if mask is None else mask.detach().to(native.device)
-    prev = None
-    if not native.holds_regressor(J, m):
-        prev = native._reg
-        native.set_regressor(J, m)
     B = max(shape.shape[0], pose.shape[0])
     full = torch.cat([orient.reshape(-1, 1, 3, 3).expand(B, -1, -1, -1),
                       pose.reshape(-1, 23, 3, 3).expand(B, -1, -1, -1)], dim=1).reshape(B, 24, 9)
     betas = shape if shape.shape[0] == B else shape.expand(B, -1)
-    try:
+    if needs_grad:
+        return FindJointsFunction.apply(betas, full, native, J, m)
+    with _RegressorInstalled(native, J, m):
         return native.find_joints(betas, full, POSE_ROTMAT)
-    finally:
-        if prev is not None:
-            native.set_regressor(prev[0], prev[1])
 
 
 def move_pelvis(j3ds: torch.Tensor) -> torch.Tensor:

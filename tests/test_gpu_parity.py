@@ -208,6 +208,34 @@ def test_find_joints_matches_oracle(which, smpl_tc, osmpl64, oracle, jrr, J_ship
     assert rel(out2, ref) < 1e-5 and verts.shape == (64, 6890, 3)
 
 
+@pytest.mark.parametrize("which", ["shipped", "dense"])
+def test_find_joints_autograd_through_fused_kernels(which, smpl_tc, osmpl64, oracle, jrr, J_shipped, J_dense, frames64):
+    """utils.find_joints differentiated by the caller (renderer.py:27-28 -> the 2-D loss, optimize.py:193-199): forward and
+    backward run on the fused loss-path kernels (jrr_find_joints / jrr_find_joints_backward, no torch contraction); gradients
+    w.r.t. betas and the rotation matrices vs fp64 autograd; a regressor that requires grad still takes the eager path."""
+    J = J_shipped if which == "shipped" else J_dense
+    n = 70
+    R, b = frames64["true_rotmat"][:n], frames64["true_betas"][:n]
+    n = R.shape[0]
+    g = torch.Generator().manual_seed(2)
+    up = torch.randn(n, 17, 3, generator=g)
+    Ro, bo = R.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = oracle.find_joints(osmpl64, bo, Ro[:, :1], Ro[:, 1:], J.double())
+    (ref * up.double()).sum().backward()
+    Rc, bc = R.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    nat = smpl_tc.native()
+    out = jrr.find_joints(smpl_tc, bc, Rc[:, :1], Rc[:, 1:], J.to(DEV))
+    assert isinstance(out.grad_fn, torch.autograd.function.BackwardCFunction) or "FindJoints" in type(out.grad_fn).__name__
+    (out * up.to(DEV)).sum().backward()
+    eb, er = rel(bc.grad, bo.grad), rel(Rc.grad, Ro.grad)
+    print(f"[find_joints autograd {which}] joints {rel(out, ref):.2e}, d/d betas {eb:.2e}, d/d rotations {er:.2e}")
+    assert rel(out, ref) < 1e-5 and eb < 1e-4 and er < 1e-4
+    Jg = J.to(DEV).clone().requires_grad_(True)
+    out2 = jrr.find_joints(smpl_tc, b.to(DEV), R[:, :1].to(DEV), R[:, 1:].to(DEV), Jg)
+    out2.sum().backward()
+    assert Jg.grad is not None and rel(out2, ref) < 1e-5
+
+
 def test_find_joints_golden(smpl_tc, jrr, J_shipped):
     z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "ref_utils_golden.npz"))
     R = torch.from_numpy(z["rotmat"]).to(DEV)

@@ -78,7 +78,7 @@ def _scene(jrr, B, S, seed=3):
     inp = jrr.synthetic.make_pose_inputs(B, seed)
     R = torch.from_numpy(inp["true_rotmat"]).to(DEV)
     betas = torch.from_numpy(inp["true_betas"]).to(DEV)
-    faces = jrr.synthetic.make_local_faces(model["v_template"])
+    faces = jrr.synthetic.make_local_faces(model["v_template"], lbs_weights=model["lbs_weights"])
     g = torch.Generator().manual_seed(seed)
     cam = torch.tensor([0.0, 0.4, 5000.0 / S * 2.3]) + torch.randn(B, 3, generator=g) * torch.tensor([0.1, 0.1, 1.0])
     return smpl, R, betas, faces, cam.to(DEV)
@@ -213,7 +213,7 @@ def test_refine_with_silhouette_term_matches_oracle(smpl_tc, jrr, oracle, osmpl3
     from test_gpu_parity import _cam_problem
     B, S = 4, 224
     fr, gt2d, cam0 = _cam_problem(jrr, oracle, osmpl32, J_shipped, B, 11)
-    faces = jrr.synthetic.make_local_faces(smpl_tc._model_np["v_template"])
+    faces = jrr.synthetic.make_local_faces(smpl_tc._model_np["v_template"], lbs_weights=smpl_tc._model_np["lbs_weights"])
     rend = jrr.Mesh_Renderer(image_size=S, faces=faces)
     g = torch.Generator().manual_seed(3)
     mask = (torch.rand(B, 1, S, S, generator=g) > 0.7).float()
