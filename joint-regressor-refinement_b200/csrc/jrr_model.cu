@@ -384,8 +384,11 @@ __global__ void fold_prep_kernel(const VtxRec* __restrict__ vrec, double* __rest
   for (int s4 = 0; s4 < 4; s4++) wj[(int64_t)idx * 4 + s4] = (double)vrec[p].w[s4] * jh;
 }
 
-constexpr int FOLD_R = 3;                   // regressor rows per CTA: the blend-matrix rows are read 6 times instead of 17
-constexpr int FOLD_SMEM = FOLD_R * NJ * KA * (int)sizeof(double);   // 129 KB
+// regressor rows per CTA.  Measured: 3 rows per CTA (the blend-matrix rows re-read 6 times instead of 17, 129 KB of
+// accumulators, one 7-warp CTA per SM) is SLOWER than 1 (332 vs 270 us): the kernel is bound by the latency of its dependent
+// load -> DFMA groups, which five co-resident CTAs per SM hide and one does not -- not by L2 bandwidth.
+constexpr int FOLD_R = 1;
+constexpr int FOLD_SMEM = FOLD_R * NJ * KA * (int)sizeof(double);   // 43 KB
 
 __global__ void __launch_bounds__(KA)
 fold_kernel(const VtxRec* __restrict__ vrec, const double* __restrict__ wj, const float* __restrict__ Pt_hi,
@@ -395,8 +398,7 @@ fold_kernel(const VtxRec* __restrict__ vrec, const double* __restrict__ wj, cons
   // accumulators only when a slot's joint changes (the records' reload bits: ~190 times over the whole model) -- the
   // first version updated the shared accumulators for every (vertex, slot), one dependent shared-memory round trip each
   // (0.46 ms).  Same fp64 arithmetic; groups of four vertices without a slot change take a branch-free path.
-  // A CTA folds FOLD_R regressor rows at once (the kernel was bound by re-reading the blend matrix from L2 once per row:
-  // 17 x 37 MB per fold, 0.27 ms).
+  // A CTA folds FOLD_R regressor rows at once (see FOLD_R).
   extern __shared__ double fold_acc[];          // [FOLD_R][NJ * KA]
   const int i0 = blockIdx.x * FOLD_R, c = blockIdx.y, ch = blockIdx.z, k = threadIdx.x;
   for (int e = k; e < FOLD_R * NJ * KA; e += KA) fold_acc[e] = 0.0;

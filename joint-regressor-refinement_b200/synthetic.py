@@ -157,7 +157,8 @@ def make_smpl_model(seed: int = 0, skin_weights_per_vertex: int = 4) -> dict:
 def make_local_faces(v_template: np.ndarray, n_faces: int = 13776, lbs_weights: np.ndarray | None = None) -> np.ndarray:
     """A surface-like triangle soup for the silhouette term: the model's own ``faces`` are random vertex triples (nothing on
     the hot path reads them), which would be body-sized triangles.  Here every vertex spans triangles with its nearest
-    neighbours (2 per vertex: neighbours 3-4 and 7-8), so faces are a few centimetres across like SMPL's 13 776.  With
+    neighbours (2 per vertex: neighbours 1-2 and 3-4), so faces have edges of 1-2 cm like SMPL's 13 776 (two to three pixels at
+    224 x 224; the rasteriser's cost goes with the pixel area of the faces' bounding boxes).  With
     ``lbs_weights`` the neighbours are taken among the vertices of the same body part (dominant skinning joint), so no face
     bridges two parts that merely touch in the rest pose (hand / thigh, arm / torso) and stretches across the image once
     the body is posed -- a real mesh has no such faces."""
@@ -174,8 +175,8 @@ def make_local_faces(v_template: np.ndarray, n_faces: int = 13776, lbs_weights: 
             continue
         _, loc = cKDTree(v[idx]).query(v[idx], k=9)
         nb[idx] = idx[loc]
-    a = np.stack([nb[:, 0], nb[:, 3], nb[:, 4]], axis=1)
-    b = np.stack([nb[:, 0], nb[:, 7], nb[:, 8]], axis=1)
+    a = np.stack([nb[:, 0], nb[:, 1], nb[:, 2]], axis=1)
+    b = np.stack([nb[:, 0], nb[:, 3], nb[:, 4]], axis=1)
     faces = np.concatenate([a, b], axis=0)
     return np.ascontiguousarray(faces[:n_faces], dtype=np.int64)
 
