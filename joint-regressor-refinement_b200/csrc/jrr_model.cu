@@ -371,7 +371,10 @@ int regressor_accumulate_folded(const JrrModel* m, Workspace& w, const float* gt
 // T[(j,i,c)][k] = sum_v Jhat_iv w_vj P[3v+c][k],  c_ji = sum_v Jhat_iv w_vj   (see folded_seed_kernel).
 // grid (17 regressor rows in groups of FOLD_R, 4 = three coordinates + the homogeneous one, FOLD_CH vertex chunks), thread = k;
 // double accumulators in shared memory, fixed summation order (chunk partials reduced in order).
-constexpr int FOLD_CH = VP / VS_F;          // 12 chunks = the forward record ranges (a range start reloads all four slots)
+// 12 chunks = the forward record ranges (a range start reloads all four slots).  Measured alternatives: 9 chunks of 768
+// vertices (612 CTAs = ONE wave at five CTAs per SM instead of a wave and a 76-CTA tail) 301 vs 270 us -- the time follows the
+// vertices a CTA walks, i.e. the kernel pulls 842 MB of blend-matrix rows through L2 at ~3 TB/s with 35 warps per SM
+constexpr int FOLD_CH = VP / VS_F;
 
 // wj[i][p][slot] = w_p,slot * Jhat_i,p in double (exact: 24 + 24 significand bits), once per regressor version -- the fold
 // kernel's 224 threads per CTA would otherwise each redo these conversions and products for every vertex
@@ -384,9 +387,9 @@ __global__ void fold_prep_kernel(const VtxRec* __restrict__ vrec, double* __rest
   for (int s4 = 0; s4 < 4; s4++) wj[(int64_t)idx * 4 + s4] = (double)vrec[p].w[s4] * jh;
 }
 
-// regressor rows per CTA.  Measured: 3 rows per CTA (the blend-matrix rows re-read 6 times instead of 17, 129 KB of
-// accumulators, one 7-warp CTA per SM) is SLOWER than 1 (332 vs 270 us): the kernel is bound by the latency of its dependent
-// load -> DFMA groups, which five co-resident CTAs per SM hide and one does not -- not by L2 bandwidth.
+// regressor rows per CTA.  Measured: 3 rows per CTA (the blend-matrix rows re-read 6 times instead of 17, but 129 KB of
+// accumulators = one 7-warp CTA per SM) is SLOWER than 1 (332 vs 270 us): seven warps per SM cannot keep enough loads in
+// flight; five co-resident CTAs can.
 constexpr int FOLD_R = 1;
 constexpr int FOLD_SMEM = FOLD_R * NJ * KA * (int)sizeof(double);   // 43 KB
 

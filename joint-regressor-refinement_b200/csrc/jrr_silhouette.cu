@@ -108,24 +108,55 @@ __global__ void sil_project_kernel(const float* __restrict__ verts, const float*
   ndc[idx * 3 + 2] = Z;
 }
 
+// A face whose box holds more than SIL_BIG pixel centres is not walked by its own thread (one lane looping over thousands of
+// centres while 31 wait) but by the whole warp: its data is broadcast by shuffles and the lanes stride over the box.  SMPL faces
+// at 224 x 224 never get there; a close-up camera, a coarse mesh or a larger image do.
+constexpr int SIL_BIG = 64;
+constexpr unsigned SIL_FULL = 0xffffffffu;
+
+__device__ __forceinline__ SilFace sil_shfl_face(const SilFace& t, int src) {
+  SilFace s;
+  s.x0 = __shfl_sync(SIL_FULL, t.x0, src); s.y0 = __shfl_sync(SIL_FULL, t.y0, src); s.z0 = __shfl_sync(SIL_FULL, t.z0, src);
+  s.x1 = __shfl_sync(SIL_FULL, t.x1, src); s.y1 = __shfl_sync(SIL_FULL, t.y1, src); s.z1 = __shfl_sync(SIL_FULL, t.z1, src);
+  s.x2 = __shfl_sync(SIL_FULL, t.x2, src); s.y2 = __shfl_sync(SIL_FULL, t.y2, src); s.z2 = __shfl_sync(SIL_FULL, t.z2, src);
+  s.lo_x = __shfl_sync(SIL_FULL, t.lo_x, src); s.hi_x = __shfl_sync(SIL_FULL, t.hi_x, src);
+  s.lo_y = __shfl_sync(SIL_FULL, t.lo_y, src); s.hi_y = __shfl_sync(SIL_FULL, t.hi_y, src);
+  s.live = true;
+  return s;
+}
+__device__ __forceinline__ int sil_box(const SilFace& t) { return t.live ? (t.hi_x - t.lo_x + 1) * (t.hi_y - t.lo_y + 1) : 0; }
+
+__device__ __forceinline__ void sil_raster_pixel(const SilFace& t, int xi, int yi, int S, uint32_t f, unsigned long long* zb) {
+  float pz;
+  if (!sil_covers(t, sil_pix_to_ndc(xi, S), sil_pix_to_ndc(yi, S), &pz)) return;
+  // pz >= 0: its bit pattern orders like the value; ties go to the lower face id
+  const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)f;
+  atomicMin(zb + (int64_t)(S - 1 - yi) * S + (S - 1 - xi), key);
+}
+
 __global__ void sil_raster_kernel(const float* __restrict__ ndc, const int32_t* __restrict__ faces, int64_t B, int64_t V,
                                   int64_t F, int S, unsigned long long* __restrict__ zbuf) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * F) return;
-  const int64_t b = idx / F, f = idx % F;
-  const SilFace t = sil_load_face(ndc + b * V * 3, faces, f, S);
-  if (!t.live) return;
-  unsigned long long* zb = zbuf + b * (int64_t)S * S;
-  for (int yi = t.lo_y; yi <= t.hi_y; yi++) {
-    const float py = sil_pix_to_ndc(yi, S);
-    for (int xi = t.lo_x; xi <= t.hi_x; xi++) {
-      const float px = sil_pix_to_ndc(xi, S);
-      float pz;
-      if (!sil_covers(t, px, py, &pz)) continue;
-      // pz >= 0: its bit pattern orders like the value; ties go to the lower face id
-      const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(uint32_t)f;
-      atomicMin(zb + (int64_t)(S - 1 - yi) * S + (S - 1 - xi), key);
-    }
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (whole warps stay for the cooperative part)
+  const bool in = idx < B * F;
+  const int64_t b = in ? idx / F : 0, f = in ? idx % F : 0;
+  SilFace t = sil_load_face(ndc + b * V * 3, faces, f, S);
+  t.live = t.live && in;
+  const int box = sil_box(t);
+  if (box > 0 && box <= SIL_BIG) {
+    unsigned long long* zb = zbuf + b * (int64_t)S * S;
+    for (int yi = t.lo_y; yi <= t.hi_y; yi++)
+      for (int xi = t.lo_x; xi <= t.hi_x; xi++) sil_raster_pixel(t, xi, yi, S, (uint32_t)f, zb);
+  }
+  const int lane = threadIdx.x & 31;
+  unsigned todo = __ballot_sync(SIL_FULL, box > SIL_BIG);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const SilFace s = sil_shfl_face(t, src);
+    const int64_t sidx = __shfl_sync(SIL_FULL, idx, src);
+    unsigned long long* zb = zbuf + (sidx / F) * (int64_t)S * S;
+    const int nx = s.hi_x - s.lo_x + 1, n = nx * (s.hi_y - s.lo_y + 1);
+    for (int p = lane; p < n; p += 32) sil_raster_pixel(s, s.lo_x + p % nx, s.lo_y + p / nx, S, (uint32_t)(sidx % F), zb);
   }
 }
 
@@ -199,51 +230,85 @@ sil_loss_finish_kernel(const float* __restrict__ frame_loss, int64_t B, float sc
 }
 
 // d loss / d (the face's three projected corners, x and y), summed over the pixels the face won
+__device__ __forceinline__ void sil_grad_pixel(const SilFace& t, int xi, int yi, int S, int32_t f, int64_t base,
+                                               const int32_t* __restrict__ pix_to_face, const float* __restrict__ alpha,
+                                               const float* __restrict__ dalpha, const float* __restrict__ target,
+                                               float mse_scale, float inv_sigma, float g[6]) {
+  const int64_t pix = base + (int64_t)(S - 1 - yi) * S + (S - 1 - xi);
+  if (pix_to_face[pix] != f) return;
+  const float px = sil_pix_to_ndc(xi, S), py = sil_pix_to_ndc(yi, S);
+  const float a = alpha[pix];
+  const float up = dalpha != nullptr ? dalpha[pix] : mse_scale * 2.f * (a - target[pix]);
+  // alpha = sigmoid(d2 / sigma); rasterize_meshes backward: PointLineDistanceBackward on the closest edge with the
+  // segment parameter held fixed: grad_v0 = g (1 - t) 2 (q - p), grad_v1 = g t 2 (q - p), q = the closest point
+  const float gd = up * a * (1.f - a) * inv_sigma;
+  int edge;
+  float tt;
+  sil_tri_dist(t, px, py, &edge, &tt);
+  const int ia = edge == 2 ? 1 : 0, ib = edge == 0 ? 1 : 2;
+  const float ax = ia == 0 ? t.x0 : t.x1, ay = ia == 0 ? t.y0 : t.y1;
+  const float bx = ib == 1 ? t.x1 : t.x2, by = ib == 1 ? t.y1 : t.y2;
+  const float bax = bx - ax, bay = by - ay;
+  float ga[2] = {0.f, 0.f}, gb[2];
+  if (bax * bax + bay * bay <= SIL_EPS) {
+    // degenerate edge: distance to b; grad_v1 = -2 (p - b) g
+    gb[0] = -2.f * (px - bx) * gd;
+    gb[1] = -2.f * (py - by) * gd;
+  } else {
+    const float qx = ax + tt * bax - px, qy = ay + tt * bay - py;       // q - p
+    ga[0] = gd * (1.f - tt) * 2.f * qx;
+    ga[1] = gd * (1.f - tt) * 2.f * qy;
+    gb[0] = gd * tt * 2.f * qx;
+    gb[1] = gd * tt * 2.f * qy;
+  }
+  // (no dynamic register indexing: the corner of each end point is one of two)
+  if (ia == 0) { g[0] += ga[0]; g[1] += ga[1]; } else { g[2] += ga[0]; g[3] += ga[1]; }
+  if (ib == 1) { g[2] += gb[0]; g[3] += gb[1]; } else { g[4] += gb[0]; g[5] += gb[1]; }
+}
+
 __global__ void sil_face_grad_kernel(const float* __restrict__ ndc, const int32_t* __restrict__ faces,
                                      const int32_t* __restrict__ pix_to_face, const float* __restrict__ alpha,
                                      const float* __restrict__ dalpha, const float* __restrict__ target, float mse_scale,
                                      int64_t B, int64_t V, int64_t F, int S, float inv_sigma, float* __restrict__ gface) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * F) return;
-  const int64_t b = idx / F, f = idx % F;
+  const bool in = idx < B * F;
+  const int64_t b = in ? idx / F : 0, f = in ? idx % F : 0;
   float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const SilFace t = sil_load_face(ndc + b * V * 3, faces, f, S);
-  if (t.live) {
+  SilFace t = sil_load_face(ndc + b * V * 3, faces, f, S);
+  t.live = t.live && in;
+  const int box = sil_box(t);
+  if (box > 0 && box <= SIL_BIG) {
     const int64_t base = b * (int64_t)S * S;
-    for (int yi = t.lo_y; yi <= t.hi_y; yi++) {
-      const float py = sil_pix_to_ndc(yi, S);
-      for (int xi = t.lo_x; xi <= t.hi_x; xi++) {
-        const int64_t pix = base + (int64_t)(S - 1 - yi) * S + (S - 1 - xi);
-        if (pix_to_face[pix] != (int32_t)f) continue;
-        const float px = sil_pix_to_ndc(xi, S);
-        const float a = alpha[pix];
-        const float up = dalpha != nullptr ? dalpha[pix] : mse_scale * 2.f * (a - target[pix]);
-        // alpha = sigmoid(d2 / sigma); rasterize_meshes backward: PointLineDistanceBackward on the closest edge with the
-        // segment parameter held fixed: grad_v0 = g (1 - t) 2 (q - p), grad_v1 = g t 2 (q - p), q = the closest point
-        const float gd = up * a * (1.f - a) * inv_sigma;
-        int edge;
-        float tt;
-        sil_tri_dist(t, px, py, &edge, &tt);
-        const int ia = edge == 2 ? 1 : 0, ib = edge == 0 ? 1 : 2;
-        const float ax = ia == 0 ? t.x0 : t.x1, ay = ia == 0 ? t.y0 : t.y1;
-        const float bx = ib == 1 ? t.x1 : t.x2, by = ib == 1 ? t.y1 : t.y2;
-        const float bax = bx - ax, bay = by - ay;
-        if (bax * bax + bay * bay <= SIL_EPS) {
-          // degenerate edge: distance to b; grad_v1 = -2 (p - b) g
-          g[ib * 2 + 0] += -2.f * (px - bx) * gd;
-          g[ib * 2 + 1] += -2.f * (py - by) * gd;
-        } else {
-          const float qx = ax + tt * bax - px, qy = ay + tt * bay - py;       // q - p
-          g[ia * 2 + 0] += gd * (1.f - tt) * 2.f * qx;
-          g[ia * 2 + 1] += gd * (1.f - tt) * 2.f * qy;
-          g[ib * 2 + 0] += gd * tt * 2.f * qx;
-          g[ib * 2 + 1] += gd * tt * 2.f * qy;
-        }
-      }
+    for (int yi = t.lo_y; yi <= t.hi_y; yi++)
+      for (int xi = t.lo_x; xi <= t.hi_x; xi++)
+        sil_grad_pixel(t, xi, yi, S, (int32_t)f, base, pix_to_face, alpha, dalpha, target, mse_scale, inv_sigma, g);
+  }
+  // large boxes: the warp strides over the box, then a butterfly (a fixed order) sums the lanes' shares for the owner
+  const int lane = threadIdx.x & 31;
+  unsigned todo = __ballot_sync(SIL_FULL, box > SIL_BIG);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const SilFace s = sil_shfl_face(t, src);
+    const int64_t sidx = __shfl_sync(SIL_FULL, idx, src);
+    const int nx = s.hi_x - s.lo_x + 1, n = nx * (s.hi_y - s.lo_y + 1);
+    float gs[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = lane; p < n; p += 32)
+      sil_grad_pixel(s, s.lo_x + p % nx, s.lo_y + p / nx, S, (int32_t)(sidx % F), (sidx / F) * (int64_t)S * S, pix_to_face, alpha,
+                     dalpha, target, mse_scale, inv_sigma, gs);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int e = 0; e < 6; e++) gs[e] += __shfl_xor_sync(SIL_FULL, gs[e], o);
+    if (lane == src) {
+#pragma unroll
+      for (int e = 0; e < 6; e++) g[e] = gs[e];
     }
   }
+  if (in) {
 #pragma unroll
-  for (int e = 0; e < 6; e++) gface[idx * 6 + e] = g[e];
+    for (int e = 0; e < 6; e++) gface[idx * 6 + e] = g[e];
+  }
 }
 
 // per vertex: its faces' corner gradients (CSR, fixed order) chained through ndc = f (X, Y) / Z, view = (-2x, -2y, 2z) + cam

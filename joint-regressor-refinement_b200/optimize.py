@@ -1,11 +1,11 @@
-"""The pseudo-ground-truth refinement loop of ``scripts/optimize.py:144-312`` on the CUDA kernels,
-restricted to the in-scope terms (everything except the silhouette render):
+"""The pseudo-ground-truth refinement loop of ``scripts/optimize.py:144-312`` on the CUDA kernels, with every term of
+``opt_loss`` (optimize.py:252-253; the silhouette term when the batch carries masks and a renderer is given):
 
     per batch (optimize.py:150-312)
       1. move_pelvis(gt_j3d)                                        (:162)
       2. camera-only Adam on the 2-D reprojection, 1000 iterations  (:187-199)   jrr_camera_fit
       3. 100 Adam iterations on [pose, orient, betas, cam]          (:201-265)   jrr_refine_step(_2d)
-         loss = w_2d*loss_j2d + w_joint*joint + w_pose*pose_critic + w_shape*shape_critic
+         loss = w_2d*loss_j2d + w_sil*silhouette + w_joint*joint + w_pose*pose_critic + w_shape*shape_critic
       4. critic / shape-critic training step, real = the initial (SPIN) estimates,
          fake = the refined ones                                    (:276-293)   jrr_critic_grad/apply
       5. regressor refit step on the refined meshes                 (:300-312)   jrr_regressor_*
@@ -28,10 +28,12 @@ from .utils import evaluate, move_pelvis
 class RefinementLoop:
     def __init__(self, smpl, J_regressor, critic_state_dict, shape_critic_state_dict=None, mask=None,
                  lr=1e-2, disc_lr=1e-3, j_reg_lr=1e-2, refine_iters=100, cam_iters=1000,
-                 w_joint=10000.0, w_pose=10.0, w_shape=10.0, w_2d=0.01, chunk=4096, loss_path=None):
+                 w_joint=10000.0, w_pose=10.0, w_shape=10.0, w_2d=0.01, chunk=4096, loss_path=None,
+                 silhouette_renderer=None, w_sil=100.0):
         self.native = smpl.native() if hasattr(smpl, "native") else smpl
         self.device = self.native.device
         self.refine_iters, self.cam_iters, self.w_2d = int(refine_iters), int(cam_iters), float(w_2d)
+        self.renderer, self.w_sil = silhouette_renderer, float(w_sil)      # jrr_b200.Mesh_Renderer (optimize.py:111)
         # order matters: the refit owns the regressor, the trainer owns the critic weights; the refiner
         # reads both through the native model (its captured graphs stay valid across their updates)
         self.refit = RegressorRefit(smpl, J_regressor, mask=mask, lr=j_reg_lr, chunk=chunk)
@@ -50,7 +52,8 @@ class RefinementLoop:
 
     def run_batch(self, batch: dict, global_batch: int | None = None) -> dict:
         """``batch`` holds THIS RANK's frames: 'orient' [n,1,6], 'pose' [n,23,6], 'betas' [n,10], 'gt_j3d'
-        [n,17,3] (mm), optional 'gt_j2d' [n,17,2] + 'cam' [n,3].  ``global_batch`` is the frame count over
+        [n,17,3] (mm), optional 'gt_j2d' [n,17,2] + 'cam' [n,3], optional 'mask_rcnn' [n,1,S,S] (used when the loop has a
+        silhouette renderer; needs the 2-D fields: the camera is fitted on them first).  ``global_batch`` is the frame count over
         all ranks (the divisor of every mean loss, optimize.py:128); default: n * world size."""
         dev = self.device
         rank, world = self._world()
@@ -72,8 +75,13 @@ class RefinementLoop:
             gt2d = batch["gt_j2d"].to(dev).float().contiguous()
             cam = batch["cam"].to(dev).float().contiguous().clone()
             self.refiner.fit_camera(x6, betas, gt2d, cam, iters=self.cam_iters, logical_batch=LB)
-            loss = self.refiner.refine_2d(x6, betas, cam, gt, gt2d, iters=self.refine_iters, w_2d=self.w_2d,
-                                          logical_batch=LB)
+            if self.renderer is not None and batch.get("mask_rcnn") is not None:
+                loss, out["silhouette_loss"] = self.refiner.refine_silhouette(
+                    x6, betas, cam, gt, gt2d, batch["mask_rcnn"], self.renderer, iters=self.refine_iters, w_2d=self.w_2d,
+                    w_sil=self.w_sil, logical_batch=LB)
+            else:
+                loss = self.refiner.refine_2d(x6, betas, cam, gt, gt2d, iters=self.refine_iters, w_2d=self.w_2d,
+                                              logical_batch=LB)
             out["cam"] = cam
         else:
             loss = self.refiner.refine(x6, betas, gt, iters=self.refine_iters, logical_batch=LB)

@@ -192,6 +192,19 @@ def test_silhouette_edge_cases(jrr):
     assert (a > 0.5).all()                                      # the big triangle covers every pixel centre
     a.sum().backward()
     assert torch.isfinite(verts.grad).all()
+    # a box of several hundred pixel centres is walked by the whole warp (SIL_BIG): same image and gradient as the oracle
+    # (triangle inside the image, so that pixel centres sit next to its edges -- far from an edge the sigmoid saturates)
+    tri2 = torch.tensor([[-0.8, -0.7], [0.7, -0.6], [0.1, 0.8], [0.1, 0.1]]) * 100.0 / f
+    v2 = torch.cat([tri2, torch.zeros(4, 1)], dim=1)[None].to(DEV).requires_grad_(True)
+    g = torch.Generator().manual_seed(0)
+    up = torch.randn(1, S, S, generator=g)
+    a2 = rend.silhouette(cam, v2, flip_scale=False)
+    (a2 * up.to(DEV)).sum().backward()
+    vo = v2.detach().double().cpu().requires_grad_(True)
+    ao, p2fo = so.soft_silhouette(vo, cam.double().cpu(), torch.tensor([[0, 1, 2], [1, 1, 2], [3, 3, 3]]), S, flip_scale=False)
+    assert 200 < (p2fo == 0).sum().item() < S * S and (a2.detach().cpu().double() - ao.detach()).abs().max().item() < 1e-4
+    (ao * up.double()).sum().backward()
+    assert vo.grad.abs().max().item() > 1e-2 and rel(v2.grad, vo.grad) < 2e-3, rel(v2.grad, vo.grad)
     b = rend.silhouette(-cam, verts.detach(), flip_scale=False)
     assert b.abs().max().item() == 0
     with pytest.raises(jrr.JrrError):
@@ -263,3 +276,35 @@ def test_refine_with_silhouette_term_matches_oracle(smpl_tc, jrr, oracle, osmpl3
     x6b, beb, camb = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone(), cam0.to(DEV).clone()
     ref.refine_2d(x6b, beb, camb, fr["gt_mm"].to(DEV), gt2d.to(DEV), iters=1)
     assert (x6b.cpu() - x6p).abs().max().item() < 2e-4
+
+
+@pytest.mark.gpu
+def test_refinement_loop_with_silhouette_masks(smpl_tc, jrr, oracle, osmpl32, critic_sd, J_shipped):
+    """RefinementLoop.run_batch with 'mask_rcnn' in the batch and a renderer: camera fit, refinement with all five terms,
+    critic step, refit.  Masks rendered from the TRUE poses: the silhouette loss must fall over the iterations, and the
+    regressor / critic updates stay finite."""
+    from test_gpu_parity import _cam_problem
+    B, S = 6, 64
+    fr, gt2d, cam0 = _cam_problem(jrr, oracle, osmpl32, J_shipped, B, 21)
+    # the 2-D joints of _cam_problem live on the 224-pixel screen of renderer.py; the silhouettes are rendered at S
+    faces = jrr.synthetic.make_local_faces(smpl_tc._model_np["v_template"], lbs_weights=smpl_tc._model_np["lbs_weights"])
+    rend = jrr.Mesh_Renderer(image_size=S, faces=faces)
+    Rt = fr["true_rotmat"].to(DEV)
+    cam_sil = torch.tensor([0.0, 0.4, 5000.0 / S * 2.3], device=DEV).repeat(B, 1)
+    with torch.no_grad():
+        true_img = jrr.render_mesh(smpl_tc, rend, fr["true_betas"].to(DEV), Rt[:, :1], Rt[:, 1:], {"cam": cam_sil})
+    mask = (true_img > 0.5).float()
+    ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, use_graph=False)
+    x6, be, cam = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone(), cam_sil.clone()
+    gt, g2 = fr["gt_mm"].to(DEV), torch.full((B, 17, 2), 112.0, device=DEV)
+    _, s0 = ref.refine_silhouette(x6, be, cam, gt, g2, mask, rend, iters=1, w_2d=0.0)
+    s0 = s0.item()
+    _, s1 = ref.refine_silhouette(x6, be, cam, gt, g2, mask, rend, iters=30, w_2d=0.0)
+    print(f"silhouette loss against masks of the true poses: {s0:.5f} -> {s1.item():.5f} after 30 iterations")
+    assert s1.item() < s0
+    loop = jrr.RefinementLoop(smpl_tc, J_shipped, critic_sd, refine_iters=3, cam_iters=5, silhouette_renderer=rend)
+    out = loop.run_batch({"orient": fr["x6"][:, :1], "pose": fr["x6"][:, 1:], "betas": fr["betas"], "gt_j3d": fr["gt_mm"],
+                          "gt_j2d": gt2d, "cam": cam0, "mask_rcnn": mask})
+    assert "silhouette_loss" in out and torch.isfinite(out["silhouette_loss"]).all()
+    assert torch.isfinite(out["refine_loss"]).all() and torch.isfinite(out["refit_loss"]).all()
+    assert torch.isfinite(out["x6"]).all() and torch.isfinite(out["cam"]).all()
