@@ -1,10 +1,23 @@
-# folded-path GEMMs on CTA pairs: parity tests, then the step per tile-width / off
-timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 -k "folded or bench_config or refit or gemm or multi_step or loss_history" 2>&1 | tail -4
-for cfg in "JRR_FOLD_TS=0" "JRR_FOLD_BN=256" "JRR_FOLD_BN=192" "JRR_FOLD_BN=128"; do
-  env $cfg timeout 300 python bench.py --no-cpu-baseline --no-secondary > gpurun_out/r2_fold_tmp.json 2> gpurun_out/r2_fold_tmp.err || { echo "$cfg FAILED"; tail -3 gpurun_out/r2_fold_tmp.err; }
+timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 -k "folded or fold or refit or loop or six_weight or bench" 2>&1 | tail -4
+cat > /tmp/fold_probe.py <<'PY'
+import os, sys
+sys.path.insert(0, os.getcwd())
+import torch
+import jrr_b200 as jrr
+dev = torch.device("cuda", 0)
+smpl = jrr.SMPL(model_dict=jrr.synthetic.make_smpl_model(0), create_transl=False).to(dev)
+nat = smpl.native(); nat.set_loss_path("folded")
+J = torch.rand(17, 6890, device=dev) + 0.01
+for _ in range(3): nat.set_regressor(J)
+torch.cuda.synchronize()
+PY
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_fold_launches.csv python /tmp/fold_probe.py > /dev/null 2>&1
+grep -i "fold" gpurun_out/r2_fold_launches.csv | awk -F'","' '{print $5, $NF}' | cut -c1-100 | tail -5
+for cfg in "JRR_FOLD_RUNS=1" "JRR_FOLD_RUNS=0"; do
+  env $cfg timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-secondary > gpurun_out/r2_tmp.json 2> gpurun_out/r2_tmp.err || { echo "$cfg FAILED"; tail -3 gpurun_out/r2_tmp.err; }
   python - "$cfg" <<'PY'
 import json,sys
-d=json.loads(open("gpurun_out/r2_fold_tmp.json").read().strip().splitlines()[-1])
-print(sys.argv[1], d['value'], d['ms_per_step'], d['e2e']['value'], [(k['name'][:14],k['ms']) for k in d['kernels']], d['quality']['oracle_one_step_rel_err'])
+d=json.loads(open("gpurun_out/r2_tmp.json").read().strip().splitlines()[-1])
+print(sys.argv[1], "value", round(d['value']), d['ms_per_step'], "e2e", round(d['e2e']['value']), d['e2e']['ms_per_step'], d['refit_ms'], d['quality']['mpjpe_after_mm'])
 PY
 done

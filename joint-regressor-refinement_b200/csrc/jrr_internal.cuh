@@ -214,6 +214,9 @@ struct JrrModel {
   float* Tc = nullptr;                       // [24][17]        sum_v Jhat_iv w_vj
   double* fold_part = nullptr;               // scratch of fold_kernel
   double* fold_wj = nullptr;                 // [17][VP][4] w * Jhat in double (fold_prep_kernel)
+  double* fold_acc = nullptr;                // [1224*224 + 24*17] the folded operator in double (fold_gather_kernel)
+  double* fold_ev = nullptr;                 // [fold_ev_cap][17][4][224] run sums per flush event (fold_runs_kernel)
+  int fold_ev_cap = 0;
   bool fused_fwd = true;   // loss path: skinning + regressor in the blend GEMM's epilogue
   bool fused_bwd = true;   // loss path: skinning backward generates the A operand of the blend-gradient GEMM
   // skinning passes (see PassTab): n_pass = ceil(max non-zeros per lbs_weights row / 4)

@@ -378,13 +378,15 @@ constexpr int FOLD_CH = VP / VS_F;
 
 // wj[i][p][slot] = w_p,slot * Jhat_i,p in double (exact: 24 + 24 significand bits), once per regressor version -- the fold
 // kernel's 224 threads per CTA would otherwise each redo these conversions and products for every vertex
-__global__ void fold_prep_kernel(const VtxRec* __restrict__ vrec, double* __restrict__ wj) {
+// (wrec: the record table whose SLOT ORDER the fold kernel walks -- slots are re-assigned at every range start, so the tables of
+// different range sizes order a vertex's weights differently; jrec: any table that carries the regressor columns)
+__global__ void fold_prep_kernel(const VtxRec* __restrict__ wrec, const VtxRec* __restrict__ jrec, double* __restrict__ wj) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= NH * VP) return;
   const int i = idx / VP, p = idx % VP;
-  const double jh = (double)vrec[p].jh[i];
+  const double jh = (double)jrec[p].jh[i];
 #pragma unroll
-  for (int s4 = 0; s4 < 4; s4++) wj[(int64_t)idx * 4 + s4] = (double)vrec[p].w[s4] * jh;
+  for (int s4 = 0; s4 < 4; s4++) wj[(int64_t)idx * 4 + s4] = (double)wrec[p].w[s4] * jh;
 }
 
 // regressor rows per CTA.  Measured: 3 rows per CTA (the blend-matrix rows re-read 6 times instead of 17, but 129 KB of
@@ -509,6 +511,136 @@ __global__ void fold_finish_kernel(const double* __restrict__ part, float* __res
   }
 }
 
+// ---- the fold on register run-sums with NO shared accumulators (JRR_FOLD_RUNS=1; measured SLOWER, so not the default) --------
+// fold_kernel keeps one regressor row per CTA because its per-joint accumulators take 43 KB of shared memory per row, so the
+// blend matrix travels through L2 once per row: 17 x 2 x 18.6 MB x 4/3 = 842 MB per fold at ~3 TB/s = 0.27 ms.  Here a CTA
+// walks ONE 192-vertex record range for 8-9 regressor rows at once: thread = blend feature k, run[row][slot] in registers
+// (a record slot keeps its joint over long runs of the joint-sorted packing), and when a slot changes its joint the run sums
+// leave as a FLUSH EVENT -- the very events, in the very order, of the skinning backward's joint-transform gradients
+// (range_flush_base_s / flush_ptr_s / flush_idx_s, built with the records) -- so a gather over each joint's event list
+// finishes the fold in a fixed order.  The blend matrix is read twice per fold instead of 17 times.
+// Measured on a B200: 495 us against 270 us for fold_kernel (same 421 M DFMAs, 14 instead of 35 warps per SM): the fold is
+// paced by the double-precision FMAs, ~6 SM cycles per warp-DFMA in fold_kernel and ~10 here -- not by the L2 traffic this
+// variant removes.  Kept behind the switch as the record of that experiment; same results (parity suite green with it).
+constexpr int FR_ROWS = 9;       // regressor rows per CTA: [0, 9) and [9, 17)
+
+__global__ void __launch_bounds__(KA)
+fold_runs_kernel(const VtxRec* __restrict__ vrec, const double* __restrict__ wj, const float* __restrict__ Pt_hi,
+                 const float* __restrict__ Pt_lo, const int* __restrict__ range_base, double* __restrict__ part_ev) {
+  const int c = blockIdx.x, rg = blockIdx.y, i0 = blockIdx.z * FR_ROWS, k = threadIdx.x;
+  const int nrow = min(FR_ROWS, NH - i0);
+  double run[FR_ROWS][4];
+#pragma unroll
+  for (int r = 0; r < FR_ROWS; r++)
+#pragma unroll
+    for (int s4 = 0; s4 < 4; s4++) run[r][s4] = 0.0;
+  int ev = range_base[rg];
+  const int p0 = rg * VS_S;
+  auto flush = [&](int s4sel) {
+    // run sums of slot s4sel (compile-time after unrolling) -> event ev, rows i0 .. i0 + nrow
+#pragma unroll
+    for (int r = 0; r < FR_ROWS; r++) {
+      if (r < nrow) {
+        const double v = s4sel == 0 ? run[r][0] : s4sel == 1 ? run[r][1] : s4sel == 2 ? run[r][2] : run[r][3];
+        part_ev[(((int64_t)ev * NH + i0 + r) * 4 + c) * KA + k] = v;
+      }
+      if (s4sel == 0) run[r][0] = 0.0; else if (s4sel == 1) run[r][1] = 0.0; else if (s4sel == 2) run[r][2] = 0.0; else run[r][3] = 0.0;
+    }
+    ev++;
+  };
+#pragma unroll 2
+  for (int q = 0; q < VS_S; q++) {
+    const int pi = p0 + q;
+    const uint32_t meta = __ldg(&vrec[pi].meta);
+    const double p = c < 3 ? (double)__ldg(Pt_hi + (int64_t)(3 * pi + c) * KA + k) + (double)__ldg(Pt_lo + (int64_t)(3 * pi + c) * KA + k)
+                           : (k == 0 ? 1.0 : 0.0);
+    if (((meta >> 20) & 0xFu) && !((meta >> 25) & 1u)) {       // a slot changes its joint before this vertex (uniform)
+      if ((meta >> 20) & 1u) flush(0);
+      if ((meta >> 21) & 1u) flush(1);
+      if ((meta >> 22) & 1u) flush(2);
+      if ((meta >> 23) & 1u) flush(3);
+    }
+#pragma unroll
+    for (int r = 0; r < FR_ROWS; r++) {
+      if (r < nrow) {
+        const double2* w2 = reinterpret_cast<const double2*>(wj + ((int64_t)(i0 + r) * VP + pi) * 4);
+        const double2 wa = __ldg(w2), wb = __ldg(w2 + 1);
+        run[r][0] = fma(wa.x, p, run[r][0]);
+        run[r][1] = fma(wa.y, p, run[r][1]);
+        run[r][2] = fma(wb.x, p, run[r][2]);
+        run[r][3] = fma(wb.y, p, run[r][3]);
+      }
+    }
+  }
+  flush(0); flush(1); flush(2); flush(3);       // the range's last four events
+}
+
+// T[(j,i,c)][k] (and c_ji) = the sum of joint j's flush events, in the order of its list; later skinning passes add
+__global__ void fold_gather_kernel(const double* __restrict__ part_ev, const int* __restrict__ fptr, const int* __restrict__ fidx,
+                                   double* __restrict__ Tacc, int accumulate) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)FOLD_N * KA + NJ * NH) return;
+  int j, i, c, k;
+  if (idx < (int64_t)FOLD_N * KA) {
+    const int n = (int)(idx / KA);
+    k = (int)(idx % KA); c = n % 3; i = (n / 3) % NH; j = n / (3 * NH);
+  } else {
+    const int e = (int)(idx - (int64_t)FOLD_N * KA);
+    j = e / NH; i = e % NH; c = 3; k = 0;
+  }
+  double a = accumulate ? Tacc[idx] : 0.0;
+  for (int q = fptr[j]; q < fptr[j + 1]; q++) a += part_ev[(((int64_t)fidx[q] * NH + i) * 4 + c) * KA + k];
+  Tacc[idx] = a;
+}
+
+__global__ void fold_split_kernel(const double* __restrict__ Tacc, float* __restrict__ T_hi, float* __restrict__ T_lo,
+                                  float* __restrict__ Tt_hi, float* __restrict__ Tt_lo, float* __restrict__ Tc) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (int64_t)FOLD_N * KA) {
+    const int n = (int)(idx / KA), k = (int)(idx % KA);
+    const float x = (float)Tacc[idx];
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    const float hi = __uint_as_float(r);
+    const float d = x - hi;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
+    const float lo = __uint_as_float(r);
+    T_hi[idx] = hi;
+    T_lo[idx] = lo;
+    Tt_hi[(int64_t)k * FOLD_NP + n] = hi;
+    Tt_lo[(int64_t)k * FOLD_NP + n] = lo;
+  } else if (idx < (int64_t)FOLD_N * KA + NJ * NH) {
+    Tc[idx - (int64_t)FOLD_N * KA] = (float)Tacc[idx];
+  }
+}
+
+static int launch_fold_runs(JrrModel* m, cudaStream_t st) {
+  int max_ev = 0;
+  for (int pass = 0; pass < m->n_pass; pass++) max_ev = std::max(max_ev, m->passes[pass].n_flush_s);
+  if (max_ev > m->fold_ev_cap) {
+    // (only when the packing changed: jrr_set_regressor with a new support re-packs the vertices on the host anyway)
+    JRR_CUDA(cudaStreamSynchronize(st));
+    if (m->fold_ev) JRR_CUDA(cudaFree(m->fold_ev));
+    m->fold_ev = nullptr;
+    m->fold_ev_cap = max_ev + 64;
+    JRR_CUDA(cudaMalloc((void**)&m->fold_ev, (size_t)m->fold_ev_cap * NH * 4 * KA * sizeof(double)));
+  }
+  const int64_t n = (int64_t)FOLD_N * KA + NJ * NH;
+  for (int pass = 0; pass < m->n_pass; pass++) {
+    const PassTab& t = m->passes[pass];
+    fold_prep_kernel<<<(NH * VP + 255) / 256, 256, 0, st>>>(t.vrec_s, t.vrec, m->fold_wj);
+    JRR_LAUNCH_CHECK();
+    fold_runs_kernel<<<dim3(4, NSPLIT_S, (NH + FR_ROWS - 1) / FR_ROWS), KA, 0, st>>>(t.vrec_s, m->fold_wj, m->Pt_hi, m->Pt_lo,
+                                                                                  t.range_flush_base_s, m->fold_ev);
+    JRR_LAUNCH_CHECK();
+    fold_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->fold_ev, t.flush_ptr_s, t.flush_idx_s, m->fold_acc, pass > 0 ? 1 : 0);
+    JRR_LAUNCH_CHECK();
+  }
+  fold_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->fold_acc, m->T_hi, m->T_lo, m->Tt_hi, m->Tt_lo, m->Tc);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
 int launch_fold(JrrModel* m, cudaStream_t st) {
   if (!m->T_hi) {
     if (int rc = dalloc(m, &m->T_hi, (size_t)FOLD_NP * KA)) return rc;      // zero-filled: the padding rows stay zero
@@ -518,10 +650,13 @@ int launch_fold(JrrModel* m, cudaStream_t st) {
     if (int rc = dalloc(m, &m->Tc, (size_t)NJ * NH)) return rc;
     if (int rc = dalloc(m, &m->fold_part, (size_t)FOLD_CH * NH * 4 * NJ * KA)) return rc;
     if (int rc = dalloc(m, &m->fold_wj, (size_t)NH * VP * 4)) return rc;
+    if (int rc = dalloc(m, &m->fold_acc, (size_t)FOLD_N * KA + NJ * NH)) return rc;
   }
+  static const bool runs = [] { const char* e = getenv("JRR_FOLD_RUNS"); return e && e[0] == '1'; }();
+  if (runs) return launch_fold_runs(m, st);
   for (int pass = 0; pass < m->n_pass; pass++) {      // linear in the skinning weights: passes add up in the fp64 partials
     const PassTab& t = m->passes[pass];
-    fold_prep_kernel<<<(NH * VP + 255) / 256, 256, 0, st>>>(t.vrec, m->fold_wj);
+    fold_prep_kernel<<<(NH * VP + 255) / 256, 256, 0, st>>>(t.vrec, t.vrec, m->fold_wj);
     JRR_LAUNCH_CHECK();
     JRR_CUDA(cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FOLD_SMEM));
     fold_kernel<<<dim3((NH + FOLD_R - 1) / FOLD_R, 4, FOLD_CH), KA, FOLD_SMEM, st>>>(t.vrec, m->fold_wj, m->Pt_hi, m->Pt_lo, m->fold_part, pass > 0 ? 1 : 0);
@@ -737,6 +872,7 @@ extern "C" int jrr_model_destroy(JrrModel* m) {
   if (!m) return JRR_OK;
   cudaSetDevice(m->device);
   for (void* p : m->allocs) cudaFree(p);
+  if (m->fold_ev) cudaFree(m->fold_ev);
   if (m->side) cudaStreamDestroy(m->side);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
