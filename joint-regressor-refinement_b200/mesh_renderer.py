@@ -41,21 +41,28 @@ def load_obj_faces(path: str) -> np.ndarray:
     return np.asarray(faces, dtype=np.int64)
 
 
+def vertex_face_csr(faces, n_verts: int):
+    """CSR vertex -> (face * 3 + corner) entries, ascending inside a vertex's list (the fixed order in which the backward
+    sums a vertex's corner gradients).  Returns (faces int32 [F,3], ptr int32 [V+1], idx int32 [3F])."""
+    f = np.ascontiguousarray(np.asarray(faces).reshape(-1, 3), dtype=np.int64)
+    if f.size == 0 or f.min() < 0 or f.max() >= n_verts:
+        raise JrrError("faces must index the mesh vertices")
+    flat = f.reshape(-1)
+    order = np.argsort(flat, kind="stable")
+    ptr = np.zeros(n_verts + 1, dtype=np.int64)
+    np.add.at(ptr, flat + 1, 1)
+    return f.astype(np.int32), np.cumsum(ptr).astype(np.int32), order.astype(np.int32)
+
+
 class _Mesh:
     """Device copies of the faces and the vertex -> (face, corner) CSR the backward gathers through."""
 
     def __init__(self, faces, n_verts: int, device):
-        f = np.ascontiguousarray(np.asarray(faces).reshape(-1, 3), dtype=np.int64)
-        if f.size == 0 or f.min() < 0 or f.max() >= n_verts:
-            raise JrrError("faces must index the mesh vertices")
+        f, ptr, idx = vertex_face_csr(faces, n_verts)
         self.F, self.V = int(f.shape[0]), int(n_verts)
-        flat = f.reshape(-1)
-        order = np.argsort(flat, kind="stable")                    # by vertex, then by (face, corner): a fixed order
-        ptr = np.zeros(n_verts + 1, dtype=np.int64)
-        np.add.at(ptr, flat + 1, 1)
-        self.faces = torch.from_numpy(f.astype(np.int32)).to(device)
-        self.vf_ptr = torch.from_numpy(np.cumsum(ptr).astype(np.int32)).to(device)
-        self.vf_idx = torch.from_numpy(order.astype(np.int32)).to(device)
+        self.faces = torch.from_numpy(f).to(device)
+        self.vf_ptr = torch.from_numpy(ptr).to(device)
+        self.vf_idx = torch.from_numpy(idx).to(device)
         self._ws = None
 
     def workspace(self, B: int, S: int):

@@ -66,6 +66,14 @@ def test_obj_face_reader_and_vertex_face_csr(tmp_path, jrr):
     p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nvt 0 0\nf 1/1 2/1 3/1\nf 2//1 4//1 3//1 1//1\n")
     faces = jrr.load_obj_faces(str(p))
     assert faces.tolist() == [[0, 1, 2], [1, 3, 2], [1, 2, 0]]
+    vertex_face_csr = jrr.mesh_renderer.vertex_face_csr
+    f32, ptr, idx = vertex_face_csr(faces, 4)
+    assert ptr.tolist() == [0, 2, 5, 8, 9]                       # vertex 0 in 2 corners, 1 in 3, 2 in 3, 3 in 1
+    for v in range(4):
+        ent = idx[ptr[v]:ptr[v + 1]].tolist()
+        assert ent == sorted(ent) and all(f32.reshape(-1)[e] == v for e in ent)
+    with pytest.raises(jrr.JrrError):
+        vertex_face_csr([[0, 1, 4]], 4)
     local = jrr.synthetic.make_local_faces(jrr.synthetic.make_smpl_model(0)["v_template"])
     assert local.shape == (13776, 3) and local.min() >= 0 and local.max() < 6890
     assert (local[:, 0] != local[:, 1]).all() and (local[:, 1] != local[:, 2]).all()
@@ -98,7 +106,7 @@ def test_silhouette_forward_and_backward_match_oracle(S, jrr):
     fo = torch.from_numpy(faces)
     alpha_o, p2f_o = so.soft_silhouette(vo, co, fo, S)
     mesh = rend.mesh(6890, DEV)
-    from jrr_b200.mesh_renderer import _forward
+    _forward = jrr.mesh_renderer._forward
     _, p2f, _ = _forward(mesh, verts, cam, S, True)
     covered = (p2f_o >= 0).sum().item()
     mism = (p2f.cpu().long() != p2f_o).sum().item()
@@ -156,7 +164,7 @@ def test_silhouette_fused_mse_and_reference_call_shapes(jrr):
     g = torch.Generator().manual_seed(2)
     target = (torch.rand(B, 1, S, S, generator=g) > 0.5).float().to(DEV)
     loss, dverts, dcam, alpha = jrr.silhouette_mse(rend, verts, cam, target, logical_batch=2 * B, weight=100.0)
-    from jrr_b200.mesh_renderer import _forward
+    _forward = jrr.mesh_renderer._forward
     _, p2f, _ = _forward(rend.mesh(6890, DEV), verts, cam, S, True)
     vo, co = verts.double().cpu().requires_grad_(True), cam.double().cpu().requires_grad_(True)
     lo, _, _ = so.silhouette_loss(vo, co, torch.from_numpy(faces), target[:, 0].double().cpu(), S, logical_batch=2 * B,
@@ -233,7 +241,7 @@ def test_refine_with_silhouette_term_matches_oracle(smpl_tc, jrr, oracle, osmpl3
     ref = jrr.PoseRefiner(smpl_tc, J_shipped, critic_sd, use_graph=False)
     x6, be, cam = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone(), cam0.to(DEV).clone()
     # coverage of the FIRST iteration as the CUDA rasteriser sees it (handed to the oracle: identical winner maps)
-    from jrr_b200.mesh_renderer import _forward
+    _forward = jrr.mesh_renderer._forward
     R0 = jrr.rot6d_to_rotmat(x6.reshape(-1, 6)).reshape(B, 24, 3, 3)
     v0 = smpl_tc(betas=be, body_pose=R0[:, 1:], global_orient=R0[:, :1], pose2rot=False).vertices
     _, p2f, _ = _forward(rend.mesh(6890, DEV), v0.contiguous(), cam, S, True)
