@@ -234,6 +234,13 @@ extern "C" int jrr_smpl_backward(JrrModel* m, int64_t B, const float* betas, con
   cudaStream_t st = (cudaStream_t)stream;
   const bool use_x = djoints49 != nullptr;
   static const bool fused_module = [] { const char* e = getenv("JRR_FUSED_MODULE"); return !(e && e[0] == '0'); }();
+  if (smpl_small_bwd_available(m, B)) {
+    // a handful of poses: warp-per-vertex backward (chain, blended vertex, dA and dfeat partials), a fixed-order reduction,
+    // then the unchanged chain backward
+    if (int rc = launch_smpl_small_bwd(m, w, betas, pose, kind, dvertices, djoints49, st)) return rc;
+    return launch_pose_bwd(m, w, betas, pose, kind, use_x, false, false, dbetas_out, dpose_out, nullptr, nullptr,
+                           nullptr, nullptr, nullptr, 0.f, st);
+  }
   if (m->gemm_impl == 0 && m->fused_fwd && m->fused_bwd && fused_module) {
     // recompute: chain | blend GEMM + skinning (stores the blended vertices, pose-contiguous) ; then
     // joints49 gradient -> its sources | re-pack d vertices | skinning backward generating the A operand of the

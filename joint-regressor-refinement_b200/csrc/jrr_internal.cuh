@@ -355,6 +355,10 @@ int launch_camera_fit(const Workspace& w, const float* joints17, const float* gt
 bool smpl_small_fwd_available(const JrrModel* m, int64_t B);
 int launch_smpl_small_fwd(const JrrModel* m, int64_t B, const float* betas, const float* pose, int kind,
                           float* vertices, float* joints49, cudaStream_t st);
+// ... and its backward: joint-transform / blend-feature / posed-joint gradients into the workspace for launch_pose_bwd
+bool smpl_small_bwd_available(const JrrModel* m, int64_t B);
+int launch_smpl_small_bwd(const JrrModel* m, Workspace& w, const float* betas, const float* pose, int kind,
+                          const float* dverts, const float* dj49, cudaStream_t st);
 // fused blend GEMM + skinning + regressor partial sums (jrr_fused_fwd.cu)
 struct FusedSched { int n_tiles, T, G, mdiv; };   // see jrr_fused_fwd.cu
 FusedSched fused_fwd_sched(const JrrModel* m, int64_t BP, int nv);

@@ -680,6 +680,260 @@ int launch_smpl_small_fwd(const JrrModel* m, int64_t B, const float* betas, cons
   return JRR_OK;
 }
 
+// ---- small batches: the module BACKWARD in three launches ----------------------------------------------------------
+// Same grain as smpl_small_fwd_kernel (warp = packed vertex, lanes = the vertex's blend-matrix rows split along K, lane b =
+// pose b once the blended vertex is reduced): every block repeats the chain, recomputes the blended vertex, takes the
+// vertex gradient (the caller's d loss / d vertices plus the joints49 gradient that reaches this vertex through a pick or an
+// extra-regressor row), and leaves (i) its contribution to the joint-transform gradients in a per-WARP shared accumulator
+// (lanes = poses: no two lanes touch one address, no atomics), (ii) its contribution to the blend-feature gradient in the
+// lanes' registers (d blended vertex broadcast by shuffles against the rows the lane already holds).  Warps, then blocks,
+// are summed in a fixed order (small_bwd_reduce_kernel), and the unchanged chain backward (pose_bwd_kernel) finishes.
+// The tensor-core path pads to 256 poses and walks the vertices in 36 serial ranges: 180 us at one pose.
+constexpr int SMALLB_DA = NJ * 12;        // 288 joint-transform entries
+
+template <int KIND>
+__global__ void __launch_bounds__(SMALL_WARPS * 32, 2)
+smpl_small_bwd_kernel(const __grid_constant__ ChainTab tab, const float* __restrict__ J0, const float* __restrict__ JS,
+                      const float* __restrict__ betas, const float* __restrict__ pose, int B, int BS,
+                      const float* __restrict__ Pt_hi, const float* __restrict__ Pt_lo, const VtxRec* __restrict__ vrec,
+                      const int* __restrict__ perm, const int* __restrict__ joint_map, const int* __restrict__ vx_src,
+                      const float* __restrict__ vx_coef, const float* __restrict__ dverts, const float* __restrict__ dj49,
+                      float* __restrict__ part_dA /* [grid][288][BS] */, float* __restrict__ part_df /* [grid][BS][224] */) {
+  extern __shared__ float small_smem[];
+  float* sA = small_smem;                               // [288][BS]
+  float* sF = sA + SMALLB_DA * BS;                      // [BS][224]
+  float* sd30 = sF + BS * KA;                           // [BS][90]  joints49 gradient on its 30 vertex-borne sources
+  float* wdA = sd30 + BS * 90;                          // [SMALL_WARPS][288][BS]; later [SMALL_WARPS][BS][224] (it is larger)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool tail = lane < (KA - 128) / 4;
+  const int gw = blockIdx.x * SMALL_WARPS + warp, GW = gridDim.x * SMALL_WARPS;
+  float p[3][8];
+  auto load_rows = [&](int i) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const int64_t row = (int64_t)(3 * i + c) * KA;
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(Pt_hi + row) + lane);
+      const float4 l0 = __ldg(reinterpret_cast<const float4*>(Pt_lo + row) + lane);
+      float4 h1 = make_float4(0.f, 0.f, 0.f, 0.f), l1 = h1;
+      if (tail) {
+        h1 = __ldg(reinterpret_cast<const float4*>(Pt_hi + row + 128) + lane);
+        l1 = __ldg(reinterpret_cast<const float4*>(Pt_lo + row + 128) + lane);
+      }
+      p[c][0] = h0.x + l0.x; p[c][1] = h0.y + l0.y; p[c][2] = h0.z + l0.z; p[c][3] = h0.w + l0.w;
+      p[c][4] = h1.x + l1.x; p[c][5] = h1.y + l1.y; p[c][6] = h1.z + l1.z; p[c][7] = h1.w + l1.w;
+    }
+  };
+  if (gw < VP) load_rows(gw);
+  for (int e = threadIdx.x; e < SMALL_WARPS * SMALLB_DA * BS; e += SMALL_WARPS * 32) wdA[e] = 0.f;
+  for (int e = threadIdx.x; e < BS * 90; e += SMALL_WARPS * 32) {
+    const int b = e / 90, sc = e % 90, src = NJ + sc / 3, c = sc % 3;
+    float d = 0.f;
+    if (b < B && dj49 != nullptr)
+      for (int o = 0; o < JRR_NUM_OUT_JOINTS; o++)
+        if (joint_map[o] == src) d += dj49[((int64_t)b * JRR_NUM_OUT_JOINTS + o) * 3 + c];
+    sd30[e] = d;
+  }
+  for (int b = warp; b < BS; b += SMALL_WARPS) {
+    const bool valid = b < B;
+    const int j = lane < NJ ? lane : NJ - 1;
+    float beta[NB];
+    for (int l = 0; l < NB; l++) beta[l] = valid ? betas[b * NB + l] : 0.f;
+    float raw[9], R[9], Jr[3], GR[9], Gt[3], GRp[9], rel[3];
+    decode_rot<KIND>(pose, b, j, valid, raw, R);
+    rest_joint(J0, JS, beta, j, Jr);
+    chain_forward(tab, j, R, Jr, GR, Gt, GRp, rel);
+    for (int i = lane; i < KA; i += 32) sF[b * KA + i] = 0.f;
+    __syncwarp();
+    if (lane < NJ) {
+      for (int r = 0; r < 3; r++) {
+        const float t = Gt[r] - (GR[r * 3 + 0] * Jr[0] + GR[r * 3 + 1] * Jr[1] + GR[r * 3 + 2] * Jr[2]);
+        sA[(lane * 12 + r * 4 + 0) * BS + b] = GR[r * 3 + 0];
+        sA[(lane * 12 + r * 4 + 1) * BS + b] = GR[r * 3 + 1];
+        sA[(lane * 12 + r * 4 + 2) * BS + b] = GR[r * 3 + 2];
+        sA[(lane * 12 + r * 4 + 3) * BS + b] = t;
+      }
+      if (lane >= 1)
+        for (int i = 0; i < 9; i++) sF[b * KA + (lane - 1) * 9 + i] = R[i] - ((i % 4 == 0) ? 1.f : 0.f);
+    }
+    if (lane < NB) sF[b * KA + FEAT_BETA + lane] = beta[lane];
+    if (lane == 0) sF[b * KA + FEAT_ONE] = 1.f;
+  }
+  __syncthreads();
+
+  float dfp[8][8];                 // [pose][this lane's 8 blend features]: d loss / d feature, summed over the warp's vertices
+#pragma unroll
+  for (int b = 0; b < 8; b++)
+#pragma unroll
+    for (int e = 0; e < 8; e++) dfp[b][e] = 0.f;
+  float* mydA = wdA + warp * SMALLB_DA * BS;
+  for (int i = gw; i < VP; i += GW) {
+    if (i != gw) load_rows(i);
+    const int vid = perm[i];
+    if (vid < 0) continue;
+    const VtxRec* rec = vrec + i;
+    const uint32_t meta = __ldg(&rec->meta);
+    float wk[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) wk[k] = __ldg(&rec->w[k]);
+    const int xptr = __ldg(&rec->xptr), xcnt = __ldg(&rec->xcnt);
+    float x = 0.f, y = 0.f, z = 0.f;
+    for (int b0 = 0; b0 < BS; b0 += SMALL_CHUNK) {
+      float acc[SMALL_CHUNK][3];
+#pragma unroll
+      for (int bb = 0; bb < SMALL_CHUNK; bb++) {
+        const float4 f0 = *reinterpret_cast<const float4*>(sF + (b0 + bb) * KA + 4 * lane);
+        float4 f1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tail) f1 = *reinterpret_cast<const float4*>(sF + (b0 + bb) * KA + 128 + 4 * lane);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          float a = p[c][0] * f0.x;
+          a = fmaf(p[c][1], f0.y, a); a = fmaf(p[c][2], f0.z, a); a = fmaf(p[c][3], f0.w, a);
+          a = fmaf(p[c][4], f1.x, a); a = fmaf(p[c][5], f1.y, a); a = fmaf(p[c][6], f1.z, a); a = fmaf(p[c][7], f1.w, a);
+          acc[bb][c] = a;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int bb = 0; bb < SMALL_CHUNK; bb++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) acc[bb][c] += __shfl_xor_sync(FULL, acc[bb][c], o);
+#pragma unroll
+      for (int bb = 0; bb < SMALL_CHUNK; bb++)
+        if (lane == b0 + bb) { x = acc[bb][0]; y = acc[bb][1]; z = acc[bb][2]; }
+    }
+    // lane b: the vertex gradient of pose b, its share of dA, and d blended vertex
+    float dvp0 = 0.f, dvp1 = 0.f, dvp2 = 0.f;
+    if (lane < B) {
+      const int b = lane;
+      float dv[3] = {0.f, 0.f, 0.f};
+      if (dverts != nullptr) {
+        const float* src = dverts + ((int64_t)b * V + vid) * 3;
+        dv[0] = src[0]; dv[1] = src[1]; dv[2] = src[2];
+      }
+      for (int q = 0; q < xcnt; q++) {
+        const float cf = vx_coef[xptr + q];
+        const float* d3 = sd30 + b * 90 + vx_src[xptr + q] * 3;
+        dv[0] = fmaf(cf, d3[0], dv[0]); dv[1] = fmaf(cf, d3[1], dv[1]); dv[2] = fmaf(cf, d3[2], dv[2]);
+      }
+      const float v4[4] = {x, y, z, 1.f};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int j = (int)((meta >> (5 * k)) & 31u);
+        const float* a = sA + j * 12 * BS + b;
+        float* da = mydA + j * 12 * BS + b;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          const float u = wk[k] * dv[r];
+          dvp0 = fmaf(a[(r * 4 + 0) * BS], u, dvp0);
+          dvp1 = fmaf(a[(r * 4 + 1) * BS], u, dvp1);
+          dvp2 = fmaf(a[(r * 4 + 2) * BS], u, dvp2);
+#pragma unroll
+          for (int cc = 0; cc < 4; cc++) da[(r * 4 + cc) * BS] += u * v4[cc];
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      if (b < B) {                                   // (uniform)
+        const float d0 = __shfl_sync(FULL, dvp0, b), d1 = __shfl_sync(FULL, dvp1, b), d2 = __shfl_sync(FULL, dvp2, b);
+#pragma unroll
+        for (int e = 0; e < 8; e++) dfp[b][e] = fmaf(d0, p[0][e], fmaf(d1, p[1][e], fmaf(d2, p[2][e], dfp[b][e])));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- joint-transform gradients: warps summed in order -> this block's partial
+  for (int e = threadIdx.x; e < SMALLB_DA * BS; e += SMALL_WARPS * 32) {
+    float a = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < SMALL_WARPS; w8++) a += wdA[w8 * SMALLB_DA * BS + e];
+    part_dA[(int64_t)blockIdx.x * SMALLB_DA * BS + e] = a;
+  }
+  __syncthreads();
+  // ---- blend-feature gradients: lanes' registers -> [warp][pose][224] (re-using the accumulator region), warps summed in order
+  float* wdf = wdA;
+#pragma unroll
+  for (int b = 0; b < 8; b++) {
+    if (b < BS) {
+      float* dst = wdf + (warp * BS + b) * KA;
+      *reinterpret_cast<float4*>(dst + 4 * lane) = make_float4(dfp[b][0], dfp[b][1], dfp[b][2], dfp[b][3]);
+      if (tail) *reinterpret_cast<float4*>(dst + 128 + 4 * lane) = make_float4(dfp[b][4], dfp[b][5], dfp[b][6], dfp[b][7]);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < BS * KA; e += SMALL_WARPS * 32) {
+    float a = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < SMALL_WARPS; w8++) a += wdf[w8 * BS * KA + e];
+    part_df[(int64_t)blockIdx.x * BS * KA + e] = a;
+  }
+}
+
+// block partials summed in order -> dAT [288][BP], dfeat [1][BP][224] (one split), dJp [BP][72] for the chain backward
+__global__ void small_bwd_reduce_kernel(const float* __restrict__ part_dA, const float* __restrict__ part_df, int nblk, int B,
+                                        int BS, int64_t BP, const int* __restrict__ joint_map, const float* __restrict__ dj49,
+                                        float* __restrict__ dAT, float* __restrict__ dfeat, float* __restrict__ dJp) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nA = SMALLB_DA * BS, nF = BS * KA, nJ = BS * 72;
+  if (idx < nA) {
+    const int e = idx / BS, b = idx % BS;
+    float a = 0.f;
+    for (int k = 0; k < nblk; k++) a += part_dA[(int64_t)k * nA + idx];
+    dAT[(int64_t)e * BP + b] = b < B ? a : 0.f;
+  } else if (idx < nA + nF) {
+    const int q = idx - nA, b = q / KA, k = q % KA;
+    float a = 0.f;
+    for (int kb = 0; kb < nblk; kb++) a += part_df[(int64_t)kb * nF + q];
+    dfeat[(int64_t)b * KA + k] = b < B ? a : 0.f;
+  } else if (idx < nA + nF + nJ) {
+    const int q = idx - nA - nF, b = q / 72, src = (q % 72) / 3, c = q % 3;
+    float d = 0.f;
+    if (b < B && dj49 != nullptr)
+      for (int o = 0; o < JRR_NUM_OUT_JOINTS; o++)
+        if (joint_map[o] == src) d += dj49[((int64_t)b * JRR_NUM_OUT_JOINTS + o) * 3 + c];
+    dJp[(int64_t)b * 72 + src * 3 + c] = d;
+  }
+}
+
+bool smpl_small_bwd_available(const JrrModel* m, int64_t B) {
+  static const bool on = [] { const char* e = getenv("JRR_SMALL_BWD"); return !(e && e[0] == '0'); }();
+  return on && B <= SMALL_MAX && m->n_pass == 1 && m->gemm_impl == 0;
+}
+
+// leaves dAT / dfeat (ksplit = 1) / dJp in the workspace for launch_pose_bwd; scratch: the (idle) blend-gradient buffer
+int launch_smpl_small_bwd(const JrrModel* m, Workspace& w, const float* betas, const float* pose, int kind,
+                          const float* dverts, const float* dj49, cudaStream_t st) {
+  const int B = (int)w.B, BS = (int)round_up(w.B, SMALL_CHUNK);
+  const int grid = 2 * m->num_sms;
+  const size_t smem = (size_t)(SMALLB_DA * BS + BS * KA + BS * 90 + SMALL_WARPS * SMALLB_DA * BS) * sizeof(float);
+  float* part_dA = w.dvp_hi;
+  float* part_df = part_dA + (size_t)grid * SMALLB_DA * BS;
+#define JRR_SB(KIND)                                                                                               \
+  do {                                                                                                             \
+    auto kern = smpl_small_bwd_kernel<KIND>;                                                                       \
+    JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+    kern<<<grid, SMALL_WARPS * 32, smem, st>>>(m->chain, m->J0, m->JS, betas, pose, B, BS, m->Pt_hi, m->Pt_lo,      \
+                                               m->passes[0].vrec, m->perm, m->joint_map, m->vx_src, m->vx_coef, dverts, \
+                                               dj49, part_dA, part_df);                                            \
+  } while (0)
+  switch (kind) {
+    case JRR_POSE_ROTMAT: JRR_SB(JRR_POSE_ROTMAT); break;
+    case JRR_POSE_AXIS_ANGLE: JRR_SB(JRR_POSE_AXIS_ANGLE); break;
+    case JRR_POSE_ROT6D: JRR_SB(JRR_POSE_ROT6D); break;
+    default: return fail(JRR_ERR_INVALID, "unknown pose kind");
+  }
+#undef JRR_SB
+  JRR_LAUNCH_CHECK();
+  const int n = SMALLB_DA * BS + BS * KA + BS * 72;
+  small_bwd_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part_dA, part_df, grid, B, BS, w.BP, m->joint_map, dj49, w.dAT,
+                                                          w.dfeat, w.dJp);
+  JRR_LAUNCH_CHECK();
+  w.ksplit = 1;
+  return JRR_OK;
+}
+
 // ---- host wrappers ---------------------------------------------------------------------------
 int launch_adam_params(const Workspace& w, bool use_critic, bool use_shape, float* x6, float* betas, float* adam_m,
                        float* adam_v, int32_t* step_count, float lr, cudaStream_t st, const float* ext_dx6,

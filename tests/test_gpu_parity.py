@@ -188,6 +188,47 @@ def test_smpl_backward_matches_oracle_autograd(impl, pose2rot, smpl_tc, smpl_sim
     assert eb < 1e-4 and eo < 1e-4 and ep < 1e-4
 
 
+@pytest.mark.parametrize("B", [1, 3, 4, 5, 8])
+@pytest.mark.parametrize("pose2rot", [False, True])
+def test_smpl_small_batch_backward(B, pose2rot, smpl_tc, osmpl64, jrr):
+    """Up to 8 poses SMPL.backward is three launches (warp-per-vertex gradients, fixed-order reduction, chain backward:
+    csrc/jrr_pose.cu smpl_small_bwd_kernel) instead of the padded tensor-core path: gradients w.r.t. betas / orientation /
+    pose vs fp64 autograd, with vertex-only, joints-only and combined upstream gradients; reruns are bit-identical."""
+    inp = jrr.synthetic.make_pose_inputs(16, 23)
+    g = torch.Generator().manual_seed(29)
+    betas = torch.from_numpy(inp["true_betas"][:B])
+    if pose2rot:
+        go, bp = torch.randn(B, 3, generator=g), 0.3 * torch.randn(B, 69, generator=g)
+    else:
+        R = torch.from_numpy(inp["true_rotmat"][:B])
+        go, bp = R[:, :1].contiguous(), R[:, 1:].contiguous()
+    wv, wj = torch.randn(B, 6890, 3, generator=g), torch.randn(B, 49, 3, generator=g)
+    nat = smpl_tc.native()
+
+    def run(fn, dt, dev, use_v, use_j):
+        b = betas.to(dev, dt).requires_grad_(True)
+        o = go.to(dev, dt).requires_grad_(True)
+        p = bp.to(dev, dt).requires_grad_(True)
+        out = fn(betas=b, body_pose=p, global_orient=o, pose2rot=pose2rot)
+        loss = 0
+        if use_v:
+            loss = loss + (out.vertices * wv.to(dev, dt)).sum()
+        if use_j:
+            loss = loss + (out.joints * wj.to(dev, dt)).sum()
+        loss.backward()
+        return b.grad, o.grad, p.grad
+
+    for use_v, use_j in ((True, True), (True, False), (False, True)):
+        rb, ro, rp = run(osmpl64, torch.float64, "cpu", use_v, use_j)
+        gb, go_, gp = run(smpl_tc, torch.float32, DEV, use_v, use_j)
+        assert nat.launches == 3, nat.launches
+        eb, eo, ep = rel(gb, rb), rel(go_, ro), rel(gp, rp)
+        assert eb < 1e-4 and eo < 1e-4 and ep < 1e-4, (use_v, use_j, eb, eo, ep)
+    gb2, go2, gp2 = run(smpl_tc, torch.float32, DEV, False, True)
+    assert torch.equal(gb2, gb) and torch.equal(go2, go_) and torch.equal(gp2, gp)
+    print(f"[small backward B={B} pose2rot={pose2rot}] dbetas {eb:.2e} dorient {eo:.2e} dpose {ep:.2e}, {nat.launches} launches")
+
+
 # ------------------------------------------------------------------ find_joints / critic
 @pytest.mark.parametrize("which", ["shipped", "dense"])
 def test_find_joints_matches_oracle(which, smpl_tc, osmpl64, oracle, jrr, J_shipped, J_dense, frames64):
