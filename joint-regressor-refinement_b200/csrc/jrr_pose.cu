@@ -871,6 +871,22 @@ smpl_small_bwd_kernel(const __grid_constant__ ChainTab tab, const float* __restr
   }
 }
 
+// fixed-order sum of `n` block partials `stride` floats apart: four interleaved chains (eight loads in flight per thread; one
+// chain of dependent adds behind one load at a time made this kernel as long as the gradient kernel itself, 23 us)
+__device__ __forceinline__ float small_sum_partials(const float* __restrict__ p, int n, int64_t stride) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+#pragma unroll 2
+  for (; k + 3 < n; k += 4) {
+    a0 += p[(int64_t)k * stride];
+    a1 += p[(int64_t)(k + 1) * stride];
+    a2 += p[(int64_t)(k + 2) * stride];
+    a3 += p[(int64_t)(k + 3) * stride];
+  }
+  for (; k < n; k++) a0 += p[(int64_t)k * stride];
+  return (a0 + a1) + (a2 + a3);
+}
+
 // block partials summed in order -> dAT [288][BP], dfeat [1][BP][224] (one split), dJp [BP][72] for the chain backward
 __global__ void small_bwd_reduce_kernel(const float* __restrict__ part_dA, const float* __restrict__ part_df, int nblk, int B,
                                         int BS, int64_t BP, const int* __restrict__ joint_map, const float* __restrict__ dj49,
@@ -879,13 +895,11 @@ __global__ void small_bwd_reduce_kernel(const float* __restrict__ part_dA, const
   const int nA = SMALLB_DA * BS, nF = BS * KA, nJ = BS * 72;
   if (idx < nA) {
     const int e = idx / BS, b = idx % BS;
-    float a = 0.f;
-    for (int k = 0; k < nblk; k++) a += part_dA[(int64_t)k * nA + idx];
+    const float a = small_sum_partials(part_dA + idx, nblk, nA);
     dAT[(int64_t)e * BP + b] = b < B ? a : 0.f;
   } else if (idx < nA + nF) {
     const int q = idx - nA, b = q / KA, k = q % KA;
-    float a = 0.f;
-    for (int kb = 0; kb < nblk; kb++) a += part_df[(int64_t)kb * nF + q];
+    const float a = small_sum_partials(part_df + q, nblk, nF);
     dfeat[(int64_t)b * KA + k] = b < B ? a : 0.f;
   } else if (idx < nA + nF + nJ) {
     const int q = idx - nA - nF, b = q / 72, src = (q % 72) / 3, c = q % 3;
