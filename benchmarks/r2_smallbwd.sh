@@ -7,5 +7,5 @@ import jrr_b200 as jrr
 dev = torch.device("cuda", 0)
 smpl = jrr.SMPL(model_dict=jrr.synthetic.make_smpl_model(0), create_transl=False).to(dev)
 pk = {"bf16_burst": 1638.9, "hbm_gbs": 6555.5}
-for r in bench.run_c5(jrr, smpl, dev, pk, [1, 4, 8, 16, 256]): print(json.dumps(r))
+for r in bench.run_c5(jrr, smpl, dev, pk, [1, 8, 9, 16, 32]): print(json.dumps(r))
 PY

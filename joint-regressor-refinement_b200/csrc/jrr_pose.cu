@@ -6,6 +6,7 @@
 // smplx.lbs.{batch_rodrigues, vertices2joints, batch_rigid_transform} reached through
 // scripts/smpl.py:72-74, their autograd backward (scripts/optimize.py:264) and
 // torch.optim.Adam.step (scripts/optimize.py:201-202,265).
+#include <algorithm>
 #include <cstdlib>
 
 #include "jrr_internal.cuh"
@@ -888,62 +889,74 @@ __device__ __forceinline__ float small_sum_partials(const float* __restrict__ p,
 }
 
 // block partials summed in order -> dAT [288][BP], dfeat [1][BP][224] (one split), dJp [BP][72] for the chain backward
+// (b0: the first pose of this group of up to 8 inside the batch; dj49 already points at the group)
 __global__ void small_bwd_reduce_kernel(const float* __restrict__ part_dA, const float* __restrict__ part_df, int nblk, int B,
-                                        int BS, int64_t BP, const int* __restrict__ joint_map, const float* __restrict__ dj49,
-                                        float* __restrict__ dAT, float* __restrict__ dfeat, float* __restrict__ dJp) {
+                                        int BS, int64_t BP, int b0, const int* __restrict__ joint_map,
+                                        const float* __restrict__ dj49, float* __restrict__ dAT, float* __restrict__ dfeat,
+                                        float* __restrict__ dJp) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int nA = SMALLB_DA * BS, nF = BS * KA, nJ = BS * 72;
   if (idx < nA) {
     const int e = idx / BS, b = idx % BS;
     const float a = small_sum_partials(part_dA + idx, nblk, nA);
-    dAT[(int64_t)e * BP + b] = b < B ? a : 0.f;
+    dAT[(int64_t)e * BP + b0 + b] = b < B ? a : 0.f;
   } else if (idx < nA + nF) {
     const int q = idx - nA, b = q / KA, k = q % KA;
     const float a = small_sum_partials(part_df + q, nblk, nF);
-    dfeat[(int64_t)b * KA + k] = b < B ? a : 0.f;
+    dfeat[(int64_t)(b0 + b) * KA + k] = b < B ? a : 0.f;
   } else if (idx < nA + nF + nJ) {
     const int q = idx - nA - nF, b = q / 72, src = (q % 72) / 3, c = q % 3;
     float d = 0.f;
     if (b < B && dj49 != nullptr)
       for (int o = 0; o < JRR_NUM_OUT_JOINTS; o++)
         if (joint_map[o] == src) d += dj49[((int64_t)b * JRR_NUM_OUT_JOINTS + o) * 3 + c];
-    dJp[(int64_t)b * 72 + src * 3 + c] = d;
+    dJp[(int64_t)(b0 + b) * 72 + src * 3 + c] = d;
   }
 }
+
+constexpr int SMALLB_MAX = 16;        // two groups of 8 poses still beat the padded tensor-core path (127 us at 8, 250 us at 16)
 
 bool smpl_small_bwd_available(const JrrModel* m, int64_t B) {
   static const bool on = [] { const char* e = getenv("JRR_SMALL_BWD"); return !(e && e[0] == '0'); }();
-  return on && B <= SMALL_MAX && m->n_pass == 1 && m->gemm_impl == 0;
+  return on && B <= SMALLB_MAX && m->n_pass == 1 && m->gemm_impl == 0;
 }
 
-// leaves dAT / dfeat (ksplit = 1) / dJp in the workspace for launch_pose_bwd; scratch: the (idle) blend-gradient buffer
+// leaves dAT / dfeat (ksplit = 1) / dJp in the workspace for launch_pose_bwd; scratch: the (idle) blend-gradient buffer.
+// Groups of up to 8 poses (the lanes' register budget for the feature gradients), each with its own pair of launches.
 int launch_smpl_small_bwd(const JrrModel* m, Workspace& w, const float* betas, const float* pose, int kind,
                           const float* dverts, const float* dj49, cudaStream_t st) {
-  const int B = (int)w.B, BS = (int)round_up(w.B, SMALL_CHUNK);
   const int grid = 2 * m->num_sms;
-  const size_t smem = (size_t)(SMALLB_DA * BS + BS * KA + BS * 90 + SMALL_WARPS * SMALLB_DA * BS) * sizeof(float);
-  float* part_dA = w.dvp_hi;
-  float* part_df = part_dA + (size_t)grid * SMALLB_DA * BS;
+  const int pose_stride = kind == JRR_POSE_ROTMAT ? NJ * 9 : (kind == JRR_POSE_AXIS_ANGLE ? NJ * 3 : NJ * 6);
+  if (kind != JRR_POSE_ROTMAT && kind != JRR_POSE_AXIS_ANGLE && kind != JRR_POSE_ROT6D) return fail(JRR_ERR_INVALID, "unknown pose kind");
+  for (int b0 = 0; b0 < (int)w.B; b0 += SMALL_MAX) {
+    const int B = std::min((int)w.B - b0, SMALL_MAX), BS = (int)round_up(B, SMALL_CHUNK);
+    const size_t smem = (size_t)(SMALLB_DA * BS + BS * KA + BS * 90 + SMALL_WARPS * SMALLB_DA * BS) * sizeof(float);
+    float* part_dA = w.dvp_hi;
+    float* part_df = part_dA + (size_t)grid * SMALLB_DA * BS;
+    const float* g_betas = betas + (size_t)b0 * NB;
+    const float* g_pose = pose + (size_t)b0 * pose_stride;
+    const float* g_dv = dverts ? dverts + (size_t)b0 * V * 3 : nullptr;
+    const float* g_dj = dj49 ? dj49 + (size_t)b0 * JRR_NUM_OUT_JOINTS * 3 : nullptr;
 #define JRR_SB(KIND)                                                                                               \
-  do {                                                                                                             \
-    auto kern = smpl_small_bwd_kernel<KIND>;                                                                       \
-    JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
-    kern<<<grid, SMALL_WARPS * 32, smem, st>>>(m->chain, m->J0, m->JS, betas, pose, B, BS, m->Pt_hi, m->Pt_lo,      \
-                                               m->passes[0].vrec, m->perm, m->joint_map, m->vx_src, m->vx_coef, dverts, \
-                                               dj49, part_dA, part_df);                                            \
-  } while (0)
-  switch (kind) {
-    case JRR_POSE_ROTMAT: JRR_SB(JRR_POSE_ROTMAT); break;
-    case JRR_POSE_AXIS_ANGLE: JRR_SB(JRR_POSE_AXIS_ANGLE); break;
-    case JRR_POSE_ROT6D: JRR_SB(JRR_POSE_ROT6D); break;
-    default: return fail(JRR_ERR_INVALID, "unknown pose kind");
-  }
+    do {                                                                                                           \
+      auto kern = smpl_small_bwd_kernel<KIND>;                                                                     \
+      JRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+      kern<<<grid, SMALL_WARPS * 32, smem, st>>>(m->chain, m->J0, m->JS, g_betas, g_pose, B, BS, m->Pt_hi, m->Pt_lo, \
+                                                 m->passes[0].vrec, m->perm, m->joint_map, m->vx_src, m->vx_coef, g_dv, \
+                                                 g_dj, part_dA, part_df);                                          \
+    } while (0)
+    switch (kind) {
+      case JRR_POSE_ROTMAT: JRR_SB(JRR_POSE_ROTMAT); break;
+      case JRR_POSE_AXIS_ANGLE: JRR_SB(JRR_POSE_AXIS_ANGLE); break;
+      default: JRR_SB(JRR_POSE_ROT6D); break;
+    }
 #undef JRR_SB
-  JRR_LAUNCH_CHECK();
-  const int n = SMALLB_DA * BS + BS * KA + BS * 72;
-  small_bwd_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part_dA, part_df, grid, B, BS, w.BP, m->joint_map, dj49, w.dAT,
-                                                          w.dfeat, w.dJp);
-  JRR_LAUNCH_CHECK();
+    JRR_LAUNCH_CHECK();
+    const int n = SMALLB_DA * BS + BS * KA + BS * 72;
+    small_bwd_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part_dA, part_df, grid, B, BS, w.BP, b0, m->joint_map, g_dj, w.dAT,
+                                                            w.dfeat, w.dJp);
+    JRR_LAUNCH_CHECK();
+  }
   w.ksplit = 1;
   return JRR_OK;
 }
