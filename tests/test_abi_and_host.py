@@ -37,6 +37,21 @@ def test_argument_errors_surface_without_a_gpu(jrr):
     assert L.jrr_model_create(None, None) == 1
     assert b"null" in L.jrr_last_error()
     assert L.jrr_workspace_bytes(None, 10) == 0
+    # entry points added in round 2: argument checks come before any CUDA call
+    assert L.jrr_set_external_gradient(None, None, None, None) != 0 and b"null model" in L.jrr_last_error()
+    assert L.jrr_find_joints_backward(None, 4, None, None, 0, None, None, None, None, 0, None) != 0
+    assert L.jrr_silhouette_forward(0, None, 6890, None, None, 13776, 224, 22.3, 1e-4, 1, None, 0, None, None, None, None, 0, None) != 0
+    assert b"empty batch" in L.jrr_last_error()
+    assert L.jrr_silhouette_forward(2, None, 6890, None, None, 13776, 224, 22.3, 1e-4, 1, None, 0, None, None, None, None, 0, None) != 0
+    assert b"null argument" in L.jrr_last_error()
+    assert L.jrr_silhouette_forward(2, None, 6890, None, None, 13776, 0, 22.3, 1e-4, 1, None, 0, None, None, None, None, 0, None) != 0
+    assert b"image size" in L.jrr_last_error()
+    assert L.jrr_silhouette_backward(2, None, 6890, None, None, 13776, None, None, 224, 22.3, -1.0, 1, None, None, None, None, 0, 1.0,
+                                     None, None, None, 0, None) != 0
+    assert b"sigma" in L.jrr_last_error()
+    need = L.jrr_silhouette_workspace_bytes(4, 6890, 13776, 224)
+    # ndc + 64-bit z-buffer + per-face corner gradients + per-frame losses (each 256-byte aligned)
+    assert need >= 4 * (6890 * 12 + 224 * 224 * 8 + 13776 * 24 + 4) and need < 4 * (6890 * 12 + 224 * 224 * 8 + 13776 * 24 + 4) + 2048
 
 
 def test_no_cpu_fallback(jrr, model):
