@@ -1,4 +1,4 @@
-timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 -k "folded or fold or refit or loop or six_weight or bench" 2>&1 | tail -4
+timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 -k "folded or fold or refit or loop or six_weight or bench or 100_iterations or find_joints" 2>&1 | tail -4
 cat > /tmp/fold_probe.py <<'PY'
 import os, sys
 sys.path.insert(0, os.getcwd())
@@ -13,7 +13,7 @@ torch.cuda.synchronize()
 PY
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_fold_launches.csv python /tmp/fold_probe.py > /dev/null 2>&1
 grep -i "fold" gpurun_out/r2_fold_launches.csv | awk -F'","' '{print $5, $NF}' | cut -c1-100 | tail -5
-for cfg in "JRR_FOLD_RUNS=1" "JRR_FOLD_RUNS=0"; do
+for cfg in "JRR_FOLD_GEMM=1" "JRR_FOLD_GEMM=0"; do
   env $cfg timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-secondary > gpurun_out/r2_tmp.json 2> gpurun_out/r2_tmp.err || { echo "$cfg FAILED"; tail -3 gpurun_out/r2_tmp.err; }
   python - "$cfg" <<'PY'
 import json,sys

@@ -143,6 +143,7 @@ struct JrrModel {
   // augmented blend matrix, tf32 hi/lo split, both majors
   float *Pt_hi = nullptr, *Pt_lo = nullptr;  // [NP][KA]  (K contiguous)  forward B operand
   float *P_hi = nullptr, *P_lo = nullptr;    // [KA][NP]  (N contiguous)  backward B operand
+  float *P3_hi = nullptr, *P3_lo = nullptr;  // [3][KA][VP] (vertex contiguous, per coordinate): B operand of the fold GEMM
   float* Pn = nullptr;                       // [KA][3*6890] natural-order fp32 master the packings are gathered from
   float* J0 = nullptr;                       // [24][3]      J_regressor . v_template
   float* JS = nullptr;                       // [24][3][10]  J_regressor . shapedirs
@@ -213,6 +214,8 @@ struct JrrModel {
   float *Tt_hi = nullptr, *Tt_lo = nullptr;  // [KA][FOLD_NP]   backward B operand
   float* Tc = nullptr;                       // [24][17]        sum_v Jhat_iv w_vj
   double* fold_part = nullptr;               // scratch of fold_kernel
+  float *fg_wj = nullptr, *fg_wj_hi = nullptr, *fg_wj_lo = nullptr;   // [512][VP] w * Jhat per (joint, regressor row): A operand of the fold GEMM
+  float* fg_part = nullptr;                  // [3][36][512][224] K-split partials of the fold GEMM
   double* fold_wj = nullptr;                 // [17][VP][4] w * Jhat in double (fold_prep_kernel)
   double* fold_acc = nullptr;                // [1224*224 + 24*17] the folded operator in double (fold_gather_kernel)
   double* fold_ev = nullptr;                 // [fold_ev_cap][17][4][224] run sums per flush event (fold_runs_kernel)

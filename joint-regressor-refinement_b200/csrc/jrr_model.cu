@@ -195,7 +195,8 @@ __global__ void bump_kernel(int32_t* c) { *c += 1; }
 // packed blend matrices from the natural-order master: P[k][3i+c] = Pn[k][3 perm[i] + c]
 __global__ void repack_blend_kernel(const float* __restrict__ Pn, const int* __restrict__ perm,
                                     float* __restrict__ P_hi, float* __restrict__ P_lo,
-                                    float* __restrict__ Pt_hi, float* __restrict__ Pt_lo) {
+                                    float* __restrict__ Pt_hi, float* __restrict__ Pt_lo,
+                                    float* __restrict__ P3_hi, float* __restrict__ P3_lo) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)KA * NP) return;
   const int k = (int)(idx / NP), n = (int)(idx % NP);
@@ -211,6 +212,9 @@ __global__ void repack_blend_kernel(const float* __restrict__ Pn, const int* __r
   P_lo[idx] = lo;
   Pt_hi[(int64_t)n * KA + k] = hi;
   Pt_lo[(int64_t)n * KA + k] = lo;
+  // per coordinate, feature-major, vertex-contiguous: the B operand of the fold GEMM (K = vertices)
+  P3_hi[((int64_t)(n % 3) * KA + k) * VP + n / 3] = hi;
+  P3_lo[((int64_t)(n % 3) * KA + k) * VP + n / 3] = lo;
 }
 
 // active[v] = 1 when column v of the normalised regressor has a non-zero entry
@@ -641,6 +645,105 @@ static int launch_fold_runs(JrrModel* m, cudaStream_t st) {
   return JRR_OK;
 }
 
+// ---- the fold as three tensor-core GEMMs (default; JRR_FOLD_GEMM=0 selects fold_kernel) ------------------------------------
+// T[(j,i,c)][k] = sum_p WJ[(j,i)][p] P3[c][k][p] with WJ[(j,i)][p] = w_pj Jhat_ip: per coordinate c one [512 x 6912] x
+// [6912 x 224] GEMM over the packed vertices -- the mirror image of the refit's unfold GEMM above.  fold_kernel does the same
+// sum with 421 M double-precision FMAs (0.27 ms: the DFMAs pace it, three restructurings measured); the tensor cores do it in
+// 3xTF32 over 36 K splits of 192 vertices (truncation grows with the length of a split's accumulation chain: 1e-6 relative at
+// 192-224, the blend GEMM's own figure), and the splits are summed in double in a fixed order.  WJ is 408 x 6912 with
+// 4 x 17 non-zeros per vertex: dense on purpose -- 11.6 GFLOP of 3xTF32 is 20 us of tensor time.
+constexpr int FG_M = 512;                  // (j, i) rows, 408 padded to the 128-row tile
+constexpr int FG_KSPLIT = 36;              // 6912 vertices = 36 x 192
+
+// (one launch per skinning pass, in order: thread (p, i) owns WJ[(., i)][p], so the passes of a vertex add up without races)
+__global__ void fold_wj_kernel(const VtxRec* __restrict__ vrec, float* __restrict__ WJ) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NH * VP) return;
+  const int i = idx / VP, p = idx % VP;
+  const float jh = vrec[p].jh[i];
+  const uint32_t meta = vrec[p].meta;
+#pragma unroll
+  for (int s4 = 0; s4 < 4; s4++) {
+    const float wgt = vrec[p].w[s4];
+    if (wgt != 0.f && jh != 0.f) WJ[(int64_t)(((meta >> (5 * s4)) & 31u) * NH + i) * VP + p] += wgt * jh;
+  }
+}
+
+__global__ void fold_wj_split_kernel(const float* __restrict__ WJ, float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)FG_M * VP) return;
+  const float x = WJ[idx];
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  const float h = __uint_as_float(r);
+  const float d = x - h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
+  hi[idx] = h;
+  lo[idx] = __uint_as_float(r);
+}
+
+// c_ji = sum_p WJ[(j,i)][p]: one warp per row, lane-strided partial sums in double + a butterfly (fixed order)
+__global__ void fold_rowsum_kernel(const float* __restrict__ WJ, float* __restrict__ Tc) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= NJ * NH) return;
+  double a = 0.0;
+  for (int p = lane; p < VP; p += 32) a += (double)WJ[(int64_t)row * VP + p];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) Tc[row] = (float)a;
+}
+
+// K splits summed in double, rounded once, split into the tf32 pair, both majors
+__global__ void fold_gemm_finish_kernel(const float* __restrict__ part, float* __restrict__ T_hi, float* __restrict__ T_lo,
+                                        float* __restrict__ Tt_hi, float* __restrict__ Tt_lo) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)FOLD_N * KA) return;
+  const int n = (int)(idx / KA), k = (int)(idx % KA);
+  const int c = n % 3, ji = n / 3;           // n = (j * 17 + i) * 3 + c
+  const float* src = part + (int64_t)c * FG_KSPLIT * FG_M * KA + (int64_t)ji * KA + k;
+  double a = 0.0;
+  for (int sp = 0; sp < FG_KSPLIT; sp++) a += (double)src[(int64_t)sp * FG_M * KA];
+  const float x = (float)a;
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  const float hi = __uint_as_float(r);
+  const float d = x - hi;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
+  const float lo = __uint_as_float(r);
+  T_hi[idx] = hi;
+  T_lo[idx] = lo;
+  Tt_hi[(int64_t)k * FOLD_NP + n] = hi;
+  Tt_lo[(int64_t)k * FOLD_NP + n] = lo;
+}
+
+static int launch_fold_gemm(JrrModel* m, cudaStream_t st) {
+  if (!m->fg_wj) {
+    if (int rc = dalloc(m, &m->fg_wj, (size_t)FG_M * VP)) return rc;                    // zero-filled: the padding rows stay zero
+    if (int rc = dalloc(m, &m->fg_wj_hi, (size_t)FG_M * VP, false)) return rc;
+    if (int rc = dalloc(m, &m->fg_wj_lo, (size_t)FG_M * VP, false)) return rc;
+    if (int rc = dalloc(m, &m->fg_part, (size_t)3 * FG_KSPLIT * FG_M * KA, false)) return rc;
+  }
+  JRR_CUDA(cudaMemsetAsync(m->fg_wj, 0, sizeof(float) * (size_t)NJ * NH * VP, st));
+  for (int pass = 0; pass < m->n_pass; pass++) {
+    fold_wj_kernel<<<(NH * VP + 255) / 256, 256, 0, st>>>(m->passes[pass].vrec, m->fg_wj);
+    JRR_LAUNCH_CHECK();
+  }
+  fold_wj_split_kernel<<<(unsigned)(((int64_t)FG_M * VP + 255) / 256), 256, 0, st>>>(m->fg_wj, m->fg_wj_hi, m->fg_wj_lo);
+  JRR_LAUNCH_CHECK();
+  fold_rowsum_kernel<<<(NJ * NH * 32 + 255) / 256, 256, 0, st>>>(m->fg_wj, m->Tc);
+  JRR_LAUNCH_CHECK();
+  for (int c = 0; c < 3; c++) {
+    GemmDesc g{};                       // part_c[split][(j,i)][k] = sum_{p in split} WJ[(j,i)][p] P3[c][k][p]
+    g.A_hi = m->fg_wj_hi; g.A_lo = m->fg_wj_lo; g.lda = VP;
+    g.B_hi = m->P3_hi + (size_t)c * KA * VP; g.B_lo = m->P3_lo + (size_t)c * KA * VP; g.ldb = VP;
+    g.M = FG_M; g.N = KA; g.K = VP / FG_KSPLIT; g.ksplit = FG_KSPLIT; g.epi = EPI_STORE_SPLITK;
+    g.out0 = m->fg_part + (size_t)c * FG_KSPLIT * FG_M * KA; g.ldo = KA;
+    if (int rc = launch_gemm(m, g, st)) return rc;
+  }
+  fold_gemm_finish_kernel<<<(unsigned)(((int64_t)FOLD_N * KA + 255) / 256), 256, 0, st>>>(m->fg_part, m->T_hi, m->T_lo, m->Tt_hi, m->Tt_lo);
+  JRR_LAUNCH_CHECK();
+  return JRR_OK;
+}
+
 int launch_fold(JrrModel* m, cudaStream_t st) {
   if (!m->T_hi) {
     if (int rc = dalloc(m, &m->T_hi, (size_t)FOLD_NP * KA)) return rc;      // zero-filled: the padding rows stay zero
@@ -654,6 +757,8 @@ int launch_fold(JrrModel* m, cudaStream_t st) {
   }
   static const bool runs = [] { const char* e = getenv("JRR_FOLD_RUNS"); return e && e[0] == '1'; }();
   if (runs) return launch_fold_runs(m, st);
+  static const bool fgemm = [] { const char* e = getenv("JRR_FOLD_GEMM"); return !(e && e[0] == '0'); }();
+  if (fgemm) return launch_fold_gemm(m, st);
   for (int pass = 0; pass < m->n_pass; pass++) {      // linear in the skinning weights: passes add up in the fp64 partials
     const PassTab& t = m->passes[pass];
     fold_prep_kernel<<<(NH * VP + 255) / 256, 256, 0, st>>>(t.vrec, t.vrec, m->fold_wj);
@@ -854,7 +959,7 @@ int build_packing(JrrModel* m, const std::vector<uint8_t>& active) {
   }
   m->select_pass(0);
   const int64_t n = (int64_t)KA * NP;
-  repack_blend_kernel<<<(unsigned)((n + 255) / 256), 256>>>(m->Pn, m->perm, m->P_hi, m->P_lo, m->Pt_hi, m->Pt_lo);
+  repack_blend_kernel<<<(unsigned)((n + 255) / 256), 256>>>(m->Pn, m->perm, m->P_hi, m->P_lo, m->Pt_hi, m->Pt_lo, m->P3_hi, m->P3_lo);
   JRR_CUDA(cudaGetLastError());
   JRR_CUDA(cudaDeviceSynchronize());
   return JRR_OK;
@@ -965,6 +1070,8 @@ static int model_create_impl(const JrrModelDesc* d, JrrModel* m) {
     if (int rc = dalloc(m, &m->P_hi, (size_t)KA * NP, false)) return rc;
     if (int rc = dalloc(m, &m->P_lo, (size_t)KA * NP, false)) return rc;
     if (int rc = dalloc(m, &m->Pt_hi, (size_t)KA * NP, false)) return rc;
+    if (int rc = dalloc(m, &m->P3_hi, (size_t)KA * NP, false)) return rc;
+    if (int rc = dalloc(m, &m->P3_lo, (size_t)KA * NP, false)) return rc;
     if (int rc = dalloc(m, &m->Pt_lo, (size_t)KA * NP, false)) return rc;
   }
 
