@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 if [ "$P" != "2" ]; then
 timeout 900 python -m pytest tests -m gpu -q --timeout 600 -s 2>&1 | grep -E "^\[|MPJPE|refit|gradient rel|tcgen05 3xTF32|passed|failed|rel err|max \|" > gpurun_out/${T}_gpu_tests.txt; tail -1 gpurun_out/${T}_gpu_tests.txt
 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; tail -2 gpurun_out/${T}_bench.err
+python bench.py --steps 20 --warmup 5 --no-secondary > gpurun_out/${T}_bench_k20.json 2>> gpurun_out/${T}_bench.err      # the driver's command line
 python bench.py --loss-path vertex --no-cpu-baseline --no-secondary > gpurun_out/${T}_bench_vertex.json 2>> gpurun_out/${T}_bench.err
 python bench.py --regressor shipped --no-cpu-baseline --no-secondary > gpurun_out/${T}_bench_shipped.json 2>> gpurun_out/${T}_bench.err
 python bench.py --impl reference --steps 20 --warmup 2 > gpurun_out/${T}_bench_reference.json 2>> gpurun_out/${T}_bench.err

@@ -127,7 +127,7 @@ def top_kernels():
 
 
 def main():
-    for f in (f"{TAG}_bench.json", f"{TAG}_bench_vertex.json", f"{TAG}_bench_shipped.json", f"{TAG}_bench_reference.json", f"{TAG}_gpu_tests.txt",
+    for f in (f"{TAG}_bench.json", f"{TAG}_bench_k20.json", f"{TAG}_bench_vertex.json", f"{TAG}_bench_shipped.json", f"{TAG}_bench_reference.json", f"{TAG}_gpu_tests.txt",
               f"{TAG}_sweep.jsonl", f"{TAG}_memcheck.txt", f"{TAG}_bench_2gpu.json", f"{TAG}_bench_8gpu.json", f"{TAG}_launches.csv",
               f"{TAG}_gemm_pair_check.jsonl", f"{TAG}_gemm_role_stamps.jsonl", f"{TAG}_step_breakdown.jsonl",
               f"{TAG}_multi_gpu_check_2.json", f"{TAG}_multi_gpu_check_8.json", f"{TAG}_module_launches.csv", f"{TAG}_silhouette_launches.csv",
