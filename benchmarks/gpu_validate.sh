@@ -27,6 +27,7 @@ fi
 if [ "$P" != "1" ]; then
 ncu --set full --clock-control none --import-source on -k regex:'fused_fwd|fused_bwd|smpl_small' -c 13 -f -o gpurun_out/${T}_prof_module python benchmarks/module_calls.py >> gpurun_out/ncu_full.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_module_launches.csv python benchmarks/module_calls.py > gpurun_out/${T}_module.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'sil_|small_bwd' -c 12 -f -o gpurun_out/${T}_prof_sil python benchmarks/sil_calls.py >> gpurun_out/ncu_full.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_silhouette_launches.csv python benchmarks/sil_calls.py > gpurun_out/${T}_sil.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.txt 2>&1; tail -1 gpurun_out/${T}_smoke.txt
 ls -la gpurun_out/${T}_prof*.ncu-rep; du -sh gpurun_out

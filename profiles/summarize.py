@@ -95,10 +95,12 @@ def top_kernels():
            "pose_bwd|adam_params' -s 60 -c 26 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary",
            "ncu --set full ... -k regex:'fused_bwd|fused_fwd' -s 30 -c 4 python bench.py --loss-path vertex --steps 3 --warmup 3 --no-cpu-baseline",
            "ncu --set full ... -k regex:'fused_fwd|fused_bwd|smpl_small' -c 14 python benchmarks/module_calls.py   (module path: SMPL.forward / backward at 4096, 256, 8 poses)",
+           "ncu --set full ... -k regex:'sil_|small_bwd' -c 12 python benchmarks/sil_calls.py   (one refinement iteration with the silhouette term, 1024 frames at 224 x 224)",
+           "ncu --set full ... -k regex:'small_bwd|smpl_small' -s 0 -c 6 python benchmarks/module_calls.py with B in (8, 1) only   (single-launch small-batch paths)",
            "(first captured launch of each kernel; B = 4096 poses, dense 17x6890 regressor; times under ncu are cold-cache and serialised)", ""]
     traffic = {}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    for tag in (f"{TAG}_prof", f"{TAG}_prof_vertex", f"{TAG}_prof_module"):
+    for tag in (f"{TAG}_prof", f"{TAG}_prof_vertex", f"{TAG}_prof_module", f"{TAG}_prof_sil", f"{TAG}_prof_smallbwd"):
         rep = os.path.join(SRC, tag + ".ncu-rep")
         if not os.path.exists(rep):
             continue
