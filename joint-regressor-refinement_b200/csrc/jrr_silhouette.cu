@@ -112,6 +112,7 @@ __global__ void sil_project_kernel(const float* __restrict__ verts, const float*
 // centres while 31 wait) but by the whole warp: its data is broadcast by shuffles and the lanes stride over the box.  SMPL faces
 // at 224 x 224 never get there; a close-up camera, a coarse mesh or a larger image do.
 constexpr int SIL_BIG = 64;
+constexpr bool SIL_FLATTEN = true;     // raster kernel: the warp's small boxes as one pixel list (false: a loop per lane)
 constexpr unsigned SIL_FULL = 0xffffffffu;
 
 __device__ __forceinline__ SilFace sil_shfl_face(const SilFace& t, int src) {
@@ -136,10 +137,10 @@ __device__ __forceinline__ void sil_raster_pixel(const SilFace& t, int xi, int y
 
 __global__ void sil_raster_kernel(const float* __restrict__ ndc, const int32_t* __restrict__ faces, int64_t B, int64_t V,
                                   int64_t F, int S, unsigned long long* __restrict__ zbuf) {
-  // grid (faces, frames); whole warps stay for the cooperative part.  (Measured, 1024 frames at 224 x 224: 0.72 ms, issue
-  // slots 77 % busy, ~1 460 instructions per warp of 32 faces -- the warp waits for its largest box (~30 centres) while the
-  // mean is 9.  Neither a lower SIL_BIG (16) nor dropping the 64-bit index division changed the time; flattening the warp's
-  // boxes into one pixel list -- prefix sum, owner by binary search over shuffles -- is the step that would.)
+  // grid (faces, frames); whole warps stay for the cooperative parts.  (Measured, 1024 frames at 224 x 224: with a loop per
+  // lane 0.72 ms, issue slots 77 % busy, ~1 460 instructions per warp of 32 faces -- the warp waits for its largest box (~30
+  // centres) while the mean is 9; neither a lower SIL_BIG nor dropping the 64-bit index division changed that.  Flattened
+  // into one pixel list per warp: 0.45 ms.)
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t b = blockIdx.y;
   const bool in = f < F;
@@ -147,11 +148,43 @@ __global__ void sil_raster_kernel(const float* __restrict__ ndc, const int32_t* 
   t.live = t.live && in;
   const int box = sil_box(t);
   unsigned long long* zb = zbuf + b * (int64_t)S * S;
-  if (box > 0 && box <= SIL_BIG) {
+  const int lane = threadIdx.x & 31;
+  static_assert(SIL_BIG <= 64, "the flattened list indexes a box with a float quotient");
+  if (SIL_FLATTEN) {
+    // the warp's small boxes as ONE list of pixel centres: entry q belongs to the last lane whose exclusive prefix is <= q
+    // (binary search over the lanes' registers), whose face arrives by shuffles -- every lane tests a centre in every round
+    // instead of waiting for the warp's largest box
+    const int n = box <= SIL_BIG ? box : 0;
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(SIL_FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int excl = incl - n;
+    const int total = __shfl_sync(SIL_FULL, incl, 31);
+    const int nx_own = t.hi_x - t.lo_x + 1;
+    for (int q0 = 0; q0 < total; q0 += 32) {
+      const int q = q0 + lane;
+      const bool act = q < total;
+      const int qq = act ? q : 0;
+      int owner = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int e = __shfl_sync(SIL_FULL, excl, (owner + step) & 31);
+        if (owner + step < 32 && e <= qq) owner += step;
+      }
+      const SilFace s = sil_shfl_face(t, owner);
+      const int local = qq - __shfl_sync(SIL_FULL, excl, owner);
+      const int nx = __shfl_sync(SIL_FULL, nx_own, owner);
+      const int sf = __shfl_sync(SIL_FULL, f, owner);
+      const int ly = (int)(((float)local + 0.5f) / (float)nx);      // exact for local < 64
+      if (act) sil_raster_pixel(s, s.lo_x + (local - ly * nx), s.lo_y + ly, S, (uint32_t)sf, zb);
+    }
+  } else if (box > 0 && box <= SIL_BIG) {
     for (int yi = t.lo_y; yi <= t.hi_y; yi++)
       for (int xi = t.lo_x; xi <= t.hi_x; xi++) sil_raster_pixel(t, xi, yi, S, (uint32_t)f, zb);
   }
-  const int lane = threadIdx.x & 31;
   unsigned todo = __ballot_sync(SIL_FULL, box > SIL_BIG);
   while (todo) {
     const int src = __ffs(todo) - 1;
@@ -283,13 +316,58 @@ __global__ void sil_face_grad_kernel(const float* __restrict__ ndc, const int32_
   SilFace t = sil_load_face(ndc + b * V * 3, faces, in ? f : 0, S);
   t.live = t.live && in;
   const int box = sil_box(t);
-  if (box > 0 && box <= SIL_BIG) {
+  const int lane = threadIdx.x & 31;
+  if (SIL_FLATTEN) {
+    // phase 1, the warp's small boxes as one list of pixel centres (as in the raster kernel): which centres of its box did
+    // each face WIN?  One bit per centre, OR-ed into the owner's 64-bit word (an order-free atomic on shared memory).
+    // phase 2: every lane walks the set bits of its own word in ascending order -- the few pixels it has a gradient for.
+    __shared__ unsigned long long won[4][32];
+    const int wp = threadIdx.x >> 5;
+    won[wp][lane] = 0ull;
+    __syncwarp();
+    const int n = box <= SIL_BIG ? box : 0;
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(SIL_FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int excl = incl - n;
+    const int total = __shfl_sync(SIL_FULL, incl, 31);
+    const int nx_own = t.hi_x - t.lo_x + 1;
+    for (int q0 = 0; q0 < total; q0 += 32) {
+      const int q = q0 + lane;
+      const bool act = q < total;
+      const int qq = act ? q : 0;
+      int owner = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int e = __shfl_sync(SIL_FULL, excl, (owner + step) & 31);
+        if (owner + step < 32 && e <= qq) owner += step;
+      }
+      const int local = qq - __shfl_sync(SIL_FULL, excl, owner);
+      const int nx = __shfl_sync(SIL_FULL, nx_own, owner);
+      const int ox = __shfl_sync(SIL_FULL, t.lo_x, owner), oy = __shfl_sync(SIL_FULL, t.lo_y, owner);
+      const int sf = __shfl_sync(SIL_FULL, f, owner);
+      const int ly = (int)(((float)local + 0.5f) / (float)nx);
+      const int xi = ox + (local - ly * nx), yi = oy + ly;
+      if (act && pix_to_face[base + (int64_t)(S - 1 - yi) * S + (S - 1 - xi)] == sf) atomicOr(&won[wp][owner], 1ull << local);
+    }
+    __syncwarp();
+    unsigned long long mine = won[wp][lane];
+    while (mine) {
+      const int local = __ffsll((long long)mine) - 1;
+      mine &= mine - 1;
+      const int ly = (int)(((float)local + 0.5f) / (float)nx_own);
+      sil_grad_pixel(t, t.lo_x + (local - ly * nx_own), t.lo_y + ly, S, (int32_t)f, base, pix_to_face, alpha, dalpha, target,
+                     mse_scale, inv_sigma, g);
+    }
+  } else if (box > 0 && box <= SIL_BIG) {
     for (int yi = t.lo_y; yi <= t.hi_y; yi++)
       for (int xi = t.lo_x; xi <= t.hi_x; xi++)
         sil_grad_pixel(t, xi, yi, S, (int32_t)f, base, pix_to_face, alpha, dalpha, target, mse_scale, inv_sigma, g);
   }
   // large boxes: the warp strides over the box, then a butterfly (a fixed order) sums the lanes' shares for the owner
-  const int lane = threadIdx.x & 31;
   unsigned todo = __ballot_sync(SIL_FULL, box > SIL_BIG);
   while (todo) {
     const int src = __ffs(todo) - 1;
