@@ -197,7 +197,7 @@ class PoseRefiner:
         fused step as an external gradient, so ONE Adam step is taken on the sum of all terms like the reference's
         `opt_loss.backward(); optimizer.step()`.  mask [N,1,S,S] or [N,S,S].  Returns (step losses, silhouette loss) of the
         last iteration.  One iteration is ~40 launches across five C calls, issued eagerly: the host runs ahead of the device
-        (2.6 ms of kernels per 1024 frames at 224 x 224), so there are no launch gaps to remove -- measured: a replayed
+        (2.2-2.6 ms of kernels per 1024 frames at 224 x 224), so there are no launch gaps to remove -- measured: a replayed
         iteration takes the same 2.64 ms and the capture costs 5 ms per call.  ``use_graph=True`` is kept for callers with
         a slow host: the first iteration runs eagerly, the second is captured into a CUDA graph (its intermediate tensors
         live in the graph's memory pool, so the external-gradient pointers stay valid), the rest are replays; results are
